@@ -1,0 +1,185 @@
+/* lsa_b200.h -- C ABI of the B200-native shift-and-invert eigensolve backend.
+ *
+ * The reference (ferdean/lsa-fw) has no FFI of its own: the seam is the Python class API
+ * `Solver/eigen.py:48-155` + `Solver/utils.py:190-328`, whose numerical work is done by
+ * slepc4py/petsc4py calls.  Each entry point below names the reference call it stands in
+ * for; the Python host (lsa_fw_b200/backend.py) binds them with ctypes.  INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 on success, a negative lsa_status otherwise, with a
+ * text in lsa_last_error().  Plain pointers + sizes only.  Host or device pointers are both
+ * accepted where an `on_device` flag exists (device pointers come from DLPack / torch on the
+ * Python side).  One handle = one solver object = one CUDA stream; not thread-safe (neither is
+ * the reference: one EPS per Python object, Solver/utils.py:203).
+ * Complex numbers are interleaved (re, im) doubles.  Indices are int32, row pointers int64.
+ */
+#ifndef LSA_B200_H
+#define LSA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsa_handle lsa_handle;
+
+enum lsa_status {
+  LSA_OK = 0,
+  LSA_ERR_ARG = -1,         /* bad argument / call order                                  */
+  LSA_ERR_CUDA = -2,        /* CUDA runtime error or no device (there is NO CPU fallback)  */
+  LSA_ERR_ZERO_PIVOT = -3,  /* exactly singular pivot (PETSc.Error "zero pivot" in the reference) */
+  LSA_ERR_NONFINITE = -4,   /* NaN/Inf met in the factor or the Krylov basis (eigen2.py:186-189) */
+  LSA_ERR_INTERNAL = -5
+};
+
+enum lsa_scalar { LSA_F64 = 0, LSA_C128 = 1 };
+enum lsa_trans { LSA_OP_N = 0, LSA_OP_T = 1, LSA_OP_H = 2 };
+enum lsa_matrix { LSA_MAT_A = 0, LSA_MAT_M = 1 };
+
+/* EPSWhich of SLEPc as exposed by iEpsWhich (Solver/utils.py:152-187). */
+enum lsa_which {
+  LSA_LARGEST_MAGNITUDE = 1,
+  LSA_SMALLEST_MAGNITUDE = 2,
+  LSA_LARGEST_REAL = 3,
+  LSA_SMALLEST_REAL = 4,
+  LSA_LARGEST_IMAGINARY = 5,
+  LSA_SMALLEST_IMAGINARY = 6,
+  LSA_TARGET_MAGNITUDE = 7,
+  LSA_TARGET_REAL = 8,
+  LSA_TARGET_IMAGINARY = 9
+};
+
+/* Spectral transformation (iSTType, Solver/utils.py:131-149); only these two are built. */
+enum lsa_transform { LSA_ST_SHIFT = 0, LSA_ST_SINVERT = 1 };
+
+typedef struct {
+  int32_t n, n_decoupled, n_fronts, n_levels;
+  int32_t max_pivots, max_front, max_rows, pad;
+  int64_t nnz_a, nnz_m;
+  int64_t factor_entries;  /* elements allocated for the factor store                         */
+  int64_t nnz_lu;          /* algorithmic entries of L+U: sum k^2 + 2 k r (+ decoupled pivots) */
+  int64_t pool_entries[2]; /* contribution-block pools                                        */
+  int64_t struct_entries;  /* total front row-structure length                                */
+  double flops_real;       /* sum 2/3 k^3 + 2 k^2 r + 2 k r^2 ; x4 for complex                */
+  double seconds[4];       /* graph, ordering, structure, maps                                */
+} lsa_symbolic_info;
+
+typedef struct {
+  double seconds;          /* device time of the numeric factorisation (CUDA events)  */
+  double flops;            /* real flops executed (flops_real x 4 when complex)        */
+  int64_t n_perturbed;     /* tiny pivots replaced (static pivoting, cf. MUMPS CNTL(3) in eigen2.py:135-136) */
+  int64_t n_row_swaps;     /* pivot rows exchanged inside fronts                       */
+  int32_t scalar;          /* lsa_scalar actually used                                  */
+  int32_t n_kernels;       /* kernel launches issued                                    */
+  double min_pivot, max_pivot;
+} lsa_factor_stats;
+
+typedef struct {
+  int32_t nev, ncv, max_restarts;
+  int32_t which;           /* lsa_which, applied to the back-transformed eigenvalue    */
+  int32_t transform;       /* lsa_transform                                             */
+  int32_t adjoint;         /* 1: left problem (A^H, M^H) at conj(sigma) on the SAME factors
+                              (what Sensitivity/__init__.py:246-262 obtains by re-factorising) */
+  int32_t purify;          /* 1: one extra OP apply per Ritz vector (singular M)        */
+  int32_t refine_steps;    /* iterative-refinement steps inside each OP apply           */
+  double tol;              /* relative: beta |s_i| <= tol |theta_i|  (EigensolverConfig.atol is
+                              handed to SLEPc as its relative tol, Solver/utils.py:236-238) */
+  double sigma_re, sigma_im;    /* shift / target                                        */
+  uint64_t seed;                /* start vector: splitmix64 Gaussian stream, OP applied once */
+  const double* v0;             /* optional host start vector (n complex); NULL = seeded random */
+} lsa_eigs_params;
+
+typedef struct {
+  int32_t nconv, n_restarts, n_op_applies, breakdown;
+  double seconds;               /* device time of the Krylov-Schur loop (CUDA events)    */
+  double seconds_solve, seconds_spmv, seconds_ortho, seconds_rr, seconds_restart;
+  int32_t n_kernels, pad;
+} lsa_eigs_result;
+
+typedef struct {
+  double bytes_solve;     /* algorithmic bytes of one fwd+bwd triangular solve   */
+  double bytes_spmv_m;    /* algorithmic bytes of one SpMV with M                              */
+  double bytes_spmv_a;
+  double factor_flops, factor_seconds;
+  double solve_seconds;   /* mean device seconds of one fwd+bwd solve                          */
+  double spmv_seconds;
+  int64_t n_solves, n_spmv;
+} lsa_counters;
+
+/* -- lifetime ------------------------------------------------------------------------------
+ * lsa_create  <- SLEPc.EPS().create(comm)                       Solver/utils.py:203
+ * device >= 0: CUDA device ordinal.  device = -1: symbolic-only handle (no GPU touched); every
+ * numeric call on such a handle fails with LSA_ERR_CUDA.                                      */
+int lsa_create(int32_t n, int32_t device, lsa_handle** out);
+void lsa_destroy(lsa_handle* h);
+const char* lsa_last_error(const lsa_handle* h);
+const char* lsa_version(void);
+
+/* -- operators ------------------------------------------------------------------------------
+ * lsa_analyze  <- eps.setOperators(A.raw, M.raw) + PCSetUp_LU symbolic part
+ *                 (Solver/utils.py:216-221; MatGetOrdering/MatLUFactorSymbolic inside PETSc)
+ * CSR patterns of A and M as delivered by iPETScMatrix.as_scipy_array() (FEM/utils.py:585-588).
+ * m_rowptr == NULL: standard problem (M = I).  coords (n x dim doubles) and order_last (n bytes)
+ * are optional hints, NULL allowed.  Runs on the host; reusable across shifts / Reynolds numbers. */
+int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx, const int64_t* m_rowptr,
+                const int32_t* m_colidx, int32_t leaf_size, int32_t dim, const double* coords,
+                const uint8_t* order_last, int32_t nthreads);
+int lsa_symbolic_info_get(const lsa_handle* h, lsa_symbolic_info* out);
+/* Copies a named internal array (perm, iperm, sn_ptr, st_ptr, st_idx, ea_map, parent, level, front_k,
+ * front_r, p_off, q_off, c_off, a_dst, m_dst, lvl_ptr, lvl_front) to `out`; returns its length in elements
+ * or a negative status.  With out == NULL only the length is returned.  Used by the host-logic tests. */
+int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int64_t capacity_bytes);
+
+/* lsa_set_values <- values of the AIJ matrices handed to eps.setOperators; may be called again
+ * with new values on the same pattern (Reynolds sweep, BASELINE config 3).  `a_scalar`/`m_scalar`
+ * are lsa_scalar; values are in the ORIGINAL CSR entry order.  on_device: pointers are device memory. */
+int lsa_set_values(lsa_handle* h, const void* a_vals, int32_t a_scalar, const void* m_vals, int32_t m_scalar,
+                   int32_t on_device);
+
+/* -- numeric factorisation -------------------------------------------------------------------
+ * lsa_factor <- STSetUp_Sinvert (MatAXPY T = A - sigma M) + PCSetUp_LU numeric part, reached from
+ *               set_st_type(SINVERT)/set_target/set_st_pc_type(LU) + solve()  (Solver/utils.py:244-270;
+ *               explicit in Solver/eigen2.py:109-151).
+ * Factors  F = alpha A + beta M  (sinvert: alpha = 1, beta = -sigma; shift on a generalized problem:
+ * alpha = 0, beta = 1).  scalar = LSA_F64 requires real values and real alpha/beta.
+ * tiny_pivot > 0: pivots smaller than tiny_pivot * max|F| are replaced by that magnitude and counted;
+ * tiny_pivot == 0: an exactly zero pivot fails with LSA_ERR_ZERO_PIVOT (PETSc's default behaviour,
+ * tests/unit/Solver/test_eigen.py:272-281).                                                        */
+int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, double beta_im, int32_t scalar,
+               double tiny_pivot, lsa_factor_stats* stats);
+
+/* lsa_solve <- KSPSolve(preonly + LU) = MatSolve / MatSolveTranspose   (Solver/eigen2.py:178;
+ * the adjoint use of Sensitivity/__init__.py:246-262 maps to trans = LSA_OP_H on the same factors).
+ * b, x: n complex numbers (interleaved) in the ORIGINAL ordering; b == x allowed.                 */
+int lsa_solve(lsa_handle* h, int32_t trans, const double* b, double* x, int32_t refine_steps, int32_t on_device);
+
+/* lsa_spmv <- MatMult / MatMultHermitianTranspose with A or M    (Solver/eigen2.py:174, :52-53). */
+int lsa_spmv(lsa_handle* h, int32_t which_matrix, int32_t trans, const double* x, double* y, int32_t on_device);
+
+/* -- eigensolve ------------------------------------------------------------------------------
+ * lsa_eigs <- SLEPc.EPS.solve()  (Solver/utils.py:268-270): Krylov-Schur on OP with CGS2,
+ * Rayleigh-Ritz, locking restart, purification, 2-norm normalisation, `which` ordering.          */
+int lsa_eigs(lsa_handle* h, const lsa_eigs_params* p, lsa_eigs_result* out);
+/* <- eps.getConverged / getEigenvalue / getEigenvector  (Solver/utils.py:272-297) */
+int lsa_get_eigenvalues(const lsa_handle* h, double* out_c128, int32_t capacity);
+int lsa_get_eigenvectors(const lsa_handle* h, double* out_c128, int64_t ld, int32_t count, int32_t on_device);
+/* ||A x - lambda M x|| / (||A||_F ||x||)  per returned pair, evaluated on the device (north-star bar). */
+int lsa_get_residuals(lsa_handle* h, double* out, int32_t capacity);
+int lsa_get_counters(const lsa_handle* h, lsa_counters* out);
+int lsa_sync(lsa_handle* h);
+
+/* -- stand-alone kernels exposed for parity tests and roofline measurement -------------------- */
+/* Dense Rayleigh-Ritz step (DSSolve/DSSort of SLEPc): Schur form of the m x m matrix S (column-major,
+ * ld), ordered by `which` on the back-transformed values.  Runs the SAME kernel the eigensolver uses. */
+int lsa_dense_schur(lsa_handle* h, int32_t m, double* S_c128, int32_t ld, double* Q_c128, int32_t which,
+                    int32_t transform, double sigma_re, double sigma_im);
+/* C -= A B on column-major FP64 (scalar = LSA_F64) or complex (LSA_C128) device matrices with the
+ * front-update DMMA kernel; returns device milliseconds in *ms (mean of `reps` launches).          */
+int lsa_gemm_bench(lsa_handle* h, int32_t scalar, int32_t m, int32_t n, int32_t k, int32_t reps, double* ms,
+                   double* max_abs_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSA_B200_H */

@@ -1,0 +1,751 @@
+// C ABI of the B200 shift-and-invert eigensolve backend (see include/lsa_b200.h).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "factor.cuh"
+
+namespace lsa {
+
+template <class T>
+void post_factor(lsa_handle_impl& h, int* n_kernels);
+
+namespace {
+
+template <class T>
+T* dalloc(size_t count) {
+  T* p = nullptr;
+  if (count == 0) count = 1;
+  LSA_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  return p;
+}
+template <class T>
+T* dupload(const std::vector<T>& v, cudaStream_t st) {
+  T* p = dalloc<T>(v.size());
+  if (!v.empty()) LSA_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return p;
+}
+template <class T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_csr(CsrDev& c) {
+  dfree(c.rowptr);
+  dfree(c.colidx);
+  dfree(c.src);
+  if (c.vals) cudaFree(c.vals);
+  c.vals = nullptr;
+  c.nnz = 0;
+}
+
+void free_device(lsa_handle_impl& h) {
+  dfree(h.d_fronts); dfree(h.d_lvl_front); dfree(h.d_st_idx); dfree(h.d_ea_map); dfree(h.d_child_idx);
+  dfree(h.d_a_dst); dfree(h.d_m_dst); dfree(h.d_perm); dfree(h.d_ipiv); dfree(h.d_gperm); dfree(h.d_stats);
+  if (h.d_a_orig) cudaFree(h.d_a_orig);
+  if (h.d_m_orig) cudaFree(h.d_m_orig);
+  h.d_a_orig = h.d_m_orig = nullptr;
+  free_csr(h.dA); free_csr(h.dM); free_csr(h.dAt); free_csr(h.dMt);
+  if (h.d_fac) cudaFree(h.d_fac);
+  h.d_fac = nullptr;
+  h.fac_capacity_bytes = 0;
+  for (int q = 0; q < 2; ++q) {
+    if (h.d_pool[q]) cudaFree(h.d_pool[q]);
+    h.d_pool[q] = nullptr;
+    h.pool_capacity_bytes[q] = 0;
+  }
+  dfree(h.d_x); dfree(h.d_w); dfree(h.d_t); dfree(h.d_cb); dfree(h.d_io); dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q);
+  dfree(h.d_part); dfree(h.d_npart); dfree(h.d_h); dfree(h.d_brow); dfree(h.d_ywork); dfree(h.d_r1); dfree(h.d_r2);
+  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
+  h.V_cols = 0; h.X_cols = 0; h.ncv_alloc = 0; h.scalar = -1; h.have_values = false;
+}
+
+// permuted CSR view of a matrix given in the caller's ordering
+void build_permuted(int n, const int64_t* rowptr, const int32_t* colidx, const Symbolic& sym, CsrHost& out) {
+  out.rowptr.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    const int v = sym.perm[i];
+    out.rowptr[i + 1] = out.rowptr[i] + (rowptr[v + 1] - rowptr[v]);
+  }
+  const long long nnz = out.rowptr[n];
+  out.colidx.resize(nnz);
+  out.src.resize(nnz);
+#pragma omp parallel
+  {
+    std::vector<std::pair<int, long long>> tmp;
+#pragma omp for schedule(dynamic, 512)
+    for (int i = 0; i < n; ++i) {
+      const int v = sym.perm[i];
+      tmp.clear();
+      for (long long e = rowptr[v]; e < rowptr[v + 1]; ++e) tmp.emplace_back(sym.iperm[colidx[e]], e);
+      std::sort(tmp.begin(), tmp.end());
+      long long o = out.rowptr[i];
+      for (auto& t : tmp) {
+        out.colidx[o] = t.first;
+        out.src[o] = t.second;
+        ++o;
+      }
+    }
+  }
+}
+
+void build_transpose(int n, const CsrHost& a, CsrHost& t) {
+  const long long nnz = a.rowptr[n];
+  t.rowptr.assign(n + 1, 0);
+  for (long long e = 0; e < nnz; ++e) t.rowptr[a.colidx[e] + 1]++;
+  for (int i = 0; i < n; ++i) t.rowptr[i + 1] += t.rowptr[i];
+  t.colidx.resize(nnz);
+  t.src.resize(nnz);
+  std::vector<long long> pos(t.rowptr.begin(), t.rowptr.end() - 1);
+  for (int i = 0; i < n; ++i)
+    for (long long e = a.rowptr[i]; e < a.rowptr[i + 1]; ++e) {
+      const long long o = pos[a.colidx[e]]++;
+      t.colidx[o] = i;
+      t.src[o] = a.src[e];
+    }
+}
+
+void upload_csr(lsa_handle_impl& h, const CsrHost& c, CsrDev& d, bool is_complex) {
+  free_csr(d);
+  d.nnz = (long long)c.colidx.size();
+  d.rowptr = dupload(c.rowptr, h.stream);
+  d.colidx = dupload(c.colidx, h.stream);
+  d.src = dupload(c.src, h.stream);
+  d.is_complex = is_complex;
+  LSA_CUDA(cudaMalloc(&d.vals, std::max<size_t>(16, (size_t)d.nnz * (is_complex ? 16 : 8))));
+}
+
+void refresh_values(lsa_handle_impl& h, CsrDev& d, const void* orig, bool is_complex) {
+  if (d.is_complex != is_complex) {
+    if (d.vals) cudaFree(d.vals);
+    LSA_CUDA(cudaMalloc(&d.vals, std::max<size_t>(16, (size_t)d.nnz * (is_complex ? 16 : 8))));
+    d.is_complex = is_complex;
+  }
+  gather_values(h.stream, orig, is_complex, d.src, d.vals, d.nnz);
+}
+
+void ensure_transposes(lsa_handle_impl& h) {
+  if (h.dAt.rowptr) return;
+  build_transpose(h.n, h.hA, h.hAt);
+  upload_csr(h, h.hAt, h.dAt, h.a_complex);
+  if (h.has_m) {
+    build_transpose(h.n, h.hM, h.hMt);
+    upload_csr(h, h.hMt, h.dMt, h.m_complex);
+  }
+  if (h.have_values) {
+    refresh_values(h, h.dAt, h.d_a_orig, h.a_complex);
+    if (h.has_m) refresh_values(h, h.dMt, h.d_m_orig, h.m_complex);
+  }
+}
+
+void ensure_krylov(lsa_handle_impl& h, int ncv) {
+  if (ncv <= h.ncv_alloc) return;
+  dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q); dfree(h.d_Xp); dfree(h.d_ywork); dfree(h.d_theta); dfree(h.d_resid);
+  dfree(h.d_brow);
+  const size_t n = h.n;
+  h.d_V = dalloc<z128>(n * (size_t)(ncv + 1));
+  h.d_Xp = dalloc<z128>(n * (size_t)ncv);
+  h.d_S = dalloc<z128>((size_t)(ncv + 1) * ncv);
+  h.d_Q = dalloc<z128>((size_t)ncv * ncv);
+  h.d_ywork = dalloc<z128>((size_t)ncv * ncv);
+  h.d_theta = dalloc<z128>(ncv);
+  h.d_resid = dalloc<double>(ncv);
+  h.d_brow = dalloc<z128>(ncv + 1);
+  h.ncv_alloc = ncv;
+}
+
+__global__ void k_conj_inplace(z128* x, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i].y = -x[i].y;
+}
+
+template <class T>
+__global__ void k_fill_random(T* p, long long n, unsigned long long seed) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  p[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+template <bool CPLX>
+__global__ void k_gemm_naive(const double* A, const double* B, double* C, int M, int N, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= M || j >= N) return;
+  if (CPLX) {
+    const z128* a = (const z128*)A;
+    const z128* b = (const z128*)B;
+    z128 acc = mk(0, 0);
+    for (int k = 0; k < K; ++k) acc += a[i + (long long)k * M] * b[k + (long long)j * K];
+    z128* c = (z128*)C;
+    c[i + (long long)j * M] -= acc;
+  } else {
+    double acc = 0;
+    for (int k = 0; k < K; ++k) acc += A[i + (long long)k * M] * B[k + (long long)j * K];
+    C[i + (long long)j * M] -= acc;
+  }
+}
+
+__global__ void k_maxdiff(const double* a, const double* b, long long n, double* out) {
+  __shared__ double s[256];
+  double m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(a[i] - b[i]));
+  s[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = s[0];
+}
+
+int fail(lsa_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define LSA_API_BEGIN try {
+#define LSA_API_END(h)                                             \
+  }                                                                \
+  catch (const lsa::CudaError& e) { return fail(h, LSA_ERR_CUDA, e.what()); } \
+  catch (const std::bad_alloc&) { return fail(h, LSA_ERR_INTERNAL, "host out of memory"); } \
+  catch (const std::exception& e) { return fail(h, LSA_ERR_INTERNAL, e.what()); }
+
+int need_device(lsa_handle* h) {
+  if (h->device < 0) return fail(h, LSA_ERR_CUDA, "handle was created without a CUDA device; there is no CPU fallback");
+  LSA_API_BEGIN
+  LSA_CUDA(cudaSetDevice(h->device));
+  LSA_API_END(h)
+  return 0;
+}
+
+}  // namespace
+}  // namespace lsa
+
+using namespace lsa;
+
+extern "C" {
+
+const char* lsa_version(void) { return "lsa_b200 0.1 (sm_100a)"; }
+
+int lsa_create(int32_t n, int32_t device, lsa_handle** out) {
+  if (!out || n < 0) return LSA_ERR_ARG;
+  lsa_handle* h = new lsa_handle();
+  h->n = n;
+  h->device = device;
+  if (device >= 0) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device >= count) {
+      delete h;
+      *out = nullptr;
+      return LSA_ERR_CUDA;
+    }
+    cudaSetDevice(device);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete h;
+      *out = nullptr;
+      return LSA_ERR_CUDA;
+    }
+  }
+  *out = h;
+  return LSA_OK;
+}
+
+void lsa_destroy(lsa_handle* h) {
+  if (!h) return;
+  if (h->device >= 0) {
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_device(*h);
+    if (h->stream) cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+const char* lsa_last_error(const lsa_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx, const int64_t* m_rowptr,
+                const int32_t* m_colidx, int32_t leaf_size, int32_t dim, const double* coords,
+                const uint8_t* order_last, int32_t nthreads) {
+  if (!h || !a_rowptr || !a_colidx) return LSA_ERR_ARG;
+  LSA_API_BEGIN
+  const int n = h->n;
+  h->has_m = m_rowptr != nullptr;
+  h->nnz_a = a_rowptr[n];
+  h->nnz_m = h->has_m ? m_rowptr[n] : 0;
+  // union pattern for the graph
+  std::vector<long long> urow(n + 1, 0);
+  std::vector<int> ucol;
+  if (h->has_m) {
+    ucol.reserve(h->nnz_a + h->nnz_m);
+    for (int i = 0; i < n; ++i) {
+      ucol.insert(ucol.end(), a_colidx + a_rowptr[i], a_colidx + a_rowptr[i + 1]);
+      ucol.insert(ucol.end(), m_colidx + m_rowptr[i], m_colidx + m_rowptr[i + 1]);
+      urow[i + 1] = (long long)ucol.size();
+    }
+  }
+  AnalyzeOptions opt;
+  opt.leaf_size = leaf_size > 0 ? leaf_size : 64;
+  opt.dim = coords ? dim : 0;
+  opt.coords = coords;
+  opt.order_last = order_last;
+  opt.nthreads = nthreads;
+  if (h->has_m) analyze(n, urow.data(), ucol.data(), opt, h->sym);
+  else analyze(n, (const long long*)a_rowptr, a_colidx, opt, h->sym);
+  // scatter maps for the caller's entry order of A and M (the union map is recomputed per matrix)
+  const Symbolic& sym = h->sym;
+  auto local_index = [&](int s, int idx) -> int {
+    const Front& f = sym.fronts[s];
+    if (idx < f.col0 + f.k) return idx - f.col0;
+    const int* b = sym.st_idx.data() + f.st0;
+    const int* e = b + f.r;
+    const int* it = std::lower_bound(b, e, idx);
+    return (it == e || *it != idx) ? -1 : f.k + (int)(it - b);
+  };
+  auto build_dst = [&](const int64_t* rowptr, const int32_t* colidx, std::vector<long long>& dst) {
+    dst.resize(rowptr[n]);
+    bool bad = false;
+#pragma omp parallel for schedule(dynamic, 512)
+    for (int i = 0; i < n; ++i) {
+      const int pi = sym.iperm[i];
+      for (long long e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+        const int pj = sym.iperm[colidx[e]];
+        if (pi < sym.n_iso || pj < sym.n_iso) {
+          if (pi != pj) bad = true;
+          dst[e] = sym.diag_off + pi;
+          continue;
+        }
+        const int s = sym.sn_of[std::min(pi, pj)];
+        const Front& f = sym.fronts[s];
+        const int lr = local_index(s, pi), lc = local_index(s, pj);
+        if (lr < 0 || lc < 0) {
+          bad = true;
+          continue;
+        }
+        const long long m = f.k + f.r;
+        dst[e] = lc < f.k ? f.p_off + lr + (long long)lc * m : f.q_off + lr + (long long)(lc - f.k) * f.k;
+      }
+    }
+    if (bad) throw std::runtime_error("front structure does not cover the matrix pattern");
+  };
+  build_dst(a_rowptr, a_colidx, h->sym.a_dst);
+  if (h->has_m) build_dst(m_rowptr, m_colidx, h->m_dst);
+  build_permuted(n, a_rowptr, a_colidx, sym, h->hA);
+  if (h->has_m) build_permuted(n, m_rowptr, m_colidx, sym, h->hM);
+  h->hAt = CsrHost();
+  h->hMt = CsrHost();
+  h->analyzed = true;
+
+  if (h->device >= 0) {
+    LSA_CUDA(cudaSetDevice(h->device));
+    free_device(*h);
+    cudaStream_t st = h->stream;
+    h->d_fronts = dupload(sym.fronts, st);
+    h->d_lvl_front = dupload(sym.lvl_front, st);
+    h->d_st_idx = dupload(sym.st_idx, st);
+    h->d_ea_map = dupload(sym.ea_map, st);
+    h->d_child_idx = dupload(sym.child_idx, st);
+    h->d_a_dst = dupload(sym.a_dst, st);
+    if (h->has_m) h->d_m_dst = dupload(h->m_dst, st);
+    h->d_perm = dupload(sym.perm, st);
+    h->d_ipiv = dalloc<int>(n);
+    h->d_gperm = dalloc<int>(n);
+    h->d_stats = dalloc<DevStats>(1);
+    h->d_x = dalloc<z128>(n); h->d_w = dalloc<z128>(n); h->d_t = dalloc<z128>(n); h->d_io = dalloc<z128>(n);
+    h->d_r1 = dalloc<z128>(n); h->d_r2 = dalloc<z128>(n); h->d_r3 = dalloc<z128>(n);
+    h->d_cb = dalloc<z128>(sym.st_idx.size());
+    h->d_part = dalloc<z128>((size_t)1024 * 128);
+    h->d_npart = dalloc<double>((size_t)cdiv(n, 256) + 1);
+    h->d_h = dalloc<z128>(256);
+    h->d_flag = dalloc<int>(1);
+    h->d_rr = dalloc<RrInfo>(1);
+    upload_csr(*h, h->hA, h->dA, false);
+    if (h->has_m) upload_csr(*h, h->hM, h->dM, false);
+    LSA_CUDA(cudaStreamSynchronize(st));
+  }
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_symbolic_info_get(const lsa_handle* h, lsa_symbolic_info* out) {
+  if (!h || !out || !h->analyzed) return LSA_ERR_ARG;
+  const Symbolic& s = h->sym;
+  std::memset(out, 0, sizeof(*out));
+  out->n = s.n; out->n_decoupled = s.n_iso; out->n_fronts = s.ns; out->n_levels = s.nlevels;
+  out->max_pivots = s.max_k; out->max_front = s.max_m; out->max_rows = s.max_r;
+  out->nnz_a = h->nnz_a; out->nnz_m = h->nnz_m;
+  out->factor_entries = s.fac_size; out->nnz_lu = s.nnz_lu;
+  out->pool_entries[0] = s.pool_size[0]; out->pool_entries[1] = s.pool_size[1];
+  out->struct_entries = (int64_t)s.st_idx.size();
+  out->flops_real = s.flops;
+  for (int q = 0; q < 4; ++q) out->seconds[q] = s.seconds[q];
+  return LSA_OK;
+}
+
+int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int64_t capacity_bytes) {
+  if (!h || !name || !h->analyzed) return LSA_ERR_ARG;
+  const Symbolic& s = h->sym;
+  const std::string nm(name);
+  auto give = [&](const void* data, size_t count, size_t elem) -> int64_t {
+    if (out) {
+      if ((int64_t)(count * elem) > capacity_bytes) return LSA_ERR_ARG;
+      std::memcpy(out, data, count * elem);
+    }
+    return (int64_t)count;
+  };
+  auto from_fronts = [&](auto getter, size_t elem) -> int64_t {
+    if (elem == 4) {
+      std::vector<int> v(s.ns);
+      for (int i = 0; i < s.ns; ++i) v[i] = (int)getter(s.fronts[i]);
+      return give(v.data(), v.size(), 4);
+    }
+    std::vector<long long> v(s.ns);
+    for (int i = 0; i < s.ns; ++i) v[i] = (long long)getter(s.fronts[i]);
+    return give(v.data(), v.size(), 8);
+  };
+  if (nm == "perm") return give(s.perm.data(), s.perm.size(), 4);
+  if (nm == "iperm") return give(s.iperm.data(), s.iperm.size(), 4);
+  if (nm == "sn_ptr") return give(s.sn_ptr.data(), s.sn_ptr.size(), 4);
+  if (nm == "st_ptr") return give(s.st_ptr.data(), s.st_ptr.size(), 8);
+  if (nm == "st_idx") return give(s.st_idx.data(), s.st_idx.size(), 4);
+  if (nm == "ea_map") return give(s.ea_map.data(), s.ea_map.size(), 4);
+  if (nm == "lvl_ptr") return give(s.lvl_ptr.data(), s.lvl_ptr.size(), 4);
+  if (nm == "lvl_front") return give(s.lvl_front.data(), s.lvl_front.size(), 4);
+  if (nm == "a_dst") return give(s.a_dst.data(), s.a_dst.size(), 8);
+  if (nm == "m_dst") return give(h->m_dst.data(), h->m_dst.size(), 8);
+  if (nm == "parent") return from_fronts([](const Front& f) { return f.parent; }, 4);
+  if (nm == "level") return from_fronts([](const Front& f) { return f.level; }, 4);
+  if (nm == "front_k") return from_fronts([](const Front& f) { return f.k; }, 4);
+  if (nm == "front_r") return from_fronts([](const Front& f) { return f.r; }, 4);
+  if (nm == "p_off") return from_fronts([](const Front& f) { return f.p_off; }, 8);
+  if (nm == "q_off") return from_fronts([](const Front& f) { return f.q_off; }, 8);
+  if (nm == "c_off") return from_fronts([](const Front& f) { return f.c_off; }, 8);
+  return LSA_ERR_ARG;
+}
+
+int lsa_set_values(lsa_handle* h, const void* a_vals, int32_t a_scalar, const void* m_vals, int32_t m_scalar,
+                   int32_t on_device) {
+  if (!h || !h->analyzed || !a_vals) return LSA_ERR_ARG;
+  if (h->has_m && !m_vals) return fail(h, LSA_ERR_ARG, "M values missing");
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  cudaStream_t st = h->stream;
+  const auto kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  auto put = [&](void*& dst, const void* src, long long nnz, bool cplx, bool& flag) {
+    if (dst && flag != cplx) {
+      cudaFree(dst);
+      dst = nullptr;
+    }
+    const size_t bytes = std::max<size_t>(16, (size_t)nnz * (cplx ? 16 : 8));
+    if (!dst) LSA_CUDA(cudaMalloc(&dst, bytes));
+    flag = cplx;
+    if (nnz > 0) LSA_CUDA(cudaMemcpyAsync(dst, src, (size_t)nnz * (cplx ? 16 : 8), kind, st));
+  };
+  put(h->d_a_orig, a_vals, h->nnz_a, a_scalar == LSA_C128, h->a_complex);
+  if (h->has_m) put(h->d_m_orig, m_vals, h->nnz_m, m_scalar == LSA_C128, h->m_complex);
+  refresh_values(*h, h->dA, h->d_a_orig, h->a_complex);
+  if (h->has_m) refresh_values(*h, h->dM, h->d_m_orig, h->m_complex);
+  if (h->dAt.rowptr) {
+    refresh_values(*h, h->dAt, h->d_a_orig, h->a_complex);
+    if (h->has_m) refresh_values(*h, h->dMt, h->d_m_orig, h->m_complex);
+  }
+  value_norms(*h, h->d_a_orig, h->a_complex, h->nnz_a, &h->a_fro, &h->a_max);
+  double dummy = 0;
+  if (h->has_m) value_norms(*h, h->d_m_orig, h->m_complex, h->nnz_m, &dummy, &h->m_max);
+  h->have_values = true;
+  h->scalar = -1;  // previous factors are stale
+  LSA_CUDA(cudaStreamSynchronize(st));
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, double beta_im, int32_t scalar,
+               double tiny_pivot, lsa_factor_stats* stats) {
+  if (!h || !h->have_values) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  if (scalar == LSA_F64 && (alpha_im != 0.0 || beta_im != 0.0 || h->a_complex || (h->has_m && h->m_complex)))
+    return fail(h, LSA_ERR_ARG, "real factorisation requested for complex data or a complex shift");
+  LSA_API_BEGIN
+  const Symbolic& sym = h->sym;
+  cudaStream_t st = h->stream;
+  const size_t esz = scalar == LSA_C128 ? 16 : 8;
+  const long long need = sym.fac_size * (long long)esz;
+  if (need > h->fac_capacity_bytes) {
+    if (h->d_fac) cudaFree(h->d_fac);
+    h->d_fac = nullptr;
+    LSA_CUDA(cudaMalloc(&h->d_fac, std::max<long long>(need, 16)));
+    h->fac_capacity_bytes = need;
+  }
+  for (int q = 0; q < 2; ++q) {
+    const long long pn = sym.pool_size[q] * (long long)esz;
+    if (pn > h->pool_capacity_bytes[q]) {
+      if (h->d_pool[q]) cudaFree(h->d_pool[q]);
+      h->d_pool[q] = nullptr;
+      LSA_CUDA(cudaMalloc(&h->d_pool[q], std::max<long long>(pn, 16)));
+      h->pool_capacity_bytes[q] = pn;
+    }
+  }
+  const z128 alpha = mk(alpha_re, alpha_im), beta = mk(beta_re, beta_im);
+  const double fmax_est = absz(alpha) * h->a_max + (h->has_m ? absz(beta) * h->m_max : 0.0);
+  const double tiny_abs = tiny_pivot * fmax_est;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int nk = 0;
+  cudaEventRecord(e0, st);
+  h->scalar = -1;
+  if (scalar == LSA_C128) {
+    factor_numeric<z128>(*h, alpha, beta, tiny_abs, &nk);
+    post_factor<z128>(*h, &nk);
+  } else {
+    factor_numeric<double>(*h, alpha, beta, tiny_abs, &nk);
+    post_factor<double>(*h, &nk);
+  }
+  cudaEventRecord(e1, st);
+  DevStats ds{};
+  LSA_CUDA(cudaMemcpyAsync(&ds, h->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+  LSA_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  lsa_factor_stats fs{};
+  fs.seconds = ms * 1e-3;
+  fs.flops = sym.flops * (scalar == LSA_C128 ? 4.0 : 1.0);
+  fs.n_perturbed = (int64_t)ds.n_perturbed;
+  fs.n_row_swaps = (int64_t)ds.n_swaps;
+  fs.scalar = scalar;
+  fs.n_kernels = nk;
+  std::memcpy(&fs.min_pivot, &ds.min_piv_bits, 8);
+  std::memcpy(&fs.max_pivot, &ds.max_piv_bits, 8);
+  h->fstats = fs;
+  if (stats) *stats = fs;
+  if (ds.nonfinite) return fail(h, LSA_ERR_NONFINITE, "non-finite value met during the factorisation");
+  if (ds.zero_pivot) return fail(h, LSA_ERR_ZERO_PIVOT, "zero pivot: the shifted operator is singular");
+  h->scalar = scalar;
+  h->f_alpha = alpha;
+  h->f_beta = beta;
+  h->counters.factor_flops = fs.flops;
+  h->counters.factor_seconds = fs.seconds;
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_solve(lsa_handle* h, int32_t trans, const double* b, double* x, int32_t refine_steps, int32_t on_device) {
+  if (!h || !b || !x) return LSA_ERR_ARG;
+  if (h->scalar < 0) return fail(h, LSA_ERR_ARG, "lsa_solve called without a valid factorisation");
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  const int n = h->n;
+  cudaStream_t st = h->stream;
+  const z128* src = (const z128*)b;
+  if (!on_device) {
+    LSA_CUDA(cudaMemcpyAsync(h->d_io, b, sizeof(z128) * (size_t)n, cudaMemcpyHostToDevice, st));
+    src = h->d_io;
+  }
+  permute_gather(st, src, h->d_x, h->d_perm, n);
+  if (trans != LSA_OP_N && refine_steps > 0) ensure_transposes(*h);
+  if (trans == LSA_OP_T) {
+    k_conj_inplace<<<cdiv(n, 256), 256, 0, st>>>(h->d_x, n);
+    op_solve(*h, LSA_OP_H, h->d_x, refine_steps);
+    k_conj_inplace<<<cdiv(n, 256), 256, 0, st>>>(h->d_x, n);
+  } else {
+    op_solve(*h, trans, h->d_x, refine_steps);
+  }
+  if (on_device) {
+    permute_scatter(st, h->d_x, (z128*)x, h->d_perm, n);
+  } else {
+    permute_scatter(st, h->d_x, h->d_io, h->d_perm, n);
+    LSA_CUDA(cudaMemcpyAsync(x, h->d_io, sizeof(z128) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  LSA_CUDA(cudaStreamSynchronize(st));
+  h->counters.n_solves++;
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_spmv(lsa_handle* h, int32_t which_matrix, int32_t trans, const double* x, double* y, int32_t on_device) {
+  if (!h || !x || !y || !h->have_values) return LSA_ERR_ARG;
+  if (which_matrix == LSA_MAT_M && !h->has_m) return fail(h, LSA_ERR_ARG, "no M operator");
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  const int n = h->n;
+  cudaStream_t st = h->stream;
+  const z128* src = (const z128*)x;
+  if (!on_device) {
+    LSA_CUDA(cudaMemcpyAsync(h->d_io, x, sizeof(z128) * (size_t)n, cudaMemcpyHostToDevice, st));
+    src = h->d_io;
+  }
+  permute_gather(st, src, h->d_x, h->d_perm, n);
+  if (trans != LSA_OP_N) ensure_transposes(*h);
+  const CsrDev& mat = which_matrix == LSA_MAT_A ? (trans == LSA_OP_N ? h->dA : h->dAt) : (trans == LSA_OP_N ? h->dM : h->dMt);
+  spmv(*h, mat, trans == LSA_OP_H, h->d_x, h->d_w);
+  if (on_device) {
+    permute_scatter(st, h->d_w, (z128*)y, h->d_perm, n);
+  } else {
+    permute_scatter(st, h->d_w, h->d_io, h->d_perm, n);
+    LSA_CUDA(cudaMemcpyAsync(y, h->d_io, sizeof(z128) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  LSA_CUDA(cudaStreamSynchronize(st));
+  h->counters.n_spmv++;
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_eigs(lsa_handle* h, const lsa_eigs_params* p, lsa_eigs_result* out) {
+  if (!h || !p || !out || !h->have_values) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  const bool needs_factor = p->transform == LSA_ST_SINVERT || h->has_m;
+  if (needs_factor && h->scalar < 0) return fail(h, LSA_ERR_ARG, "lsa_eigs needs lsa_factor first");
+  if (p->which < 1 || p->which > 9) return fail(h, LSA_ERR_ARG, "unsupported `which`");
+  LSA_API_BEGIN
+  const int ncv = std::max(1, std::min(p->ncv, h->n));
+  ensure_krylov(*h, ncv);
+  if (p->adjoint || p->refine_steps > 0) ensure_transposes(*h);
+  h->last_params = *p;
+  h->last_params.v0 = nullptr;
+  std::memset(out, 0, sizeof(*out));
+  run_eigs(*h, *p, *out);
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_get_eigenvalues(const lsa_handle* h, double* out_c128, int32_t capacity) {
+  if (!h || !out_c128) return LSA_ERR_ARG;
+  const int cnt = std::min<int>(capacity, h->nconv);
+  for (int i = 0; i < cnt; ++i) {
+    out_c128[2 * i] = h->eigenvalues[i].x;
+    out_c128[2 * i + 1] = h->eigenvalues[i].y;
+  }
+  return cnt;
+}
+
+int lsa_get_eigenvectors(const lsa_handle* hc, double* out_c128, int64_t ld, int32_t count, int32_t on_device) {
+  lsa_handle* h = const_cast<lsa_handle*>(hc);
+  if (!h || !out_c128 || ld < h->n) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  const int cnt = std::min<int>(count, h->nconv);
+  for (int i = 0; i < cnt; ++i) {
+    const z128* src = h->d_X + (long long)h->eig_order[i] * h->n;
+    LSA_CUDA(cudaMemcpyAsync((z128*)out_c128 + (long long)i * ld, src, sizeof(z128) * (size_t)h->n,
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  }
+  LSA_CUDA(cudaStreamSynchronize(h->stream));
+  return cnt;
+  LSA_API_END(h)
+  return LSA_ERR_INTERNAL;
+}
+
+int lsa_get_residuals(lsa_handle* h, double* out, int32_t capacity) {
+  if (!h || !out) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  if (capacity < h->nconv) return fail(h, LSA_ERR_ARG, "capacity too small");
+  if (h->last_params.adjoint) ensure_transposes(*h);
+  residual_norms(*h, out);
+  return h->nconv;
+  LSA_API_END(h)
+  return LSA_ERR_INTERNAL;
+}
+
+int lsa_get_counters(const lsa_handle* h, lsa_counters* out) {
+  if (!h || !out || !h->analyzed) return LSA_ERR_ARG;
+  *out = h->counters;
+  const Symbolic& s = h->sym;
+  const double esz = h->scalar == LSA_C128 ? 16.0 : 8.0;
+  double idx = 0;
+  for (const Front& f : s.fronts) idx += 4.0 * (f.k + f.r);
+  out->bytes_solve = (double)s.nnz_lu * esz + idx + 2.0 * s.n * 16.0;
+  out->bytes_spmv_m = (double)h->nnz_m * ((h->m_complex ? 16.0 : 8.0) + 4.0) + 8.0 * (s.n + 1) + 2.0 * s.n * 16.0;
+  out->bytes_spmv_a = (double)h->nnz_a * ((h->a_complex ? 16.0 : 8.0) + 4.0) + 8.0 * (s.n + 1) + 2.0 * s.n * 16.0;
+  return LSA_OK;
+}
+
+int lsa_sync(lsa_handle* h) {
+  if (!h) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  LSA_CUDA(cudaStreamSynchronize(h->stream));
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_dense_schur(lsa_handle* h, int32_t m, double* S_c128, int32_t ld, double* Q_c128, int32_t which,
+                    int32_t transform, double sigma_re, double sigma_im) {
+  if (!h || !S_c128 || !Q_c128 || m < 1 || ld < m) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  z128* dS = dalloc<z128>((size_t)ld * m);
+  z128* dQ = dalloc<z128>((size_t)m * m);
+  LSA_CUDA(cudaMemcpyAsync(dS, S_c128, sizeof(z128) * (size_t)ld * m, cudaMemcpyHostToDevice, h->stream));
+  try {
+    dense_schur_device(*h, m, dS, ld, dQ, which, transform, mk(sigma_re, sigma_im));
+  } catch (...) {
+    cudaFree(dS);
+    cudaFree(dQ);
+    throw;
+  }
+  LSA_CUDA(cudaMemcpyAsync(S_c128, dS, sizeof(z128) * (size_t)ld * m, cudaMemcpyDeviceToHost, h->stream));
+  LSA_CUDA(cudaMemcpyAsync(Q_c128, dQ, sizeof(z128) * (size_t)m * m, cudaMemcpyDeviceToHost, h->stream));
+  LSA_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(dS);
+  cudaFree(dQ);
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_gemm_bench(lsa_handle* h, int32_t scalar, int32_t m, int32_t n, int32_t k, int32_t reps, double* ms,
+                   double* max_abs_err) {
+  if (!h || m < 1 || n < 1 || k < 1 || reps < 1) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  const bool cplx = scalar == LSA_C128;
+  const size_t S = cplx ? 2 : 1;
+  cudaStream_t st = h->stream;
+  double* A = dalloc<double>((size_t)m * k * S);
+  double* B = dalloc<double>((size_t)k * n * S);
+  double* C = dalloc<double>((size_t)m * n * S);
+  double* C2 = dalloc<double>((size_t)m * n * S);
+  double* red = dalloc<double>(256);
+  k_fill_random<double><<<cdiv((long long)m * k * S, 256), 256, 0, st>>>(A, (long long)m * k * S, 1);
+  k_fill_random<double><<<cdiv((long long)k * n * S, 256), 256, 0, st>>>(B, (long long)k * n * S, 2);
+  LSA_CUDA(cudaMemsetAsync(C, 0, sizeof(double) * (size_t)m * n * S, st));
+  LSA_CUDA(cudaMemsetAsync(C2, 0, sizeof(double) * (size_t)m * n * S, st));
+  double err = -1.0;
+  if ((double)m * n * k <= 4.0e9) {
+    gemm_plain(st, cplx, A, m, B, k, C, m, m, n, k);
+    if (cplx) k_gemm_naive<true><<<dim3(cdiv(m, 128), n), 128, 0, st>>>(A, B, C2, m, n, k);
+    else k_gemm_naive<false><<<dim3(cdiv(m, 128), n), 128, 0, st>>>(A, B, C2, m, n, k);
+    k_maxdiff<<<256, 256, 0, st>>>(C, C2, (long long)m * n * S, red);
+    double hred[256];
+    LSA_CUDA(cudaMemcpyAsync(hred, red, sizeof(hred), cudaMemcpyDeviceToHost, st));
+    LSA_CUDA(cudaStreamSynchronize(st));
+    err = 0;
+    for (double v : hred) err = std::max(err, v);
+  }
+  for (int w = 0; w < 2; ++w) gemm_plain(st, cplx, A, m, B, k, C, m, m, n, k);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int r = 0; r < reps; ++r) gemm_plain(st, cplx, A, m, B, k, C, m, m, n, k);
+  cudaEventRecord(e1, st);
+  LSA_CUDA(cudaStreamSynchronize(st));
+  float t = 0;
+  cudaEventElapsedTime(&t, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms) *ms = t / reps;
+  if (max_abs_err) *max_abs_err = err;
+  cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(C2); cudaFree(red);
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,677 @@
+// Numeric multifrontal LU of  F = alpha A + beta M  on one B200, real or complex FP64.
+//
+// Stands in for PETSc's MatLUFactorNumeric / MUMPS' numeric phase reached from
+// `iEpsSolver.set_st_pc_type(LU)` + `solve()` (reference Solver/utils.py:261-270; explicit in
+// Solver/eigen2.py:109-151).  Structure is static (restricted partial pivoting inside the pivot
+// block of each front + tiny-pivot replacement), so the whole factorisation is a fixed sequence
+// of batched launches over assembly-tree levels:
+//
+//   scatter      F entries -> front panels                      (HBM bound, bytes only)
+//   extend_add   children contribution blocks -> parent front   (HBM bound, smem-staged maps)
+//   panel_lu     nb-wide pivot panel, pivot search in rows [j, k)
+//   swap_trsm    row interchanges + U-row block (unit-lower solve, smem-staged tiles)
+//   trsm_cols    L21 panel (upper solve from the right)
+//   gemm         trailing update / Schur complement  C -= A B   (FP64 DMMA tensor pipe)
+//
+// The GEMM is the one dense contraction; it runs on the FP64 tensor pipe with
+// mma.sync.m8n8k4.f64 (SASS: DMMA) -- tcgen05 has no f64 kind on sm_100a.  Complex products use the
+// real embedding  C~ = A^ B~  on the interleaved storage (A^ built on the fly in the fragment
+// loader), i.e. 4 real DMMAs per complex multiply-add and no planar copies.
+#include "factor.cuh"
+
+namespace lsa {
+
+static constexpr int NB = 32;  // panel width
+
+// ------------------------------------------------------------------------------------------ scatter
+
+template <class T, class VT>
+__global__ void k_scatter(T* __restrict__ fac, const long long* __restrict__ dst, const VT* __restrict__ vals,
+                          long long nnz, z128 coef, int accumulate) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; e < nnz; e += stride) {
+    z128 v;
+    if constexpr (sizeof(VT) == 16) v = coef * vals[e];
+    else v = coef * (double)vals[e];
+    T t = scalar_traits<T>::from(v);
+    T* p = fac + dst[e];
+    if (accumulate) *p = *p + t;
+    else *p = t;
+  }
+}
+
+template <class T>
+__global__ void k_decoupled_pivots(T* __restrict__ diag, int n_iso, double tiny_abs, DevStats* st) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_iso) return;
+  T d = diag[i];
+  double a = abs1(d);
+  if (!(a == a) || isinf(a)) {
+    st->nonfinite = 1;
+    return;
+  }
+  if (a <= tiny_abs) {
+    if (tiny_abs == 0.0) {
+      st->zero_pivot = 1;
+      return;
+    }
+    diag[i] = scalar_traits<T>::from(mk(tiny_abs, 0.0));
+    atomicAdd(&st->n_perturbed, 1ULL);
+    a = tiny_abs;
+  }
+  atomicMin(&st->min_piv_bits, (unsigned long long)__double_as_longlong(a));
+  atomicMax(&st->max_piv_bits, (unsigned long long)__double_as_longlong(a));
+}
+
+// --------------------------------------------------------------------------------------- extend-add
+
+// grid: (column groups, fronts of the level); block: 256 threads.
+// Adds the contribution block of the `slot`-th child of each parent into the parent's P / Q / C.
+// Children are processed slot by slot in separate launches, so no two blocks ever add to the same
+// destination concurrently: deterministic, no atomics.
+template <class T>
+__global__ void k_extend_add(const Front* __restrict__ fronts, const int* __restrict__ lvl_front, int first,
+                             const int* __restrict__ child_idx, const int* __restrict__ ea_map, int slot,
+                             T* __restrict__ fac, const T* __restrict__ pool_child, T* __restrict__ pool_parent) {
+  constexpr int CHUNK = 2048;
+  __shared__ int s_map[CHUNK];
+  const Front p = fronts[lvl_front[first + blockIdx.y]];
+  if (slot >= p.nchild) return;
+  const Front c = fronts[child_idx[p.child0 + slot]];
+  const int rc = c.r;
+  if (rc == 0) return;
+  const int* map = ea_map + c.st0;
+  const T* cb = pool_child + c.c_off;
+  T* P = fac + p.p_off;
+  T* Q = fac + p.q_off;
+  T* C = pool_parent + p.c_off;
+  const long long kp = p.k, rp = p.r, mp = kp + rp;
+  for (int base = 0; base < rc; base += CHUNK) {
+    const int len = min(CHUNK, rc - base);
+    __syncthreads();
+    for (int t = threadIdx.x; t < len; t += blockDim.x) s_map[t] = map[base + t];
+    __syncthreads();
+    for (int b = blockIdx.x; b < rc; b += gridDim.x) {
+      const long long jp = map[b];
+      const T* col = cb + (long long)b * rc + base;
+      T* dcol;
+      int mode;
+      if (jp < kp) {
+        dcol = P + jp * mp;  // rows anywhere in [0, m)
+        mode = 0;
+      } else {
+        mode = 1;
+        dcol = nullptr;
+      }
+      for (int t = threadIdx.x; t < len; t += blockDim.x) {
+        const long long ip = s_map[t];
+        const T v = col[t];
+        if (mode == 0) {
+          dcol[ip] = dcol[ip] + v;
+        } else if (ip < kp) {
+          T* d = Q + ip + (jp - kp) * kp;
+          *d = *d + v;
+        } else {
+          T* d = C + (ip - kp) + (jp - kp) * rp;
+          *d = *d + v;
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------- panel LU
+
+struct ArgMax {
+  double v;
+  int i;
+};
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+
+// One CTA per front.  Factors columns [j0, j0+jb) of the pivot rows [j0, k) of P with partial
+// pivoting restricted to those rows; interchanges are applied inside the panel only (the rest of
+// the row is swapped by k_swap_trsm).
+template <class T>
+__global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                  int first, int j0, T* __restrict__ fac, int* __restrict__ ipiv,
+                                                  double tiny_abs, DevStats* st) {
+  const Front f = fronts[lvl_front[first + blockIdx.x]];
+  const int k = f.k;
+  if (k <= j0) return;
+  const long long m = (long long)f.k + f.r;
+  const int jb = min(NB, k - j0);
+  T* P = fac + f.p_off;
+  __shared__ ArgMax s_red[8];
+  __shared__ int s_piv;
+  __shared__ T s_inv;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int j = j0; j < j0 + jb; ++j) {
+    // 1. pivot search in column j, rows [j, k)
+    ArgMax best{-1.0, 0x7fffffff};
+    for (int i = j + tid; i < k; i += blockDim.x) {
+      double a = abs1(P[i + j * m]);
+      if (!(a == a)) a = INFINITY;  // propagate NaN as "largest" so it is detected below
+      best = better(best, ArgMax{a, i});
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMax other{__shfl_down_sync(0xffffffffu, best.v, o), __shfl_down_sync(0xffffffffu, best.i, o)};
+      best = better(best, other);
+    }
+    if (lane == 0) s_red[wid] = best;
+    __syncthreads();
+    if (tid == 0) {
+      ArgMax b = s_red[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) b = better(b, s_red[w]);
+      int piv = b.i;
+      double a = b.v;
+      if (isinf(a)) st->nonfinite = 1;
+      if (a <= tiny_abs) {
+        if (tiny_abs == 0.0) {
+          st->zero_pivot = 1;
+          a = 1.0;  // keep going with a harmless value; the host reports the error
+          P[piv + j * m] = scalar_traits<T>::one();
+        } else {
+          // static pivoting: keep the diagonal candidate, replace by tiny_abs with its phase
+          piv = j;
+          T d = P[j + j * m];
+          double ad = absz(d);
+          T repl = ad > 0.0 ? d * (tiny_abs / ad) : scalar_traits<T>::from(mk(tiny_abs, 0.0));
+          P[j + j * m] = repl;
+          atomicAdd(&st->n_perturbed, 1ULL);
+          a = tiny_abs;
+        }
+      }
+      atomicMin(&st->min_piv_bits, (unsigned long long)__double_as_longlong(a));
+      atomicMax(&st->max_piv_bits, (unsigned long long)__double_as_longlong(a));
+      if (piv != j) atomicAdd(&st->n_swaps, 1ULL);
+      ipiv[f.col0 + j] = piv;
+      s_piv = piv;
+    }
+    __syncthreads();
+    // 2. interchange inside the panel
+    const int piv = s_piv;
+    if (piv != j && tid < jb) {
+      const long long c = j0 + tid;
+      T a = P[j + c * m], b = P[piv + c * m];
+      P[j + c * m] = b;
+      P[piv + c * m] = a;
+    }
+    __syncthreads();
+    if (tid == 0) s_inv = recip(P[j + j * m]);
+    __syncthreads();
+    // 3. scale the column and rank-1 update of the remaining panel columns
+    const T inv = s_inv;
+    const int nc = j0 + jb - (j + 1);
+    for (int i = j + 1 + tid; i < k; i += blockDim.x) {
+      const T l = P[i + j * m] * inv;
+      P[i + j * m] = l;
+      for (int c = 0; c < nc; ++c) {
+        const long long cc = j + 1 + c;
+        P[i + cc * m] = P[i + cc * m] - l * P[j + cc * m];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ row swaps + U rows
+
+// After panel [j0, j0+jb): apply its interchanges to every other column of the k pivot rows
+// (left part of P, right part of P, all of Q) and solve the unit-lower block system for the columns
+// to the right (U12 rows).  grid: (column groups of 128, fronts); block 128 threads.
+// The jb x 128 tile is staged through shared memory so that global traffic is coalesced.
+template <class T>
+__global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, int j0, T* __restrict__ fac,
+                                                   const int* __restrict__ ipiv) {
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k, r = f.r;
+  if (k <= j0) return;
+  const int jb = min(NB, k - j0), j1 = j0 + jb;
+  const long long m = (long long)k + r;
+  // logical column space: [0, j0) left of panel | [j1, k) right of panel in P | [0, r) of Q
+  const int n_left = j0, n_right = k - j1, ncols = n_left + n_right + r;
+  const int cbase = blockIdx.x * 128;
+  if (cbase >= ncols) return;
+  T* P = fac + f.p_off;
+  T* Q = fac + f.q_off;
+  extern __shared__ unsigned char smem_raw[];
+  T* s_L = reinterpret_cast<T*>(smem_raw);  // NB x NB, column-major, unit lower
+  T* s_tile = s_L + NB * NB;                // 128 columns x (NB+1)
+  __shared__ int s_piv[NB];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 128) {
+    const int i = e % NB, c = e / NB;
+    s_L[e] = (i < jb && c < jb && i > c) ? P[(j0 + i) + (long long)(j0 + c) * m] : scalar_traits<T>::zero();
+  }
+  if (tid < NB) s_piv[tid] = tid < jb ? ipiv[f.col0 + j0 + tid] : -1;
+  __syncthreads();
+  // this thread's column
+  const int lc = cbase + tid;
+  T* col = nullptr;
+  bool right = false;
+  if (lc < ncols) {
+    if (lc < n_left) col = P + (long long)lc * m;
+    else if (lc < n_left + n_right) {
+      col = P + (long long)(j1 + lc - n_left) * m;
+      right = true;
+    } else {
+      col = Q + (long long)(lc - n_left - n_right) * k;
+      right = true;
+    }
+    for (int t = 0; t < jb; ++t) {
+      const int piv = s_piv[t];
+      if (piv != j0 + t) {
+        T a = col[j0 + t], b = col[piv];
+        col[j0 + t] = b;
+        col[piv] = a;
+      }
+    }
+  }
+  // whole block: either all "left" columns (nothing more to do) or some right columns
+  const bool block_has_right = cbase + 127 >= n_left;
+  if (!block_has_right) return;
+  __syncthreads();
+  // stage rows [j0, j1) of the 128 columns: one warp per column, lanes along rows (coalesced)
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int c = wid; c < 128; c += 4) {
+    const int g = cbase + c;
+    T v = scalar_traits<T>::zero();
+    if (g < ncols && g >= n_left && lane < jb) {
+      const T* src = g < n_left + n_right ? P + (long long)(j1 + g - n_left) * m : Q + (long long)(g - n_left - n_right) * k;
+      v = src[j0 + lane];
+    }
+    s_tile[c * (NB + 1) + lane] = v;
+  }
+  __syncthreads();
+  if (right) {
+    T* u = s_tile + tid * (NB + 1);
+#pragma unroll 1
+    for (int t = 1; t < jb; ++t) {
+      T acc = u[t];
+      for (int s = 0; s < t; ++s) acc = acc - s_L[t + s * NB] * u[s];
+      u[t] = acc;
+    }
+  }
+  __syncthreads();
+  for (int c = wid; c < 128; c += 4) {
+    const int g = cbase + c;
+    if (g < ncols && g >= n_left && lane < jb) {
+      T* dst = g < n_left + n_right ? P + (long long)(j1 + g - n_left) * m : Q + (long long)(g - n_left - n_right) * k;
+      dst[j0 + lane] = s_tile[c * (NB + 1) + lane];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------- L21 panel
+
+// Rows [k, m) of the panel columns: X U_jj = B.  One thread per row; grid (row groups of 128, fronts).
+template <class T>
+__global__ void __launch_bounds__(128) k_trsm_cols(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, int j0, T* __restrict__ fac) {
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k, r = f.r;
+  if (k <= j0 || r == 0) return;
+  if (blockIdx.x * 128 >= r) return;
+  const int jb = min(NB, k - j0);
+  const long long m = (long long)k + r;
+  T* P = fac + f.p_off;
+  __shared__ T s_U[NB * NB];  // column-major upper triangle, diagonal holds reciprocals
+  for (int e = threadIdx.x; e < NB * NB; e += 128) {
+    const int i = e % NB, c = e / NB;
+    T v = scalar_traits<T>::zero();
+    if (i < jb && c < jb && i <= c) {
+      v = P[(j0 + i) + (long long)(j0 + c) * m];
+      if (i == c) v = recip(v);
+    }
+    s_U[e] = v;
+  }
+  __syncthreads();
+  const int row = blockIdx.x * 128 + threadIdx.x;
+  if (row >= r) return;
+  T* x = P + k + row + (long long)j0 * m;
+  T xs[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    if (c < jb) {
+      T acc = x[(long long)c * m];
+#pragma unroll
+      for (int s = 0; s < c; ++s) acc = acc - xs[s] * s_U[s + c * NB];
+      xs[c] = acc * s_U[c + c * NB];
+      x[(long long)c * m] = xs[c];
+    } else {
+      xs[c] = scalar_traits<T>::zero();
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------- FP64 DMMA GEMM
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// C(Mr x N) -= A^(Mr x Kr) B(Kr x N), everything in the "real view" of column-major storage.
+//   real    : A^ = A                                   (lda_r = lda)
+//   complex : rows/ld doubled (interleaved re,im);  A^[2i+a, 2k+b] = a==b ? Re A[i,k] : (a ? +Im : -Im)
+// CTA tile 64 x 64, 4 warps as 2 x 2, warp tile 32 x 32 = 4 x 4 m8n8k4 fragments, K chunk 16.
+template <bool CPLX>
+__device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long long lda_r, const double* __restrict__ B,
+                                          long long ldb_r, double* __restrict__ C, long long ldc_r, int Mr, int N,
+                                          int Kr, int m0, int n0) {
+  constexpr int BM = 64, BN = 64, KC = 16;
+  constexpr int LDA_S = BM + 4;               // conflict-free fragment reads
+  constexpr int LDB_S = KC + 4;
+  constexpr int KA = CPLX ? KC / 2 : KC;      // stored A columns per chunk
+  constexpr int A_PER_T = BM * KA / 128;      // 8 real, 4 complex
+  __shared__ double As[2][KA * LDA_S];
+  __shared__ double Bs[2][BN * LDB_S];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int wm = wid & 1, wn = wid >> 1;
+  const int g = lane >> 2, tg = lane & 3;
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // global -> register staging
+  const int a_row = tid & 63, a_kg = tid >> 6;  // 2 groups of stored columns
+  const int b_n = tid >> 1, b_kh = (tid & 1) * 8;
+  double ra[A_PER_T], rb[8];
+  const int nchunks = (Kr + KC - 1) / KC;
+
+  auto load_global = [&](int kc) {
+    const int k0 = kc * KC;  // real-view K offset
+    const int ka0 = CPLX ? k0 / 2 : k0;
+    const int ka_lim = CPLX ? Kr / 2 : Kr;
+    const bool rok = (m0 + a_row) < Mr;
+#pragma unroll
+    for (int q = 0; q < A_PER_T; ++q) {
+      const int ka = a_kg * A_PER_T + q;
+      ra[q] = (rok && (ka0 + ka) < ka_lim) ? __ldg(A + (m0 + a_row) + (long long)(ka0 + ka) * lda_r) : 0.0;
+    }
+    const bool nok = (n0 + b_n) < N;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int kk = k0 + b_kh + q;
+      rb[q] = (nok && kk < Kr) ? __ldg(B + kk + (long long)(n0 + b_n) * ldb_r) : 0.0;
+    }
+  };
+  auto store_smem = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < A_PER_T; ++q) As[buf][(a_kg * A_PER_T + q) * LDA_S + a_row] = ra[q];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) Bs[buf][b_n * LDB_S + b_kh + q] = rb[q];
+  };
+
+  load_global(0);
+  store_smem(0);
+  __syncthreads();
+  for (int kc = 0; kc < nchunks; ++kc) {
+    const int cur = kc & 1;
+    if (kc + 1 < nchunks) load_global(kc + 1);
+    const double* as = As[cur];
+    const double* bs = Bs[cur];
+#pragma unroll
+    for (int ks = 0; ks < KC / 4; ++ks) {
+      double af[4], bf[4];
+      const int kk = ks * 4 + tg;  // real-view k inside the chunk
+#pragma unroll
+      for (int mf = 0; mf < 4; ++mf) {
+        const int R = wm * 32 + mf * 8 + g;
+        if (CPLX) {
+          const int a = R & 1, b = kk & 1;
+          const double v = as[(kk >> 1) * LDA_S + (R - a) + (a != b)];
+          af[mf] = (a == 0 && b == 1) ? -v : v;
+        } else {
+          af[mf] = as[kk * LDA_S + R];
+        }
+      }
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) bf[nf] = bs[(wn * 32 + nf * 8 + g) * LDB_S + kk];
+#pragma unroll
+      for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[mf], bf[nf]);
+    }
+    if (kc + 1 < nchunks) store_smem(cur ^ 1);
+    __syncthreads();
+  }
+  // epilogue: C -= acc
+#pragma unroll
+  for (int mf = 0; mf < 4; ++mf) {
+    const int R = m0 + wm * 32 + mf * 8 + g;
+    if (R >= Mr) continue;
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) {
+      const int c0 = n0 + wn * 32 + nf * 8 + tg * 2;
+      if (c0 < N) {
+        double* p = C + R + (long long)c0 * ldc_r;
+        *p -= acc[mf][nf][0];
+      }
+      if (c0 + 1 < N) {
+        double* p = C + R + (long long)(c0 + 1) * ldc_r;
+        *p -= acc[mf][nf][1];
+      }
+    }
+  }
+}
+
+// mode 0: trailing update after panel [j0, j1):
+//           region 1  P[j1:m, j1:k]   -= P[j1:m, j0:j1] * P[j0:j1, j1:k]
+//           region 2  Q[j1:k, 0:r]    -= P[j1:k, j0:j1] * Q[j0:j1, 0:r]
+// mode 1: Schur complement  C[0:r, 0:r] -= P[k:m, 0:k] * Q[0:k, 0:r]
+// grid: (tiles, fronts of the level)
+template <class T>
+__global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                    int first, int j0, int mode, T* __restrict__ fac,
+                                                    T* __restrict__ pool) {
+  constexpr bool CPLX = scalar_traits<T>::is_complex;
+  constexpr int S = CPLX ? 2 : 1;
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k, r = f.r;
+  const long long m = (long long)k + r;
+  T* P = fac + f.p_off;
+  T* Q = fac + f.q_off;
+  int t = blockIdx.x;
+  if (mode == 0) {
+    if (k <= j0) return;
+    const int jb = min(NB, k - j0), j1 = j0 + jb;
+    const int R1 = (int)(m - j1), C1 = k - j1, R2 = k - j1, C2 = r;
+    const int tm1 = (R1 * S + 63) / 64, tn1 = (C1 + 63) / 64;
+    const int tm2 = (R2 * S + 63) / 64, tn2 = (C2 + 63) / 64;
+    if (t < tm1 * tn1) {
+      const int tm = t % tm1, tn = t / tm1;
+      gemm_tile<CPLX>((const double*)(P + j1 + (long long)j0 * m), m * S, (const double*)(P + j0 + (long long)j1 * m),
+                      m * S, (double*)(P + j1 + (long long)j1 * m), m * S, R1 * S, C1, jb * S, tm * 64, tn * 64);
+      return;
+    }
+    t -= tm1 * tn1;
+    if (t < tm2 * tn2) {
+      const int tm = t % tm2, tn = t / tm2;
+      gemm_tile<CPLX>((const double*)(P + j1 + (long long)j0 * m), m * S, (const double*)(Q + j0), (long long)k * S,
+                      (double*)(Q + j1), (long long)k * S, R2 * S, C2, jb * S, tm * 64, tn * 64);
+    }
+  } else {
+    if (r == 0 || k == 0) return;
+    T* C = pool + f.c_off;
+    const int tm1 = (r * S + 63) / 64, tn1 = (r + 63) / 64;
+    if (t < tm1 * tn1) {
+      const int tm = t % tm1, tn = t / tm1;
+      gemm_tile<CPLX>((const double*)(P + k), m * S, (const double*)Q, (long long)k * S, (double*)C,
+                      (long long)r * S, r * S, r, k * S, tm * 64, tn * 64);
+    }
+  }
+}
+
+// stand-alone GEMM used by lsa_gemm_bench (same tile code as the front updates)
+template <bool CPLX>
+__global__ void __launch_bounds__(128) k_gemm_plain(const double* A, long long lda_r, const double* B, long long ldb_r,
+                                                    double* C, long long ldc_r, int Mr, int N, int Kr) {
+  const int tm1 = (Mr + 63) / 64;
+  const int tm = blockIdx.x % tm1, tn = blockIdx.x / tm1;
+  gemm_tile<CPLX>(A, lda_r, B, ldb_r, C, ldc_r, Mr, N, Kr, tm * 64, tn * 64);
+}
+
+void gemm_plain(cudaStream_t st, bool cplx, const void* A, long long lda, const void* B, long long ldb, void* C,
+                long long ldc, int M, int N, int K) {
+  const int S = cplx ? 2 : 1;
+  const int tiles = cdiv((long long)M * S, 64) * cdiv(N, 64);
+  if (cplx)
+    k_gemm_plain<true><<<tiles, 128, 0, st>>>((const double*)A, lda * 2, (const double*)B, ldb * 2, (double*)C,
+                                               ldc * 2, M * 2, N, K * 2);
+  else
+    k_gemm_plain<false><<<tiles, 128, 0, st>>>((const double*)A, lda, (const double*)B, ldb, (double*)C, ldc, M, N, K);
+  LSA_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- driver
+
+template <class T, class VT>
+static void launch_scatter(cudaStream_t st, T* fac, const long long* dst, const void* vals, long long nnz, z128 coef,
+                           int accumulate) {
+  if (nnz == 0) return;
+  const int blocks = (int)std::min<long long>((nnz + 255) / 256, 148LL * 16);
+  k_scatter<T, VT><<<blocks, 256, 0, st>>>(fac, dst, (const VT*)vals, nnz, coef, accumulate);
+  LSA_LAUNCH_CHECK();
+}
+
+template <class T>
+void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, int* n_kernels) {
+  const Symbolic& sym = h.sym;
+  cudaStream_t st = h.stream;
+  T* fac = (T*)h.d_fac;
+  T* pool[2] = {(T*)h.d_pool[0], (T*)h.d_pool[1]};
+  int launches = 0;
+  LSA_CUDA(cudaMemsetAsync(fac, 0, sym.fac_size * sizeof(T), st));
+  DevStats init{};
+  init.min_piv_bits = (unsigned long long)0x7ff0000000000000ULL;  // +inf
+  init.max_piv_bits = 0ULL;
+  LSA_CUDA(cudaMemcpyAsync(h.d_stats, &init, sizeof(DevStats), cudaMemcpyHostToDevice, st));
+
+  // ---- assemble F = alpha A + beta M into the front panels (never materialised as a matrix)
+  const bool use_a = alpha.x != 0.0 || alpha.y != 0.0;
+  const bool use_m = h.has_m && (beta.x != 0.0 || beta.y != 0.0);
+  if (use_a) {
+    if (h.a_complex) {
+      if constexpr (scalar_traits<T>::is_complex) launch_scatter<T, z128>(st, fac, h.d_a_dst, h.d_a_orig, h.nnz_a, alpha, 0);
+    } else {
+      launch_scatter<T, double>(st, fac, h.d_a_dst, h.d_a_orig, h.nnz_a, alpha, 0);
+    }
+    launches++;
+  }
+  if (use_m) {
+    if (h.m_complex) {
+      if constexpr (scalar_traits<T>::is_complex) launch_scatter<T, z128>(st, fac, h.d_m_dst, h.d_m_orig, h.nnz_m, beta, 1);
+    } else {
+      launch_scatter<T, double>(st, fac, h.d_m_dst, h.d_m_orig, h.nnz_m, beta, 1);
+    }
+    launches++;
+  }
+  if (sym.n_iso > 0) {
+    k_decoupled_pivots<T><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, tiny_abs, h.d_stats);
+    LSA_LAUNCH_CHECK();
+    launches++;
+  }
+
+  const size_t swap_smem = (size_t)(NB * NB + 128 * (NB + 1)) * sizeof(T);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[scalar_traits<T>::is_complex]) {
+    LSA_CUDA(cudaFuncSetAttribute(k_swap_trsm<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem));
+    attr_set[scalar_traits<T>::is_complex] = true;
+  }
+  constexpr int S = scalar_traits<T>::is_complex ? 2 : 1;
+  constexpr int YMAX = 32768;
+
+  for (int d = sym.nlevels - 1; d >= 0; --d) {
+    const int lbeg = sym.lvl_ptr[d], lend = sym.lvl_ptr[d + 1];
+    const int cnt_all = lend - lbeg;
+    // contribution blocks of this level start from zero
+    long long pool_used = 0;
+    for (int q = lbeg; q < lend; ++q) {
+      const Front& f = sym.fronts[sym.lvl_front[q]];
+      pool_used = std::max(pool_used, f.c_off + (long long)f.r * f.r);
+    }
+    if (pool_used > 0) LSA_CUDA(cudaMemsetAsync(pool[d & 1], 0, pool_used * sizeof(T), st));
+    for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
+      const int cnt = std::min(YMAX, cnt_all - y0);
+      const int first = lbeg + y0;
+      // level-chunk extents (fronts are sorted by descending k inside a level)
+      int maxk = 0, maxchild = 0, max_rc = 0;
+      for (int q = first; q < first + cnt; ++q) {
+        const Front& f = sym.fronts[sym.lvl_front[q]];
+        maxk = std::max(maxk, f.k);
+        maxchild = std::max(maxchild, f.nchild);
+        for (int c = 0; c < f.nchild; ++c) max_rc = std::max(max_rc, sym.fronts[sym.child_idx[f.child0 + c]].r);
+      }
+      // ---- extend-add, one child slot per launch
+      for (int slot = 0; slot < maxchild; ++slot) {
+        const int gx = std::max(1, std::min(64, max_rc / 8));
+        k_extend_add<T><<<dim3(gx, cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_child_idx, h.d_ea_map, slot,
+                                                       fac, pool[(d + 1) & 1], pool[d & 1]);
+        LSA_LAUNCH_CHECK();
+        launches++;
+      }
+      // ---- blocked partial LU of every front of the chunk
+      for (int j0 = 0; j0 < maxk; j0 += NB) {
+        // fronts with k > j0 form a prefix of the chunk
+        int act = 0;
+        int gx_cols = 1, gx_rows = 0, gx_tiles = 0;
+        for (int q = first; q < first + cnt; ++q) {
+          const Front& f = sym.fronts[sym.lvl_front[q]];
+          if (f.k <= j0) break;
+          act++;
+          const int jb = std::min(NB, f.k - j0), j1 = j0 + jb;
+          const long long m = (long long)f.k + f.r;
+          gx_cols = std::max(gx_cols, cdiv((long long)j0 + (f.k - j1) + f.r, 128));
+          gx_rows = std::max(gx_rows, cdiv(f.r, 128));
+          const long long t1 = (long long)cdiv((m - j1) * S, 64) * cdiv(f.k - j1, 64);
+          const long long t2 = (long long)cdiv((long long)(f.k - j1) * S, 64) * cdiv(f.r, 64);
+          gx_tiles = (int)std::max<long long>(gx_tiles, t1 + t2);
+        }
+        if (act == 0) break;
+        k_panel_lu<T><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs, h.d_stats);
+        LSA_LAUNCH_CHECK();
+        k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv);
+        LSA_LAUNCH_CHECK();
+        launches += 2;
+        if (gx_rows > 0) {
+          k_trsm_cols<T><<<dim3(gx_rows, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac);
+          LSA_LAUNCH_CHECK();
+          launches++;
+        }
+        if (gx_tiles > 0) {
+          k_front_gemm<T><<<dim3(gx_tiles, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, 0, fac, pool[d & 1]);
+          LSA_LAUNCH_CHECK();
+          launches++;
+        }
+      }
+      // ---- Schur complement of every front of the chunk
+      int gx_schur = 0;
+      for (int q = first; q < first + cnt; ++q) {
+        const Front& f = sym.fronts[sym.lvl_front[q]];
+        if (f.r > 0 && f.k > 0)
+          gx_schur = (int)std::max<long long>(gx_schur, (long long)cdiv((long long)f.r * S, 64) * cdiv(f.r, 64));
+      }
+      if (gx_schur > 0) {
+        k_front_gemm<T><<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, 1, fac, pool[d & 1]);
+        LSA_LAUNCH_CHECK();
+        launches++;
+      }
+    }
+  }
+  if (n_kernels) *n_kernels = launches;
+}
+
+template void factor_numeric<double>(lsa_handle_impl&, z128, z128, double, int*);
+template void factor_numeric<z128>(lsa_handle_impl&, z128, z128, double, int*);
+
+}  // namespace lsa

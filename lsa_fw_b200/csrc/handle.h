@@ -1,0 +1,138 @@
+// Solver handle: host symbolic data, device plan, device buffers.  One handle = one stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lsa_b200.h"
+#include "common.cuh"
+#include "lsa_internal.h"
+
+namespace lsa {
+
+// CSR operator in the PERMUTED ordering, values gathered from the caller's entry order.
+struct CsrHost {
+  std::vector<long long> rowptr;
+  std::vector<int> colidx;
+  std::vector<long long> src;  // permuted entry -> original entry
+};
+struct CsrDev {
+  long long nnz = 0;
+  long long* rowptr = nullptr;
+  int* colidx = nullptr;
+  long long* src = nullptr;
+  void* vals = nullptr;  // permuted values, double or z128 (is_complex)
+  bool is_complex = false;
+};
+
+struct DevStats {
+  unsigned long long n_perturbed;
+  unsigned long long n_swaps;
+  unsigned long long min_piv_bits;  // bit pattern of a non-negative double
+  unsigned long long max_piv_bits;
+  int zero_pivot;
+  int nonfinite;
+};
+
+// Result block written by the Rayleigh-Ritz kernel, read back once per restart.
+struct RrInfo {
+  int nconv;      // length of the converged leading run
+  int keep;       // columns kept for the restart (nconv + l)
+  int status;     // 0 ok, 1 QR iteration did not converge
+  int pad;
+};
+
+struct Launch {
+  int kind;   // see factor.cu
+  int level;
+  int j0;
+  int gx;     // tiles
+  int pad;
+};
+
+struct lsa_handle_impl {
+  int n = 0;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // ---- host symbolic
+  Symbolic sym;
+  bool analyzed = false;
+  bool has_m = false;
+  CsrHost hA, hM, hAt, hMt;     // permuted patterns (transposes built on demand)
+  std::vector<long long> m_dst;  // like sym.a_dst for the entries of M
+  long long nnz_a = 0, nnz_m = 0;
+
+  // ---- device plan
+  Front* d_fronts = nullptr;
+  int* d_lvl_front = nullptr;
+  int* d_st_idx = nullptr;
+  int* d_ea_map = nullptr;
+  int* d_child_idx = nullptr;
+  long long* d_a_dst = nullptr;
+  long long* d_m_dst = nullptr;
+  int* d_perm = nullptr;
+  int* d_ipiv = nullptr;
+  int* d_gperm = nullptr;   // composed row interchanges of all fronts (gather form)
+  DevStats* d_stats = nullptr;
+  std::vector<int> lvl_maxchild;   // per level: max number of children of its fronts
+  std::vector<int> lvl_maxk;       // per level: largest pivot count
+  std::vector<int> lvl_maxrchild;  // per level: largest child contribution block order
+
+  // ---- values
+  void* d_a_orig = nullptr;  // caller entry order
+  void* d_m_orig = nullptr;
+  bool a_complex = false, m_complex = false;
+  bool have_values = false;
+  CsrDev dA, dM, dAt, dMt;
+  double a_fro = 0.0, a_max = 0.0, m_max = 0.0;
+
+  // ---- factor
+  int scalar = -1;  // lsa_scalar of the current factor, -1: none
+  void* d_fac = nullptr;
+  long long fac_capacity_bytes = 0;
+  void* d_pool[2] = {nullptr, nullptr};
+  long long pool_capacity_bytes[2] = {0, 0};
+  lsa_factor_stats fstats{};
+  z128 f_alpha{1, 0}, f_beta{0, 0};
+
+  // ---- solve / Krylov work space (permuted ordering, complex)
+  z128* d_x = nullptr;     // n
+  z128* d_w = nullptr;     // n
+  z128* d_t = nullptr;     // n
+  z128* d_cb = nullptr;    // total structure length: per-front contribution vectors
+  z128* d_io = nullptr;    // n staging for host vectors
+  z128* d_V = nullptr;     // n x (ncv+1)
+  long long V_cols = 0;
+  z128* d_S = nullptr;     // (ncv+1) x ncv projected matrix, ld = ncv+1
+  z128* d_Q = nullptr;     // ncv x ncv
+  z128* d_part = nullptr;  // partial dot products [blocks][128]
+  double* d_npart = nullptr;  // partial squared norms
+  z128* d_h = nullptr;     // CGS coefficients
+  z128* d_brow = nullptr;
+  z128* d_ywork = nullptr;
+  z128* d_r1 = nullptr;    // refinement / residual scratch vectors
+  z128* d_r2 = nullptr;
+  z128* d_r3 = nullptr;
+  z128* d_Xp = nullptr;    // n x ncv Ritz vectors, permuted ordering
+  int* d_flag = nullptr;
+  RrInfo* d_rr = nullptr;
+  z128* d_theta = nullptr;
+  double* d_resid = nullptr;
+  int ncv_alloc = 0;
+
+  // ---- results
+  int nconv = 0;
+  std::vector<z128> eigenvalues;   // back-transformed, `which` order
+  std::vector<int> eig_order;      // column of d_X for each returned pair
+  z128* d_X = nullptr;             // n x nconv eigenvectors, ORIGINAL ordering
+  int X_cols = 0;
+  lsa_eigs_params last_params{};
+  lsa_counters counters{};
+};
+
+}  // namespace lsa
+
+struct lsa_handle : lsa::lsa_handle_impl {};

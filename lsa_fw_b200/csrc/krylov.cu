@@ -1,0 +1,752 @@
+// Krylov-Schur eigensolver on the device: operator application (SpMV + triangular solves),
+// block CGS2 orthogonalisation, Rayleigh-Ritz, locking restart, Ritz vectors, purification.
+//
+// Stands in for `SLEPc.EPS.solve()` with EPS type krylovschur and ST sinvert/shift
+// (reference Solver/utils.py:268-270 and the defaults discussed in SURVEY.md section 8a):
+//   OP = (A - sigma M)^-1 M          (STApply_Sinvert; explicit in Solver/eigen2.py:164-190)
+//   BVOrthogonalizeColumn            -> k_dots / k_reduce_h / k_update   (tall-skinny, HBM bound)
+//   DSSolve + DSSort + convergence   -> k_rr (single CTA, rr_core.h)
+//   BVMultInPlace (restart)          -> k_basis_gemm
+//   EPSComputeVectors + purification -> k_ritz_vectors + k_basis_gemm + one more OP apply
+// The host only sequences launches; it reads back one small struct per restart.
+#include <cstring>
+#include <vector>
+
+#include "factor.cuh"
+#include "rr_core.h"
+
+namespace lsa {
+
+// ---------------------------------------------------------------------------------------- SpMV
+
+// y = Op x, CSR with 8 lanes per row (rows of the FE pencils hold 10-100 entries).
+template <class VT, bool CONJ>
+__global__ void __launch_bounds__(256) k_spmv(int n, const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+                                              const VT* __restrict__ vals, const z128* __restrict__ x,
+                                              z128* __restrict__ y) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gid >> 3, sub = gid & 7;
+  z128 acc = mk(0, 0);
+  if (row < n) {
+    const long long b = rowptr[row], e = rowptr[row + 1];
+    for (long long p = b + sub; p < e; p += 8) acc += cj<CONJ>(vals[p]) * x[colidx[p]];
+  }
+  for (int o = 4; o > 0; o >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+  }
+  if (row < n && sub == 0) y[row] = acc;
+}
+
+void spmv(lsa_handle_impl& h, const CsrDev& M, bool conj_vals, const z128* x, z128* y) {
+  const int n = h.n;
+  const int blocks = cdiv((long long)n * 8, 256);
+  if (M.is_complex) {
+    if (conj_vals) k_spmv<z128, true><<<blocks, 256, 0, h.stream>>>(n, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
+    else k_spmv<z128, false><<<blocks, 256, 0, h.stream>>>(n, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
+  } else {
+    k_spmv<double, false><<<blocks, 256, 0, h.stream>>>(n, M.rowptr, M.colidx, (const double*)M.vals, x, y);
+  }
+  LSA_LAUNCH_CHECK();
+}
+
+// ----------------------------------------------------------------------------- small vector kernels
+
+__global__ void k_perm_gather(const z128* __restrict__ src, z128* __restrict__ dst, const int* __restrict__ perm, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
+}
+__global__ void k_perm_scatter(const z128* __restrict__ src, z128* __restrict__ dst, const int* __restrict__ perm, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[perm[i]] = src[i];
+}
+void permute_gather(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n) {
+  if (n > 0) k_perm_gather<<<cdiv(n, 256), 256, 0, st>>>(src, dst, perm, n);
+  LSA_LAUNCH_CHECK();
+}
+void permute_scatter(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n) {
+  if (n > 0) k_perm_scatter<<<cdiv(n, 256), 256, 0, st>>>(src, dst, perm, n);
+  LSA_LAUNCH_CHECK();
+}
+
+template <class VT>
+__global__ void k_gather_vals(const VT* __restrict__ orig, const long long* __restrict__ src, VT* __restrict__ out,
+                              long long nnz) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; e < nnz; e += stride) out[e] = orig[src[e]];
+}
+void gather_values(cudaStream_t st, const void* orig, bool is_complex, const long long* src, void* out, long long nnz) {
+  if (nnz == 0) return;
+  const int blocks = (int)std::min<long long>((nnz + 255) / 256, 148LL * 16);
+  if (is_complex) k_gather_vals<z128><<<blocks, 256, 0, st>>>((const z128*)orig, src, (z128*)out, nnz);
+  else k_gather_vals<double><<<blocks, 256, 0, st>>>((const double*)orig, src, (double*)out, nnz);
+  LSA_LAUNCH_CHECK();
+}
+
+// sum |v|^2 and max |v| of a value array -> part[2*blk], part[2*blk+1]
+template <class VT>
+__global__ void __launch_bounds__(256) k_value_norms(const VT* __restrict__ v, long long nnz, double* __restrict__ part) {
+  double s = 0.0, mx = 0.0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+    const double a2 = abs2(v[e]);
+    s += a2;
+    mx = fmax(mx, a2);
+  }
+  __shared__ double ss[256], sm[256];
+  ss[threadIdx.x] = s;
+  sm[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      ss[threadIdx.x] += ss[threadIdx.x + o];
+      sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = ss[0];
+    part[2 * blockIdx.x + 1] = sm[0];
+  }
+}
+void value_norms(lsa_handle_impl& h, const void* vals, bool is_complex, long long nnz, double* fro, double* amax) {
+  *fro = 0.0;
+  *amax = 0.0;
+  if (nnz == 0) return;
+  const int blocks = (int)std::min<long long>((nnz + 255) / 256, 256);
+  double* d_part = nullptr;
+  LSA_CUDA(cudaMalloc(&d_part, sizeof(double) * 2 * blocks));
+  if (is_complex) k_value_norms<z128><<<blocks, 256, 0, h.stream>>>((const z128*)vals, nnz, d_part);
+  else k_value_norms<double><<<blocks, 256, 0, h.stream>>>((const double*)vals, nnz, d_part);
+  std::vector<double> part(2 * blocks);
+  LSA_CUDA(cudaMemcpyAsync(part.data(), d_part, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, h.stream));
+  LSA_CUDA(cudaStreamSynchronize(h.stream));
+  cudaFree(d_part);
+  double s = 0, mx = 0;
+  for (int b = 0; b < blocks; ++b) {
+    s += part[2 * b];
+    mx = std::max(mx, part[2 * b + 1]);
+  }
+  *fro = std::sqrt(s);
+  *amax = std::sqrt(mx);
+}
+
+// splitmix64 -> Box-Muller standard normal start vector (real part; imaginary part zero)
+__global__ void k_randn(z128* __restrict__ x, int n, unsigned long long seed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(2 * i + 1);
+  auto next = [&]() {
+    z += 0x9E3779B97F4A7C15ULL;
+    unsigned long long r = z;
+    r = (r ^ (r >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    r = (r ^ (r >> 27)) * 0x94D049BB133111EBULL;
+    return r ^ (r >> 31);
+  };
+  const double u1 = ((next() >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+  const double u2 = (next() >> 11) * (1.0 / 9007199254740992.0);
+  x[i] = mk(sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2), 0.0);
+}
+
+// y = a x + y   /  y = x * s
+__global__ void k_axpy(int n, z128 a, const z128* __restrict__ x, z128* __restrict__ y) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a * x[i];
+}
+__global__ void k_copy(int n, const z128* __restrict__ x, z128* __restrict__ y) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i];
+}
+__global__ void k_sub(int n, const z128* __restrict__ a, const z128* __restrict__ b, z128* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] - b[i];
+}
+
+// ------------------------------------------------------------------------------------- CGS2 kernels
+
+static constexpr int DOT_ROWS = 32;   // row lanes
+static constexpr int DOT_CG = 8;      // column groups
+static constexpr int MAXC_PER = 16;   // columns per thread -> up to 128 basis vectors
+
+// part[blk * ldp + c] = sum over the block's rows of conj(V[i, c]) w[i],  c < j
+__global__ void __launch_bounds__(256) k_dots(int n, int j, const z128* __restrict__ V, long long ldv,
+                                              const z128* __restrict__ w, z128* __restrict__ part, int ldp,
+                                              int rows_per_block) {
+  const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min((long long)n, r0 + rows_per_block);
+  z128 acc[MAXC_PER];
+#pragma unroll
+  for (int q = 0; q < MAXC_PER; ++q) acc[q] = mk(0, 0);
+  for (long long i = r0 + lane; i < r1; i += DOT_ROWS) {
+    const z128 wi = w[i];
+#pragma unroll
+    for (int q = 0; q < MAXC_PER; ++q) {
+      const int c = cg + q * DOT_CG;
+      if (c < j) acc[q] += conj_(V[i + c * ldv]) * wi;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < MAXC_PER; ++q) {
+    const int c = cg + q * DOT_CG;
+    if (c < j) {
+      z128 a = acc[q];
+      for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      }
+      if (lane == 0) part[(long long)blockIdx.x * ldp + c] = a;
+    }
+  }
+}
+
+// h[c] = sum_blk part[blk, c]; S column update: scol[c] = (accumulate ? scol[c] : 0) + h[c].
+// One warp per column.
+__global__ void __launch_bounds__(256) k_reduce_h(int j, int nblk, const z128* __restrict__ part, int ldp,
+                                                  z128* __restrict__ h, z128* __restrict__ scol, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= j) return;
+  z128 a = mk(0, 0);
+  for (int b = lane; b < nblk; b += 32) a += part[(long long)b * ldp + c];
+  for (int o = 16; o > 0; o >>= 1) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+  }
+  if (lane == 0) {
+    h[c] = a;
+    scol[c] = accumulate ? scol[c] + a : a;
+  }
+}
+
+// w -= V[:, 0:j] h ; optionally npart[blk] = sum |w_new|^2 over the block's rows
+__global__ void __launch_bounds__(256) k_update(int n, int j, const z128* __restrict__ V, long long ldv,
+                                                const z128* __restrict__ h, z128* __restrict__ w,
+                                                double* __restrict__ npart) {
+  __shared__ z128 hs[128];
+  __shared__ double red[8];
+  if ((int)threadIdx.x < j) hs[threadIdx.x] = h[threadIdx.x];
+  __syncthreads();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double nn = 0.0;
+  if (i < n) {
+    z128 acc = w[i];
+    const z128* v = V + i;
+#pragma unroll 8
+    for (int c = 0; c < j; ++c) acc -= v[c * ldv] * hs[c];
+    w[i] = acc;
+    nn = abs2(acc);
+  }
+  if (npart) {
+    for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0;
+      for (int q = 0; q < 8; ++q) s += red[q];
+      npart[blockIdx.x] = s;
+    }
+  }
+}
+
+// npart[blk] = sum |w|^2 over the block's rows
+__global__ void __launch_bounds__(256) k_norm2_part(int n, const z128* __restrict__ w, double* __restrict__ npart) {
+  __shared__ double red[8];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double nn = i < n ? abs2(w[i]) : 0.0;
+  for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int q = 0; q < 8; ++q) s += red[q];
+    npart[blockIdx.x] = s;
+  }
+}
+
+// beta = sqrt(sum npart); out = w / beta.  Every block re-reduces the partials in the same order
+// (deterministic).  Block 0 stores beta (to *beta_out, and to *s_entry as a complex number) and
+// flags a breakdown (beta tiny relative to hnorm_ref) in *flag.
+__global__ void __launch_bounds__(256) k_normalize(int n, const z128* __restrict__ w, z128* __restrict__ out,
+                                                   const double* __restrict__ npart, int nparts,
+                                                   double* __restrict__ beta_out, z128* __restrict__ s_entry,
+                                                   const z128* __restrict__ hcol, int hlen, int* __restrict__ flag,
+                                                   int step) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nparts; b += blockDim.x) s += npart[b];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double beta = sqrt(red[0]);
+  __shared__ int s_break;
+  if (threadIdx.x == 0) {
+    double hn = 0.0;
+    for (int c = 0; c < hlen; ++c) hn += abs2(hcol[c]);
+    hn = sqrt(hn);
+    const bool brk = !(beta > 1e-13 * fmax(hn, 1e-300)) || !(beta == beta);
+    s_break = brk;
+    if (blockIdx.x == 0) {
+      if (beta_out) *beta_out = beta;
+      if (s_entry) *s_entry = mk(brk ? 0.0 : beta, 0.0);
+      if (brk && flag) atomicMin(flag, step);
+    }
+  }
+  __syncthreads();
+  const double inv = s_break ? 0.0 : 1.0 / beta;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = w[i] * inv;
+}
+
+// ------------------------------------------------------------------------------ basis GEMM (restart)
+
+// Out[:, c] = sum_p V[:, p] Qm[p, c],  p < mp, c < nk.  In-place safe (Out may alias V) because each
+// block stages its 32 rows of V in shared memory before writing.
+__global__ void __launch_bounds__(256) k_basis_gemm(int n, int mp, int nk, const z128* __restrict__ V, long long ldv,
+                                                    const z128* __restrict__ Qm, int ldq, z128* __restrict__ Out,
+                                                    long long ldo) {
+  extern __shared__ unsigned char smem_raw[];
+  z128* vs = reinterpret_cast<z128*>(smem_raw);  // [mp][33]
+  const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * 32 + lane;
+  for (int p = cg; p < mp; p += 8) vs[p * 33 + lane] = row < n ? V[row + p * ldv] : mk(0, 0);
+  __syncthreads();
+  for (int c0 = cg; c0 < nk; c0 += 8 * 4) {
+    z128 acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = mk(0, 0);
+    for (int p = 0; p < mp; ++p) {
+      const z128 v = vs[p * 33 + lane];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c0 + q * 8;
+        if (c < nk) acc[q] += v * Qm[p + (long long)c * ldq];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + q * 8;
+      if (c < nk && row < n) Out[row + c * ldo] = acc[q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ Rayleigh-Ritz
+
+__global__ void __launch_bounds__(128) k_rr(z128* S, z128* Q, RrParams p, z128* theta, double* resid, z128* brow,
+                                            z128* ywork, RrInfo* info) {
+  __shared__ double s_rot_c[160];
+  __shared__ z128 s_rot_s[160];
+  __shared__ z128 s_vec[160];
+  __shared__ double s_key[160];
+  __shared__ int s_flag[4];
+  RrWork w{s_rot_c, s_rot_s, s_vec, s_key, s_flag};
+  RrOut out;
+  __shared__ RrOut s_out;
+  rr_full(S, Q, p, theta, resid, brow, ywork, &s_out, threadIdx.x, blockDim.x, w);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out = s_out;
+    info->nconv = out.nconv;
+    info->keep = out.keep;
+    info->status = out.status;
+    info->pad = 0;
+  }
+}
+
+// Schur form only (lsa_dense_schur): S (m x m, ld), sorted by `which`.
+__global__ void __launch_bounds__(128) k_schur_only(z128* S, int ld, z128* Q, int m, RrParams p, RrInfo* info) {
+  __shared__ double s_rot_c[160];
+  __shared__ z128 s_rot_s[160];
+  __shared__ z128 s_vec[160];
+  __shared__ double s_key[160];
+  __shared__ int s_flag[4];
+  RrWork w{s_rot_c, s_rot_s, s_vec, s_key, s_flag};
+  const int st = rr_schur(S, ld, Q, m, m, 0, threadIdx.x, blockDim.x, w);
+  rr_sort(S, ld, Q, m, m, 0, p, threadIdx.x, blockDim.x, w);
+  if (threadIdx.x == 0) {
+    info->status = st;
+    info->nconv = 0;
+    info->keep = 0;
+  }
+}
+
+void dense_schur_device(lsa_handle_impl& h, int m, z128* dS, int ld, z128* dQ, int which, int transform, z128 sigma) {
+  if (m > 150) throw std::runtime_error("dense Schur kernel supports m <= 150");
+  RrParams p{};
+  p.m = m; p.ld = ld; p.ldq = m; p.nconv = 0; p.nev = m; p.which = which; p.transform = transform;
+  p.sigma = sigma; p.tol = 0; p.last = 1; p.beta_scale = 1.0;
+  RrInfo* d_info;
+  LSA_CUDA(cudaMalloc(&d_info, sizeof(RrInfo)));
+  k_schur_only<<<1, 128, 0, h.stream>>>(dS, ld, dQ, m, p, d_info);
+  LSA_LAUNCH_CHECK();
+  RrInfo info;
+  LSA_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(RrInfo), cudaMemcpyDeviceToHost, h.stream));
+  LSA_CUDA(cudaStreamSynchronize(h.stream));
+  cudaFree(d_info);
+  if (info.status != 0) throw std::runtime_error("dense Schur: QR iteration did not converge");
+}
+
+// Eigenvectors of the leading nc x nc triangle of S: column c of Y (nc x nc, ld = ldy), unit 2-norm.
+__global__ void k_ritz_vectors(const z128* __restrict__ S, int ld, int nc, z128* __restrict__ Y, int ldy) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  z128* y = Y + (long long)c * ldy;
+  for (int i = c + 1; i < nc; ++i) y[i] = mk(0, 0);
+  // brow unused: pass a zero row through y itself is not possible, so replicate the substitution here
+  const z128 tkk = S[c + (long long)c * ld];
+  double smax = 0.0;
+  for (int i = 0; i <= c; ++i) smax = fmax(smax, abs1(S[i + (long long)i * ld]));
+  const double smin = fmax(smax * 2.220446049250313e-16, 1e-300);
+  y[c] = mk(1, 0);
+  for (int i = c - 1; i >= 0; --i) {
+    z128 acc = mk(0, 0);
+    for (int j = i + 1; j <= c; ++j) acc += S[i + (long long)j * ld] * y[j];
+    z128 d = S[i + (long long)i * ld] - tkk;
+    if (abs1(d) < smin) d = mk(smin, 0);
+    y[i] = mk(0, 0) - acc / d;
+  }
+  double nrm2 = 0.0;
+  for (int i = 0; i <= c; ++i) nrm2 += abs2(y[i]);
+  const double inv = 1.0 / sqrt(nrm2);
+  for (int i = 0; i <= c; ++i) y[i] = y[i] * inv;
+}
+
+// ------------------------------------------------------------------------------------- OP and driver
+
+static void solve_dispatch(lsa_handle_impl& h, int trans, z128* x, int* nk) {
+  if (h.scalar == LSA_C128) solve_permuted<z128>(h, trans, x, nk);
+  else solve_permuted<double>(h, trans, x, nk);
+}
+
+// x <- F^-1 x (or F^-H x) with optional iterative refinement against F = alpha A + beta M.
+void op_solve(lsa_handle_impl& h, int trans, z128* x, int refine_steps) {
+  int nk = 0;
+  const int n = h.n;
+  if (refine_steps <= 0) {
+    solve_dispatch(h, trans, x, &nk);
+    return;
+  }
+  // keep b in d_w2, iterate x_{k+1} = x_k + F^-1 (b - F x_k)
+  z128* b = h.d_r1;
+  z128* r = h.d_r2;
+  z128* t = h.d_r3;
+  const int blocks = cdiv(n, 256);
+  k_copy<<<blocks, 256, 0, h.stream>>>(n, x, b);
+  solve_dispatch(h, trans, x, &nk);
+  const bool H = trans == LSA_OP_H;
+  for (int it = 0; it < refine_steps; ++it) {
+    // r = b - (alpha A + beta M) x     (H: conj(alpha) A^H + conj(beta) M^H)
+    k_copy<<<blocks, 256, 0, h.stream>>>(n, b, r);
+    const z128 al = H ? conj_(h.f_alpha) : h.f_alpha, be = H ? conj_(h.f_beta) : h.f_beta;
+    if (al.x != 0.0 || al.y != 0.0) {
+      spmv(h, H ? h.dAt : h.dA, H, x, t);
+      k_axpy<<<blocks, 256, 0, h.stream>>>(n, mk(0, 0) - al, t, r);
+    }
+    if (h.has_m && (be.x != 0.0 || be.y != 0.0)) {
+      spmv(h, H ? h.dMt : h.dM, H, x, t);
+      k_axpy<<<blocks, 256, 0, h.stream>>>(n, mk(0, 0) - be, t, r);
+    }
+    solve_dispatch(h, trans, r, &nk);
+    k_axpy<<<blocks, 256, 0, h.stream>>>(n, mk(1, 0), r, x);
+  }
+  LSA_LAUNCH_CHECK();
+}
+
+struct EventTimer {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  cudaStream_t st;
+  explicit EventTimer(cudaStream_t s) : st(s) {}
+  size_t begin() {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    ev.emplace_back(a, b);
+    return ev.size() - 1;
+  }
+  void end(size_t i) { cudaEventRecord(ev[i].second, st); }
+  double total_seconds() {
+    double s = 0;
+    for (auto& e : ev) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e.first, e.second);
+      s += ms * 1e-3;
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    ev.clear();
+    return s;
+  }
+};
+
+// w = OP v   (all vectors in the permuted ordering)
+static void apply_op(lsa_handle_impl& h, const lsa_eigs_params& p, const z128* v, z128* w, EventTimer& t_spmv,
+                     EventTimer& t_solve) {
+  const bool adj = p.adjoint != 0;
+  const int n = h.n, blocks = cdiv(n, 256);
+  if (p.transform == LSA_ST_SINVERT) {
+    size_t e = t_spmv.begin();
+    if (h.has_m) spmv(h, adj ? h.dMt : h.dM, adj, v, w);
+    else k_copy<<<blocks, 256, 0, h.stream>>>(n, v, w);
+    t_spmv.end(e);
+    e = t_solve.begin();
+    op_solve(h, adj ? LSA_OP_H : LSA_OP_N, w, p.refine_steps);
+    t_solve.end(e);
+  } else {
+    // shift: OP = M^-1 A - sigma I   (standard problem: A - sigma I)
+    size_t e = t_spmv.begin();
+    spmv(h, adj ? h.dAt : h.dA, adj, v, w);
+    t_spmv.end(e);
+    if (h.has_m) {
+      e = t_solve.begin();
+      op_solve(h, adj ? LSA_OP_H : LSA_OP_N, w, p.refine_steps);
+      t_solve.end(e);
+    }
+    z128 sg = mk(p.sigma_re, p.sigma_im);
+    if (adj) sg = conj_(sg);
+    if (sg.x != 0.0 || sg.y != 0.0) k_axpy<<<blocks, 256, 0, h.stream>>>(n, mk(0, 0) - sg, v, w);
+  }
+  LSA_LAUNCH_CHECK();
+}
+
+void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out) {
+  const int n = h.n;
+  cudaStream_t st = h.stream;
+  const int ncv = std::max(1, std::min(p.ncv, n));
+  const int nev = std::max(1, std::min(p.nev, n));
+  if (ncv > 128) throw std::runtime_error("ncv > 128 is not supported by the orthogonalisation kernels");
+  const int ld = ncv + 1;
+  const int blocks = cdiv(n, 256);
+  z128* V = h.d_V;
+  const long long ldv = n;
+  z128* S = h.d_S;
+  z128* Q = h.d_Q;
+  const int rows_per_block = std::max(1024, (int)(((long long)n + 591) / 592 + 31) / 32 * 32);
+  const int nblk = cdiv(n, rows_per_block);
+  const int ldp = 128;
+  z128 sigma = mk(p.sigma_re, p.sigma_im);
+  if (p.adjoint) sigma = conj_(sigma);
+
+  EventTimer t_all(st), t_spmv(st), t_solve(st), t_ortho(st), t_rr(st), t_restart(st);
+  const size_t e_all = t_all.begin();
+
+  LSA_CUDA(cudaMemsetAsync(S, 0, sizeof(z128) * (size_t)ld * ncv, st));
+  int h_flag = 0x7fffffff;
+  LSA_CUDA(cudaMemcpyAsync(h.d_flag, &h_flag, sizeof(int), cudaMemcpyHostToDevice, st));
+
+  // ---- start vector: random (or caller supplied), pushed through OP once (range of OP; M singular)
+  if (p.v0) {
+    LSA_CUDA(cudaMemcpyAsync(h.d_io, p.v0, sizeof(z128) * (size_t)n, cudaMemcpyHostToDevice, st));
+    permute_gather(st, h.d_io, h.d_x, h.d_perm, n);
+  } else {
+    k_randn<<<blocks, 256, 0, st>>>(h.d_x, n, p.seed);
+  }
+  int n_applies = 0;
+  apply_op(h, p, h.d_x, h.d_w, t_spmv, t_solve);
+  n_applies++;
+  k_norm2_part<<<blocks, 256, 0, st>>>(n, h.d_w, h.d_npart);
+  k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
+  LSA_LAUNCH_CHECK();
+
+  int nconv = 0, keep = 0, restarts = 0, breakdown = 0;
+  RrInfo info{};
+  while (true) {
+    restarts++;
+    int m = ncv;
+    // ---- Arnoldi expansion with CGS2
+    for (int j = keep; j < ncv; ++j) {
+      apply_op(h, p, V + (long long)j * ldv, h.d_w, t_spmv, t_solve);
+      n_applies++;
+      const size_t e = t_ortho.begin();
+      const int jj = j + 1;  // orthogonalise against columns 0..j
+      z128* scol = S + (long long)j * ld;
+      k_dots<<<nblk, 256, 0, st>>>(n, jj, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
+      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 0);
+      k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, nullptr);
+      k_dots<<<nblk, 256, 0, st>>>(n, jj, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
+      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 1);
+      k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart);
+      k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V + (long long)(j + 1) * ldv, h.d_npart, blocks, nullptr,
+                                          scol + j + 1, scol, jj, h.d_flag, j);
+      LSA_LAUNCH_CHECK();
+      t_ortho.end(e);
+    }
+    // ---- breakdown check (one small read-back per restart)
+    LSA_CUDA(cudaMemcpyAsync(&h_flag, h.d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LSA_CUDA(cudaStreamSynchronize(st));
+    if (h_flag < ncv) {
+      m = h_flag + 1;
+      breakdown = 1;
+    }
+    // an exhausted Krylov space (breakdown, or m = n) is an exactly invariant subspace
+    const bool invariant = (h_flag < ncv) || m >= n;
+    const double beta_scale = invariant ? 0.0 : 1.0;
+    // ---- Rayleigh-Ritz
+    RrParams rp{};
+    rp.m = m; rp.ld = ld; rp.ldq = ncv; rp.nconv = nconv; rp.nev = nev; rp.which = p.which;
+    rp.transform = p.transform; rp.tol = p.tol; rp.sigma = sigma; rp.beta_scale = beta_scale;
+    rp.last = (restarts >= p.max_restarts) || m >= n;
+    size_t e = t_rr.begin();
+    k_rr<<<1, 128, 0, st>>>(S, Q, rp, h.d_theta, h.d_resid, h.d_brow, h.d_ywork, h.d_rr);
+    LSA_LAUNCH_CHECK();
+    t_rr.end(e);
+    LSA_CUDA(cudaMemcpyAsync(&info, h.d_rr, sizeof(RrInfo), cudaMemcpyDeviceToHost, st));
+    LSA_CUDA(cudaStreamSynchronize(st));
+    if (info.status != 0) throw std::runtime_error("Rayleigh-Ritz: QR iteration did not converge");
+    const int nconv_old = nconv;
+    nconv = info.nconv;
+    keep = info.keep;
+    // ---- restart: V[:, nconv_old:keep] = V[:, nconv_old:m] Q[nconv_old:m, nconv_old:keep]
+    e = t_restart.begin();
+    const int mp = m - nconv_old, nk = keep - nconv_old;
+    if (nk > 0) {
+      const size_t smem = sizeof(z128) * (size_t)mp * 33;
+      k_basis_gemm<<<cdiv(n, 32), 256, smem, st>>>(n, mp, nk, V + (long long)nconv_old * ldv, ldv,
+                                                   Q + nconv_old + (long long)nconv_old * ncv, ncv,
+                                                   V + (long long)nconv_old * ldv, ldv);
+      LSA_LAUNCH_CHECK();
+    }
+    const bool done = rp.last || nconv >= nev;
+    if (!done && invariant) {
+      // the invariant subspace found so far is locked (keep == m); continue from a fresh random
+      // direction orthogonal to it (SLEPc does the same after a breakdown)
+      z128* vnew = V + (long long)keep * ldv;
+      k_randn<<<blocks, 256, 0, st>>>(h.d_w, n, p.seed + 7919ULL * (unsigned long long)restarts);
+      for (int pass = 0; pass < 2; ++pass) {
+        k_dots<<<nblk, 256, 0, st>>>(n, keep, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
+        k_reduce_h<<<cdiv(keep, 8), 256, 0, st>>>(keep, nblk, h.d_part, ldp, h.d_h, h.d_brow, 0);
+        k_update<<<blocks, 256, 0, st>>>(n, keep, V, ldv, h.d_h, h.d_w, pass ? h.d_npart : nullptr);
+      }
+      k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, vnew, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
+      h_flag = 0x7fffffff;
+      LSA_CUDA(cudaMemcpyAsync(h.d_flag, &h_flag, sizeof(int), cudaMemcpyHostToDevice, st));
+      LSA_LAUNCH_CHECK();
+    } else if (!done && keep != m) {
+      k_copy<<<blocks, 256, 0, st>>>(n, V + (long long)m * ldv, V + (long long)keep * ldv);
+    }
+    t_restart.end(e);
+    if (done) break;
+  }
+
+  // ---- Ritz vectors of the converged block, purification, normalisation, un-permutation
+  h.nconv = nconv;
+  h.eigenvalues.assign(nconv, mk(0, 0));
+  h.eig_order.assign(nconv, 0);
+  if (nconv > 0) {
+    if (nconv > h.X_cols) {
+      if (h.d_X) cudaFree(h.d_X);
+      LSA_CUDA(cudaMalloc(&h.d_X, sizeof(z128) * (size_t)n * nconv));
+      h.X_cols = nconv;
+    }
+    k_ritz_vectors<<<cdiv(nconv, 64), 64, 0, st>>>(S, ld, nconv, Q, ncv);
+    const size_t smem = sizeof(z128) * (size_t)nconv * 33;
+    // Xp (permuted) staged in the tail of the basis is not possible in general -> use d_Xp
+    k_basis_gemm<<<cdiv(n, 32), 256, smem, st>>>(n, nconv, nconv, V, ldv, Q, ncv, h.d_Xp, n);
+    LSA_LAUNCH_CHECK();
+    for (int i = 0; i < nconv; ++i) {
+      z128* xi = h.d_Xp + (long long)i * n;
+      if (p.purify) {
+        apply_op(h, p, xi, h.d_w, t_spmv, t_solve);
+        n_applies++;
+        k_norm2_part<<<blocks, 256, 0, st>>>(n, h.d_w, h.d_npart);
+        k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, xi, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
+      } else {
+        k_norm2_part<<<blocks, 256, 0, st>>>(n, xi, h.d_npart);
+        k_normalize<<<blocks, 256, 0, st>>>(n, xi, xi, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
+      }
+      permute_scatter(st, xi, h.d_X + (long long)i * n, h.d_perm, n);
+    }
+    LSA_LAUNCH_CHECK();
+    std::vector<z128> theta(nconv);
+    LSA_CUDA(cudaMemcpyAsync(theta.data(), h.d_theta, sizeof(z128) * nconv, cudaMemcpyDeviceToHost, st));
+    LSA_CUDA(cudaStreamSynchronize(st));
+    RrParams kp{};
+    kp.which = p.which; kp.transform = p.transform; kp.sigma = sigma;
+    std::vector<double> key(nconv);
+    for (int i = 0; i < nconv; ++i) {
+      h.eigenvalues[i] = rr_back(kp, theta[i]);
+      key[i] = rr_key(kp, theta[i]);
+      h.eig_order[i] = i;
+    }
+    std::stable_sort(h.eig_order.begin(), h.eig_order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::vector<z128> sorted(nconv);
+    for (int i = 0; i < nconv; ++i) sorted[i] = h.eigenvalues[h.eig_order[i]];
+    h.eigenvalues = sorted;
+  }
+  t_all.end(e_all);
+  LSA_CUDA(cudaStreamSynchronize(st));
+  out.nconv = nconv;
+  out.n_restarts = restarts;
+  out.n_op_applies = n_applies;
+  out.breakdown = breakdown;
+  out.seconds = t_all.total_seconds();
+  out.seconds_solve = t_solve.total_seconds();
+  out.seconds_spmv = t_spmv.total_seconds();
+  out.seconds_ortho = t_ortho.total_seconds();
+  out.seconds_rr = t_rr.total_seconds();
+  out.seconds_restart = t_restart.total_seconds();
+  out.n_kernels = 0;
+}
+
+// ||A x - lambda M x|| / (||A||_F ||x||) for every returned pair (original ordering)
+__global__ void __launch_bounds__(256) k_resid_part(int n, const z128* __restrict__ ax, const z128* __restrict__ mx,
+                                                    z128 lam, const z128* __restrict__ x, double* __restrict__ part) {
+  __shared__ double r1[8], r2[8];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double a = 0, b = 0;
+  if (i < n) {
+    a = abs2(ax[i] - lam * mx[i]);
+    b = abs2(x[i]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    r1[threadIdx.x >> 5] = a;
+    r2[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s1 = 0, s2 = 0;
+    for (int q = 0; q < 8; ++q) {
+      s1 += r1[q];
+      s2 += r2[q];
+    }
+    part[2 * blockIdx.x] = s1;
+    part[2 * blockIdx.x + 1] = s2;
+  }
+}
+
+void residual_norms(lsa_handle_impl& h, double* out_host) {
+  const int n = h.n, blocks = cdiv(n, 256);
+  const bool adj = h.last_params.adjoint != 0;
+  std::vector<double> part(2 * (size_t)blocks);
+  double* d_part = nullptr;
+  LSA_CUDA(cudaMalloc(&d_part, sizeof(double) * 2 * blocks));
+  for (int i = 0; i < h.nconv; ++i) {
+    const int col = h.eig_order[i];
+    // work in the permuted ordering: x_p = gather(x)
+    permute_gather(h.stream, h.d_X + (long long)col * n, h.d_x, h.d_perm, n);
+    spmv(h, adj ? h.dAt : h.dA, adj, h.d_x, h.d_w);
+    if (h.has_m) spmv(h, adj ? h.dMt : h.dM, adj, h.d_x, h.d_r1);
+    else k_copy<<<blocks, 256, 0, h.stream>>>(n, h.d_x, h.d_r1);
+    k_resid_part<<<blocks, 256, 0, h.stream>>>(n, h.d_w, h.d_r1, h.eigenvalues[i], h.d_x, d_part);
+    LSA_LAUNCH_CHECK();
+    LSA_CUDA(cudaMemcpyAsync(part.data(), d_part, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, h.stream));
+    LSA_CUDA(cudaStreamSynchronize(h.stream));
+    double s1 = 0, s2 = 0;
+    for (int b = 0; b < blocks; ++b) {
+      s1 += part[2 * b];
+      s2 += part[2 * b + 1];
+    }
+    out_host[i] = std::sqrt(s1) / (std::max(h.a_fro, 1e-300) * std::sqrt(std::max(s2, 1e-300)));
+  }
+  cudaFree(d_part);
+}
+
+}  // namespace lsa

@@ -1,0 +1,72 @@
+// Internal data structures shared by the host symbolic phase and the CUDA numeric phase.
+//
+// Path covered: the work SLEPc/PETSc/MUMPS do behind `iEpsSolver.solve()`
+// (reference Solver/utils.py:268-270): sparse LU of A - sigma M, triangular solves, SpMV with M,
+// Krylov-Schur.  Nothing here is derived from those libraries' sources (they are not vendored in
+// the reference); the design is a static-structure multifrontal method laid out for one B200.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace lsa {
+
+// One frontal matrix of the multifrontal LU.  A front with k pivots and r remaining rows is
+// stored as three dense column-major pieces:
+//   P  (k+r) x k   [F11; F21]  -> after factorisation L11\U11 on top, L21 below   (factor store)
+//   Q   k    x r    F12        -> after factorisation U12                          (factor store)
+//   C   r    x r    F22        -> Schur complement / contribution block            (level pool)
+struct Front {
+  long long p_off;  // element offset of P in the factor store
+  long long q_off;  // element offset of Q in the factor store
+  long long c_off;  // element offset of C in the contribution pool of parity (level & 1)
+  long long st0;    // offset of this front's row structure in st_idx / ea_map / cb vector
+  int k;            // number of pivots (fully summed variables)
+  int r;            // number of remaining (not fully summed) rows
+  int col0;         // first permuted column index
+  int parent;       // parent front (-1: root)
+  int level;        // depth in the assembly tree (roots are level 0)
+  int child0;       // first entry in child_idx
+  int nchild;       // number of children
+  int pad;
+};
+
+struct Symbolic {
+  int n = 0;        // matrix order
+  int n_iso = 0;    // decoupled 1x1 pivots (e.g. Dirichlet identity rows); permuted first
+  int ns = 0;       // number of fronts (supernodes)
+  int nlevels = 0;
+  std::vector<int> perm;    // perm[new] = old
+  std::vector<int> iperm;   // iperm[old] = new
+  std::vector<int> sn_ptr;  // ns+1 permuted column ranges; sn_ptr[0] == n_iso
+  std::vector<int> sn_of;   // n: front owning a permuted column (-1 for decoupled pivots)
+  std::vector<long long> st_ptr;  // ns+1
+  std::vector<int> st_idx;        // sorted permuted row indices below each front's pivot block
+  std::vector<int> ea_map;        // same indexing as st_idx: local row index in the parent front
+  std::vector<int> child_idx;     // children of each front, ascending
+  std::vector<int> lvl_ptr;       // nlevels+1
+  std::vector<int> lvl_front;     // fronts of each level sorted by descending k
+  std::vector<Front> fronts;
+  std::vector<long long> a_dst;   // per entry of the input CSR pattern: destination in the factor store
+  long long fac_size = 0;         // elements in the factor store (P and Q of all fronts + decoupled pivots)
+  long long diag_off = 0;         // offset of the decoupled pivots in the factor store
+  long long pool_size[2] = {0, 0};
+  long long nnz_lu = 0;           // sum k^2 + 2 k r + n_iso (algorithmic factor entries)
+  double flops = 0.0;             // sum 2/3 k^3 + 2 k^2 r + 2 k r^2 (real-arithmetic flops for T = double)
+  int max_k = 0, max_m = 0, max_r = 0;
+  double seconds[4] = {0, 0, 0, 0};  // graph, ordering, structure, maps
+};
+
+struct AnalyzeOptions {
+  int leaf_size = 64;
+  int dim = 0;                   // >0: geometric bisection with `coords` (n x dim, row-major)
+  const double* coords = nullptr;
+  const unsigned char* order_last = nullptr;  // n flags: order this unknown last inside its front
+  int nthreads = 0;
+};
+
+// Host symbolic phase: nested dissection, supernode partition, row structures, assembly tree,
+// scatter maps.  `rowptr`/`colidx`: CSR pattern of A (union with M), n rows.
+void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOptions& opt, Symbolic& sym);
+
+}  // namespace lsa

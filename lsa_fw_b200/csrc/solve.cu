@@ -1,0 +1,534 @@
+// Supernodal forward / backward triangular solves on the multifrontal factors, incl. the
+// conjugate-transposed solve used for adjoint modes.
+//
+// Stands in for PETSc's MatSolve / MatSolveTranspose behind `KSP preonly + PC lu`, executed once per
+// Krylov step by SLEPc's STApply (reference call site Solver/utils.py:268-270; explicit in
+// Solver/eigen2.py:174-178).  The adjoint eigensolve of Sensitivity/__init__.py:246-262 re-factors
+// (A^H - conj(sigma) M^H); here it is the `trans = H` sweep over the SAME factors.
+//
+// Every kernel is HBM bound: one pass over L (forward) and one over U (backward), i.e.
+// nnz(L+U) * sizeof(T) bytes per solve plus the index vectors.  Launches are batched per assembly
+// tree level; within a front the pivot block is processed in 256-wide steps whose 32 x 32 diagonal
+// blocks were inverted after the factorisation, so a step is a short chain of small GEMVs instead
+// of a scalar substitution.
+//
+//   trans = N :  up sweep   y_top = L11^-1 P x_top ;  contrib  -= L21 y_top
+//                down sweep y_top = U11^-1 (y_top - U12 y_anc)
+//   trans = H :  up sweep   y_top = U11^-H x_top   ;  contrib  -= U12^H y_top
+//                down sweep y_top = L11^-H (y_top - L21^H y_anc) ; x = P^T y
+#include "factor.cuh"
+
+namespace lsa {
+
+static constexpr int SB = 256;  // pivot-block step of the solve kernels
+static constexpr int IB = 32;   // inverted diagonal block order (= factorisation panel width)
+
+// ------------------------------------------------------------------------------- post-factor set-up
+
+// Composes the row interchanges of every front into one gather permutation:
+// (P x)[col0 + i] = x[gperm[col0 + i]].
+__global__ void k_compose_perm(const Front* __restrict__ fronts, int ns, const int* __restrict__ ipiv,
+                               int* __restrict__ gperm) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns) return;
+  const Front f = fronts[s];
+  int* g = gperm + f.col0;
+  for (int j = 0; j < f.k; ++j) g[j] = f.col0 + j;
+  for (int j = 0; j < f.k; ++j) {
+    const int p = ipiv[f.col0 + j];
+    if (p != j) {
+      const int a = g[j];
+      g[j] = g[p];
+      g[p] = a;
+    }
+  }
+}
+
+__global__ void k_iota(int* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+// Inverts the 32 x 32 diagonal blocks of L11 (unit lower) and U11 (upper) in place.
+// grid: (diagonal blocks, fronts); block: 32 threads, thread c computes column c of both inverses.
+template <class T>
+__global__ void __launch_bounds__(32) k_invert_diag(const Front* __restrict__ fronts, int first, T* __restrict__ fac) {
+  const Front f = fronts[first + blockIdx.y];
+  const int j0 = blockIdx.x * IB;
+  if (j0 >= f.k) return;
+  const int nb = min(IB, f.k - j0);
+  const long long m = (long long)f.k + f.r;
+  T* D = fac + f.p_off + j0 + (long long)j0 * m;
+  __shared__ T s_a[IB][IB + 1];  // original block
+  __shared__ T s_x[IB][IB + 1];  // s_x[c][i]: column c of an inverse
+  const int c = threadIdx.x;
+  for (int j = 0; j < nb; ++j)
+    if (c < nb) s_a[c][j] = D[c + (long long)j * m];  // s_a[row][col]
+  __syncwarp();
+  if (c < nb) {
+    // unit lower inverse, column c
+    for (int i = c + 1; i < nb; ++i) {
+      T acc = s_a[i][c];
+      for (int s = c + 1; s < i; ++s) acc = acc + s_a[i][s] * s_x[c][s];
+      s_x[c][i] = scalar_traits<T>::zero() - acc;
+    }
+  }
+  __syncwarp();
+  for (int j = 0; j < nb; ++j)
+    if (c < nb && c > j) D[c + (long long)j * m] = s_x[j][c];
+  __syncwarp();
+  if (c < nb) {
+    // upper inverse, column c
+    s_x[c][c] = recip(s_a[c][c]);
+    for (int i = c - 1; i >= 0; --i) {
+      T acc = scalar_traits<T>::zero();
+      for (int s = i + 1; s <= c; ++s) acc = acc + s_a[i][s] * s_x[c][s];
+      s_x[c][i] = scalar_traits<T>::zero() - acc * recip(s_a[i][i]);
+    }
+  }
+  __syncwarp();
+  for (int j = 0; j < nb; ++j)
+    if (c < nb && c <= j) D[c + (long long)j * m] = s_x[j][c];
+}
+
+template <class T>
+void post_factor(lsa_handle_impl& h, int* n_kernels) {
+  const Symbolic& sym = h.sym;
+  cudaStream_t st = h.stream;
+  if (h.n > 0) k_iota<<<cdiv(h.n, 256), 256, 0, st>>>(h.d_gperm, h.n);
+  LSA_LAUNCH_CHECK();
+  if (sym.ns > 0) {
+    k_compose_perm<<<cdiv(sym.ns, 64), 64, 0, st>>>(h.d_fronts, sym.ns, h.d_ipiv, h.d_gperm);
+    LSA_LAUNCH_CHECK();
+    for (int s0 = 0; s0 < sym.ns; s0 += 32768) {
+      const int cnt = std::min(32768, sym.ns - s0);
+      int maxk = 0;
+      for (int s = s0; s < s0 + cnt; ++s) maxk = std::max(maxk, sym.fronts[s].k);
+      k_invert_diag<T><<<dim3(cdiv(maxk, IB), cnt), 32, 0, st>>>(h.d_fronts, s0, (T*)h.d_fac);
+      LSA_LAUNCH_CHECK();
+      if (n_kernels) (*n_kernels)++;
+    }
+  }
+  if (n_kernels) (*n_kernels) += 2;
+}
+template void post_factor<double>(lsa_handle_impl&, int*);
+template void post_factor<z128>(lsa_handle_impl&, int*);
+
+// --------------------------------------------------------------------------------- decoupled pivots
+
+template <class T, bool H>
+__global__ void k_solve_decoupled(const T* __restrict__ diag, int n_iso, const z128* __restrict__ x, z128* __restrict__ y) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_iso) y[i] = recip(cj<H>(diag[i])) * x[i];
+}
+
+// ----------------------------------------------------------------------------------------- up sweep
+
+// One CTA per front: collect the children's contribution vectors, then move the pivot rows into
+// the work vector y (with the front's row permutation when PERM).
+template <bool PERM>
+__global__ void __launch_bounds__(256) k_up_gather(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, const int* __restrict__ child_idx,
+                                                   const int* __restrict__ ea_map, const int* __restrict__ gperm,
+                                                   z128* __restrict__ x, z128* __restrict__ y, z128* __restrict__ cb) {
+  const Front p = fronts[lvl_front[first + blockIdx.x]];
+  z128* cbp = cb + p.st0;
+  for (int t = threadIdx.x; t < p.r; t += blockDim.x) cbp[t] = mk(0, 0);
+  __syncthreads();
+  for (int q = 0; q < p.nchild; ++q) {
+    const Front c = fronts[child_idx[p.child0 + q]];
+    const int* map = ea_map + c.st0;
+    const z128* cbc = cb + c.st0;
+    for (int t = threadIdx.x; t < c.r; t += blockDim.x) {
+      const int ip = map[t];
+      const z128 v = cbc[t];
+      if (ip < p.k) x[p.col0 + ip] += v;
+      else cbp[ip - p.k] += v;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < p.k; i += blockDim.x) y[p.col0 + i] = x[PERM ? gperm[p.col0 + i] : p.col0 + i];
+}
+
+// Element (i, c) of the lower-triangular operator of the up sweep, i > c (or the inverted diagonal
+// block when both lie in the same 32-block):  N: L[i, c] = P[i + c m] ;  H: conj(U[c, i]) = conj(P[c + i m]).
+template <class T, bool H>
+__device__ __forceinline__ T up_elem(const T* __restrict__ P, long long m, int i, int c) {
+  return H ? conj_(P[c + (long long)i * m]) : P[i + (long long)c * m];
+}
+
+// One CTA (256 threads) per front: solve the pivot block rows [j0, j1) of the up sweep.
+template <class T, bool H>
+__global__ void __launch_bounds__(256) k_up_diag(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                 int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
+  const Front f = fronts[lvl_front[first + blockIdx.x]];
+  const int k = f.k;
+  if (k <= j0) return;
+  const int j1 = min(k, j0 + SB), len = j1 - j0;
+  const long long m = (long long)k + f.r;
+  const T* P = fac + f.p_off;
+  __shared__ z128 ys[SB];
+  __shared__ z128 yb[IB];
+  const int tid = threadIdx.x;
+  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
+  __syncthreads();
+  for (int b0 = 0; b0 < len; b0 += IB) {
+    const int nb = min(IB, len - b0);
+    // (i) block GEMV with the inverted diagonal block: 8 threads per row
+    {
+      const int i = tid >> 3, part = tid & 7;
+      z128 acc = mk(0, 0);
+      if (i < nb) {
+        for (int c = part; c <= i; c += 8) {
+          if (c == i) {
+            if (H) acc += up_elem<T, H>(P, m, j0 + b0 + i, j0 + b0 + c) * ys[b0 + c];
+            else acc += ys[b0 + c];  // unit diagonal of L^-1
+          } else {
+            acc += up_elem<T, H>(P, m, j0 + b0 + i, j0 + b0 + c) * ys[b0 + c];
+          }
+        }
+      }
+      for (int o = 4; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      }
+      if (i < nb && part == 0) yb[i] = acc;
+    }
+    __syncthreads();
+    if (tid < nb) ys[b0 + tid] = yb[tid];
+    // (ii) update the remaining rows of this step
+    const int i = b0 + IB + tid;
+    if (i < len) {
+      z128 acc = ys[i];
+      for (int c = 0; c < nb; ++c) acc -= up_elem<T, H>(P, m, j0 + i, j0 + b0 + c) * yb[c];
+      ys[i] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid < len) y[f.col0 + j0 + tid] = ys[tid];
+}
+
+// Rows below the step: remaining pivot rows (-> y) and contribution rows (-> cb).
+// grid: (row chunks of 64, fronts); block 256.
+template <class T, bool H>
+__global__ void __launch_bounds__(256) k_up_update(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, int j0, const T* __restrict__ fac, z128* __restrict__ y,
+                                                   z128* __restrict__ cb) {
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k;
+  if (k <= j0) return;
+  const int j1 = min(k, j0 + SB), len = j1 - j0;
+  const long long m = (long long)k + f.r;
+  const int nrows = (int)(m - j1);
+  const int r0 = blockIdx.x * 64;
+  if (r0 >= nrows) return;
+  const T* P = fac + f.p_off;
+  const T* Q = fac + f.q_off;
+  __shared__ z128 ys[SB];
+  __shared__ z128 red[4][64];
+  const int tid = threadIdx.x;
+  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
+  __syncthreads();
+  if (!H) {
+    // axpy type: thread (row, column group), rows contiguous in memory
+    const int rr = tid & 63, cg = tid >> 6;
+    const int row = j1 + r0 + rr;  // local front row
+    z128 acc = mk(0, 0);
+    if (r0 + rr < nrows) {
+      const T* a = P + row + (long long)j0 * m;
+#pragma unroll 4
+      for (int c = cg; c < len; c += 4) acc += a[(long long)c * m] * ys[c];
+    }
+    red[cg][rr] = acc;
+    __syncthreads();
+    if (tid < 64 && r0 + tid < nrows) {
+      const z128 s = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+      const int rw = j1 + r0 + tid;
+      if (rw < k) y[f.col0 + rw] -= s;
+      else cb[f.st0 + (rw - k)] -= s;
+    }
+  } else {
+    // dot type: warp per row, lanes along the contiguous column of U
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int rr = wid; rr < 64; rr += 8) {
+      if (r0 + rr >= nrows) break;
+      const int row = j1 + r0 + rr;
+      const T* u = row < k ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
+      z128 acc = mk(0, 0);
+      for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * ys[c];
+      for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      }
+      if (lane == 0) {
+        if (row < k) y[f.col0 + row] -= acc;
+        else cb[f.st0 + (row - k)] -= acc;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------- down sweep
+
+// y_top -= Off * y[ancestor rows].  N: Off = U12 = Q (k x r);  H: Off = L21^H, L21 = P[k:m, 0:k].
+// grid: (pivot-row chunks of 64, fronts); block 256.
+template <class T, bool H>
+__global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                  int first, const int* __restrict__ st_idx, const T* __restrict__ fac,
+                                                  z128* __restrict__ y) {
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k, r = f.r;
+  const int r0 = blockIdx.x * 64;
+  if (r0 >= k || r == 0) return;
+  const long long m = (long long)k + r;
+  const T* P = fac + f.p_off;
+  const T* Q = fac + f.q_off;
+  const int* idx = st_idx + f.st0;
+  __shared__ z128 xs[SB];
+  __shared__ z128 red[4][64];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int rr = tid & 63, cg = tid >> 6;
+  z128 acc = mk(0, 0);       // axpy type accumulator (N)
+  z128 accw[8];              // dot type accumulators (H): rows wid, wid+8, ...
+#pragma unroll
+  for (int q = 0; q < 8; ++q) accw[q] = mk(0, 0);
+  for (int c0 = 0; c0 < r; c0 += SB) {
+    const int len = min(SB, r - c0);
+    __syncthreads();
+    if (tid < len) xs[tid] = y[idx[c0 + tid]];
+    __syncthreads();
+    if (!H) {
+      if (r0 + rr < k) {
+        const T* a = Q + (r0 + rr) + (long long)c0 * k;
+#pragma unroll 4
+        for (int c = cg; c < len; c += 4) acc += a[(long long)c * k] * xs[c];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int row = r0 + wid + q * 8;
+        if (row < k) {
+          const T* l = P + k + c0 + (long long)row * m;
+          for (int c = lane; c < len; c += 32) accw[q] += conj_(l[c]) * xs[c];
+        }
+      }
+    }
+  }
+  if (!H) {
+    red[cg][rr] = acc;
+    __syncthreads();
+    if (tid < 64 && r0 + tid < k) y[f.col0 + r0 + tid] -= red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      z128 a = accw[q];
+      for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      }
+      const int row = r0 + wid + q * 8;
+      if (lane == 0 && row < k) y[f.col0 + row] -= a;
+    }
+  }
+}
+
+// Element (i, c), i < c, of the upper-triangular operator of the down sweep (or the inverted
+// diagonal block):  N: U[i, c] = P[i + c m] ;  H: conj(L[c, i]) = conj(P[c + i m]).
+template <class T, bool H>
+__device__ __forceinline__ T down_elem(const T* __restrict__ P, long long m, int i, int c) {
+  return H ? conj_(P[c + (long long)i * m]) : P[i + (long long)c * m];
+}
+
+template <class T, bool H>
+__global__ void __launch_bounds__(256) k_down_diag(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
+  const Front f = fronts[lvl_front[first + blockIdx.x]];
+  const int k = f.k;
+  if (k <= j0) return;
+  const int j1 = min(k, j0 + SB), len = j1 - j0;
+  const long long m = (long long)k + f.r;
+  const T* P = fac + f.p_off;
+  __shared__ z128 ys[SB];
+  __shared__ z128 yb[IB];
+  const int tid = threadIdx.x;
+  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
+  __syncthreads();
+  const int nblk = (len + IB - 1) / IB;
+  for (int bi = nblk - 1; bi >= 0; --bi) {
+    const int b0 = bi * IB, nb = min(IB, len - b0);
+    {
+      const int i = tid >> 3, part = tid & 7;
+      z128 acc = mk(0, 0);
+      if (i < nb) {
+        for (int c = i + part; c < nb; c += 8) {
+          if (c == i) {
+            if (H) acc += ys[b0 + c];  // unit diagonal of L^-H
+            else acc += down_elem<T, H>(P, m, j0 + b0 + i, j0 + b0 + c) * ys[b0 + c];
+          } else {
+            acc += down_elem<T, H>(P, m, j0 + b0 + i, j0 + b0 + c) * ys[b0 + c];
+          }
+        }
+      }
+      for (int o = 4; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      }
+      if (i < nb && part == 0) yb[i] = acc;
+    }
+    __syncthreads();
+    if (tid < nb) ys[b0 + tid] = yb[tid];
+    const int i = tid;
+    if (i < b0) {
+      z128 acc = ys[i];
+      for (int c = 0; c < nb; ++c) acc -= down_elem<T, H>(P, m, j0 + i, j0 + b0 + c) * yb[c];
+      ys[i] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid < len) y[f.col0 + j0 + tid] = ys[tid];
+}
+
+// Pivot rows above the step: y[0:j0] -= Upper[0:j0, j0:j1] y[j0:j1].  grid: (row chunks of 64, fronts).
+template <class T, bool H>
+__global__ void __launch_bounds__(256) k_down_update(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                     int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k;
+  if (k <= j0 || j0 == 0) return;
+  const int r0 = blockIdx.x * 64;
+  if (r0 >= j0) return;
+  const int j1 = min(k, j0 + SB), len = j1 - j0;
+  const long long m = (long long)k + f.r;
+  const T* P = fac + f.p_off;
+  __shared__ z128 ys[SB];
+  __shared__ z128 red[4][64];
+  const int tid = threadIdx.x;
+  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
+  __syncthreads();
+  if (!H) {
+    const int rr = tid & 63, cg = tid >> 6;
+    z128 acc = mk(0, 0);
+    if (r0 + rr < j0) {
+      const T* a = P + (r0 + rr) + (long long)j0 * m;
+#pragma unroll 4
+      for (int c = cg; c < len; c += 4) acc += a[(long long)c * m] * ys[c];
+    }
+    red[cg][rr] = acc;
+    __syncthreads();
+    if (tid < 64 && r0 + tid < j0) y[f.col0 + r0 + tid] -= red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+  } else {
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int rr = wid; rr < 64; rr += 8) {
+      const int row = r0 + rr;
+      if (row >= j0) break;
+      const T* l = P + j0 + (long long)row * m;
+      z128 acc = mk(0, 0);
+      for (int c = lane; c < len; c += 32) acc += conj_(l[c]) * ys[c];
+      for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      }
+      if (lane == 0) y[f.col0 + row] -= acc;
+    }
+  }
+}
+
+__global__ void k_unpermute(const z128* __restrict__ y, z128* __restrict__ x, const int* __restrict__ gperm, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[gperm[i]] = y[i];
+}
+
+// ------------------------------------------------------------------------------------------- driver
+
+template <class T, bool H>
+static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
+  const Symbolic& sym = h.sym;
+  cudaStream_t st = h.stream;
+  const T* fac = (const T*)h.d_fac;
+  z128* y = h.d_t;
+  z128* cb = h.d_cb;
+  int launches = 0;
+  constexpr int YMAX = 32768;
+  if (sym.n_iso > 0) {
+    k_solve_decoupled<T, H><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, x, y);
+    LSA_LAUNCH_CHECK();
+    launches++;
+  }
+  // ---- up sweep: deepest level first
+  for (int d = sym.nlevels - 1; d >= 0; --d) {
+    const int lbeg = sym.lvl_ptr[d], cnt_all = sym.lvl_ptr[d + 1] - lbeg;
+    for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
+      const int cnt = std::min(YMAX, cnt_all - y0), first = lbeg + y0;
+      k_up_gather<!H><<<cnt, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+      LSA_LAUNCH_CHECK();
+      launches++;
+      const int maxk = sym.fronts[sym.lvl_front[first]].k;
+      for (int j0 = 0; j0 < maxk; j0 += SB) {
+        int act = 0, max_rows = 0;
+        for (int q = first; q < first + cnt; ++q) {
+          const Front& f = sym.fronts[sym.lvl_front[q]];
+          if (f.k <= j0) break;
+          act++;
+          max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
+        }
+        k_up_diag<T, H><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+        LSA_LAUNCH_CHECK();
+        launches++;
+        if (max_rows > 0) {
+          k_up_update<T, H><<<dim3(cdiv(max_rows, 64), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, cb);
+          LSA_LAUNCH_CHECK();
+          launches++;
+        }
+      }
+    }
+  }
+  // ---- down sweep: roots first
+  for (int d = 0; d < sym.nlevels; ++d) {
+    const int lbeg = sym.lvl_ptr[d], cnt_all = sym.lvl_ptr[d + 1] - lbeg;
+    for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
+      const int cnt = std::min(YMAX, cnt_all - y0), first = lbeg + y0;
+      const int maxk = sym.fronts[sym.lvl_front[first]].k;
+      int maxr = 0;
+      for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[sym.lvl_front[q]].r);
+      if (maxr > 0) {
+        k_down_off<T, H><<<dim3(cdiv(maxk, 64), cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, y);
+        LSA_LAUNCH_CHECK();
+        launches++;
+      }
+      for (int j0 = ((maxk - 1) / SB) * SB; j0 >= 0; j0 -= SB) {
+        int act = 0;
+        for (int q = first; q < first + cnt; ++q) {
+          if (sym.fronts[sym.lvl_front[q]].k <= j0) break;
+          act++;
+        }
+        if (act == 0) continue;
+        k_down_diag<T, H><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+        LSA_LAUNCH_CHECK();
+        launches++;
+        if (j0 > 0) {
+          k_down_update<T, H><<<dim3(cdiv(j0, 64), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+          LSA_LAUNCH_CHECK();
+          launches++;
+        }
+      }
+    }
+  }
+  if (H) {
+    k_unpermute<<<cdiv(h.n, 256), 256, 0, st>>>(y, x, h.d_gperm, h.n);
+    LSA_LAUNCH_CHECK();
+  } else {
+    LSA_CUDA(cudaMemcpyAsync(x, y, (size_t)h.n * sizeof(z128), cudaMemcpyDeviceToDevice, st));
+  }
+  launches++;
+  if (n_kernels) *n_kernels += launches;
+}
+
+template <class T>
+void solve_permuted(lsa_handle_impl& h, int trans, z128* x, int* n_kernels) {
+  if (trans == LSA_OP_H) solve_impl<T, true>(h, x, n_kernels);
+  else solve_impl<T, false>(h, x, n_kernels);
+}
+template void solve_permuted<double>(lsa_handle_impl&, int, z128*, int*);
+template void solve_permuted<z128>(lsa_handle_impl&, int, z128*, int*);
+
+}  // namespace lsa
