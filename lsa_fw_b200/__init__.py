@@ -1,0 +1,12 @@
+"""lsa_fw_b200 -- B200-native shift-and-invert eigensolve backend with the API of LSA-FW's Solver/eigen.py."""
+
+from .carriers import iComplexPETScVector, iPETScMatrix, iPETScVector
+from .eigen import EigenSolver, EigensolverConfig
+from .utils import (LsaError, PreconditionerType, clear_symbolic_cache, iEpsProblemType, iEpsSolver, iEpsWhich,
+                    iSTType)
+
+__all__ = [
+    "EigenSolver", "EigensolverConfig", "iEpsSolver", "iEpsProblemType", "iEpsWhich", "iSTType",
+    "PreconditionerType", "iPETScMatrix", "iPETScVector", "iComplexPETScVector", "LsaError",
+    "clear_symbolic_cache",
+]

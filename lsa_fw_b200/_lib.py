@@ -1,0 +1,285 @@
+"""ctypes binding of liblsa_b200.so (the C ABI declared in include/lsa_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing it is built in-tree
+(nvcc cross-compiles without a GPU); if it cannot be built or no CUDA device is present, every
+numeric entry point raises `LsaError`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "liblsa_b200.so"
+
+LSA_F64, LSA_C128 = 0, 1
+LSA_OP_N, LSA_OP_T, LSA_OP_H = 0, 1, 2
+LSA_MAT_A, LSA_MAT_M = 0, 1
+LSA_ST_SHIFT, LSA_ST_SINVERT = 0, 1
+WHICH = {
+    "LARGEST_MAGNITUDE": 1, "SMALLEST_MAGNITUDE": 2, "LARGEST_REAL": 3, "SMALLEST_REAL": 4,
+    "LARGEST_IMAGINARY": 5, "SMALLEST_IMAGINARY": 6, "TARGET_MAGNITUDE": 7, "TARGET_REAL": 8,
+    "TARGET_IMAGINARY": 9,
+}
+STATUS = {0: "OK", -1: "ARG", -2: "CUDA", -3: "ZERO_PIVOT", -4: "NONFINITE", -5: "INTERNAL"}
+
+
+class LsaError(RuntimeError):
+    """Failure reported by the CUDA backend (stands where the reference raises PETSc.Error)."""
+
+    def __init__(self, status: int, message: str) -> None:
+        super().__init__(f"lsa_b200 status {STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+class SymbolicInfo(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("n_decoupled", C.c_int32), ("n_fronts", C.c_int32), ("n_levels", C.c_int32),
+        ("max_pivots", C.c_int32), ("max_front", C.c_int32), ("max_rows", C.c_int32), ("pad", C.c_int32),
+        ("nnz_a", C.c_int64), ("nnz_m", C.c_int64), ("factor_entries", C.c_int64), ("nnz_lu", C.c_int64),
+        ("pool_entries", C.c_int64 * 2), ("struct_entries", C.c_int64), ("flops_real", C.c_double),
+        ("seconds", C.c_double * 4),
+    ]
+
+
+class FactorStats(C.Structure):
+    _fields_ = [
+        ("seconds", C.c_double), ("flops", C.c_double), ("n_perturbed", C.c_int64), ("n_row_swaps", C.c_int64),
+        ("scalar", C.c_int32), ("n_kernels", C.c_int32), ("min_pivot", C.c_double), ("max_pivot", C.c_double),
+    ]
+
+
+class EigsParams(C.Structure):
+    _fields_ = [
+        ("nev", C.c_int32), ("ncv", C.c_int32), ("max_restarts", C.c_int32), ("which", C.c_int32),
+        ("transform", C.c_int32), ("adjoint", C.c_int32), ("purify", C.c_int32), ("refine_steps", C.c_int32),
+        ("tol", C.c_double), ("sigma_re", C.c_double), ("sigma_im", C.c_double), ("seed", C.c_uint64),
+        ("v0", C.POINTER(C.c_double)),
+    ]
+
+
+class EigsResult(C.Structure):
+    _fields_ = [
+        ("nconv", C.c_int32), ("n_restarts", C.c_int32), ("n_op_applies", C.c_int32), ("breakdown", C.c_int32),
+        ("seconds", C.c_double), ("seconds_solve", C.c_double), ("seconds_spmv", C.c_double),
+        ("seconds_ortho", C.c_double), ("seconds_rr", C.c_double), ("seconds_restart", C.c_double),
+        ("n_kernels", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("bytes_solve", C.c_double), ("bytes_spmv_m", C.c_double), ("bytes_spmv_a", C.c_double),
+        ("factor_flops", C.c_double), ("factor_seconds", C.c_double), ("solve_seconds", C.c_double),
+        ("spmv_seconds", C.c_double), ("n_solves", C.c_int64), ("n_spmv", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load (building in-tree when necessary) the shared library and declare its prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        if not build_if_missing:
+            raise LsaError(-2, f"{_LIB_PATH} is missing and there is no CPU fallback")
+        from . import build as _build
+
+        _build.build()
+    lib = C.CDLL(str(_LIB_PATH))
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pd = C.POINTER(C.c_double)
+    lib.lsa_version.restype = C.c_char_p
+    lib.lsa_create.argtypes = [i32, i32, C.POINTER(vp)]
+    lib.lsa_destroy.argtypes = [vp]
+    lib.lsa_destroy.restype = None
+    lib.lsa_last_error.argtypes = [vp]
+    lib.lsa_last_error.restype = C.c_char_p
+    lib.lsa_analyze.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32]
+    lib.lsa_symbolic_info_get.argtypes = [vp, C.POINTER(SymbolicInfo)]
+    lib.lsa_symbolic_array.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.lsa_symbolic_array.restype = i64
+    lib.lsa_set_values.argtypes = [vp, vp, i32, vp, i32, i32]
+    lib.lsa_factor.argtypes = [vp, dbl, dbl, dbl, dbl, i32, dbl, C.POINTER(FactorStats)]
+    lib.lsa_solve.argtypes = [vp, i32, vp, vp, i32, i32]
+    lib.lsa_spmv.argtypes = [vp, i32, i32, vp, vp, i32]
+    lib.lsa_eigs.argtypes = [vp, C.POINTER(EigsParams), C.POINTER(EigsResult)]
+    lib.lsa_get_eigenvalues.argtypes = [vp, vp, i32]
+    lib.lsa_get_eigenvectors.argtypes = [vp, vp, i64, i32, i32]
+    lib.lsa_get_residuals.argtypes = [vp, vp, i32]
+    lib.lsa_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    lib.lsa_sync.argtypes = [vp]
+    lib.lsa_dense_schur.argtypes = [vp, i32, vp, i32, vp, i32, i32, dbl, dbl]
+    lib.lsa_gemm_bench.argtypes = [vp, i32, i32, i32, i32, i32, pd, pd]
+    _lib = lib
+    return lib
+
+
+EXPORTS = [
+    "lsa_version", "lsa_create", "lsa_destroy", "lsa_last_error", "lsa_analyze", "lsa_symbolic_info_get",
+    "lsa_symbolic_array", "lsa_set_values", "lsa_factor", "lsa_solve", "lsa_spmv", "lsa_eigs",
+    "lsa_get_eigenvalues", "lsa_get_eigenvectors", "lsa_get_residuals", "lsa_get_counters", "lsa_sync",
+    "lsa_dense_schur", "lsa_gemm_bench",
+]
+
+_ARRAY_DTYPES = {
+    "perm": np.int32, "iperm": np.int32, "sn_ptr": np.int32, "st_ptr": np.int64, "st_idx": np.int32,
+    "ea_map": np.int32, "lvl_ptr": np.int32, "lvl_front": np.int32, "a_dst": np.int64, "m_dst": np.int64,
+    "parent": np.int32, "level": np.int32, "front_k": np.int32, "front_r": np.int32, "p_off": np.int64,
+    "q_off": np.int64, "c_off": np.int64,
+}
+
+
+class Handle:
+    """Thin RAII wrapper over `lsa_handle*` (one solver object = one handle = one CUDA stream)."""
+
+    def __init__(self, n: int, device: int = 0) -> None:
+        self.lib = load()
+        self.n = int(n)
+        self.device = device
+        self._h = C.c_void_p()
+        rc = self.lib.lsa_create(self.n, device, C.byref(self._h))
+        if rc != 0:
+            raise LsaError(rc, "cannot create a handle on CUDA device %d (no GPU? there is no CPU fallback)" % device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.lsa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self) -> None:  # pragma: no cover - interpreter shutdown order
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int) -> int:
+        if rc < 0:
+            raise LsaError(rc, self.lib.lsa_last_error(self._h).decode(errors="replace"))
+        return rc
+
+    # -- symbolic
+    def analyze(self, a_rowptr, a_colidx, m_rowptr=None, m_colidx=None, *, leaf_size=64, coords=None,
+                order_last=None, nthreads=0) -> SymbolicInfo:
+        a_rowptr = np.ascontiguousarray(a_rowptr, dtype=np.int64)
+        a_colidx = np.ascontiguousarray(a_colidx, dtype=np.int32)
+        mr = mc = None
+        if m_rowptr is not None:
+            mr = np.ascontiguousarray(m_rowptr, dtype=np.int64)
+            mc = np.ascontiguousarray(m_colidx, dtype=np.int32)
+        dim = 0
+        cptr = None
+        if coords is not None:
+            coords = np.ascontiguousarray(coords, dtype=np.float64)
+            dim = coords.shape[1]
+            cptr = coords.ctypes.data
+        optr = None
+        if order_last is not None:
+            order_last = np.ascontiguousarray(order_last, dtype=np.uint8)
+            optr = order_last.ctypes.data
+        self.check(self.lib.lsa_analyze(
+            self._h, a_rowptr.ctypes.data, a_colidx.ctypes.data,
+            mr.ctypes.data if mr is not None else None, mc.ctypes.data if mc is not None else None,
+            leaf_size, dim, cptr, optr, nthreads))
+        return self.symbolic_info()
+
+    def symbolic_info(self) -> SymbolicInfo:
+        info = SymbolicInfo()
+        self.check(self.lib.lsa_symbolic_info_get(self._h, C.byref(info)))
+        return info
+
+    def symbolic_array(self, name: str) -> np.ndarray:
+        cnt = self.check(self.lib.lsa_symbolic_array(self._h, name.encode(), None, 0))
+        out = np.empty(cnt, dtype=_ARRAY_DTYPES[name])
+        self.check(self.lib.lsa_symbolic_array(self._h, name.encode(), out.ctypes.data, out.nbytes))
+        return out
+
+    # -- numeric
+    def set_values(self, a_vals: np.ndarray, m_vals: np.ndarray | None) -> None:
+        a_vals = np.ascontiguousarray(a_vals)
+        a_sc = LSA_C128 if np.iscomplexobj(a_vals) else LSA_F64
+        a_vals = a_vals.astype(np.complex128 if a_sc else np.float64, copy=False)
+        mp, m_sc = None, LSA_F64
+        if m_vals is not None:
+            m_vals = np.ascontiguousarray(m_vals)
+            m_sc = LSA_C128 if np.iscomplexobj(m_vals) else LSA_F64
+            m_vals = m_vals.astype(np.complex128 if m_sc else np.float64, copy=False)
+            mp = m_vals.ctypes.data
+        self.check(self.lib.lsa_set_values(self._h, a_vals.ctypes.data, a_sc, mp, m_sc, 0))
+
+    def factor(self, alpha: complex, beta: complex, scalar: int, tiny_pivot: float) -> FactorStats:
+        st = FactorStats()
+        alpha, beta = complex(alpha), complex(beta)
+        self.check(self.lib.lsa_factor(self._h, alpha.real, alpha.imag, beta.real, beta.imag, scalar,
+                                       float(tiny_pivot), C.byref(st)))
+        return st
+
+    def solve(self, b: np.ndarray, trans: int = LSA_OP_N, refine_steps: int = 0) -> np.ndarray:
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        x = np.empty_like(b)
+        self.check(self.lib.lsa_solve(self._h, trans, b.ctypes.data, x.ctypes.data, refine_steps, 0))
+        return x
+
+    def spmv(self, which: int, x: np.ndarray, trans: int = LSA_OP_N) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        y = np.empty_like(x)
+        self.check(self.lib.lsa_spmv(self._h, which, trans, x.ctypes.data, y.ctypes.data, 0))
+        return y
+
+    def eigs(self, *, nev, ncv, tol, max_restarts, which, transform, sigma=0.0, adjoint=False, purify=True,
+             refine_steps=0, seed=0, v0=None) -> EigsResult:
+        p = EigsParams()
+        p.nev, p.ncv, p.max_restarts = int(nev), int(ncv), int(max_restarts)
+        p.which = WHICH[which] if isinstance(which, str) else int(which)
+        p.transform, p.adjoint, p.purify, p.refine_steps = int(transform), int(adjoint), int(purify), int(refine_steps)
+        p.tol = float(tol)
+        sigma = complex(sigma)
+        p.sigma_re, p.sigma_im = sigma.real, sigma.imag
+        p.seed = int(seed)
+        keep = None
+        if v0 is not None:
+            keep = np.ascontiguousarray(v0, dtype=np.complex128)
+            p.v0 = keep.ctypes.data_as(C.POINTER(C.c_double))
+        res = EigsResult()
+        self.check(self.lib.lsa_eigs(self._h, C.byref(p), C.byref(res)))
+        return res
+
+    def eigenvalues(self, count: int) -> np.ndarray:
+        out = np.empty(max(count, 1), dtype=np.complex128)
+        cnt = self.check(self.lib.lsa_get_eigenvalues(self._h, out.ctypes.data, count))
+        return out[:cnt]
+
+    def eigenvectors(self, count: int) -> np.ndarray:
+        out = np.empty((max(count, 1), self.n), dtype=np.complex128)
+        cnt = self.check(self.lib.lsa_get_eigenvectors(self._h, out.ctypes.data, self.n, count, 0))
+        return out[:cnt].T
+
+    def residuals(self, count: int) -> np.ndarray:
+        out = np.empty(max(count, 1), dtype=np.float64)
+        cnt = self.check(self.lib.lsa_get_residuals(self._h, out.ctypes.data, max(count, 1)))
+        return out[:cnt]
+
+    def counters(self) -> Counters:
+        c = Counters()
+        self.check(self.lib.lsa_get_counters(self._h, C.byref(c)))
+        return c
+
+    def dense_schur(self, S: np.ndarray, which: str = "LARGEST_MAGNITUDE", transform: int = 0, sigma: complex = 0.0):
+        S = np.asfortranarray(S, dtype=np.complex128).copy(order="F")
+        m = S.shape[0]
+        Q = np.zeros((m, m), dtype=np.complex128, order="F")
+        sigma = complex(sigma)
+        self.check(self.lib.lsa_dense_schur(self._h, m, S.ctypes.data, S.shape[0], Q.ctypes.data, WHICH[which],
+                                            transform, sigma.real, sigma.imag))
+        return S, Q
+
+    def gemm_bench(self, scalar: int, m: int, n: int, k: int, reps: int = 5) -> tuple[float, float]:
+        ms, err = C.c_double(), C.c_double()
+        self.check(self.lib.lsa_gemm_bench(self._h, scalar, m, n, k, reps, C.byref(ms), C.byref(err)))
+        return ms.value, err.value

@@ -274,6 +274,57 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
     Dissector d(g, opt);
     d.run(rest, nd);
   }
+  // ---- constrained placement of structurally-zero-diagonal unknowns (pressure): such an unknown
+  // must not be eliminated before at least one of the regular unknowns it is coupled to, otherwise
+  // its pivot column is still empty when it is reached (MUMPS would delay the pivot dynamically; a
+  // static structure has to settle it here).  It is moved up to the front of its earliest regular
+  // neighbour when all of them lie in ancestor separators.
+  {
+    std::vector<int> sn_tmp(n, -1);
+    {
+      int pos = 0;
+      for (size_t s = 0; s < nd.sn_sizes.size(); ++s)
+        for (int q = 0; q < nd.sn_sizes[s]; ++q) sn_tmp[nd.order[pos++]] = (int)s;
+    }
+    const int ns0 = (int)nd.sn_sizes.size();
+    std::vector<int> target(n, -1);
+    std::vector<int> nb;
+    int moved = 0;
+    if (opt.order_last) {
+      for (int v : nd.order) {
+        target[v] = sn_tmp[v];
+        if (!opt.order_last[v]) continue;
+        // front index such that at least `frac` of the regular neighbours are eliminated no later
+        nb.clear();
+        for (long long e = g.xadj[v]; e < g.xadj[v + 1]; ++e) {
+          const int u = g.adj[e];
+          if (!opt.order_last[u]) nb.push_back(sn_tmp[u]);
+        }
+        if (nb.empty()) continue;
+        std::sort(nb.begin(), nb.end());
+        size_t q = (size_t)std::ceil(opt.coupled_fraction * (double)nb.size());
+        if (q < 1) q = 1;
+        if (q > nb.size()) q = nb.size();
+        const int sreq = nb[q - 1];
+        if (sreq > sn_tmp[v]) {
+          target[v] = sreq;
+          moved++;
+        }
+      }
+    }
+    if (moved > 0) {
+      std::vector<int> cnt(ns0 + 1, 0);
+      for (int v : nd.order) cnt[target[v] + 1]++;
+      for (int s = 0; s < ns0; ++s) cnt[s + 1] += cnt[s];
+      std::vector<int> order2(nd.order.size());
+      std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+      for (int v : nd.order) order2[pos[target[v]]++] = v;  // stable inside each front
+      nd.order.swap(order2);
+      nd.sn_sizes.clear();
+      for (int s = 0; s < ns0; ++s)
+        if (cnt[s + 1] > cnt[s]) nd.sn_sizes.push_back(cnt[s + 1] - cnt[s]);
+    }
+  }
   sym.perm = iso;
   sym.perm.insert(sym.perm.end(), nd.order.begin(), nd.order.end());
   if ((int)sym.perm.size() != n) throw std::runtime_error("ordering lost vertices");

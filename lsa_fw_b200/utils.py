@@ -1,0 +1,557 @@
+"""LSA-FW Solver utilities, B200 backend: enums and the `iEpsSolver` wrapper.
+
+Mirror of the EPS half of the reference's `Solver/utils.py` (`:27-63` iEpsProblemType, `:66-93`
+PreconditionerType, `:131-149` iSTType, `:152-187` iEpsWhich, `:190-328` iEpsSolver) with the same
+member names, setter/getter names, argument meaning and error behaviour, so that code written
+against the SLEPc-backed class runs unchanged.  Where the reference forwards to `SLEPc.EPS`, this
+class records the setting and `solve()` drives the CUDA library through the C ABI of
+`include/lsa_b200.h` (ctypes, `_lib.py`).  There is no CPU path: without the CUDA extension or
+without a GPU `solve()` raises.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import logging
+import weakref
+from enum import Enum, StrEnum, auto
+from typing import Iterator
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import LsaError
+from .carriers import iComplexPETScVector, iPETScMatrix, iPETScVector
+
+logger = logging.getLogger(__name__)
+
+__all__ = [
+    "iEpsProblemType", "PreconditionerType", "iSTType", "iEpsWhich", "iEpsSolver", "LsaError",
+    "clear_symbolic_cache",
+]
+
+
+class iEpsProblemType(Enum):  # noqa: N801
+    """EPS problem types (reference `Solver/utils.py:27-63`)."""
+
+    HEP = 1
+    """Standard Hermitian eigenvalue problem. Ax = λx, with A Hermitian."""
+    NHEP = 2
+    """Standard non-Hermitian eigenvalue problem: Ax = λx, with A arbitrary."""
+    GHEP = 3
+    """Generalized Hermitian eigenvalue problem: Ax = λBx, with A, B Hermitian."""
+    GNHEP = 4
+    """Generalized non-Hermitian eigenvalue problem: Ax = λBx, with arbitrary A, B."""
+    PGNHEP = 5
+    """Generalized non-Hermitian eigenvalue problem with positive (semi-)definite B."""
+    GHIEP = 6
+    """Generalized Hermitian indefinite eigenvalue problem."""
+
+    def to_slepc(self) -> int:
+        """Backend code of this problem type (SLEPc's enum value in the reference)."""
+        return self.value
+
+    @classmethod
+    def from_slepc(cls, problem_type) -> "iEpsProblemType":
+        try:
+            return cls(int(problem_type))
+        except ValueError:
+            raise ValueError(f"Unsupported SLEPc EPS ProblemType: {problem_type}")
+
+    @classmethod
+    def from_string(cls, name: str) -> "iEpsProblemType":
+        try:
+            return cls[name.upper()]
+        except KeyError:
+            raise ValueError(f"Invalid problem type: {name}. Choose from {list(cls.__members__.keys())}.")
+
+
+class PreconditionerType(StrEnum):
+    """Preconditioner names accepted by `set_st_pc_type` (reference `Solver/utils.py:66-93`).
+
+    Only the direct factorisations (LU, CHOLESKY) are executed by the B200 backend; the other names
+    are recorded (and round-trip through `.raw.getST().getKSP().getPC().getType()`), and `solve()`
+    raises NotImplementedError for them.
+    """
+
+    NONE = auto()
+    JACOBI = auto()
+    SOR = auto()
+    ASM = auto()
+    ILU = auto()
+    ICC = auto()
+    LU = auto()
+    CHOLESKY = auto()
+    GAMG = auto()
+    HYPRE = auto()
+    REDUNDANT = auto()
+    SHELL = auto()
+
+
+class iSTType(Enum):  # noqa: N801
+    """Spectral transformations (reference `Solver/utils.py:131-149`); SHIFT and SINVERT are built."""
+
+    SHELL = "shell"
+    SHIFT = "shift"
+    SINVERT = "sinvert"
+    CAYLEY = "cayley"
+    PRECOND = "precond"
+    FILTER = "filter"
+
+    def to_slepc(self) -> str:
+        return self.value
+
+
+class iEpsWhich(Enum):  # noqa: N801
+    """Which eigenpairs (reference `Solver/utils.py:152-187`).
+
+    The reference maps BOTH `SMALLEST_MAGNITUDE` and `LARGEST_REAL` to `SLEPc.EPS.Which.LARGEST_REAL`
+    (`Solver/utils.py:157-158`), which makes them the same enum member; that alias is kept, so callers
+    observe identical behaviour.
+    """
+
+    ALL = "ALL"
+    LARGEST_MAGNITUDE = "LARGEST_MAGNITUDE"
+    SMALLEST_MAGNITUDE = "LARGEST_REAL"
+    LARGEST_REAL = "LARGEST_REAL"
+    SMALLEST_REAL = "SMALLEST_REAL"
+    LARGEST_IMAGINARY = "LARGEST_IMAGINARY"
+    SMALLEST_IMAGINARY = "SMALLEST_IMAGINARY"
+    TARGET_MAGNITUDE = "TARGET_MAGNITUDE"
+    TARGET_REAL = "TARGET_REAL"
+    TARGET_IMAGINARY = "TARGET_IMAGINARY"
+    USER = "USER"
+
+    def to_slepc(self) -> str:
+        return self.value
+
+    def to_arpack(self) -> str:
+        """ARPACK-style code (reference `Solver/utils.py:170-187`)."""
+        match self:
+            case iEpsWhich.LARGEST_REAL:
+                return "LR"
+            case iEpsWhich.LARGEST_IMAGINARY:
+                return "LI"
+            case iEpsWhich.SMALLEST_REAL:
+                return "SR"
+            case iEpsWhich.SMALLEST_IMAGINARY:
+                return "SI"
+            case iEpsWhich.LARGEST_MAGNITUDE:
+                return "LM_abs"
+            case _:
+                raise ValueError(f"Unsupported type for ARPACK-based eigensolver: {self.name}.")
+
+
+_HERMITIAN = {iEpsProblemType.HEP, iEpsProblemType.GHEP}
+
+# --------------------------------------------------------------------------- symbolic reuse
+
+_SYM_CACHE: dict[str, "_lib.Handle"] = {}
+_SYM_CACHE_MAX = 4
+# (id(A carrier), id(M carrier)) -> weakref of the solver that factored that pencil
+_FACTOR_REGISTRY: dict[tuple[int, int], "weakref.ReferenceType[iEpsSolver]"] = {}
+
+
+def clear_symbolic_cache() -> None:
+    """Drop cached symbolic analyses (and their device buffers)."""
+    for h in _SYM_CACHE.values():
+        h.close()
+    _SYM_CACHE.clear()
+    _FACTOR_REGISTRY.clear()
+
+
+def _pattern_key(a: sp.csr_matrix, m: sp.csr_matrix | None, extra: tuple) -> str:
+    hsh = hashlib.blake2b(digest_size=16)
+    for mat in (a, m):
+        if mat is None:
+            hsh.update(b"none")
+            continue
+        hsh.update(np.int64(mat.shape[0]).tobytes())
+        hsh.update(np.ascontiguousarray(mat.indptr).tobytes())
+        hsh.update(np.ascontiguousarray(mat.indices).tobytes())
+    hsh.update(repr(extra).encode())
+    return hsh.hexdigest()
+
+
+def _as_csr(mat) -> sp.csr_matrix:
+    m = mat.as_scipy_array() if hasattr(mat, "as_scipy_array") else sp.csr_matrix(mat)
+    m = sp.csr_matrix(m)
+    if not m.has_canonical_format:
+        m = m.copy()
+        m.sum_duplicates()
+    return m
+
+
+class _RawPC:
+    def __init__(self, s: "iEpsSolver") -> None:
+        self._s = s
+
+    def getType(self) -> str:  # noqa: N802
+        return self._s._pc_type
+
+
+class _RawKSP:
+    def __init__(self, s: "iEpsSolver") -> None:
+        self._s = s
+
+    def getPC(self) -> _RawPC:  # noqa: N802
+        return _RawPC(self._s)
+
+    def getIterationNumber(self) -> int:  # noqa: N802
+        """Number of linear solves of the last eigensolve (each is one direct fwd+bwd solve)."""
+        return int(self._s._stats.get("n_op_applies", 0))
+
+
+class _RawST:
+    def __init__(self, s: "iEpsSolver") -> None:
+        self._s = s
+
+    def getKSP(self) -> _RawKSP:  # noqa: N802
+        return _RawKSP(self._s)
+
+    def getType(self) -> str:  # noqa: N802
+        return self._s._st_type.value
+
+    def getShift(self):  # noqa: N802
+        return self._s._target
+
+
+class _RawEPS:
+    """Shim exposing the few `SLEPc.EPS` getters that callers and the reference's tests touch
+    (`Solver/eigen.py:142`; `tests/unit/Solver/test_eigen.py:97-104,320-322`)."""
+
+    def __init__(self, s: "iEpsSolver") -> None:
+        self._s = s
+
+    def getTolerances(self):  # noqa: N802
+        return self._s._tol, self._s._max_it
+
+    def getDimensions(self):  # noqa: N802
+        return self._s._nev, self._s._ncv_effective(), self._s._ncv_effective()
+
+    def getProblemType(self):  # noqa: N802
+        return self._s._problem_type.to_slepc()
+
+    def getST(self) -> _RawST:  # noqa: N802
+        return _RawST(self._s)
+
+    def getConverged(self) -> int:  # noqa: N802
+        return self._s.get_num_converged()
+
+    def getEigenvalue(self, i: int):  # noqa: N802
+        return self._s.get_eigenvalue(i)
+
+    def getTarget(self):  # noqa: N802
+        return self._s._target
+
+    def getWhichEigenpairs(self):  # noqa: N802
+        return self._s._which_effective().to_slepc()
+
+    def getIterationNumber(self) -> int:  # noqa: N802
+        return int(self._s._stats.get("n_restarts", 0))
+
+
+class iEpsSolver:  # noqa: N801
+    """Eigenproblem solver object with the interface of the reference's SLEPc wrapper
+    (`Solver/utils.py:190-328`), executing on one B200 through liblsa_b200.so."""
+
+    def __init__(self, A: iPETScMatrix | None = None, M: iPETScMatrix | None = None, comm=None) -> None:
+        if M is not None and A is None:
+            raise ValueError("Cannot set right-hand operator M without left-hand operator A.")
+        self._A = None
+        self._M = None
+        self._problem_type = iEpsProblemType.NHEP
+        self._nev = 1
+        self._ncv: int | None = None
+        self._tol = 1e-8
+        self._max_it = 100
+        self._which: iEpsWhich | None = None
+        self._target: float | complex = 0.0
+        self._st_type = iSTType.SHIFT
+        self._pc_type = "lu"
+        self._interval = None
+        # backend options (extensions; all optional)
+        self._opts = dict(leaf_size=64, coords=None, refine_steps=0, tiny_pivot=1e-13, seed=0, device=0,
+                          purify=True, nthreads=0, v0=None, force_complex=False)
+        self._adjoint = False
+        self._handle: _lib.Handle | None = None
+        self._factor_key = None
+        self._stats: dict = {}
+        self._nconv = 0
+        self._eigenvalues: np.ndarray = np.zeros(0, dtype=complex)
+        self._eigenvectors: np.ndarray | None = None
+        self._complex_mode = False
+        if A is not None:
+            self.set_operators(A, M)
+
+    # ------------------------------------------------------------------ reference interface
+    @property
+    def raw(self) -> _RawEPS:
+        """Access the underlying solver object (a shim with SLEPc.EPS getter names)."""
+        return _RawEPS(self)
+
+    def set_operators(self, A: iPETScMatrix, M: iPETScMatrix | None = None) -> None:
+        """Set the matrix operators for the generalized eigenproblem Ax = λMx."""
+        self._A, self._M = A, M
+        self._factor_key = None
+
+    def set_problem_type(self, problem_type: iEpsProblemType) -> None:
+        """Set the eigenproblem type. Refer to iEpsProblemType enum."""
+        self._problem_type = problem_type
+
+    def set_dimensions(self, number_eigenpairs: int, subspace_dimension: int | None = None) -> None:
+        """Set number of eigenpairs (nev) and subspace dimension (ncv)."""
+        self._nev = int(number_eigenpairs)
+        self._ncv = None if subspace_dimension is None else int(subspace_dimension)
+
+    def set_tolerances(self, atol: float, max_it: int) -> None:
+        """Set convergence tolerance (relative, as SLEPc's `tol`) and maximum number of restarts."""
+        self._tol, self._max_it = float(atol), int(max_it)
+
+    def set_which_eigenpairs(self, which: iEpsWhich) -> None:
+        """Select which eigenpairs to compute. Refer to iEpsWhich enum."""
+        self._which = which
+
+    def set_target(self, sigma: float | complex) -> None:
+        """Set spectral transformation shift (target)."""
+        self._target = sigma
+        self._factor_key = None
+
+    def set_interval(self, a: float, b: float) -> None:
+        """Compute eigenvalues in real interval [a, b] (spectrum slicing: not built)."""
+        self._interval = (a, b)
+
+    def set_interval_complex(self, a: float, b: float, c: float, d: float) -> None:
+        """Compute eigenvalues in complex rectangle [a,b]x[c,d] (contour methods: not built)."""
+        self._interval = (a, b, c, d)
+
+    def set_st_type(self, st_type: iSTType) -> None:
+        """Set spectral transformation type. Refer to iSTType enum."""
+        self._st_type = st_type
+        self._factor_key = None
+
+    def set_st_pc_type(self, pc_type: PreconditionerType) -> None:
+        """Set the factorisation used inside the spectral transformation."""
+        self._pc_type = pc_type.name.lower()
+
+    # ------------------------------------------------------------------ extensions
+    def set_backend_options(self, **kw) -> None:
+        """B200-backend knobs: leaf_size, coords (n x dim ordering hint), refine_steps, tiny_pivot,
+        seed, device, purify, nthreads, v0 (start vector), force_complex."""
+        unknown = set(kw) - set(self._opts)
+        if unknown:
+            raise TypeError(f"unknown backend option(s): {sorted(unknown)}")
+        self._opts.update(kw)
+
+    def set_adjoint(self, flag: bool = True) -> None:
+        """Solve the adjoint problem (A^H, M^H) at conj(target) on the factors of (A, M, target):
+        left eigenvectors without the second factorisation of `Sensitivity/__init__.py:246-262`."""
+        self._adjoint = bool(flag)
+
+    @property
+    def stats(self) -> dict:
+        """Timings and counters of the last `solve()` (symbolic, factor, eigs, residual data)."""
+        return self._stats
+
+    @property
+    def handle(self) -> "_lib.Handle | None":
+        return self._handle
+
+    # ------------------------------------------------------------------ helpers
+    def _ncv_effective(self) -> int:
+        n = self._A.shape[0] if self._A is not None else 1 << 30
+        ncv = self._ncv if self._ncv is not None else max(2 * self._nev, self._nev + 15)
+        return max(1, min(ncv, n))
+
+    def _which_effective(self) -> iEpsWhich:
+        if self._which is not None:
+            return self._which
+        return iEpsWhich.TARGET_MAGNITUDE if self._st_type == iSTType.SINVERT else iEpsWhich.LARGEST_MAGNITUDE
+
+    def _resolve_adjoint_reuse(self):
+        """If (A, M) are `.H` views of a pencil that another live solver factored at conj(target),
+        return that solver (drop-in form of the Sensitivity adjoint solve)."""
+        a0 = getattr(self._A, "_adjoint_of", None)
+        m0 = getattr(self._M, "_adjoint_of", None) if self._M is not None else None
+        if a0 is None or (self._M is not None and m0 is None):
+            return None
+        ref = _FACTOR_REGISTRY.get((id(a0), id(m0) if m0 is not None else 0))
+        other = ref() if ref is not None else None
+        if other is None or other._handle is None or other._factor_key is None:
+            return None
+        if other._st_type != iSTType.SINVERT or self._st_type != iSTType.SINVERT:
+            return None
+        if complex(other._target).conjugate() != complex(self._target):
+            return None
+        return other
+
+    # ------------------------------------------------------------------ solve
+    def solve(self) -> None:
+        """Run the eigensolver on the configured operators and settings."""
+        if self._A is None:
+            raise ValueError("Operators must be set before solve().")
+        if self._interval is not None or self._which == iEpsWhich.ALL:
+            raise NotImplementedError("interval / ALL (spectrum slicing, contour integrals) is not built on the B200 backend")
+        if self._st_type not in (iSTType.SHIFT, iSTType.SINVERT):
+            raise NotImplementedError(f"spectral transformation {self._st_type.name} is not built on the B200 backend")
+        if self._which == iEpsWhich.USER:
+            raise NotImplementedError("user-defined eigenvalue ordering is not built on the B200 backend")
+        needs_factor = self._st_type == iSTType.SINVERT or self._M is not None
+        if needs_factor and self._pc_type not in ("lu", "cholesky"):
+            raise NotImplementedError(
+                f"st_pc_type '{self._pc_type}' is not built on the B200 backend (direct LU/CHOLESKY only)")
+        import time
+
+        t_start = time.perf_counter()
+        n = self._A.shape[0]
+        sigma = complex(self._target)
+        sinvert = self._st_type == iSTType.SINVERT
+        adjoint = self._adjoint
+        donor = self._resolve_adjoint_reuse()
+        stats: dict = {"n": n}
+
+        if donor is not None:
+            # adjoint modes on the donor's factors: same handle, trans = H sweeps
+            h = donor._handle
+            self._handle = h
+            adjoint = True
+            sigma_fact = complex(donor._target)
+            self._complex_mode = donor._complex_mode
+            stats["reused_factorisation"] = True
+            stats["symbolic_seconds"] = 0.0
+            stats["factor_seconds"] = 0.0
+        else:
+            A = _as_csr(self._A)
+            M = _as_csr(self._M) if self._M is not None else None
+            data_complex = np.iscomplexobj(A.data) or (M is not None and np.iscomplexobj(M.data))
+            use_complex = data_complex or sigma.imag != 0.0 or self._opts["force_complex"]
+            self._complex_mode = use_complex
+            coords = self._opts["coords"]
+            key = _pattern_key(A, M, (self._opts["leaf_size"], None if coords is None else id(coords),
+                                      self._opts["device"]))
+            t0 = time.perf_counter()
+            h = _SYM_CACHE.get(key)
+            if h is None:
+                h = _lib.Handle(n, self._opts["device"])
+                # structurally zero diagonal of the matrix to be factored (pressure rows): ordered last
+                if sinvert:
+                    dF = A.diagonal() - sigma * (M.diagonal() if M is not None else np.ones(n))
+                else:
+                    dF = M.diagonal() if M is not None else A.diagonal()
+                order_last = (dF == 0).astype(np.uint8)
+                h.analyze(A.indptr, A.indices, None if M is None else M.indptr, None if M is None else M.indices,
+                          leaf_size=self._opts["leaf_size"], coords=coords, order_last=order_last,
+                          nthreads=self._opts["nthreads"])
+                while len(_SYM_CACHE) >= _SYM_CACHE_MAX:
+                    _SYM_CACHE.pop(next(iter(_SYM_CACHE))).close()
+                _SYM_CACHE[key] = h
+                stats["symbolic_cached"] = False
+            else:
+                stats["symbolic_cached"] = True
+            stats["symbolic_seconds"] = time.perf_counter() - t0
+            self._handle = h
+            info = h.symbolic_info()
+            stats.update(n_fronts=info.n_fronts, n_levels=info.n_levels, nnz_lu=info.nnz_lu,
+                         n_decoupled=info.n_decoupled, max_front=info.max_front,
+                         symbolic_phases=list(info.seconds))
+            t0 = time.perf_counter()
+            h.set_values(A.data, None if M is None else M.data)
+            stats["upload_seconds"] = time.perf_counter() - t0
+            sigma_fact = sigma
+            if needs_factor:
+                scalar = _lib.LSA_C128 if use_complex else _lib.LSA_F64
+                if sinvert:
+                    fs = h.factor(1.0, -sigma, scalar, self._opts["tiny_pivot"])
+                else:
+                    fs = h.factor(0.0, 1.0, scalar, 0.0)  # plain M^-1: an exactly singular M must raise
+                stats.update(factor_seconds=fs.seconds, factor_flops=fs.flops, n_perturbed=fs.n_perturbed,
+                             n_row_swaps=fs.n_row_swaps, min_pivot=fs.min_pivot, max_pivot=fs.max_pivot,
+                             factor_kernels=fs.n_kernels)
+                self._factor_key = (sigma_fact, self._st_type)
+                _FACTOR_REGISTRY[(id(self._A), id(self._M) if self._M is not None else 0)] = weakref.ref(self)
+
+        which = self._which_effective()
+        res = h.eigs(nev=self._nev, ncv=self._ncv_effective(), tol=self._tol, max_restarts=self._max_it,
+                     which=which.value, transform=_lib.LSA_ST_SINVERT if sinvert else _lib.LSA_ST_SHIFT,
+                     sigma=sigma_fact, adjoint=adjoint, purify=self._opts["purify"] and sinvert,
+                     refine_steps=self._opts["refine_steps"], seed=self._opts["seed"], v0=self._opts["v0"])
+        self._nconv = res.nconv
+        self._eigenvalues = h.eigenvalues(res.nconv)
+        # the handle (and its device buffers) may be shared with other solver objects through the
+        # symbolic cache / adjoint reuse: bring the vectors to the host now
+        self._eigenvectors = None
+        t0 = time.perf_counter()
+        if res.nconv > 0:
+            self._fetch_vectors()
+        stats["fetch_seconds"] = time.perf_counter() - t0
+        stats.update(nconv=res.nconv, n_restarts=res.n_restarts, n_op_applies=res.n_op_applies,
+                     breakdown=res.breakdown, eigs_seconds=res.seconds, solve_seconds=res.seconds_solve,
+                     spmv_seconds=res.seconds_spmv, ortho_seconds=res.seconds_ortho, rr_seconds=res.seconds_rr,
+                     restart_seconds=res.seconds_restart, total_seconds=time.perf_counter() - t_start)
+        self._stats = stats
+
+    # ------------------------------------------------------------------ results
+    def get_num_converged(self) -> int:
+        """Return number of converged eigenpairs."""
+        return int(self._nconv)
+
+    def get_eigenvalue(self, idx: int) -> float | complex:
+        """Get the eigenvalue at index idx (real number for Hermitian problem types)."""
+        if not 0 <= idx < self._nconv:
+            raise IndexError(f"eigenvalue index {idx} out of range (converged: {self._nconv})")
+        lam = complex(self._eigenvalues[idx])
+        if self._problem_type in _HERMITIAN:
+            return float(lam.real)
+        return lam
+
+    def _fetch_vectors(self) -> np.ndarray:
+        if self._eigenvectors is None:
+            X = self._handle.eigenvectors(self._nconv)
+            # fix the arbitrary phase: largest component real positive (deterministic output)
+            for i in range(X.shape[1]):
+                j = int(np.argmax(np.abs(X[:, i])))
+                if X[j, i] != 0:
+                    X[:, i] *= np.conj(X[j, i]) / abs(X[j, i])
+            if self._problem_type in (iEpsProblemType.GHEP,) and self._M is not None:
+                # SLEPc normalises GHEP eigenvectors to unit B-norm
+                Mh = _as_csr(self._M)
+                for i in range(X.shape[1]):
+                    bn = np.sqrt(abs(np.vdot(X[:, i], Mh @ X[:, i])))
+                    if bn > 0:
+                        X[:, i] /= bn
+            self._eigenvectors = X
+        return self._eigenvectors
+
+    def get_eigenvector(self, idx: int) -> iComplexPETScVector:
+        """Get the eigenvector at index idx (unit 2-norm; B-norm for GHEP).
+
+        Complex mode (complex shift or data; the reference's complex PETSc build): one complex vector,
+        `.imag is None` (`Solver/utils.py:293-297`).  Real mode (the real build): `(vr, vi)` with `vi`
+        dropped when `||vi|| <= 1e-6` (`Solver/utils.py:280-291`).
+        """
+        if not 0 <= idx < self._nconv:
+            raise IndexError(f"eigenvector index {idx} out of range (converged: {self._nconv})")
+        x = self._fetch_vectors()[:, idx]
+        if self._complex_mode:
+            return iComplexPETScVector(iPETScVector(x.copy()))
+        vi = x.imag
+        if np.linalg.norm(vi) <= 1e-6:
+            return iComplexPETScVector(iPETScVector(x.real.copy()))
+        return iComplexPETScVector(iPETScVector(x.real.copy()), iPETScVector(vi.copy()))
+
+    def get_eigenpair(self, idx: int) -> tuple[float | complex, iComplexPETScVector]:
+        """Get (eigenvalue, eigenvector) tuple at index idx."""
+        return self.get_eigenvalue(idx), self.get_eigenvector(idx)
+
+    def get_all_eigenpairs_up_to(self, num: int) -> Iterator[tuple[float | complex, iComplexPETScVector]]:
+        """Lazily yield up to `num` converged eigenpairs."""
+        limit = min(self.get_num_converged(), num)
+        for i in range(limit):
+            yield self.get_eigenpair(i)
+
+    def get_residuals(self) -> np.ndarray:
+        """||A x - λ M x|| / (||A||_F ||x||) of every converged pair, evaluated on the device."""
+        if self._nconv == 0:
+            return np.zeros(0)
+        return self._handle.residuals(self._nconv)

@@ -1,0 +1,147 @@
+"""NumPy emulation of the multifrontal numeric phase, driven by the C++ symbolic structures.
+
+TEST INFRASTRUCTURE (CPU).  It follows the CUDA kernels of lsa_fw_b200/csrc/factor.cu and solve.cu
+step by step (scatter -> extend-add -> partial LU with pivoting restricted to the pivot block ->
+Schur complement; up/down sweeps for trans = N and trans = H) so that the host-side index maps and the
+algebra of the sweeps can be verified against SciPy without a GPU.  Never imported by the package.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+
+class Emulator:
+    def __init__(self, handle, n: int):
+        g = handle.symbolic_array
+        self.n = n
+        self.perm = g("perm")
+        self.sn_ptr = g("sn_ptr")
+        self.st_ptr = g("st_ptr")
+        self.st_idx = g("st_idx")
+        self.ea_map = g("ea_map")
+        self.parent = g("parent")
+        self.level = g("level")
+        self.k = g("front_k")
+        self.r = g("front_r")
+        self.p_off = g("p_off")
+        self.q_off = g("q_off")
+        self.a_dst = g("a_dst")
+        try:
+            self.m_dst = g("m_dst")
+        except Exception:
+            self.m_dst = None
+        info = handle.symbolic_info()
+        self.fac_size = info.factor_entries
+        self.n_iso = info.n_decoupled
+        self.ns = info.n_fronts
+        self.diag_off = self.fac_size - ((self.n_iso + 3) // 4) * 4 if self.n_iso else self.fac_size
+        self.nlevels = info.n_levels
+
+    # ---- factorisation of alpha A + beta M (values in the caller's CSR entry order)
+    def factor(self, a_vals, m_vals, alpha, beta, dtype=np.complex128):
+        fac = np.zeros(self.fac_size, dtype=dtype)
+        fac[self.a_dst] = alpha * a_vals
+        if m_vals is not None:
+            np.add.at(fac, self.m_dst, beta * m_vals)
+        self.fac = fac
+        ns = self.ns
+        self.cb = [None] * ns
+        self.piv = [None] * ns
+        children = [[] for _ in range(ns)]
+        for s in range(ns):
+            if self.parent[s] >= 0:
+                children[self.parent[s]].append(s)
+        self.children = children
+        order = np.argsort(-self.level, kind="stable")
+        for s in order:
+            k, r = int(self.k[s]), int(self.r[s])
+            m = k + r
+            P = fac[self.p_off[s]: self.p_off[s] + m * k].reshape((m, k), order="F")
+            Q = fac[self.q_off[s]: self.q_off[s] + k * r].reshape((k, r), order="F")
+            Cb = np.zeros((r, r), dtype=dtype)
+            for c in children[s]:
+                mp = self.ea_map[self.st_ptr[c]: self.st_ptr[c + 1]]
+                cbc = self.cb[c]
+                top = mp < k
+                bot = ~top
+                P[np.ix_(mp, mp[top])] += cbc[:, top]
+                Q[np.ix_(mp[top], mp[bot] - k)] += cbc[np.ix_(top, bot)]
+                Cb[np.ix_(mp[bot] - k, mp[bot] - k)] += cbc[np.ix_(bot, bot)]
+                self.cb[c] = None
+            # partial LU, pivot search restricted to rows [j, k)
+            piv = np.arange(k)
+            for j in range(k):
+                p = j + int(np.argmax(np.abs(P[j:k, j].real) + np.abs(P[j:k, j].imag)))
+                piv[j] = p
+                if p != j:
+                    P[[j, p], :] = P[[p, j], :]
+                    Q[[j, p], :] = Q[[p, j], :]
+                P[j + 1:, j] /= P[j, j]
+                P[j + 1:, j + 1:] -= np.outer(P[j + 1:, j], P[j, j + 1:])
+                Q[j + 1:, :] -= np.outer(P[j + 1: k, j], Q[j, :])
+            Cb -= P[k:, :] @ Q
+            self.cb[s] = Cb
+            self.piv[s] = piv
+        if self.n_iso:
+            self.diag = fac[self.diag_off: self.diag_off + self.n_iso]
+
+    def _front(self, s):
+        k, r = int(self.k[s]), int(self.r[s])
+        m = k + r
+        P = self.fac[self.p_off[s]: self.p_off[s] + m * k].reshape((m, k), order="F")
+        Q = self.fac[self.q_off[s]: self.q_off[s] + k * r].reshape((k, r), order="F")
+        return k, r, P, Q
+
+    def solve(self, b, trans="N"):
+        """x = F^-1 b (trans='N') or F^-H b (trans='H'); b in the caller's ordering."""
+        x = np.asarray(b, dtype=complex)[self.perm].copy()
+        H = trans == "H"
+        if self.n_iso:
+            d = np.conj(self.diag) if H else self.diag
+            x[: self.n_iso] = x[: self.n_iso] / d
+        ns = self.ns
+        up = np.argsort(-self.level, kind="stable")
+        cbv = [None] * ns
+        for s in up:
+            k, r, P, Q = self._front(s)
+            c0 = self.sn_ptr[s]
+            bot = np.zeros(r, dtype=complex)
+            for c in self.children[s]:
+                mp = self.ea_map[self.st_ptr[c]: self.st_ptr[c + 1]]
+                top = mp < k
+                x[c0 + mp[top]] += cbv[c][top]
+                bot[mp[~top] - k] += cbv[c][~top]
+                cbv[c] = None
+            xt = x[c0: c0 + k].copy()
+            if not H:
+                for j in range(k):
+                    p = self.piv[s][j]
+                    if p != j:
+                        xt[[j, p]] = xt[[p, j]]
+                xt = sla.solve_triangular(P[:k, :k], xt, lower=True, unit_diagonal=True)
+                bot -= P[k:, :] @ xt
+            else:
+                xt = sla.solve_triangular(P[:k, :k].conj().T, xt, lower=True)
+                bot -= Q.conj().T @ xt
+            x[c0: c0 + k] = xt
+            cbv[s] = bot
+        for s in up[::-1]:
+            k, r, P, Q = self._front(s)
+            c0 = self.sn_ptr[s]
+            anc = x[self.st_idx[self.st_ptr[s]: self.st_ptr[s + 1]]]
+            xt = x[c0: c0 + k]
+            if not H:
+                xt = sla.solve_triangular(P[:k, :k], xt - Q @ anc, lower=False)
+            else:
+                xt = sla.solve_triangular(P[:k, :k].conj().T, xt - P[k:, :].conj().T @ anc, lower=False,
+                                          unit_diagonal=True)
+                for j in range(k - 1, -1, -1):
+                    p = self.piv[s][j]
+                    if p != j:
+                        xt[[j, p]] = xt[[p, j]]
+            x[c0: c0 + k] = xt
+        out = np.empty_like(x)
+        out[self.perm] = x
+        return out
