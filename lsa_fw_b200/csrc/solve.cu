@@ -270,12 +270,14 @@ __global__ void __launch_bounds__(256) k_up_update(const Front* __restrict__ fro
 
 // --------------------------------------------------------------------------------------- down sweep
 
-// y_top -= Off * y[ancestor rows].  N: Off = U12 = Q (k x r);  H: Off = L21^H, L21 = P[k:m, 0:k].
+// y_top -= Off * anc[ancestor rows].  N: Off = U12 = Q (k x r);  H: Off = L21^H, L21 = P[k:m, 0:k].
+// `anc` holds the FINAL values of the ancestors: the work vector itself for N; for H the output
+// vector, because each front applies its own P^T as soon as its pivot block is solved.
 // grid: (pivot-row chunks of 64, fronts); block 256.
 template <class T, bool H>
 __global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                   int first, const int* __restrict__ st_idx, const T* __restrict__ fac,
-                                                  z128* __restrict__ y) {
+                                                  const z128* anc, z128* y) {
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k, r = f.r;
   const int r0 = blockIdx.x * 64;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fron
   for (int c0 = 0; c0 < r; c0 += SB) {
     const int len = min(SB, r - c0);
     __syncthreads();
-    if (tid < len) xs[tid] = y[idx[c0 + tid]];
+    if (tid < len) xs[tid] = anc[idx[c0 + tid]];
     __syncthreads();
     if (!H) {
       if (r0 + rr < k) {
@@ -438,6 +440,14 @@ __global__ void k_unpermute(const z128* __restrict__ y, z128* __restrict__ x, co
   if (i < n) x[gperm[i]] = y[i];
 }
 
+// H down sweep: x[pivot rows of the level's fronts] = P^T y  (one CTA per front)
+__global__ void __launch_bounds__(256) k_level_unpermute(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                         int first, const int* __restrict__ gperm,
+                                                         const z128* __restrict__ y, z128* __restrict__ x) {
+  const Front f = fronts[lvl_front[first + blockIdx.x]];
+  for (int i = threadIdx.x; i < f.k; i += blockDim.x) x[gperm[f.col0 + i]] = y[f.col0 + i];
+}
+
 // ------------------------------------------------------------------------------------------- driver
 
 template <class T, bool H>
@@ -491,7 +501,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       int maxr = 0;
       for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[sym.lvl_front[q]].r);
       if (maxr > 0) {
-        k_down_off<T, H><<<dim3(cdiv(maxk, 64), cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, y);
+        k_down_off<T, H><<<dim3(cdiv(maxk, 64), cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, y);
         LSA_LAUNCH_CHECK();
         launches++;
       }
@@ -511,10 +521,15 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           launches++;
         }
       }
+      if (H) {
+        k_level_unpermute<<<cnt, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_gperm, y, x);
+        LSA_LAUNCH_CHECK();
+        launches++;
+      }
     }
   }
   if (H) {
-    k_unpermute<<<cdiv(h.n, 256), 256, 0, st>>>(y, x, h.d_gperm, h.n);
+    if (sym.n_iso > 0) k_unpermute<<<cdiv(sym.n_iso, 256), 256, 0, st>>>(y, x, h.d_gperm, sym.n_iso);
     LSA_LAUNCH_CHECK();
   } else {
     LSA_CUDA(cudaMemcpyAsync(x, y, (size_t)h.n * sizeof(z128), cudaMemcpyDeviceToDevice, st));

@@ -454,3 +454,61 @@ def cylinder_wake_3d(n: int = 74, re: float = 300.0, **kw) -> Pencil:
     return assemble_pencil(
         (n, n, n), (12.0, 6.0, 6.0), re=re, baseflow=wake_profile(0.9, 1.5, 3.0), **kw
     )
+
+
+def membrane_pencil(nx: int, ny: int, a: float = 1.0, b: float = 1.0) -> Pencil:
+    """Vibrating membrane: P2 Laplace eigenproblem K x = lambda M x on an a x b rectangle with
+    homogeneous Dirichlet boundary (reference `tests/benchmark/vibrating_membrane.py:130-173`):
+    analytic spectrum pi^2 (m^2/a^2 + n^2/b^2); Dirichlet rows are identity in K and M, which adds
+    the spurious eigenvalue 1 the reference filters out (`:169-173`)."""
+    shape = (nx, ny)
+    dim = 2
+    fine_shape = (2 * nx + 1, 2 * ny + 1)
+    axes = [_grid_spacing(nx, a, 1.0), _grid_spacing(ny, b, 1.0)]
+    strides = np.array([fine_shape[1], 1], dtype=np.int64)
+    n = fine_shape[0] * fine_shape[1]
+    cells = _simplices(shape)
+    lam, wq = simplex_quadrature(dim, 4)
+    nv = 3
+    pairs = [(i, i) for i in range(nv)] + [(i, j) for i in range(nv) for j in range(i + 1, nv)]
+    nq = len(wq)
+    phi = np.zeros((nq, 6))
+    dphi = np.zeros((nq, 6, nv))
+    for k, (i, j) in enumerate(pairs):
+        if i == j:
+            phi[:, k] = lam[:, i] * (2.0 * lam[:, i] - 1.0)
+            dphi[:, k, i] = 4.0 * lam[:, i] - 1.0
+        else:
+            phi[:, k] = 4.0 * lam[:, i] * lam[:, j]
+            dphi[:, k, i] = 4.0 * lam[:, j]
+            dphi[:, k, j] = 4.0 * lam[:, i]
+    X = np.stack([axes[d][cells[:, :, d]] for d in range(dim)], axis=-1)
+    J = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))
+    detJ = np.abs(np.linalg.det(J))
+    Jinv = np.linalg.inv(J)
+    glam = np.concatenate([-Jinv.sum(axis=1, keepdims=True), Jinv], axis=1)
+    gphi = np.einsum("qbi,eid->eqbd", dphi, glam)
+    w = wq[None, :] * detJ[:, None]
+    mass = np.einsum("eq,qa,qb->eab", w, phi, phi)
+    stiff = np.einsum("eq,eqad,eqbd->eab", w, gphi, gphi)
+    node = np.zeros((cells.shape[0], 6), dtype=np.int64)
+    for k, (i, j) in enumerate(pairs):
+        node[:, k] = (((cells[:, i, :] + cells[:, j, :]) // 2) * strides[None, :]).sum(axis=1)
+    r = np.broadcast_to(node[:, :, None], mass.shape).ravel()
+    c = np.broadcast_to(node[:, None, :], mass.shape).ravel()
+    K = sp.coo_matrix((stiff.ravel(), (r, c)), shape=(n, n)).tocsr()
+    M = sp.coo_matrix((mass.ravel(), (r, c)), shape=(n, n)).tocsr()
+    idx = np.stack(np.meshgrid(np.arange(fine_shape[0]), np.arange(fine_shape[1]), indexing="ij"), -1).reshape(-1, 2)
+    on_bnd = (idx[:, 0] == 0) | (idx[:, 0] == fine_shape[0] - 1) | (idx[:, 1] == 0) | (idx[:, 1] == fine_shape[1] - 1)
+    bc = np.nonzero(on_bnd)[0]
+    K = _apply_identity_rows_cols(K, bc)
+    M = _apply_identity_rows_cols(M, bc)
+    coords = np.stack([axes[0][idx[:, 0]], axes[1][idx[:, 1]]], axis=1)
+    return Pencil(A=_canonical(K), M=_canonical(M), dofs_u=np.arange(n), dofs_p=np.zeros(0, np.int64),
+                  dirichlet=bc.astype(np.int64), coords=coords, meta=dict(kind="membrane", a=a, b=b, shape=shape))
+
+
+def membrane_analytic(count: int, a: float = 1.0, b: float = 1.0) -> np.ndarray:
+    """First `count` analytic eigenvalues pi^2 (m^2/a^2 + n^2/b^2), m, n >= 1, ascending."""
+    vals = sorted(np.pi**2 * (m * m / a**2 + n * n / b**2) for m in range(1, 40) for n in range(1, 40))
+    return np.array(vals[:count])
