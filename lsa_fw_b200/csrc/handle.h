@@ -131,6 +131,7 @@ struct lsa_handle_impl {
   int X_cols = 0;
   lsa_eigs_params last_params{};
   lsa_counters counters{};
+  long long launch_count = 0;      // kernels launched (running total)
 };
 
 }  // namespace lsa

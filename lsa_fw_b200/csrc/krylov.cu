@@ -418,8 +418,11 @@ __global__ void k_ritz_vectors(const z128* __restrict__ S, int ld, int nc, z128*
 // ------------------------------------------------------------------------------------- OP and driver
 
 static void solve_dispatch(lsa_handle_impl& h, int trans, z128* x, int* nk) {
-  if (h.scalar == LSA_C128) solve_permuted<z128>(h, trans, x, nk);
-  else solve_permuted<double>(h, trans, x, nk);
+  int local = 0;
+  if (h.scalar == LSA_C128) solve_permuted<z128>(h, trans, x, &local);
+  else solve_permuted<double>(h, trans, x, &local);
+  h.launch_count += local;
+  if (nk) *nk += local;
 }
 
 // x <- F^-1 x (or F^-H x) with optional iterative refinement against F = alpha A + beta M.
@@ -532,6 +535,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   if (p.adjoint) sigma = conj_(sigma);
 
   EventTimer t_all(st), t_spmv(st), t_solve(st), t_ortho(st), t_rr(st), t_restart(st);
+  const long long launches0 = h.launch_count;
   const size_t e_all = t_all.begin();
 
   LSA_CUDA(cudaMemsetAsync(S, 0, sizeof(z128) * (size_t)ld * ncv, st));
@@ -573,6 +577,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V + (long long)(j + 1) * ldv, h.d_npart, blocks, nullptr,
                                           scol + j + 1, scol, jj, h.d_flag, j);
       LSA_LAUNCH_CHECK();
+      h.launch_count += 8;  // spmv + 7 orthogonalisation kernels
       t_ortho.end(e);
     }
     // ---- breakdown check (one small read-back per restart)
@@ -593,6 +598,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
     size_t e = t_rr.begin();
     k_rr<<<1, 128, 0, st>>>(S, Q, rp, h.d_theta, h.d_resid, h.d_brow, h.d_ywork, h.d_rr);
     LSA_LAUNCH_CHECK();
+    h.launch_count += 3;  // rr + restart gemm + copy
     t_rr.end(e);
     LSA_CUDA(cudaMemcpyAsync(&info, h.d_rr, sizeof(RrInfo), cudaMemcpyDeviceToHost, st));
     LSA_CUDA(cudaStreamSynchronize(st));
@@ -689,7 +695,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   out.seconds_ortho = t_ortho.total_seconds();
   out.seconds_rr = t_rr.total_seconds();
   out.seconds_restart = t_restart.total_seconds();
-  out.n_kernels = 0;
+  out.n_kernels = (int)(h.launch_count - launches0);
 }
 
 // ||A x - lambda M x|| / (||A||_F ||x||) for every returned pair (original ordering)

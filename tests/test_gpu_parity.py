@@ -1,0 +1,322 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the reference-facing API and
+the C ABI, against the SciPy oracle, the reference's golden known answers and size-independent
+properties.  Tolerances are the north star's: eigenvalues 1e-8 relative, residuals
+||A x - lambda M x|| / (||A||_F ||x||) <= 1e-10."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import lsa_fw_b200 as L
+from lsa_fw_b200 import _lib, pencils
+from oracle import eigen_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+EIG_RTOL = 1e-8
+RESID_BAR = 1e-10
+
+
+def _mat(a):
+    return L.iPETScMatrix.from_matrix(np.asarray(a, dtype=float)) if a is not None else None
+
+
+def _solver(c, **kw):
+    cfg = L.EigensolverConfig(num_eig=c["num_eig"], problem_type=L.iEpsProblemType[c["problem_type"]], atol=c["atol"],
+                              max_it=c["max_it"])
+    return L.EigenSolver(cfg, A=_mat(c["A"]), M=_mat(c["M"]), **kw)
+
+
+def _vec(v):
+    a = v.real.as_array()
+    return a if v.imag is None else a + 1j * v.imag.as_array()
+
+
+# ------------------------------------------------------------------ reference known-answer tests
+@pytest.mark.parametrize("name", ["diag3_standard", "diag3_generalized_identity", "random_spd5", "repeated_223"])
+def test_kat_sorted_eigenvalues(golden, name):
+    c = golden["cases"][name]
+    pairs = _solver(c).solve()
+    found = sorted(val for val, _ in pairs)          # floats for Hermitian problem types
+    tol = dict(abs=c["abs_tol"]) if "abs_tol" in c else dict(rel=c["rel_tol"])
+    assert found == pytest.approx(c["expected_sorted"], **tol)
+    for _, vec in pairs:
+        assert vec.norm() == pytest.approx(1.0, abs=1e-12)       # test_eigen.py:231-239
+        assert vec.real.size == 3 or vec.real.size == 5
+    if "rank" in c:
+        V = np.vstack([_vec(v) for _, v in pairs]).T
+        assert np.linalg.matrix_rank(V) == c["rank"]
+
+
+def test_kat_jordan_block(golden):
+    c = golden["cases"]["jordan2"]
+    vals = sorted(val.real for val, _ in _solver(c).solve())
+    assert vals == pytest.approx(c["expected_sorted_real"], abs=c["abs_tol"])
+
+
+def test_kat_complex_pair_in_real_mode(golden):
+    c = golden["cases"]["complex_pair"]
+    pairs = _solver(c).solve()
+    (val1, vec1), (val2, vec2) = sorted(pairs, key=lambda p: p[0].imag)
+    assert val1 == pytest.approx(complex(*c["expected_by_imag"][0]), abs=c["abs_tol"])
+    assert val2 == pytest.approx(complex(*c["expected_by_imag"][1]), abs=c["abs_tol"])
+    for vec, ratio in ((vec1, c["ratios_by_imag"][0]), (vec2, c["ratios_by_imag"][1])):
+        assert vec.imag is not None                   # real mode returns (vr, vi), Solver/utils.py:280-291
+        arr = _vec(vec)
+        assert arr[0] / arr[1] == pytest.approx(complex(*ratio), abs=c["abs_tol"])
+
+
+def test_kat_smallest_magnitude_alias(golden):
+    c = golden["cases"]["smallest_magnitude_alias"]
+    es = _solver(c)
+    es.solver.set_which_eigenpairs(L.iEpsWhich.SMALLEST_MAGNITUDE)
+    es.solve()
+    found = sorted(val for val, _ in es.solver.get_all_eigenpairs_up_to(2))
+    assert found == pytest.approx(c["first_two_sorted"], abs=c["abs_tol"])
+
+
+def test_kat_shift_invert_epsilon(golden):
+    c = golden["cases"]["shift_invert_epsilon"]
+    es = _solver(c)
+    es.solver.set_st_type(L.iSTType.SINVERT)
+    es.solver.set_target(c["target"])
+    found = sorted(float(v.real) for v, _ in es.solve())
+    assert found == pytest.approx(c["expected_sorted"], rel=c["rel_tol"])
+
+
+def test_kat_singular_m_raises(golden):
+    c = golden["cases"]["singular_m_raises"]
+    with pytest.raises(L.LsaError):
+        _solver(c).solve()
+
+
+def test_real_eigenvector_has_no_imaginary_part(golden):
+    c = dict(golden["cases"]["diag3_standard"], problem_type="GNHEP", num_eig=2)
+    for _, vec in _solver(c).solve():
+        assert isinstance(vec, L.iComplexPETScVector) and vec.imag is None and vec.real.size == 3
+
+
+def test_membrane_table_of_the_reference(golden):
+    g = golden["membrane"]
+    pm = pencils.membrane_pencil(*g["mesh"], g["a"], g["b"])
+    cfg = L.EigensolverConfig(num_eig=22, problem_type=L.iEpsProblemType.GHEP, atol=1e-12, max_it=200)
+    es = L.EigenSolver(L.iPETScMatrix(pm.A), L.iPETScMatrix(pm.M), cfg, check_hermitian=False)
+    es.solver.set_st_type(L.iSTType.SINVERT)
+    es.solver.set_target(15.0)
+    lam = np.sort([v for v, _ in es.solve()])
+    lam = lam[np.abs(lam - 1.0) > 1e-6][: g["modes"]]
+    ana = pencils.membrane_analytic(g["modes"], g["a"], g["b"])
+    err = np.abs(lam - ana) / ana
+    assert err[:3] == pytest.approx(g["rel_err_first3"], rel=2e-2)
+    assert err.mean() == pytest.approx(g["rel_err_mean"], rel=2e-2)
+
+
+# ------------------------------------------------------------------ linearised Navier-Stokes pencils
+def _ns(kind):
+    if kind == "th2d":
+        return pencils.assemble_pencil((24, 12), (8.0, 3.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.5)), 0.05 + 0.6j
+    if kind == "mini2d":
+        return pencils.assemble_pencil((20, 12), (8.0, 3.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.5), space="MINI"), 0.05 + 0.6j
+    if kind == "th3d":
+        return pencils.cavity_3d(6), 0.1 + 0.3j
+    if kind == "th2d_real":
+        return pencils.assemble_pencil((24, 12), (8.0, 3.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.5)), -0.3
+    raise ValueError(kind)
+
+
+def _run(pc, sigma, nev=6, ncv=40, tol=1e-11, adjoint=False, **opts):
+    cfg = L.EigensolverConfig(num_eig=nev, atol=tol, max_it=200, ncv=ncv)
+    es = L.EigenSolver(L.iPETScMatrix(pc.A), L.iPETScMatrix(pc.M), cfg, check_hermitian=False)
+    es.solver.set_st_type(L.iSTType.SINVERT)
+    es.solver.set_target(sigma)
+    es.solver.set_st_pc_type(L.PreconditionerType.LU)
+    es.solver.set_backend_options(leaf_size=32, **opts)
+    es.solver.set_adjoint(adjoint)
+    return es, es.solve()
+
+
+def _match(lam, ref):
+    return max(min(abs(l - ref)) / abs(l) for l in lam)
+
+
+@pytest.mark.parametrize("kind", ["th2d", "mini2d", "th3d", "th2d_real"])
+@pytest.mark.parametrize("use_coords", [False, True], ids=["graph", "geometric"])
+def test_eigenpairs_match_oracle(kind, use_coords):
+    pc, sigma = _ns(kind)
+    es, pairs = _run(pc, sigma, coords=pc.coords if use_coords else None)
+    assert len(pairs) == 6
+    lam = np.array([p[0] for p in pairs])
+    orc = O.shift_invert_krylov_schur(pc.A, pc.M, sigma, 8, ncv=40, tol=1e-12)
+    assert _match(lam, orc.eigenvalues) < EIG_RTOL
+    # `which` order: increasing |lambda - sigma| (TARGET_MAGNITUDE default under sinvert)
+    assert np.all(np.diff(np.abs(lam - sigma)) >= -1e-9 * np.abs(lam[:-1] - sigma))
+    X = np.stack([_vec(v) for _, v in pairs], axis=1)
+    assert np.linalg.norm(X, axis=0) == pytest.approx(1.0, abs=1e-12)
+    assert O.north_star_residuals(pc.A, pc.M, lam, X).max() < RESID_BAR
+    assert es.solver.get_residuals()[:6].max() < RESID_BAR
+    complex_mode = isinstance(sigma, complex)
+    assert all((v.imag is None) for _, v in pairs) if complex_mode else True
+    assert es.solver.stats["n_perturbed"] == 0
+    # eigenvectors agree with the oracle up to phase (simple eigenvalues only)
+    for i, l in enumerate(lam):
+        j = int(np.argmin(abs(orc.eigenvalues - l)))
+        others = np.delete(orc.eigenvalues, j)
+        if min(abs(others - l)) > 1e-6:
+            assert abs(np.vdot(orc.eigenvectors[:, j], X[:, i])) == pytest.approx(1.0, abs=1e-6)
+
+
+def test_adjoint_modes_reuse_the_factorisation():
+    """Sensitivity/__init__.py:230-311: left eigenvectors at conj(sigma); here on the same LU."""
+    pc, sigma = _ns("th2d")
+    A, M = L.iPETScMatrix(pc.A), L.iPETScMatrix(pc.M)
+    cfg = L.EigensolverConfig(num_eig=5, atol=1e-11, max_it=200, ncv=40)
+    es = L.EigenSolver(A, M, cfg, check_hermitian=False)
+    es.solver.set_st_type(L.iSTType.SINVERT)
+    es.solver.set_target(sigma)
+    es.solver.set_st_pc_type(L.PreconditionerType.LU)
+    pairs = es.solve()
+    lam, v = min(pairs, key=lambda p: abs(p[0] - sigma))
+    # drop-in form: explicit Hermitian transposes, target conj(sigma), TARGET_REAL (Sensitivity :246-262)
+    es_adj = L.EigenSolver(A.H, M.H, cfg, check_hermitian=False)
+    es_adj.solver.set_st_type(L.iSTType.SINVERT)
+    es_adj.solver.set_st_pc_type(L.PreconditionerType.LU)
+    es_adj.solver.set_target(np.conj(sigma))
+    es_adj.solver.set_which_eigenpairs(L.iEpsWhich.TARGET_REAL)
+    pairs_adj = es_adj.solve()
+    assert es_adj.solver.stats.get("reused_factorisation") is True
+    lam_adj, a = min(pairs_adj, key=lambda p: abs(p[0] - np.conj(lam)))
+    assert lam_adj == pytest.approx(np.conj(lam), rel=EIG_RTOL)
+    av, vv = _vec(a), _vec(v)
+    AH, MH = pc.A.conj().T.tocsr(), pc.M.conj().T.tocsr()
+    assert np.linalg.norm(AH @ av - lam_adj * (MH @ av)) / (np.sqrt((pc.A.data**2).sum()) * np.linalg.norm(av)) < RESID_BAR
+    # bi-orthonormalisation a^H M v = 1 (Sensitivity :280-287)
+    prod = a.dot(L.iPETScVector(pc.M @ vv))
+    assert abs(prod) > 1e-8
+    a.scale(1.0 / prod)
+    assert a.dot(L.iPETScVector(pc.M @ vv)) == pytest.approx(1.0, abs=1e-10)
+    # explicit-matrix route without reuse gives the same eigenvalue
+    es2 = L.EigenSolver(L.iPETScMatrix(AH), L.iPETScMatrix(MH), cfg, check_hermitian=False)
+    es2.solver.set_st_type(L.iSTType.SINVERT)
+    es2.solver.set_target(np.conj(sigma))
+    lam2 = min((p[0] for p in es2.solve()), key=lambda z: abs(z - np.conj(lam)))
+    assert lam2 == pytest.approx(lam_adj, rel=EIG_RTOL)
+
+
+def test_symbolic_analysis_is_reused_across_shifts_and_reynolds():
+    L.clear_symbolic_cache()
+    base = dict(shape=(24, 12), lengths=(8.0, 3.0), baseflow=pencils.wake_profile(0.9, 1.2, 1.5))
+    cached = []
+    for re_, sigma in ((40.0, 0.02 + 0.55j), (50.0, 0.05 + 0.6j), (60.0, 0.06 + 0.62j)):
+        pc = pencils.assemble_pencil(base["shape"], base["lengths"], re=re_, baseflow=base["baseflow"])
+        es, pairs = _run(pc, sigma, nev=4, ncv=30)
+        cached.append(es.solver.stats["symbolic_cached"])
+        lam = np.array([p[0] for p in pairs])
+        orc = O.shift_invert_arpack(pc.A, pc.M, sigma, 6, ncv=30, tol=1e-12)
+        assert _match(lam, orc.eigenvalues) < EIG_RTOL
+    assert cached == [False, True, True]
+
+
+# ------------------------------------------------------------------ C-ABI level kernels
+@pytest.fixture(scope="module")
+def factored():
+    pc = pencils.assemble_pencil((30, 16), (8.0, 3.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.5))
+    sigma = 0.05 + 0.6j
+    h = _lib.Handle(pc.n, 0)
+    flag = ((pc.A.diagonal() - sigma * pc.M.diagonal()) == 0).astype(np.uint8)
+    h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=32, order_last=flag)
+    h.set_values(pc.A.data, pc.M.data)
+    fs = h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
+    yield pc, sigma, h, fs
+    h.close()
+
+
+def test_triangular_solves_all_modes(factored):
+    pc, sigma, h, fs = factored
+    assert fs.n_perturbed == 0 and fs.min_pivot > 0
+    C = (pc.A - sigma * pc.M).tocsc()
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(pc.n) + 1j * rng.standard_normal(pc.n)
+    for trans, op in ((_lib.LSA_OP_N, C), (_lib.LSA_OP_T, C.T), (_lib.LSA_OP_H, C.conj().T)):
+        x = h.solve(b, trans)
+        assert np.linalg.norm(op @ x - b) / np.linalg.norm(b) < 1e-12
+        x = h.solve(b, trans, refine_steps=1)
+        assert np.linalg.norm(op @ x - b) / np.linalg.norm(b) < 1e-13
+    import scipy.sparse.linalg as spla
+
+    xs = spla.splu(C).solve(b)
+    assert np.linalg.norm(h.solve(b) - xs) / np.linalg.norm(xs) < 1e-10
+
+
+def test_spmv_all_operators(factored):
+    pc, _, h, _ = factored
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal(pc.n) + 1j * rng.standard_normal(pc.n)
+    for which, mat in ((_lib.LSA_MAT_A, pc.A), (_lib.LSA_MAT_M, pc.M)):
+        for trans, op in ((_lib.LSA_OP_N, mat), (_lib.LSA_OP_T, mat.T), (_lib.LSA_OP_H, mat.conj().T)):
+            y = h.spmv(which, x, trans)
+            assert np.linalg.norm(y - op @ x) <= 1e-14 * np.linalg.norm(op @ x)
+
+
+def test_real_factor_with_complex_vectors():
+    pc, _ = _ns("th2d")
+    h = _lib.Handle(pc.n, 0)
+    h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=32,
+              order_last=((pc.A.diagonal() + 0.3 * pc.M.diagonal()) == 0).astype(np.uint8))
+    h.set_values(pc.A.data, pc.M.data)
+    fs = h.factor(1.0, 0.3, _lib.LSA_F64, 1e-13)
+    assert fs.scalar == _lib.LSA_F64
+    C = (pc.A + 0.3 * pc.M).tocsc()
+    rng = np.random.default_rng(7)
+    b = rng.standard_normal(pc.n) + 1j * rng.standard_normal(pc.n)
+    for trans, op in ((_lib.LSA_OP_N, C), (_lib.LSA_OP_H, C.T)):
+        assert np.linalg.norm(op @ h.solve(b, trans) - b) / np.linalg.norm(b) < 1e-12
+    with pytest.raises(_lib.LsaError):
+        h.factor(1.0, 0.3j, _lib.LSA_F64, 1e-13)
+    h.close()
+
+
+def test_dense_schur_kernel_and_gemm_tiles():
+    h = _lib.Handle(4, 0)
+    rng = np.random.default_rng(8)
+    for m in (1, 2, 7, 40, 80, 120):
+        S0 = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
+        T, Q = h.dense_schur(S0, "SMALLEST_REAL")
+        assert np.abs(Q @ T @ Q.conj().T - S0).max() < 1e-12 * m
+        assert np.abs(np.tril(T, -1)).max() == 0 and np.all(np.diff(np.diag(T).real) >= -1e-10)
+    for scalar in (_lib.LSA_F64, _lib.LSA_C128):
+        for (m, n, k) in ((1, 1, 1), (64, 64, 32), (65, 63, 33), (200, 130, 70), (33, 257, 19)):
+            _, err = h.gemm_bench(scalar, m, n, k, 1)
+            assert 0 <= err < 1e-12 * k
+    h.close()
+
+
+def test_tiny_pivot_replacement_counts_and_zero_pivot_error():
+    A = sp.csr_matrix(np.array([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 0.0]]))
+    h = _lib.Handle(3, 0)
+    h.analyze(A.indptr, A.indices)
+    h.set_values(A.data, None)
+    with pytest.raises(_lib.LsaError) as e:
+        h.factor(1.0, 0.0, _lib.LSA_F64, 0.0)
+    assert e.value.status == -3
+    fs = h.factor(1.0, 0.0, _lib.LSA_F64, 1e-10)
+    assert fs.n_perturbed >= 1
+    h.close()
+
+
+# ------------------------------------------------------------------ BASELINE config 1 at full size
+def test_config1_full_size_properties_and_oracle():
+    """2-D wake pencil, 50 303 DOFs, complex shift, nev = 10, ncv = 80 (.examples/eigenvalues.py path)."""
+    pc = pencils.cylinder_wake_2d()
+    sigma = 0.05 + 0.74j
+    es, pairs = _run(pc, sigma, nev=10, ncv=80, tol=1e-10)
+    assert len(pairs) == 10
+    lam = np.array([p[0] for p in pairs])
+    X = np.stack([_vec(v) for _, v in pairs], axis=1)
+    assert O.north_star_residuals(pc.A, pc.M, lam, X).max() < RESID_BAR
+    assert es.solver.get_residuals()[:10].max() < RESID_BAR
+    orc = O.shift_invert_arpack(pc.A, pc.M, sigma, 12, ncv=80, tol=1e-12)
+    assert _match(lam, orc.eigenvalues) < EIG_RTOL
+    # the adjoint spectrum is the conjugate spectrum (size-independent property)
+    es2, pairs2 = _run(pc, sigma, nev=10, ncv=80, tol=1e-10, adjoint=True)
+    lam2 = np.array([p[0] for p in pairs2])
+    assert _match(np.conj(lam2), lam) < EIG_RTOL or _match(np.conj(lam2[:8]), orc.eigenvalues) < EIG_RTOL

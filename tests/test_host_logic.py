@@ -1,0 +1,296 @@
+"""CPU tests of the host side: C-ABI surface, symbolic phase, Rayleigh-Ritz core, Python boundary."""
+
+import ctypes
+import logging
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import lsa_fw_b200 as L
+from lsa_fw_b200 import _lib, pencils
+from mf_emulator import Emulator
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------- C ABI
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "lsa_b200.h")).read()
+    declared = set(re.findall(r"\b(lsa_[a-z_0-9]+)\s*\(", header))
+    assert declared >= set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/lsa_b200.h but not exported"
+    assert b"sm_100a" in lib.lsa_version()
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.SymbolicInfo) == 4 * 8 + 8 * 7 + 8 + 32
+    assert ctypes.sizeof(_lib.EigsParams) == 8 * 4 + 8 * 3 + 8 + 8
+    assert ctypes.sizeof(_lib.FactorStats) == 8 * 4 + 8 + 16
+
+
+def test_numeric_entry_points_fail_loudly_without_device():
+    h = _lib.Handle(3, device=-1)
+    a = sp.identity(3, format="csr")
+    h.analyze(a.indptr, a.indices)
+    with pytest.raises(_lib.LsaError):
+        h.set_values(a.data, None)
+
+
+# ------------------------------------------------------------------------------- symbolic phase
+CASES = [
+    ("th2d", dict(shape=(12, 8), lengths=(6.0, 2.0)), {}),
+    ("th3d", dict(shape=(5, 4, 3), lengths=(2.0, 1.0, 1.0)), {}),
+    ("cavity3d", dict(shape=(5, 5, 5), lengths=(1.0, 1.0, 1.0)),
+     dict(dirichlet_faces=("x0", "x1", "y0", "y1", "z0", "z1"), pin_pressure=True)),
+    ("mini2d", dict(shape=(16, 10), lengths=(6.0, 2.0)), dict(space="MINI")),
+]
+
+
+@pytest.mark.parametrize("name,geo,kw", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("use_coords", [False, True], ids=["graph", "geometric"])
+def test_symbolic_structures_drive_a_correct_multifrontal_lu(name, geo, kw, use_coords):
+    pc = pencils.assemble_pencil(geo["shape"], geo["lengths"], re=40.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.0), **kw)
+    n, sigma = pc.n, 0.1 + 0.6j
+    h = _lib.Handle(n, device=-1)
+    flag = ((pc.A.diagonal() - sigma * pc.M.diagonal()) == 0).astype(np.uint8)
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=24,
+                     coords=pc.coords if use_coords else None, order_last=flag)
+    perm = h.symbolic_array("perm")
+    assert sorted(perm.tolist()) == list(range(n))
+    parent, level = h.symbolic_array("parent"), h.symbolic_array("level")
+    has_parent = parent >= 0
+    assert np.all(level[has_parent] == level[parent[has_parent]] + 1) and np.all(level[~has_parent] == 0)
+    assert np.all(parent[has_parent] > np.nonzero(has_parent)[0])          # postorder
+    st_ptr, st_idx, sn_ptr = h.symbolic_array("st_ptr"), h.symbolic_array("st_idx"), h.symbolic_array("sn_ptr")
+    for s in range(info.n_fronts):
+        rows = st_idx[st_ptr[s]:st_ptr[s + 1]]
+        assert np.all(np.diff(rows) > 0) and (len(rows) == 0 or rows[0] >= sn_ptr[s + 1])
+    assert info.n_decoupled == len(pc.dirichlet) + len(pc.meta["pinned"])
+    em = Emulator(h, n)
+    em.factor(pc.A.data, pc.M.data, 1.0, -sigma)
+    C = (pc.A - sigma * pc.M).tocsc()
+    b = np.random.default_rng(0).standard_normal(n) + 1j * np.random.default_rng(1).standard_normal(n)
+    assert np.linalg.norm(C @ em.solve(b) - b) / np.linalg.norm(b) < 1e-11
+    assert np.linalg.norm(C.conj().T @ em.solve(b, "H") - b) / np.linalg.norm(b) < 1e-11
+
+
+def test_symbolic_counters_and_pattern_reuse():
+    pc = pencils.assemble_pencil((20, 10), (6.0, 2.0), re=40.0)
+    h = _lib.Handle(pc.n, device=-1)
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=32)
+    k, r = h.symbolic_array("front_k").astype(float), h.symbolic_array("front_r").astype(float)
+    assert info.nnz_lu == int((k * k + 2 * k * r).sum()) + info.n_decoupled
+    assert info.flops_real == pytest.approx((2 / 3 * k**3 + 2 * k * k * r + 2 * k * r * r).sum())
+    assert k.sum() + info.n_decoupled == pc.n
+    a_dst, m_dst = h.symbolic_array("a_dst"), h.symbolic_array("m_dst")
+    assert len(np.unique(a_dst)) == len(a_dst) == pc.A.nnz and len(m_dst) == pc.M.nnz
+    assert a_dst.max() < info.factor_entries
+
+
+# ------------------------------------------------------------------------------- Rayleigh-Ritz core
+@pytest.fixture(scope="module")
+def rr_lib():
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "librr_host.so")
+    src = os.path.join(ROOT, "tests", "csrc", "rr_host.cpp")
+    hdr = os.path.join(ROOT, "lsa_fw_b200", "csrc", "rr_core.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+                               "-x", "c++", src, "-o", so])
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 5, 17, 80])
+def test_rr_schur_form(rr_lib, m):
+    rng = np.random.default_rng(m)
+    S0 = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
+    S, Q = np.asfortranarray(S0.copy()), np.zeros((m, m), complex, order="F")
+    assert rr_lib.rr_host_schur(m, m, 0, _p(S), _p(Q)) == 0
+    assert np.abs(Q @ S @ Q.conj().T - S0).max() < 1e-12 * max(1, np.abs(S0).max()) * m
+    assert np.abs(np.tril(S, -1)).max() == 0.0
+    assert np.abs(Q.conj().T @ Q - np.eye(m)).max() < 1e-13 * m
+    assert np.sort_complex(np.diag(S)) == pytest.approx(np.sort_complex(np.linalg.eigvals(S0)), abs=1e-10)
+
+
+def test_rr_defective_and_repeated(rr_lib):
+    for S0 in (np.array([[1, 1], [0, 1]], complex), np.diag([2.0, 2.0, 3.0]).astype(complex)):
+        m = S0.shape[0]
+        S, Q = np.asfortranarray(S0.copy()), np.zeros((m, m), complex, order="F")
+        assert rr_lib.rr_host_schur(m, m, 0, _p(S), _p(Q)) == 0
+        assert np.abs(Q @ S @ Q.conj().T - S0).max() < 1e-14
+
+
+@pytest.mark.parametrize("which,key", [(1, lambda l, s: -abs(l)), (3, lambda l, s: -l.real), (4, lambda l, s: l.real),
+                                       (7, lambda l, s: abs(l - s)), (8, lambda l, s: abs(l.real - s.real))])
+def test_rr_full_ordering_locking_and_restart(rr_lib, which, key):
+    rng = np.random.default_rng(7)
+    m, ld, nconv, nev, sigma = 30, 31, 3, 6, 0.2 + 0.5j
+    S = np.zeros((ld, m), complex, order="F")
+    S[:m, :] = np.triu(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)), -1)
+    S[nconv:, :nconv] = 0.0                       # locked block is triangular and decoupled
+    S[:nconv, :nconv] = np.triu(S[:nconv, :nconv])
+    S[m, m - 1] = 0.37
+    S0 = S.copy()
+    Q, theta, resid, out = np.zeros((m, m), complex, order="F"), np.zeros(m, complex), np.zeros(m), np.zeros(4, np.int32)
+    rr_lib.rr_host_full(m, ld, nconv, nev, which, 1, 0, ctypes.c_double(1e-30), ctypes.c_double(sigma.real),
+                        ctypes.c_double(sigma.imag), ctypes.c_double(1.0), _p(S), _p(Q), _p(theta), _p(resid),
+                        out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    k, keep, status = out[:3]
+    assert status == 0 and k == nconv and keep == nconv + (m - nconv) // 2
+    assert np.abs(Q[:nconv, :nconv] - np.eye(nconv)).max() == 0 and np.abs(Q[:nconv, nconv:]).max() == 0
+    lam = sigma + 1.0 / theta[nconv:]
+    keys = np.array([key(l, sigma) for l in lam])
+    assert np.all(np.diff(keys) >= -1e-12)        # active block ordered by `which` on lambda = sigma + 1/theta
+    T = Q.conj().T @ S0[:m, :m] @ Q
+    assert np.abs(T[:keep, :keep] - S[:keep, :keep]).max() < 1e-12
+    assert np.abs(S[keep, nconv:keep] - 0.37 * Q[m - 1, nconv:keep]).max() < 1e-13   # coupling row
+    assert np.abs(S[keep, :nconv]).max() == 0 and np.abs(S[:, keep:]).max() == 0 and np.abs(S[keep + 1:, :]).max() == 0
+    # residual estimate of the first active Ritz pair: beta |e_m^T Q y|
+    w, Y = np.linalg.eig(T[:nconv + 1, :nconv + 1])
+    y = Y[:, np.argmin(abs(w - theta[nconv]))]
+    assert resid[nconv] == pytest.approx(abs(0.37 * Q[m - 1, :nconv + 1] @ y) / np.linalg.norm(y), rel=1e-8)
+
+
+# ------------------------------------------------------------------------------- Python boundary
+def test_enums_keep_reference_names_and_alias():
+    assert L.iEpsWhich.SMALLEST_MAGNITUDE is L.iEpsWhich.LARGEST_REAL      # Solver/utils.py:157-158
+    assert [m.name for m in L.iEpsProblemType] == ["HEP", "NHEP", "GHEP", "GNHEP", "PGNHEP", "GHIEP"]
+    assert L.iEpsProblemType.from_string("gnhep") is L.iEpsProblemType.GNHEP
+    with pytest.raises(ValueError):
+        L.iEpsProblemType.from_string("nope")
+    assert L.iEpsWhich.LARGEST_REAL.to_arpack() == "LR"
+    with pytest.raises(ValueError):
+        L.iEpsWhich.TARGET_REAL.to_arpack()
+    assert {t.name for t in L.iSTType} == {"SHELL", "SHIFT", "SINVERT", "CAYLEY", "PRECOND", "FILTER"}
+
+
+def test_config_defaults_and_solver_properties():
+    cfg = L.EigensolverConfig()
+    assert (cfg.num_eig, cfg.problem_type, cfg.atol, cfg.max_it, cfg.ncv) == (5, L.iEpsProblemType.GNHEP, 1e-6, 500, 80)
+    A = L.iPETScMatrix.from_matrix(np.diag([1.0, 1.5, -42.0]))
+    cfg = L.EigensolverConfig(num_eig=3, problem_type=L.iEpsProblemType.GHEP, atol=1e-3, max_it=100)
+    for es in (L.EigenSolver(cfg, A=A), L.EigenSolver(A, None, cfg), L.EigenSolver(A, cfg=cfg), L.EigenSolver(cfg, A)):
+        assert es.config is cfg and isinstance(es.solver, L.iEpsSolver)      # test_eigen.py:87-104
+        assert es.solver.raw.getTolerances() == (cfg.atol, cfg.max_it)
+        assert es.solver.raw.getDimensions()[0] == cfg.num_eig
+        assert es.solver.raw.getProblemType() == cfg.problem_type.to_slepc()
+
+
+def test_constructor_validation():
+    A = L.iPETScMatrix.from_matrix(np.ones((2, 3)))
+    with pytest.raises(ValueError, match="must be square"):
+        L.EigenSolver(A)
+    with pytest.raises(ValueError, match="does not match"):
+        L.EigenSolver(L.iPETScMatrix.from_matrix(np.eye(3)), L.iPETScMatrix.from_matrix(np.eye(2)))
+    with pytest.raises(ValueError):
+        L.iEpsSolver(M=L.iPETScMatrix.from_matrix(np.eye(3)))                  # test_eigen.py:81-84
+    with pytest.raises(TypeError):
+        L.EigenSolver()
+
+
+def test_hermitian_warning(caplog):
+    caplog.set_level(logging.WARNING)
+    A = L.iPETScMatrix.from_matrix(np.diag([1.0, 1.5, -42.0]))
+    A[0, 1] = 0.1
+    A.assemble()
+    L.EigenSolver(L.EigensolverConfig(problem_type=L.iEpsProblemType.GHEP), A=A)
+    assert any("assumes Hermitian A" in r.getMessage() for r in caplog.records)   # test_eigen.py:188-200
+
+
+@pytest.mark.parametrize("pc_type", list(L.PreconditionerType))
+def test_set_st_pc_type_round_trip(pc_type):
+    s = L.iEpsSolver(A=L.iPETScMatrix.from_matrix(np.diag([1.0, 1.5, -42.0])))
+    s.set_problem_type(L.iEpsProblemType.HEP)
+    s.set_dimensions(number_eigenpairs=3)
+    s.set_tolerances(atol=1e-8, max_it=50)
+    s.set_st_type(L.iSTType.SINVERT)
+    s.set_target(2.0)
+    s.set_st_pc_type(pc_type)
+    assert s.raw.getST().getKSP().getPC().getType() == pc_type.name.lower()       # test_eigen.py:307-322
+
+
+def test_unsupported_combinations_raise_not_implemented():
+    A = L.iPETScMatrix.from_matrix(np.diag([1.0, 1.5, -42.0]))
+    s = L.iEpsSolver(A)
+    s.set_st_type(L.iSTType.CAYLEY)
+    with pytest.raises(NotImplementedError):
+        s.solve()
+    s = L.iEpsSolver(A)
+    s.set_st_type(L.iSTType.SINVERT)
+    s.set_st_pc_type(L.PreconditionerType.ILU)
+    with pytest.raises(NotImplementedError):
+        s.solve()
+    s = L.iEpsSolver(A)
+    s.set_interval(0.0, 1.0)
+    with pytest.raises(NotImplementedError):
+        s.solve()
+
+
+def test_solve_without_gpu_raises_instead_of_falling_back():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    A = L.iPETScMatrix.from_matrix(np.diag([1.0, 1.5, -42.0]))
+    with pytest.raises(L.LsaError):
+        L.EigenSolver(A).solve()
+
+
+def test_carriers_follow_reference_semantics(tmp_path):
+    v = L.iComplexPETScVector(np.array([3.0, 0.0]), np.array([0.0, 4.0]))
+    assert v.norm() == pytest.approx(5.0) and v.imag is not None
+    w = L.iComplexPETScVector(np.array([1.0, 1.0]))
+    assert v.dot(w) == pytest.approx(np.vdot([3, 4j], [1, 1]))                  # conjugates self
+    v.scale(1j)
+    assert v.as_array() == pytest.approx([3j, -4.0])
+    z = L.iComplexPETScVector(L.iPETScVector(np.array([1 + 1j, 2.0])))          # complex-build flavour
+    assert z.imag is None and z.real.raw.getArray(readonly=True).dtype == np.complex128
+    assert z.dot(L.iPETScVector(np.array([1j, 1.0]))) == pytest.approx(np.vdot([1j, 1.0], [1 + 1j, 2.0]))
+    with pytest.raises(ValueError):
+        z.real.raw.getArray(readonly=True)[0] = 0
+    M = L.iPETScMatrix.from_matrix(np.array([[2.0, 1.0], [0.0, 3.0]]))
+    assert M.shape == (2, 2) and M.nonzero_entries == 3 and M.norm == pytest.approx(np.sqrt(14))
+    assert not M.is_numerically_hermitian() and (M.H.as_array() == M.as_array().T).all()
+    csr = M.as_scipy_array()
+    assert csr.indices.dtype == np.int32 and csr.has_sorted_indices
+    M.export(tmp_path / "m.mtx")
+    assert (L.iPETScMatrix.from_path(tmp_path / "m.mtx").as_array() == M.as_array()).all()
+    M.pin_dof(0)
+    assert (M.as_array() == [[1.0, 0.0], [0.0, 3.0]]).all()
+
+
+# ------------------------------------------------------------------------------- replicas (gloo, world 2)
+def test_shard_tasks():
+    from lsa_fw_b200.replicas import shard_tasks
+
+    assert shard_tasks(8, 0, 2) == [0, 2, 4, 6] and shard_tasks(8, 1, 2) == [1, 3, 5, 7]
+    assert sorted(sum((shard_tasks(11, r, 4) for r in range(4)), [])) == list(range(11))
+
+
+def test_run_sharded_gloo_world_size_2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys\nsys.path.insert(0, %r)\nimport torch.distributed as dist\n"
+        "from lsa_fw_b200.replicas import run_sharded\n"
+        "dist.init_process_group('gloo')\n"
+        "res = run_sharded(list(range(7)), lambda t: (t * t, dist.get_rank()))\n"
+        "assert [r[0] for r in res] == [t * t for t in range(7)], res\n"
+        "assert [r[1] for r in res] == [t %% 2 for t in range(7)], res\n"
+        "dist.destroy_process_group()\nprint('ok', flush=True)\n" % ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
