@@ -647,10 +647,10 @@ int lsa_get_residuals(lsa_handle* h, double* out, int32_t capacity) {
   if (!h || !out) return LSA_ERR_ARG;
   if (int rc = need_device(h)) return rc;
   LSA_API_BEGIN
-  if (capacity < h->nconv) return fail(h, LSA_ERR_ARG, "capacity too small");
+  const int cnt = std::min<int>(capacity, h->nconv);
   if (h->last_params.adjoint) ensure_transposes(*h);
-  residual_norms(*h, out);
-  return h->nconv;
+  residual_norms(*h, out, cnt);
+  return cnt;
   LSA_API_END(h)
   return LSA_ERR_INTERNAL;
 }

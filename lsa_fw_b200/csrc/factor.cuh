@@ -26,6 +26,6 @@ void permute_gather(cudaStream_t st, const z128* src, z128* dst, const int* perm
 void permute_scatter(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n);  // dst[perm[i]] = src[i]
 void gather_values(cudaStream_t st, const void* orig, bool is_complex, const long long* src, void* out, long long nnz);
 void value_norms(lsa_handle_impl& h, const void* vals, bool is_complex, long long nnz, double* fro, double* amax);
-void residual_norms(lsa_handle_impl& h, double* out_host);
+void residual_norms(lsa_handle_impl& h, double* out_host, int count);
 
 }  // namespace lsa

@@ -728,13 +728,13 @@ __global__ void __launch_bounds__(256) k_resid_part(int n, const z128* __restric
   }
 }
 
-void residual_norms(lsa_handle_impl& h, double* out_host) {
+void residual_norms(lsa_handle_impl& h, double* out_host, int count) {
   const int n = h.n, blocks = cdiv(n, 256);
   const bool adj = h.last_params.adjoint != 0;
   std::vector<double> part(2 * (size_t)blocks);
   double* d_part = nullptr;
   LSA_CUDA(cudaMalloc(&d_part, sizeof(double) * 2 * blocks));
-  for (int i = 0; i < h.nconv; ++i) {
+  for (int i = 0; i < count && i < h.nconv; ++i) {
     const int col = h.eig_order[i];
     // work in the permuted ordering: x_p = gather(x)
     permute_gather(h.stream, h.d_X + (long long)col * n, h.d_x, h.d_perm, n);

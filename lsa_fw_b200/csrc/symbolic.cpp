@@ -125,6 +125,118 @@ class Dissector {
     out.sn_sizes.push_back((int)verts.size());
   }
 
+  // Hopcroft-Karp maximum matching + Koenig construction on the cut graph (SL x SR).
+  std::vector<int> min_vertex_cover(const std::vector<int>& SL, const std::vector<int>& SR, int tok) {
+    const int nl = (int)SL.size(), nr = (int)SR.size();
+    if (nl == 0 || nr == 0) return {};
+    // local ids of the right side via db_ (scratch, reset afterwards)
+    for (int j = 0; j < nr; ++j) db_[SR[j]] = -2 - j;
+    std::vector<int> xadj(nl + 1, 0), adj;
+    for (int i = 0; i < nl; ++i) {
+      const int v = SL[i];
+      for (long long e = g_.xadj[v]; e < g_.xadj[v + 1]; ++e) {
+        const int u = g_.adj[e];
+        if (mark_[u] == tok && side_[u] == 1 && db_[u] <= -2) adj.push_back(-2 - db_[u]);
+      }
+      xadj[i + 1] = (int)adj.size();
+    }
+    for (int j = 0; j < nr; ++j) db_[SR[j]] = -1;
+    std::vector<int> matchL(nl, -1), matchR(nr, -1), dist(nl), queue, it(nl);
+    const int INF = 0x3fffffff;
+    auto bfs_layers = [&]() {
+      queue.clear();
+      bool found = false;
+      for (int i = 0; i < nl; ++i) {
+        if (matchL[i] < 0) {
+          dist[i] = 0;
+          queue.push_back(i);
+        } else {
+          dist[i] = INF;
+        }
+      }
+      for (size_t qh = 0; qh < queue.size(); ++qh) {
+        const int i = queue[qh];
+        for (int e = xadj[i]; e < xadj[i + 1]; ++e) {
+          const int i2 = matchR[adj[e]];
+          if (i2 < 0) found = true;
+          else if (dist[i2] == INF) {
+            dist[i2] = dist[i] + 1;
+            queue.push_back(i2);
+          }
+        }
+      }
+      return found;
+    };
+    // iterative DFS along the layered graph
+    std::vector<int> stack;
+    auto try_augment = [&](int root) {
+      stack.clear();
+      stack.push_back(root);
+      while (!stack.empty()) {
+        const int i = stack.back();
+        bool advanced = false;
+        while (it[i] < xadj[i + 1]) {
+          const int j = adj[it[i]++];
+          const int i2 = matchR[j];
+          if (i2 < 0) {
+            // augment along the stack
+            int jj = j;
+            for (int q = (int)stack.size() - 1; q >= 0; --q) {
+              const int ii = stack[q];
+              const int prev = matchL[ii];
+              matchL[ii] = jj;
+              matchR[jj] = ii;
+              jj = prev;
+            }
+            return true;
+          }
+          if (dist[i2] == dist[i] + 1) {
+            stack.push_back(i2);
+            advanced = true;
+            break;
+          }
+        }
+        if (!advanced) {
+          dist[i] = INF;
+          stack.pop_back();
+        }
+      }
+      return false;
+    };
+    while (bfs_layers()) {
+      for (int i = 0; i < nl; ++i) it[i] = xadj[i];
+      for (int i = 0; i < nl; ++i)
+        if (matchL[i] < 0) try_augment(i);
+    }
+    // Koenig: Z = vertices reachable from unmatched left vertices by alternating paths
+    std::vector<char> zl(nl, 0), zr(nr, 0);
+    queue.clear();
+    for (int i = 0; i < nl; ++i)
+      if (matchL[i] < 0) {
+        zl[i] = 1;
+        queue.push_back(i);
+      }
+    for (size_t qh = 0; qh < queue.size(); ++qh) {
+      const int i = queue[qh];
+      for (int e = xadj[i]; e < xadj[i + 1]; ++e) {
+        const int j = adj[e];
+        if (zr[j] || matchL[i] == j) continue;
+        zr[j] = 1;
+        const int i2 = matchR[j];
+        if (i2 >= 0 && !zl[i2]) {
+          zl[i2] = 1;
+          queue.push_back(i2);
+        }
+      }
+    }
+    std::vector<int> cover;
+    for (int i = 0; i < nl; ++i)
+      if (!zl[i]) cover.push_back(SL[i]);
+    for (int j = 0; j < nr; ++j)
+      if (zr[j]) cover.push_back(SR[j]);
+    return cover;
+  }
+
   void rec(std::vector<int>& verts, int depth, NDResult& out) {
     const int nv = (int)verts.size();
     if (nv == 0) return;
@@ -225,8 +337,10 @@ class Dissector {
         }
         if (cut) (sv ? SR : SL).push_back(v);
       }
-      const bool takeR = SR.size() <= SL.size();
-      S = takeR ? SR : SL;
+      // minimum vertex separator for this edge cut = minimum vertex cover of the bipartite graph of
+      // cut edges between the two boundary layers (Koenig's theorem via Hopcroft-Karp matching).
+      // On FE graphs (every element is a clique) this is about half of either boundary layer.
+      S = min_vertex_cover(SL, SR, tok);
       if ((double)S.size() > 0.45 * nv) {
         emit_leaf(verts, out);
         return;

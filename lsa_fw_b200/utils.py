@@ -424,6 +424,9 @@ class iEpsSolver:  # noqa: N801
         else:
             A = _as_csr(self._A)
             M = _as_csr(self._M) if self._M is not None else None
+            if M is None and sinvert:
+                # standard problem: the shifted operator is A - sigma I
+                M = sp.identity(n, dtype=np.float64, format="csr")
             data_complex = np.iscomplexobj(A.data) or (M is not None and np.iscomplexobj(M.data))
             use_complex = data_complex or sigma.imag != 0.0 or self._opts["force_complex"]
             self._complex_mode = use_complex
