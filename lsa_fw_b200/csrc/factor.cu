@@ -21,7 +21,8 @@
 
 namespace lsa {
 
-static constexpr int NB = 32;  // panel width
+static constexpr int NB = 32;   // panel width
+static constexpr int OB = 128;  // outer block: trailing updates beyond it are deferred and done with K = 128
 
 // ------------------------------------------------------------------------------------------ scatter
 
@@ -465,14 +466,20 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
   }
 }
 
-// mode 0: trailing update after panel [j0, j1):
-//           region 1  P[j1:m, j1:k]   -= P[j1:m, j0:j1] * P[j0:j1, j1:k]
-//           region 2  Q[j1:k, 0:r]    -= P[j1:k, j0:j1] * Q[j0:j1, 0:r]
+// Two-level blocking of the partial LU: panels of NB = 32 columns inside outer blocks of OB = 128.
+// mode 0: after panel [j0, j1) of the outer block [ob0, ob1): rank-32 updates of what the next
+//         panels of THIS outer block need
+//           region 1  P[j1:m,   j1:ob1] -= P[j1:m,   j0:j1] * P[j0:j1, j1:ob1]     (panel columns)
+//           region 2  P[j1:ob1, ob1:k]  -= P[j1:ob1, j0:j1] * P[j0:j1, ob1:k]      (U rows, right of the block)
+//           region 3  Q[j1:ob1, 0:r]    -= P[j1:ob1, j0:j1] * Q[j0:j1, 0:r]        (U12 rows)
+// mode 2: after the whole outer block: the bulk of the flops as rank-128 updates
+//           region 1  P[ob1:m, ob1:k]   -= P[ob1:m, ob0:ob1] * P[ob0:ob1, ob1:k]
+//           region 2  Q[ob1:k, 0:r]     -= P[ob1:k, ob0:ob1] * Q[ob0:ob1, 0:r]
 // mode 1: Schur complement  C[0:r, 0:r] -= P[k:m, 0:k] * Q[0:k, 0:r]
 // grid: (tiles, fronts of the level)
 template <class T>
 __global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                    int first, int j0, int mode, T* __restrict__ fac,
+                                                    int first, int j0, int ob0, int mode, T* __restrict__ fac,
                                                     T* __restrict__ pool) {
   constexpr bool CPLX = scalar_traits<T>::is_complex;
   constexpr int S = CPLX ? 2 : 1;
@@ -482,33 +489,59 @@ __global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fr
   T* P = fac + f.p_off;
   T* Q = fac + f.q_off;
   int t = blockIdx.x;
+  auto tiles = [](long long rows, long long cols) { return (int)(((rows * S + 63) / 64) * ((cols + 63) / 64)); };
   if (mode == 0) {
     if (k <= j0) return;
-    const int jb = min(NB, k - j0), j1 = j0 + jb;
-    const int R1 = (int)(m - j1), C1 = k - j1, R2 = k - j1, C2 = r;
-    const int tm1 = (R1 * S + 63) / 64, tn1 = (C1 + 63) / 64;
-    const int tm2 = (R2 * S + 63) / 64, tn2 = (C2 + 63) / 64;
-    if (t < tm1 * tn1) {
-      const int tm = t % tm1, tn = t / tm1;
-      gemm_tile<CPLX>((const double*)(P + j1 + (long long)j0 * m), m * S, (const double*)(P + j0 + (long long)j1 * m),
-                      m * S, (double*)(P + j1 + (long long)j1 * m), m * S, R1 * S, C1, jb * S, tm * 64, tn * 64);
+    const int jb = min(NB, k - j0), j1 = j0 + jb, ob1 = min(ob0 + OB, k);
+    const int R1 = (int)(m - j1), C1 = ob1 - j1, R2 = ob1 - j1, C2 = k - ob1, C3 = r;
+    const double* A = (const double*)(P + j1 + (long long)j0 * m);
+    int nt = tiles(R1, C1);
+    if (t < nt) {
+      const int tm1 = (R1 * S + 63) / 64;
+      gemm_tile<CPLX>(A, m * S, (const double*)(P + j0 + (long long)j1 * m), m * S,
+                      (double*)(P + j1 + (long long)j1 * m), m * S, R1 * S, C1, jb * S, (t % tm1) * 64, (t / tm1) * 64);
       return;
     }
-    t -= tm1 * tn1;
-    if (t < tm2 * tn2) {
-      const int tm = t % tm2, tn = t / tm2;
-      gemm_tile<CPLX>((const double*)(P + j1 + (long long)j0 * m), m * S, (const double*)(Q + j0), (long long)k * S,
-                      (double*)(Q + j1), (long long)k * S, R2 * S, C2, jb * S, tm * 64, tn * 64);
+    t -= nt;
+    const int tm2 = (R2 * S + 63) / 64;
+    if (tm2 == 0) return;
+    nt = tiles(R2, C2);
+    if (t < nt) {
+      gemm_tile<CPLX>(A, m * S, (const double*)(P + j0 + (long long)ob1 * m), m * S,
+                      (double*)(P + j1 + (long long)ob1 * m), m * S, R2 * S, C2, jb * S, (t % tm2) * 64, (t / tm2) * 64);
+      return;
+    }
+    t -= nt;
+    nt = tiles(R2, C3);
+    if (t < nt)
+      gemm_tile<CPLX>(A, m * S, (const double*)(Q + j0), (long long)k * S, (double*)(Q + j1), (long long)k * S, R2 * S, C3,
+                      jb * S, (t % tm2) * 64, (t / tm2) * 64);
+  } else if (mode == 2) {
+    const int ob1 = ob0 + OB;
+    if (k <= ob1) return;
+    const int R1 = (int)(m - ob1), C1 = k - ob1, R2 = k - ob1, C2 = r;
+    const double* A = (const double*)(P + ob1 + (long long)ob0 * m);
+    int nt = tiles(R1, C1);
+    if (t < nt) {
+      const int tm1 = (R1 * S + 63) / 64;
+      gemm_tile<CPLX>(A, m * S, (const double*)(P + ob0 + (long long)ob1 * m), m * S,
+                      (double*)(P + ob1 + (long long)ob1 * m), m * S, R1 * S, C1, OB * S, (t % tm1) * 64, (t / tm1) * 64);
+      return;
+    }
+    t -= nt;
+    nt = tiles(R2, C2);
+    if (t < nt) {
+      const int tm2 = (R2 * S + 63) / 64;
+      gemm_tile<CPLX>(A, m * S, (const double*)(Q + ob0), (long long)k * S, (double*)(Q + ob1), (long long)k * S, R2 * S, C2,
+                      OB * S, (t % tm2) * 64, (t / tm2) * 64);
     }
   } else {
     if (r == 0 || k == 0) return;
     T* C = pool + f.c_off;
-    const int tm1 = (r * S + 63) / 64, tn1 = (r + 63) / 64;
-    if (t < tm1 * tn1) {
-      const int tm = t % tm1, tn = t / tm1;
-      gemm_tile<CPLX>((const double*)(P + k), m * S, (const double*)Q, (long long)k * S, (double*)C,
-                      (long long)r * S, r * S, r, k * S, tm * 64, tn * 64);
-    }
+    const int tm1 = (r * S + 63) / 64;
+    if (t < tiles(r, r))
+      gemm_tile<CPLX>((const double*)(P + k), m * S, (const double*)Q, (long long)k * S, (double*)C, (long long)r * S,
+                      r * S, r, k * S, (t % tm1) * 64, (t / tm1) * 64);
   }
 }
 
@@ -620,36 +653,52 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
         LSA_LAUNCH_CHECK();
         launches++;
       }
-      // ---- blocked partial LU of every front of the chunk
-      for (int j0 = 0; j0 < maxk; j0 += NB) {
-        // fronts with k > j0 form a prefix of the chunk
-        int act = 0;
-        int gx_cols = 1, gx_rows = 0, gx_tiles = 0;
+      // ---- blocked partial LU of every front of the chunk (fronts with k > j0 form a prefix)
+      auto tiles = [](long long rows, long long cols) { return ((rows * S + 63) / 64) * ((cols + 63) / 64); };
+      for (int ob0 = 0; ob0 < maxk; ob0 += OB) {
+        for (int j0 = ob0; j0 < std::min(ob0 + OB, maxk); j0 += NB) {
+          int act = 0, gx_cols = 1, gx_rows = 0;
+          long long gx_tiles = 0;
+          for (int q = first; q < first + cnt; ++q) {
+            const Front& f = sym.fronts[sym.lvl_front[q]];
+            if (f.k <= j0) break;
+            act++;
+            const int jb = std::min(NB, f.k - j0), j1 = j0 + jb, ob1 = std::min(ob0 + OB, f.k);
+            const long long m = (long long)f.k + f.r;
+            gx_cols = std::max(gx_cols, cdiv((long long)j0 + (f.k - j1) + f.r, 128));
+            gx_rows = std::max(gx_rows, cdiv(f.r, 128));
+            gx_tiles = std::max(gx_tiles, tiles(m - j1, ob1 - j1) + tiles(ob1 - j1, f.k - ob1) + tiles(ob1 - j1, f.r));
+          }
+          if (act == 0) break;
+          k_panel_lu<T><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs, h.d_stats);
+          LSA_LAUNCH_CHECK();
+          k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv);
+          LSA_LAUNCH_CHECK();
+          launches += 2;
+          if (gx_rows > 0) {
+            k_trsm_cols<T><<<dim3(gx_rows, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac);
+            LSA_LAUNCH_CHECK();
+            launches++;
+          }
+          if (gx_tiles > 0) {
+            k_front_gemm<T><<<dim3((unsigned)gx_tiles, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, ob0, 0, fac,
+                                                                             pool[d & 1]);
+            LSA_LAUNCH_CHECK();
+            launches++;
+          }
+        }
+        // deferred rank-128 update of everything right of / below the outer block
+        int act2 = 0;
+        long long gx2 = 0;
         for (int q = first; q < first + cnt; ++q) {
           const Front& f = sym.fronts[sym.lvl_front[q]];
-          if (f.k <= j0) break;
-          act++;
-          const int jb = std::min(NB, f.k - j0), j1 = j0 + jb;
-          const long long m = (long long)f.k + f.r;
-          gx_cols = std::max(gx_cols, cdiv((long long)j0 + (f.k - j1) + f.r, 128));
-          gx_rows = std::max(gx_rows, cdiv(f.r, 128));
-          const long long t1 = (long long)cdiv((m - j1) * S, 64) * cdiv(f.k - j1, 64);
-          const long long t2 = (long long)cdiv((long long)(f.k - j1) * S, 64) * cdiv(f.r, 64);
-          gx_tiles = (int)std::max<long long>(gx_tiles, t1 + t2);
+          if (f.k <= ob0 + OB) break;
+          act2++;
+          const long long m = (long long)f.k + f.r, ob1 = ob0 + OB;
+          gx2 = std::max(gx2, tiles(m - ob1, f.k - ob1) + tiles(f.k - ob1, f.r));
         }
-        if (act == 0) break;
-        k_panel_lu<T><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs, h.d_stats);
-        LSA_LAUNCH_CHECK();
-        k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv);
-        LSA_LAUNCH_CHECK();
-        launches += 2;
-        if (gx_rows > 0) {
-          k_trsm_cols<T><<<dim3(gx_rows, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac);
-          LSA_LAUNCH_CHECK();
-          launches++;
-        }
-        if (gx_tiles > 0) {
-          k_front_gemm<T><<<dim3(gx_tiles, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, 0, fac, pool[d & 1]);
+        if (act2 > 0 && gx2 > 0) {
+          k_front_gemm<T><<<dim3((unsigned)gx2, act2), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, ob0, 2, fac, pool[d & 1]);
           LSA_LAUNCH_CHECK();
           launches++;
         }
@@ -662,7 +711,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
           gx_schur = (int)std::max<long long>(gx_schur, (long long)cdiv((long long)f.r * S, 64) * cdiv(f.r, 64));
       }
       if (gx_schur > 0) {
-        k_front_gemm<T><<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, 1, fac, pool[d & 1]);
+        k_front_gemm<T><<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, 0, 1, fac, pool[d & 1]);
         LSA_LAUNCH_CHECK();
         launches++;
       }

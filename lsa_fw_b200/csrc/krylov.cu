@@ -337,22 +337,38 @@ __global__ void __launch_bounds__(256) k_basis_gemm(int n, int mp, int nk, const
 // ------------------------------------------------------------------------------------ Rayleigh-Ritz
 
 __global__ void __launch_bounds__(128) k_rr(z128* S, z128* Q, RrParams p, z128* theta, double* resid, z128* brow,
-                                            z128* ywork, RrInfo* info) {
+                                            z128* ywork, RrInfo* info, int use_smem) {
   __shared__ double s_rot_c[160];
   __shared__ z128 s_rot_s[160];
   __shared__ z128 s_vec[160];
   __shared__ double s_key[160];
   __shared__ int s_flag[4];
-  RrWork w{s_rot_c, s_rot_s, s_vec, s_key, s_flag};
-  RrOut out;
   __shared__ RrOut s_out;
-  rr_full(S, Q, p, theta, resid, brow, ywork, &s_out, threadIdx.x, blockDim.x, w);
+  extern __shared__ unsigned char rr_dyn[];
+  RrWork w{s_rot_c, s_rot_s, s_vec, s_key, s_flag};
+  const int m = p.m, tid = threadIdx.x, nt = blockDim.x;
+  if (use_smem) {
+    // the projected matrix and the accumulated transformation live in shared memory for the whole
+    // Schur iteration (global round trips were 18 ms per call at m = 80, see profiles/)
+    z128* Ss = reinterpret_cast<z128*>(rr_dyn);
+    z128* Qs = Ss + (size_t)(m + 1) * m;
+    for (int e = tid; e < (m + 1) * m; e += nt) Ss[e] = S[(e % (m + 1)) + (long long)(e / (m + 1)) * p.ld];
+    __syncthreads();
+    RrParams ps = p;
+    ps.ld = m + 1;
+    ps.ldq = m;
+    rr_full(Ss, Qs, ps, theta, resid, brow, ywork, &s_out, tid, nt, w);
+    __syncthreads();
+    for (int e = tid; e < (m + 1) * m; e += nt) S[(e % (m + 1)) + (long long)(e / (m + 1)) * p.ld] = Ss[e];
+    for (int e = tid; e < m * m; e += nt) Q[(e % m) + (long long)(e / m) * p.ldq] = Qs[e];
+  } else {
+    rr_full(S, Q, p, theta, resid, brow, ywork, &s_out, tid, nt, w);
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    out = s_out;
-    info->nconv = out.nconv;
-    info->keep = out.keep;
-    info->status = out.status;
+  if (tid == 0) {
+    info->nconv = s_out.nconv;
+    info->keep = s_out.keep;
+    info->status = s_out.status;
     info->pad = 0;
   }
 }
@@ -596,7 +612,16 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
     rp.transform = p.transform; rp.tol = p.tol; rp.sigma = sigma; rp.beta_scale = beta_scale;
     rp.last = (restarts >= p.max_restarts) || m >= n;
     size_t e = t_rr.begin();
-    k_rr<<<1, 128, 0, st>>>(S, Q, rp, h.d_theta, h.d_resid, h.d_brow, h.d_ywork, h.d_rr);
+    {
+      const size_t rr_smem = sizeof(z128) * ((size_t)(m + 1) * m + (size_t)m * m);
+      const int use_smem = rr_smem <= 210 * 1024;
+      static bool rr_attr = false;
+      if (use_smem && !rr_attr) {
+        LSA_CUDA(cudaFuncSetAttribute(k_rr, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        rr_attr = true;
+      }
+      k_rr<<<1, 128, use_smem ? rr_smem : 0, st>>>(S, Q, rp, h.d_theta, h.d_resid, h.d_brow, h.d_ywork, h.d_rr, use_smem);
+    }
     LSA_LAUNCH_CHECK();
     h.launch_count += 3;  // rr + restart gemm + copy
     t_rr.end(e);

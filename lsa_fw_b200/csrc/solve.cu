@@ -20,7 +20,7 @@
 
 namespace lsa {
 
-static constexpr int SB = 256;  // pivot-block step of the solve kernels
+static constexpr int SB = 128;  // pivot-block step of the solve kernels = order of the inverted diagonal blocks
 static constexpr int IB = 32;   // inverted diagonal block order (= factorisation panel width)
 
 // ------------------------------------------------------------------------------- post-factor set-up
@@ -91,6 +91,53 @@ __global__ void __launch_bounds__(32) k_invert_diag(const Front* __restrict__ fr
     if (c < nb && c <= j) D[c + (long long)j * m] = s_x[j][c];
 }
 
+// Merges the inverses of two adjacent HB x HB diagonal blocks (A above-left, D below-right) into the
+// inverse of the 2HB block, in place:   lower  X = -D^-1 C A^-1 ,   upper  X = -A^-1 B D^-1 .
+// Launched for HB = 32 and HB = 64, so that 128 x 128 diagonal blocks of L11 (unit lower) and U11
+// (upper) end up explicitly inverted: the solve sweeps then need ONE small GEMV per 128 pivots
+// instead of a chain of dependent substitutions.   grid: (block pairs, fronts); block 256.
+template <class T, int HB>
+__global__ void __launch_bounds__(256) k_merge_inv(const Front* __restrict__ fronts, int first, T* __restrict__ fac) {
+  const Front f = fronts[first + blockIdx.y];
+  const int j0 = blockIdx.x * 2 * HB, jd = j0 + HB;
+  if (jd >= f.k) return;
+  const int hd = min(HB, f.k - jd);
+  const long long m = (long long)f.k + f.r;
+  T* P = fac + f.p_off;
+  extern __shared__ unsigned char smem_raw[];
+  T* Tm = reinterpret_cast<T*>(smem_raw);  // HB x HB scratch, column-major
+  const int tid = threadIdx.x;
+  // ---- lower part
+  for (int e = tid; e < hd * HB; e += 256) {
+    const int p = e % hd, c = e / hd;
+    T acc = P[(jd + p) + (long long)(j0 + c) * m];  // q == c: unit diagonal of A^-1
+    for (int q = c + 1; q < HB; ++q) acc = acc + P[(jd + p) + (long long)(j0 + q) * m] * P[(j0 + q) + (long long)(j0 + c) * m];
+    Tm[p + c * HB] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < hd * HB; e += 256) {
+    const int i = e % hd, c = e / hd;
+    T acc = Tm[i + c * HB];
+    for (int p = 0; p < i; ++p) acc = acc + P[(jd + i) + (long long)(jd + p) * m] * Tm[p + c * HB];
+    P[(jd + i) + (long long)(j0 + c) * m] = scalar_traits<T>::zero() - acc;
+  }
+  __syncthreads();
+  // ---- upper part
+  for (int e = tid; e < HB * hd; e += 256) {
+    const int p = e % HB, c = e / HB;
+    T acc = scalar_traits<T>::zero();
+    for (int q = 0; q <= c; ++q) acc = acc + P[(j0 + p) + (long long)(jd + q) * m] * P[(jd + q) + (long long)(jd + c) * m];
+    Tm[p + c * HB] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < HB * hd; e += 256) {
+    const int i = e % HB, c = e / HB;
+    T acc = scalar_traits<T>::zero();
+    for (int p = i; p < HB; ++p) acc = acc + P[(j0 + i) + (long long)(j0 + p) * m] * Tm[p + c * HB];
+    P[(j0 + i) + (long long)(jd + c) * m] = scalar_traits<T>::zero() - acc;
+  }
+}
+
 template <class T>
 void post_factor(lsa_handle_impl& h, int* n_kernels) {
   const Symbolic& sym = h.sym;
@@ -106,7 +153,21 @@ void post_factor(lsa_handle_impl& h, int* n_kernels) {
       for (int s = s0; s < s0 + cnt; ++s) maxk = std::max(maxk, sym.fronts[s].k);
       k_invert_diag<T><<<dim3(cdiv(maxk, IB), cnt), 32, 0, st>>>(h.d_fronts, s0, (T*)h.d_fac);
       LSA_LAUNCH_CHECK();
-      if (n_kernels) (*n_kernels)++;
+      if (maxk > 32) {
+        k_merge_inv<T, 32><<<dim3(cdiv(maxk, 64), cnt), 256, 32 * 32 * sizeof(T), st>>>(h.d_fronts, s0, (T*)h.d_fac);
+        LSA_LAUNCH_CHECK();
+      }
+      if (maxk > 64) {
+        static bool attr_done[2] = {false, false};
+        if (!attr_done[scalar_traits<T>::is_complex]) {
+          LSA_CUDA(cudaFuncSetAttribute(k_merge_inv<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(64 * 64 * sizeof(T))));
+          attr_done[scalar_traits<T>::is_complex] = true;
+        }
+        k_merge_inv<T, 64><<<dim3(cdiv(maxk, 128), cnt), 256, 64 * 64 * sizeof(T), st>>>(h.d_fronts, s0, (T*)h.d_fac);
+        LSA_LAUNCH_CHECK();
+      }
+      if (n_kernels) (*n_kernels) += 3;
     }
   }
   if (n_kernels) (*n_kernels) += 2;
@@ -150,62 +211,60 @@ __global__ void __launch_bounds__(256) k_up_gather(const Front* __restrict__ fro
   for (int i = threadIdx.x; i < p.k; i += blockDim.x) y[p.col0 + i] = x[PERM ? gperm[p.col0 + i] : p.col0 + i];
 }
 
-// Element (i, c) of the lower-triangular operator of the up sweep, i > c (or the inverted diagonal
-// block when both lie in the same 32-block):  N: L[i, c] = P[i + c m] ;  H: conj(U[c, i]) = conj(P[c + i m]).
-template <class T, bool H>
-__device__ __forceinline__ T up_elem(const T* __restrict__ P, long long m, int i, int c) {
-  return H ? conj_(P[c + (long long)i * m]) : P[i + (long long)c * m];
-}
-
-// One CTA (256 threads) per front: solve the pivot block rows [j0, j1) of the up sweep.
-template <class T, bool H>
-__global__ void __launch_bounds__(256) k_up_diag(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                 int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
+// y[j0:j1) <- Op y[j0:j1) with Op the explicitly inverted 128 x 128 diagonal block of this step:
+//   UP,  N : L^-1   (unit lower)         UP,  H : (U^-1)^H (lower)
+//   DOWN,N : U^-1   (upper)              DOWN,H : (L^-1)^H (unit upper)
+// One CTA (256 threads) per front.  N reads rows contiguously (thread per row, two column phases);
+// H reads columns contiguously (warp per row).
+template <class T, bool H, bool UP>
+__global__ void __launch_bounds__(256) k_tri_block(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
   const Front f = fronts[lvl_front[first + blockIdx.x]];
   const int k = f.k;
   if (k <= j0) return;
-  const int j1 = min(k, j0 + SB), len = j1 - j0;
+  const int len = min(SB, k - j0);
   const long long m = (long long)k + f.r;
-  const T* P = fac + f.p_off;
+  const T* D = fac + f.p_off + j0 + (long long)j0 * m;  // block origin
   __shared__ z128 ys[SB];
-  __shared__ z128 yb[IB];
+  __shared__ z128 part[SB];
   const int tid = threadIdx.x;
-  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
+  z128* yo = y + f.col0 + j0;
+  if (tid < len) ys[tid] = yo[tid];
   __syncthreads();
-  for (int b0 = 0; b0 < len; b0 += IB) {
-    const int nb = min(IB, len - b0);
-    // (i) block GEMV with the inverted diagonal block: 8 threads per row
-    {
-      const int i = tid >> 3, part = tid & 7;
-      z128 acc = mk(0, 0);
-      if (i < nb) {
-        for (int c = part; c <= i; c += 8) {
-          if (c == i) {
-            if (H) acc += up_elem<T, H>(P, m, j0 + b0 + i, j0 + b0 + c) * ys[b0 + c];
-            else acc += ys[b0 + c];  // unit diagonal of L^-1
-          } else {
-            acc += up_elem<T, H>(P, m, j0 + b0 + i, j0 + b0 + c) * ys[b0 + c];
-          }
-        }
+  if (!H) {
+    const int i = tid & (SB - 1), hf = tid >> 7;
+    z128 acc = mk(0, 0);
+    if (i < len) {
+      const T* row = D + i;
+      if (UP) {
+#pragma unroll 4
+        for (int c = hf; c < i; c += 2) acc += row[(long long)c * m] * ys[c];
+        if (hf == 0) acc += ys[i];
+      } else {
+#pragma unroll 4
+        for (int c = i + hf; c < len; c += 2) acc += row[(long long)c * m] * ys[c];
       }
-      for (int o = 4; o > 0; o >>= 1) {
+    }
+    if (hf == 1) part[i] = acc;
+    __syncthreads();
+    if (hf == 0 && i < len) yo[i] = acc + part[i];
+  } else {
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int i = wid; i < len; i += 8) {
+      const T* col = D + (long long)i * m;
+      z128 acc = mk(0, 0);
+      if (UP) {
+        for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
+      } else {
+        for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
+      }
+      for (int o = 16; o > 0; o >>= 1) {
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
         acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
       }
-      if (i < nb && part == 0) yb[i] = acc;
+      if (lane == 0) yo[i] = UP ? acc : acc + ys[i];
     }
-    __syncthreads();
-    if (tid < nb) ys[b0 + tid] = yb[tid];
-    // (ii) update the remaining rows of this step
-    const int i = b0 + IB + tid;
-    if (i < len) {
-      z128 acc = ys[i];
-      for (int c = 0; c < nb; ++c) acc -= up_elem<T, H>(P, m, j0 + i, j0 + b0 + c) * yb[c];
-      ys[i] = acc;
-    }
-    __syncthreads();
   }
-  if (tid < len) y[f.col0 + j0 + tid] = ys[tid];
 }
 
 // Rows below the step: remaining pivot rows (-> y) and contribution rows (-> cb).
@@ -278,24 +337,25 @@ template <class T, bool H>
 __global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                   int first, const int* __restrict__ st_idx, const T* __restrict__ fac,
                                                   const z128* anc, z128* y) {
+  constexpr int ROWS = 32;  // pivot rows per CTA; 8 column groups (N) / 8 warps x 4 rows (H)
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k, r = f.r;
-  const int r0 = blockIdx.x * 64;
+  const int r0 = blockIdx.x * ROWS;
   if (r0 >= k || r == 0) return;
   const long long m = (long long)k + r;
   const T* P = fac + f.p_off;
   const T* Q = fac + f.q_off;
   const int* idx = st_idx + f.st0;
-  __shared__ z128 xs[SB];
-  __shared__ z128 red[4][64];
+  __shared__ z128 xs[256];
+  __shared__ z128 red[8][ROWS];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int rr = tid & 63, cg = tid >> 6;
-  z128 acc = mk(0, 0);       // axpy type accumulator (N)
-  z128 accw[8];              // dot type accumulators (H): rows wid, wid+8, ...
+  const int rr = lane, cg = wid;
+  z128 acc = mk(0, 0);  // axpy type accumulator (N)
+  z128 accw[4];         // dot type accumulators (H): rows wid, wid+8, wid+16, wid+24
 #pragma unroll
-  for (int q = 0; q < 8; ++q) accw[q] = mk(0, 0);
-  for (int c0 = 0; c0 < r; c0 += SB) {
-    const int len = min(SB, r - c0);
+  for (int q = 0; q < 4; ++q) accw[q] = mk(0, 0);
+  for (int c0 = 0; c0 < r; c0 += 256) {
+    const int len = min(256, r - c0);
     __syncthreads();
     if (tid < len) xs[tid] = anc[idx[c0 + tid]];
     __syncthreads();
@@ -303,11 +363,11 @@ __global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fron
       if (r0 + rr < k) {
         const T* a = Q + (r0 + rr) + (long long)c0 * k;
 #pragma unroll 4
-        for (int c = cg; c < len; c += 4) acc += a[(long long)c * k] * xs[c];
+        for (int c = cg; c < len; c += 8) acc += a[(long long)c * k] * xs[c];
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 4; ++q) {
         const int row = r0 + wid + q * 8;
         if (row < k) {
           const T* l = P + k + c0 + (long long)row * m;
@@ -319,10 +379,15 @@ __global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fron
   if (!H) {
     red[cg][rr] = acc;
     __syncthreads();
-    if (tid < 64 && r0 + tid < k) y[f.col0 + r0 + tid] -= red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    if (tid < ROWS && r0 + tid < k) {
+      z128 s = red[0][tid];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) s += red[q][tid];
+      y[f.col0 + r0 + tid] -= s;
+    }
   } else {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 4; ++q) {
       z128 a = accw[q];
       for (int o = 16; o > 0; o >>= 1) {
         a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
@@ -332,62 +397,6 @@ __global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fron
       if (lane == 0 && row < k) y[f.col0 + row] -= a;
     }
   }
-}
-
-// Element (i, c), i < c, of the upper-triangular operator of the down sweep (or the inverted
-// diagonal block):  N: U[i, c] = P[i + c m] ;  H: conj(L[c, i]) = conj(P[c + i m]).
-template <class T, bool H>
-__device__ __forceinline__ T down_elem(const T* __restrict__ P, long long m, int i, int c) {
-  return H ? conj_(P[c + (long long)i * m]) : P[i + (long long)c * m];
-}
-
-template <class T, bool H>
-__global__ void __launch_bounds__(256) k_down_diag(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                   int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
-  const Front f = fronts[lvl_front[first + blockIdx.x]];
-  const int k = f.k;
-  if (k <= j0) return;
-  const int j1 = min(k, j0 + SB), len = j1 - j0;
-  const long long m = (long long)k + f.r;
-  const T* P = fac + f.p_off;
-  __shared__ z128 ys[SB];
-  __shared__ z128 yb[IB];
-  const int tid = threadIdx.x;
-  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
-  __syncthreads();
-  const int nblk = (len + IB - 1) / IB;
-  for (int bi = nblk - 1; bi >= 0; --bi) {
-    const int b0 = bi * IB, nb = min(IB, len - b0);
-    {
-      const int i = tid >> 3, part = tid & 7;
-      z128 acc = mk(0, 0);
-      if (i < nb) {
-        for (int c = i + part; c < nb; c += 8) {
-          if (c == i) {
-            if (H) acc += ys[b0 + c];  // unit diagonal of L^-H
-            else acc += down_elem<T, H>(P, m, j0 + b0 + i, j0 + b0 + c) * ys[b0 + c];
-          } else {
-            acc += down_elem<T, H>(P, m, j0 + b0 + i, j0 + b0 + c) * ys[b0 + c];
-          }
-        }
-      }
-      for (int o = 4; o > 0; o >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-      }
-      if (i < nb && part == 0) yb[i] = acc;
-    }
-    __syncthreads();
-    if (tid < nb) ys[b0 + tid] = yb[tid];
-    const int i = tid;
-    if (i < b0) {
-      z128 acc = ys[i];
-      for (int c = 0; c < nb; ++c) acc -= down_elem<T, H>(P, m, j0 + i, j0 + b0 + c) * yb[c];
-      ys[i] = acc;
-    }
-    __syncthreads();
-  }
-  if (tid < len) y[f.col0 + j0 + tid] = ys[tid];
 }
 
 // Pivot rows above the step: y[0:j0] -= Upper[0:j0, j0:j1] y[j0:j1].  grid: (row chunks of 64, fronts).
@@ -481,7 +490,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           act++;
           max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
         }
-        k_up_diag<T, H><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+        k_tri_block<T, H, true><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
         LSA_LAUNCH_CHECK();
         launches++;
         if (max_rows > 0) {
@@ -501,7 +510,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       int maxr = 0;
       for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[sym.lvl_front[q]].r);
       if (maxr > 0) {
-        k_down_off<T, H><<<dim3(cdiv(maxk, 64), cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, y);
+        k_down_off<T, H><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, y);
         LSA_LAUNCH_CHECK();
         launches++;
       }
@@ -512,7 +521,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           act++;
         }
         if (act == 0) continue;
-        k_down_diag<T, H><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+        k_tri_block<T, H, false><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
         LSA_LAUNCH_CHECK();
         launches++;
         if (j0 > 0) {
