@@ -73,6 +73,7 @@ typedef struct {
   int32_t scalar;          /* lsa_scalar actually used                                  */
   int32_t n_kernels;       /* kernel launches issued                                    */
   double min_pivot, max_pivot;
+  double max_multiplier;   /* largest |l_ij| met: element-growth monitor of the restricted pivoting */
 } lsa_factor_stats;
 
 typedef struct {

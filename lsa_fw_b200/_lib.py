@@ -49,6 +49,7 @@ class FactorStats(C.Structure):
     _fields_ = [
         ("seconds", C.c_double), ("flops", C.c_double), ("n_perturbed", C.c_int64), ("n_row_swaps", C.c_int64),
         ("scalar", C.c_int32), ("n_kernels", C.c_int32), ("min_pivot", C.c_double), ("max_pivot", C.c_double),
+        ("max_multiplier", C.c_double),
     ]
 
 

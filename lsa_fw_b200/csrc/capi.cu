@@ -41,6 +41,7 @@ void free_csr(CsrDev& c) {
 }
 
 void free_device(lsa_handle_impl& h) {
+  drop_solve_graphs(h);
   dfree(h.d_fronts); dfree(h.d_lvl_front); dfree(h.d_st_idx); dfree(h.d_ea_map); dfree(h.d_child_idx);
   dfree(h.d_a_dst); dfree(h.d_m_dst); dfree(h.d_perm); dfree(h.d_ipiv); dfree(h.d_gperm); dfree(h.d_stats);
   if (h.d_a_orig) cudaFree(h.d_a_orig);
@@ -57,7 +58,7 @@ void free_device(lsa_handle_impl& h) {
   }
   dfree(h.d_x); dfree(h.d_w); dfree(h.d_t); dfree(h.d_cb); dfree(h.d_io); dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q);
   dfree(h.d_part); dfree(h.d_npart); dfree(h.d_h); dfree(h.d_brow); dfree(h.d_ywork); dfree(h.d_r1); dfree(h.d_r2);
-  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
+  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
   h.V_cols = 0; h.X_cols = 0; h.ncv_alloc = 0; h.scalar = -1; h.have_values = false;
 }
 
@@ -364,6 +365,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     h->d_npart = dalloc<double>((size_t)cdiv(n, 256) + 1);
     h->d_h = dalloc<z128>(256);
     h->d_flag = dalloc<int>(1);
+    h->d_ipart = dalloc<int>(256);
     h->d_rr = dalloc<RrInfo>(1);
     upload_csr(*h, h->hA, h->dA, false);
     if (h->has_m) upload_csr(*h, h->hM, h->dM, false);
@@ -500,6 +502,8 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   int nk = 0;
   cudaEventRecord(e0, st);
   h->scalar = -1;
+  drop_solve_graphs(*h);
+  if (const char* e = getenv("LSA_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
   if (scalar == LSA_C128) {
     factor_numeric<z128>(*h, alpha, beta, tiny_abs, &nk);
     post_factor<z128>(*h, &nk);
@@ -524,6 +528,7 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   fs.n_kernels = nk;
   std::memcpy(&fs.min_pivot, &ds.min_piv_bits, 8);
   std::memcpy(&fs.max_pivot, &ds.max_piv_bits, 8);
+  std::memcpy(&fs.max_multiplier, &ds.max_l_bits, 8);
   h->fstats = fs;
   if (stats) *stats = fs;
   if (ds.nonfinite) return fail(h, LSA_ERR_NONFINITE, "non-finite value met during the factorisation");

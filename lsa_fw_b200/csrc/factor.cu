@@ -22,6 +22,7 @@
 namespace lsa {
 
 static constexpr int NB = 32;   // panel width
+static constexpr int PANEL_SMEM_CAP = 192 * 1024;  // shared-memory budget of the panel kernel
 static constexpr int OB = 128;  // outer block: trailing updates beyond it are deferred and done with K = 128
 
 // ------------------------------------------------------------------------------------------ scatter
@@ -135,26 +136,46 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
 
 // One CTA per front.  Factors columns [j0, j0+jb) of the pivot rows [j0, k) of P with partial
 // pivoting restricted to those rows; interchanges are applied inside the panel only (the rest of
-// the row is swapped by k_swap_trsm).
+// the row is swapped by k_swap_trsm).  The panel is staged in shared memory whenever it fits
+// (`smem_bytes`), so the 32 dependent column steps run at shared-memory latency; taller panels are
+// processed in place in global memory (L2).
 template <class T>
 __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                   int first, int j0, T* __restrict__ fac, int* __restrict__ ipiv,
-                                                  double tiny_abs, DevStats* st) {
+                                                  double tiny_abs, DevStats* st, int smem_bytes, int ob0) {
   const Front f = fronts[lvl_front[first + blockIdx.x]];
   const int k = f.k;
   if (k <= j0) return;
   const long long m = (long long)f.k + f.r;
-  const int jb = min(NB, k - j0);
-  T* P = fac + f.p_off;
+  const int jb = min(NB, k - j0), pk = k - j0;
+  // pivot candidates: rows of the current outer block only.  Rows below it have not yet received
+  // the deferred rank-128 updates in the columns right of the block, so they must not be swapped in.
+  const int pcand = min(pk, ob0 + OB - j0);
+  T* G = fac + f.p_off + j0 + (long long)j0 * m;  // panel origin in global memory
+  extern __shared__ unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  const bool use_smem = (long long)pk * jb * (long long)sizeof(T) <= (long long)smem_bytes;
   __shared__ ArgMax s_red[8];
   __shared__ int s_piv;
   __shared__ T s_inv;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int j = j0; j < j0 + jb; ++j) {
-    // 1. pivot search in column j, rows [j, k)
+  T* base = G;
+  long long ld = m;
+  double lmax = 0.0;  // largest multiplier (growth monitor)
+  if (use_smem) {
+    for (int e = tid; e < pk * jb; e += blockDim.x) {
+      const int il = e % pk, cl = e / pk;
+      sm[il + (long long)cl * pk] = G[il + (long long)cl * m];
+    }
+    __syncthreads();
+    base = sm;
+    ld = pk;
+  }
+  for (int jl = 0; jl < jb; ++jl) {
+    // 1. pivot search in column jl, local rows [jl, pk)
     ArgMax best{-1.0, 0x7fffffff};
-    for (int i = j + tid; i < k; i += blockDim.x) {
-      double a = abs1(P[i + j * m]);
+    for (int i = jl + tid; i < pcand; i += blockDim.x) {
+      double a = abs1(base[i + jl * ld]);
       if (!(a == a)) a = INFINITY;  // propagate NaN as "largest" so it is detected below
       best = better(best, ArgMax{a, i});
     }
@@ -174,49 +195,53 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
         if (tiny_abs == 0.0) {
           st->zero_pivot = 1;
           a = 1.0;  // keep going with a harmless value; the host reports the error
-          P[piv + j * m] = scalar_traits<T>::one();
+          base[piv + jl * ld] = scalar_traits<T>::one();
         } else {
           // static pivoting: keep the diagonal candidate, replace by tiny_abs with its phase
-          piv = j;
-          T d = P[j + j * m];
+          piv = jl;
+          T d = base[jl + jl * ld];
           double ad = absz(d);
           T repl = ad > 0.0 ? d * (tiny_abs / ad) : scalar_traits<T>::from(mk(tiny_abs, 0.0));
-          P[j + j * m] = repl;
+          base[jl + jl * ld] = repl;
           atomicAdd(&st->n_perturbed, 1ULL);
           a = tiny_abs;
         }
       }
       atomicMin(&st->min_piv_bits, (unsigned long long)__double_as_longlong(a));
       atomicMax(&st->max_piv_bits, (unsigned long long)__double_as_longlong(a));
-      if (piv != j) atomicAdd(&st->n_swaps, 1ULL);
-      ipiv[f.col0 + j] = piv;
+      if (piv != jl) atomicAdd(&st->n_swaps, 1ULL);
+      ipiv[f.col0 + j0 + jl] = j0 + piv;  // front-local row index
       s_piv = piv;
     }
     __syncthreads();
     // 2. interchange inside the panel
     const int piv = s_piv;
-    if (piv != j && tid < jb) {
-      const long long c = j0 + tid;
-      T a = P[j + c * m], b = P[piv + c * m];
-      P[j + c * m] = b;
-      P[piv + c * m] = a;
+    if (piv != jl && tid < jb) {
+      T a = base[jl + tid * ld], b = base[piv + tid * ld];
+      base[jl + tid * ld] = b;
+      base[piv + tid * ld] = a;
     }
     __syncthreads();
-    if (tid == 0) s_inv = recip(P[j + j * m]);
+    if (tid == 0) s_inv = recip(base[jl + jl * ld]);
     __syncthreads();
     // 3. scale the column and rank-1 update of the remaining panel columns
     const T inv = s_inv;
-    const int nc = j0 + jb - (j + 1);
-    for (int i = j + 1 + tid; i < k; i += blockDim.x) {
-      const T l = P[i + j * m] * inv;
-      P[i + j * m] = l;
-      for (int c = 0; c < nc; ++c) {
-        const long long cc = j + 1 + c;
-        P[i + cc * m] = P[i + cc * m] - l * P[j + cc * m];
-      }
+    for (int i = jl + 1 + tid; i < pk; i += blockDim.x) {
+      const T l = base[i + jl * ld] * inv;
+      lmax = fmax(lmax, abs1(l));
+      base[i + jl * ld] = l;
+      for (int c = jl + 1; c < jb; ++c) base[i + c * ld] = base[i + c * ld] - l * base[jl + c * ld];
     }
     __syncthreads();
   }
+  if (use_smem) {
+    for (int e = tid; e < pk * jb; e += blockDim.x) {
+      const int il = e % pk, cl = e / pk;
+      G[il + (long long)cl * m] = sm[il + (long long)cl * pk];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if (lane == 0 && lmax > 0.0) atomicMax(&st->max_l_bits, (unsigned long long)__double_as_longlong(lmax));
 }
 
 // ------------------------------------------------------------------------------ row swaps + U rows
@@ -313,7 +338,7 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
 // Rows [k, m) of the panel columns: X U_jj = B.  One thread per row; grid (row groups of 128, fronts).
 template <class T>
 __global__ void __launch_bounds__(128) k_trsm_cols(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                   int first, int j0, T* __restrict__ fac) {
+                                                   int first, int j0, T* __restrict__ fac, DevStats* st) {
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k, r = f.r;
   if (k <= j0 || r == 0) return;
@@ -336,6 +361,7 @@ __global__ void __launch_bounds__(128) k_trsm_cols(const Front* __restrict__ fro
   if (row >= r) return;
   T* x = P + k + row + (long long)j0 * m;
   T xs[NB];
+  double lmax = 0.0;
 #pragma unroll
   for (int c = 0; c < NB; ++c) {
     if (c < jb) {
@@ -343,11 +369,13 @@ __global__ void __launch_bounds__(128) k_trsm_cols(const Front* __restrict__ fro
 #pragma unroll
       for (int s = 0; s < c; ++s) acc = acc - xs[s] * s_U[s + c * NB];
       xs[c] = acc * s_U[c + c * NB];
+      lmax = fmax(lmax, abs1(xs[c]));
       x[(long long)c * m] = xs[c];
     } else {
       xs[c] = scalar_traits<T>::zero();
     }
   }
+  atomicMax(&st->max_l_bits, (unsigned long long)__double_as_longlong(lmax));
 }
 
 // --------------------------------------------------------------------------------- FP64 DMMA GEMM
@@ -619,6 +647,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
   static bool attr_set[2] = {false, false};
   if (!attr_set[scalar_traits<T>::is_complex]) {
     LSA_CUDA(cudaFuncSetAttribute(k_swap_trsm<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem));
+    LSA_CUDA(cudaFuncSetAttribute(k_panel_lu<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_CAP));
     attr_set[scalar_traits<T>::is_complex] = true;
   }
   constexpr int S = scalar_traits<T>::is_complex ? 2 : 1;
@@ -670,13 +699,20 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
             gx_tiles = std::max(gx_tiles, tiles(m - j1, ob1 - j1) + tiles(ob1 - j1, f.k - ob1) + tiles(ob1 - j1, f.r));
           }
           if (act == 0) break;
-          k_panel_lu<T><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs, h.d_stats);
+          {
+            // the level's fronts are sorted by descending k: the first one has the tallest panel
+            const int max_pk = sym.fronts[sym.lvl_front[first]].k - j0;
+            const long long want = (long long)max_pk * NB * (long long)sizeof(T);
+            const int panel_smem = (int)std::min<long long>(want, PANEL_SMEM_CAP);
+            k_panel_lu<T><<<act, 256, panel_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs,
+                                                        h.d_stats, panel_smem, ob0);
+          }
           LSA_LAUNCH_CHECK();
           k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv);
           LSA_LAUNCH_CHECK();
           launches += 2;
           if (gx_rows > 0) {
-            k_trsm_cols<T><<<dim3(gx_rows, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac);
+            k_trsm_cols<T><<<dim3(gx_rows, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_stats);
             LSA_LAUNCH_CHECK();
             launches++;
           }

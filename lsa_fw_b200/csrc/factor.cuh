@@ -22,6 +22,7 @@ void spmv(lsa_handle_impl& h, const CsrDev& M, bool conj_vals, const z128* x, z1
 void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out);
 void dense_schur_device(lsa_handle_impl& h, int m, z128* dS, int ld, z128* dQ, int which, int transform, z128 sigma);
 void op_solve(lsa_handle_impl& h, int trans, z128* x, int refine_steps);
+void drop_solve_graphs(lsa_handle_impl& h);
 void permute_gather(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n);   // dst[i] = src[perm[i]]
 void permute_scatter(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n);  // dst[perm[i]] = src[i]
 void gather_values(cudaStream_t st, const void* orig, bool is_complex, const long long* src, void* out, long long nnz);

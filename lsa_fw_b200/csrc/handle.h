@@ -31,6 +31,7 @@ struct DevStats {
   unsigned long long n_swaps;
   unsigned long long min_piv_bits;  // bit pattern of a non-negative double
   unsigned long long max_piv_bits;
+  unsigned long long max_l_bits;    // largest |multiplier| met (element growth monitor)
   int zero_pivot;
   int nonfinite;
 };
@@ -118,6 +119,7 @@ struct lsa_handle_impl {
   z128* d_r3 = nullptr;
   z128* d_Xp = nullptr;    // n x ncv Ritz vectors, permuted ordering
   int* d_flag = nullptr;
+  int* d_ipart = nullptr;  // arg-max partial indices
   RrInfo* d_rr = nullptr;
   z128* d_theta = nullptr;
   double* d_resid = nullptr;
@@ -132,6 +134,16 @@ struct lsa_handle_impl {
   lsa_eigs_params last_params{};
   lsa_counters counters{};
   long long launch_count = 0;      // kernels launched (running total)
+
+  // captured solve sweeps (CUDA graphs), keyed by (trans, vector); invalidated by every factorisation
+  struct SolveGraph {
+    int trans;
+    const void* vec;
+    cudaGraphExec_t exec;
+    int launches;
+  };
+  std::vector<SolveGraph> solve_graphs;
+  bool use_graphs = true;
 };
 
 }  // namespace lsa

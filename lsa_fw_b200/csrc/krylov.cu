@@ -431,12 +431,104 @@ __global__ void k_ritz_vectors(const z128* __restrict__ S, int ld, int nc, z128*
   for (int i = 0; i <= c; ++i) y[i] = y[i] * inv;
 }
 
+// ---- phase normalisation of a Ritz vector: rotate so that its largest component is real positive
+// (eigenvectors are defined up to a phase; fixing it on the device makes the output deterministic and
+// saves a host pass over n x nev numbers).  Two-stage arg-max with index tie-break, then the rotation
+// is fused into the un-permutation scatter.
+__global__ void __launch_bounds__(256) k_absmax_part(int n, const z128* __restrict__ x, double* __restrict__ pv,
+                                                     int* __restrict__ pi) {
+  __shared__ double sv[256];
+  __shared__ int si[256];
+  double best = -1.0;
+  int bi = 0x7fffffff;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = abs2(x[i]);
+    if (a > best) {
+      best = a;
+      bi = (int)i;
+    }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double v = sv[threadIdx.x + o];
+      const int j = si[threadIdx.x + o];
+      if (v > sv[threadIdx.x] || (v == sv[threadIdx.x] && j < si[threadIdx.x])) {
+        sv[threadIdx.x] = v;
+        si[threadIdx.x] = j;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    pv[blockIdx.x] = sv[0];
+    pi[blockIdx.x] = si[0];
+  }
+}
+__global__ void k_absmax_final(int nparts, const double* __restrict__ pv, const int* __restrict__ pi,
+                               const z128* __restrict__ x, z128* __restrict__ phase) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double best = -1.0;
+  int bi = 0;
+  for (int b = 0; b < nparts; ++b)
+    if (pv[b] > best || (pv[b] == best && pi[b] < bi)) {
+      best = pv[b];
+      bi = pi[b];
+    }
+  const z128 v = x[bi];
+  const double a = absz(v);
+  *phase = a > 0.0 ? conj_(v) * (1.0 / a) : mk(1, 0);
+}
+__global__ void k_perm_scatter_scaled(const z128* __restrict__ src, z128* __restrict__ dst, const int* __restrict__ perm,
+                                      int n, const z128* __restrict__ phase) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[perm[i]] = src[i] * (*phase);
+}
+
 // ------------------------------------------------------------------------------------- OP and driver
 
+void drop_solve_graphs(lsa_handle_impl& h) {
+  for (auto& g : h.solve_graphs) cudaGraphExecDestroy(g.exec);
+  h.solve_graphs.clear();
+}
+
+// One triangular-solve sweep is a fixed sequence of ~10 launches per tree level; it is captured once
+// per (trans, vector) into a CUDA graph and replayed, which removes the per-launch CPU cost from the
+// latency-bound 2-D cases (a tracing compiler is not involved: plain stream capture of our kernels).
 static void solve_dispatch(lsa_handle_impl& h, int trans, z128* x, int* nk) {
+  auto run = [&](int* count) {
+    if (h.scalar == LSA_C128) solve_permuted<z128>(h, trans, x, count);
+    else solve_permuted<double>(h, trans, x, count);
+  };
   int local = 0;
-  if (h.scalar == LSA_C128) solve_permuted<z128>(h, trans, x, &local);
-  else solve_permuted<double>(h, trans, x, &local);
+  if (!h.use_graphs) {
+    run(&local);
+  } else {
+    lsa_handle_impl::SolveGraph* found = nullptr;
+    for (auto& g : h.solve_graphs)
+      if (g.trans == trans && g.vec == (const void*)x) found = &g;
+    if (!found) {
+      cudaGraph_t graph = nullptr;
+      LSA_CUDA(cudaStreamBeginCapture(h.stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        run(&local);
+      } catch (...) {
+        cudaStreamEndCapture(h.stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      LSA_CUDA(cudaStreamEndCapture(h.stream, &graph));
+      cudaGraphExec_t exec = nullptr;
+      LSA_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      h.solve_graphs.push_back({trans, (const void*)x, exec, local});
+      found = &h.solve_graphs.back();
+    }
+    LSA_CUDA(cudaGraphLaunch(found->exec, h.stream));
+    local = found->launches;
+  }
   h.launch_count += local;
   if (nk) *nk += local;
 }
@@ -689,7 +781,12 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
         k_norm2_part<<<blocks, 256, 0, st>>>(n, xi, h.d_npart);
         k_normalize<<<blocks, 256, 0, st>>>(n, xi, xi, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
       }
-      permute_scatter(st, xi, h.d_X + (long long)i * n, h.d_perm, n);
+      {
+        const int nb = std::min(blocks, 256);
+        k_absmax_part<<<nb, 256, 0, st>>>(n, xi, h.d_npart, h.d_ipart);
+        k_absmax_final<<<1, 32, 0, st>>>(nb, h.d_npart, h.d_ipart, xi, h.d_h);
+        k_perm_scatter_scaled<<<blocks, 256, 0, st>>>(xi, h.d_X + (long long)i * n, h.d_perm, n, h.d_h);
+      }
     }
     LSA_LAUNCH_CHECK();
     std::vector<z128> theta(nconv);

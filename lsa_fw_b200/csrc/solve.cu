@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(256) k_up_gather(const Front* __restrict__ fro
 // One CTA (256 threads) per front.  N reads rows contiguously (thread per row, two column phases);
 // H reads columns contiguously (warp per row).
 template <class T, bool H, bool UP>
-__global__ void __launch_bounds__(256) k_tri_block(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                   int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
+__global__ void __launch_bounds__(1024) k_tri_block(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                    int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
   const Front f = fronts[lvl_front[first + blockIdx.x]];
   const int k = f.k;
   if (k <= j0) return;
@@ -226,31 +226,36 @@ __global__ void __launch_bounds__(256) k_tri_block(const Front* __restrict__ fro
   const long long m = (long long)k + f.r;
   const T* D = fac + f.p_off + j0 + (long long)j0 * m;  // block origin
   __shared__ z128 ys[SB];
-  __shared__ z128 part[SB];
+  __shared__ z128 part[8][SB];
   const int tid = threadIdx.x;
   z128* yo = y + f.col0 + j0;
   if (tid < len) ys[tid] = yo[tid];
   __syncthreads();
   if (!H) {
-    const int i = tid & (SB - 1), hf = tid >> 7;
+    // thread (row i, column group cg): 1024 independent short dot products -> deep memory parallelism
+    const int i = tid & (SB - 1), cg = tid >> 7;
     z128 acc = mk(0, 0);
     if (i < len) {
       const T* row = D + i;
       if (UP) {
-#pragma unroll 4
-        for (int c = hf; c < i; c += 2) acc += row[(long long)c * m] * ys[c];
-        if (hf == 0) acc += ys[i];
+#pragma unroll 8
+        for (int c = cg; c < i; c += 8) acc += row[(long long)c * m] * ys[c];
       } else {
-#pragma unroll 4
-        for (int c = i + hf; c < len; c += 2) acc += row[(long long)c * m] * ys[c];
+#pragma unroll 8
+        for (int c = i + cg; c < len; c += 8) acc += row[(long long)c * m] * ys[c];
       }
     }
-    if (hf == 1) part[i] = acc;
+    part[cg][i] = acc;
     __syncthreads();
-    if (hf == 0 && i < len) yo[i] = acc + part[i];
+    if (tid < len) {
+      z128 s = part[0][tid];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) s += part[q][tid];
+      yo[tid] = UP ? s + ys[tid] : s;  // unit diagonal of L^-1
+    }
   } else {
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int i = wid; i < len; i += 8) {
+    const int lane = tid & 31, wid = tid >> 5;  // 32 warps, 4 rows each
+    for (int i = wid; i < len; i += 32) {
       const T* col = D + (long long)i * m;
       z128 acc = mk(0, 0);
       if (UP) {
@@ -273,43 +278,46 @@ template <class T, bool H>
 __global__ void __launch_bounds__(256) k_up_update(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                    int first, int j0, const T* __restrict__ fac, z128* __restrict__ y,
                                                    z128* __restrict__ cb) {
+  constexpr int ROWS = 32;
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k;
   if (k <= j0) return;
   const int j1 = min(k, j0 + SB), len = j1 - j0;
   const long long m = (long long)k + f.r;
   const int nrows = (int)(m - j1);
-  const int r0 = blockIdx.x * 64;
+  const int r0 = blockIdx.x * ROWS;
   if (r0 >= nrows) return;
   const T* P = fac + f.p_off;
   const T* Q = fac + f.q_off;
   __shared__ z128 ys[SB];
-  __shared__ z128 red[4][64];
-  const int tid = threadIdx.x;
+  __shared__ z128 red[8][ROWS];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
   __syncthreads();
   if (!H) {
-    // axpy type: thread (row, column group), rows contiguous in memory
-    const int rr = tid & 63, cg = tid >> 6;
-    const int row = j1 + r0 + rr;  // local front row
+    // axpy type: thread (row = lane, column group = warp), rows contiguous in memory
+    const int row = j1 + r0 + lane;  // local front row
     z128 acc = mk(0, 0);
-    if (r0 + rr < nrows) {
+    if (r0 + lane < nrows) {
       const T* a = P + row + (long long)j0 * m;
-#pragma unroll 4
-      for (int c = cg; c < len; c += 4) acc += a[(long long)c * m] * ys[c];
+#pragma unroll 8
+      for (int c = wid; c < len; c += 8) acc += a[(long long)c * m] * ys[c];
     }
-    red[cg][rr] = acc;
+    red[wid][lane] = acc;
     __syncthreads();
-    if (tid < 64 && r0 + tid < nrows) {
-      const z128 s = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    if (tid < ROWS && r0 + tid < nrows) {
+      z128 s = red[0][tid];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) s += red[q][tid];
       const int rw = j1 + r0 + tid;
       if (rw < k) y[f.col0 + rw] -= s;
       else cb[f.st0 + (rw - k)] -= s;
     }
   } else {
     // dot type: warp per row, lanes along the contiguous column of U
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int rr = wid; rr < 64; rr += 8) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rr = wid + q * 8;
       if (r0 + rr >= nrows) break;
       const int row = j1 + r0 + rr;
       const T* u = row < k ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
@@ -334,10 +342,11 @@ __global__ void __launch_bounds__(256) k_up_update(const Front* __restrict__ fro
 // vector, because each front applies its own P^T as soon as its pivot block is solved.
 // grid: (pivot-row chunks of 64, fronts); block 256.
 template <class T, bool H>
-__global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                  int first, const int* __restrict__ st_idx, const T* __restrict__ fac,
-                                                  const z128* anc, z128* y) {
-  constexpr int ROWS = 32;  // pivot rows per CTA; 8 column groups (N) / 8 warps x 4 rows (H)
+__global__ void __launch_bounds__(1024) k_down_off(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, const int* __restrict__ st_idx, const T* __restrict__ fac,
+                                                   const z128* anc, z128* y) {
+  constexpr int ROWS = 32;   // pivot rows per CTA; 32 warps = 32 column groups (N) / one row each (H)
+  constexpr int CHUNK = 1024;
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k, r = f.r;
   const int r0 = blockIdx.x * ROWS;
@@ -346,40 +355,77 @@ __global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fron
   const T* P = fac + f.p_off;
   const T* Q = fac + f.q_off;
   const int* idx = st_idx + f.st0;
-  __shared__ z128 xs[256];
-  __shared__ z128 red[8][ROWS];
+  __shared__ z128 xs[CHUNK];
+  __shared__ z128 red[32][ROWS + 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int rr = lane, cg = wid;
-  z128 acc = mk(0, 0);  // axpy type accumulator (N)
-  z128 accw[4];         // dot type accumulators (H): rows wid, wid+8, wid+16, wid+24
-#pragma unroll
-  for (int q = 0; q < 4; ++q) accw[q] = mk(0, 0);
-  for (int c0 = 0; c0 < r; c0 += 256) {
-    const int len = min(256, r - c0);
+  z128 acc = mk(0, 0);
+  const int rowN = r0 + lane;  // N: this thread's pivot row
+  const int rowH = r0 + wid;   // H: this warp's pivot row
+  for (int c0 = 0; c0 < r; c0 += CHUNK) {
+    const int len = min(CHUNK, r - c0);
     __syncthreads();
     if (tid < len) xs[tid] = anc[idx[c0 + tid]];
     __syncthreads();
     if (!H) {
-      if (r0 + rr < k) {
-        const T* a = Q + (r0 + rr) + (long long)c0 * k;
-#pragma unroll 4
-        for (int c = cg; c < len; c += 8) acc += a[(long long)c * k] * xs[c];
+      if (rowN < k) {
+        const T* a = Q + rowN + (long long)c0 * k;
+#pragma unroll 8
+        for (int c = wid; c < len; c += 32) acc += a[(long long)c * k] * xs[c];
       }
     } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int row = r0 + wid + q * 8;
-        if (row < k) {
-          const T* l = P + k + c0 + (long long)row * m;
-          for (int c = lane; c < len; c += 32) accw[q] += conj_(l[c]) * xs[c];
-        }
+      if (rowH < k) {
+        const T* l = P + k + c0 + (long long)rowH * m;
+#pragma unroll 4
+        for (int c = lane; c < len; c += 32) acc += conj_(l[c]) * xs[c];
       }
     }
   }
   if (!H) {
-    red[cg][rr] = acc;
+    red[wid][lane] = acc;
     __syncthreads();
     if (tid < ROWS && r0 + tid < k) {
+      z128 s = red[0][tid];
+#pragma unroll 8
+      for (int q = 1; q < 32; ++q) s += red[q][tid];
+      y[f.col0 + r0 + tid] -= s;
+    }
+  } else {
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (lane == 0 && rowH < k) y[f.col0 + rowH] -= acc;
+  }
+}
+
+// Pivot rows above the step: y[0:j0] -= Upper[0:j0, j0:j1] y[j0:j1].  grid: (row chunks of 64, fronts).
+template <class T, bool H>
+__global__ void __launch_bounds__(256) k_down_update(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                     int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
+  constexpr int ROWS = 32;
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k;
+  if (k <= j0 || j0 == 0) return;
+  const int r0 = blockIdx.x * ROWS;
+  if (r0 >= j0) return;
+  const int j1 = min(k, j0 + SB), len = j1 - j0;
+  const long long m = (long long)k + f.r;
+  const T* P = fac + f.p_off;
+  __shared__ z128 ys[SB];
+  __shared__ z128 red[8][ROWS];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
+  __syncthreads();
+  if (!H) {
+    z128 acc = mk(0, 0);
+    if (r0 + lane < j0) {
+      const T* a = P + (r0 + lane) + (long long)j0 * m;
+#pragma unroll 8
+      for (int c = wid; c < len; c += 8) acc += a[(long long)c * m] * ys[c];
+    }
+    red[wid][lane] = acc;
+    __syncthreads();
+    if (tid < ROWS && r0 + tid < j0) {
       z128 s = red[0][tid];
 #pragma unroll
       for (int q = 1; q < 8; ++q) s += red[q][tid];
@@ -388,49 +434,7 @@ __global__ void __launch_bounds__(256) k_down_off(const Front* __restrict__ fron
   } else {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      z128 a = accw[q];
-      for (int o = 16; o > 0; o >>= 1) {
-        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
-        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-      }
       const int row = r0 + wid + q * 8;
-      if (lane == 0 && row < k) y[f.col0 + row] -= a;
-    }
-  }
-}
-
-// Pivot rows above the step: y[0:j0] -= Upper[0:j0, j0:j1] y[j0:j1].  grid: (row chunks of 64, fronts).
-template <class T, bool H>
-__global__ void __launch_bounds__(256) k_down_update(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                     int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
-  const Front f = fronts[lvl_front[first + blockIdx.y]];
-  const int k = f.k;
-  if (k <= j0 || j0 == 0) return;
-  const int r0 = blockIdx.x * 64;
-  if (r0 >= j0) return;
-  const int j1 = min(k, j0 + SB), len = j1 - j0;
-  const long long m = (long long)k + f.r;
-  const T* P = fac + f.p_off;
-  __shared__ z128 ys[SB];
-  __shared__ z128 red[4][64];
-  const int tid = threadIdx.x;
-  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
-  __syncthreads();
-  if (!H) {
-    const int rr = tid & 63, cg = tid >> 6;
-    z128 acc = mk(0, 0);
-    if (r0 + rr < j0) {
-      const T* a = P + (r0 + rr) + (long long)j0 * m;
-#pragma unroll 4
-      for (int c = cg; c < len; c += 4) acc += a[(long long)c * m] * ys[c];
-    }
-    red[cg][rr] = acc;
-    __syncthreads();
-    if (tid < 64 && r0 + tid < j0) y[f.col0 + r0 + tid] -= red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-  } else {
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int rr = wid; rr < 64; rr += 8) {
-      const int row = r0 + rr;
       if (row >= j0) break;
       const T* l = P + j0 + (long long)row * m;
       z128 acc = mk(0, 0);
@@ -490,11 +494,11 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           act++;
           max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
         }
-        k_tri_block<T, H, true><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+        k_tri_block<T, H, true><<<act, 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
         LSA_LAUNCH_CHECK();
         launches++;
         if (max_rows > 0) {
-          k_up_update<T, H><<<dim3(cdiv(max_rows, 64), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, cb);
+          k_up_update<T, H><<<dim3(cdiv(max_rows, 32), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, cb);
           LSA_LAUNCH_CHECK();
           launches++;
         }
@@ -510,7 +514,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       int maxr = 0;
       for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[sym.lvl_front[q]].r);
       if (maxr > 0) {
-        k_down_off<T, H><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, y);
+        k_down_off<T, H><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, y);
         LSA_LAUNCH_CHECK();
         launches++;
       }
@@ -521,11 +525,11 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           act++;
         }
         if (act == 0) continue;
-        k_tri_block<T, H, false><<<act, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+        k_tri_block<T, H, false><<<act, 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
         LSA_LAUNCH_CHECK();
         launches++;
         if (j0 > 0) {
-          k_down_update<T, H><<<dim3(cdiv(j0, 64), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+          k_down_update<T, H><<<dim3(cdiv(j0, 32), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
           LSA_LAUNCH_CHECK();
           launches++;
         }

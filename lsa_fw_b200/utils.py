@@ -161,6 +161,26 @@ def clear_symbolic_cache() -> None:
     _FACTOR_REGISTRY.clear()
 
 
+_HASH_MEMO: dict[tuple, bytes] = {}
+
+
+def _array_digest(arr: np.ndarray) -> bytes:
+    """blake2b of an index array, memoised on (buffer address, length, sampled content, sum, xor) so that the
+    repeated solves of a sweep do not re-hash ~100 MB of pattern per call."""
+    arr = np.ascontiguousarray(arr)
+    n = arr.size
+    sample = arr[:: max(1, n // 4096)].tobytes()
+    key = (arr.__array_interface__["data"][0], n, arr.dtype.str, hashlib.blake2b(sample, digest_size=8).digest(),
+           int(arr.sum(dtype=np.uint64)) if n else 0, int(np.bitwise_xor.reduce(arr)) if n else 0)
+    dig = _HASH_MEMO.get(key)
+    if dig is None:
+        dig = hashlib.blake2b(arr.tobytes(), digest_size=16).digest()
+        if len(_HASH_MEMO) > 64:
+            _HASH_MEMO.clear()
+        _HASH_MEMO[key] = dig
+    return dig
+
+
 def _pattern_key(a: sp.csr_matrix, m: sp.csr_matrix | None, extra: tuple) -> str:
     hsh = hashlib.blake2b(digest_size=16)
     for mat in (a, m):
@@ -168,8 +188,8 @@ def _pattern_key(a: sp.csr_matrix, m: sp.csr_matrix | None, extra: tuple) -> str
             hsh.update(b"none")
             continue
         hsh.update(np.int64(mat.shape[0]).tobytes())
-        hsh.update(np.ascontiguousarray(mat.indptr).tobytes())
-        hsh.update(np.ascontiguousarray(mat.indices).tobytes())
+        hsh.update(_array_digest(mat.indptr))
+        hsh.update(_array_digest(mat.indices))
     hsh.update(repr(extra).encode())
     return hsh.hexdigest()
 
@@ -470,6 +490,7 @@ class iEpsSolver:  # noqa: N801
                     fs = h.factor(0.0, 1.0, scalar, 0.0)  # plain M^-1: an exactly singular M must raise
                 stats.update(factor_seconds=fs.seconds, factor_flops=fs.flops, n_perturbed=fs.n_perturbed,
                              n_row_swaps=fs.n_row_swaps, min_pivot=fs.min_pivot, max_pivot=fs.max_pivot,
+                             max_multiplier=fs.max_multiplier,
                              factor_kernels=fs.n_kernels)
                 self._factor_key = (sigma_fact, self._st_type)
                 _FACTOR_REGISTRY[(id(self._A), id(self._M) if self._M is not None else 0)] = weakref.ref(self)
@@ -511,11 +532,7 @@ class iEpsSolver:  # noqa: N801
     def _fetch_vectors(self) -> np.ndarray:
         if self._eigenvectors is None:
             X = self._handle.eigenvectors(self._nconv)
-            # fix the arbitrary phase: largest component real positive (deterministic output)
-            for i in range(X.shape[1]):
-                j = int(np.argmax(np.abs(X[:, i])))
-                if X[j, i] != 0:
-                    X[:, i] *= np.conj(X[j, i]) / abs(X[j, i])
+            # (the arbitrary phase is fixed on the device: largest component real positive)
             if self._problem_type in (iEpsProblemType.GHEP,) and self._M is not None:
                 # SLEPc normalises GHEP eigenvectors to unit B-norm
                 Mh = _as_csr(self._M)

@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.SymbolicInfo) == 4 * 8 + 8 * 7 + 8 + 32
     assert ctypes.sizeof(_lib.EigsParams) == 8 * 4 + 8 * 3 + 8 + 8
-    assert ctypes.sizeof(_lib.FactorStats) == 8 * 4 + 8 + 16
+    assert ctypes.sizeof(_lib.FactorStats) == 8 * 4 + 8 + 24
 
 
 def test_numeric_entry_points_fail_loudly_without_device():
