@@ -612,6 +612,8 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
   T* fac = (T*)h.d_fac;
   T* pool[2] = {(T*)h.d_pool[0], (T*)h.d_pool[1]};
   int launches = 0;
+  SweepTrace tr;
+  tr.begin(st);
   LSA_CUDA(cudaMemsetAsync(fac, 0, sym.fac_size * sizeof(T), st));
   DevStats init{};
   init.min_piv_bits = (unsigned long long)0x7ff0000000000000ULL;  // +inf
@@ -680,6 +682,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
         k_extend_add<T><<<dim3(gx, cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_child_idx, h.d_ea_map, slot,
                                                        fac, pool[(d + 1) & 1], pool[d & 1]);
         LSA_LAUNCH_CHECK();
+        tr.mark("extend_add", d, slot, gx, cnt);
         launches++;
       }
       // ---- blocked partial LU of every front of the chunk (fronts with k > j0 form a prefix)
@@ -708,18 +711,22 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
                                                         h.d_stats, panel_smem, ob0);
           }
           LSA_LAUNCH_CHECK();
+          tr.mark("panel_lu", d, j0, act, 1);
           k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv);
           LSA_LAUNCH_CHECK();
+          tr.mark("swap_trsm", d, j0, gx_cols, act);
           launches += 2;
           if (gx_rows > 0) {
             k_trsm_cols<T><<<dim3(gx_rows, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_stats);
             LSA_LAUNCH_CHECK();
+            tr.mark("trsm_cols", d, j0, gx_rows, act);
             launches++;
           }
           if (gx_tiles > 0) {
             k_front_gemm<T><<<dim3((unsigned)gx_tiles, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, ob0, 0, fac,
                                                                              pool[d & 1]);
             LSA_LAUNCH_CHECK();
+            tr.mark("gemm_inner", d, j0, (int)gx_tiles, act);
             launches++;
           }
         }
@@ -736,6 +743,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
         if (act2 > 0 && gx2 > 0) {
           k_front_gemm<T><<<dim3((unsigned)gx2, act2), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, ob0, 2, fac, pool[d & 1]);
           LSA_LAUNCH_CHECK();
+          tr.mark("gemm_outer", d, ob0, (int)gx2, act2);
           launches++;
         }
       }
@@ -749,10 +757,12 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
       if (gx_schur > 0) {
         k_front_gemm<T><<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, 0, 1, fac, pool[d & 1]);
         LSA_LAUNCH_CHECK();
+        tr.mark("gemm_schur", d, 0, gx_schur, cnt);
         launches++;
       }
     }
   }
+  tr.end();
   if (n_kernels) *n_kernels = launches;
 }
 

@@ -1,11 +1,57 @@
 // Declarations of the numeric phases (factor.cu, solve.cu, krylov.cu).
 #pragma once
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "handle.h"
 
 namespace lsa {
+
+// Optional per-launch timing of one sweep (LSA_TRACE=1, graphs off): prints level / kernel /
+// step / grid / microseconds to stderr.  Debug aid for the latency analysis in profiles/.
+struct SweepTrace {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  struct Rec { const char* name; int level, j0, gx, gy; cudaEvent_t ev; };
+  std::vector<Rec> recs;
+  cudaEvent_t start = nullptr;
+  void begin(cudaStream_t s) {
+    const char* e = getenv("LSA_TRACE");
+    on = e && atoi(e) != 0;
+    st = s;
+    if (on) {
+      cudaEventCreate(&start);
+      cudaEventRecord(start, st);
+    }
+  }
+  void mark(const char* name, int level, int j0, int gx, int gy) {
+    if (!on) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    recs.push_back({name, level, j0, gx, gy, ev});
+  }
+  void end() {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    cudaEvent_t prev = start;
+    double total = 0;
+    for (auto& r : recs) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, prev, r.ev);
+      total += ms;
+      fprintf(stderr, "TRACE level %2d %-14s j0 %5d grid %6d x %6d  %9.2f us\n", r.level, r.name, r.j0, r.gx, r.gy, ms * 1e3);
+      prev = r.ev;
+    }
+    fprintf(stderr, "TRACE total %.3f ms over %zu launches\n", total, recs.size());
+    for (auto& r : recs) cudaEventDestroy(r.ev);
+    cudaEventDestroy(start);
+    recs.clear();
+  }
+};
 
 // factor.cu
 template <class T>

@@ -16,6 +16,10 @@
 //                down sweep y_top = U11^-1 (y_top - U12 y_anc)
 //   trans = H :  up sweep   y_top = U11^-H x_top   ;  contrib  -= U12^H y_top
 //                down sweep y_top = L11^-H (y_top - L21^H y_anc) ; x = P^T y
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "factor.cuh"
 
 namespace lsa {
@@ -472,6 +476,8 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   z128* cb = h.d_cb;
   int launches = 0;
   constexpr int YMAX = 32768;
+  SweepTrace tr;
+  tr.begin(st);
   if (sym.n_iso > 0) {
     k_solve_decoupled<T, H><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, x, y);
     LSA_LAUNCH_CHECK();
@@ -484,6 +490,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       const int cnt = std::min(YMAX, cnt_all - y0), first = lbeg + y0;
       k_up_gather<!H><<<cnt, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
       LSA_LAUNCH_CHECK();
+      tr.mark("up_gather", d, 0, cnt, 1);
       launches++;
       const int maxk = sym.fronts[sym.lvl_front[first]].k;
       for (int j0 = 0; j0 < maxk; j0 += SB) {
@@ -496,10 +503,12 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         }
         k_tri_block<T, H, true><<<act, 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
         LSA_LAUNCH_CHECK();
+        tr.mark("up_tri", d, j0, act, 1);
         launches++;
         if (max_rows > 0) {
           k_up_update<T, H><<<dim3(cdiv(max_rows, 32), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, cb);
           LSA_LAUNCH_CHECK();
+          tr.mark("up_update", d, j0, cdiv(max_rows, 32), act);
           launches++;
         }
       }
@@ -516,6 +525,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       if (maxr > 0) {
         k_down_off<T, H><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, y);
         LSA_LAUNCH_CHECK();
+        tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
         launches++;
       }
       for (int j0 = ((maxk - 1) / SB) * SB; j0 >= 0; j0 -= SB) {
@@ -527,10 +537,12 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         if (act == 0) continue;
         k_tri_block<T, H, false><<<act, 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
         LSA_LAUNCH_CHECK();
+        tr.mark("down_tri", d, j0, act, 1);
         launches++;
         if (j0 > 0) {
           k_down_update<T, H><<<dim3(cdiv(j0, 32), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
           LSA_LAUNCH_CHECK();
+          tr.mark("down_update", d, j0, cdiv(j0, 32), act);
           launches++;
         }
       }
@@ -548,6 +560,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     LSA_CUDA(cudaMemcpyAsync(x, y, (size_t)h.n * sizeof(z128), cudaMemcpyDeviceToDevice, st));
   }
   launches++;
+  tr.end();
   if (n_kernels) *n_kernels += launches;
 }
 

@@ -40,12 +40,13 @@ class Emulator:
         self.nlevels = info.n_levels
 
     # ---- factorisation of alpha A + beta M (values in the caller's CSR entry order)
-    def factor(self, a_vals, m_vals, alpha, beta, dtype=np.complex128):
+    def factor(self, a_vals, m_vals, alpha, beta, dtype=np.complex128, pivot_block=128):
         fac = np.zeros(self.fac_size, dtype=dtype)
         fac[self.a_dst] = alpha * a_vals
         if m_vals is not None:
             np.add.at(fac, self.m_dst, beta * m_vals)
         self.fac = fac
+        self.max_multiplier = 0.0
         ns = self.ns
         self.cb = [None] * ns
         self.piv = [None] * ns
@@ -70,10 +71,13 @@ class Emulator:
                 Q[np.ix_(mp[top], mp[bot] - k)] += cbc[np.ix_(top, bot)]
                 Cb[np.ix_(mp[bot] - k, mp[bot] - k)] += cbc[np.ix_(bot, bot)]
                 self.cb[c] = None
-            # partial LU, pivot search restricted to rows [j, k)
+            # partial LU, pivot search restricted to the rows of the current 128-wide outer block of
+            # the pivot block (as k_panel_lu does: rows below it still miss deferred updates)
             piv = np.arange(k)
             for j in range(k):
-                p = j + int(np.argmax(np.abs(P[j:k, j].real) + np.abs(P[j:k, j].imag)))
+                hi = min(k, (j // pivot_block + 1) * pivot_block)
+                p = j + int(np.argmax(np.abs(P[j:hi, j].real) + np.abs(P[j:hi, j].imag)))
+                self.max_multiplier = max(self.max_multiplier, float(np.abs(P[j + 1:, j] / P[p, j]).max()) if j + 1 < m else 0.0)
                 piv[j] = p
                 if p != j:
                     P[[j, p], :] = P[[p, j], :]

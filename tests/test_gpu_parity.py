@@ -99,10 +99,10 @@ def test_real_eigenvector_has_no_imaginary_part(golden):
 def test_membrane_table_of_the_reference(golden):
     g = golden["membrane"]
     pm = pencils.membrane_pencil(*g["mesh"], g["a"], g["b"])
-    cfg = L.EigensolverConfig(num_eig=30, problem_type=L.iEpsProblemType.GHEP, atol=1e-12, max_it=200)
+    cfg = L.EigensolverConfig(num_eig=20, problem_type=L.iEpsProblemType.GHEP, atol=1e-12, max_it=200)
     es = L.EigenSolver(L.iPETScMatrix(pm.A), L.iPETScMatrix(pm.M), cfg, check_hermitian=False)
     es.solver.set_st_type(L.iSTType.SINVERT)
-    es.solver.set_target(15.0)
+    es.solver.set_target(17.5)   # the 15 lowest modes (3.08 .. 32.08) lie closer to 17.5 than the spurious 1
     lam = np.sort([v for v, _ in es.solve()])
     lam = lam[np.abs(lam - 1.0) > 1e-6][: g["modes"]]
     ana = pencils.membrane_analytic(g["modes"], g["a"], g["b"])
