@@ -151,10 +151,12 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
   // pivot candidates: rows of the current outer block only.  Rows below it have not yet received
   // the deferred rank-128 updates in the columns right of the block, so they must not be swapped in.
   const int pcand = min(pk, ob0 + OB - j0);
+  // ... and ONLY those rows are factored here (<= 128 x 32, always fits in shared memory); the rows
+  // below the outer block get their L entries from k_trsm_cols, in parallel over many CTAs.
   T* G = fac + f.p_off + j0 + (long long)j0 * m;  // panel origin in global memory
   extern __shared__ unsigned char smem_raw[];
   T* sm = reinterpret_cast<T*>(smem_raw);
-  const bool use_smem = (long long)pk * jb * (long long)sizeof(T) <= (long long)smem_bytes;
+  const bool use_smem = (long long)pcand * jb * (long long)sizeof(T) <= (long long)smem_bytes;
   __shared__ ArgMax s_red[8];
   __shared__ int s_piv;
   __shared__ T s_inv;
@@ -163,13 +165,13 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
   long long ld = m;
   double lmax = 0.0;  // largest multiplier (growth monitor)
   if (use_smem) {
-    for (int e = tid; e < pk * jb; e += blockDim.x) {
-      const int il = e % pk, cl = e / pk;
-      sm[il + (long long)cl * pk] = G[il + (long long)cl * m];
+    for (int e = tid; e < pcand * jb; e += blockDim.x) {
+      const int il = e % pcand, cl = e / pcand;
+      sm[il + (long long)cl * pcand] = G[il + (long long)cl * m];
     }
     __syncthreads();
     base = sm;
-    ld = pk;
+    ld = pcand;
   }
   for (int jl = 0; jl < jb; ++jl) {
     // 1. pivot search in column jl, local rows [jl, pk)
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
     __syncthreads();
     // 3. scale the column and rank-1 update of the remaining panel columns
     const T inv = s_inv;
-    for (int i = jl + 1 + tid; i < pk; i += blockDim.x) {
+    for (int i = jl + 1 + tid; i < pcand; i += blockDim.x) {
       const T l = base[i + jl * ld] * inv;
       lmax = fmax(lmax, abs1(l));
       base[i + jl * ld] = l;
@@ -235,9 +237,9 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
     __syncthreads();
   }
   if (use_smem) {
-    for (int e = tid; e < pk * jb; e += blockDim.x) {
-      const int il = e % pk, cl = e / pk;
-      G[il + (long long)cl * m] = sm[il + (long long)cl * pk];
+    for (int e = tid; e < pcand * jb; e += blockDim.x) {
+      const int il = e % pcand, cl = e / pcand;
+      G[il + (long long)cl * m] = sm[il + (long long)cl * pcand];
     }
   }
   for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -335,16 +337,20 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
 
 // ----------------------------------------------------------------------------------- L21 panel
 
-// Rows [k, m) of the panel columns: X U_jj = B.  One thread per row; grid (row groups of 128, fronts).
+// Rows below the current outer block (remaining pivot rows and contribution rows) of the panel
+// columns: X U_jj = B.  One thread per row; grid (row groups of 128, fronts).
 template <class T>
 __global__ void __launch_bounds__(128) k_trsm_cols(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                   int first, int j0, T* __restrict__ fac, DevStats* st) {
+                                                   int first, int j0, int ob0, T* __restrict__ fac, DevStats* st) {
   const Front f = fronts[lvl_front[first + blockIdx.y]];
-  const int k = f.k, r = f.r;
-  if (k <= j0 || r == 0) return;
+  const int k = f.k;
+  if (k <= j0) return;
+  const int rbase = min(ob0 + OB, k);           // first row below the outer block
+  const int r = (int)((long long)k + f.r - rbase);  // rows to process: rest of the pivot rows + CB rows
+  if (r <= 0) return;
   if (blockIdx.x * 128 >= r) return;
   const int jb = min(NB, k - j0);
-  const long long m = (long long)k + r;
+  const long long m = (long long)k + f.r;
   T* P = fac + f.p_off;
   __shared__ T s_U[NB * NB];  // column-major upper triangle, diagonal holds reciprocals
   for (int e = threadIdx.x; e < NB * NB; e += 128) {
@@ -359,7 +365,7 @@ __global__ void __launch_bounds__(128) k_trsm_cols(const Front* __restrict__ fro
   __syncthreads();
   const int row = blockIdx.x * 128 + threadIdx.x;
   if (row >= r) return;
-  T* x = P + k + row + (long long)j0 * m;
+  T* x = P + rbase + row + (long long)j0 * m;
   T xs[NB];
   double lmax = 0.0;
 #pragma unroll
@@ -698,13 +704,13 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
             const int jb = std::min(NB, f.k - j0), j1 = j0 + jb, ob1 = std::min(ob0 + OB, f.k);
             const long long m = (long long)f.k + f.r;
             gx_cols = std::max(gx_cols, cdiv((long long)j0 + (f.k - j1) + f.r, 128));
-            gx_rows = std::max(gx_rows, cdiv(f.r, 128));
+            gx_rows = std::max(gx_rows, cdiv(m - ob1, 128));
             gx_tiles = std::max(gx_tiles, tiles(m - j1, ob1 - j1) + tiles(ob1 - j1, f.k - ob1) + tiles(ob1 - j1, f.r));
           }
           if (act == 0) break;
           {
             // the level's fronts are sorted by descending k: the first one has the tallest panel
-            const int max_pk = sym.fronts[sym.lvl_front[first]].k - j0;
+            const int max_pk = std::min(sym.fronts[sym.lvl_front[first]].k, ob0 + OB) - j0;
             const long long want = (long long)max_pk * NB * (long long)sizeof(T);
             const int panel_smem = (int)std::min<long long>(want, PANEL_SMEM_CAP);
             k_panel_lu<T><<<act, 256, panel_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs,
@@ -717,7 +723,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
           tr.mark("swap_trsm", d, j0, gx_cols, act);
           launches += 2;
           if (gx_rows > 0) {
-            k_trsm_cols<T><<<dim3(gx_rows, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_stats);
+            k_trsm_cols<T><<<dim3(gx_rows, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, ob0, fac, h.d_stats);
             LSA_LAUNCH_CHECK();
             tr.mark("trsm_cols", d, j0, gx_rows, act);
             launches++;
