@@ -56,7 +56,7 @@ void free_device(lsa_handle_impl& h) {
     h.d_pool[q] = nullptr;
     h.pool_capacity_bytes[q] = 0;
   }
-  dfree(h.d_x); dfree(h.d_w); dfree(h.d_t); dfree(h.d_cb); dfree(h.d_io); dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q);
+  dfree(h.d_x); dfree(h.d_w); dfree(h.d_t); dfree(h.d_t2); dfree(h.d_cb); dfree(h.d_io); dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q);
   dfree(h.d_part); dfree(h.d_npart); dfree(h.d_h); dfree(h.d_brow); dfree(h.d_ywork); dfree(h.d_r1); dfree(h.d_r2);
   dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
   h.V_cols = 0; h.X_cols = 0; h.ncv_alloc = 0; h.scalar = -1; h.have_values = false;
@@ -358,7 +358,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     h->d_ipiv = dalloc<int>(n);
     h->d_gperm = dalloc<int>(n);
     h->d_stats = dalloc<DevStats>(1);
-    h->d_x = dalloc<z128>(n); h->d_w = dalloc<z128>(n); h->d_t = dalloc<z128>(n); h->d_io = dalloc<z128>(n);
+    h->d_x = dalloc<z128>(n); h->d_w = dalloc<z128>(n); h->d_t = dalloc<z128>(n); h->d_t2 = dalloc<z128>(n); h->d_io = dalloc<z128>(n);
     h->d_r1 = dalloc<z128>(n); h->d_r2 = dalloc<z128>(n); h->d_r3 = dalloc<z128>(n);
     h->d_cb = dalloc<z128>(sym.st_idx.size());
     h->d_part = dalloc<z128>((size_t)1024 * 128);

@@ -103,6 +103,7 @@ struct lsa_handle_impl {
   z128* d_x = nullptr;     // n
   z128* d_w = nullptr;     // n
   z128* d_t = nullptr;     // n
+  z128* d_t2 = nullptr;    // n (second sweep vector)
   z128* d_cb = nullptr;    // total structure length: per-front contribution vectors
   z128* d_io = nullptr;    // n staging for host vectors
   z128* d_V = nullptr;     // n x (ncv+1)

@@ -215,130 +215,6 @@ __global__ void __launch_bounds__(256) k_up_gather(const Front* __restrict__ fro
   for (int i = threadIdx.x; i < p.k; i += blockDim.x) y[p.col0 + i] = x[PERM ? gperm[p.col0 + i] : p.col0 + i];
 }
 
-// y[j0:j1) <- Op y[j0:j1) with Op the explicitly inverted 128 x 128 diagonal block of this step:
-//   UP,  N : L^-1   (unit lower)         UP,  H : (U^-1)^H (lower)
-//   DOWN,N : U^-1   (upper)              DOWN,H : (L^-1)^H (unit upper)
-// One CTA (256 threads) per front.  N reads rows contiguously (thread per row, two column phases);
-// H reads columns contiguously (warp per row).
-template <class T, bool H, bool UP>
-__global__ void __launch_bounds__(1024) k_tri_block(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                    int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
-  const Front f = fronts[lvl_front[first + blockIdx.x]];
-  const int k = f.k;
-  if (k <= j0) return;
-  const int len = min(SB, k - j0);
-  const long long m = (long long)k + f.r;
-  const T* D = fac + f.p_off + j0 + (long long)j0 * m;  // block origin
-  __shared__ z128 ys[SB];
-  __shared__ z128 part[8][SB];
-  const int tid = threadIdx.x;
-  z128* yo = y + f.col0 + j0;
-  if (tid < len) ys[tid] = yo[tid];
-  __syncthreads();
-  if (!H) {
-    // thread (row i, column group cg): 1024 independent short dot products -> deep memory parallelism
-    const int i = tid & (SB - 1), cg = tid >> 7;
-    z128 acc = mk(0, 0);
-    if (i < len) {
-      const T* row = D + i;
-      if (UP) {
-#pragma unroll 8
-        for (int c = cg; c < i; c += 8) acc += row[(long long)c * m] * ys[c];
-      } else {
-#pragma unroll 8
-        for (int c = i + cg; c < len; c += 8) acc += row[(long long)c * m] * ys[c];
-      }
-    }
-    part[cg][i] = acc;
-    __syncthreads();
-    if (tid < len) {
-      z128 s = part[0][tid];
-#pragma unroll
-      for (int q = 1; q < 8; ++q) s += part[q][tid];
-      yo[tid] = UP ? s + ys[tid] : s;  // unit diagonal of L^-1
-    }
-  } else {
-    const int lane = tid & 31, wid = tid >> 5;  // 32 warps, 4 rows each
-    for (int i = wid; i < len; i += 32) {
-      const T* col = D + (long long)i * m;
-      z128 acc = mk(0, 0);
-      if (UP) {
-        for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
-      } else {
-        for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-      }
-      if (lane == 0) yo[i] = UP ? acc : acc + ys[i];
-    }
-  }
-}
-
-// Rows below the step: remaining pivot rows (-> y) and contribution rows (-> cb).
-// grid: (row chunks of 64, fronts); block 256.
-template <class T, bool H>
-__global__ void __launch_bounds__(256) k_up_update(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                   int first, int j0, const T* __restrict__ fac, z128* __restrict__ y,
-                                                   z128* __restrict__ cb) {
-  constexpr int ROWS = 32;
-  const Front f = fronts[lvl_front[first + blockIdx.y]];
-  const int k = f.k;
-  if (k <= j0) return;
-  const int j1 = min(k, j0 + SB), len = j1 - j0;
-  const long long m = (long long)k + f.r;
-  const int nrows = (int)(m - j1);
-  const int r0 = blockIdx.x * ROWS;
-  if (r0 >= nrows) return;
-  const T* P = fac + f.p_off;
-  const T* Q = fac + f.q_off;
-  __shared__ z128 ys[SB];
-  __shared__ z128 red[8][ROWS];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
-  __syncthreads();
-  if (!H) {
-    // axpy type: thread (row = lane, column group = warp), rows contiguous in memory
-    const int row = j1 + r0 + lane;  // local front row
-    z128 acc = mk(0, 0);
-    if (r0 + lane < nrows) {
-      const T* a = P + row + (long long)j0 * m;
-#pragma unroll 8
-      for (int c = wid; c < len; c += 8) acc += a[(long long)c * m] * ys[c];
-    }
-    red[wid][lane] = acc;
-    __syncthreads();
-    if (tid < ROWS && r0 + tid < nrows) {
-      z128 s = red[0][tid];
-#pragma unroll
-      for (int q = 1; q < 8; ++q) s += red[q][tid];
-      const int rw = j1 + r0 + tid;
-      if (rw < k) y[f.col0 + rw] -= s;
-      else cb[f.st0 + (rw - k)] -= s;
-    }
-  } else {
-    // dot type: warp per row, lanes along the contiguous column of U
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int rr = wid + q * 8;
-      if (r0 + rr >= nrows) break;
-      const int row = j1 + r0 + rr;
-      const T* u = row < k ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
-      z128 acc = mk(0, 0);
-      for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * ys[c];
-      for (int o = 16; o > 0; o >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-      }
-      if (lane == 0) {
-        if (row < k) y[f.col0 + row] -= acc;
-        else cb[f.st0 + (row - k)] -= acc;
-      }
-    }
-  }
-}
-
 // --------------------------------------------------------------------------------------- down sweep
 
 // y_top -= Off * anc[ancestor rows].  N: Off = U12 = Q (k x r);  H: Off = L21^H, L21 = P[k:m, 0:k].
@@ -402,52 +278,118 @@ __global__ void __launch_bounds__(1024) k_down_off(const Front* __restrict__ fro
   }
 }
 
-// Pivot rows above the step: y[0:j0] -= Upper[0:j0, j0:j1] y[j0:j1].  grid: (row chunks of 64, fronts).
-template <class T, bool H>
-__global__ void __launch_bounds__(256) k_down_update(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                     int first, int j0, const T* __restrict__ fac, z128* __restrict__ y) {
-  constexpr int ROWS = 32;
+// ---------------------------------------------------------------------------- fused sweep steps
+//
+// One launch per 128-pivot step: every CTA first applies the explicitly inverted diagonal block to
+// the step's slice of the input vector (a 128 x 128 triangular GEMV, redundantly per CTA: the block
+// is L2 resident after the first read) and then updates its own 128 rows with the result.  CTA 0 also
+// stores the solved slice to `out`.  Input and output vectors are distinct (in: pre-solve values,
+// out: solved values), so no CTA can read a slice that another one has already overwritten.
+//
+//   up   (UP = true ):  z = Op in[j0:j1) ;  rows below:  in[row] / cb[row-k]  -=  Off[row, :] z
+//   down (UP = false):  z = Op in[j0:j1) ;  rows above:  in[row]              -=  Off[row, :] z
+//        Op / Off:   up,N: L^-1 / L      up,H: (U^-1)^H / U^H     down,N: U^-1 / U     down,H: (L^-1)^H / L^H
+template <class T, bool H, bool UP>
+__global__ void __launch_bounds__(1024) k_step(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                               int first, int j0, const T* __restrict__ fac, z128* in, z128* out,
+                                               z128* __restrict__ cb) {
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k;
-  if (k <= j0 || j0 == 0) return;
-  const int r0 = blockIdx.x * ROWS;
-  if (r0 >= j0) return;
-  const int j1 = min(k, j0 + SB), len = j1 - j0;
+  if (k <= j0) return;
+  const int len = min(SB, k - j0), j1 = j0 + len;
   const long long m = (long long)k + f.r;
+  const int nrows = UP ? (int)(m - j1) : j0;          // rows to update
+  const int r0 = blockIdx.x * SB;
+  if (blockIdx.x > 0 && r0 >= nrows) return;
   const T* P = fac + f.p_off;
+  const T* Q = fac + f.q_off;
+  const T* D = P + j0 + (long long)j0 * m;            // diagonal block origin
   __shared__ z128 ys[SB];
-  __shared__ z128 red[8][ROWS];
+  __shared__ z128 zs[SB];
+  __shared__ z128 part[8][SB];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid < len) ys[tid] = y[f.col0 + j0 + tid];
+  if (tid < len) ys[tid] = in[f.col0 + j0 + tid];
   __syncthreads();
+  // ---- phase 1: z = Op ys
   if (!H) {
+    const int i = tid & (SB - 1), cg = tid >> 7;
     z128 acc = mk(0, 0);
-    if (r0 + lane < j0) {
-      const T* a = P + (r0 + lane) + (long long)j0 * m;
+    if (i < len) {
+      const T* row = D + i;
+      if (UP) {
 #pragma unroll 8
-      for (int c = wid; c < len; c += 8) acc += a[(long long)c * m] * ys[c];
+        for (int c = cg; c < i; c += 8) acc += row[(long long)c * m] * ys[c];
+      } else {
+#pragma unroll 8
+        for (int c = i + cg; c < len; c += 8) acc += row[(long long)c * m] * ys[c];
+      }
     }
-    red[wid][lane] = acc;
+    part[cg][i] = acc;
     __syncthreads();
-    if (tid < ROWS && r0 + tid < j0) {
-      z128 s = red[0][tid];
+    if (tid < len) {
+      z128 sum = part[0][tid];
 #pragma unroll
-      for (int q = 1; q < 8; ++q) s += red[q][tid];
-      y[f.col0 + r0 + tid] -= s;
+      for (int q = 1; q < 8; ++q) sum += part[q][tid];
+      zs[tid] = UP ? sum + ys[tid] : sum;  // unit diagonal of L^-1
     }
   } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int row = r0 + wid + q * 8;
-      if (row >= j0) break;
-      const T* l = P + j0 + (long long)row * m;
+    for (int i = wid; i < len; i += 32) {
+      const T* col = D + (long long)i * m;
       z128 acc = mk(0, 0);
-      for (int c = lane; c < len; c += 32) acc += conj_(l[c]) * ys[c];
+      if (UP) {
+        for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
+      } else {
+        for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
+      }
       for (int o = 16; o > 0; o >>= 1) {
         acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
         acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
       }
-      if (lane == 0) y[f.col0 + row] -= acc;
+      if (lane == 0) zs[i] = UP ? acc : acc + ys[i];  // unit diagonal of L^-H
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < len) out[f.col0 + j0 + tid] = zs[tid];
+  if (r0 >= nrows) return;
+  // ---- phase 2: update this CTA's rows with z
+  if (!H) {
+    const int rr = tid & (SB - 1), cg = tid >> 7;
+    const int row = (UP ? j1 : 0) + r0 + rr;  // front-local row
+    z128 acc = mk(0, 0);
+    if (r0 + rr < nrows) {
+      const T* a = P + row + (long long)j0 * m;
+#pragma unroll 8
+      for (int c = cg; c < len; c += 8) acc += a[(long long)c * m] * zs[c];
+    }
+    __syncthreads();  // part[] is being reused
+    part[cg][rr] = acc;
+    __syncthreads();
+    if (tid < SB && r0 + tid < nrows) {
+      z128 sum = part[0][tid];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) sum += part[q][tid];
+      const int rw = (UP ? j1 : 0) + r0 + tid;
+      if (!UP || rw < k) in[f.col0 + rw] -= sum;
+      else cb[f.st0 + (rw - k)] -= sum;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rr = wid + q * 32;
+      if (r0 + rr >= nrows) break;
+      const int row = (UP ? j1 : 0) + r0 + rr;
+      // column `row` of U (up) / of L (down), entries of the step's rows: contiguous in memory
+      const T* u = (!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
+      z128 acc = mk(0, 0);
+      for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * zs[c];
+      for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      }
+      if (lane == 0) {
+        if (!UP || row < k) in[f.col0 + row] -= acc;
+        else cb[f.st0 + (row - k)] -= acc;
+      }
     }
   }
 }
@@ -472,7 +414,8 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   const Symbolic& sym = h.sym;
   cudaStream_t st = h.stream;
   const T* fac = (const T*)h.d_fac;
-  z128* y = h.d_t;
+  z128* y = h.d_t;    // up sweep: pre-solve values;  down sweep: final values
+  z128* z = h.d_t2;   // up sweep: solved values;     down sweep: pre-solve values
   z128* cb = h.d_cb;
   int launches = 0;
   constexpr int YMAX = 32768;
@@ -501,16 +444,11 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           act++;
           max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
         }
-        k_tri_block<T, H, true><<<act, 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+        const int gx = std::max(1, cdiv(max_rows, SB));
+        k_step<T, H, true><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, z, cb);
         LSA_LAUNCH_CHECK();
-        tr.mark("up_tri", d, j0, act, 1);
+        tr.mark("up_step", d, j0, gx, act);
         launches++;
-        if (max_rows > 0) {
-          k_up_update<T, H><<<dim3(cdiv(max_rows, 32), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, cb);
-          LSA_LAUNCH_CHECK();
-          tr.mark("up_update", d, j0, cdiv(max_rows, 32), act);
-          launches++;
-        }
       }
     }
   }
@@ -523,7 +461,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       int maxr = 0;
       for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[sym.lvl_front[q]].r);
       if (maxr > 0) {
-        k_down_off<T, H><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, y);
+        k_down_off<T, H><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
         LSA_LAUNCH_CHECK();
         tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
         launches++;
@@ -535,16 +473,11 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           act++;
         }
         if (act == 0) continue;
-        k_tri_block<T, H, false><<<act, 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
+        const int gx = std::max(1, cdiv(j0, SB));
+        k_step<T, H, false><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
         LSA_LAUNCH_CHECK();
-        tr.mark("down_tri", d, j0, act, 1);
+        tr.mark("down_step", d, j0, gx, act);
         launches++;
-        if (j0 > 0) {
-          k_down_update<T, H><<<dim3(cdiv(j0, 32), act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y);
-          LSA_LAUNCH_CHECK();
-          tr.mark("down_update", d, j0, cdiv(j0, 32), act);
-          launches++;
-        }
       }
       if (H) {
         k_level_unpermute<<<cnt, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_gperm, y, x);

@@ -195,9 +195,10 @@ def _pattern_key(a: sp.csr_matrix, m: sp.csr_matrix | None, extra: tuple) -> str
 
 
 def _as_csr(mat) -> sp.csr_matrix:
-    m = mat.as_scipy_array() if hasattr(mat, "as_scipy_array") else sp.csr_matrix(mat)
-    m = sp.csr_matrix(m)
-    if not m.has_canonical_format:
+    m = mat.as_scipy_array() if hasattr(mat, "as_scipy_array") else mat
+    if not sp.isspmatrix_csr(m):
+        m = sp.csr_matrix(m)
+    if not m.has_canonical_format:  # cached on the matrix object after the first check
         m = m.copy()
         m.sum_duplicates()
     return m
@@ -553,12 +554,17 @@ class iEpsSolver:  # noqa: N801
         if not 0 <= idx < self._nconv:
             raise IndexError(f"eigenvector index {idx} out of range (converged: {self._nconv})")
         x = self._fetch_vectors()[:, idx]
+        from .carriers import _RawVec
+
+        def wrap(a: np.ndarray) -> iPETScVector:  # one copy, not two
+            return iPETScVector(_RawVec(np.array(a, copy=True)))
+
         if self._complex_mode:
-            return iComplexPETScVector(iPETScVector(x.copy()))
+            return iComplexPETScVector(wrap(x))
         vi = x.imag
         if np.linalg.norm(vi) <= 1e-6:
-            return iComplexPETScVector(iPETScVector(x.real.copy()))
-        return iComplexPETScVector(iPETScVector(x.real.copy()), iPETScVector(vi.copy()))
+            return iComplexPETScVector(wrap(x.real))
+        return iComplexPETScVector(wrap(x.real), wrap(vi))
 
     def get_eigenpair(self, idx: int) -> tuple[float | complex, iComplexPETScVector]:
         """Get (eigenvalue, eigenvector) tuple at index idx."""
