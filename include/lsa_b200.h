@@ -126,6 +126,12 @@ const char* lsa_version(void);
 int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx, const int64_t* m_rowptr,
                 const int32_t* m_colidx, int32_t leaf_size, int32_t dim, const double* coords,
                 const uint8_t* order_last, int32_t nthreads);
+/* Tuning knobs, to be set before lsa_analyze / lsa_factor:
+ *   "coupled_fraction" (default 0.5): an unknown with a structurally zero diagonal (pressure) is eliminated
+ *       no earlier than the front in which this share of its coupled regular unknowns has been eliminated
+ *       (1.0 = all of them: most robust, ~+40-70 % flops in 2-D);
+ *   "use_graphs" (default 1): replay the triangular-solve sweeps from CUDA graphs. */
+int lsa_set_option(lsa_handle* h, const char* name, double value);
 int lsa_symbolic_info_get(const lsa_handle* h, lsa_symbolic_info* out);
 /* Copies a named internal array (perm, iperm, sn_ptr, st_ptr, st_idx, ea_map, parent, level, front_k,
  * front_r, p_off, q_off, c_off, a_dst, m_dst, lvl_ptr, lvl_front) to `out`; returns its length in elements

@@ -103,6 +103,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lsa_last_error.argtypes = [vp]
     lib.lsa_last_error.restype = C.c_char_p
     lib.lsa_analyze.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32]
+    lib.lsa_set_option.argtypes = [vp, C.c_char_p, dbl]
     lib.lsa_symbolic_info_get.argtypes = [vp, C.POINTER(SymbolicInfo)]
     lib.lsa_symbolic_array.argtypes = [vp, C.c_char_p, vp, i64]
     lib.lsa_symbolic_array.restype = i64
@@ -123,7 +124,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
 
 
 EXPORTS = [
-    "lsa_version", "lsa_create", "lsa_destroy", "lsa_last_error", "lsa_analyze", "lsa_symbolic_info_get",
+    "lsa_version", "lsa_create", "lsa_destroy", "lsa_last_error", "lsa_analyze", "lsa_set_option", "lsa_symbolic_info_get",
     "lsa_symbolic_array", "lsa_set_values", "lsa_factor", "lsa_solve", "lsa_spmv", "lsa_eigs",
     "lsa_get_eigenvalues", "lsa_get_eigenvectors", "lsa_get_residuals", "lsa_get_counters", "lsa_sync",
     "lsa_dense_schur", "lsa_gemm_bench",
@@ -164,6 +165,9 @@ class Handle:
         if rc < 0:
             raise LsaError(rc, self.lib.lsa_last_error(self._h).decode(errors="replace"))
         return rc
+
+    def set_option(self, name: str, value: float) -> None:
+        self.check(self.lib.lsa_set_option(self._h, name.encode(), float(value)))
 
     # -- symbolic
     def analyze(self, a_rowptr, a_colidx, m_rowptr=None, m_colidx=None, *, leaf_size=64, coords=None,

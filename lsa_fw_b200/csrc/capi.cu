@@ -296,6 +296,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   opt.coords = coords;
   opt.order_last = order_last;
   opt.nthreads = nthreads;
+  opt.coupled_fraction = h->coupled_fraction;
   if (const char* e = getenv("LSA_COUPLED_FRACTION")) opt.coupled_fraction = atof(e);
   if (h->has_m) analyze(n, urow.data(), ucol.data(), opt, h->sym);
   else analyze(n, (const long long*)a_rowptr, a_colidx, opt, h->sym);
@@ -372,6 +373,20 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     LSA_CUDA(cudaStreamSynchronize(st));
   }
   LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_set_option(lsa_handle* h, const char* name, double value) {
+  if (!h || !name) return LSA_ERR_ARG;
+  const std::string nm(name);
+  if (nm == "coupled_fraction") {
+    if (!(value >= 0.0 && value <= 1.0)) return fail(h, LSA_ERR_ARG, "coupled_fraction must lie in [0, 1]");
+    h->coupled_fraction = value;
+  } else if (nm == "use_graphs") {
+    h->use_graphs = value != 0.0;
+  } else {
+    return fail(h, LSA_ERR_ARG, "unknown option " + nm);
+  }
   return LSA_OK;
 }
 
@@ -503,7 +518,9 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   cudaEventRecord(e0, st);
   h->scalar = -1;
   drop_solve_graphs(*h);
-  if (const char* e = getenv("LSA_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
+  if (const char* e = getenv("LSA_NO_GRAPHS")) {
+    if (atoi(e) != 0) h->use_graphs = false;
+  }
   if (scalar == LSA_C128) {
     factor_numeric<z128>(*h, alpha, beta, tiny_abs, &nk);
     post_factor<z128>(*h, &nk);

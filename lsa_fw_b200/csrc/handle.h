@@ -145,6 +145,7 @@ struct lsa_handle_impl {
   };
   std::vector<SolveGraph> solve_graphs;
   bool use_graphs = true;
+  double coupled_fraction = 0.5;
 };
 
 }  // namespace lsa

@@ -221,12 +221,12 @@ __global__ void __launch_bounds__(256) k_up_gather(const Front* __restrict__ fro
 // `anc` holds the FINAL values of the ancestors: the work vector itself for N; for H the output
 // vector, because each front applies its own P^T as soon as its pivot block is solved.
 // grid: (pivot-row chunks of 64, fronts); block 256.
-template <class T, bool H>
-__global__ void __launch_bounds__(1024) k_down_off(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+template <class T, bool H, int NW>
+__global__ void __launch_bounds__(NW * 32) k_down_off(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                    int first, const int* __restrict__ st_idx, const T* __restrict__ fac,
                                                    const z128* anc, z128* y) {
-  constexpr int ROWS = 32;   // pivot rows per CTA; 32 warps = 32 column groups (N) / one row each (H)
-  constexpr int CHUNK = 1024;
+  constexpr int ROWS = 32;   // pivot rows per CTA; NW warps = NW column groups (N) / NW rows per pass (H)
+  constexpr int CHUNK = NW * 32;
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k, r = f.r;
   const int r0 = blockIdx.x * ROWS;
@@ -236,11 +236,13 @@ __global__ void __launch_bounds__(1024) k_down_off(const Front* __restrict__ fro
   const T* Q = fac + f.q_off;
   const int* idx = st_idx + f.st0;
   __shared__ z128 xs[CHUNK];
-  __shared__ z128 red[32][ROWS + 1];
+  __shared__ z128 red[NW][ROWS + 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   z128 acc = mk(0, 0);
   const int rowN = r0 + lane;  // N: this thread's pivot row
-  const int rowH = r0 + wid;   // H: this warp's pivot row
+  z128 accH[ROWS / NW];        // H: rows wid, wid + NW, ...
+#pragma unroll
+  for (int q = 0; q < ROWS / NW; ++q) accH[q] = mk(0, 0);
   for (int c0 = 0; c0 < r; c0 += CHUNK) {
     const int len = min(CHUNK, r - c0);
     __syncthreads();
@@ -250,13 +252,17 @@ __global__ void __launch_bounds__(1024) k_down_off(const Front* __restrict__ fro
       if (rowN < k) {
         const T* a = Q + rowN + (long long)c0 * k;
 #pragma unroll 8
-        for (int c = wid; c < len; c += 32) acc += a[(long long)c * k] * xs[c];
+        for (int c = wid; c < len; c += NW) acc += a[(long long)c * k] * xs[c];
       }
     } else {
-      if (rowH < k) {
-        const T* l = P + k + c0 + (long long)rowH * m;
+#pragma unroll
+      for (int q = 0; q < ROWS / NW; ++q) {
+        const int rowH = r0 + wid + q * NW;
+        if (rowH < k) {
+          const T* l = P + k + c0 + (long long)rowH * m;
 #pragma unroll 4
-        for (int c = lane; c < len; c += 32) acc += conj_(l[c]) * xs[c];
+          for (int c = lane; c < len; c += 32) accH[q] += conj_(l[c]) * xs[c];
+        }
       }
     }
   }
@@ -266,15 +272,20 @@ __global__ void __launch_bounds__(1024) k_down_off(const Front* __restrict__ fro
     if (tid < ROWS && r0 + tid < k) {
       z128 s = red[0][tid];
 #pragma unroll 8
-      for (int q = 1; q < 32; ++q) s += red[q][tid];
+      for (int q = 1; q < NW; ++q) s += red[q][tid];
       y[f.col0 + r0 + tid] -= s;
     }
   } else {
-    for (int o = 16; o > 0; o >>= 1) {
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+#pragma unroll
+    for (int q = 0; q < ROWS / NW; ++q) {
+      z128 a = accH[q];
+      for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      }
+      const int rowH = r0 + wid + q * NW;
+      if (lane == 0 && rowH < k) y[f.col0 + rowH] -= a;
     }
-    if (lane == 0 && rowH < k) y[f.col0 + rowH] -= acc;
   }
 }
 
@@ -289,8 +300,8 @@ __global__ void __launch_bounds__(1024) k_down_off(const Front* __restrict__ fro
 //   up   (UP = true ):  z = Op in[j0:j1) ;  rows below:  in[row] / cb[row-k]  -=  Off[row, :] z
 //   down (UP = false):  z = Op in[j0:j1) ;  rows above:  in[row]              -=  Off[row, :] z
 //        Op / Off:   up,N: L^-1 / L      up,H: (U^-1)^H / U^H     down,N: U^-1 / U     down,H: (L^-1)^H / L^H
-template <class T, bool H, bool UP>
-__global__ void __launch_bounds__(1024) k_step(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+template <class T, bool H, bool UP, int NT>
+__global__ void __launch_bounds__(NT) k_step(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                int first, int j0, const T* __restrict__ fac, z128* in, z128* out,
                                                z128* __restrict__ cb) {
   const Front f = fronts[lvl_front[first + blockIdx.y]];
@@ -306,7 +317,9 @@ __global__ void __launch_bounds__(1024) k_step(const Front* __restrict__ fronts,
   const T* D = P + j0 + (long long)j0 * m;            // diagonal block origin
   __shared__ z128 ys[SB];
   __shared__ z128 zs[SB];
-  __shared__ z128 part[8][SB];
+  constexpr int CG = NT / SB;      // column groups of the row-contiguous (N) phases
+  constexpr int NWARP = NT / 32;   // warps: one row each in the column-contiguous (H) phases
+  __shared__ z128 part[CG][SB];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid < len) ys[tid] = in[f.col0 + j0 + tid];
   __syncthreads();
@@ -318,10 +331,10 @@ __global__ void __launch_bounds__(1024) k_step(const Front* __restrict__ fronts,
       const T* row = D + i;
       if (UP) {
 #pragma unroll 8
-        for (int c = cg; c < i; c += 8) acc += row[(long long)c * m] * ys[c];
+        for (int c = cg; c < i; c += CG) acc += row[(long long)c * m] * ys[c];
       } else {
 #pragma unroll 8
-        for (int c = i + cg; c < len; c += 8) acc += row[(long long)c * m] * ys[c];
+        for (int c = i + cg; c < len; c += CG) acc += row[(long long)c * m] * ys[c];
       }
     }
     part[cg][i] = acc;
@@ -329,11 +342,11 @@ __global__ void __launch_bounds__(1024) k_step(const Front* __restrict__ fronts,
     if (tid < len) {
       z128 sum = part[0][tid];
 #pragma unroll
-      for (int q = 1; q < 8; ++q) sum += part[q][tid];
+      for (int q = 1; q < CG; ++q) sum += part[q][tid];
       zs[tid] = UP ? sum + ys[tid] : sum;  // unit diagonal of L^-1
     }
   } else {
-    for (int i = wid; i < len; i += 32) {
+    for (int i = wid; i < len; i += NWARP) {
       const T* col = D + (long long)i * m;
       z128 acc = mk(0, 0);
       if (UP) {
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(1024) k_step(const Front* __restrict__ fronts,
     if (r0 + rr < nrows) {
       const T* a = P + row + (long long)j0 * m;
 #pragma unroll 8
-      for (int c = cg; c < len; c += 8) acc += a[(long long)c * m] * zs[c];
+      for (int c = cg; c < len; c += CG) acc += a[(long long)c * m] * zs[c];
     }
     __syncthreads();  // part[] is being reused
     part[cg][rr] = acc;
@@ -367,15 +380,15 @@ __global__ void __launch_bounds__(1024) k_step(const Front* __restrict__ fronts,
     if (tid < SB && r0 + tid < nrows) {
       z128 sum = part[0][tid];
 #pragma unroll
-      for (int q = 1; q < 8; ++q) sum += part[q][tid];
+      for (int q = 1; q < CG; ++q) sum += part[q][tid];
       const int rw = (UP ? j1 : 0) + r0 + tid;
       if (!UP || rw < k) in[f.col0 + rw] -= sum;
       else cb[f.st0 + (rw - k)] -= sum;
     }
   } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int rr = wid + q * 32;
+    for (int q = 0; q < SB / NWARP; ++q) {
+      const int rr = wid + q * NWARP;
       if (r0 + rr >= nrows) break;
       const int row = (UP ? j1 : 0) + r0 + rr;
       // column `row` of U (up) / of L (down), entries of the step's rows: contiguous in memory
@@ -445,7 +458,10 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
         }
         const int gx = std::max(1, cdiv(max_rows, SB));
-        k_step<T, H, true><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, z, cb);
+        // big fronts (several dependent steps): 1024 threads for memory-level parallelism; small fronts
+        // (thousands per level, one step each): 256 threads so that many CTAs share an SM
+        if (maxk > SB) k_step<T, H, true, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, z, cb);
+        else k_step<T, H, true, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, z, cb);
         LSA_LAUNCH_CHECK();
         tr.mark("up_step", d, j0, gx, act);
         launches++;
@@ -461,7 +477,8 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       int maxr = 0;
       for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[sym.lvl_front[q]].r);
       if (maxr > 0) {
-        k_down_off<T, H><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
+        if (maxr > 512) k_down_off<T, H, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
+        else k_down_off<T, H, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
         LSA_LAUNCH_CHECK();
         tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
         launches++;
@@ -474,7 +491,8 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         }
         if (act == 0) continue;
         const int gx = std::max(1, cdiv(j0, SB));
-        k_step<T, H, false><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
+        if (maxk > SB) k_step<T, H, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
+        else k_step<T, H, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
         LSA_LAUNCH_CHECK();
         tr.mark("down_step", d, j0, gx, act);
         launches++;

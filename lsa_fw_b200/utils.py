@@ -294,7 +294,7 @@ class iEpsSolver:  # noqa: N801
         self._interval = None
         # backend options (extensions; all optional)
         self._opts = dict(leaf_size=64, coords=None, refine_steps=0, tiny_pivot=1e-13, seed=0, device=0,
-                          purify=True, nthreads=0, v0=None, force_complex=False)
+                          purify=True, nthreads=0, v0=None, force_complex=False, coupled_fraction=0.5)
         self._adjoint = False
         self._handle: _lib.Handle | None = None
         self._factor_key = None
@@ -359,7 +359,7 @@ class iEpsSolver:  # noqa: N801
     # ------------------------------------------------------------------ extensions
     def set_backend_options(self, **kw) -> None:
         """B200-backend knobs: leaf_size, coords (n x dim ordering hint), refine_steps, tiny_pivot,
-        seed, device, purify, nthreads, v0 (start vector), force_complex."""
+        seed, device, purify, nthreads, v0 (start vector), force_complex, coupled_fraction."""
         unknown = set(kw) - set(self._opts)
         if unknown:
             raise TypeError(f"unknown backend option(s): {sorted(unknown)}")
@@ -453,11 +453,12 @@ class iEpsSolver:  # noqa: N801
             self._complex_mode = use_complex
             coords = self._opts["coords"]
             key = _pattern_key(A, M, (self._opts["leaf_size"], None if coords is None else id(coords),
-                                      self._opts["device"]))
+                                      self._opts["device"], self._opts["coupled_fraction"]))
             t0 = time.perf_counter()
             h = _SYM_CACHE.get(key)
             if h is None:
                 h = _lib.Handle(n, self._opts["device"])
+                h.set_option("coupled_fraction", self._opts["coupled_fraction"])
                 # structurally zero diagonal of the matrix to be factored (pressure rows): ordered last
                 if sinvert:
                     dF = A.diagonal() - sigma * (M.diagonal() if M is not None else np.ones(n))
@@ -489,6 +490,13 @@ class iEpsSolver:  # noqa: N801
                     fs = h.factor(1.0, -sigma, scalar, self._opts["tiny_pivot"])
                 else:
                     fs = h.factor(0.0, 1.0, scalar, 0.0)  # plain M^-1: an exactly singular M must raise
+                if sinvert and fs.n_perturbed > 0 and self._opts["coupled_fraction"] < 1.0:
+                    # tiny pivots were replaced: the cheap placement of the zero-diagonal unknowns was not
+                    # enough for this pencil -> redo the analysis with the robust rule and factor again
+                    logger.warning("%d tiny pivots replaced; re-analysing with coupled_fraction = 1", fs.n_perturbed)
+                    self._opts["coupled_fraction"] = 1.0
+                    self._factor_key = None
+                    return self.solve()
                 stats.update(factor_seconds=fs.seconds, factor_flops=fs.flops, n_perturbed=fs.n_perturbed,
                              n_row_swaps=fs.n_row_swaps, min_pivot=fs.min_pivot, max_pivot=fs.max_pivot,
                              max_multiplier=fs.max_multiplier,
