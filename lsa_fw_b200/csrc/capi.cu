@@ -384,6 +384,8 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->coupled_fraction = value;
   } else if (nm == "use_graphs") {
     h->use_graphs = value != 0.0;
+  } else if (nm == "use_clusters") {
+    h->use_clusters = value != 0.0;
   } else {
     return fail(h, LSA_ERR_ARG, "unknown option " + nm);
   }
@@ -518,6 +520,9 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   cudaEventRecord(e0, st);
   h->scalar = -1;
   drop_solve_graphs(*h);
+  if (const char* e = getenv("LSA_NO_CLUSTERS")) {
+    if (atoi(e) != 0) h->use_clusters = false;
+  }
   if (const char* e = getenv("LSA_NO_GRAPHS")) {
     if (atoi(e) != 0) h->use_graphs = false;
   }

@@ -145,6 +145,7 @@ struct lsa_handle_impl {
   };
   std::vector<SolveGraph> solve_graphs;
   bool use_graphs = true;
+  bool use_clusters = true;   // sweep multi-step levels with thread-block clusters (one launch per level)
   double coupled_fraction = 0.5;
 };
 

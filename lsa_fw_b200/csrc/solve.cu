@@ -20,6 +20,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "factor.cuh"
 
 namespace lsa {
@@ -407,6 +409,162 @@ __global__ void __launch_bounds__(NT) k_step(const Front* __restrict__ fronts, c
   }
 }
 
+__device__ __forceinline__ z128 ld_cg(const z128* p) {  // L2 read (data written by a peer CTA of the cluster)
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return mk(v.x, v.y);
+}
+
+// ---------------------------------------------------------------------- cluster sweep (big fronts)
+//
+// Levels whose fronts need several dependent 128-pivot steps are swept with ONE launch per level and
+// direction: every front is owned by a thread-block cluster of C CTAs (C = 1, 2, 4, 8 by front height),
+// the steps run inside the kernel and are separated by the hardware cluster barrier (release/acquire at
+// cluster scope) instead of kernel boundaries.  Per step every CTA redundantly applies the inverted
+// diagonal block (L2 resident) and updates its share of the rows; rank 0 stores the solved slice.
+template <class T, bool H, bool UP, int C>
+__global__ void __launch_bounds__(1024) k_sweep_cluster(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                        int first, const T* __restrict__ fac, z128* in, z128* out,
+                                                        z128* cb) {
+  namespace cg = cooperative_groups;
+  constexpr int NT = 1024, CG = NT / SB, NWARP = NT / 32;
+  const int rank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const Front f = fronts[lvl_front[first + blockIdx.x / C]];
+  const int k = f.k;
+  const long long m = (long long)k + f.r;
+  const T* P = fac + f.p_off;
+  const T* Q = fac + f.q_off;
+  __shared__ z128 ys[SB];
+  __shared__ z128 zs[SB];
+  __shared__ z128 part[CG][SB];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nsteps = (k + SB - 1) / SB;
+  for (int s = 0; s < nsteps; ++s) {
+    const int j0 = (UP ? s : nsteps - 1 - s) * SB;
+    const int len = min(SB, k - j0), j1 = j0 + len;
+    const int nrows = UP ? (int)(m - j1) : j0;
+    const T* D = P + j0 + (long long)j0 * m;
+    if (tid < len) {
+      // values written by peer CTAs in the previous step: read through L2
+      ys[tid] = ld_cg(in + f.col0 + j0 + tid);
+    }
+    __syncthreads();
+    // ---- phase 1: z = Op ys
+    if (!H) {
+      const int i = tid & (SB - 1), cgi = tid >> 7;
+      z128 acc = mk(0, 0);
+      if (i < len) {
+        const T* row = D + i;
+        if (UP) {
+#pragma unroll 8
+          for (int c = cgi; c < i; c += CG) acc += row[(long long)c * m] * ys[c];
+        } else {
+#pragma unroll 8
+          for (int c = i + cgi; c < len; c += CG) acc += row[(long long)c * m] * ys[c];
+        }
+      }
+      part[cgi][i] = acc;
+      __syncthreads();
+      if (tid < len) {
+        z128 sum = part[0][tid];
+#pragma unroll
+        for (int q = 1; q < CG; ++q) sum += part[q][tid];
+        zs[tid] = UP ? sum + ys[tid] : sum;
+      }
+    } else {
+      for (int i = wid; i < len; i += NWARP) {
+        const T* col = D + (long long)i * m;
+        z128 acc = mk(0, 0);
+        if (UP) {
+          for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
+        } else {
+          for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (lane == 0) zs[i] = UP ? acc : acc + ys[i];
+      }
+    }
+    __syncthreads();
+    if (rank == 0 && tid < len) out[f.col0 + j0 + tid] = zs[tid];
+    // ---- phase 2: this CTA's row chunks
+    for (int r0 = rank * SB; r0 < nrows; r0 += C * SB) {
+      if (!H) {
+        const int rr = tid & (SB - 1), cgi = tid >> 7;
+        const int row = (UP ? j1 : 0) + r0 + rr;
+        z128 acc = mk(0, 0);
+        if (r0 + rr < nrows) {
+          const T* a = P + row + (long long)j0 * m;
+#pragma unroll 8
+          for (int c = cgi; c < len; c += CG) acc += a[(long long)c * m] * zs[c];
+        }
+        __syncthreads();
+        part[cgi][rr] = acc;
+        __syncthreads();
+        if (tid < SB && r0 + tid < nrows) {
+          z128 sum = part[0][tid];
+#pragma unroll
+          for (int q = 1; q < CG; ++q) sum += part[q][tid];
+          const int rw = (UP ? j1 : 0) + r0 + tid;
+          z128* dst = (!UP || rw < k) ? in + f.col0 + rw : cb + f.st0 + (rw - k);
+          *dst = ld_cg(dst) - sum;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < SB / NWARP; ++q) {
+          const int rr = wid + q * NWARP;
+          if (r0 + rr >= nrows) break;
+          const int row = (UP ? j1 : 0) + r0 + rr;
+          const T* u = (!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
+          z128 acc = mk(0, 0);
+          for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * zs[c];
+          for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+          }
+          if (lane == 0) {
+            z128* dst = (!UP || row < k) ? in + f.col0 + row : cb + f.st0 + (row - k);
+            *dst = ld_cg(dst) - acc;
+          }
+        }
+      }
+    }
+    // ---- all updates of this step visible to the whole cluster before the next slice is read
+    if (C > 1) cg::this_cluster().sync();
+    else __syncthreads();
+  }
+}
+
+template <class T, bool H, bool UP, int C>
+static void launch_sweep_cluster(cudaStream_t st, int cnt, const Front* fronts, const int* lvl_front, int first, const T* fac,
+                                 z128* in, z128* out, z128* cb) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(C * cnt), 1, 1);
+  cfg.blockDim = dim3(1024, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb));
+}
+
+template <class T, bool H, bool UP>
+static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fronts, const int* lvl_front, int first,
+                          const T* fac, z128* in, z128* out, z128* cb) {
+  switch (csize) {
+    case 1: launch_sweep_cluster<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+    case 2: launch_sweep_cluster<T, H, UP, 2>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+    case 4: launch_sweep_cluster<T, H, UP, 4>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+    default: launch_sweep_cluster<T, H, UP, 8>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+  }
+}
+
 __global__ void k_unpermute(const z128* __restrict__ y, z128* __restrict__ x, const int* __restrict__ gperm, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[gperm[i]] = y[i];
@@ -449,6 +607,15 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       tr.mark("up_gather", d, 0, cnt, 1);
       launches++;
       const int maxk = sym.fronts[sym.lvl_front[first]].k;
+      int max_m = 0;
+      for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[sym.lvl_front[q]].k + sym.fronts[sym.lvl_front[q]].r);
+      const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
+      if (maxk > SB && h.use_clusters) {
+        sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, h.d_lvl_front, first, fac, y, z, cb);
+        tr.mark("up_cluster", d, csize, csize * cnt, 1);
+        launches++;
+        continue;
+      }
       for (int j0 = 0; j0 < maxk; j0 += SB) {
         int act = 0, max_rows = 0;
         for (int q = first; q < first + cnt; ++q) {
@@ -458,8 +625,6 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
         }
         const int gx = std::max(1, cdiv(max_rows, SB));
-        // big fronts (several dependent steps): 1024 threads for memory-level parallelism; small fronts
-        // (thousands per level, one step each): 256 threads so that many CTAs share an SM
         if (maxk > SB) k_step<T, H, true, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, z, cb);
         else k_step<T, H, true, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, z, cb);
         LSA_LAUNCH_CHECK();
@@ -483,19 +648,28 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
         launches++;
       }
-      for (int j0 = ((maxk - 1) / SB) * SB; j0 >= 0; j0 -= SB) {
-        int act = 0;
-        for (int q = first; q < first + cnt; ++q) {
-          if (sym.fronts[sym.lvl_front[q]].k <= j0) break;
-          act++;
-        }
-        if (act == 0) continue;
-        const int gx = std::max(1, cdiv(j0, SB));
-        if (maxk > SB) k_step<T, H, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
-        else k_step<T, H, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
-        LSA_LAUNCH_CHECK();
-        tr.mark("down_step", d, j0, gx, act);
+      if (maxk > SB && h.use_clusters) {
+        int max_m = 0;
+        for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[sym.lvl_front[q]].k);
+        const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
+        sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, h.d_lvl_front, first, fac, z, y, cb);
+        tr.mark("down_cluster", d, csize, csize * cnt, 1);
         launches++;
+      } else {
+        for (int j0 = ((maxk - 1) / SB) * SB; j0 >= 0; j0 -= SB) {
+          int act = 0;
+          for (int q = first; q < first + cnt; ++q) {
+            if (sym.fronts[sym.lvl_front[q]].k <= j0) break;
+            act++;
+          }
+          if (act == 0) continue;
+          const int gx = std::max(1, cdiv(j0, SB));
+          if (maxk > SB) k_step<T, H, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
+          else k_step<T, H, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
+          LSA_LAUNCH_CHECK();
+          tr.mark("down_step", d, j0, gx, act);
+          launches++;
+        }
       }
       if (H) {
         k_level_unpermute<<<cnt, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_gperm, y, x);

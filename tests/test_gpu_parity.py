@@ -143,7 +143,10 @@ def _match(lam, ref):
 @pytest.mark.parametrize("use_coords", [False, True], ids=["graph", "geometric"])
 def test_eigenpairs_match_oracle(kind, use_coords):
     pc, sigma = _ns(kind)
-    es, pairs = _run(pc, sigma, coords=pc.coords if use_coords else None)
+    # the real shift -0.3 sits close to the spectrum: (A - sigma M) is ~1e4 times worse conditioned than
+    # for the complex shifts, so that case runs with one step of iterative refinement per solve
+    extra = dict(refine_steps=1) if kind == "th2d_real" else {}
+    es, pairs = _run(pc, sigma, coords=pc.coords if use_coords else None, **extra)
     assert len(pairs) == 6
     lam = np.array([p[0] for p in pairs])
     orc = O.shift_invert_krylov_schur(pc.A, pc.M, sigma, 8, ncv=40, tol=1e-12)
