@@ -610,7 +610,9 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       int max_m = 0;
       for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[sym.lvl_front[q]].k + sym.fronts[sym.lvl_front[q]].r);
       const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
-      if (maxk > SB && h.use_clusters) {
+      // very tall fronts (3-D top separators) need the whole GPU per step; up to ~4 k rows a cluster of 8
+      // SMs keeps up and saves the launches
+      if (maxk > SB && max_m <= 4096 && h.use_clusters) {
         sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, h.d_lvl_front, first, fac, y, z, cb);
         tr.mark("up_cluster", d, csize, csize * cnt, 1);
         launches++;
@@ -648,7 +650,9 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
         launches++;
       }
-      if (maxk > SB && h.use_clusters) {
+      int max_mk = 0;
+      for (int q = first; q < first + cnt; ++q) max_mk = std::max(max_mk, sym.fronts[sym.lvl_front[q]].k + sym.fronts[sym.lvl_front[q]].r);
+      if (maxk > SB && max_mk <= 4096 && h.use_clusters) {
         int max_m = 0;
         for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[sym.lvl_front[q]].k);
         const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
