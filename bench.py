@@ -319,6 +319,14 @@ def main() -> None:
     resid_adj = float(h.residuals(min(nev, ra.nconv)).max()) if ra.nconv else None
     lam_adj = h.eigenvalues(min(nev, ra.nconv))
     conj_mismatch = float(max(min(abs(np.conj(l) - lam_direct)) / abs(l) for l in lam_adj)) if len(lam_adj) and len(lam_direct) else None
+    # accuracy of the triangular solves themselves (both sweeps) at full size
+    Csh = (pc.A - sigma * pc.M).tocsr()
+    bb = np.random.default_rng(99).standard_normal(n) + 1j * np.random.default_rng(98).standard_normal(n)
+    xs = h.solve(bb)
+    solve_resid_n = float(np.linalg.norm(Csh @ xs - bb) / np.linalg.norm(bb))
+    xs = h.solve(bb, _lib.LSA_OP_H)
+    solve_resid_h = float(np.linalg.norm(Csh.conj().T @ xs - bb) / np.linalg.norm(bb))
+    del Csh, xs, bb
     counters = h.counters()
     solve_mean = acc["solve"] / max(1, acc["applies"])
     spmv_mean = acc["spmv"] / max(1, acc["applies"])
@@ -415,7 +423,8 @@ def main() -> None:
                        "nconv_adjoint": len(pairs_adj), "lambda0": [lam0.real, lam0.imag] if lam0 else None,
                        "lambda0_adjoint": [lam0_adj.real, lam0_adj.imag] if lam0_adj else None,
                        "n_perturbed": int(st.get("n_perturbed", -1)),
-                       "adjoint_vs_conj_direct_rel": conj_mismatch},
+                       "adjoint_vs_conj_direct_rel": conj_mismatch, "solve_resid_N": solve_resid_n,
+                       "solve_resid_H": solve_resid_h, "max_multiplier": fs.max_multiplier},
             "wall_s_timed_region": wall, "assemble_s": t_assemble, "fp64_peak_tflops_measured": fp64_peak,
         }
         if cb is not None:
