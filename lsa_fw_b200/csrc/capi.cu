@@ -298,6 +298,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   opt.nthreads = nthreads;
   opt.coupled_fraction = h->coupled_fraction;
   if (const char* e = getenv("LSA_COUPLED_FRACTION")) opt.coupled_fraction = atof(e);
+  if (const char* e = getenv("LSA_CAP_FRACTION")) opt.cap_fraction = atof(e);
   if (h->has_m) analyze(n, urow.data(), ucol.data(), opt, h->sym);
   else analyze(n, (const long long*)a_rowptr, a_colidx, opt, h->sym);
   // scatter maps for the caller's entry order of A and M (the union map is recomputed per matrix)

@@ -63,6 +63,7 @@ struct AnalyzeOptions {
   const double* coords = nullptr;
   const unsigned char* order_last = nullptr;  // n flags: order this unknown last inside its front
   int nthreads = 0;
+  double cap_fraction = 0.15;     // end-cap thickness (share of the diameter) of the graph bisector; 0: point pair
   double coupled_fraction = 1.0;  // share of a flagged unknown's regular neighbours eliminated before it
 };
 

@@ -120,6 +120,24 @@ class Dissector {
     return queue.back();
   }
 
+  void bfs_multi(const std::vector<int>& sources, int tok, std::vector<int>& dist, std::vector<int>& queue) {
+    queue.clear();
+    for (int v : sources) {
+      dist[v] = 0;
+      queue.push_back(v);
+    }
+    for (size_t head = 0; head < queue.size(); ++head) {
+      const int v = queue[head];
+      for (long long e = g_.xadj[v]; e < g_.xadj[v + 1]; ++e) {
+        const int u = g_.adj[e];
+        if (mark_[u] == tok && dist[u] < 0) {
+          dist[u] = dist[v] + 1;
+          queue.push_back(u);
+        }
+      }
+    }
+  }
+
   static void emit_leaf(const std::vector<int>& verts, NDResult& out) {
     out.order.insert(out.order.end(), verts.begin(), verts.end());
     out.sn_sizes.push_back((int)verts.size());
@@ -304,6 +322,28 @@ class Dissector {
         for (int v : verts) da_[v] = -1;
         queue.clear();
         bfs(a2, tok, da_, queue);
+        // da_ = d(a, .), db_ = d(b, .).  The bisector of two POINTS is slanted on meshes whose hop metric
+        // is anisotropic (structured triangulations); the bisector of the two END CAPS
+        //   A = {v : d(b, v) >= (1 - eps) D},  B = {v : d(a, v) >= (1 - eps) D}
+        // is perpendicular to the long axis whatever the metric: multi-source BFS from the caps.
+        if (opt_.cap_fraction > 0.0) {
+          int D = 0;
+          for (int v : verts) D = std::max(D, da_[v]);
+          const int thr = (int)std::floor((1.0 - opt_.cap_fraction) * D);
+          std::vector<int> capA, capB;
+          for (int v : verts) {
+            if (db_[v] >= thr) capA.push_back(v);
+            if (da_[v] >= thr) capB.push_back(v);
+          }
+          if (!capA.empty() && !capB.empty()) {
+            for (int v : verts) {
+              da_[v] = -1;
+              db_[v] = -1;
+            }
+            bfs_multi(capA, tok, da_, queue);
+            bfs_multi(capB, tok, db_, queue);
+          }
+        }
         for (int i = 0; i < nv; ++i) key[i] = (double)da_[verts[i]] - (double)db_[verts[i]];
       }
       std::vector<double> tmp(key);

@@ -94,6 +94,36 @@ def test_symbolic_counters_and_pattern_reuse():
     assert a_dst.max() < info.factor_entries
 
 
+def test_options_and_pressure_placement_rule():
+    pc = pencils.assemble_pencil((20, 10), (6.0, 2.0), re=40.0)
+    flag = (pc.A.diagonal() == 0).astype(np.uint8)
+    entries = {}
+    for frac in (0.0, 0.5, 1.0):
+        h = _lib.Handle(pc.n, device=-1)
+        h.set_option("coupled_fraction", frac)
+        info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=32, order_last=flag)
+        entries[frac] = info.nnz_lu
+        # a flagged unknown never precedes the required share of its regular neighbours
+        iperm, sn_ptr = h.symbolic_array("iperm"), h.symbolic_array("sn_ptr")
+        sn_of = np.searchsorted(sn_ptr, iperm, side="right") - 1
+        G = (pc.A + pc.A.T).tocsr()
+        for v in np.nonzero(flag)[0][:200]:
+            nb = G.indices[G.indptr[v]:G.indptr[v + 1]]
+            nb = nb[(flag[nb] == 0) & (nb != v)]
+            if len(nb) == 0 or iperm[v] < info.n_decoupled:
+                continue
+            need = max(1, int(np.ceil(frac * len(nb))))
+            assert np.sum(sn_of[nb] <= sn_of[v]) >= need
+    assert entries[0.0] <= entries[0.5] <= entries[1.0]
+    h = _lib.Handle(3, device=-1)
+    with pytest.raises(_lib.LsaError):
+        h.set_option("coupled_fraction", 1.5)
+    with pytest.raises(_lib.LsaError):
+        h.set_option("no_such_option", 1.0)
+    h.set_option("use_graphs", 0)
+    h.set_option("use_clusters", 0)
+
+
 # ------------------------------------------------------------------------------- Rayleigh-Ritz core
 @pytest.fixture(scope="module")
 def rr_lib():
