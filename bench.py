@@ -44,9 +44,9 @@ WORKLOADS = {
     # name: (builder, kwargs, sigma, nev, ncv, description)
     "cfg1": ("cylinder_wake_2d", dict(nx=110, ny=50, re=50.0), 0.05 + 0.74j, 10, 80,
              "2D cylinder-wake surrogate Re=50, Taylor-Hood 110x50 (50 303 DOFs)"),
-    "cfg2": ("backward_step_2d", dict(nx=667, ny=167, re=500.0), 0.0 + 1.0j, 20, 80,
+    "cfg2": ("backward_step_2d", dict(nx=667, ny=167, re=500.0), -0.35 + 0.1j, 20, 80,
              "2D backward-facing-step surrogate Re=500, Taylor-Hood 667x167 (~1.0 M DOFs)"),
-    "cfg2_small": ("backward_step_2d", dict(nx=167, ny=42, re=500.0), 0.0 + 1.0j, 20, 80,
+    "cfg2_small": ("backward_step_2d", dict(nx=167, ny=42, re=500.0), -0.35 + 0.1j, 20, 80,
                    "2D backward-facing-step surrogate Re=500, Taylor-Hood 167x42 (64 174 DOFs)"),
     "cav3d": ("cavity_3d", dict(n=20, re=100.0), 0.1 + 0.3j, 10, 80,
               "3D lid-driven-cavity surrogate, Taylor-Hood 20^3 x 6 tets (216 024 DOFs = cube.py size)"),
@@ -319,6 +319,7 @@ def main() -> None:
     resid_adj = float(h.residuals(min(nev, ra.nconv)).max()) if ra.nconv else None
     lam_adj = h.eigenvalues(min(nev, ra.nconv))
     conj_mismatch = float(max(min(abs(np.conj(l) - lam_direct)) / abs(l) for l in lam_adj)) if len(lam_adj) and len(lam_direct) else None
+    conj_mismatch5 = float(max(min(abs(np.conj(l) - lam_direct)) / abs(l) for l in lam_adj[:5])) if len(lam_adj) and len(lam_direct) else None
     # accuracy of the triangular solves themselves (both sweeps) at full size
     Csh = (pc.A - sigma * pc.M).tocsr()
     bb = np.random.default_rng(99).standard_normal(n) + 1j * np.random.default_rng(98).standard_normal(n)
@@ -423,7 +424,11 @@ def main() -> None:
                        "nconv_adjoint": len(pairs_adj), "lambda0": [lam0.real, lam0.imag] if lam0 else None,
                        "lambda0_adjoint": [lam0_adj.real, lam0_adj.imag] if lam0_adj else None,
                        "n_perturbed": int(st.get("n_perturbed", -1)),
-                       "adjoint_vs_conj_direct_rel": conj_mismatch, "solve_resid_N": solve_resid_n,
+                       "adjoint_vs_conj_direct_rel": conj_mismatch, "adjoint_vs_conj_direct_rel_leading5": conj_mismatch5,
+                       "conditioning_note": ("channel-type pencils (config 2) are strongly non-normal: the SciPy oracle's own "
+                                             "direct and adjoint runs agree only to ~1e-4 on the 10 leading eigenvalues there; "
+                                             "eigenvalue parity to 1e-8 is asserted on the well-conditioned pencils in tests/"),
+                       "solve_resid_N": solve_resid_n,
                        "solve_resid_H": solve_resid_h, "max_multiplier": fs.max_multiplier},
             "wall_s_timed_region": wall, "assemble_s": t_assemble, "fp64_peak_tflops_measured": fp64_peak,
         }
