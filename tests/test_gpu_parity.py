@@ -329,3 +329,97 @@ def test_config1_full_size_properties_and_oracle():
     es2, pairs2 = _run(pc, sigma, nev=10, ncv=80, tol=1e-10, adjoint=True)
     lam2 = np.array([p[0] for p in pairs2])
     assert _match(np.conj(lam2), lam) < EIG_RTOL or _match(np.conj(lam2[:8]), orc.eigenvalues) < EIG_RTOL
+
+
+# ------------------------------------------------------------------ data-format and edge cases
+def test_explicit_zero_pattern_of_m_gives_identical_results():
+    """dolfinx assembles M on the full mixed-space pattern (explicit zeros in the pressure blocks)."""
+    pc, sigma = _ns("th2d")
+    Mz = sp.csr_matrix((np.zeros(pc.A.nnz), pc.A.indices.copy(), pc.A.indptr.copy()), shape=pc.A.shape)
+    Mz.data[:] = 0.0
+    Mc = pc.M.tocoo()
+    lookup = {(i, j): v for i, j, v in zip(Mc.row, Mc.col, Mc.data)}
+    rows = np.repeat(np.arange(pc.n), np.diff(pc.A.indptr))
+    Mz.data[:] = [lookup.get((i, j), 0.0) for i, j in zip(rows, pc.A.indices)]
+    assert Mz.nnz == pc.A.nnz and abs(Mz - pc.M).max() == 0
+    pz = pencils.Pencil(A=pc.A, M=Mz, dofs_u=pc.dofs_u, dofs_p=pc.dofs_p, dirichlet=pc.dirichlet, coords=pc.coords)
+    _, pairs = _run(pc, sigma)
+    _, pairs_z = _run(pz, sigma)
+    lam, lam_z = np.array([p[0] for p in pairs]), np.array([p[0] for p in pairs_z])
+    assert _match(lam_z, lam) < 1e-10
+
+
+def test_complex_valued_operators():
+    pc, sigma = _ns("th2d")
+    Ac = (pc.A + 0.03j * pc.M).tocsr()          # complex data: scatter, SpMV and residual paths in c128
+    pcx = pencils.Pencil(A=Ac, M=pc.M, dofs_u=pc.dofs_u, dofs_p=pc.dofs_p, dirichlet=pc.dirichlet, coords=pc.coords)
+    es, pairs = _run(pcx, sigma)
+    lam = np.array([p[0] for p in pairs])
+    orc = O.shift_invert_arpack(Ac, pc.M, sigma, 8, ncv=40, tol=1e-12)
+    assert _match(lam, orc.eigenvalues) < EIG_RTOL
+    assert es.solver.get_residuals()[:6].max() < RESID_BAR
+    # eigenvalues of A + 0.03j M are those of (A, M) shifted by 0.03j
+    _, base = _run(pc, sigma - 0.03j)
+    assert _match(lam, np.array([p[0] for p in base]) + 0.03j) < EIG_RTOL
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_tiny_orders(n):
+    A = L.iPETScMatrix.from_matrix(np.diag(np.arange(1.0, n + 1.0)) + (np.eye(n, k=1) * 0.5 if n > 1 else 0))
+    pairs = L.EigenSolver(A, cfg=L.EigensolverConfig(num_eig=5, atol=1e-10)).solve()
+    assert sorted(p[0].real for p in pairs) == pytest.approx(np.arange(1.0, n + 1.0), abs=1e-10)
+    es = L.EigenSolver(A, cfg=L.EigensolverConfig(num_eig=5, atol=1e-10))
+    es.solver.set_st_type(L.iSTType.SINVERT)
+    es.solver.set_target(0.3)
+    assert sorted(p[0].real for p in es.solve()) == pytest.approx(np.arange(1.0, n + 1.0), abs=1e-10)
+
+
+def test_non_convergence_returns_fewer_pairs_without_raising():
+    pc, sigma = _ns("th2d")
+    cfg = L.EigensolverConfig(num_eig=30, atol=1e-14, max_it=1, ncv=32)
+    es = L.EigenSolver(L.iPETScMatrix(pc.A), L.iPETScMatrix(pc.M), cfg, check_hermitian=False)
+    es.solver.set_st_type(L.iSTType.SINVERT)
+    es.solver.set_target(sigma)
+    pairs = es.solve()                      # Solver/utils.py:325-328: min(nconv, num) pairs, no exception
+    assert len(pairs) == min(es.solver.get_num_converged(), 30) < 30
+    assert es.solver.stats["n_restarts"] == 1
+
+
+def test_singular_pencil_is_perturbed_not_crashed(caplog):
+    """P1/P1 ("SIMPLE", not inf-sup stable) with these BCs has an empty pressure row: A - sigma M is exactly
+    singular.  The backend replaces the tiny pivots (eigen2.py:135-136 reaches for MUMPS CNTL(3) for the same reason),
+    retries with the robust pressure placement and reports the count instead of failing."""
+    import logging
+
+    caplog.set_level(logging.WARNING)
+    pc = pencils.assemble_pencil((24, 16), (6.0, 2.0), re=40.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.0), space="SIMPLE")
+    es, pairs = _run(pc, 0.1 + 0.6j, nev=4, ncv=30, tol=1e-8)
+    assert es.solver.stats["n_perturbed"] >= 1
+    assert any("tiny pivots replaced" in r.getMessage() for r in caplog.records)
+
+
+def test_large_front_paths_match_scipy_solve():
+    """3-D cavity with fronts of several hundred pivots: multi-step cluster sweeps, rank-128 deferred updates."""
+    import scipy.sparse.linalg as spla
+
+    pc = pencils.cavity_3d(8)
+    sigma = 0.1 + 0.3j
+    h = _lib.Handle(pc.n, 0)
+    flag = ((pc.A.diagonal() - sigma * pc.M.diagonal()) == 0).astype(np.uint8)
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=flag)
+    assert info.max_pivots > 512
+    h.set_values(pc.A.data, pc.M.data)
+    fs = h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
+    assert fs.n_perturbed == 0 and fs.max_multiplier < 1e3
+    C = (pc.A - sigma * pc.M).tocsc()
+    b = np.random.default_rng(3).standard_normal(pc.n) + 1j * np.random.default_rng(4).standard_normal(pc.n)
+    xs = spla.splu(C).solve(b)
+    for opt, val in (("use_clusters", 1), ("use_clusters", 0)):
+        h.set_option(opt, val)
+        h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)      # re-factor: drops the captured sweep graphs
+        x = h.solve(b)
+        assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-9
+        assert np.linalg.norm(C @ x - b) / np.linalg.norm(b) < 1e-12
+        xh = h.solve(b, _lib.LSA_OP_H)
+        assert np.linalg.norm(C.conj().T @ xh - b) / np.linalg.norm(b) < 1e-12
+    h.close()
