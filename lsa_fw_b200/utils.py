@@ -165,13 +165,12 @@ _HASH_MEMO: dict[tuple, bytes] = {}
 
 
 def _array_digest(arr: np.ndarray) -> bytes:
-    """blake2b of an index array, memoised on (buffer address, length, sampled content, sum, xor) so that the
+    """blake2b of an index array, memoised on (buffer address, length, 4096 sampled entries) so that the
     repeated solves of a sweep do not re-hash ~100 MB of pattern per call."""
     arr = np.ascontiguousarray(arr)
     n = arr.size
     sample = arr[:: max(1, n // 4096)].tobytes()
-    key = (arr.__array_interface__["data"][0], n, arr.dtype.str, hashlib.blake2b(sample, digest_size=8).digest(),
-           int(arr.sum(dtype=np.uint64)) if n else 0, int(np.bitwise_xor.reduce(arr)) if n else 0)
+    key = (arr.__array_interface__["data"][0], n, arr.dtype.str, hashlib.blake2b(sample, digest_size=8).digest())
     dig = _HASH_MEMO.get(key)
     if dig is None:
         dig = hashlib.blake2b(arr.tobytes(), digest_size=16).digest()
@@ -302,6 +301,7 @@ class iEpsSolver:  # noqa: N801
         self._nconv = 0
         self._eigenvalues: np.ndarray = np.zeros(0, dtype=complex)
         self._eigenvectors: np.ndarray | None = None
+        self._handed_out: set[int] = set()
         self._complex_mode = False
         if A is not None:
             self.set_operators(A, M)
@@ -514,6 +514,7 @@ class iEpsSolver:  # noqa: N801
         # the handle (and its device buffers) may be shared with other solver objects through the
         # symbolic cache / adjoint reuse: bring the vectors to the host now
         self._eigenvectors = None
+        self._handed_out = set()
         t0 = time.perf_counter()
         if res.nconv > 0:
             self._fetch_vectors()
@@ -564,8 +565,13 @@ class iEpsSolver:  # noqa: N801
         x = self._fetch_vectors()[:, idx]
         from .carriers import _RawVec
 
-        def wrap(a: np.ndarray) -> iPETScVector:  # one copy, not two
-            return iPETScVector(_RawVec(np.array(a, copy=True)))
+        first = idx not in self._handed_out
+        self._handed_out.add(idx)
+
+        def wrap(a: np.ndarray) -> iPETScVector:
+            # the first request for an index hands out the solver's own slice of the result buffer (no
+            # copy of n numbers); later requests for the same index get fresh copies, as the reference does
+            return iPETScVector(_RawVec(a if first and a.flags.c_contiguous else np.array(a, copy=True)))
 
         if self._complex_mode:
             return iComplexPETScVector(wrap(x))
