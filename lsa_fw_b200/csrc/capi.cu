@@ -42,7 +42,7 @@ void free_csr(CsrDev& c) {
 
 void free_device(lsa_handle_impl& h) {
   drop_solve_graphs(h);
-  dfree(h.d_fronts); dfree(h.d_lvl_front); dfree(h.d_st_idx); dfree(h.d_ea_map); dfree(h.d_child_idx);
+  dfree(h.d_fronts); dfree(h.d_lvl_front); dfree(h.d_top_lvl_front); dfree(h.d_sub_first); dfree(h.d_sub_last); dfree(h.d_st_idx); dfree(h.d_ea_map); dfree(h.d_child_idx);
   dfree(h.d_a_dst); dfree(h.d_m_dst); dfree(h.d_perm); dfree(h.d_ipiv); dfree(h.d_gperm); dfree(h.d_stats);
   if (h.d_a_orig) cudaFree(h.d_a_orig);
   if (h.d_m_orig) cudaFree(h.d_m_orig);
@@ -351,6 +351,9 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     cudaStream_t st = h->stream;
     h->d_fronts = dupload(sym.fronts, st);
     h->d_lvl_front = dupload(sym.lvl_front, st);
+    h->d_top_lvl_front = dupload(sym.top_lvl_front, st);
+    h->d_sub_first = dupload(sym.sub_first, st);
+    h->d_sub_last = dupload(sym.sub_last, st);
     h->d_st_idx = dupload(sym.st_idx, st);
     h->d_ea_map = dupload(sym.ea_map, st);
     h->d_child_idx = dupload(sym.child_idx, st);
@@ -387,6 +390,8 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->use_graphs = value != 0.0;
   } else if (nm == "use_clusters") {
     h->use_clusters = value != 0.0;
+  } else if (nm == "use_subtrees") {
+    h->use_subtrees = value != 0.0;
   } else {
     return fail(h, LSA_ERR_ARG, "unknown option " + nm);
   }
@@ -437,6 +442,10 @@ int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int
   if (nm == "ea_map") return give(s.ea_map.data(), s.ea_map.size(), 4);
   if (nm == "lvl_ptr") return give(s.lvl_ptr.data(), s.lvl_ptr.size(), 4);
   if (nm == "lvl_front") return give(s.lvl_front.data(), s.lvl_front.size(), 4);
+  if (nm == "sub_first") return give(s.sub_first.data(), s.sub_first.size(), 4);
+  if (nm == "sub_last") return give(s.sub_last.data(), s.sub_last.size(), 4);
+  if (nm == "top_lvl_ptr") return give(s.top_lvl_ptr.data(), s.top_lvl_ptr.size(), 4);
+  if (nm == "top_lvl_front") return give(s.top_lvl_front.data(), s.top_lvl_front.size(), 4);
   if (nm == "a_dst") return give(s.a_dst.data(), s.a_dst.size(), 8);
   if (nm == "m_dst") return give(h->m_dst.data(), h->m_dst.size(), 8);
   if (nm == "parent") return from_fronts([](const Front& f) { return f.parent; }, 4);
@@ -521,6 +530,9 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   cudaEventRecord(e0, st);
   h->scalar = -1;
   drop_solve_graphs(*h);
+  if (const char* e = getenv("LSA_NO_SUBTREES")) {
+    if (atoi(e) != 0) h->use_subtrees = false;
+  }
   if (const char* e = getenv("LSA_NO_CLUSTERS")) {
     if (atoi(e) != 0) h->use_clusters = false;
   }

@@ -69,6 +69,9 @@ struct lsa_handle_impl {
   // ---- device plan
   Front* d_fronts = nullptr;
   int* d_lvl_front = nullptr;
+  int* d_top_lvl_front = nullptr;
+  int* d_sub_first = nullptr;
+  int* d_sub_last = nullptr;
   int* d_st_idx = nullptr;
   int* d_ea_map = nullptr;
   int* d_child_idx = nullptr;
@@ -145,7 +148,8 @@ struct lsa_handle_impl {
   };
   std::vector<SolveGraph> solve_graphs;
   bool use_graphs = true;
-  bool use_clusters = true;   // sweep multi-step levels with thread-block clusters (one launch per level)
+  bool use_clusters = true;
+  bool use_subtrees = true;   // sweep the bottom sub-trees inside single CTAs (one launch per direction)   // sweep multi-step levels with thread-block clusters (one launch per level)
   double coupled_fraction = 0.5;
 };
 

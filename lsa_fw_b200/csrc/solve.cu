@@ -565,6 +565,209 @@ static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fron
   }
 }
 
+// ------------------------------------------------------------------ bottom sub-trees (one CTA each)
+//
+// The lowest levels of the assembly tree hold most fronts but little data per front; sweeping them
+// level by level costs four dependent launches per level.  Instead every bottom sub-tree (chosen by the
+// symbolic phase: <= 1 M factor entries, pivot blocks <= 256) is swept front by front inside ONE CTA:
+// post-order on the way up, reverse on the way down, __syncthreads between fronts and no launch
+// boundaries.  Data written earlier by the same CTA is re-read through L2 (ld.cg).
+template <class T, bool H, bool UP>
+__global__ void __launch_bounds__(256) k_subtree(const Front* __restrict__ fronts, const int* __restrict__ sub_first,
+                                                 const int* __restrict__ sub_last, const int* __restrict__ child_idx,
+                                                 const int* __restrict__ ea_map, const int* __restrict__ gperm,
+                                                 const int* __restrict__ st_idx, const T* __restrict__ fac, z128* x,
+                                                 z128* y, z128* z, z128* cb) {
+  constexpr int NT = 256, CG = NT / SB, NWARP = NT / 32;
+  __shared__ z128 ys[SB];
+  __shared__ z128 zs[SB];
+  __shared__ z128 part[CG][SB];
+  __shared__ z128 xs[NT];
+  __shared__ z128 red[NWARP][33];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int first = sub_first[blockIdx.x], last = sub_last[blockIdx.x];
+  for (int it = 0; it <= last - first; ++it) {
+    const int s = UP ? first + it : last - it;
+    const Front f = fronts[s];
+    const int k = f.k, r = f.r;
+    const long long m = (long long)k + r;
+    const T* P = fac + f.p_off;
+    const T* Q = fac + f.q_off;
+    if (UP) {
+      // ---- children contributions, then the pivot rows into the work vector
+      for (int t = tid; t < r; t += NT) cb[f.st0 + t] = mk(0, 0);
+      __syncthreads();
+      for (int q = 0; q < f.nchild; ++q) {
+        const Front c = fronts[child_idx[f.child0 + q]];
+        const int* map = ea_map + c.st0;
+        for (int t = tid; t < c.r; t += NT) {
+          const int ip = map[t];
+          const z128 v = ld_cg(cb + c.st0 + t);
+          z128* dst = ip < k ? x + f.col0 + ip : cb + f.st0 + (ip - k);
+          *dst = ld_cg(dst) + v;
+        }
+        __syncthreads();
+      }
+      for (int i = tid; i < k; i += NT) y[f.col0 + i] = ld_cg(x + (H ? f.col0 + i : gperm[f.col0 + i]));
+      __syncthreads();
+    } else if (r > 0) {
+      // ---- pivot rows -= Off * (final values of the ancestors)
+      const z128* anc = H ? x : y;
+      const int* idx = st_idx + f.st0;
+      for (int r0 = 0; r0 < k; r0 += 32) {
+        z128 acc = mk(0, 0);
+        z128 accH[32 / NWARP];
+#pragma unroll
+        for (int q = 0; q < 32 / NWARP; ++q) accH[q] = mk(0, 0);
+        for (int c0 = 0; c0 < r; c0 += NT) {
+          const int len = min(NT, r - c0);
+          __syncthreads();
+          if (tid < len) xs[tid] = ld_cg(anc + idx[c0 + tid]);
+          __syncthreads();
+          if (!H) {
+            if (r0 + lane < k) {
+              const T* a = Q + (r0 + lane) + (long long)c0 * k;
+#pragma unroll 8
+              for (int c = wid; c < len; c += NWARP) acc += a[(long long)c * k] * xs[c];
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32 / NWARP; ++q) {
+              const int row = r0 + wid + q * NWARP;
+              if (row < k) {
+                const T* l = P + k + c0 + (long long)row * m;
+                for (int c = lane; c < len; c += 32) accH[q] += conj_(l[c]) * xs[c];
+              }
+            }
+          }
+        }
+        if (!H) {
+          red[wid][lane] = acc;
+          __syncthreads();
+          if (tid < 32 && r0 + tid < k) {
+            z128 sum = red[0][tid];
+#pragma unroll
+            for (int q = 1; q < NWARP; ++q) sum += red[q][tid];
+            z128* dst = z + f.col0 + r0 + tid;
+            *dst = ld_cg(dst) - sum;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32 / NWARP; ++q) {
+            z128 a = accH[q];
+            for (int o = 16; o > 0; o >>= 1) {
+              a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+              a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+            }
+            const int row = r0 + wid + q * NWARP;
+            if (lane == 0 && row < k) {
+              z128* dst = z + f.col0 + row;
+              *dst = ld_cg(dst) - a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- the front's pivot block in 128-wide steps
+    z128* in = UP ? y : z;
+    z128* out = UP ? z : y;
+    const int nsteps = (k + SB - 1) / SB;
+    for (int st = 0; st < nsteps; ++st) {
+      const int j0 = (UP ? st : nsteps - 1 - st) * SB;
+      const int len = min(SB, k - j0), j1 = j0 + len;
+      const int nrows = UP ? (int)(m - j1) : j0;
+      const T* D = P + j0 + (long long)j0 * m;
+      if (tid < len) ys[tid] = ld_cg(in + f.col0 + j0 + tid);
+      __syncthreads();
+      if (!H) {
+        const int i = tid & (SB - 1), cgi = tid >> 7;
+        z128 acc = mk(0, 0);
+        if (i < len) {
+          const T* row = D + i;
+          if (UP) {
+#pragma unroll 8
+            for (int c = cgi; c < i; c += CG) acc += row[(long long)c * m] * ys[c];
+          } else {
+#pragma unroll 8
+            for (int c = i + cgi; c < len; c += CG) acc += row[(long long)c * m] * ys[c];
+          }
+        }
+        part[cgi][i] = acc;
+        __syncthreads();
+        if (tid < len) {
+          z128 sum = part[0][tid];
+#pragma unroll
+          for (int q = 1; q < CG; ++q) sum += part[q][tid];
+          zs[tid] = UP ? sum + ys[tid] : sum;
+        }
+      } else {
+        for (int i = wid; i < len; i += NWARP) {
+          const T* col = D + (long long)i * m;
+          z128 acc = mk(0, 0);
+          if (UP) {
+            for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
+          } else {
+            for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
+          }
+          for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+          }
+          if (lane == 0) zs[i] = UP ? acc : acc + ys[i];
+        }
+      }
+      __syncthreads();
+      if (tid < len) {
+        out[f.col0 + j0 + tid] = zs[tid];
+        if (!UP && H) x[gperm[f.col0 + j0 + tid]] = zs[tid];  // P^T of this front, final values
+      }
+      for (int r0 = 0; r0 < nrows; r0 += SB) {
+        if (!H) {
+          const int rr = tid & (SB - 1), cgi = tid >> 7;
+          const int row = (UP ? j1 : 0) + r0 + rr;
+          z128 acc = mk(0, 0);
+          if (r0 + rr < nrows) {
+            const T* a = P + row + (long long)j0 * m;
+#pragma unroll 8
+            for (int c = cgi; c < len; c += CG) acc += a[(long long)c * m] * zs[c];
+          }
+          __syncthreads();
+          part[cgi][rr] = acc;
+          __syncthreads();
+          if (tid < SB && r0 + tid < nrows) {
+            z128 sum = part[0][tid];
+#pragma unroll
+            for (int q = 1; q < CG; ++q) sum += part[q][tid];
+            const int rw = (UP ? j1 : 0) + r0 + tid;
+            z128* dst = (!UP || rw < k) ? in + f.col0 + rw : cb + f.st0 + (rw - k);
+            *dst = ld_cg(dst) - sum;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < SB / NWARP; ++q) {
+            const int rr = wid + q * NWARP;
+            if (r0 + rr >= nrows) break;
+            const int row = (UP ? j1 : 0) + r0 + rr;
+            const T* u = (!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
+            z128 acc = mk(0, 0);
+            for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * zs[c];
+            for (int o = 16; o > 0; o >>= 1) {
+              acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+              acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            }
+            if (lane == 0) {
+              z128* dst = (!UP || row < k) ? in + f.col0 + row : cb + f.st0 + (row - k);
+              *dst = ld_cg(dst) - acc;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void k_unpermute(const z128* __restrict__ y, z128* __restrict__ x, const int* __restrict__ gperm, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[gperm[i]] = y[i];
@@ -592,28 +795,40 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   constexpr int YMAX = 32768;
   SweepTrace tr;
   tr.begin(st);
+  // bottom sub-trees are swept by k_subtree; the level loops then only see the top of the tree
+  const int nsub = h.use_subtrees ? (int)sym.sub_last.size() : 0;
+  const std::vector<int>& lvl_ptr = nsub ? sym.top_lvl_ptr : sym.lvl_ptr;
+  const std::vector<int>& lvl_front = nsub ? sym.top_lvl_front : sym.lvl_front;
+  const int* d_lvl_front = nsub ? h.d_top_lvl_front : h.d_lvl_front;
   if (sym.n_iso > 0) {
     k_solve_decoupled<T, H><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, x, y);
     LSA_LAUNCH_CHECK();
     launches++;
   }
-  // ---- up sweep: deepest level first
+  // ---- up sweep: bottom sub-trees, then the top levels (deepest first)
+  if (nsub) {
+    k_subtree<T, H, true><<<nsub, 256, 0, st>>>(h.d_fronts, h.d_sub_first, h.d_sub_last, h.d_child_idx, h.d_ea_map, h.d_gperm,
+                                                h.d_st_idx, fac, x, y, z, cb);
+    LSA_LAUNCH_CHECK();
+    tr.mark("up_subtree", -1, 0, nsub, 1);
+    launches++;
+  }
   for (int d = sym.nlevels - 1; d >= 0; --d) {
-    const int lbeg = sym.lvl_ptr[d], cnt_all = sym.lvl_ptr[d + 1] - lbeg;
+    const int lbeg = lvl_ptr[d], cnt_all = lvl_ptr[d + 1] - lbeg;
     for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
       const int cnt = std::min(YMAX, cnt_all - y0), first = lbeg + y0;
-      k_up_gather<!H><<<cnt, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+      k_up_gather<!H><<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
       LSA_LAUNCH_CHECK();
       tr.mark("up_gather", d, 0, cnt, 1);
       launches++;
-      const int maxk = sym.fronts[sym.lvl_front[first]].k;
+      const int maxk = sym.fronts[lvl_front[first]].k;
       int max_m = 0;
-      for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[sym.lvl_front[q]].k + sym.fronts[sym.lvl_front[q]].r);
+      for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
       const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
       // very tall fronts (3-D top separators) need the whole GPU per step; up to ~4 k rows a cluster of 8
       // SMs keeps up and saves the launches
       if (maxk > SB && max_m <= 4096 && h.use_clusters) {
-        sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, h.d_lvl_front, first, fac, y, z, cb);
+        sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
         tr.mark("up_cluster", d, csize, csize * cnt, 1);
         launches++;
         continue;
@@ -621,14 +836,14 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       for (int j0 = 0; j0 < maxk; j0 += SB) {
         int act = 0, max_rows = 0;
         for (int q = first; q < first + cnt; ++q) {
-          const Front& f = sym.fronts[sym.lvl_front[q]];
+          const Front& f = sym.fronts[lvl_front[q]];
           if (f.k <= j0) break;
           act++;
           max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
         }
         const int gx = std::max(1, cdiv(max_rows, SB));
-        if (maxk > SB) k_step<T, H, true, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, z, cb);
-        else k_step<T, H, true, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, y, z, cb);
+        if (maxk > SB) k_step<T, H, true, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
+        else k_step<T, H, true, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
         LSA_LAUNCH_CHECK();
         tr.mark("up_step", d, j0, gx, act);
         launches++;
@@ -637,50 +852,57 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   }
   // ---- down sweep: roots first
   for (int d = 0; d < sym.nlevels; ++d) {
-    const int lbeg = sym.lvl_ptr[d], cnt_all = sym.lvl_ptr[d + 1] - lbeg;
+    const int lbeg = lvl_ptr[d], cnt_all = lvl_ptr[d + 1] - lbeg;
     for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
       const int cnt = std::min(YMAX, cnt_all - y0), first = lbeg + y0;
-      const int maxk = sym.fronts[sym.lvl_front[first]].k;
+      const int maxk = sym.fronts[lvl_front[first]].k;
       int maxr = 0;
-      for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[sym.lvl_front[q]].r);
+      for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[lvl_front[q]].r);
       if (maxr > 0) {
-        if (maxr > 512) k_down_off<T, H, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
-        else k_down_off<T, H, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
+        if (maxr > 512) k_down_off<T, H, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
+        else k_down_off<T, H, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
         LSA_LAUNCH_CHECK();
         tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
         launches++;
       }
       int max_mk = 0;
-      for (int q = first; q < first + cnt; ++q) max_mk = std::max(max_mk, sym.fronts[sym.lvl_front[q]].k + sym.fronts[sym.lvl_front[q]].r);
+      for (int q = first; q < first + cnt; ++q) max_mk = std::max(max_mk, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
       if (maxk > SB && max_mk <= 4096 && h.use_clusters) {
         int max_m = 0;
-        for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[sym.lvl_front[q]].k);
+        for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k);
         const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
-        sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, h.d_lvl_front, first, fac, z, y, cb);
+        sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
         tr.mark("down_cluster", d, csize, csize * cnt, 1);
         launches++;
       } else {
         for (int j0 = ((maxk - 1) / SB) * SB; j0 >= 0; j0 -= SB) {
           int act = 0;
           for (int q = first; q < first + cnt; ++q) {
-            if (sym.fronts[sym.lvl_front[q]].k <= j0) break;
+            if (sym.fronts[lvl_front[q]].k <= j0) break;
             act++;
           }
           if (act == 0) continue;
           const int gx = std::max(1, cdiv(j0, SB));
-          if (maxk > SB) k_step<T, H, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
-          else k_step<T, H, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, z, y, cb);
+          if (maxk > SB) k_step<T, H, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
+          else k_step<T, H, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
           LSA_LAUNCH_CHECK();
           tr.mark("down_step", d, j0, gx, act);
           launches++;
         }
       }
       if (H) {
-        k_level_unpermute<<<cnt, 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_gperm, y, x);
+        k_level_unpermute<<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_gperm, y, x);
         LSA_LAUNCH_CHECK();
         launches++;
       }
     }
+  }
+  if (nsub) {
+    k_subtree<T, H, false><<<nsub, 256, 0, st>>>(h.d_fronts, h.d_sub_first, h.d_sub_last, h.d_child_idx, h.d_ea_map, h.d_gperm,
+                                                 h.d_st_idx, fac, x, y, z, cb);
+    LSA_LAUNCH_CHECK();
+    tr.mark("down_subtree", -1, 0, nsub, 1);
+    launches++;
   }
   if (H) {
     if (sym.n_iso > 0) k_unpermute<<<cdiv(sym.n_iso, 256), 256, 0, st>>>(y, x, h.d_gperm, sym.n_iso);

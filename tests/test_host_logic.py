@@ -94,6 +94,31 @@ def test_symbolic_counters_and_pattern_reuse():
     assert a_dst.max() < info.factor_entries
 
 
+def test_bottom_subtree_partition_is_consistent():
+    pc = pencils.assemble_pencil((60, 30), (15.0, 6.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 3.0))
+    h = _lib.Handle(pc.n, device=-1)
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64,
+                     order_last=(pc.A.diagonal() == 0).astype(np.uint8))
+    first, last = h.symbolic_array("sub_first"), h.symbolic_array("sub_last")
+    parent, k = h.symbolic_array("parent"), h.symbolic_array("front_k")
+    top = h.symbolic_array("top_lvl_front")
+    assert len(first) > 0 and np.all(first <= last)
+    covered = np.zeros(info.n_fronts, dtype=int)
+    for a, b in zip(first, last):
+        covered[a:b + 1] += 1
+        # a sub-tree is closed under "child of": every front in the range except the root has its parent inside
+        inside = np.arange(a, b)
+        assert np.all((parent[inside] > inside) & (parent[inside] <= b))
+        assert k[a:b + 1].max() <= 256
+        assert parent[b] < 0 or covered[parent[b]] == 0          # the root's parent belongs to the top part
+    assert covered.max() == 1
+    assert sorted(top.tolist()) == np.nonzero(covered == 0)[0].tolist()
+    tp = h.symbolic_array("top_lvl_ptr")
+    level = h.symbolic_array("level")
+    for d in range(info.n_levels):
+        assert np.all(level[top[tp[d]:tp[d + 1]]] == d)
+
+
 def test_options_and_pressure_placement_rule():
     pc = pencils.assemble_pencil((20, 10), (6.0, 2.0), re=40.0)
     flag = (pc.A.diagonal() == 0).astype(np.uint8)
