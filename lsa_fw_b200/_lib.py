@@ -132,7 +132,7 @@ EXPORTS = [
 
 _ARRAY_DTYPES = {
     "perm": np.int32, "iperm": np.int32, "sn_ptr": np.int32, "st_ptr": np.int64, "st_idx": np.int32,
-    "ea_map": np.int32, "lvl_ptr": np.int32, "lvl_front": np.int32, "sub_first": np.int32, "sub_last": np.int32,
+    "ea_map": np.int32, "lvl_ptr": np.int32, "lvl_front": np.int32, "bot_list": np.int32, "is_bottom": np.int32,
     "top_lvl_ptr": np.int32, "top_lvl_front": np.int32, "a_dst": np.int64, "m_dst": np.int64,
     "parent": np.int32, "level": np.int32, "front_k": np.int32, "front_r": np.int32, "p_off": np.int64,
     "q_off": np.int64, "c_off": np.int64,

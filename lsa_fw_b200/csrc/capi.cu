@@ -42,7 +42,7 @@ void free_csr(CsrDev& c) {
 
 void free_device(lsa_handle_impl& h) {
   drop_solve_graphs(h);
-  dfree(h.d_fronts); dfree(h.d_lvl_front); dfree(h.d_top_lvl_front); dfree(h.d_sub_first); dfree(h.d_sub_last); dfree(h.d_st_idx); dfree(h.d_ea_map); dfree(h.d_child_idx);
+  dfree(h.d_fronts); dfree(h.d_lvl_front); dfree(h.d_top_lvl_front); dfree(h.d_bot_list); dfree(h.d_is_bottom); dfree(h.d_bot_state); dfree(h.d_st_idx); dfree(h.d_ea_map); dfree(h.d_child_idx);
   dfree(h.d_a_dst); dfree(h.d_m_dst); dfree(h.d_perm); dfree(h.d_ipiv); dfree(h.d_gperm); dfree(h.d_stats);
   if (h.d_a_orig) cudaFree(h.d_a_orig);
   if (h.d_m_orig) cudaFree(h.d_m_orig);
@@ -352,8 +352,14 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     h->d_fronts = dupload(sym.fronts, st);
     h->d_lvl_front = dupload(sym.lvl_front, st);
     h->d_top_lvl_front = dupload(sym.top_lvl_front, st);
-    h->d_sub_first = dupload(sym.sub_first, st);
-    h->d_sub_last = dupload(sym.sub_last, st);
+    h->d_bot_list = dupload(sym.bot_list, st);
+    h->d_is_bottom = dupload(sym.is_bottom, st);
+    h->d_bot_state = dalloc<int>((size_t)sym.ns + 2);
+    {
+      cudaDeviceProp prop;
+      LSA_CUDA(cudaGetDeviceProperties(&prop, h->device));
+      h->num_sms = prop.multiProcessorCount;
+    }
     h->d_st_idx = dupload(sym.st_idx, st);
     h->d_ea_map = dupload(sym.ea_map, st);
     h->d_child_idx = dupload(sym.child_idx, st);
@@ -442,8 +448,8 @@ int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int
   if (nm == "ea_map") return give(s.ea_map.data(), s.ea_map.size(), 4);
   if (nm == "lvl_ptr") return give(s.lvl_ptr.data(), s.lvl_ptr.size(), 4);
   if (nm == "lvl_front") return give(s.lvl_front.data(), s.lvl_front.size(), 4);
-  if (nm == "sub_first") return give(s.sub_first.data(), s.sub_first.size(), 4);
-  if (nm == "sub_last") return give(s.sub_last.data(), s.sub_last.size(), 4);
+  if (nm == "bot_list") return give(s.bot_list.data(), s.bot_list.size(), 4);
+  if (nm == "is_bottom") return give(s.is_bottom.data(), s.is_bottom.size(), 4);
   if (nm == "top_lvl_ptr") return give(s.top_lvl_ptr.data(), s.top_lvl_ptr.size(), 4);
   if (nm == "top_lvl_front") return give(s.top_lvl_front.data(), s.top_lvl_front.size(), 4);
   if (nm == "a_dst") return give(s.a_dst.data(), s.a_dst.size(), 8);

@@ -70,8 +70,10 @@ struct lsa_handle_impl {
   Front* d_fronts = nullptr;
   int* d_lvl_front = nullptr;
   int* d_top_lvl_front = nullptr;
-  int* d_sub_first = nullptr;
-  int* d_sub_last = nullptr;
+  int* d_bot_list = nullptr;
+  int* d_is_bottom = nullptr;
+  int* d_bot_state = nullptr;   // [0] up queue, [1] down queue, [2 + s] completion flag of front s
+  int num_sms = 148;
   int* d_st_idx = nullptr;
   int* d_ea_map = nullptr;
   int* d_child_idx = nullptr;
@@ -149,7 +151,7 @@ struct lsa_handle_impl {
   std::vector<SolveGraph> solve_graphs;
   bool use_graphs = true;
   bool use_clusters = true;
-  bool use_subtrees = true;   // sweep the bottom sub-trees inside single CTAs (one launch per direction)   // sweep multi-step levels with thread-block clusters (one launch per level)
+  bool use_subtrees = true;   // sweep the bottom of the tree with the persistent task-based kernel   // sweep multi-step levels with thread-block clusters (one launch per level)
   double coupled_fraction = 0.5;
 };
 

@@ -565,30 +565,56 @@ static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fron
   }
 }
 
-// ------------------------------------------------------------------ bottom sub-trees (one CTA each)
+// ------------------------------------------------------- bottom of the tree (persistent, task based)
 //
 // The lowest levels of the assembly tree hold most fronts but little data per front; sweeping them
-// level by level costs four dependent launches per level.  Instead every bottom sub-tree (chosen by the
-// symbolic phase: <= 1 M factor entries, pivot blocks <= 256) is swept front by front inside ONE CTA:
-// post-order on the way up, reverse on the way down, __syncthreads between fronts and no launch
-// boundaries.  Data written earlier by the same CTA is re-read through L2 (ld.cg).
+// level by level costs four dependent launches per level and a global barrier between levels.  The
+// bottom part (sub-trees made of small fronts only) is instead swept by ONE persistent kernel per
+// direction: CTAs take fronts from a queue in post-order (up) / reverse post-order (down) and wait on
+// per-front completion flags of their children (up) or parent (down) -- a front starts as soon as what
+// it depends on is done, there is no level barrier and no launch.  Forward progress: the grid is sized
+// to be fully resident and the queue order is a topological order, so everything a CTA can wait for has
+// already been handed to a running CTA.  Data produced by other CTAs is read through L2 (ld.cg) after a
+// fence; flags are written with a release fence.
+__device__ __forceinline__ int ld_flag(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
 template <class T, bool H, bool UP>
-__global__ void __launch_bounds__(256) k_subtree(const Front* __restrict__ fronts, const int* __restrict__ sub_first,
-                                                 const int* __restrict__ sub_last, const int* __restrict__ child_idx,
-                                                 const int* __restrict__ ea_map, const int* __restrict__ gperm,
-                                                 const int* __restrict__ st_idx, const T* __restrict__ fac, z128* x,
-                                                 z128* y, z128* z, z128* cb) {
+__global__ void __launch_bounds__(256) k_bottom(const Front* __restrict__ fronts, const int* __restrict__ bot_list, int nbot,
+                                                const int* __restrict__ is_bottom, int* __restrict__ queue,
+                                                int* __restrict__ done, const int* __restrict__ child_idx,
+                                                const int* __restrict__ ea_map, const int* __restrict__ gperm,
+                                                const int* __restrict__ st_idx, const T* __restrict__ fac, z128* x,
+                                                z128* y, z128* z, z128* cb) {
   constexpr int NT = 256, CG = NT / SB, NWARP = NT / 32;
   __shared__ z128 ys[SB];
   __shared__ z128 zs[SB];
   __shared__ z128 part[CG][SB];
   __shared__ z128 xs[NT];
   __shared__ z128 red[NWARP][33];
+  __shared__ int s_front;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int first = sub_first[blockIdx.x], last = sub_last[blockIdx.x];
-  for (int it = 0; it <= last - first; ++it) {
-    const int s = UP ? first + it : last - it;
+  constexpr int DONE = UP ? 1 : 2;  // flag value written by this sweep (the flags are zeroed once per solve)
+  while (true) {
+    __syncthreads();
+    if (tid == 0) {
+      const int q = atomicAdd(queue, 1);
+      s_front = q < nbot ? bot_list[UP ? q : nbot - 1 - q] : -1;
+    }
+    __syncthreads();
+    const int s = s_front;
+    if (s < 0) break;
     const Front f = fronts[s];
+    // ---- wait for the fronts this one depends on
+    if (UP) {
+      for (int q = tid; q < f.nchild; q += NT) {
+        const int c = child_idx[f.child0 + q];
+        while (ld_flag(done + c) < 1) __nanosleep(64);
+      }
+    } else if (tid == 0 && f.parent >= 0 && is_bottom[f.parent]) {
+      while (ld_flag(done + f.parent) < 2) __nanosleep(64);
+    }
+    __threadfence();
+    __syncthreads();
     const int k = f.k, r = f.r;
     const long long m = (long long)k + r;
     const T* P = fac + f.p_off;
@@ -765,6 +791,10 @@ __global__ void __launch_bounds__(256) k_subtree(const Front* __restrict__ front
       }
       __syncthreads();
     }
+    // ---- publish: everything this front wrote is visible before its flag
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(done + s, DONE);
   }
 }
 
@@ -796,7 +826,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   SweepTrace tr;
   tr.begin(st);
   // bottom sub-trees are swept by k_subtree; the level loops then only see the top of the tree
-  const int nsub = h.use_subtrees ? (int)sym.sub_last.size() : 0;
+  const int nsub = h.use_subtrees ? (int)sym.bot_list.size() : 0;
   const std::vector<int>& lvl_ptr = nsub ? sym.top_lvl_ptr : sym.lvl_ptr;
   const std::vector<int>& lvl_front = nsub ? sym.top_lvl_front : sym.lvl_front;
   const int* d_lvl_front = nsub ? h.d_top_lvl_front : h.d_lvl_front;
@@ -805,12 +835,25 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     LSA_LAUNCH_CHECK();
     launches++;
   }
-  // ---- up sweep: bottom sub-trees, then the top levels (deepest first)
+  // ---- up sweep: bottom part (task based), then the top levels (deepest first)
+  int bottom_grid = 0;
   if (nsub) {
-    k_subtree<T, H, true><<<nsub, 256, 0, st>>>(h.d_fronts, h.d_sub_first, h.d_sub_last, h.d_child_idx, h.d_ea_map, h.d_gperm,
-                                                h.d_st_idx, fac, x, y, z, cb);
+    // persistent grid: exactly as many CTAs as are resident at once
+    static int occ[2][2] = {{0, 0}, {0, 0}};
+    int& o = occ[scalar_traits<T>::is_complex][H];
+    if (o == 0) {
+      int a = 0, b = 0;
+      LSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_bottom<T, H, true>, 256, 0));
+      LSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_bottom<T, H, false>, 256, 0));
+      o = std::max(1, std::min(a, b));
+    }
+    bottom_grid = std::min(nsub, o * h.num_sms);
+    LSA_CUDA(cudaMemsetAsync(h.d_bot_state, 0, sizeof(int) * (size_t)(sym.ns + 2), st));
+    k_bottom<T, H, true><<<bottom_grid, 256, 0, st>>>(h.d_fronts, h.d_bot_list, nsub, h.d_is_bottom, h.d_bot_state,
+                                                      h.d_bot_state + 2, h.d_child_idx, h.d_ea_map, h.d_gperm, h.d_st_idx, fac,
+                                                      x, y, z, cb);
     LSA_LAUNCH_CHECK();
-    tr.mark("up_subtree", -1, 0, nsub, 1);
+    tr.mark("up_bottom", -1, 0, bottom_grid, 1);
     launches++;
   }
   for (int d = sym.nlevels - 1; d >= 0; --d) {
@@ -898,10 +941,11 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     }
   }
   if (nsub) {
-    k_subtree<T, H, false><<<nsub, 256, 0, st>>>(h.d_fronts, h.d_sub_first, h.d_sub_last, h.d_child_idx, h.d_ea_map, h.d_gperm,
-                                                 h.d_st_idx, fac, x, y, z, cb);
+    k_bottom<T, H, false><<<bottom_grid, 256, 0, st>>>(h.d_fronts, h.d_bot_list, nsub, h.d_is_bottom, h.d_bot_state + 1,
+                                                       h.d_bot_state + 2, h.d_child_idx, h.d_ea_map, h.d_gperm, h.d_st_idx, fac,
+                                                       x, y, z, cb);
     LSA_LAUNCH_CHECK();
-    tr.mark("down_subtree", -1, 0, nsub, 1);
+    tr.mark("down_bottom", -1, 0, bottom_grid, 1);
     launches++;
   }
   if (H) {

@@ -21,6 +21,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -610,63 +611,27 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
     }
     sym.pool_size[d & 1] = std::max(sym.pool_size[d & 1], c);
   }
-  // ---- bottom sub-trees for the solve sweeps
+  // ---- bottom part of the tree for the solve sweeps: every front whose whole sub-tree consists of
+  // small fronts (pivot block <= 256, <= 1024 remaining rows).  These are swept by ONE persistent,
+  // dependency-driven kernel (k_bottom); the rest ("top") is swept level by level.
   {
-    std::vector<long long> sub_entries(ns, 0);
-    std::vector<int> desc_first(ns), desc_count(ns, 1), sub_maxk(ns, 0), sub_maxr(ns, 0);
-    long long total_entries = 0;
-    for (int s = 0; s < ns; ++s) {
-      const Front& f = sym.fronts[s];
-      sub_entries[s] += (long long)(f.k + f.r) * f.k + (long long)f.k * f.r;
-      total_entries += (long long)(f.k + f.r) * f.k + (long long)f.k * f.r;
-      desc_first[s] = std::min(s, s);
-      sub_maxk[s] = std::max(sub_maxk[s], f.k);
-      sub_maxr[s] = std::max(sub_maxr[s], f.r);
-    }
-    for (int s = 0; s < ns; ++s) desc_first[s] = s;
-    for (int s = 0; s < ns; ++s) {  // children precede parents
-      const int p = parent[s];
-      if (p < 0) continue;
-      sub_entries[p] += sub_entries[s];
-      desc_first[p] = std::min(desc_first[p], desc_first[s]);
-      desc_count[p] += desc_count[s];
-      sub_maxk[p] = std::max(sub_maxk[p], sub_maxk[s]);
-      sub_maxr[p] = std::max(sub_maxr[p], sub_maxr[s]);
-    }
-    // budget: aim at >= ~4 sub-trees per SM, each between 32 K and 1 M factor entries
-    long long budget = std::min<long long>(1 << 20, std::max<long long>(1 << 15, total_entries / 600));
-    auto eligible = [&](int s) {
-      return sub_entries[s] <= budget && desc_count[s] == s - desc_first[s] + 1 && sub_maxk[s] <= 256 &&
-             sub_maxr[s] <= 1024;
-    };
-    std::vector<char> in_sub(ns, 0);
-    for (int s = ns - 1; s >= 0; --s) {  // parents before children
-      const int p = parent[s];
-      if (p >= 0 && in_sub[p]) {
-        in_sub[s] = 1;
-        continue;
+    std::vector<char> bottom(ns, 0);
+    for (int s = 0; s < ns; ++s) bottom[s] = sym.fronts[s].k <= 256 && sym.fronts[s].r <= 1024;
+    for (int s = 0; s < ns; ++s)  // children precede parents: a non-bottom child disqualifies its ancestors
+      if (!bottom[s] && parent[s] >= 0) bottom[parent[s]] = 0;
+    // (one pass suffices because indices are a post-order: parent[s] > s)
+    sym.bot_list.clear();
+    sym.is_bottom.assign(ns, 0);
+    for (int s = 0; s < ns; ++s)
+      if (bottom[s]) {
+        sym.bot_list.push_back(s);
+        sym.is_bottom[s] = 1;
       }
-      if (eligible(s)) {
-        in_sub[s] = 1;
-        sym.sub_first.push_back(desc_first[s]);
-        sym.sub_last.push_back(s);
-      }
-    }
-    // largest sub-trees first (they finish last)
-    std::vector<int> ord(sym.sub_last.size());
-    std::iota(ord.begin(), ord.end(), 0);
-    std::sort(ord.begin(), ord.end(), [&](int a, int b) { return sub_entries[sym.sub_last[a]] > sub_entries[sym.sub_last[b]]; });
-    std::vector<int> f2(ord.size()), l2(ord.size());
-    for (size_t i = 0; i < ord.size(); ++i) {
-      f2[i] = sym.sub_first[ord[i]];
-      l2[i] = sym.sub_last[ord[i]];
-    }
-    sym.sub_first.swap(f2);
-    sym.sub_last.swap(l2);
     sym.top_lvl_ptr.assign(nlev + 1, 0);
+    sym.top_lvl_front.clear();
     for (int d = 0; d < nlev; ++d) {
       for (int q = sym.lvl_ptr[d]; q < sym.lvl_ptr[d + 1]; ++q)
-        if (!in_sub[sym.lvl_front[q]]) sym.top_lvl_front.push_back(sym.lvl_front[q]);
+        if (!bottom[sym.lvl_front[q]]) sym.top_lvl_front.push_back(sym.lvl_front[q]);
       sym.top_lvl_ptr[d + 1] = (int)sym.top_lvl_front.size();
     }
   }

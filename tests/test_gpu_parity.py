@@ -414,8 +414,10 @@ def test_large_front_paths_match_scipy_solve():
     C = (pc.A - sigma * pc.M).tocsc()
     b = np.random.default_rng(3).standard_normal(pc.n) + 1j * np.random.default_rng(4).standard_normal(pc.n)
     xs = spla.splu(C).solve(b)
-    for opt, val in (("use_clusters", 1), ("use_clusters", 0)):
-        h.set_option(opt, val)
+    for opts in (dict(use_clusters=1, use_subtrees=1), dict(use_clusters=0, use_subtrees=1),
+                 dict(use_clusters=1, use_subtrees=0), dict(use_clusters=0, use_subtrees=0, use_graphs=0)):
+        for opt, val in opts.items():
+            h.set_option(opt, val)
         h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)      # re-factor: drops the captured sweep graphs
         x = h.solve(b)
         assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-9

@@ -94,27 +94,21 @@ def test_symbolic_counters_and_pattern_reuse():
     assert a_dst.max() < info.factor_entries
 
 
-def test_bottom_subtree_partition_is_consistent():
+def test_bottom_partition_is_closed_under_descendants():
     pc = pencils.assemble_pencil((60, 30), (15.0, 6.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 3.0))
     h = _lib.Handle(pc.n, device=-1)
     info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64,
                      order_last=(pc.A.diagonal() == 0).astype(np.uint8))
-    first, last = h.symbolic_array("sub_first"), h.symbolic_array("sub_last")
-    parent, k = h.symbolic_array("parent"), h.symbolic_array("front_k")
-    top = h.symbolic_array("top_lvl_front")
-    assert len(first) > 0 and np.all(first <= last)
-    covered = np.zeros(info.n_fronts, dtype=int)
-    for a, b in zip(first, last):
-        covered[a:b + 1] += 1
-        # a sub-tree is closed under "child of": every front in the range except the root has its parent inside
-        inside = np.arange(a, b)
-        assert np.all((parent[inside] > inside) & (parent[inside] <= b))
-        assert k[a:b + 1].max() <= 256
-        assert parent[b] < 0 or covered[parent[b]] == 0          # the root's parent belongs to the top part
-    assert covered.max() == 1
-    assert sorted(top.tolist()) == np.nonzero(covered == 0)[0].tolist()
-    tp = h.symbolic_array("top_lvl_ptr")
-    level = h.symbolic_array("level")
+    bot, is_bot = h.symbolic_array("bot_list"), h.symbolic_array("is_bottom")
+    parent, k, r = h.symbolic_array("parent"), h.symbolic_array("front_k"), h.symbolic_array("front_r")
+    top, tp, level = h.symbolic_array("top_lvl_front"), h.symbolic_array("top_lvl_ptr"), h.symbolic_array("level")
+    assert len(bot) > 0 and np.all(np.diff(bot) > 0)                   # ascending = post-order (queue order)
+    assert sorted(bot.tolist()) == np.nonzero(is_bot)[0].tolist()
+    assert k[bot].max() <= 256 and r[bot].max() <= 1024
+    for s in range(info.n_fronts):                                      # a top front never sits below a bottom one
+        if parent[s] >= 0 and is_bot[parent[s]]:
+            assert is_bot[s]
+    assert sorted(top.tolist()) == np.nonzero(is_bot == 0)[0].tolist()
     for d in range(info.n_levels):
         assert np.all(level[top[tp[d]:tp[d + 1]]] == d)
 
@@ -147,6 +141,7 @@ def test_options_and_pressure_placement_rule():
         h.set_option("no_such_option", 1.0)
     h.set_option("use_graphs", 0)
     h.set_option("use_clusters", 0)
+    h.set_option("use_subtrees", 0)
 
 
 # ------------------------------------------------------------------------------- Rayleigh-Ritz core

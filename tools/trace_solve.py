@@ -26,8 +26,17 @@ if "--factor" in sys.argv:
     h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
     os.environ.pop("LSA_TRACE")
 b = np.random.default_rng(0).standard_normal(pc.n).astype(complex)
+import time
 for _ in range(3):
     h.solve(b)
+t0 = time.perf_counter()
+for _ in range(20):
+    h.solve(b)
+print(f"{name}: host-roundtrip solve {(time.perf_counter() - t0) / 20 * 1e3:.3f} ms (incl. 2 x {pc.n * 16 / 1e6:.0f} MB PCIe copies)", flush=True)
+r = h.eigs(nev=4, ncv=24, tol=1e-8, max_restarts=2, which="TARGET_MAGNITUDE", transform=_lib.LSA_ST_SINVERT, sigma=sigma, seed=1)
+print(f"{name}: device sweep {r.seconds_solve / r.n_op_applies * 1e3:.3f} ms/apply over {r.n_op_applies} applies "
+      f"(LSA_SUBTREE_DIV={os.environ.get('LSA_SUBTREE_DIV')}, NO_SUBTREES={os.environ.get('LSA_NO_SUBTREES')}, "
+      f"NO_GRAPHS={os.environ.get('LSA_NO_GRAPHS')})", flush=True)
 os.environ["LSA_TRACE"] = "1"
 h.solve(b)
 os.environ.pop("LSA_TRACE")
