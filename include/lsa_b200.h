@@ -130,7 +130,10 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
  *   "coupled_fraction" (default 0.5): an unknown with a structurally zero diagonal (pressure) is eliminated
  *       no earlier than the front in which this share of its coupled regular unknowns has been eliminated
  *       (1.0 = all of them: most robust, ~+40-70 % flops in 2-D);
- *   "use_graphs" (default 1): replay the triangular-solve sweeps from CUDA graphs. */
+ *   "use_graphs" (default 1): replay the triangular-solve sweeps from CUDA graphs;
+ *   "use_clusters" (default 1): sweep multi-step levels with one thread-block cluster per front;
+ *   "use_subtrees" (default 0): sweep the bottom of the tree with the persistent task-based kernel
+ *       (kept for comparison: measured 2.7x - 7x slower than the level-synchronous sweep). */
 int lsa_set_option(lsa_handle* h, const char* name, double value);
 int lsa_symbolic_info_get(const lsa_handle* h, lsa_symbolic_info* out);
 /* Copies a named internal array (perm, iperm, sn_ptr, st_ptr, st_idx, ea_map, parent, level, front_k,

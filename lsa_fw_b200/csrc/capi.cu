@@ -536,9 +536,7 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   cudaEventRecord(e0, st);
   h->scalar = -1;
   drop_solve_graphs(*h);
-  if (const char* e = getenv("LSA_NO_SUBTREES")) {
-    if (atoi(e) != 0) h->use_subtrees = false;
-  }
+  if (const char* e = getenv("LSA_SUBTREES")) h->use_subtrees = atoi(e) != 0;
   if (const char* e = getenv("LSA_NO_CLUSTERS")) {
     if (atoi(e) != 0) h->use_clusters = false;
   }

@@ -151,7 +151,7 @@ struct lsa_handle_impl {
   std::vector<SolveGraph> solve_graphs;
   bool use_graphs = true;
   bool use_clusters = true;
-  bool use_subtrees = true;   // sweep the bottom of the tree with the persistent task-based kernel   // sweep multi-step levels with thread-block clusters (one launch per level)
+  bool use_subtrees = false;  // sweep the bottom of the tree with the persistent task-based kernel (measured slower)   // sweep multi-step levels with thread-block clusters (one launch per level)
   double coupled_fraction = 0.5;
 };
 

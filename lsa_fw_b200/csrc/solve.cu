@@ -825,7 +825,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   constexpr int YMAX = 32768;
   SweepTrace tr;
   tr.begin(st);
-  // bottom sub-trees are swept by k_subtree; the level loops then only see the top of the tree
+  // optional: the bottom of the tree swept by k_bottom; the level loops then only see the top of the tree
   const int nsub = h.use_subtrees ? (int)sym.bot_list.size() : 0;
   const std::vector<int>& lvl_ptr = nsub ? sym.top_lvl_ptr : sym.lvl_ptr;
   const std::vector<int>& lvl_front = nsub ? sym.top_lvl_front : sym.lvl_front;
