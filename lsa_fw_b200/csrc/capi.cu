@@ -396,6 +396,8 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->use_graphs = value != 0.0;
   } else if (nm == "use_clusters") {
     h->use_clusters = value != 0.0;
+  } else if (nm == "cluster_max_rows") {
+    h->cluster_max_rows = (int)value;
   } else if (nm == "use_subtrees") {
     h->use_subtrees = value != 0.0;
   } else {
@@ -537,6 +539,7 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   h->scalar = -1;
   drop_solve_graphs(*h);
   if (const char* e = getenv("LSA_SUBTREES")) h->use_subtrees = atoi(e) != 0;
+  if (const char* e = getenv("LSA_CLUSTER_MAX_ROWS")) h->cluster_max_rows = atoi(e);
   if (const char* e = getenv("LSA_NO_CLUSTERS")) {
     if (atoi(e) != 0) h->use_clusters = false;
   }

@@ -870,7 +870,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
       // very tall fronts (3-D top separators) need the whole GPU per step; up to ~4 k rows a cluster of 8
       // SMs keeps up and saves the launches
-      if (maxk > SB && max_m <= 4096 && h.use_clusters) {
+      if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
         sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
         tr.mark("up_cluster", d, csize, csize * cnt, 1);
         launches++;
@@ -910,7 +910,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       }
       int max_mk = 0;
       for (int q = first; q < first + cnt; ++q) max_mk = std::max(max_mk, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
-      if (maxk > SB && max_mk <= 4096 && h.use_clusters) {
+      if (maxk > SB && max_mk <= h.cluster_max_rows && h.use_clusters) {
         int max_m = 0;
         for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k);
         const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
