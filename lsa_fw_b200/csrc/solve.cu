@@ -868,8 +868,8 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       int max_m = 0;
       for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
       const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
-      // very tall fronts (3-D top separators) need the whole GPU per step; up to ~4 k rows a cluster of 8
-      // SMs keeps up and saves the launches
+      // tall fronts need the whole GPU per step; up to `cluster_max_rows` rows a cluster of <= 8 SMs keeps up
+      // and saves the launches (inside a CUDA graph the two are within 3 % of each other, profiles/r1f_*)
       if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
         sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
         tr.mark("up_cluster", d, csize, csize * cnt, 1);
