@@ -32,7 +32,6 @@ import shutil
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np

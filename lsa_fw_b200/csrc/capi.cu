@@ -372,9 +372,9 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     h->d_x = dalloc<z128>(n); h->d_w = dalloc<z128>(n); h->d_t = dalloc<z128>(n); h->d_t2 = dalloc<z128>(n); h->d_io = dalloc<z128>(n);
     h->d_r1 = dalloc<z128>(n); h->d_r2 = dalloc<z128>(n); h->d_r3 = dalloc<z128>(n);
     h->d_cb = dalloc<z128>(sym.st_idx.size());
-    h->d_part = dalloc<z128>((size_t)1024 * 128);
+    h->d_part = dalloc<z128>((size_t)1024 * 256);
     h->d_npart = dalloc<double>((size_t)cdiv(n, 256) + 1);
-    h->d_h = dalloc<z128>(256);
+    h->d_h = dalloc<z128>(512);
     h->d_flag = dalloc<int>(1);
     h->d_ipart = dalloc<int>(256);
     h->d_rr = dalloc<RrInfo>(1);

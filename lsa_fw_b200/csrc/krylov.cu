@@ -168,8 +168,8 @@ static constexpr int DOT_ROWS = 32;   // row lanes
 static constexpr int DOT_CG = 8;      // column groups
 static constexpr int MAXC_PER = 16;   // columns per thread -> up to 128 basis vectors
 
-// part[blk * ldp + c] = sum over the block's rows of conj(V[i, c]) w[i],  c < j
-__global__ void __launch_bounds__(256) k_dots(int n, int j, const z128* __restrict__ V, long long ldv,
+// part[blk * ldp + c] = sum over the block's rows of conj(V[i, c]) w[i],  c0 <= c < min(j, c0 + 128)
+__global__ void __launch_bounds__(256) k_dots(int n, int j, int c0, const z128* __restrict__ V, long long ldv,
                                               const z128* __restrict__ w, z128* __restrict__ part, int ldp,
                                               int rows_per_block) {
   const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;
@@ -182,13 +182,13 @@ __global__ void __launch_bounds__(256) k_dots(int n, int j, const z128* __restri
     const z128 wi = w[i];
 #pragma unroll
     for (int q = 0; q < MAXC_PER; ++q) {
-      const int c = cg + q * DOT_CG;
+      const int c = c0 + cg + q * DOT_CG;
       if (c < j) acc[q] += conj_(V[i + c * ldv]) * wi;
     }
   }
 #pragma unroll
   for (int q = 0; q < MAXC_PER; ++q) {
-    const int c = cg + q * DOT_CG;
+    const int c = c0 + cg + q * DOT_CG;
     if (c < j) {
       z128 a = acc[q];
       for (int o = 16; o > 0; o >>= 1) {
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) k_reduce_h(int j, int nblk, const z128* _
 __global__ void __launch_bounds__(256) k_update(int n, int j, const z128* __restrict__ V, long long ldv,
                                                 const z128* __restrict__ h, z128* __restrict__ w,
                                                 double* __restrict__ npart) {
-  __shared__ z128 hs[128];
+  __shared__ z128 hs[256];
   __shared__ double red[8];
   if ((int)threadIdx.x < j) hs[threadIdx.x] = h[threadIdx.x];
   __syncthreads();
@@ -338,10 +338,10 @@ __global__ void __launch_bounds__(256) k_basis_gemm(int n, int mp, int nk, const
 
 __global__ void __launch_bounds__(128) k_rr(z128* S, z128* Q, RrParams p, z128* theta, double* resid, z128* brow,
                                             z128* ywork, RrInfo* info, int use_smem) {
-  __shared__ double s_rot_c[160];
-  __shared__ z128 s_rot_s[160];
-  __shared__ z128 s_vec[160];
-  __shared__ double s_key[160];
+  __shared__ double s_rot_c[264];
+  __shared__ z128 s_rot_s[264];
+  __shared__ z128 s_vec[264];
+  __shared__ double s_key[264];
   __shared__ int s_flag[4];
   __shared__ RrOut s_out;
   extern __shared__ unsigned char rr_dyn[];
@@ -375,10 +375,10 @@ __global__ void __launch_bounds__(128) k_rr(z128* S, z128* Q, RrParams p, z128* 
 
 // Schur form only (lsa_dense_schur): S (m x m, ld), sorted by `which`.
 __global__ void __launch_bounds__(128) k_schur_only(z128* S, int ld, z128* Q, int m, RrParams p, RrInfo* info) {
-  __shared__ double s_rot_c[160];
-  __shared__ z128 s_rot_s[160];
-  __shared__ z128 s_vec[160];
-  __shared__ double s_key[160];
+  __shared__ double s_rot_c[264];
+  __shared__ z128 s_rot_s[264];
+  __shared__ z128 s_vec[264];
+  __shared__ double s_key[264];
   __shared__ int s_flag[4];
   RrWork w{s_rot_c, s_rot_s, s_vec, s_key, s_flag};
   const int st = rr_schur(S, ld, Q, m, m, 0, threadIdx.x, blockDim.x, w);
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128) k_schur_only(z128* S, int ld, z128* Q, in
 }
 
 void dense_schur_device(lsa_handle_impl& h, int m, z128* dS, int ld, z128* dQ, int which, int transform, z128 sigma) {
-  if (m > 150) throw std::runtime_error("dense Schur kernel supports m <= 150");
+  if (m > 256) throw std::runtime_error("dense Schur kernel supports m <= 256");
   RrParams p{};
   p.m = m; p.ld = ld; p.ldq = m; p.nconv = 0; p.nev = m; p.which = which; p.transform = transform;
   p.sigma = sigma; p.tol = 0; p.last = 1; p.beta_scale = 1.0;
@@ -629,7 +629,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   cudaStream_t st = h.stream;
   const int ncv = std::max(1, std::min(p.ncv, n));
   const int nev = std::max(1, std::min(p.nev, n));
-  if (ncv > 128) throw std::runtime_error("ncv > 128 is not supported by the orthogonalisation kernels");
+  if (ncv > 256) throw std::runtime_error("ncv > 256 is not supported by the orthogonalisation kernels");
   const int ld = ncv + 1;
   const int blocks = cdiv(n, 256);
   z128* V = h.d_V;
@@ -638,10 +638,17 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   z128* Q = h.d_Q;
   const int rows_per_block = std::max(1024, (int)(((long long)n + 591) / 592 + 31) / 32 * 32);
   const int nblk = cdiv(n, rows_per_block);
-  const int ldp = 128;
+  const int ldp = 256;
   z128 sigma = mk(p.sigma_re, p.sigma_im);
   if (p.adjoint) sigma = conj_(sigma);
 
+  {
+    static bool gemm_attr = false;
+    if (!gemm_attr) {
+      LSA_CUDA(cudaFuncSetAttribute(k_basis_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * 33 * (int)sizeof(z128)));
+      gemm_attr = true;
+    }
+  }
   EventTimer t_all(st), t_spmv(st), t_solve(st), t_ortho(st), t_rr(st), t_restart(st);
   const long long launches0 = h.launch_count;
   const size_t e_all = t_all.begin();
@@ -676,10 +683,10 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       const size_t e = t_ortho.begin();
       const int jj = j + 1;  // orthogonalise against columns 0..j
       z128* scol = S + (long long)j * ld;
-      k_dots<<<nblk, 256, 0, st>>>(n, jj, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
+      for (int c0 = 0; c0 < jj; c0 += 128) k_dots<<<nblk, 256, 0, st>>>(n, jj, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
       k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 0);
       k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, nullptr);
-      k_dots<<<nblk, 256, 0, st>>>(n, jj, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
+      for (int c0 = 0; c0 < jj; c0 += 128) k_dots<<<nblk, 256, 0, st>>>(n, jj, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
       k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 1);
       k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart);
       k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V + (long long)(j + 1) * ldv, h.d_npart, blocks, nullptr,
@@ -740,7 +747,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       z128* vnew = V + (long long)keep * ldv;
       k_randn<<<blocks, 256, 0, st>>>(h.d_w, n, p.seed + 7919ULL * (unsigned long long)restarts);
       for (int pass = 0; pass < 2; ++pass) {
-        k_dots<<<nblk, 256, 0, st>>>(n, keep, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
+        for (int c0 = 0; c0 < keep; c0 += 128) k_dots<<<nblk, 256, 0, st>>>(n, keep, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
         k_reduce_h<<<cdiv(keep, 8), 256, 0, st>>>(keep, nblk, h.d_part, ldp, h.d_h, h.d_brow, 0);
         k_update<<<blocks, 256, 0, st>>>(n, keep, V, ldv, h.d_h, h.d_w, pass ? h.d_npart : nullptr);
       }

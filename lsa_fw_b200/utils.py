@@ -382,7 +382,9 @@ class iEpsSolver:  # noqa: N801
     # ------------------------------------------------------------------ helpers
     def _ncv_effective(self) -> int:
         n = self._A.shape[0] if self._A is not None else 1 << 30
-        ncv = self._ncv if self._ncv is not None else max(2 * self._nev, self._nev + 15)
+        # SLEPc's default rule (EPSSetDimensions, ncv = max(2 nev, nev + 15)), capped at the widest basis
+        # the device kernels hold (MAX_NCV = 256); an explicit ncv is passed through and checked there
+        ncv = self._ncv if self._ncv is not None else min(max(2 * self._nev, self._nev + 15), 256)
         return max(1, min(ncv, n))
 
     def _which_effective(self) -> iEpsWhich:

@@ -12,13 +12,12 @@ import json
 import os
 import sys
 
-import numpy as np
 import scipy.io
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import lsa_fw_b200 as L  # noqa: E402
-from bench import TOL, WORKLOADS, build_pencil  # noqa: E402
+from bench import TOL, build_pencil  # noqa: E402
 
 
 def main() -> None:

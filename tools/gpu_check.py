@@ -13,8 +13,8 @@ import time
 import traceback
 
 import numpy as np
-import scipy.sparse as sp
-import scipy.sparse.linalg as spla
+
+
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
