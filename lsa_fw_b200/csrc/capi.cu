@@ -396,8 +396,14 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->use_graphs = value != 0.0;
   } else if (nm == "use_clusters") {
     h->use_clusters = value != 0.0;
+  } else if (nm == "use_stream") {
+    h->use_stream = value != 0.0;
   } else if (nm == "cluster_max_rows") {
     h->cluster_max_rows = (int)value;
+  } else if (nm == "cluster_max_width") {
+    if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+      return fail(h, LSA_ERR_ARG, "cluster_max_width must be 1, 2, 4, 8 or 16");
+    h->cluster_max_width = (int)value;
   } else if (nm == "use_subtrees") {
     h->use_subtrees = value != 0.0;
   } else {
@@ -540,6 +546,8 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   drop_solve_graphs(*h);
   if (const char* e = getenv("LSA_SUBTREES")) h->use_subtrees = atoi(e) != 0;
   if (const char* e = getenv("LSA_CLUSTER_MAX_ROWS")) h->cluster_max_rows = atoi(e);
+  if (const char* e = getenv("LSA_CLUSTER_MAX_WIDTH")) h->cluster_max_width = atoi(e);
+  if (const char* e = getenv("LSA_NO_STREAM")) h->use_stream = atoi(e) == 0;
   if (const char* e = getenv("LSA_NO_CLUSTERS")) {
     if (atoi(e) != 0) h->use_clusters = false;
   }

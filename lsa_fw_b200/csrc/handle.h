@@ -150,7 +150,9 @@ struct lsa_handle_impl {
   };
   std::vector<SolveGraph> solve_graphs;
   bool use_graphs = true;
+  int cluster_max_width = 16;   // CTAs per front in the cluster sweep (16 = non-portable cluster size)
   int cluster_max_rows = 1280;  // fronts taller than this are swept with one grid-wide launch per step (measured optimum)
+  bool use_stream = true;     // single-step levels: bulk-copy/mbarrier streamed kernel (complex factors)
   bool use_clusters = true;
   bool use_subtrees = false;  // sweep the bottom of the tree with the persistent task-based kernel (measured slower)   // sweep multi-step levels with thread-block clusters (one launch per level)
   double coupled_fraction = 0.5;

@@ -291,6 +291,16 @@ __global__ void __launch_bounds__(NW * 32) k_down_off(const Front* __restrict__ 
   }
 }
 
+// L2 prefetch of a contiguous run of factor entries (bulk prefetch: 16-byte aligned address and size; a
+// misaligned first/last real entry is simply left to the demand load).  The factor data never depends on
+// the sweep's dependency chain, so the panel of step s+1 is pulled into L2 while step s is being solved.
+template <class T>
+__device__ __forceinline__ void prefetch_l2(const T* p, int count) {
+  const unsigned long long a0 = ((unsigned long long)p + 15ull) & ~15ull;
+  const unsigned long long a1 = ((unsigned long long)(p + count)) & ~15ull;
+  if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
+}
+
 // ---------------------------------------------------------------------------- fused sweep steps
 //
 // One launch per 128-pivot step: every CTA first applies the explicitly inverted diagonal block to
@@ -324,6 +334,23 @@ __global__ void __launch_bounds__(NT) k_step(const Front* __restrict__ fronts, c
   __shared__ z128 part[CG][SB];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid < len) ys[tid] = in[f.col0 + j0 + tid];
+  // panel of the next step (the next launch) -> L2, same chunk position
+  const int nj0 = UP ? j0 + SB : j0 - SB;
+  if (NT > SB && nj0 >= 0 && nj0 < k && tid >= NT - SB) {
+    const int i = tid - (NT - SB);
+    const int plen = min(SB, k - nj0), pj1 = nj0 + plen;
+    const int pn = UP ? (int)(m - pj1) : nj0;
+    if (blockIdx.x == 0 && i < plen) prefetch_l2(P + nj0 + (long long)(nj0 + i) * m, plen);
+    if (r0 < pn) {
+      const int rows = min(SB, pn - r0), row0 = (UP ? pj1 : 0) + r0;
+      if (!H) {
+        if (i < plen) prefetch_l2(P + row0 + (long long)(nj0 + i) * m, rows);
+      } else if (i < rows) {
+        const int row = row0 + i;
+        prefetch_l2((!UP || row < k) ? P + nj0 + (long long)row * m : Q + nj0 + (long long)(row - k) * k, plen);
+      }
+    }
+  }
   __syncthreads();
   // ---- phase 1: z = Op ys
   if (!H) {
@@ -438,7 +465,28 @@ __global__ void __launch_bounds__(1024) k_sweep_cluster(const Front* __restrict_
   __shared__ z128 part[CG][SB];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nsteps = (k + SB - 1) / SB;
+  // panel of step sp -> L2: the diagonal block (one rank) and this rank's row chunks
+  auto prefetch_step = [&](int sp) {
+    if (sp >= nsteps) return;
+    const int pj0 = (UP ? sp : nsteps - 1 - sp) * SB;
+    const int plen = min(SB, k - pj0), pj1 = pj0 + plen;
+    const int pn = UP ? (int)(m - pj1) : pj0;
+    if (rank == sp % C && tid < plen) prefetch_l2(P + pj0 + (long long)(pj0 + tid) * m, plen);
+    const int q = tid >> 7, i = tid & (SB - 1);   // 8 chunks of 128 segments per pass
+    for (int r0 = (rank + q * C) * SB; r0 < pn; r0 += 8 * C * SB) {
+      const int rows = min(SB, pn - r0);
+      const int row0 = (UP ? pj1 : 0) + r0;
+      if (!H) {
+        if (i < plen) prefetch_l2(P + row0 + (long long)(pj0 + i) * m, rows);
+      } else if (i < rows) {
+        const int row = row0 + i;
+        prefetch_l2((!UP || row < k) ? P + pj0 + (long long)row * m : Q + pj0 + (long long)(row - k) * k, plen);
+      }
+    }
+  };
+  prefetch_step(0);
   for (int s = 0; s < nsteps; ++s) {
+    prefetch_step(s + 1);
     const int j0 = (UP ? s : nsteps - 1 - s) * SB;
     const int len = min(SB, k - j0), j1 = j0 + len;
     const int nrows = UP ? (int)(m - j1) : j0;
@@ -551,7 +599,24 @@ static void launch_sweep_cluster(cudaStream_t st, int cnt, const Front* fronts, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (C > 8) {
+    static bool allowed = false;   // per instantiation
+    if (!allowed) {
+      LSA_CUDA(cudaFuncSetAttribute(k_sweep_cluster<T, H, UP, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      allowed = true;
+    }
+  }
   LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb));
+}
+
+// Cluster width of a level: as many SMs per front as the level leaves free (one 1024-thread CTA per SM),
+// but no more than the front has 128-row chunks to hand out.
+static int cluster_width(int cnt, int max_rows, int num_sms, int max_width) {
+  int c = 1;
+  while (c * 2 <= max_width && cnt * c * 2 <= num_sms) c *= 2;
+  const int chunks = std::max(1, cdiv(max_rows, SB));
+  while (c > 1 && c / 2 >= chunks) c /= 2;
+  return c;
 }
 
 template <class T, bool H, bool UP>
@@ -561,8 +626,264 @@ static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fron
     case 1: launch_sweep_cluster<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
     case 2: launch_sweep_cluster<T, H, UP, 2>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
     case 4: launch_sweep_cluster<T, H, UP, 4>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-    default: launch_sweep_cluster<T, H, UP, 8>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+    case 8: launch_sweep_cluster<T, H, UP, 8>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+    default: launch_sweep_cluster<T, H, UP, 16>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
   }
+}
+
+// ------------------------------------------------- streamed sweep of the single-step levels (bulk copies)
+//
+// Levels whose fronts have at most 128 pivots hold most of the factor bytes but little work per front;
+// with plain loads every front is a chain of four or five dependent memory round trips and the SMs
+// idle.  Here the factor entries are STREAMED: each CTA owns a ring of shared-memory stages, a producer
+// warp walks the tile list of the CTA's fronts (persistent grid, round robin) and fills the ring with
+// `cp.async.bulk` copies that complete on mbarriers, running ahead of the consumers across front
+// boundaries; four consumer warps apply each tile to the right-hand side out of shared memory.
+// Tiles are 128 rows x 8 columns of a column-major block (8 bulk copies of <= 2 KB, triangular blocks
+// only load the half that is used).  Per front two block operations run back to back:
+//
+//   up,N:   z = y + strict_lower(D) y        ;  cb -= L21 z          (row-wise, tiles row-block major)
+//   up,H:   z = upper(D)^H y                 ;  cb -= Q^H z          (column-wise, tiles column-chunk major)
+//   down,N: y = z_in - Q anc                 ;  x = upper(D) y
+//   down,H: y = z_in - L21^H anc             ;  x = y + strict_lower(D)^H y
+//
+// D = the explicitly inverted k x k pivot block (unit lower L^-1 below, U^-1 on and above the diagonal),
+// L21 = P[k:m, 0:k], Q = U12 (k x r).  Complex factors only (16-byte entries: every segment is aligned).
+namespace stream {
+constexpr int TR = 128;             // tile rows
+constexpr int TC = 8;               // tile columns
+constexpr int LDT = TR + 1;         // shared-memory column stride: odd, column-wise reads are conflict free
+constexpr int STAGES = 3;
+constexpr int TILE = TC * LDT;      // entries per stage
+constexpr int NCONS = 128;          // consumer threads; warp 4 is the producer
+constexpr int NTHREADS = NCONS + 32;
+constexpr int STREAM_MAX_SMEM = 160 * 1024;   // ring + ancestor values; levels that need more use the plain kernels
+enum Mask { NONE = 0, STRICT_LOWER = 1, UPPER = 2 };
+struct Block {
+  const z128* src;   // entry (0, 0)
+  long long ld;
+  int R, C;          // rows, columns
+  int mask;
+};
+__device__ __forceinline__ unsigned sa(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sa(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sa(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sa(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(sa(b)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(z128* dst, const z128* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa(dst)),
+               "l"(src), "r"(bytes), "r"(sa(b))
+               : "memory");
+}
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
+// rows [lo, hi) of column c that a tile covering rows [r0, r1) has to hold
+__device__ __forceinline__ void seg(int mask, int c, int r0, int r1, int& lo, int& hi) {
+  lo = r0;
+  hi = r1;
+  if (mask == STRICT_LOWER) lo = max(r0, c + 1);
+  if (mask == UPPER) hi = min(r1, c + 1);
+  if (hi < lo) hi = lo;
+}
+template <bool H, bool UP>
+__device__ __forceinline__ void blocks_of(const Front& f, const z128* fac, Block& a, Block& b) {
+  const long long m = (long long)f.k + f.r;
+  const z128* P = fac + f.p_off;
+  const z128* Q = fac + f.q_off;
+  const Block d_lo{P, m, f.k, f.k, STRICT_LOWER}, d_up{P, m, f.k, f.k, UPPER};
+  const Block l21{P + f.k, m, f.r, f.k, NONE}, u12{Q, (long long)f.k, f.k, f.r, NONE};
+  if (UP) {
+    a = H ? d_up : d_lo;
+    b = H ? u12 : l21;
+  } else {
+    a = H ? l21 : u12;
+    b = H ? d_lo : d_up;
+  }
+}
+}  // namespace stream
+
+template <bool H, bool UP>
+__global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* __restrict__ fronts,
+                                                                   const int* __restrict__ lvl_front, int first, int cnt,
+                                                                   const int* __restrict__ st_idx,
+                                                                   const z128* __restrict__ fac, const z128* vin,
+                                                                   z128* vout, z128* cb, const z128* anc) {
+  using namespace stream;
+  extern __shared__ __align__(16) unsigned char stream_smem[];
+  z128* stages = reinterpret_cast<z128*>(stream_smem);
+  z128* vbuf = stages + STAGES * TILE;   // ancestor values (down sweep), length = max r of the level
+  __shared__ z128 ys[TR];
+  __shared__ z128 zs[TR];
+  __shared__ z128 part[2][4][TC];
+  __shared__ __align__(8) unsigned long long full[STAGES], empty[STAGES];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCONS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned it = 0;   // tiles issued (producer) / consumed (consumers): same enumeration on both sides
+  if (wid == NCONS / 32) {
+    // ------------------------------------------------------------------ producer warp
+    for (int fi = blockIdx.x; fi < cnt; fi += gridDim.x) {
+      const Front f = fronts[lvl_front[first + fi]];
+      Block blk[2];
+      blocks_of<H, UP>(f, fac, blk[0], blk[1]);
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const Block b = blk[o];
+        const int nrb = (b.R + TR - 1) / TR, ncc = (b.C + TC - 1) / TC;
+        const int nt = nrb * ncc;
+        for (int t = 0; t < nt; ++t, ++it) {
+          const int rb = H ? t % nrb : t / ncc, cc = H ? t / nrb : t % ncc;
+          const int r0 = rb * TR, r1 = min(b.R, r0 + TR);
+          const int c = cc * TC + lane;
+          int lo = 0, hi = 0;
+          if (lane < TC && c < b.C) seg(b.mask, c, r0, r1, lo, hi);
+          unsigned bytes = (unsigned)(hi - lo) * (unsigned)sizeof(z128);
+          unsigned total = bytes;
+          for (int o2 = 4; o2 > 0; o2 >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o2);
+          const unsigned s = it % STAGES, use = it / STAGES;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+          if (lane == 0) mbar_expect_tx(&full[s], total);
+          __syncwarp();
+          if (bytes) bulk_g2s(stages + s * TILE + lane * LDT + (lo - r0), b.src + lo + (long long)c * b.ld, bytes, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- consumer warps
+  for (int fi = blockIdx.x; fi < cnt; fi += gridDim.x) {
+    const Front f = fronts[lvl_front[first + fi]];
+    const int k = f.k, r = f.r;
+    Block blk[2];
+    blocks_of<H, UP>(f, fac, blk[0], blk[1]);
+    if (tid < k) ys[tid] = vin[f.col0 + tid];
+    if (!UP) {
+      const int* idx = st_idx + f.st0;
+      for (int j = tid; j < r; j += NCONS) vbuf[j] = anc[idx[j]];
+    }
+    cons_sync();
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const Block b = blk[o];
+      // the vector this block is applied to: indexed by column (N) / by row (H)
+      const z128* v = UP ? (o == 0 ? ys : zs) : (o == 0 ? vbuf : ys);
+      const int nrb = (b.R + TR - 1) / TR, ncc = (b.C + TC - 1) / TC;
+      const int nt = nrb * ncc;
+      z128 acc = mk(0, 0);
+      for (int t = 0; t < nt; ++t, ++it) {
+        const int rb = H ? t % nrb : t / ncc, cc = H ? t / nrb : t % ncc;
+        const int r0 = rb * TR, c0 = cc * TC;
+        const unsigned s = it % STAGES, use = it / STAGES;
+        mbar_wait(&full[s], use & 1);
+        const z128* tile = stages + s * TILE;
+        if (!H) {
+          // thread = row, all columns of the tile
+          const int row = r0 + tid;
+          if (row < b.R) {
+#pragma unroll
+            for (int j = 0; j < TC; ++j) {
+              const int c = c0 + j;
+              const bool ok = c < b.C && (b.mask == NONE || (b.mask == STRICT_LOWER ? row > c : row <= c));
+              if (ok) acc += tile[tid + j * LDT] * v[c];
+            }
+          }
+        } else {
+          // thread = (column, group of 8 rows)
+          const int col = tid & (TC - 1), rg = tid >> 3;
+          const int c = c0 + col;
+          if (c < b.C) {
+#pragma unroll
+            for (int i = 0; i < TR / (NCONS / TC); ++i) {
+              const int rl = rg * (TR / (NCONS / TC)) + i, row = r0 + rl;
+              const bool ok = row < b.R && (b.mask == NONE || (b.mask == STRICT_LOWER ? row > c : row <= c));
+              if (ok) acc += conj_(tile[rl + col * LDT]) * v[row];
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        // ---- end of an output group: row block (N) / column chunk (H)
+        const bool last = H ? (rb == nrb - 1) : (cc == ncc - 1);
+        if (!last) continue;
+        z128 total = acc;
+        int out_i = r0 + tid;   // N: this thread's row
+        bool have = !H && out_i < b.R;
+        if (H) {
+          for (int o2 = 8; o2 < 32; o2 <<= 1) {
+            total.x += __shfl_xor_sync(0xffffffffu, total.x, o2);
+            total.y += __shfl_xor_sync(0xffffffffu, total.y, o2);
+          }
+          const int p = cc & 1;
+          if (lane < TC) part[p][wid][lane] = total;
+          cons_sync();
+          have = tid < TC && c0 + tid < b.C;
+          out_i = c0 + tid;
+          if (have) total = part[p][0][tid] + part[p][1][tid] + part[p][2][tid] + part[p][3][tid];
+        }
+        if (have) {
+          if (UP) {
+            if (o == 0) {
+              const z128 z = H ? total : ys[out_i] + total;
+              zs[out_i] = z;
+              vout[f.col0 + out_i] = z;
+            } else {
+              cb[f.st0 + out_i] -= total;
+            }
+          } else {
+            if (o == 0) ys[out_i] -= total;
+            else vout[f.col0 + out_i] = H ? ys[out_i] + total : total;
+          }
+        }
+        acc = mk(0, 0);
+      }
+      cons_sync();   // the vector produced by this block is complete / ys, vbuf may be overwritten
+    }
+  }
+}
+
+template <bool H, bool UP>
+static void launch_front_stream(lsa_handle_impl& h, cudaStream_t st, int cnt, const int* lvl_front, int first, int maxr,
+                                const z128* fac, const z128* vin, z128* vout, z128* cb, const z128* anc) {
+  using namespace stream;
+  const size_t smem = sizeof(z128) * ((size_t)STAGES * TILE + (size_t)(UP ? 0 : maxr));
+  static bool attr_done = false;   // per instantiation
+  static int occ_cache[2] = {0, 0};
+  if (!attr_done) {
+    LSA_CUDA(cudaFuncSetAttribute(k_front_stream<H, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_MAX_SMEM));
+    attr_done = true;
+  }
+  int occ = 0;
+  if (occ_cache[0] == (int)smem) occ = occ_cache[1];
+  else {
+    LSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_front_stream<H, UP>, NTHREADS, smem));
+    occ_cache[0] = (int)smem;
+    occ_cache[1] = occ;
+  }
+  const int grid = std::max(1, std::min(cnt, std::max(1, occ) * h.num_sms));
+  k_front_stream<H, UP><<<grid, NTHREADS, smem, st>>>(h.d_fronts, lvl_front, first, cnt, h.d_st_idx, fac, vin, vout, cb, anc);
+  LSA_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------- bottom of the tree (persistent, task based)
@@ -867,7 +1188,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       const int maxk = sym.fronts[lvl_front[first]].k;
       int max_m = 0;
       for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
-      const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
+      const int csize = cluster_width(cnt, max_m, h.num_sms, h.cluster_max_width);
       // tall fronts need the whole GPU per step; up to `cluster_max_rows` rows a cluster of <= 8 SMs keeps up
       // and saves the launches (inside a CUDA graph the two are within 3 % of each other, profiles/r1f_*)
       if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
@@ -875,6 +1196,14 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         tr.mark("up_cluster", d, csize, csize * cnt, 1);
         launches++;
         continue;
+      }
+      if constexpr (scalar_traits<T>::is_complex) {
+        if (maxk <= SB && h.use_stream) {
+          launch_front_stream<H, true>(h, st, cnt, d_lvl_front, first, 0, fac, y, z, cb, nullptr);
+          tr.mark("up_stream", d, 0, cnt, 1);
+          launches++;
+          continue;
+        }
       }
       for (int j0 = 0; j0 < maxk; j0 += SB) {
         int act = 0, max_rows = 0;
@@ -901,7 +1230,17 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       const int maxk = sym.fronts[lvl_front[first]].k;
       int maxr = 0;
       for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[lvl_front[q]].r);
-      if (maxr > 0) {
+      bool streamed = false;
+      if constexpr (scalar_traits<T>::is_complex) {
+        if (maxk <= SB && h.use_stream &&
+            sizeof(z128) * ((size_t)stream::STAGES * stream::TILE + (size_t)maxr) <= (size_t)stream::STREAM_MAX_SMEM) {
+          launch_front_stream<H, false>(h, st, cnt, d_lvl_front, first, maxr, fac, z, y, cb, H ? x : y);
+          tr.mark("down_stream", d, 0, cnt, 1);
+          launches++;
+          streamed = true;
+        }
+      }
+      if (!streamed && maxr > 0) {
         if (maxr > 512) k_down_off<T, H, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
         else k_down_off<T, H, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
         LSA_LAUNCH_CHECK();
@@ -910,10 +1249,11 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       }
       int max_mk = 0;
       for (int q = first; q < first + cnt; ++q) max_mk = std::max(max_mk, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
-      if (maxk > SB && max_mk <= h.cluster_max_rows && h.use_clusters) {
+      if (streamed) {
+      } else if (maxk > SB && max_mk <= h.cluster_max_rows && h.use_clusters) {
         int max_m = 0;
         for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k);
-        const int csize = max_m <= 640 ? 1 : max_m <= 1280 ? 2 : max_m <= 2560 ? 4 : 8;
+        const int csize = cluster_width(cnt, max_m, h.num_sms, h.cluster_max_width);
         sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
         tr.mark("down_cluster", d, csize, csize * cnt, 1);
         launches++;

@@ -385,6 +385,9 @@ class iEpsSolver:  # noqa: N801
         # SLEPc's default rule (EPSSetDimensions, ncv = max(2 nev, nev + 15)), capped at the widest basis
         # the device kernels hold (MAX_NCV = 256); an explicit ncv is passed through and checked there
         ncv = self._ncv if self._ncv is not None else min(max(2 * self._nev, self._nev + 15), 256)
+        if self._ncv is not None and self._ncv < self._nev:
+            # EPSSetDimensions_Default: "The value of ncv must be at least nev"
+            raise ValueError(f"The value of ncv ({self._ncv}) must be at least nev ({self._nev})")
         return max(1, min(ncv, n))
 
     def _which_effective(self) -> iEpsWhich:

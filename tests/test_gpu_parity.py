@@ -112,17 +112,17 @@ def test_membrane_table_of_the_reference(golden):
 
 
 def test_wide_subspace_hundred_modes():
-    """nev = 100 with the default ncv = 2 nev = 200: the orthogonalisation, Rayleigh-Ritz and restart kernels
+    """nev = 100 with ncv = 2 nev = 200 (SLEPc's default rule): the orthogonalisation, Rayleigh-Ritz and restart kernels
     run past their 128-column chunk (dots in two column groups, RR out of shared memory)."""
     pm = pencils.membrane_pencil(24, 24, 1.0, 0.83)
     sigma = 1000.0   # 100 nearest modes span 180 .. 1820, clear of the spurious Dirichlet eigenvalue 1
-    cfg = L.EigensolverConfig(num_eig=100, problem_type=L.iEpsProblemType.GHEP, atol=1e-11, max_it=300)
+    cfg = L.EigensolverConfig(num_eig=100, problem_type=L.iEpsProblemType.GHEP, atol=1e-11, max_it=300, ncv=200)
     es = L.EigenSolver(L.iPETScMatrix(pm.A), L.iPETScMatrix(pm.M), cfg, check_hermitian=False)
     es.solver.set_st_type(L.iSTType.SINVERT)
     es.solver.set_target(sigma)
     pairs = es.solve()
     assert len(pairs) >= 100
-    assert es.solver.get_dimensions()[1] == 200
+    assert es.solver.raw.getDimensions()[1] == 200
     lam = np.array([v for v, _ in pairs][:100])
     ref = O.shift_invert_arpack(pm.A, pm.M, sigma, 104, tol=1e-12).eigenvalues
     ref = ref[np.argsort(np.abs(ref - sigma))][:100]

@@ -271,6 +271,23 @@ def test_set_st_pc_type_round_trip(pc_type):
     assert s.raw.getST().getKSP().getPC().getType() == pc_type.name.lower()       # test_eigen.py:307-322
 
 
+def test_dimension_rules_follow_slepc():
+    big = L.iPETScMatrix.from_matrix(np.diag(np.arange(1.0, 601.0)))
+    s = L.iEpsSolver(A=big)
+    s.set_dimensions(number_eigenpairs=5)
+    assert s.raw.getDimensions()[1] == 20            # max(2 nev, nev + 15)
+    s.set_dimensions(number_eigenpairs=100)
+    assert s.raw.getDimensions()[1] == 200
+    s.set_dimensions(number_eigenpairs=200)
+    assert s.raw.getDimensions()[1] == 256           # widest basis of the device kernels
+    s.set_dimensions(number_eigenpairs=100, subspace_dimension=80)
+    with pytest.raises(ValueError, match="must be at least nev"):
+        s.raw.getDimensions()
+    small = L.iEpsSolver(A=L.iPETScMatrix.from_matrix(np.diag([1.0, 1.5, -42.0])))
+    small.set_dimensions(number_eigenpairs=3, subspace_dimension=80)
+    assert small.raw.getDimensions()[1] == 3         # never wider than the problem
+
+
 def test_unsupported_combinations_raise_not_implemented():
     A = L.iPETScMatrix.from_matrix(np.diag([1.0, 1.5, -42.0]))
     s = L.iEpsSolver(A)
