@@ -291,14 +291,15 @@ __global__ void __launch_bounds__(NW * 32) k_down_off(const Front* __restrict__ 
   }
 }
 
-// L2 prefetch of a contiguous run of factor entries (bulk prefetch: 16-byte aligned address and size; a
-// misaligned first/last real entry is simply left to the demand load).  The factor data never depends on
-// the sweep's dependency chain, so the panel of step s+1 is pulled into L2 while step s is being solved.
+// L2 prefetch of a contiguous run of factor entries, one `prefetch.global.L2` per 128-byte line (plain LSU
+// instructions: the bulk form `cp.async.bulk.prefetch.L2` runs on the uniform datapath, one lane at a time, and
+// cost ~0.1 us per segment when measured here).  The factor data never depends on the sweep's dependency chain,
+// so the panel of step s+1 is pulled into L2 while step s is being solved.
 template <class T>
 __device__ __forceinline__ void prefetch_l2(const T* p, int count) {
-  const unsigned long long a0 = ((unsigned long long)p + 15ull) & ~15ull;
-  const unsigned long long a1 = ((unsigned long long)(p + count)) & ~15ull;
-  if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
+  const unsigned long long a1 = (unsigned long long)(p + count);
+  for (unsigned long long a = (unsigned long long)p & ~127ull; a < a1; a += 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a) : "memory");
 }
 
 // ---------------------------------------------------------------------------- fused sweep steps
@@ -631,41 +632,72 @@ static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fron
   }
 }
 
-// ------------------------------------------------- streamed sweep of the single-step levels (bulk copies)
+// ------------------------------------------------------------ streamed sweep (bulk copies + mbarrier ring)
 //
-// Levels whose fronts have at most 128 pivots hold most of the factor bytes but little work per front;
-// with plain loads every front is a chain of four or five dependent memory round trips and the SMs
-// idle.  Here the factor entries are STREAMED: each CTA owns a ring of shared-memory stages, a producer
-// warp walks the tile list of the CTA's fronts (persistent grid, round robin) and fills the ring with
-// `cp.async.bulk` copies that complete on mbarriers, running ahead of the consumers across front
-// boundaries; four consumer warps apply each tile to the right-hand side out of shared memory.
-// Tiles are 128 rows x 8 columns of a column-major block (8 bulk copies of <= 2 KB, triangular blocks
-// only load the half that is used).  Per front two block operations run back to back:
+// Levels that hold many fronts are swept with ONE persistent launch per level and direction in which the
+// factor entries are STREAMED through shared memory: every CTA owns a ring of stages, a producer warp walks
+// the tile list of the CTA's fronts (round robin over the level) and fills the ring with `cp.async.bulk`
+// copies completing on mbarriers, running ahead of the consumers across operation and front boundaries
+// (the factor never depends on the right-hand side); four consumer warps apply each tile out of shared
+// memory.  With plain loads every front was a chain of dependent memory round trips and the SMs idled.
 //
-//   up,N:   z = y + strict_lower(D) y        ;  cb -= L21 z          (row-wise, tiles row-block major)
-//   up,H:   z = upper(D)^H y                 ;  cb -= Q^H z          (column-wise, tiles column-chunk major)
-//   down,N: y = z_in - Q anc                 ;  x = upper(D) y
-//   down,H: y = z_in - L21^H anc             ;  x = y + strict_lower(D)^H y
+// A front is a short list of block operations on its column-major storage (D_s = explicitly inverted
+// 128 x 128 diagonal block s: unit lower L^-1 below, U^-1 on/above the diagonal; j0 = 128 s):
 //
-// D = the explicitly inverted k x k pivot block (unit lower L^-1 below, U^-1 on and above the diagonal),
-// L21 = P[k:m, 0:k], Q = U12 (k x r).  Complex factors only (16-byte entries: every segment is aligned).
+//   up,N   per step s:  z_s = y_s + strict_lower(D_s) y_s   ;  rows below:  y / cb -= P[j1:m, j0:j1] z_s
+//   up,H   per step s:  z_s = upper(D_s)^H y_s              ;  y -= P[j0:j1, j1:k]^H z_s ; cb -= Q[j0:j1, :]^H z_s
+//   down,N y -= Q anc ; per step s (last first):  x_s = upper(D_s) y_s        ;  y -= P[0:j0, j0:j1] x_s
+//   down,H y -= P[k:m, :]^H anc ; per step s:     x_s = y_s + strict_lower(D_s)^H y_s ;  y -= P[j0:j1, 0:j0]^H x_s
+//
+// N operations reduce along rows of the block (thread = row), H operations along columns (thread = column,
+// conjugated entries).  Tiles hold up to 128 rows; narrower blocks get proportionally more columns per tile
+// (8 ... 64) so that a tile stays ~16 KB, and a block that is contiguous in memory (Q with few pivots) is
+// fetched with a single bulk copy per tile.  Complex factors only (16-byte entries keep every copy aligned).
 namespace stream {
-constexpr int TR = 128;             // tile rows
-constexpr int TC = 8;               // tile columns
-constexpr int LDT = TR + 1;         // shared-memory column stride: odd, column-wise reads are conflict free
-constexpr int STAGES = 3;
-constexpr int TILE = TC * LDT;      // entries per stage
+constexpr int TR = 128;             // max tile rows
+constexpr int MAX_STAGES = 12;
+constexpr int TILE = 1088;          // entries per stage: 64 columns x (16 + 1) rows is the largest layout
 constexpr int NCONS = 128;          // consumer threads; warp 4 is the producer
 constexpr int NTHREADS = NCONS + 32;
-constexpr int STREAM_MAX_SMEM = 160 * 1024;   // ring + ancestor values; levels that need more use the plain kernels
+constexpr int STREAM_MAX_SMEM = 200 * 1024;
 enum Mask { NONE = 0, STRICT_LOWER = 1, UPPER = 2 };
-struct Block {
-  const z128* src;   // entry (0, 0)
+enum Emit { Z_UNIT = 0, Z_PLAIN = 1, SUB_SPLIT = 2, SUB_Y = 3 };
+struct Op {
+  const z128* src;   // entry (0, 0) of the block
   long long ld;
   int R, C;          // rows, columns
-  int mask;
+  int mask;          // triangular part that is used (block-local coordinates)
+  int vsel, voff;    // vector the block is applied to: 0 = ys, 1 = zs, 2 = vbuf; offset
+  int emit, out0;    // what happens to the results; offset of result 0 in the front's pivot numbering
 };
 __device__ __forceinline__ unsigned sa(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+struct Geo {
+  int rp_log2, tca_log2, tca, ldt, nrb, ncc, contig;
+};
+// flags: bit 0 = narrow blocks get wider tiles, bit 1 = single-copy tiles for contiguous blocks,
+// bit 2 = the producer copies with 16-byte cp.async (LDGSTS) instead of bulk copies
+__device__ __forceinline__ Geo geometry(const Op& b, bool hmode, int flags) {
+  Geo g;
+  const int rb = min(b.R, TR);
+  g.rp_log2 = !(flags & 1) ? 7 : rb <= 16 ? 4 : rb <= 32 ? 5 : rb <= 64 ? 6 : 7;
+  g.tca_log2 = 10 - g.rp_log2;
+  g.tca = 1 << g.tca_log2;
+  g.nrb = (b.R + TR - 1) / TR;
+  g.ncc = (b.C + g.tca - 1) >> g.tca_log2;
+  // whole columns back to back in memory: one copy per tile (row stride = R; column-wise reads need it odd)
+  g.contig = (flags & 2) && b.mask == NONE && b.ld == (long long)b.R && g.nrb == 1 && (!hmode || (b.R & 1));
+  g.ldt = g.contig ? b.R : (1 << g.rp_log2) + 1;
+  return g;
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sa(b)), "r"(count) : "memory");
 }
@@ -693,7 +725,7 @@ __device__ __forceinline__ void bulk_g2s(z128* dst, const z128* src, unsigned by
                : "memory");
 }
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
-// rows [lo, hi) of column c that a tile covering rows [r0, r1) has to hold
+// rows [lo, hi) of block column c that a tile covering rows [r0, r1) has to hold
 __device__ __forceinline__ void seg(int mask, int c, int r0, int r1, int& lo, int& hi) {
   lo = r0;
   hi = r1;
@@ -701,20 +733,53 @@ __device__ __forceinline__ void seg(int mask, int c, int r0, int r1, int& lo, in
   if (mask == UPPER) hi = min(r1, c + 1);
   if (hi < lo) hi = lo;
 }
+__device__ __forceinline__ bool keep(int mask, int row, int c) {
+  return mask == NONE || (mask == STRICT_LOWER ? row > c : row <= c);
+}
 template <bool H, bool UP>
-__device__ __forceinline__ void blocks_of(const Front& f, const z128* fac, Block& a, Block& b) {
-  const long long m = (long long)f.k + f.r;
+__device__ __forceinline__ int op_count(const Front& f) {
+  const int S = (f.k + SB - 1) / SB;
+  return UP ? (H ? 3 * S : 2 * S) : 1 + 2 * S;
+}
+// operation i of a front (same enumeration in the producer and the consumers)
+template <bool H, bool UP>
+__device__ __forceinline__ Op get_op(const Front& f, const z128* fac, int i) {
+  const int k = f.k, r = f.r;
+  const long long m = (long long)k + r;
   const z128* P = fac + f.p_off;
   const z128* Q = fac + f.q_off;
-  const Block d_lo{P, m, f.k, f.k, STRICT_LOWER}, d_up{P, m, f.k, f.k, UPPER};
-  const Block l21{P + f.k, m, f.r, f.k, NONE}, u12{Q, (long long)f.k, f.k, f.r, NONE};
+  const int S = (k + SB - 1) / SB;
+  Op o;
   if (UP) {
-    a = H ? d_up : d_lo;
-    b = H ? u12 : l21;
+    const int per = H ? 3 : 2;
+    const int s = i / per, kind = i % per;
+    const int j0 = s * SB, len = min(SB, k - j0), j1 = j0 + len;
+    if (kind == 0) {
+      o = Op{P + j0 + (long long)j0 * m, m, len, len, H ? UPPER : STRICT_LOWER, 0, j0, H ? Z_PLAIN : Z_UNIT, j0};
+    } else if (!H) {
+      o = Op{P + j1 + (long long)j0 * m, m, (int)(m - j1), len, NONE, 1, j0, SUB_SPLIT, j1};
+    } else if (kind == 1) {
+      o = Op{P + j0 + (long long)j1 * m, m, len, k - j1, NONE, 1, j0, SUB_SPLIT, j1};
+    } else {
+      o = Op{Q + j0, (long long)k, len, r, NONE, 1, j0, SUB_SPLIT, k};
+    }
   } else {
-    a = H ? l21 : u12;
-    b = H ? d_lo : d_up;
+    if (i == 0) {
+      if (!H) o = Op{Q, (long long)k, k, r, NONE, 2, 0, SUB_Y, 0};
+      else o = Op{P + k, m, r, k, NONE, 2, 0, SUB_Y, 0};
+    } else {
+      const int s = S - 1 - (i - 1) / 2, kind = (i - 1) % 2;
+      const int j0 = s * SB, len = min(SB, k - j0);
+      if (kind == 0) {
+        o = Op{P + j0 + (long long)j0 * m, m, len, len, H ? STRICT_LOWER : UPPER, 0, j0, H ? Z_UNIT : Z_PLAIN, j0};
+      } else if (!H) {
+        o = Op{P + (long long)j0 * m, m, j0, len, NONE, 1, j0, SUB_Y, 0};
+      } else {
+        o = Op{P + j0, m, len, j0, NONE, 1, j0, SUB_Y, 0};
+      }
+    }
   }
+  return o;
 }
 }  // namespace stream
 
@@ -723,151 +788,248 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
                                                                    const int* __restrict__ lvl_front, int first, int cnt,
                                                                    const int* __restrict__ st_idx,
                                                                    const z128* __restrict__ fac, const z128* vin,
-                                                                   z128* vout, z128* cb, const z128* anc) {
+                                                                   z128* vout, z128* cb, const z128* anc, int kmax, int rmax,
+                                                                   int nstages, int flags) {
   using namespace stream;
   extern __shared__ __align__(16) unsigned char stream_smem[];
+  // dynamic shared memory: ring | ys x 3 | zs | vb x 2 | idx x 3 (down sweep)
   z128* stages = reinterpret_cast<z128*>(stream_smem);
-  z128* vbuf = stages + STAGES * TILE;   // ancestor values (down sweep), length = max r of the level
-  __shared__ z128 ys[TR];
-  __shared__ z128 zs[TR];
-  __shared__ z128 part[2][4][TC];
-  __shared__ __align__(8) unsigned long long full[STAGES], empty[STAGES];
+  z128* ysb = stages + (size_t)nstages * TILE;   // pivot-row values of fronts n, n+1, n+2            [3][kmax]
+  z128* zs = ysb + 3 * kmax;                     // solved values of the current front                [kmax]
+  z128* vbb = zs + kmax;                         // ancestor values (down) / old cb values (up)        [2][rmax]
+  int* idxb = reinterpret_cast<int*>(vbb + 2 * rmax);   // ancestor row indices (down)                 [3][rmax]
+  __shared__ z128 part[2][NCONS];
+  __shared__ __align__(16) Front s_hdr[5];
+  __shared__ int s_fidx[5];
+  __shared__ __align__(8) unsigned long long full[MAX_STAGES], empty[MAX_STAGES];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full[s], (flags & 4) ? 32 : 1);
       mbar_init(&empty[s], NCONS / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  unsigned it = 0;   // tiles issued (producer) / consumed (consumers): same enumeration on both sides
+  const int nmine = blockIdx.x < cnt ? (cnt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // fronts of this CTA
   if (wid == NCONS / 32) {
     // ------------------------------------------------------------------ producer warp
-    for (int fi = blockIdx.x; fi < cnt; fi += gridDim.x) {
-      const Front f = fronts[lvl_front[first + fi]];
-      Block blk[2];
-      blocks_of<H, UP>(f, fac, blk[0], blk[1]);
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        const Block b = blk[o];
-        const int nrb = (b.R + TR - 1) / TR, ncc = (b.C + TC - 1) / TC;
-        const int nt = nrb * ncc;
-        for (int t = 0; t < nt; ++t, ++it) {
-          const int rb = H ? t % nrb : t / ncc, cc = H ? t / nrb : t % ncc;
+    unsigned s = 0, use = 0;   // ring position
+    Front fn = nmine > 0 ? fronts[lvl_front[first + blockIdx.x]] : Front{};
+    for (int n = 0; n < nmine; ++n) {
+      const Front f = fn;
+      if (n + 1 < nmine) fn = fronts[lvl_front[first + blockIdx.x + (n + 1) * gridDim.x]];   // in flight during this front
+      const int nops = op_count<H, UP>(f);
+      for (int oi = 0; oi < nops; ++oi) {
+        const Op b = get_op<H, UP>(f, fac, oi);
+        const Geo g = geometry(b, H, flags);
+        const int nt = g.nrb * g.ncc;
+        int rb = 0, cc = 0;
+        for (int t = 0; t < nt; ++t) {
           const int r0 = rb * TR, r1 = min(b.R, r0 + TR);
-          const int c = cc * TC + lane;
-          int lo = 0, hi = 0;
-          if (lane < TC && c < b.C) seg(b.mask, c, r0, r1, lo, hi);
-          unsigned bytes = (unsigned)(hi - lo) * (unsigned)sizeof(z128);
-          unsigned total = bytes;
-          for (int o2 = 4; o2 > 0; o2 >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o2);
-          const unsigned s = it % STAGES, use = it / STAGES;
+          const int c0 = cc * g.tca, nc = min(g.tca, b.C - c0);
+          z128* dst = stages + (size_t)s * TILE;
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-          if (lane == 0) mbar_expect_tx(&full[s], total);
-          __syncwarp();
-          if (bytes) bulk_g2s(stages + s * TILE + lane * LDT + (lo - r0), b.src + lo + (long long)c * b.ld, bytes, &full[s]);
+          if (flags & 4) {
+            // LDGSTS path: the warp copies the tile in 16-byte pieces (512 B per instruction, coalesced along
+            // the rows of a column) and every lane posts an arrive-on-completion to the stage's barrier
+            if (g.contig) {
+              const int total = nc * b.R;
+              const z128* sp = b.src + (long long)c0 * b.ld;
+              for (int e = lane; e < total; e += 32) cp_async16_cg(dst + e, sp + e);
+            } else {
+              for (int j = 0; j < nc; ++j) {
+                int lo, hi;
+                seg(b.mask, c0 + j, r0, r1, lo, hi);
+                const z128* sp = b.src + (long long)(c0 + j) * b.ld;
+                z128* dp = dst + j * g.ldt - r0;
+                for (int row = lo + lane; row < hi; row += 32) cp_async16_cg(dp + row, sp + row);
+              }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sa(&full[s])) : "memory");
+          } else if (g.contig) {
+            if (lane == 0) {
+              const unsigned bytes = (unsigned)(nc * b.R) * (unsigned)sizeof(z128);
+              mbar_expect_tx(&full[s], bytes);
+              bulk_g2s(dst, b.src + (long long)c0 * b.ld, bytes, &full[s]);
+            }
+          } else {
+            int lo[2] = {0, 0}, hi[2] = {0, 0};
+            unsigned total = 0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int j = lane + 32 * q;
+              if (j < nc) seg(b.mask, c0 + j, r0, r1, lo[q], hi[q]);
+              total += (unsigned)(hi[q] - lo[q]) * (unsigned)sizeof(z128);
+            }
+            for (int o2 = 16; o2 > 0; o2 >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o2);
+            if (lane == 0) mbar_expect_tx(&full[s], total);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int j = lane + 32 * q;
+              if (hi[q] > lo[q])
+                bulk_g2s(dst + j * g.ldt + (lo[q] - r0), b.src + lo[q] + (long long)(c0 + j) * b.ld,
+                         (unsigned)(hi[q] - lo[q]) * (unsigned)sizeof(z128), &full[s]);
+            }
+          }
+          if (++s == (unsigned)nstages) { s = 0; ++use; }
+          if (H) { if (++rb == g.nrb) { rb = 0; ++cc; } }
+          else { if (++cc == g.ncc) { cc = 0; ++rb; } }
         }
       }
     }
     return;
   }
   // -------------------------------------------------------------------- consumer warps
-  for (int fi = blockIdx.x; fi < cnt; fi += gridDim.x) {
-    const Front f = fronts[lvl_front[first + fi]];
-    const int k = f.k, r = f.r;
-    Block blk[2];
-    blocks_of<H, UP>(f, fac, blk[0], blk[1]);
-    if (tid < k) ys[tid] = vin[f.col0 + tid];
+  // Header pipeline (all cp.async, landed by the wait + barrier at the top of each front): front index 4 fronts
+  // ahead, Front record 3 ahead, pivot-row values and ancestor indices 2 ahead, ancestor / old cb values 1 ahead.
+  auto fi_of = [&](int n) { return first + blockIdx.x + n * (int)gridDim.x; };
+  auto stage_idx = [&](int n) {   // S4
+    if (n < nmine && tid == 0) cp_async4(&s_fidx[n % 5], lvl_front + fi_of(n));
+  };
+  auto stage_hdr = [&](int n) {   // S3
+    if (n < nmine && tid < 4) cp_async16(reinterpret_cast<char*>(&s_hdr[n % 5]) + 16 * tid,
+                                         reinterpret_cast<const char*>(fronts + s_fidx[n % 5]) + 16 * tid);
+  };
+  auto stage_vec = [&](int n) {   // S2
+    if (n >= nmine) return;
+    const Front& hf = s_hdr[n % 5];
+    z128* yd = ysb + (n % 3) * kmax;
+    for (int i = tid; i < hf.k; i += NCONS) cp_async16(yd + i, vin + hf.col0 + i);
     if (!UP) {
-      const int* idx = st_idx + f.st0;
-      for (int j = tid; j < r; j += NCONS) vbuf[j] = anc[idx[j]];
+      int* id = idxb + (n % 3) * rmax;
+      for (int j = tid; j < hf.r; j += NCONS) cp_async4(id + j, st_idx + hf.st0 + j);
     }
+  };
+  auto stage_anc = [&](int n) {   // S1
+    if (n >= nmine) return;
+    const Front& hf = s_hdr[n % 5];
+    z128* vd = vbb + (n & 1) * rmax;
+    if (UP) {
+      for (int j = tid; j < hf.r; j += NCONS) cp_async16(vd + j, cb + hf.st0 + j);
+    } else {
+      const int* id = idxb + (n % 3) * rmax;
+      for (int j = tid; j < hf.r; j += NCONS) cp_async16(vd + j, anc + id[j]);
+    }
+  };
+  auto land = [&]() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
     cons_sync();
-#pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      const Block b = blk[o];
-      // the vector this block is applied to: indexed by column (N) / by row (H)
-      const z128* v = UP ? (o == 0 ? ys : zs) : (o == 0 ? vbuf : ys);
-      const int nrb = (b.R + TR - 1) / TR, ncc = (b.C + TC - 1) / TC;
-      const int nt = nrb * ncc;
+  };
+  // warm-up: bring fronts 0 .. 3 to their pipeline positions
+  stage_idx(0); stage_idx(1); stage_idx(2); stage_idx(3);
+  land();
+  stage_hdr(0); stage_hdr(1); stage_hdr(2);
+  land();
+  stage_vec(0); stage_vec(1);
+  land();
+  stage_anc(0);
+  unsigned grp = 0;          // output groups that went through part[]
+  unsigned s = 0, use = 0;   // ring position
+  for (int n = 0; n < nmine; ++n) {
+    land();   // front n complete in shared memory; the stages issued one front ago have landed as well
+    stage_idx(n + 4);
+    stage_hdr(n + 3);
+    stage_vec(n + 2);
+    stage_anc(n + 1);
+    const Front f = s_hdr[n % 5];
+    const int k = f.k;
+    z128* ys = ysb + (n % 3) * kmax;
+    z128* vbuf = vbb + (n & 1) * rmax;
+    const int nops = op_count<H, UP>(f);
+    for (int oi = 0; oi < nops; ++oi) {
+      const Op b = get_op<H, UP>(f, fac, oi);
+      const Geo g = geometry(b, H, flags);
+      const z128* v = (b.vsel == 0 ? ys : b.vsel == 1 ? zs : vbuf) + b.voff;
+      const int nt = g.nrb * g.ncc;
+      // N: thread = (row, column group), 8 columns of the tile each; H: thread = (column, row group), 8 rows each
+      const int sh = H ? g.tca_log2 : g.rp_log2;
+      const int a_idx = tid & ((1 << sh) - 1);   // column (H) / row (N) inside the tile
+      const int a_grp = tid >> sh;
+      const int ngrp = NCONS >> sh;
+      const int nout = 1 << sh;                  // results per output group
       z128 acc = mk(0, 0);
-      for (int t = 0; t < nt; ++t, ++it) {
-        const int rb = H ? t % nrb : t / ncc, cc = H ? t / nrb : t % ncc;
-        const int r0 = rb * TR, c0 = cc * TC;
-        const unsigned s = it % STAGES, use = it / STAGES;
+      int rb = 0, cc = 0;
+      for (int t = 0; t < nt; ++t) {
+        const int r0 = rb * TR, c0 = cc * g.tca;
         mbar_wait(&full[s], use & 1);
-        const z128* tile = stages + s * TILE;
+        const z128* tile = stages + (size_t)s * TILE;
         if (!H) {
-          // thread = row, all columns of the tile
-          const int row = r0 + tid;
+          const int row = r0 + a_idx;
           if (row < b.R) {
 #pragma unroll
-            for (int j = 0; j < TC; ++j) {
-              const int c = c0 + j;
-              const bool ok = c < b.C && (b.mask == NONE || (b.mask == STRICT_LOWER ? row > c : row <= c));
-              if (ok) acc += tile[tid + j * LDT] * v[c];
+            for (int q = 0; q < 8; ++q) {
+              const int j = a_grp + ngrp * q, c = c0 + j;
+              if (c < b.C && keep(b.mask, row, c)) acc += tile[a_idx + j * g.ldt] * v[c];
             }
           }
         } else {
-          // thread = (column, group of 8 rows)
-          const int col = tid & (TC - 1), rg = tid >> 3;
-          const int c = c0 + col;
+          const int c = c0 + a_idx;
           if (c < b.C) {
 #pragma unroll
-            for (int i = 0; i < TR / (NCONS / TC); ++i) {
-              const int rl = rg * (TR / (NCONS / TC)) + i, row = r0 + rl;
-              const bool ok = row < b.R && (b.mask == NONE || (b.mask == STRICT_LOWER ? row > c : row <= c));
-              if (ok) acc += conj_(tile[rl + col * LDT]) * v[row];
+            for (int q = 0; q < 8; ++q) {
+              const int rl = a_grp * 8 + q, row = r0 + rl;
+              if (row < b.R && keep(b.mask, row, c)) acc += conj_(tile[rl + a_idx * g.ldt]) * v[row];
             }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == (unsigned)nstages) { s = 0; ++use; }
         // ---- end of an output group: row block (N) / column chunk (H)
-        const bool last = H ? (rb == nrb - 1) : (cc == ncc - 1);
+        bool last;
+        if (H) { last = ++rb == g.nrb; if (last) { rb = 0; ++cc; } }
+        else { last = ++cc == g.ncc; if (last) { cc = 0; ++rb; } }
         if (!last) continue;
         z128 total = acc;
-        int out_i = r0 + tid;   // N: this thread's row
-        bool have = !H && out_i < b.R;
-        if (H) {
-          for (int o2 = 8; o2 < 32; o2 <<= 1) {
-            total.x += __shfl_xor_sync(0xffffffffu, total.x, o2);
-            total.y += __shfl_xor_sync(0xffffffffu, total.y, o2);
-          }
-          const int p = cc & 1;
-          if (lane < TC) part[p][wid][lane] = total;
-          cons_sync();
-          have = tid < TC && c0 + tid < b.C;
-          out_i = c0 + tid;
-          if (have) total = part[p][0][tid] + part[p][1][tid] + part[p][2][tid] + part[p][3][tid];
-        }
-        if (have) {
-          if (UP) {
-            if (o == 0) {
-              const z128 z = H ? total : ys[out_i] + total;
-              zs[out_i] = z;
-              vout[f.col0 + out_i] = z;
-            } else {
-              cb[f.st0 + out_i] -= total;
-            }
-          } else {
-            if (o == 0) ys[out_i] -= total;
-            else vout[f.col0 + out_i] = H ? ys[out_i] + total : total;
-          }
-        }
         acc = mk(0, 0);
+        if (ngrp > 1) {
+          z128* pp = part[grp & 1];
+          ++grp;
+          pp[tid] = total;
+          cons_sync();
+          if (tid < nout) {
+            total = pp[tid];
+            for (int q = 1; q < ngrp; ++q) total += pp[tid + q * nout];
+          }
+        }
+        const int li = (H ? c0 : r0) + tid;   // block-local index of this thread's result
+        if (tid < nout && li < (H ? b.C : b.R)) {
+          const int t_i = b.out0 + li;
+          if (b.emit == Z_UNIT || b.emit == Z_PLAIN) {
+            const z128 z = b.emit == Z_UNIT ? ys[t_i] + total : total;
+            zs[t_i] = z;
+            vout[f.col0 + t_i] = z;
+          } else if (b.emit == SUB_Y || t_i < k) {
+            ys[t_i] -= total;
+          } else {
+            // cb -= total on the copy fetched ahead of time: no dependent global read here.  A row is updated
+            // once per step, so the running value is kept in shared memory across the steps.
+            const z128 nv = vbuf[t_i - k] - total;
+            vbuf[t_i - k] = nv;
+            cb[f.st0 + (t_i - k)] = nv;
+          }
+        }
       }
-      cons_sync();   // the vector produced by this block is complete / ys, vbuf may be overwritten
+      cons_sync();   // results of this operation visible to the next one
     }
   }
 }
 
 template <bool H, bool UP>
-static void launch_front_stream(lsa_handle_impl& h, cudaStream_t st, int cnt, const int* lvl_front, int first, int maxr,
-                                const z128* fac, const z128* vin, z128* vout, z128* cb, const z128* anc) {
+static bool launch_front_stream(lsa_handle_impl& h, cudaStream_t st, int cnt, const int* lvl_front, int first, int maxk,
+                                int maxr, const z128* fac, const z128* vin, z128* vout, z128* cb, const z128* anc) {
   using namespace stream;
-  const size_t smem = sizeof(z128) * ((size_t)STAGES * TILE + (size_t)(UP ? 0 : maxr));
+  const int kmax = (maxk + 7) / 8 * 8, rmax = (maxr + 7) / 8 * 8;
+  const size_t fixed = sizeof(z128) * (4 * (size_t)kmax + 2 * (size_t)rmax) + 3 * sizeof(int) * (size_t)rmax;
+  // ring depth: levels with many fronts want many CTAs per SM (the per-front latencies overlap across CTAs),
+  // levels with few fronts want one deep ring per SM (a CTA streams ~ depth x 16 KB per memory round trip)
+  const int per_sm = std::max(1, std::min(6, cdiv(cnt, h.num_sms)));
+  int nstages = h.stream_stages > 0 ? h.stream_stages : std::max(2, std::min(MAX_STAGES, 12 / per_sm));
+  while (nstages > 2 && fixed + sizeof(z128) * (size_t)nstages * TILE > (size_t)STREAM_MAX_SMEM) --nstages;
+  const size_t smem = fixed + sizeof(z128) * (size_t)nstages * TILE;
+  if (smem > (size_t)STREAM_MAX_SMEM) return false;
   static bool attr_done = false;   // per instantiation
   static int occ_cache[2] = {0, 0};
   if (!attr_done) {
@@ -882,8 +1044,10 @@ static void launch_front_stream(lsa_handle_impl& h, cudaStream_t st, int cnt, co
     occ_cache[1] = occ;
   }
   const int grid = std::max(1, std::min(cnt, std::max(1, occ) * h.num_sms));
-  k_front_stream<H, UP><<<grid, NTHREADS, smem, st>>>(h.d_fronts, lvl_front, first, cnt, h.d_st_idx, fac, vin, vout, cb, anc);
+  k_front_stream<H, UP><<<grid, NTHREADS, smem, st>>>(h.d_fronts, lvl_front, first, cnt, h.d_st_idx, fac, vin, vout, cb, anc,
+                                                      kmax, rmax, nstages, h.stream_flags);
   LSA_LAUNCH_CHECK();
+  return true;
 }
 
 // ------------------------------------------------------- bottom of the tree (persistent, task based)
@@ -1186,25 +1350,29 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       tr.mark("up_gather", d, 0, cnt, 1);
       launches++;
       const int maxk = sym.fronts[lvl_front[first]].k;
-      int max_m = 0;
-      for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
+      int max_m = 0, max_r = 0;
+      for (int q = first; q < first + cnt; ++q) {
+        max_m = std::max(max_m, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
+        max_r = std::max(max_r, sym.fronts[lvl_front[q]].r);
+      }
       const int csize = cluster_width(cnt, max_m, h.num_sms, h.cluster_max_width);
       // tall fronts need the whole GPU per step; up to `cluster_max_rows` rows a cluster of <= 8 SMs keeps up
       // and saves the launches (inside a CUDA graph the two are within 3 % of each other, profiles/r1f_*)
+      if constexpr (scalar_traits<T>::is_complex) {
+        if (h.use_stream && (maxk <= SB || cnt >= h.stream_min_fronts) &&
+            launch_front_stream<H, true>(h, st, cnt, d_lvl_front, first, maxk, max_r, fac, y, z, cb, nullptr)) {
+          tr.mark("up_stream", d, 0, cnt, 1);
+          launches++;
+          continue;
+        }
+      }
       if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
         sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
         tr.mark("up_cluster", d, csize, csize * cnt, 1);
         launches++;
         continue;
       }
-      if constexpr (scalar_traits<T>::is_complex) {
-        if (maxk <= SB && h.use_stream) {
-          launch_front_stream<H, true>(h, st, cnt, d_lvl_front, first, 0, fac, y, z, cb, nullptr);
-          tr.mark("up_stream", d, 0, cnt, 1);
-          launches++;
-          continue;
-        }
-      }
+
       for (int j0 = 0; j0 < maxk; j0 += SB) {
         int act = 0, max_rows = 0;
         for (int q = first; q < first + cnt; ++q) {
@@ -1232,9 +1400,8 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[lvl_front[q]].r);
       bool streamed = false;
       if constexpr (scalar_traits<T>::is_complex) {
-        if (maxk <= SB && h.use_stream &&
-            sizeof(z128) * ((size_t)stream::STAGES * stream::TILE + (size_t)maxr) <= (size_t)stream::STREAM_MAX_SMEM) {
-          launch_front_stream<H, false>(h, st, cnt, d_lvl_front, first, maxr, fac, z, y, cb, H ? x : y);
+        if (h.use_stream && (maxk <= SB || cnt >= h.stream_min_fronts) &&
+            launch_front_stream<H, false>(h, st, cnt, d_lvl_front, first, maxk, maxr, fac, z, y, cb, H ? x : y)) {
           tr.mark("down_stream", d, 0, cnt, 1);
           launches++;
           streamed = true;
