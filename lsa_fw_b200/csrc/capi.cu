@@ -400,6 +400,8 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->use_stream = value != 0.0;
   } else if (nm == "stream_min_fronts") {
     h->stream_min_fronts = (int)value;
+  } else if (nm == "stream_small_rows") {
+    h->stream_small_rows = (int)value;
   } else if (nm == "stream_stages") {
     if (value < 0 || value > 12 || value == 1) return fail(h, LSA_ERR_ARG, "stream_stages must be 0 (automatic) or 2 .. 12");
     h->stream_stages = (int)value;
@@ -556,6 +558,7 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   if (const char* e = getenv("LSA_CLUSTER_MAX_WIDTH")) h->cluster_max_width = atoi(e);
   if (const char* e = getenv("LSA_NO_STREAM")) h->use_stream = atoi(e) == 0;
   if (const char* e = getenv("LSA_STREAM_MIN_FRONTS")) h->stream_min_fronts = atoi(e);
+  if (const char* e = getenv("LSA_STREAM_SMALL_ROWS")) h->stream_small_rows = atoi(e);
   if (const char* e = getenv("LSA_STREAM_STAGES")) h->stream_stages = std::max(0, std::min(12, atoi(e)));
   if (const char* e = getenv("LSA_STREAM_FLAGS")) h->stream_flags = atoi(e) & 7;
   if (const char* e = getenv("LSA_NO_CLUSTERS")) {

@@ -151,11 +151,12 @@ struct lsa_handle_impl {
   std::vector<SolveGraph> solve_graphs;
   bool use_graphs = true;
   int cluster_max_width = 16;   // CTAs per front in the cluster sweep (16 = non-portable cluster size)
-  int cluster_max_rows = 1280;  // fronts taller than this are swept with one grid-wide launch per step (measured optimum)
+  int cluster_max_rows = 8192;  // fronts taller than this are swept with one grid-wide launch per step (measured optimum)
   bool use_stream = true;     // single-step levels: bulk-copy/mbarrier streamed kernel (complex factors)
   int stream_stages = 0;      // ring depth of the streamed kernel (0 = by level size)
   int stream_flags = 3;       // bit 0: wider tiles for narrow blocks, bit 1: single-copy tiles for contiguous blocks
-  int stream_min_fronts = 1 << 30; // multi-step levels with at least this many fronts are streamed too (one CTA per front)
+  int stream_small_rows = 192; // levels whose fronts have at most this many rows use the small-CTA variant
+  int stream_min_fronts = 96; // multi-step levels with at least this many fronts are streamed too (one CTA per front)
   bool use_clusters = true;
   bool use_subtrees = false;  // sweep the bottom of the tree with the persistent task-based kernel (measured slower)   // sweep multi-step levels with thread-block clusters (one launch per level)
   double coupled_fraction = 0.5;

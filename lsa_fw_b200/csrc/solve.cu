@@ -657,8 +657,6 @@ namespace stream {
 constexpr int TR = 128;             // max tile rows
 constexpr int MAX_STAGES = 12;
 constexpr int TILE = 1088;          // entries per stage: 64 columns x (16 + 1) rows is the largest layout
-constexpr int NCONS = 128;          // consumer threads; warp 4 is the producer
-constexpr int NTHREADS = NCONS + 32;
 constexpr int STREAM_MAX_SMEM = 200 * 1024;
 enum Mask { NONE = 0, STRICT_LOWER = 1, UPPER = 2 };
 enum Emit { Z_UNIT = 0, Z_PLAIN = 1, SUB_SPLIT = 2, SUB_Y = 3 };
@@ -724,6 +722,7 @@ __device__ __forceinline__ void bulk_g2s(z128* dst, const z128* src, unsigned by
                "l"(src), "r"(bytes), "r"(sa(b))
                : "memory");
 }
+template <int NCONS>
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
 // rows [lo, hi) of block column c that a tile covering rows [r0, r1) has to hold
 __device__ __forceinline__ void seg(int mask, int c, int r0, int r1, int& lo, int& hi) {
@@ -735,6 +734,19 @@ __device__ __forceinline__ void seg(int mask, int c, int r0, int r1, int& lo, in
 }
 __device__ __forceinline__ bool keep(int mask, int row, int c) {
   return mask == NONE || (mask == STRICT_LOWER ? row > c : row <= c);
+}
+// acc += a * b  /  acc += conj(a) * b  as four FMAs (the operator form compiles to 4 multiplies + 2 adds)
+__device__ __forceinline__ void cmac(z128& acc, const z128 a, const z128 b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cmac_conj(z128& acc, const z128 a, const z128 b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(-a.y, b.x, acc.y);
 }
 template <bool H, bool UP>
 __device__ __forceinline__ int op_count(const Front& f) {
@@ -783,14 +795,15 @@ __device__ __forceinline__ Op get_op(const Front& f, const z128* fac, int i) {
 }
 }  // namespace stream
 
-template <bool H, bool UP>
-__global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* __restrict__ fronts,
+template <bool H, bool UP, int NCONS, int NPROD>
+__global__ void __launch_bounds__(NCONS + 32 * NPROD) k_front_stream(const Front* __restrict__ fronts,
                                                                    const int* __restrict__ lvl_front, int first, int cnt,
                                                                    const int* __restrict__ st_idx,
                                                                    const z128* __restrict__ fac, const z128* vin,
                                                                    z128* vout, z128* cb, const z128* anc, int kmax, int rmax,
                                                                    int nstages, int flags) {
   using namespace stream;
+  constexpr int ITER = 1024 / NCONS;   // entries of a tile per consumer thread
   extern __shared__ __align__(16) unsigned char stream_smem[];
   // dynamic shared memory: ring | ys x 3 | zs | vb x 2 | idx x 3 (down sweep)
   z128* stages = reinterpret_cast<z128*>(stream_smem);
@@ -812,8 +825,10 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
   }
   __syncthreads();
   const int nmine = blockIdx.x < cnt ? (cnt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // fronts of this CTA
-  if (wid == NCONS / 32) {
-    // ------------------------------------------------------------------ producer warp
+  if (wid >= NCONS / 32) {
+    // ------------------------------------------------------------------ producer warps
+    const int pw = wid - NCONS / 32;   // tiles with (tile number mod NPROD) == pw are this warp's
+    int turn = 0;
     unsigned s = 0, use = 0;   // ring position
     Front fn = nmine > 0 ? fronts[lvl_front[first + blockIdx.x]] : Front{};
     for (int n = 0; n < nmine; ++n) {
@@ -829,6 +844,14 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
           const int r0 = rb * TR, r1 = min(b.R, r0 + TR);
           const int c0 = cc * g.tca, nc = min(g.tca, b.C - c0);
           z128* dst = stages + (size_t)s * TILE;
+          const bool mine = turn == pw;
+          if (++turn == NPROD) turn = 0;
+          if (!mine) {
+            if (++s == (unsigned)nstages) { s = 0; ++use; }
+            if (H) { if (++rb == g.nrb) { rb = 0; ++cc; } }
+            else { if (++cc == g.ncc) { cc = 0; ++rb; } }
+            continue;
+          }
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
           if (flags & 4) {
             // LDGSTS path: the warp copies the tile in 16-byte pieces (512 B per instruction, coalesced along
@@ -853,6 +876,13 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
               mbar_expect_tx(&full[s], bytes);
               bulk_g2s(dst, b.src + (long long)c0 * b.ld, bytes, &full[s]);
             }
+          } else if (b.mask == NONE) {
+            // full-height columns: every copy has the same size
+            const unsigned bytes = (unsigned)(r1 - r0) * (unsigned)sizeof(z128);
+            if (lane == 0) mbar_expect_tx(&full[s], bytes * (unsigned)nc);
+            __syncwarp();
+            for (int j = lane; j < nc; j += 32)
+              bulk_g2s(dst + j * g.ldt, b.src + r0 + (long long)(c0 + j) * b.ld, bytes, &full[s]);
           } else {
             int lo[2] = {0, 0}, hi[2] = {0, 0};
             unsigned total = 0;
@@ -915,7 +945,7 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
   };
   auto land = [&]() {
     asm volatile("cp.async.wait_all;" ::: "memory");
-    cons_sync();
+    cons_sync<NCONS>();
   };
   // warm-up: bring fronts 0 .. 3 to their pipeline positions
   stage_idx(0); stage_idx(1); stage_idx(2); stage_idx(3);
@@ -943,13 +973,13 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
       const Geo g = geometry(b, H, flags);
       const z128* v = (b.vsel == 0 ? ys : b.vsel == 1 ? zs : vbuf) + b.voff;
       const int nt = g.nrb * g.ncc;
-      // N: thread = (row, column group), 8 columns of the tile each; H: thread = (column, row group), 8 rows each
+      // N: thread = (row, column group), ITER columns of the tile each; H: thread = (column, row group), ITER rows each
       const int sh = H ? g.tca_log2 : g.rp_log2;
       const int a_idx = tid & ((1 << sh) - 1);   // column (H) / row (N) inside the tile
       const int a_grp = tid >> sh;
       const int ngrp = NCONS >> sh;
       const int nout = 1 << sh;                  // results per output group
-      z128 acc = mk(0, 0);
+      z128 acc = mk(0, 0), acc2 = mk(0, 0);
       int rb = 0, cc = 0;
       for (int t = 0; t < nt; ++t) {
         const int r0 = rb * TR, c0 = cc * g.tca;
@@ -958,19 +988,41 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
         if (!H) {
           const int row = r0 + a_idx;
           if (row < b.R) {
+            const z128* tp = tile + a_idx + a_grp * g.ldt;
+            const z128* vp = v + c0 + a_grp;
+            const int st = ngrp * g.ldt;
+            if (b.mask == NONE && c0 + a_grp + ngrp * (ITER - 1) < b.C) {
+              // all of this thread's columns exist: no predicates, two accumulators
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int j = a_grp + ngrp * q, c = c0 + j;
-              if (c < b.C && keep(b.mask, row, c)) acc += tile[a_idx + j * g.ldt] * v[c];
+              for (int q = 0; q < ITER; q += 2) {
+                cmac(acc, tp[q * st], vp[q * ngrp]);
+                cmac(acc2, tp[(q + 1) * st], vp[(q + 1) * ngrp]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < ITER; ++q) {
+                const int c = c0 + a_grp + ngrp * q;
+                if (c < b.C && keep(b.mask, row, c)) cmac(acc, tp[q * st], vp[q * ngrp]);
+              }
             }
           }
         } else {
           const int c = c0 + a_idx;
           if (c < b.C) {
+            const z128* tp = tile + a_grp * ITER + a_idx * g.ldt;
+            const z128* vp = v + r0 + a_grp * ITER;
+            if (b.mask == NONE && r0 + a_grp * ITER + ITER <= b.R) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int rl = a_grp * 8 + q, row = r0 + rl;
-              if (row < b.R && keep(b.mask, row, c)) acc += conj_(tile[rl + a_idx * g.ldt]) * v[row];
+              for (int q = 0; q < ITER; q += 2) {
+                cmac_conj(acc, tp[q], vp[q]);
+                cmac_conj(acc2, tp[q + 1], vp[q + 1]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < ITER; ++q) {
+                const int row = r0 + a_grp * ITER + q;
+                if (row < b.R && keep(b.mask, row, c)) cmac_conj(acc, tp[q], vp[q]);
+              }
             }
           }
         }
@@ -982,13 +1034,29 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
         if (H) { last = ++rb == g.nrb; if (last) { rb = 0; ++cc; } }
         else { last = ++cc == g.ncc; if (last) { cc = 0; ++rb; } }
         if (!last) continue;
-        z128 total = acc;
+        z128 total = acc + acc2;
         acc = mk(0, 0);
-        if (ngrp > 1) {
+        acc2 = mk(0, 0);
+        if (H && g.tca < 32) {
+          // row groups of a column sit tca lanes apart: fold them inside the warp, then one partial per warp
+          z128* pp = part[grp & 1];
+          ++grp;
+          for (int o2 = g.tca; o2 < 32; o2 <<= 1) {
+            total.x += __shfl_xor_sync(0xffffffffu, total.x, o2);
+            total.y += __shfl_xor_sync(0xffffffffu, total.y, o2);
+          }
+          if (lane < g.tca) pp[wid * g.tca + lane] = total;
+          cons_sync<NCONS>();
+          if (tid < nout) {
+            total = pp[tid];
+#pragma unroll
+            for (int q = 1; q < NCONS / 32; ++q) total += pp[tid + q * g.tca];
+          }
+        } else if (ngrp > 1) {
           z128* pp = part[grp & 1];
           ++grp;
           pp[tid] = total;
-          cons_sync();
+          cons_sync<NCONS>();
           if (tid < nout) {
             total = pp[tid];
             for (int q = 1; q < ngrp; ++q) total += pp[tid + q * nout];
@@ -1012,42 +1080,55 @@ __global__ void __launch_bounds__(stream::NTHREADS) k_front_stream(const Front* 
           }
         }
       }
-      cons_sync();   // results of this operation visible to the next one
+      cons_sync<NCONS>();   // results of this operation visible to the next one
     }
   }
 }
 
-template <bool H, bool UP>
-static bool launch_front_stream(lsa_handle_impl& h, cudaStream_t st, int cnt, const int* lvl_front, int first, int maxk,
+template <bool H, bool UP, int NCONS, int NPROD>
+static bool launch_front_stream_t(lsa_handle_impl& h, cudaStream_t st, int cnt, const int* lvl_front, int first, int maxk,
                                 int maxr, const z128* fac, const z128* vin, z128* vout, z128* cb, const z128* anc) {
   using namespace stream;
   const int kmax = (maxk + 7) / 8 * 8, rmax = (maxr + 7) / 8 * 8;
   const size_t fixed = sizeof(z128) * (4 * (size_t)kmax + 2 * (size_t)rmax) + 3 * sizeof(int) * (size_t)rmax;
   // ring depth: levels with many fronts want many CTAs per SM (the per-front latencies overlap across CTAs),
   // levels with few fronts want one deep ring per SM (a CTA streams ~ depth x 16 KB per memory round trip)
-  const int per_sm = std::max(1, std::min(6, cdiv(cnt, h.num_sms)));
-  int nstages = h.stream_stages > 0 ? h.stream_stages : std::max(2, std::min(MAX_STAGES, 12 / per_sm));
+  constexpr int NTHREADS = NCONS + 32 * NPROD;
+  const int max_per_sm = NCONS == 128 ? 5 : 3;   // register file: 64 registers x threads per CTA
+  const int per_sm = std::max(1, std::min(max_per_sm, cdiv(cnt, h.num_sms)));
+  int nstages = h.stream_stages > 0 ? h.stream_stages : std::max(2, std::min(MAX_STAGES, 10 / per_sm));
   while (nstages > 2 && fixed + sizeof(z128) * (size_t)nstages * TILE > (size_t)STREAM_MAX_SMEM) --nstages;
   const size_t smem = fixed + sizeof(z128) * (size_t)nstages * TILE;
   if (smem > (size_t)STREAM_MAX_SMEM) return false;
   static bool attr_done = false;   // per instantiation
   static int occ_cache[2] = {0, 0};
   if (!attr_done) {
-    LSA_CUDA(cudaFuncSetAttribute(k_front_stream<H, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_MAX_SMEM));
+    LSA_CUDA(cudaFuncSetAttribute(k_front_stream<H, UP, NCONS, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_MAX_SMEM));
     attr_done = true;
   }
   int occ = 0;
   if (occ_cache[0] == (int)smem) occ = occ_cache[1];
   else {
-    LSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_front_stream<H, UP>, NTHREADS, smem));
+    LSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_front_stream<H, UP, NCONS, NPROD>, NTHREADS, smem));
     occ_cache[0] = (int)smem;
     occ_cache[1] = occ;
   }
   const int grid = std::max(1, std::min(cnt, std::max(1, occ) * h.num_sms));
-  k_front_stream<H, UP><<<grid, NTHREADS, smem, st>>>(h.d_fronts, lvl_front, first, cnt, h.d_st_idx, fac, vin, vout, cb, anc,
+  k_front_stream<H, UP, NCONS, NPROD><<<grid, NTHREADS, smem, st>>>(h.d_fronts, lvl_front, first, cnt, h.d_st_idx, fac, vin, vout, cb, anc,
                                                       kmax, rmax, nstages, h.stream_flags);
   LSA_LAUNCH_CHECK();
   return true;
+}
+
+// Small fronts (leaf-like levels): 4 consumer warps + 1 producer, up to 5 CTAs per SM, the per-front latencies
+// overlap across CTAs.  Larger fronts: 8 consumer warps + 2 producers per CTA (per-CTA throughput matters).
+template <bool H, bool UP>
+static bool launch_front_stream(lsa_handle_impl& h, cudaStream_t st, int cnt, const int* lvl_front, int first, int maxk,
+                                int maxr, int max_m, const z128* fac, const z128* vin, z128* vout, z128* cb,
+                                const z128* anc) {
+  const bool small = h.stream_small_rows > 0 && max_m <= h.stream_small_rows;
+  if (small) return launch_front_stream_t<H, UP, 128, 1>(h, st, cnt, lvl_front, first, maxk, maxr, fac, vin, vout, cb, anc);
+  return launch_front_stream_t<H, UP, 256, 2>(h, st, cnt, lvl_front, first, maxk, maxr, fac, vin, vout, cb, anc);
 }
 
 // ------------------------------------------------------- bottom of the tree (persistent, task based)
@@ -1360,7 +1441,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       // and saves the launches (inside a CUDA graph the two are within 3 % of each other, profiles/r1f_*)
       if constexpr (scalar_traits<T>::is_complex) {
         if (h.use_stream && (maxk <= SB || cnt >= h.stream_min_fronts) &&
-            launch_front_stream<H, true>(h, st, cnt, d_lvl_front, first, maxk, max_r, fac, y, z, cb, nullptr)) {
+            launch_front_stream<H, true>(h, st, cnt, d_lvl_front, first, maxk, max_r, max_m, fac, y, z, cb, nullptr)) {
           tr.mark("up_stream", d, 0, cnt, 1);
           launches++;
           continue;
@@ -1401,7 +1482,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       bool streamed = false;
       if constexpr (scalar_traits<T>::is_complex) {
         if (h.use_stream && (maxk <= SB || cnt >= h.stream_min_fronts) &&
-            launch_front_stream<H, false>(h, st, cnt, d_lvl_front, first, maxk, maxr, fac, z, y, cb, H ? x : y)) {
+            launch_front_stream<H, false>(h, st, cnt, d_lvl_front, first, maxk, maxr, maxk + maxr, fac, z, y, cb, H ? x : y)) {
           tr.mark("down_stream", d, 0, cnt, 1);
           launches++;
           streamed = true;

@@ -419,7 +419,8 @@ def test_singular_pencil_is_perturbed_not_crashed(caplog):
 
 
 def test_large_front_paths_match_scipy_solve():
-    """3-D cavity with fronts of several hundred pivots: multi-step cluster sweeps, rank-128 deferred updates."""
+    """3-D cavity with fronts of several hundred pivots: multi-step cluster sweeps, streamed (bulk-copy) sweeps in
+    every tile geometry / ring depth / CTA shape, per-step launches, rank-128 deferred updates."""
     import scipy.sparse.linalg as spla
 
     pc = pencils.cavity_3d(8)
@@ -434,8 +435,16 @@ def test_large_front_paths_match_scipy_solve():
     C = (pc.A - sigma * pc.M).tocsc()
     b = np.random.default_rng(3).standard_normal(pc.n) + 1j * np.random.default_rng(4).standard_normal(pc.n)
     xs = spla.splu(C).solve(b)
-    for opts in (dict(use_clusters=1, use_subtrees=1), dict(use_clusters=0, use_subtrees=1),
-                 dict(use_clusters=1, use_subtrees=0), dict(use_clusters=0, use_subtrees=0, use_graphs=0)):
+    base = dict(use_clusters=1, use_subtrees=0, use_graphs=1, use_stream=1, stream_min_fronts=96, stream_flags=3,
+                stream_small_rows=192, stream_stages=0, cluster_max_rows=8192, cluster_max_width=16)
+    variants = (dict(), dict(use_subtrees=1), dict(use_clusters=0, use_subtrees=1), dict(use_clusters=0, use_graphs=0),
+                dict(use_stream=0), dict(use_stream=0, use_clusters=0, cluster_max_rows=0),
+                dict(stream_min_fronts=1), dict(stream_min_fronts=1, stream_flags=0, stream_stages=2),
+                dict(stream_min_fronts=1, stream_flags=7, stream_small_rows=0),
+                dict(stream_min_fronts=4, stream_flags=1, stream_small_rows=100000, stream_stages=12),
+                dict(cluster_max_rows=1280, cluster_max_width=4))
+    for var in variants:
+        opts = dict(base, **var)
         for opt, val in opts.items():
             h.set_option(opt, val)
         h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)      # re-factor: drops the captured sweep graphs
