@@ -289,7 +289,7 @@ def main() -> None:
     sampler.start()
     t0 = time.perf_counter()
     acc = dict(factor=0.0, eigs=0.0, solve=0.0, spmv=0.0, ortho=0.0, rr=0.0, restart=0.0, applies=0, restarts=0,
-               kernels=0, flops=0.0)
+               kernels=0, flops=0.0, reorth=0)
     for _ in range(args.steps):
         fs, rd, ra, lam_d = device_step()
         acc["factor"] += fs.seconds
@@ -304,6 +304,7 @@ def main() -> None:
             acc["restart"] += r.seconds_restart
             acc["applies"] += r.n_op_applies
             acc["restarts"] += r.n_restarts
+            acc["reorth"] += r.n_reorth
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -402,7 +403,7 @@ def main() -> None:
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(acc["kernels"]),
             "clocks": clocks,
-            "roofline": {"kernel": "supernodal triangular-solve sweep (k_up_*/k_down_*, fwd+bwd)", "bound": "hbm",
+            "roofline": {"kernel": "supernodal triangular-solve sweep (k_front_stream + k_sweep_cluster + k_up_gather + k_down_off, fwd+bwd)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_solve, "mean_launch_seconds": solve_mean,
@@ -415,6 +416,7 @@ def main() -> None:
                               "peak": hbm_peak, "unit": "GB/s"},
             "phases_s_per_step": {k: acc[k] / args.steps for k in ("factor", "eigs", "solve", "spmv", "ortho", "rr", "restart")},
             "op_applies_per_step": acc["applies"] / args.steps, "restarts_per_step": acc["restarts"] / args.steps,
+            "reorthogonalised_columns_per_step": acc["reorth"] / args.steps,
             "symbolic": {"seconds": t_symbolic, "phases": list(info.seconds), "fronts": info.n_fronts, "levels": info.n_levels,
                          "nnz_lu": int(info.nnz_lu), "flops_real": info.flops_real, "max_front": info.max_front,
                          "decoupled": info.n_decoupled},

@@ -95,7 +95,8 @@ typedef struct {
   int32_t nconv, n_restarts, n_op_applies, breakdown;
   double seconds;               /* device time of the Krylov-Schur loop (CUDA events)    */
   double seconds_solve, seconds_spmv, seconds_ortho, seconds_rr, seconds_restart;
-  int32_t n_kernels, pad;
+  int32_t n_kernels;
+  int32_t n_reorth;             /* basis columns that needed the second Gram-Schmidt pass */
 } lsa_eigs_result;
 
 typedef struct {
@@ -178,6 +179,11 @@ int lsa_get_eigenvectors(const lsa_handle* h, double* out_c128, int64_t ld, int3
 int lsa_get_residuals(lsa_handle* h, double* out, int32_t capacity);
 int lsa_get_counters(const lsa_handle* h, lsa_counters* out);
 int lsa_sync(lsa_handle* h);
+/* Page-locked host memory for result buffers (eigenvectors leave the device at PCIe speed instead of through
+ * the driver's bounce buffers; VecGetArray of the reference hands out host memory as well, Solver/utils.py:280-297).
+ * Plain cudaHostAlloc / cudaFreeHost; no handle needed. */
+int lsa_host_alloc(uint64_t bytes, void** ptr);
+int lsa_host_free(void* ptr);
 
 /* -- stand-alone kernels exposed for parity tests and roofline measurement -------------------- */
 /* Dense Rayleigh-Ritz step (DSSolve/DSSort of SLEPc): Schur form of the m x m matrix S (column-major,

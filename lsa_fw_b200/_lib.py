@@ -8,6 +8,7 @@ numeric entry point raises `LsaError`.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from pathlib import Path
 
 import numpy as np
@@ -15,6 +16,7 @@ import numpy as np
 _PKG = Path(__file__).resolve().parent
 _LIB_PATH = _PKG / "liblsa_b200.so"
 
+LSA_OK = 0
 LSA_F64, LSA_C128 = 0, 1
 LSA_OP_N, LSA_OP_T, LSA_OP_H = 0, 1, 2
 LSA_MAT_A, LSA_MAT_M = 0, 1
@@ -67,7 +69,7 @@ class EigsResult(C.Structure):
         ("nconv", C.c_int32), ("n_restarts", C.c_int32), ("n_op_applies", C.c_int32), ("breakdown", C.c_int32),
         ("seconds", C.c_double), ("seconds_solve", C.c_double), ("seconds_spmv", C.c_double),
         ("seconds_ortho", C.c_double), ("seconds_rr", C.c_double), ("seconds_restart", C.c_double),
-        ("n_kernels", C.c_int32), ("pad", C.c_int32),
+        ("n_kernels", C.c_int32), ("n_reorth", C.c_int32),
     ]
 
 
@@ -80,6 +82,69 @@ class Counters(C.Structure):
 
 
 _lib = None
+
+# ------------------------------------------------------------------ page-locked result buffers
+# Big results (n x nev eigenvector blocks) are copied straight into page-locked memory and handed out as
+# NumPy arrays on top of it.  Blocks go back to a small pool when the last array referring to them dies, so a
+# solve loop allocates once.
+_PINNED_POOL: dict[int, list[int]] = {}
+_PINNED_POOL_MAX_BYTES = 4 << 30
+_PINNED_MIN_BYTES = 1 << 20
+_pinned_pool_bytes = 0
+
+
+class _PinnedBlock:
+    """Owner of one page-locked allocation; exposes it through the array interface."""
+
+    def __init__(self, ptr: int, nbytes: int) -> None:
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def _pinned_release(lib, ptr: int, nbytes: int) -> None:
+    global _pinned_pool_bytes
+    try:
+        if _pinned_pool_bytes + nbytes <= _PINNED_POOL_MAX_BYTES:
+            _PINNED_POOL.setdefault(nbytes, []).append(ptr)
+            _pinned_pool_bytes += nbytes
+        else:
+            lib.lsa_host_free(C.c_void_p(ptr))
+    except Exception:  # interpreter shutdown
+        pass
+
+
+def pinned_empty(shape, dtype, lib=None) -> np.ndarray:
+    """`np.empty(shape, dtype)` on page-locked memory (plain pageable memory for small arrays or when the
+    allocation fails)."""
+    global _pinned_pool_bytes
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    if nbytes < _PINNED_MIN_BYTES:
+        return np.empty(shape, dtype=dtype)
+    lib = lib or load()
+    free = _PINNED_POOL.get(nbytes)
+    if free:
+        ptr = free.pop()
+        _pinned_pool_bytes -= nbytes
+    else:
+        p = C.c_void_p()
+        if lib.lsa_host_alloc(C.c_uint64(nbytes), C.byref(p)) != LSA_OK or not p.value:
+            return np.empty(shape, dtype=dtype)
+        ptr = p.value
+    blk = _PinnedBlock(ptr, nbytes)
+    weakref.finalize(blk, _pinned_release, lib, ptr, nbytes)
+    return np.asarray(blk).view(dtype).reshape(shape)
+
+
+def pinned_pool_clear() -> None:
+    """Free the page-locked blocks that are waiting in the pool."""
+    global _pinned_pool_bytes
+    lib = load()
+    for nbytes, ptrs in _PINNED_POOL.items():
+        for ptr in ptrs:
+            lib.lsa_host_free(C.c_void_p(ptr))
+    _PINNED_POOL.clear()
+    _pinned_pool_bytes = 0
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
@@ -117,6 +182,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lsa_get_residuals.argtypes = [vp, vp, i32]
     lib.lsa_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.lsa_sync.argtypes = [vp]
+    lib.lsa_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lsa_host_free.argtypes = [C.c_void_p]
     lib.lsa_dense_schur.argtypes = [vp, i32, vp, i32, vp, i32, i32, dbl, dbl]
     lib.lsa_gemm_bench.argtypes = [vp, i32, i32, i32, i32, i32, pd, pd]
     _lib = lib
@@ -127,7 +194,7 @@ EXPORTS = [
     "lsa_version", "lsa_create", "lsa_destroy", "lsa_last_error", "lsa_analyze", "lsa_set_option", "lsa_symbolic_info_get",
     "lsa_symbolic_array", "lsa_set_values", "lsa_factor", "lsa_solve", "lsa_spmv", "lsa_eigs",
     "lsa_get_eigenvalues", "lsa_get_eigenvectors", "lsa_get_residuals", "lsa_get_counters", "lsa_sync",
-    "lsa_dense_schur", "lsa_gemm_bench",
+    "lsa_host_alloc", "lsa_host_free", "lsa_dense_schur", "lsa_gemm_bench",
 ]
 
 _ARRAY_DTYPES = {
@@ -262,7 +329,7 @@ class Handle:
         return out[:cnt]
 
     def eigenvectors(self, count: int) -> np.ndarray:
-        out = np.empty((max(count, 1), self.n), dtype=np.complex128)
+        out = pinned_empty((max(count, 1), self.n), np.complex128, self.lib)
         cnt = self.check(self.lib.lsa_get_eigenvectors(self._h, out.ctypes.data, self.n, count, 0))
         return out[:cnt].T
 

@@ -58,7 +58,7 @@ void free_device(lsa_handle_impl& h) {
   }
   dfree(h.d_x); dfree(h.d_w); dfree(h.d_t); dfree(h.d_t2); dfree(h.d_cb); dfree(h.d_io); dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q);
   dfree(h.d_part); dfree(h.d_npart); dfree(h.d_h); dfree(h.d_brow); dfree(h.d_ywork); dfree(h.d_r1); dfree(h.d_r2);
-  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
+  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_refine); dfree(h.d_wn2); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
   h.V_cols = 0; h.X_cols = 0; h.ncv_alloc = 0; h.scalar = -1; h.have_values = false;
 }
 
@@ -376,6 +376,8 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     h->d_npart = dalloc<double>((size_t)cdiv(n, 256) + 1);
     h->d_h = dalloc<z128>(512);
     h->d_flag = dalloc<int>(1);
+    h->d_refine = dalloc<int>(2);
+    h->d_wn2 = dalloc<double>(1024);
     h->d_ipart = dalloc<int>(256);
     h->d_rr = dalloc<RrInfo>(1);
     upload_csr(*h, h->hA, h->dA, false);
@@ -396,6 +398,8 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->use_graphs = value != 0.0;
   } else if (nm == "use_clusters") {
     h->use_clusters = value != 0.0;
+  } else if (nm == "ortho_refine_always") {
+    h->ortho_refine_always = value != 0.0;
   } else if (nm == "use_stream") {
     h->use_stream = value != 0.0;
   } else if (nm == "stream_min_fronts") {
@@ -734,6 +738,17 @@ int lsa_get_counters(const lsa_handle* h, lsa_counters* out) {
   out->bytes_spmv_m = (double)h->nnz_m * ((h->m_complex ? 16.0 : 8.0) + 4.0) + 8.0 * (s.n + 1) + 2.0 * s.n * 16.0;
   out->bytes_spmv_a = (double)h->nnz_a * ((h->a_complex ? 16.0 : 8.0) + 4.0) + 8.0 * (s.n + 1) + 2.0 * s.n * 16.0;
   return LSA_OK;
+}
+
+int lsa_host_alloc(uint64_t bytes, void** ptr) {
+  if (!ptr || bytes == 0) return LSA_ERR_ARG;
+  *ptr = nullptr;
+  return cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? LSA_OK : LSA_ERR_CUDA;
+}
+
+int lsa_host_free(void* ptr) {
+  if (!ptr) return LSA_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? LSA_OK : LSA_ERR_CUDA;
 }
 
 int lsa_sync(lsa_handle* h) {

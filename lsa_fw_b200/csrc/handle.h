@@ -125,6 +125,9 @@ struct lsa_handle_impl {
   z128* d_r3 = nullptr;
   z128* d_Xp = nullptr;    // n x ncv Ritz vectors, permuted ordering
   int* d_flag = nullptr;
+  int* d_refine = nullptr;    // [0] second Gram-Schmidt pass wanted for the current column, [1] how many were
+  double* d_wn2 = nullptr;    // partial |w|^2 before orthogonalisation (refinement criterion)
+  bool ortho_refine_always = false;
   int* d_ipart = nullptr;  // arg-max partial indices
   RrInfo* d_rr = nullptr;
   z128* d_theta = nullptr;

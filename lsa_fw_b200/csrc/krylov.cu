@@ -169,22 +169,31 @@ static constexpr int DOT_CG = 8;      // column groups
 static constexpr int MAXC_PER = 16;   // columns per thread -> up to 128 basis vectors
 
 // part[blk * ldp + c] = sum over the block's rows of conj(V[i, c]) w[i],  c0 <= c < min(j, c0 + 128)
+// wn2 (optional): wn2[blk] = sum over the block's rows of |w[i]|^2.  skip (optional): *skip == 0 -> nothing to do
+// (second CGS pass that the refinement criterion did not ask for).
 __global__ void __launch_bounds__(256) k_dots(int n, int j, int c0, const z128* __restrict__ V, long long ldv,
                                               const z128* __restrict__ w, z128* __restrict__ part, int ldp,
-                                              int rows_per_block) {
+                                              int rows_per_block, double* __restrict__ wn2, const int* __restrict__ skip) {
+  if (skip && *skip == 0) return;
   const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min((long long)n, r0 + rows_per_block);
   z128 acc[MAXC_PER];
 #pragma unroll
   for (int q = 0; q < MAXC_PER; ++q) acc[q] = mk(0, 0);
+  double wacc = 0.0;
   for (long long i = r0 + lane; i < r1; i += DOT_ROWS) {
     const z128 wi = w[i];
+    wacc += abs2(wi);
 #pragma unroll
     for (int q = 0; q < MAXC_PER; ++q) {
       const int c = c0 + cg + q * DOT_CG;
       if (c < j) acc[q] += conj_(V[i + c * ldv]) * wi;
     }
+  }
+  if (wn2 && cg == 0) {
+    for (int o = 16; o > 0; o >>= 1) wacc += __shfl_xor_sync(0xffffffffu, wacc, o);
+    if (lane == 0) wn2[blockIdx.x] = wacc;
   }
 #pragma unroll
   for (int q = 0; q < MAXC_PER; ++q) {
@@ -203,7 +212,9 @@ __global__ void __launch_bounds__(256) k_dots(int n, int j, int c0, const z128* 
 // h[c] = sum_blk part[blk, c]; S column update: scol[c] = (accumulate ? scol[c] : 0) + h[c].
 // One warp per column.
 __global__ void __launch_bounds__(256) k_reduce_h(int j, int nblk, const z128* __restrict__ part, int ldp,
-                                                  z128* __restrict__ h, z128* __restrict__ scol, int accumulate) {
+                                                  z128* __restrict__ h, z128* __restrict__ scol, int accumulate,
+                                                  const int* __restrict__ skip) {
+  if (skip && *skip == 0) return;
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= j) return;
@@ -222,7 +233,8 @@ __global__ void __launch_bounds__(256) k_reduce_h(int j, int nblk, const z128* _
 // w -= V[:, 0:j] h ; optionally npart[blk] = sum |w_new|^2 over the block's rows
 __global__ void __launch_bounds__(256) k_update(int n, int j, const z128* __restrict__ V, long long ldv,
                                                 const z128* __restrict__ h, z128* __restrict__ w,
-                                                double* __restrict__ npart) {
+                                                double* __restrict__ npart, const int* __restrict__ skip) {
+  if (skip && *skip == 0) return;
   __shared__ z128 hs[256];
   __shared__ double red[8];
   if ((int)threadIdx.x < j) hs[threadIdx.x] = h[threadIdx.x];
@@ -246,6 +258,33 @@ __global__ void __launch_bounds__(256) k_update(int n, int j, const z128* __rest
       for (int q = 0; q < 8; ++q) s += red[q];
       npart[blockIdx.x] = s;
     }
+  }
+}
+
+// Reorthogonalisation criterion of the "refine if needed" Gram-Schmidt (SLEPc's default,
+// BV_ORTHOG_REFINE_IFNEEDED with eta = 1/sqrt(2)): a second pass only if the first one removed more than half
+// of the squared norm.  flag = 1: refine.  Fixed-order reductions (deterministic).
+__global__ void __launch_bounds__(256) k_refine_flag(int nb_before, const double* __restrict__ wn2, int nb_after,
+                                                     const double* __restrict__ npart, int always,
+                                                     int* __restrict__ flag, int* __restrict__ count) {
+  __shared__ double ra[256], rb[256];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nb_before; i += 256) a += wn2[i];
+  for (int i = threadIdx.x; i < nb_after; i += 256) b += npart[i];
+  ra[threadIdx.x] = a;
+  rb[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      ra[threadIdx.x] += ra[threadIdx.x + o];
+      rb[threadIdx.x] += rb[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int f = always || !(rb[0] >= 0.5 * ra[0]);   // also true for NaN
+    *flag = f;
+    if (f && count) atomicAdd(count, 1);
   }
 }
 
@@ -654,6 +693,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   const size_t e_all = t_all.begin();
 
   LSA_CUDA(cudaMemsetAsync(S, 0, sizeof(z128) * (size_t)ld * ncv, st));
+  LSA_CUDA(cudaMemsetAsync(h.d_refine, 0, 2 * sizeof(int), st));
   int h_flag = 0x7fffffff;
   LSA_CUDA(cudaMemcpyAsync(h.d_flag, &h_flag, sizeof(int), cudaMemcpyHostToDevice, st));
 
@@ -683,16 +723,21 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       const size_t e = t_ortho.begin();
       const int jj = j + 1;  // orthogonalise against columns 0..j
       z128* scol = S + (long long)j * ld;
-      for (int c0 = 0; c0 < jj; c0 += 128) k_dots<<<nblk, 256, 0, st>>>(n, jj, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
-      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 0);
-      k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, nullptr);
-      for (int c0 = 0; c0 < jj; c0 += 128) k_dots<<<nblk, 256, 0, st>>>(n, jj, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
-      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 1);
-      k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart);
+      // classical Gram-Schmidt, second pass only when the criterion asks for it (decided on the device: the
+      // pass-2 kernels return at once when the flag is clear)
+      for (int c0 = 0; c0 < jj; c0 += 128)
+        k_dots<<<nblk, 256, 0, st>>>(n, jj, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, c0 == 0 ? h.d_wn2 : nullptr, nullptr);
+      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 0, nullptr);
+      k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart, nullptr);
+      k_refine_flag<<<1, 256, 0, st>>>(nblk, h.d_wn2, blocks, h.d_npart, h.ortho_refine_always ? 1 : 0, h.d_refine, h.d_refine + 1);
+      for (int c0 = 0; c0 < jj; c0 += 128)
+        k_dots<<<nblk, 256, 0, st>>>(n, jj, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, nullptr, h.d_refine);
+      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 1, h.d_refine);
+      k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart, h.d_refine);
       k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V + (long long)(j + 1) * ldv, h.d_npart, blocks, nullptr,
                                           scol + j + 1, scol, jj, h.d_flag, j);
       LSA_LAUNCH_CHECK();
-      h.launch_count += 8;  // spmv + 7 orthogonalisation kernels
+      h.launch_count += 9;  // spmv + 8 orthogonalisation kernels
       t_ortho.end(e);
     }
     // ---- breakdown check (one small read-back per restart)
@@ -747,9 +792,10 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       z128* vnew = V + (long long)keep * ldv;
       k_randn<<<blocks, 256, 0, st>>>(h.d_w, n, p.seed + 7919ULL * (unsigned long long)restarts);
       for (int pass = 0; pass < 2; ++pass) {
-        for (int c0 = 0; c0 < keep; c0 += 128) k_dots<<<nblk, 256, 0, st>>>(n, keep, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block);
-        k_reduce_h<<<cdiv(keep, 8), 256, 0, st>>>(keep, nblk, h.d_part, ldp, h.d_h, h.d_brow, 0);
-        k_update<<<blocks, 256, 0, st>>>(n, keep, V, ldv, h.d_h, h.d_w, pass ? h.d_npart : nullptr);
+        for (int c0 = 0; c0 < keep; c0 += 128)
+          k_dots<<<nblk, 256, 0, st>>>(n, keep, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, nullptr, nullptr);
+        k_reduce_h<<<cdiv(keep, 8), 256, 0, st>>>(keep, nblk, h.d_part, ldp, h.d_h, h.d_brow, 0, nullptr);
+        k_update<<<blocks, 256, 0, st>>>(n, keep, V, ldv, h.d_h, h.d_w, pass ? h.d_npart : nullptr, nullptr);
       }
       k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, vnew, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
       h_flag = 0x7fffffff;
@@ -813,7 +859,10 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
     h.eigenvalues = sorted;
   }
   t_all.end(e_all);
+  int n_reorth = 0;
+  LSA_CUDA(cudaMemcpyAsync(&n_reorth, h.d_refine + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   LSA_CUDA(cudaStreamSynchronize(st));
+  out.n_reorth = n_reorth;
   out.nconv = nconv;
   out.n_restarts = restarts;
   out.n_op_applies = n_applies;

@@ -525,7 +525,7 @@ class iEpsSolver:  # noqa: N801
             self._fetch_vectors()
         stats["fetch_seconds"] = time.perf_counter() - t0
         stats.update(nconv=res.nconv, n_restarts=res.n_restarts, n_op_applies=res.n_op_applies,
-                     breakdown=res.breakdown, eigs_seconds=res.seconds, solve_seconds=res.seconds_solve,
+                     breakdown=res.breakdown, n_reorth=res.n_reorth, eigs_seconds=res.seconds, solve_seconds=res.seconds_solve,
                      spmv_seconds=res.seconds_spmv, ortho_seconds=res.seconds_ortho, rr_seconds=res.seconds_rr,
                      restart_seconds=res.seconds_restart, total_seconds=time.perf_counter() - t_start)
         self._stats = stats

@@ -245,6 +245,60 @@ def test_symbolic_analysis_is_reused_across_shifts_and_reynolds():
     assert cached == [False, True, True]
 
 
+def test_gram_schmidt_refinement_if_needed_matches_always():
+    """SLEPc's default orthogonalisation refines only when the first pass removed more than half of the squared
+    norm (BV_ORTHOG_REFINE_IFNEEDED, eta = 1/sqrt 2); the device takes that decision per column.  Same pairs as
+    with unconditional CGS2, far fewer second passes, basis-dependent quantities still at the parity bars."""
+    pc = pencils.assemble_pencil((24, 12), (8.0, 3.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.5))
+    sigma = 0.05 + 0.6j
+    h = _lib.Handle(pc.n, 0)
+    flag = ((pc.A.diagonal() - sigma * pc.M.diagonal()) == 0).astype(np.uint8)
+    h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=32, order_last=flag)
+    h.set_values(pc.A.data, pc.M.data)
+    h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
+    out = {}
+    for always in (1, 0):
+        h.set_option("ortho_refine_always", always)
+        r = h.eigs(nev=6, ncv=40, tol=1e-11, max_restarts=100, which="TARGET_MAGNITUDE", transform=_lib.LSA_ST_SINVERT,
+                   sigma=sigma, seed=1)
+        assert r.nconv >= 6
+        X = h.eigenvectors(6)
+        out[always] = (r, h.eigenvalues(6), h.residuals(6), X)
+    ra, la, resa, _ = out[1]
+    ri, li, resi, Xi = out[0]
+    assert ra.n_reorth > 0 and ri.n_reorth < ra.n_reorth
+    assert np.abs(li - la).max() < EIG_RTOL * np.abs(la).max()
+    assert resi.max() < RESID_BAR and resa.max() < RESID_BAR
+    assert np.linalg.norm(Xi, axis=0) == pytest.approx(1.0, abs=1e-12)
+    h.close()
+
+
+def test_result_buffers_are_page_locked_and_recycled():
+    import gc
+
+    _lib.pinned_pool_clear()
+    a = _lib.pinned_empty((1 << 17, 2), np.complex128)            # 4 MB: page-locked
+    assert isinstance(a.base, np.ndarray) or a.base is not None
+    addr = a.ctypes.data
+    a[:] = 1.0 + 2.0j
+    view = a[:, 1]
+    del a
+    gc.collect()
+    assert view[5] == 1.0 + 2.0j                                   # a live view keeps the block
+    assert not _lib._PINNED_POOL.get(1 << 22)
+    del view
+    gc.collect()
+    assert _lib._PINNED_POOL.get(1 << 22) == [addr]                # ... and the last one returns it to the pool
+    b = _lib.pinned_empty((1 << 18,), np.complex128)               # same size: same block again
+    assert b.ctypes.data == addr
+    small = _lib.pinned_empty((8,), np.float64)                    # small arrays stay pageable
+    assert small.base is None
+    del b
+    gc.collect()
+    _lib.pinned_pool_clear()
+    assert not _lib._PINNED_POOL
+
+
 # ------------------------------------------------------------------ C-ABI level kernels
 @pytest.fixture(scope="module")
 def factored():

@@ -38,6 +38,6 @@ print(f"{name}: device sweep {r.seconds_solve / r.n_op_applies * 1e3:.3f} ms/app
       f"(LSA_SUBTREE_DIV={os.environ.get('LSA_SUBTREE_DIV')}, NO_SUBTREES={os.environ.get('LSA_NO_SUBTREES')}, "
       f"NO_GRAPHS={os.environ.get('LSA_NO_GRAPHS')})", flush=True)
 os.environ["LSA_TRACE"] = "1"
-h.solve(b)
+h.solve(b, _lib.LSA_OP_H if "--H" in sys.argv else _lib.LSA_OP_N)
 os.environ.pop("LSA_TRACE")
 h.close()
