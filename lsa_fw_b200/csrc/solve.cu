@@ -610,6 +610,219 @@ static void launch_sweep_cluster(cudaStream_t st, int cnt, const Front* fronts, 
   LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb));
 }
 
+// ------------------------------------------------------------- cluster sweep with look-ahead (big fronts)
+//
+// Same job as k_sweep_cluster, organised so that the dependent chain of a front is as short as the
+// hardware allows:
+//  * the 128-row chunks of a front are owned STATICALLY (chunk g -> CTA g mod C of the cluster): all updates
+//    of a row come from one CTA, so nothing but the solved slices crosses CTAs;
+//  * only the owner of pivot block s applies the inverted diagonal block; it pushes the solved slice z_s into
+//    the shared memory of every CTA of the cluster (DSMEM stores) -- no redundant 128 x 128 GEMV per CTA;
+//  * split cluster barrier: a CTA ARRIVES for step s+1 as soon as its part of the critical path is done (the
+//    owner of block s+1: update that block with z_s, solve it, broadcast z_{s+1}; everybody else: at once),
+//    then updates the rest of its chunks with z_s, and only then WAITS.  The updates that are not on the
+//    critical path overlap the next triangular step.  Three z buffers: z_{s+2} can only be written after every
+//    CTA has arrived for step s+2, i.e. finished using z_s.
+template <class T, bool H, bool UP, int C>
+__global__ void __launch_bounds__(1024) k_sweep_cluster2(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                         int first, const T* __restrict__ fac, z128* in, z128* out,
+                                                         z128* cb) {
+  namespace cg = cooperative_groups;
+  constexpr int NT = 1024, CG = NT / SB, NWARP = NT / 32;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = C > 1 ? (int)cluster.block_rank() : 0;
+  const Front f = fronts[lvl_front[first + blockIdx.x / C]];
+  const int k = f.k;
+  const long long m = (long long)k + f.r;
+  const T* P = fac + f.p_off;
+  const T* Q = fac + f.q_off;
+  __shared__ z128 ys[SB];
+  __shared__ z128 zbuf[3][SB];
+  __shared__ z128 part[CG][SB];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nsteps = (k + SB - 1) / SB;
+  const int nchunks = (int)((m + SB - 1) / SB);
+
+  // ---- rows [lo, hi) of chunk g  -=  Off[rows, j0:j1) z      (plain loads/stores: the chunk is this CTA's)
+  auto update_chunk = [&](int j0, int len, int g, const z128* zs) {
+    const int j1 = j0 + len;
+    const int lo = UP ? max(j1, g * SB) : g * SB;
+    const int hi = UP ? (int)min(m, (long long)(g + 1) * SB) : min(j0, (g + 1) * SB);
+    if (hi <= lo) return;   // uniform over the CTA
+    const int base = g * SB;
+    if (!H) {
+      const int rr = tid & (SB - 1), cgi = tid >> 7;
+      const int row = base + rr;
+      z128 acc = mk(0, 0);
+      if (row >= lo && row < hi) {
+        const T* a = P + row + (long long)j0 * m;
+#pragma unroll 8
+        for (int c = cgi; c < len; c += CG) acc += a[(long long)c * m] * zs[c];
+      }
+      __syncthreads();
+      part[cgi][rr] = acc;
+      __syncthreads();
+      if (tid < SB && row >= lo && row < hi) {
+        z128 sum = part[0][tid];
+#pragma unroll
+        for (int q = 1; q < CG; ++q) sum += part[q][tid];
+        z128* dst = (!UP || row < k) ? in + f.col0 + row : cb + f.st0 + (row - k);
+        *dst = *dst - sum;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < SB / NWARP; ++q) {
+        const int row = base + wid + q * NWARP;
+        if (row < lo || row >= hi) continue;
+        const T* u = (!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
+        z128 acc = mk(0, 0);
+        for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * zs[c];
+        for (int o = 16; o > 0; o >>= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (lane == 0) {
+          z128* dst = (!UP || row < k) ? in + f.col0 + row : cb + f.st0 + (row - k);
+          *dst = *dst - acc;
+        }
+      }
+    }
+    __syncthreads();
+  };
+
+  // ---- the owner of pivot block s: z_s = Op y_s, stored to `out` and pushed to every CTA's zbuf[slot]
+  auto solve_block = [&](int s, int slot) {
+    const int j0 = s * SB, len = min(SB, k - j0);
+    const T* D = P + j0 + (long long)j0 * m;
+    if (tid < len) ys[tid] = in[f.col0 + j0 + tid];
+    __syncthreads();
+    z128 z = mk(0, 0);
+    if (!H) {
+      const int i = tid & (SB - 1), cgi = tid >> 7;
+      z128 acc = mk(0, 0);
+      if (i < len) {
+        const T* row = D + i;
+        if (UP) {
+#pragma unroll 8
+          for (int c = cgi; c < i; c += CG) acc += row[(long long)c * m] * ys[c];
+        } else {
+#pragma unroll 8
+          for (int c = i + cgi; c < len; c += CG) acc += row[(long long)c * m] * ys[c];
+        }
+      }
+      part[cgi][i] = acc;
+      __syncthreads();
+      if (tid < len) {
+        z128 sum = part[0][tid];
+#pragma unroll
+        for (int q = 1; q < CG; ++q) sum += part[q][tid];
+        z = UP ? sum + ys[tid] : sum;
+      }
+    } else {
+      // one warp per column of the block, results collected in part[0][]
+      for (int i = wid; i < len; i += NWARP) {
+        const T* col = D + (long long)i * m;
+        z128 acc = mk(0, 0);
+        if (UP) {
+          for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
+        } else {
+          for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (lane == 0) part[0][i] = UP ? acc : acc + ys[i];
+      }
+      __syncthreads();
+      if (tid < len) z = part[0][tid];
+    }
+    if (tid < len) {
+      out[f.col0 + j0 + tid] = z;
+      if (C > 1) {
+#pragma unroll
+        for (int r = 0; r < C; ++r) cluster.map_shared_rank(&zbuf[slot][0], r)[tid] = z;
+      } else {
+        zbuf[slot][tid] = z;
+      }
+    }
+    __syncthreads();
+  };
+
+  // panel of step `s` for this CTA's chunks -> L2
+  auto prefetch_step = [&](int s) {
+    if (s < 0 || s >= nsteps) return;
+    const int j0 = s * SB, len = min(SB, k - j0), j1 = j0 + len;
+    if (rank == s % C && tid < len) prefetch_l2(P + j0 + (long long)(j0 + tid) * m, len);
+    const int q = tid >> 7, i = tid & (SB - 1);
+    const int g_lo = UP ? j1 / SB : 0, g_hi = UP ? nchunks : s;   // chunks touched at this step
+    int g = g_lo + ((rank - g_lo) % C + C) % C;                   // first chunk >= g_lo owned by this rank
+    g += q * C;
+    for (; g < g_hi; g += 8 * C) {
+      const int lo = UP ? max(j1, g * SB) : g * SB;
+      const int hi = UP ? (int)min(m, (long long)(g + 1) * SB) : (g + 1) * SB;
+      if (hi <= lo) continue;
+      if (!H) {
+        if (i < len) prefetch_l2(P + lo + (long long)(j0 + i) * m, hi - lo);
+      } else if (lo + i < hi) {
+        const int row = lo + i;
+        prefetch_l2((!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k, len);
+      }
+    }
+  };
+
+  auto step_of = [&](int i) { return UP ? i : nsteps - 1 - i; };
+  prefetch_step(step_of(0));
+  if (rank == step_of(0) % C) solve_block(step_of(0), 0);
+  if (C > 1) cluster.barrier_arrive();
+  for (int i = 0; i < nsteps; ++i) {
+    const int s = step_of(i);
+    const int j0 = s * SB, len = min(SB, k - j0), j1 = j0 + len;
+    const z128* zs = zbuf[i % 3];
+    if (C > 1) cluster.barrier_wait();   // z_s has arrived
+    else __syncthreads();
+    const bool more = i + 1 < nsteps;
+    const int sn = more ? step_of(i + 1) : -1;   // next pivot block = chunk sn
+    prefetch_step(sn);
+    if (more && rank == sn % C) {
+      update_chunk(j0, len, sn, zs);             // critical path first
+      solve_block(sn, (i + 1) % 3);
+    }
+    if (more && C > 1) cluster.barrier_arrive();
+    // the rest of this CTA's chunks
+    const int g_lo = UP ? j1 / SB : 0, g_hi = UP ? nchunks : s;
+    for (int g = g_lo + ((rank - g_lo) % C + C) % C; g < g_hi; g += C) {
+      if (more && g == sn) continue;
+      update_chunk(j0, len, g, zs);
+    }
+  }
+}
+
+template <class T, bool H, bool UP, int C>
+static void launch_sweep_cluster2(cudaStream_t st, int cnt, const Front* fronts, const int* lvl_front, int first,
+                                  const T* fac, z128* in, z128* out, z128* cb) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(C * cnt), 1, 1);
+  cfg.blockDim = dim3(1024, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (C > 8) {
+    static bool allowed = false;   // per instantiation
+    if (!allowed) {
+      LSA_CUDA(cudaFuncSetAttribute(k_sweep_cluster2<T, H, UP, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      allowed = true;
+    }
+  }
+  LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster2<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb));
+}
+
 // Cluster width of a level: as many SMs per front as the level leaves free (one 1024-thread CTA per SM),
 // but no more than the front has 128-row chunks to hand out.
 static int cluster_width(int cnt, int max_rows, int num_sms, int max_width) {
@@ -622,7 +835,17 @@ static int cluster_width(int cnt, int max_rows, int num_sms, int max_width) {
 
 template <class T, bool H, bool UP>
 static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fronts, const int* lvl_front, int first,
-                          const T* fac, z128* in, z128* out, z128* cb) {
+                          const T* fac, z128* in, z128* out, z128* cb, bool lookahead) {
+  if (lookahead) {
+    switch (csize) {
+      case 1: launch_sweep_cluster2<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+      case 2: launch_sweep_cluster2<T, H, UP, 2>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+      case 4: launch_sweep_cluster2<T, H, UP, 4>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+      case 8: launch_sweep_cluster2<T, H, UP, 8>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+      default: launch_sweep_cluster2<T, H, UP, 16>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+    }
+    return;
+  }
   switch (csize) {
     case 1: launch_sweep_cluster<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
     case 2: launch_sweep_cluster<T, H, UP, 2>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
@@ -1448,7 +1671,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         }
       }
       if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
-        sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
+        sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb, h.cluster_lookahead);
         tr.mark("up_cluster", d, csize, csize * cnt, 1);
         launches++;
         continue;
@@ -1502,7 +1725,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         int max_m = 0;
         for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k);
         const int csize = cluster_width(cnt, max_m, h.num_sms, h.cluster_max_width);
-        sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
+        sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb, h.cluster_lookahead);
         tr.mark("down_cluster", d, csize, csize * cnt, 1);
         launches++;
       } else {
