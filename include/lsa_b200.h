@@ -132,7 +132,16 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
  *       no earlier than the front in which this share of its coupled regular unknowns has been eliminated
  *       (1.0 = all of them: most robust, ~+40-70 % flops in 2-D);
  *   "use_graphs" (default 1): replay the triangular-solve sweeps from CUDA graphs;
- *   "use_clusters" (default 1): sweep multi-step levels with one thread-block cluster per front;
+ *   "use_stream" (default 1): complex factors, levels with many fronts: streamed sweep kernel (bulk copies into
+ *       a shared-memory ring); "stream_min_fronts" (96): multi-step levels with at least this many fronts are
+ *       streamed too; "stream_small_rows" (192): levels whose fronts are at most this tall use the small CTA shape;
+ *       "stream_stages" (0 = by level size, 2..12): ring depth; "stream_flags" (3): bit 0 wider tiles for narrow
+ *       blocks, bit 1 single-copy tiles for contiguous blocks, bit 2 LDGSTS producer (measured slower);
+ *   "use_clusters" (default 1): sweep the remaining multi-step levels with one thread-block cluster per front;
+ *       "cluster_max_width" (16): CTAs per cluster; "cluster_max_rows" (8192): taller fronts get one grid-wide
+ *       launch per 128-pivot step instead; "cluster_lookahead" (0): look-ahead variant;
+ *   "ortho_refine_always" (default 0): second Gram-Schmidt pass for every basis column instead of SLEPc's
+ *       refine-if-needed rule;
  *   "use_subtrees" (default 0): sweep the bottom of the tree with the persistent task-based kernel
  *       (kept for comparison: measured 2.7x - 7x slower than the level-synchronous sweep). */
 int lsa_set_option(lsa_handle* h, const char* name, double value);

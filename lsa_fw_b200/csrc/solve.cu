@@ -520,19 +520,29 @@ __global__ void __launch_bounds__(1024) k_sweep_cluster(const Front* __restrict_
         zs[tid] = UP ? sum + ys[tid] : sum;
       }
     } else {
-      for (int i = wid; i < len; i += NWARP) {
-        const T* col = D + (long long)i * m;
-        z128 acc = mk(0, 0);
-        if (UP) {
-          for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
-        } else {
-          for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
+      // one warp per 4 columns of the block (i = wid + 32 q): the four column reads are issued together
+      constexpr int NQ = SB / NWARP;
+      z128 acc[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[q] = mk(0, 0);
+#pragma unroll
+      for (int cb0 = 0; cb0 < SB; cb0 += 32) {
+        const int c = cb0 + lane;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int i = wid + q * NWARP;
+          const bool use = i < len && c < len && (UP ? c <= i : c > i);
+          if (use) acc[q] += conj_(D[(long long)i * m + c]) * ys[c];
         }
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
         for (int o = 16; o > 0; o >>= 1) {
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+          acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+          acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
         }
-        if (lane == 0) zs[i] = UP ? acc : acc + ys[i];
+        const int i = wid + q * NWARP;
+        if (lane == 0 && i < len) zs[i] = UP ? acc[q] : acc[q] + ys[i];
       }
     }
     __syncthreads();
@@ -560,21 +570,44 @@ __global__ void __launch_bounds__(1024) k_sweep_cluster(const Front* __restrict_
           *dst = ld_cg(dst) - sum;
         }
       } else {
+        // one warp per 4 rows of the chunk: all reads of the four rows in flight together, then the four
+        // read-modify-writes from four lanes at once
+        constexpr int NQ = SB / NWARP;
+        const T* u[NQ];
+        z128 acc[NQ];
 #pragma unroll
-        for (int q = 0; q < SB / NWARP; ++q) {
+        for (int q = 0; q < NQ; ++q) {
           const int rr = wid + q * NWARP;
-          if (r0 + rr >= nrows) break;
           const int row = (UP ? j1 : 0) + r0 + rr;
-          const T* u = (!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
-          z128 acc = mk(0, 0);
-          for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * zs[c];
-          for (int o = 16; o > 0; o >>= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+          const bool ok = r0 + rr < nrows;
+          u[q] = !ok ? nullptr : (!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
+          acc[q] = mk(0, 0);
+        }
+#pragma unroll
+        for (int cb0 = 0; cb0 < SB; cb0 += 32) {
+          const int c = cb0 + lane;
+          if (c < len) {
+            const z128 zc = zs[c];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+              if (u[q]) acc[q] += conj_(u[q][c]) * zc;
           }
-          if (lane == 0) {
+        }
+        z128 mine = mk(0, 0);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          for (int o = 16; o > 0; o >>= 1) {
+            acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+            acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+          }
+          if (lane == q) mine = acc[q];
+        }
+        if (lane < NQ) {
+          const int rr = wid + lane * NWARP;
+          if (r0 + rr < nrows) {
+            const int row = (UP ? j1 : 0) + r0 + rr;
             z128* dst = (!UP || row < k) ? in + f.col0 + row : cb + f.st0 + (row - k);
-            *dst = ld_cg(dst) - acc;
+            *dst = ld_cg(dst) - mine;
           }
         }
       }
