@@ -202,17 +202,37 @@ __global__ void __launch_bounds__(256) k_up_gather(const Front* __restrict__ fro
   z128* cbp = cb + p.st0;
   for (int t = threadIdx.x; t < p.r; t += blockDim.x) cbp[t] = mk(0, 0);
   __syncthreads();
-  for (int q = 0; q < p.nchild; ++q) {
-    const Front c = fronts[child_idx[p.child0 + q]];
-    const int* map = ea_map + c.st0;
-    const z128* cbc = cb + c.st0;
-    for (int t = threadIdx.x; t < c.r; t += blockDim.x) {
-      const int ip = map[t];
-      const z128 v = cbc[t];
-      if (ip < p.k) x[p.col0 + ip] += v;
-      else cbp[ip - p.k] += v;
+  // children two at a time: both records and both (target, value) streams are read together, the additions are
+  // still applied child after child (fixed order: deterministic)
+  for (int q = 0; q < p.nchild; q += 2) {
+    const bool two = q + 1 < p.nchild;
+    const int i0 = child_idx[p.child0 + q], i1 = two ? child_idx[p.child0 + q + 1] : i0;
+    const Front c0 = fronts[i0];
+    const Front c1 = fronts[i1];
+    const int r1 = two ? c1.r : 0;
+    const int* map0 = ea_map + c0.st0;
+    const int* map1 = ea_map + c1.st0;
+    const z128* cb0 = cb + c0.st0;
+    const z128* cb1 = cb + c1.st0;
+    const int rmax = max(c0.r, r1);
+    for (int t0 = 0; t0 < rmax; t0 += blockDim.x) {
+      const int t = t0 + threadIdx.x;
+      const bool h0 = t < c0.r, h1 = t < r1;
+      int ip0 = 0, ip1 = 0;
+      z128 v0 = mk(0, 0), v1 = mk(0, 0);
+      if (h0) { ip0 = map0[t]; v0 = cb0[t]; }
+      if (h1) { ip1 = map1[t]; v1 = cb1[t]; }
+      if (h0) {
+        if (ip0 < p.k) x[p.col0 + ip0] += v0;
+        else cbp[ip0 - p.k] += v0;
+      }
+      __syncthreads();
+      if (h1) {
+        if (ip1 < p.k) x[p.col0 + ip1] += v1;
+        else cbp[ip1 - p.k] += v1;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   for (int i = threadIdx.x; i < p.k; i += blockDim.x) y[p.col0 + i] = x[PERM ? gperm[p.col0 + i] : p.col0 + i];
 }
@@ -257,13 +277,16 @@ __global__ void __launch_bounds__(NW * 32) k_down_off(const Front* __restrict__ 
         for (int c = wid; c < len; c += NW) acc += a[(long long)c * k] * xs[c];
       }
     } else {
+      // the rows of a warp (wid, wid + NW, ...) are read together: ROWS / NW independent streams per lane
+      for (int cb0 = 0; cb0 < len; cb0 += 32) {
+        const int c = cb0 + lane;
+        if (c < len) {
+          const z128 xc = xs[c];
 #pragma unroll
-      for (int q = 0; q < ROWS / NW; ++q) {
-        const int rowH = r0 + wid + q * NW;
-        if (rowH < k) {
-          const T* l = P + k + c0 + (long long)rowH * m;
-#pragma unroll 4
-          for (int c = lane; c < len; c += 32) accH[q] += conj_(l[c]) * xs[c];
+          for (int q = 0; q < ROWS / NW; ++q) {
+            const int rowH = r0 + wid + q * NW;
+            if (rowH < k) accH[q] += conj_(P[k + c0 + c + (long long)rowH * m]) * xc;
+          }
         }
       }
     }
@@ -938,8 +961,9 @@ __device__ __forceinline__ Geo geometry(const Op& b, bool hmode, int flags) {
   g.tca = 1 << g.tca_log2;
   g.nrb = (b.R + TR - 1) / TR;
   g.ncc = (b.C + g.tca - 1) >> g.tca_log2;
-  // whole columns back to back in memory: one copy per tile (row stride = R; column-wise reads need it odd)
-  g.contig = (flags & 2) && b.mask == NONE && b.ld == (long long)b.R && g.nrb == 1 && (!hmode || (b.R & 1));
+  // whole columns back to back in memory: one copy per tile (row stride = R; column-wise reads tolerate a 2-way
+  // bank conflict, R = 2 mod 4, but not the 4/8-way ones of R = 0 mod 4)
+  g.contig = (flags & 2) && b.mask == NONE && b.ld == (long long)b.R && g.nrb == 1 && (!hmode || (b.R & 3));
   g.ldt = g.contig ? b.R : (1 << g.rp_log2) + 1;
   return g;
 }
