@@ -879,6 +879,339 @@ static void launch_sweep_cluster2(cudaStream_t st, int cnt, const Front* fronts,
   LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster2<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb));
 }
 
+// ------------------------------------------------- cluster sweep with row slices (few, tall fronts: the tree top)
+//
+// The top levels hold 1 ... 9 fronts; a 128-pivot step there is a chain of dependent 128 x 128 block products.
+// On one SM each of them is bound by that SM's L2 port (256 KB ~ 2 us).  Here the 16 CTAs of a cluster share
+// EVERY 128-row block of a front: CTA r owns the entries with (index mod 128) / 8 == r of the pivot and the
+// contribution vector, in all blocks -- a static, perfectly balanced ownership in which the critical block
+// of a step (the next pivot block) is 8 rows per CTA.  Per step:
+//   B  every CTA applies its 8 rows (N) / columns (H) of the inverted diagonal block to the gathered pivot
+//      values y_s, and pushes its 8 entries of z_s into the shared memory of all 16 CTAs (DSMEM) -> barrier;
+//   A  every CTA updates its entries of the next pivot block with z_s and pushes them to all CTAs (the next
+//      y) -> barrier arrive; then its entries of all other blocks, eight blocks per pass -> barrier wait.
+// N: block products with one coalesced load per thread (8 rows x 4 columns per warp), partial sums over the
+// 32 warps through shared memory.  H: one warp per target entry, contiguous 2 KB reads, shuffles only.
+template <class T, bool H, bool UP>
+__global__ void __launch_bounds__(1024) k_sweep_slices(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                       int first, const T* __restrict__ fac, z128* in, z128* out,
+                                                       z128* cb) {
+  namespace cg = cooperative_groups;
+  constexpr int C = 16, SL = SB / C, NB = 8, NWARP = 32;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const Front f = fronts[lvl_front[first + blockIdx.x / C]];
+  const int k = f.k;
+  const long long m = (long long)k + f.r;
+  const T* P = fac + f.p_off;
+  const T* Q = fac + f.q_off;
+  __shared__ z128 ybuf[2][SB];
+  __shared__ z128 zbuf[2][SB];
+  __shared__ z128 part[NWARP][NB * SL];
+  __shared__ z128 loc[SL];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nsteps = (k + SB - 1) / SB;
+  const int nblocks = (int)((m + SB - 1) / SB);
+  const int row8 = lane & (SL - 1), csub = lane >> 3;   // N layout inside a warp: 8 rows x 4 columns
+
+  // entry v of the front's vector: pivot entries live in `in`, the others in the contribution vector
+  auto slot = [&](int v) -> z128* { return (!UP || v < k) ? in + f.col0 + v : cb + f.st0 + (v - k); };
+  // push loc[0:SL) (this CTA's entries of a 128-block) into buf[rank * SL + q] of every CTA of the cluster
+  auto broadcast = [&](z128* buf, int len) {
+    if (tid < SB) {
+      const int dstc = tid >> 3, q = tid & (SL - 1);
+      if (rank * SL + q < len) cluster.map_shared_rank(buf, dstc)[rank * SL + q] = loc[q];
+    }
+  };
+
+  // ---- B: entries rank*SL .. of  z = Op(D_s) y
+  auto solve_slice = [&](int s, const z128* ys, z128* zdst) {
+    const int j0 = s * SB, len = min(SB, k - j0);
+    const T* D = P + j0 + (long long)j0 * m;
+    if (!H) {
+      const int row = rank * SL + row8, col = wid * 4 + csub;
+      z128 p = mk(0, 0);
+      if (row < len && col < len && (UP ? col < row : col >= row)) p = D[row + (long long)col * m] * ys[col];
+      for (int o = 8; o < 32; o <<= 1) {
+        p.x += __shfl_xor_sync(0xffffffffu, p.x, o);
+        p.y += __shfl_xor_sync(0xffffffffu, p.y, o);
+      }
+      if (lane < SL) part[wid][lane] = p;
+      __syncthreads();
+      if (tid < SL) {
+        z128 sum = part[0][tid];
+#pragma unroll
+        for (int w = 1; w < NWARP; ++w) sum += part[w][tid];
+        const int i = rank * SL + tid;
+        if (i < len) {
+          const z128 z = UP ? sum + ys[i] : sum;
+          loc[tid] = z;
+          out[f.col0 + j0 + i] = z;
+        }
+      }
+    } else if (wid < SL) {
+      const int i = rank * SL + wid;
+      z128 acc = mk(0, 0);
+      if (i < len) {
+        const T* col = D + (long long)i * m;
+#pragma unroll
+        for (int c0 = 0; c0 < SB; c0 += 32) {
+          const int c = c0 + lane;
+          if (c < len && (UP ? c <= i : c > i)) acc += conj_(col[c]) * ys[c];
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      }
+      if (lane == 0 && i < len) {
+        const z128 z = UP ? acc : acc + ys[i];
+        loc[wid] = z;
+        out[f.col0 + j0 + i] = z;
+      }
+    }
+    __syncthreads();
+    broadcast(zdst, len);
+  };
+
+  // ---- A (critical): this CTA's entries [vlo, vhi) of block g  -=  Off(., step columns) z, all warps on the one
+  //      block (one load per thread); the new values are pushed to every CTA as the next pivot values.
+  auto update_critical = [&](int j0, int len, int g, int vlo, int vhi, const z128* zs, z128* ynext, int ylen) {
+    if (!H) {
+      const int col = wid * 4 + csub;
+      const int v = g * SB + rank * SL + row8;
+      const bool ok = v >= vlo && v < vhi;
+      z128 old = mk(0, 0);
+      if (tid < SL) {   // value to be updated: read together with the block entries
+        const int vv = g * SB + rank * SL + tid;
+        if (vv >= vlo && vv < vhi) old = *slot(vv);
+      }
+      z128 p = mk(0, 0);
+      if (col < len && ok) p = P[v + (long long)(j0 + col) * m] * zs[col];
+      for (int o = 8; o < 32; o <<= 1) {
+        p.x += __shfl_xor_sync(0xffffffffu, p.x, o);
+        p.y += __shfl_xor_sync(0xffffffffu, p.y, o);
+      }
+      if (lane < SL) part[wid][lane] = p;
+      __syncthreads();
+      if (tid < SL) {
+        z128 sum = part[0][tid];
+#pragma unroll
+        for (int w = 1; w < NWARP; ++w) sum += part[w][tid];
+        const int vv = g * SB + rank * SL + tid;
+        if (vv >= vlo && vv < vhi) {
+          const z128 nv = old - sum;
+          *slot(vv) = nv;
+          loc[tid] = nv;
+        }
+      }
+    } else if (wid < SL) {
+      const int v = g * SB + rank * SL + wid;
+      const bool ok = v >= vlo && v < vhi;
+      z128 acc = mk(0, 0), old = mk(0, 0);
+      if (ok) {
+        if (lane == 0) old = *slot(v);
+        const T* bcol = (!UP || v < k) ? P + j0 + (long long)v * m : Q + j0 + (long long)(v - k) * k;
+#pragma unroll
+        for (int c0 = 0; c0 < SB; c0 += 32) {
+          const int c = c0 + lane;
+          if (c < len) acc += conj_(bcol[c]) * zs[c];
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      }
+      if (lane == 0 && ok) {
+        const z128 nv = old - acc;
+        *slot(v) = nv;
+        loc[wid] = nv;
+      }
+    }
+    __syncthreads();
+    broadcast(ynext, ylen);
+  };
+
+  // ---- A (the rest): this CTA's entries of the blocks [ga, gb) restricted to [vlo, vhi), block `skip` left out.
+  //      N: eight blocks per pass with all warps (a warp per block was measured slower: 32 dependent-ish loads
+  //      per lane); H: one warp per entry, two entries in flight.
+  auto update_rest = [&](int j0, int len, int ga, int gb, int skip, int vlo, int vhi, const z128* zs) {
+    if (!H) {
+      // eight blocks per pass, all warps on them: one load per thread and block (8 rows x 4 columns per warp),
+      // partial sums over the 32 warps through shared memory
+      const int col = wid * 4 + csub;
+      for (int g0 = ga; g0 < gb; g0 += NB) {
+        const int cnt = min(NB, gb - g0);
+        z128 old = mk(0, 0);
+        bool mine = false;
+        if (tid < cnt * SL) {   // the values to be updated: read together with the block entries
+          const int g = g0 + (tid >> 3), v = g * SB + rank * SL + (tid & (SL - 1));
+          mine = g != skip && v >= vlo && v < vhi;
+          if (mine) old = *slot(v);
+        }
+        z128 acc[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) acc[u] = mk(0, 0);
+        if (col < len) {
+          const z128 zc = zs[col];
+          const T* a = P + (long long)(j0 + col) * m;
+#pragma unroll
+          for (int u = 0; u < NB; ++u) {
+            const int v = (g0 + u) * SB + rank * SL + row8;
+            if (u < cnt && g0 + u != skip && v >= vlo && v < vhi) acc[u] += a[v] * zc;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          for (int o = 8; o < 32; o <<= 1) {
+            acc[u].x += __shfl_xor_sync(0xffffffffu, acc[u].x, o);
+            acc[u].y += __shfl_xor_sync(0xffffffffu, acc[u].y, o);
+          }
+          if (lane < SL && u < cnt) part[wid][u * SL + lane] = acc[u];
+        }
+        __syncthreads();
+        if (mine) {
+          z128 sum = part[0][tid];
+#pragma unroll 8
+          for (int w = 1; w < NWARP; ++w) sum += part[w][tid];
+          const int v = (g0 + (tid >> 3)) * SB + rank * SL + (tid & (SL - 1));
+          *slot(v) = old - sum;
+        }
+        __syncthreads();
+      }
+    } else {
+      const int nt = (gb - ga) * SL;
+      for (int t0 = 0; t0 < nt; t0 += 2 * NWARP) {
+        int v[2];
+        const T* b[2];
+        z128 acc[2], old[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int t = t0 + wid + q * NWARP;
+          const int g = ga + (t >> 3);
+          v[q] = g * SB + rank * SL + (t & (SL - 1));
+          const bool ok = t < nt && g != skip && v[q] >= vlo && v[q] < vhi;
+          b[q] = !ok ? nullptr : (!UP || v[q] < k) ? P + j0 + (long long)v[q] * m : Q + j0 + (long long)(v[q] - k) * k;
+          acc[q] = mk(0, 0);
+          old[q] = (ok && lane == 0) ? *slot(v[q]) : mk(0, 0);
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < SB; c0 += 32) {
+          const int c = c0 + lane;
+          if (c < len) {
+            const z128 zc = zs[c];
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              if (b[q]) acc[q] += conj_(b[q][c]) * zc;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          for (int o = 16; o > 0; o >>= 1) {
+            acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+            acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+          }
+          if (lane == 0 && b[q]) *slot(v[q]) = old[q] - acc[q];
+        }
+      }
+    }
+    __syncthreads();
+  };
+
+  auto step_of = [&](int i) { return UP ? i : nsteps - 1 - i; };
+  // everything this CTA reads at step index i -> L2 (one step ahead: the factor does not depend on the vectors)
+  auto prefetch_step = [&](int i) {
+    if (i >= nsteps) return;
+    const int s = step_of(i);
+    const int j0 = s * SB, len = min(SB, k - j0), j1 = j0 + len;
+    const T* D = P + j0 + (long long)j0 * m;
+    const int gl = UP ? j1 / SB : 0, gh = UP ? nblocks : s;
+    const int vlo = UP ? j1 : 0, vhi = UP ? (int)m : j0;
+    if (!H) {
+      if (tid < len) prefetch_l2(D + rank * SL + (long long)tid * m, SL);
+      for (int e = tid; e < (gh - gl) * SB; e += 1024) {
+        const int g = gl + (e >> 7), col = e & (SB - 1);
+        const int v0 = max(vlo, g * SB + rank * SL), v1 = min(vhi, g * SB + rank * SL + SL);
+        if (col < len && v1 > v0) prefetch_l2(P + v0 + (long long)(j0 + col) * m, v1 - v0);
+      }
+    } else {
+      constexpr int LINES = SB * (int)sizeof(T) / 128 + 1;   // 128-byte lines of one contiguous run (+1: not aligned)
+      for (int e = tid; e < SL * LINES; e += 1024) {
+        const int i2 = rank * SL + e / LINES, l = e % LINES;
+        if (i2 < len) {
+          const char* b = (const char*)(D + (long long)i2 * m);
+          const char* a = (const char*)((unsigned long long)b & ~127ull) + 128 * l;
+          if (a < b + len * sizeof(T)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a) : "memory");
+        }
+      }
+      for (int e = tid; e < (gh - gl) * SL * LINES; e += 1024) {
+        const int t = e / LINES, l = e % LINES;
+        const int v = (gl + (t >> 3)) * SB + rank * SL + (t & (SL - 1));
+        if (v >= vlo && v < vhi) {
+          const char* b = (const char*)((!UP || v < k) ? P + j0 + (long long)v * m : Q + j0 + (long long)(v - k) * k);
+          const char* a = (const char*)((unsigned long long)b & ~127ull) + 128 * l;
+          if (a < b + len * sizeof(T)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a) : "memory");
+        }
+      }
+    }
+  };
+  // pivot values of the first block: nobody has touched them in this launch
+  {
+    const int s = step_of(0), j0 = s * SB, len = min(SB, k - j0);
+    if (tid < len) ybuf[0][tid] = in[f.col0 + j0 + tid];
+    prefetch_step(0);
+    __syncthreads();
+  }
+  for (int i = 0; i < nsteps; ++i) {
+    const int s = step_of(i);
+    const int j0 = s * SB, len = min(SB, k - j0), j1 = j0 + len;
+    z128* zs = zbuf[i & 1];
+    prefetch_step(i + 1);
+    solve_slice(s, ybuf[i & 1], zs);
+    cluster.sync();                                   // z_s complete in every CTA
+    const bool more = i + 1 < nsteps;
+    const int gl = UP ? j1 / SB : 0, gh = UP ? nblocks : s;      // blocks with entries to update: [gl, gh)
+    const int vlo = UP ? j1 : 0, vhi = UP ? (int)m : j0;
+    const int gc = UP ? s + 1 : s - 1;                            // next pivot block
+    int skip = -1;
+    if (more) {
+      const int jn = gc * SB, lenn = min(SB, k - jn);
+      // entries of block gc that are pivots of the next step
+      update_critical(j0, len, gc, max(vlo, jn), min(vhi, jn + lenn), zs, ybuf[(i + 1) & 1], lenn);
+      cluster.barrier_arrive();
+      // (a block that holds both next-step pivots and contribution entries, k not a multiple of 128, is visited
+      //  again below for the latter)
+      if (UP && jn + lenn < min((int)m, jn + SB)) update_rest(j0, len, gc, gc + 1, -1, jn + lenn, vhi, zs);
+      skip = gc;
+    }
+    update_rest(j0, len, gl, gh, skip, vlo, vhi, zs);
+    if (more) cluster.barrier_wait();                 // y_{next} complete in every CTA
+  }
+}
+
+template <class T, bool H, bool UP>
+static void launch_sweep_slices(cudaStream_t st, int cnt, const Front* fronts, const int* lvl_front, int first,
+                                const T* fac, z128* in, z128* out, z128* cb) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(16 * cnt), 1, 1);
+  cfg.blockDim = dim3(1024, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 16;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static bool allowed = false;   // per instantiation
+  if (!allowed) {
+    LSA_CUDA(cudaFuncSetAttribute(k_sweep_slices<T, H, UP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    allowed = true;
+  }
+  LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_slices<T, H, UP>, fronts, lvl_front, first, fac, in, out, cb));
+}
+
 // Cluster width of a level: as many SMs per front as the level leaves free (one 1024-thread CTA per SM),
 // but no more than the front has 128-row chunks to hand out.
 static int cluster_width(int cnt, int max_rows, int num_sms, int max_width) {
@@ -1727,6 +2060,12 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
           continue;
         }
       }
+      if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {
+        launch_sweep_slices<T, H, true>(st, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
+        tr.mark("up_slices", d, 16, 16 * cnt, 1);
+        launches++;
+        continue;
+      }
       if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
         sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb, h.cluster_lookahead);
         tr.mark("up_cluster", d, csize, csize * cnt, 1);
@@ -1778,6 +2117,10 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       int max_mk = 0;
       for (int q = first; q < first + cnt; ++q) max_mk = std::max(max_mk, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
       if (streamed) {
+      } else if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {
+        launch_sweep_slices<T, H, false>(st, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
+        tr.mark("down_slices", d, 16, 16 * cnt, 1);
+        launches++;
       } else if (maxk > SB && max_mk <= h.cluster_max_rows && h.use_clusters) {
         int max_m = 0;
         for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k);
