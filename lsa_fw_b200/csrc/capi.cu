@@ -411,6 +411,8 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->stream_stages = (int)value;
   } else if (nm == "stream_flags") {
     h->stream_flags = (int)value & 7;
+  } else if (nm == "defer_cb") {
+    h->defer_cb = value != 0.0;
   } else if (nm == "cluster_slices") {
     h->cluster_slices = value != 0.0;
   } else if (nm == "cluster_lookahead") {
@@ -563,6 +565,7 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   drop_solve_graphs(*h);
   if (const char* e = getenv("LSA_SUBTREES")) h->use_subtrees = atoi(e) != 0;
   if (const char* e = getenv("LSA_CLUSTER_MAX_ROWS")) h->cluster_max_rows = atoi(e);
+  if (const char* e = getenv("LSA_DEFER_CB")) h->defer_cb = atoi(e) != 0;
   if (const char* e = getenv("LSA_CLUSTER_SLICES")) h->cluster_slices = atoi(e) != 0;
   if (const char* e = getenv("LSA_CLUSTER_LOOKAHEAD")) h->cluster_lookahead = atoi(e) != 0;
   if (const char* e = getenv("LSA_CLUSTER_MAX_WIDTH")) h->cluster_max_width = atoi(e);

@@ -153,6 +153,7 @@ struct lsa_handle_impl {
   };
   std::vector<SolveGraph> solve_graphs;
   bool use_graphs = true;
+  bool defer_cb = true;          // cluster up sweeps: contribution rows updated by one wide GEMV after the pivot steps
   bool cluster_slices = true;    // levels with <= 9 fronts: 16-CTA clusters sharing every 128-row block by 8-row slices
   bool cluster_lookahead = false; // cluster sweep with static chunk ownership, owner-only solves and split barriers (measured equal)
   int cluster_max_width = 16;   // CTAs per front in the cluster sweep (16 = non-portable cluster size)

@@ -325,6 +325,79 @@ __device__ __forceinline__ void prefetch_l2(const T* p, int count) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(a) : "memory");
 }
 
+// cb -= Off * z_front  once all pivots of the front are solved (up sweep of the tall fronts: the rows of the
+// contribution vector do not take part in the dependent chain of 128-pivot steps, so they are updated by ONE
+// wide GEMV afterwards instead of step by step).  N: Off = L21 = P[k:m, 0:k];  H: Off = U12^H, U12 = Q (k x r).
+// grid: (chunks of 32 contribution rows, fronts); block NW * 32.
+template <class T, bool H, int NW>
+__global__ void __launch_bounds__(NW * 32) k_up_off(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                 int first, const T* __restrict__ fac, const z128* __restrict__ zsol,
+                                                 z128* __restrict__ cb) {
+  constexpr int ROWS = 32;
+  constexpr int CHUNK = NW * 32;
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k, r = f.r;
+  const int r0 = blockIdx.x * ROWS;
+  if (r0 >= r) return;
+  const long long m = (long long)k + r;
+  const T* P = fac + f.p_off;
+  const T* Q = fac + f.q_off;
+  __shared__ z128 xs[CHUNK];
+  __shared__ z128 red[NW][ROWS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  z128 acc = mk(0, 0);
+  const int rowN = r0 + lane;
+  z128 accH[ROWS / NW];
+#pragma unroll
+  for (int q = 0; q < ROWS / NW; ++q) accH[q] = mk(0, 0);
+  for (int c0 = 0; c0 < k; c0 += CHUNK) {
+    const int len = min(CHUNK, k - c0);
+    __syncthreads();
+    if (tid < len) xs[tid] = zsol[f.col0 + c0 + tid];
+    __syncthreads();
+    if (!H) {
+      if (rowN < r) {
+        const T* a = P + k + rowN + (long long)c0 * m;
+#pragma unroll 8
+        for (int c = wid; c < len; c += NW) acc += a[(long long)c * m] * xs[c];
+      }
+    } else {
+      for (int cb0 = 0; cb0 < len; cb0 += 32) {
+        const int c = cb0 + lane;
+        if (c < len) {
+          const z128 xc = xs[c];
+#pragma unroll
+          for (int q = 0; q < ROWS / NW; ++q) {
+            const int j = r0 + wid + q * NW;
+            if (j < r) accH[q] += conj_(Q[c0 + c + (long long)j * k]) * xc;
+          }
+        }
+      }
+    }
+  }
+  if (!H) {
+    red[wid][lane] = acc;
+    __syncthreads();
+    if (tid < ROWS && r0 + tid < r) {
+      z128 sacc = red[0][tid];
+#pragma unroll 8
+      for (int q = 1; q < NW; ++q) sacc += red[q][tid];
+      cb[f.st0 + r0 + tid] -= sacc;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < ROWS / NW; ++q) {
+      z128 a = accH[q];
+      for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      }
+      const int j = r0 + wid + q * NW;
+      if (lane == 0 && j < r) cb[f.st0 + j] -= a;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- fused sweep steps
 //
 // One launch per 128-pivot step: every CTA first applies the explicitly inverted diagonal block to
@@ -475,7 +548,7 @@ __device__ __forceinline__ z128 ld_cg(const z128* p) {  // L2 read (data written
 template <class T, bool H, bool UP, int C>
 __global__ void __launch_bounds__(1024) k_sweep_cluster(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                         int first, const T* __restrict__ fac, z128* in, z128* out,
-                                                        z128* cb) {
+                                                        z128* cb, int pivots_only) {
   namespace cg = cooperative_groups;
   constexpr int NT = 1024, CG = NT / SB, NWARP = NT / 32;
   const int rank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
@@ -489,12 +562,13 @@ __global__ void __launch_bounds__(1024) k_sweep_cluster(const Front* __restrict_
   __shared__ z128 part[CG][SB];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nsteps = (k + SB - 1) / SB;
+  const long long mtop = (UP && pivots_only) ? (long long)k : m;   // rows of the step-by-step updates (up)
   // panel of step sp -> L2: the diagonal block (one rank) and this rank's row chunks
   auto prefetch_step = [&](int sp) {
     if (sp >= nsteps) return;
     const int pj0 = (UP ? sp : nsteps - 1 - sp) * SB;
     const int plen = min(SB, k - pj0), pj1 = pj0 + plen;
-    const int pn = UP ? (int)(m - pj1) : pj0;
+    const int pn = UP ? (int)(mtop - pj1) : pj0;
     if (rank == sp % C && tid < plen) prefetch_l2(P + pj0 + (long long)(pj0 + tid) * m, plen);
     const int q = tid >> 7, i = tid & (SB - 1);   // 8 chunks of 128 segments per pass
     for (int r0 = (rank + q * C) * SB; r0 < pn; r0 += 8 * C * SB) {
@@ -513,7 +587,7 @@ __global__ void __launch_bounds__(1024) k_sweep_cluster(const Front* __restrict_
     prefetch_step(s + 1);
     const int j0 = (UP ? s : nsteps - 1 - s) * SB;
     const int len = min(SB, k - j0), j1 = j0 + len;
-    const int nrows = UP ? (int)(m - j1) : j0;
+    const int nrows = UP ? (int)(mtop - j1) : j0;
     const T* D = P + j0 + (long long)j0 * m;
     if (tid < len) {
       // values written by peer CTAs in the previous step: read through L2
@@ -643,7 +717,7 @@ __global__ void __launch_bounds__(1024) k_sweep_cluster(const Front* __restrict_
 
 template <class T, bool H, bool UP, int C>
 static void launch_sweep_cluster(cudaStream_t st, int cnt, const Front* fronts, const int* lvl_front, int first, const T* fac,
-                                 z128* in, z128* out, z128* cb) {
+                                 z128* in, z128* out, z128* cb, int pivots_only) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(C * cnt), 1, 1);
   cfg.blockDim = dim3(1024, 1, 1);
@@ -663,7 +737,7 @@ static void launch_sweep_cluster(cudaStream_t st, int cnt, const Front* fronts, 
       allowed = true;
     }
   }
-  LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb));
+  LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb, pivots_only));
 }
 
 // ------------------------------------------------------------- cluster sweep with look-ahead (big fronts)
@@ -1125,8 +1199,8 @@ __global__ void __launch_bounds__(1024) k_sweep_slices(const Front* __restrict__
     const int s = step_of(i);
     const int j0 = s * SB, len = min(SB, k - j0), j1 = j0 + len;
     const T* D = P + j0 + (long long)j0 * m;
-    const int gl = UP ? j1 / SB : 0, gh = UP ? nblocks : s;
-    const int vlo = UP ? j1 : 0, vhi = UP ? (int)m : j0;
+    const int gl = UP ? j1 / SB : 0, gh = UP ? nsteps : s;
+    const int vlo = UP ? j1 : 0, vhi = UP ? k : j0;
     if (!H) {
       if (tid < len) prefetch_l2(D + rank * SL + (long long)tid * m, SL);
       for (int e = tid; e < (gh - gl) * SB; e += 1024) {
@@ -1170,8 +1244,10 @@ __global__ void __launch_bounds__(1024) k_sweep_slices(const Front* __restrict__
     solve_slice(s, ybuf[i & 1], zs);
     cluster.sync();                                   // z_s complete in every CTA
     const bool more = i + 1 < nsteps;
-    const int gl = UP ? j1 / SB : 0, gh = UP ? nblocks : s;      // blocks with entries to update: [gl, gh)
-    const int vlo = UP ? j1 : 0, vhi = UP ? (int)m : j0;
+    // up: pivot entries only -- the contribution rows are not on the dependent chain, k_up_off updates them
+    // with one wide GEMV once z is complete
+    const int gl = UP ? j1 / SB : 0, gh = UP ? nsteps : s;       // blocks with entries to update: [gl, gh)
+    const int vlo = UP ? j1 : 0, vhi = UP ? k : j0;
     const int gc = UP ? s + 1 : s - 1;                            // next pivot block
     int skip = -1;
     if (more) {
@@ -1179,9 +1255,6 @@ __global__ void __launch_bounds__(1024) k_sweep_slices(const Front* __restrict__
       // entries of block gc that are pivots of the next step
       update_critical(j0, len, gc, max(vlo, jn), min(vhi, jn + lenn), zs, ybuf[(i + 1) & 1], lenn);
       cluster.barrier_arrive();
-      // (a block that holds both next-step pivots and contribution entries, k not a multiple of 128, is visited
-      //  again below for the latter)
-      if (UP && jn + lenn < min((int)m, jn + SB)) update_rest(j0, len, gc, gc + 1, -1, jn + lenn, vhi, zs);
       skip = gc;
     }
     update_rest(j0, len, gl, gh, skip, vlo, vhi, zs);
@@ -1224,7 +1297,7 @@ static int cluster_width(int cnt, int max_rows, int num_sms, int max_width) {
 
 template <class T, bool H, bool UP>
 static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fronts, const int* lvl_front, int first,
-                          const T* fac, z128* in, z128* out, z128* cb, bool lookahead) {
+                          const T* fac, z128* in, z128* out, z128* cb, bool lookahead, int pivots_only = 0) {
   if (lookahead) {
     switch (csize) {
       case 1: launch_sweep_cluster2<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
@@ -1236,11 +1309,11 @@ static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fron
     return;
   }
   switch (csize) {
-    case 1: launch_sweep_cluster<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-    case 2: launch_sweep_cluster<T, H, UP, 2>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-    case 4: launch_sweep_cluster<T, H, UP, 4>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-    case 8: launch_sweep_cluster<T, H, UP, 8>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-    default: launch_sweep_cluster<T, H, UP, 16>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
+    case 1: launch_sweep_cluster<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb, pivots_only); break;
+    case 2: launch_sweep_cluster<T, H, UP, 2>(st, cnt, fronts, lvl_front, first, fac, in, out, cb, pivots_only); break;
+    case 4: launch_sweep_cluster<T, H, UP, 4>(st, cnt, fronts, lvl_front, first, fac, in, out, cb, pivots_only); break;
+    case 8: launch_sweep_cluster<T, H, UP, 8>(st, cnt, fronts, lvl_front, first, fac, in, out, cb, pivots_only); break;
+    default: launch_sweep_cluster<T, H, UP, 16>(st, cnt, fronts, lvl_front, first, fac, in, out, cb, pivots_only); break;
   }
 }
 
@@ -2064,12 +2137,29 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         launch_sweep_slices<T, H, true>(st, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
         tr.mark("up_slices", d, 16, 16 * cnt, 1);
         launches++;
+        if (max_r > 0) {
+          if (maxk > 512) k_up_off<T, H, 32><<<dim3(cdiv(max_r, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, cb);
+          else k_up_off<T, H, 8><<<dim3(cdiv(max_r, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, cb);
+          LSA_LAUNCH_CHECK();
+          tr.mark("up_off", d, 0, cdiv(max_r, 32), cnt);
+          launches++;
+        }
         continue;
       }
       if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
-        sweep_cluster<T, H, true>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb, h.cluster_lookahead);
-        tr.mark("up_cluster", d, csize, csize * cnt, 1);
+        // contribution rows deferred to one wide GEMV (not with the look-ahead variant, which owns whole chunks)
+        const int defer = (h.defer_cb && !h.cluster_lookahead && max_r > 0) ? 1 : 0;
+        const int cs = defer ? cluster_width(cnt, maxk, h.num_sms, h.cluster_max_width) : csize;
+        sweep_cluster<T, H, true>(st, cs, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb, h.cluster_lookahead, defer);
+        tr.mark("up_cluster", d, cs, cs * cnt, 1);
         launches++;
+        if (defer) {
+          if (maxk > 512) k_up_off<T, H, 32><<<dim3(cdiv(max_r, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, cb);
+          else k_up_off<T, H, 8><<<dim3(cdiv(max_r, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, cb);
+          LSA_LAUNCH_CHECK();
+          tr.mark("up_off", d, 0, cdiv(max_r, 32), cnt);
+          launches++;
+        }
         continue;
       }
 

@@ -490,13 +490,13 @@ def test_large_front_paths_match_scipy_solve():
     b = np.random.default_rng(3).standard_normal(pc.n) + 1j * np.random.default_rng(4).standard_normal(pc.n)
     xs = spla.splu(C).solve(b)
     base = dict(use_clusters=1, use_subtrees=0, use_graphs=1, use_stream=1, stream_min_fronts=96, stream_flags=3,
-                stream_small_rows=192, stream_stages=0, cluster_max_rows=8192, cluster_max_width=16, cluster_lookahead=0, cluster_slices=1)
+                stream_small_rows=192, stream_stages=0, cluster_max_rows=8192, cluster_max_width=16, cluster_lookahead=0, cluster_slices=1, defer_cb=1)
     variants = (dict(), dict(use_subtrees=1), dict(use_clusters=0, use_subtrees=1), dict(use_clusters=0, use_graphs=0),
                 dict(use_stream=0), dict(use_stream=0, use_clusters=0, cluster_max_rows=0),
                 dict(stream_min_fronts=1), dict(stream_min_fronts=1, stream_flags=0, stream_stages=2),
                 dict(stream_min_fronts=1, stream_flags=7, stream_small_rows=0),
                 dict(stream_min_fronts=4, stream_flags=1, stream_small_rows=100000, stream_stages=12),
-                dict(cluster_max_rows=1280, cluster_max_width=4), dict(cluster_slices=0), dict(cluster_slices=0, cluster_lookahead=1),
+                dict(cluster_max_rows=1280, cluster_max_width=4), dict(cluster_slices=0), dict(cluster_slices=0, defer_cb=0), dict(cluster_slices=0, cluster_lookahead=1),
                 dict(cluster_slices=0, cluster_lookahead=1, use_stream=0, cluster_max_width=4), dict(use_stream=0, use_graphs=0),
                 dict(use_stream=0, cluster_max_width=2), dict(use_stream=0, cluster_max_width=1),
                 dict(use_stream=0, cluster_max_width=8, use_graphs=0))
