@@ -139,7 +139,10 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
  *       blocks, bit 1 single-copy tiles for contiguous blocks, bit 2 LDGSTS producer (measured slower);
  *   "use_clusters" (default 1): sweep the remaining multi-step levels with one thread-block cluster per front;
  *       "cluster_max_width" (16): CTAs per cluster; "cluster_max_rows" (8192): taller fronts get one grid-wide
- *       launch per 128-pivot step instead; "cluster_lookahead" (0): look-ahead variant;
+ *       launch per 128-pivot step instead; "cluster_slices" (1): levels with <= 9 fronts use 16-CTA clusters that
+ *       share every 128-row block by 8-row slices (DSMEM all-gather of the solved entries); "defer_cb" (1): the
+ *       contribution rows are updated by one wide GEMV after the pivot steps; "cluster_lookahead" (0): look-ahead
+ *       variant of the chunk-owning cluster kernel;
  *   "ortho_refine_always" (default 0): second Gram-Schmidt pass for every basis column instead of SLEPc's
  *       refine-if-needed rule;
  *   "use_subtrees" (default 0): sweep the bottom of the tree with the persistent task-based kernel
