@@ -139,6 +139,15 @@ def test_options_and_pressure_placement_rule():
         h.set_option("coupled_fraction", 1.5)
     with pytest.raises(_lib.LsaError):
         h.set_option("no_such_option", 1.0)
+    # sweep tuning knobs (include/lsa_b200.h): accepted without a device, value-checked where it matters
+    for name, val in (("use_graphs", 0), ("use_clusters", 1), ("use_stream", 1), ("stream_min_fronts", 48),
+                      ("stream_small_rows", 0), ("stream_stages", 6), ("stream_flags", 7), ("cluster_max_rows", 4096),
+                      ("cluster_max_width", 8), ("cluster_slices", 0), ("cluster_lookahead", 1), ("defer_cb", 0),
+                      ("ortho_refine_always", 1), ("use_subtrees", 0)):
+        h.set_option(name, val)
+    for name, val in (("cluster_max_width", 3), ("stream_stages", 1), ("stream_stages", 13)):
+        with pytest.raises(_lib.LsaError):
+            h.set_option(name, val)
     h.set_option("use_graphs", 0)
     h.set_option("use_clusters", 0)
     h.set_option("use_subtrees", 0)
