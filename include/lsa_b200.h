@@ -181,7 +181,8 @@ int lsa_solve(lsa_handle* h, int32_t trans, const double* b, double* x, int32_t 
 int lsa_spmv(lsa_handle* h, int32_t which_matrix, int32_t trans, const double* x, double* y, int32_t on_device);
 
 /* -- eigensolve ------------------------------------------------------------------------------
- * lsa_eigs <- SLEPc.EPS.solve()  (Solver/utils.py:268-270): Krylov-Schur on OP with CGS2,
+ * lsa_eigs <- SLEPc.EPS.solve()  (Solver/utils.py:268-270): Krylov-Schur on OP, Gram-Schmidt with
+ * refinement if needed (up to 256 basis columns),
  * Rayleigh-Ritz, locking restart, purification, 2-norm normalisation, `which` ordering.          */
 int lsa_eigs(lsa_handle* h, const lsa_eigs_params* p, lsa_eigs_result* out);
 /* <- eps.getConverged / getEigenvalue / getEigenvector  (Solver/utils.py:272-297) */
