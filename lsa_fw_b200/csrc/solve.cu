@@ -985,7 +985,6 @@ __global__ void __launch_bounds__(1024) k_sweep_slices(const Front* __restrict__
   __shared__ z128 loc[SL];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nsteps = (k + SB - 1) / SB;
-  const int nblocks = (int)((m + SB - 1) / SB);
   const int row8 = lane & (SL - 1), csub = lane >> 3;   // N layout inside a warp: 8 rows x 4 columns
 
   // entry v of the front's vector: pivot entries live in `in`, the others in the contribution vector
