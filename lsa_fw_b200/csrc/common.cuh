@@ -96,6 +96,19 @@ struct CudaError : std::runtime_error {
 
 #define LSA_LAUNCH_CHECK() LSA_CUDA(cudaGetLastError())
 
+// Function attributes (opt-in shared memory, non-portable cluster size) belong to the device a kernel is loaded
+// on: `first()` is true once per device and call site, so a process that drives several GPUs sets them on each.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace lsa

@@ -652,11 +652,10 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
   }
 
   const size_t swap_smem = (size_t)(NB * NB + 128 * (NB + 1)) * sizeof(T);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[scalar_traits<T>::is_complex]) {
+  static PerDeviceOnce attr_set;   // per instantiation (T)
+  if (attr_set.first()) {
     LSA_CUDA(cudaFuncSetAttribute(k_swap_trsm<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem));
     LSA_CUDA(cudaFuncSetAttribute(k_panel_lu<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_CAP));
-    attr_set[scalar_traits<T>::is_complex] = true;
   }
   constexpr int S = scalar_traits<T>::is_complex ? 2 : 1;
   constexpr int YMAX = 32768;

@@ -682,11 +682,9 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   if (p.adjoint) sigma = conj_(sigma);
 
   {
-    static bool gemm_attr = false;
-    if (!gemm_attr) {
+    static PerDeviceOnce gemm_attr;
+    if (gemm_attr.first())
       LSA_CUDA(cudaFuncSetAttribute(k_basis_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * 33 * (int)sizeof(z128)));
-      gemm_attr = true;
-    }
   }
   EventTimer t_all(st), t_spmv(st), t_solve(st), t_ortho(st), t_rr(st), t_restart(st);
   const long long launches0 = h.launch_count;
@@ -759,11 +757,9 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
     {
       const size_t rr_smem = sizeof(z128) * ((size_t)(m + 1) * m + (size_t)m * m);
       const int use_smem = rr_smem <= 210 * 1024;
-      static bool rr_attr = false;
-      if (use_smem && !rr_attr) {
+      static PerDeviceOnce rr_attr;
+      if (use_smem && rr_attr.first())
         LSA_CUDA(cudaFuncSetAttribute(k_rr, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-        rr_attr = true;
-      }
       k_rr<<<1, 128, use_smem ? rr_smem : 0, st>>>(S, Q, rp, h.d_theta, h.d_resid, h.d_brow, h.d_ywork, h.d_rr, use_smem);
     }
     LSA_LAUNCH_CHECK();

@@ -164,12 +164,10 @@ void post_factor(lsa_handle_impl& h, int* n_kernels) {
         LSA_LAUNCH_CHECK();
       }
       if (maxk > 64) {
-        static bool attr_done[2] = {false, false};
-        if (!attr_done[scalar_traits<T>::is_complex]) {
+        static PerDeviceOnce attr_done;   // per instantiation (T)
+        if (attr_done.first())
           LSA_CUDA(cudaFuncSetAttribute(k_merge_inv<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(64 * 64 * sizeof(T))));
-          attr_done[scalar_traits<T>::is_complex] = true;
-        }
         k_merge_inv<T, 64><<<dim3(cdiv(maxk, 128), cnt), 256, 64 * 64 * sizeof(T), st>>>(h.d_fronts, s0, (T*)h.d_fac);
         LSA_LAUNCH_CHECK();
       }
@@ -731,11 +729,9 @@ static void launch_sweep_cluster(cudaStream_t st, int cnt, const Front* fronts, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (C > 8) {
-    static bool allowed = false;   // per instantiation
-    if (!allowed) {
+    static PerDeviceOnce allowed;   // per instantiation
+    if (allowed.first())
       LSA_CUDA(cudaFuncSetAttribute(k_sweep_cluster<T, H, UP, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      allowed = true;
-    }
   }
   LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb, pivots_only));
 }
@@ -944,11 +940,9 @@ static void launch_sweep_cluster2(cudaStream_t st, int cnt, const Front* fronts,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (C > 8) {
-    static bool allowed = false;   // per instantiation
-    if (!allowed) {
+    static PerDeviceOnce allowed;   // per instantiation
+    if (allowed.first())
       LSA_CUDA(cudaFuncSetAttribute(k_sweep_cluster2<T, H, UP, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      allowed = true;
-    }
   }
   LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster2<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb));
 }
@@ -1276,11 +1270,9 @@ static void launch_sweep_slices(cudaStream_t st, int cnt, const Front* fronts, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static bool allowed = false;   // per instantiation
-  if (!allowed) {
+  static PerDeviceOnce allowed;   // per instantiation
+  if (allowed.first())
     LSA_CUDA(cudaFuncSetAttribute(k_sweep_slices<T, H, UP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    allowed = true;
-  }
   LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_slices<T, H, UP>, fronts, lvl_front, first, fac, in, out, cb));
 }
 
@@ -1785,12 +1777,10 @@ static bool launch_front_stream_t(lsa_handle_impl& h, cudaStream_t st, int cnt, 
   while (nstages > 2 && fixed + sizeof(z128) * (size_t)nstages * TILE > (size_t)STREAM_MAX_SMEM) --nstages;
   const size_t smem = fixed + sizeof(z128) * (size_t)nstages * TILE;
   if (smem > (size_t)STREAM_MAX_SMEM) return false;
-  static bool attr_done = false;   // per instantiation
-  static int occ_cache[2] = {0, 0};
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;   // per instantiation
+  static int occ_cache[2] = {0, 0};  // (shared-memory size, CTAs per SM): the same for every B200 of a node
+  if (attr_done.first())
     LSA_CUDA(cudaFuncSetAttribute(k_front_stream<H, UP, NCONS, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_MAX_SMEM));
-    attr_done = true;
-  }
   int occ = 0;
   if (occ_cache[0] == (int)smem) occ = occ_cache[1];
   else {
