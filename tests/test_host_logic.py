@@ -370,3 +370,26 @@ def test_run_sharded_gloo_world_size_2(tmp_path):
                          capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+# ------------------------------------------------------------------------------- bench contract (CPU arm)
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU and prints ONE JSON line with the keys the driver reads
+    (the oracle port is what it times; config 1 is the reference's own CPU-runnable case)."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "s" and d["higher_is_better"] is False
+    assert d["metric"].startswith("shift-invert eigensolve") and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "SuperLU" in cb["sample"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert abs(complex(*cb["sample_eig0"]) - (-0.030502986 + 0.738731056j)) < 1e-6     # same leading mode as the GPU path
