@@ -273,6 +273,37 @@ def test_gram_schmidt_refinement_if_needed_matches_always():
     h.close()
 
 
+def test_large_front_paths_real_factor():
+    """Same 3-D cavity with a REAL shift: real FP64 factor (the reference's real PETSc build) through the multi-step
+    kernels -- sliced / chunked cluster sweeps, deferred contribution rows, per-step launches; the streamed kernel is
+    complex-only, so the wide levels take the plain-load path here."""
+    import scipy.sparse.linalg as spla
+
+    pc = pencils.cavity_3d(8)
+    sigma = 0.1
+    h = _lib.Handle(pc.n, 0)
+    flag = ((pc.A.diagonal() - sigma * pc.M.diagonal()) == 0).astype(np.uint8)
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=flag)
+    assert info.max_pivots > 512
+    h.set_values(pc.A.data, pc.M.data)
+    C = (pc.A - sigma * pc.M).tocsc()
+    lu = spla.splu(C)
+    b = np.random.default_rng(5).standard_normal(pc.n) + 1j * np.random.default_rng(6).standard_normal(pc.n)
+    xs = lu.solve(b.real) + 1j * lu.solve(b.imag)
+    for opts in (dict(), dict(cluster_slices=0), dict(cluster_slices=0, defer_cb=0), dict(use_clusters=0),
+                 dict(cluster_slices=0, cluster_lookahead=1)):
+        for opt, val in dict(dict(cluster_slices=1, defer_cb=1, use_clusters=1, cluster_lookahead=0), **opts).items():
+            h.set_option(opt, val)
+        fs = h.factor(1.0, -sigma, _lib.LSA_F64, 1e-13)
+        assert fs.scalar == _lib.LSA_F64 and fs.n_perturbed == 0
+        x = h.solve(b)
+        assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-9
+        assert np.linalg.norm(C @ x - b) / np.linalg.norm(b) < 1e-12
+        xh = h.solve(b, _lib.LSA_OP_H)
+        assert np.linalg.norm(C.conj().T @ xh - b) / np.linalg.norm(b) < 1e-12
+    h.close()
+
+
 def test_result_buffers_are_page_locked_and_recycled():
     import gc
 
