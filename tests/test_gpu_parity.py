@@ -231,6 +231,28 @@ def test_adjoint_modes_reuse_the_factorisation():
     assert lam2 == pytest.approx(lam_adj, rel=EIG_RTOL)
 
 
+def test_direct_and_adjoint_modes_are_biorthonormal():
+    """Sensitivity/__init__.py:171-311 in one call: direct mode, adjoint mode on the same LU, a^H M v = 1, and
+    the classical bi-orthogonality a_i^H M v_j = 0 for i != j of a non-normal pencil."""
+    pc = pencils.assemble_pencil((24, 12), (8.0, 3.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.5))
+    sigma = 0.05 + 0.6j
+    A, M = L.iPETScMatrix(pc.A), L.iPETScMatrix(pc.M)
+    cfg = L.EigensolverConfig(num_eig=4, atol=1e-11, max_it=200, ncv=40)
+    (lam, v), (lam_adj, a) = L.direct_and_adjoint_modes(A, M, sigma, cfg, backend_options=dict(leaf_size=32))
+    assert abs(lam_adj - np.conj(lam)) < 1e-8 * abs(lam)
+    va, aa = _vec(v), _vec(a)
+    assert np.vdot(aa, pc.M @ va) == pytest.approx(1.0, abs=1e-10)
+    norm_a = float(np.sqrt((np.abs(pc.A.data) ** 2).sum()))
+    assert np.linalg.norm(pc.A.conj().T @ aa - lam_adj * (pc.M.conj().T @ aa)) / (norm_a * np.linalg.norm(aa)) < RESID_BAR
+    # the next direct mode is M-orthogonal to this adjoint mode
+    es = L.EigenSolver(A, M, cfg, check_hermitian=False)
+    es.solver.set_st_type(L.iSTType.SINVERT)
+    es.solver.set_target(sigma)
+    es.solver.set_backend_options(leaf_size=32)
+    others = [(l, _vec(x)) for l, x in es.solve() if abs(l - lam) > 1e-6]
+    assert others and all(abs(np.vdot(aa, pc.M @ x)) < 1e-7 * np.linalg.norm(aa) for _, x in others)
+
+
 def test_symbolic_analysis_is_reused_across_shifts_and_reynolds():
     L.clear_symbolic_cache()
     base = dict(shape=(24, 12), lengths=(8.0, 3.0), baseflow=pencils.wake_profile(0.9, 1.2, 1.5))

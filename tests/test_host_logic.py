@@ -393,3 +393,28 @@ def test_bench_reference_arm_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "SuperLU" in cb["sample"]
     assert "workload" in d["config"] and "model" not in d["config"]
     assert abs(complex(*cb["sample_eig0"]) - (-0.030502986 + 0.738731056j)) < 1e-6     # same leading mode as the GPU path
+
+
+# ------------------------------------------------------------------------------- sensitivity helpers (row f2)
+def test_select_mode_and_biorthonormal_scaling():
+    rng = np.random.default_rng(0)
+    n = 60
+    Md = sp.random(n, n, 0.15, random_state=3) + sp.eye(n)
+    M = L.iPETScMatrix(sp.csr_matrix(Md))
+    v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    a = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    # complex build (one complex vector, VecDot conjugates the argument): exactly a^H M v = 1
+    ac = L.iComplexPETScVector(L.iPETScVector.from_array(a.copy()))
+    prod = L.normalize_adjoint(ac, M, v)
+    assert prod == pytest.approx(np.conj(np.vdot(a, Md @ v)))
+    assert np.vdot(ac.as_array(), Md @ v) == pytest.approx(1.0, abs=1e-13)
+    # real build ((real, imag) pair, the dot conjugates self, Sensitivity/__init__.py:280-287 as written): modulus 1
+    ar = L.iComplexPETScVector.from_array(a.copy())
+    L.normalize_adjoint(ar, M, L.iComplexPETScVector.from_array(v))
+    assert abs(np.vdot(ar.as_array(), Md @ v)) == pytest.approx(1.0, abs=1e-13)
+    with pytest.raises(RuntimeError, match="Bi-orthonormal"):
+        L.normalize_adjoint(L.iComplexPETScVector(L.iPETScVector.from_array(a.copy())), M, np.zeros(n))
+    pairs = [(1 + 1j, "x"), (0.2 - 0.5j, "y"), (0.3 + 0.5j, "z")]
+    assert L.select_mode(pairs, 0.25 - 0.4j)[1] == "y" and L.select_mode(pairs, np.conj(0.25 - 0.4j))[1] == "z"
+    with pytest.raises(RuntimeError):
+        L.select_mode([], 0.0)
