@@ -6,11 +6,18 @@
 // Solver/eigen2.py:174-178).  The adjoint eigensolve of Sensitivity/__init__.py:246-262 re-factors
 // (A^H - conj(sigma) M^H); here it is the `trans = H` sweep over the SAME factors.
 //
-// Every kernel is HBM bound: one pass over L (forward) and one over U (backward), i.e.
-// nnz(L+U) * sizeof(T) bytes per solve plus the index vectors.  Launches are batched per assembly
-// tree level; within a front the pivot block is processed in 256-wide steps whose 32 x 32 diagonal
-// blocks were inverted after the factorisation, so a step is a short chain of small GEMVs instead
-// of a scalar substitution.
+// The work is HBM bound by nature: one pass over L (forward) and one over U (backward), i.e.
+// nnz(L+U) * sizeof(T) bytes per solve plus the index vectors.  Launches are batched per assembly tree level;
+// within a front the pivot block advances in 128-wide steps whose diagonal blocks were inverted explicitly
+// after the factorisation (32 -> 64 -> 128), so a step is one small GEMV instead of a scalar substitution.
+// Which kernel sweeps a level depends on its shape (solve_impl at the end of the file):
+//   many fronts (>= 96, or all fronts <= 128 pivots), complex   k_front_stream   bulk copies into a smem ring
+//   <= 9 tall fronts                                            k_sweep_slices   16-CTA clusters, 8-row slices
+//   10 .. 95 multi-step fronts                                  k_sweep_cluster  1-16 CTAs per front, by chunk
+//   fronts taller than cluster_max_rows, real wide levels       k_step           one launch per 128-pivot step
+//   rows outside the step chain                                 k_up_off / k_down_off (wide GEMVs)
+//   children -> parent contributions                            k_up_gather
+// Kept for comparison behind options: k_sweep_cluster2 (look-ahead), k_bottom (task based).
 //
 //   trans = N :  up sweep   y_top = L11^-1 P x_top ;  contrib  -= L21 y_top
 //                down sweep y_top = U11^-1 (y_top - U12 y_anc)
