@@ -3,7 +3,7 @@
  * The reference (ferdean/lsa-fw) has no FFI of its own: the seam is the Python class API
  * `Solver/eigen.py:48-155` + `Solver/utils.py:190-328`, whose numerical work is done by
  * slepc4py/petsc4py calls.  Each entry point below names the reference call it stands in
- * for; the Python host (lsa_fw_b200/backend.py) binds them with ctypes.  INTEGRATION.md shows
+ * for; the Python host (lsa_fw_b200/_lib.py, driven by lsa_fw_b200/utils.py) binds them with ctypes.  INTEGRATION.md shows
  * the stub a maintainer of the reference would add.
  *
  * Conventions: every function returns 0 on success, a negative lsa_status otherwise, with a
@@ -82,7 +82,9 @@ typedef struct {
   int32_t transform;       /* lsa_transform                                             */
   int32_t adjoint;         /* 1: left problem (A^H, M^H) at conj(sigma) on the SAME factors
                               (what Sensitivity/__init__.py:246-262 obtains by re-factorising) */
-  int32_t purify;          /* 1: one extra OP apply per Ritz vector (singular M)        */
+  int32_t purify;          /* singular M: Ritz vectors multiplied once by OP.  1: through the Krylov-Schur
+                              relation x = V y + v_next (b.y)/theta (no operator application, what SLEPc's
+                              EPSComputeVectors does); 2: one explicit OP apply per vector; 0: off */
   int32_t refine_steps;    /* iterative-refinement steps inside each OP apply           */
   double tol;              /* relative: beta |s_i| <= tol |theta_i|  (EigensolverConfig.atol is
                               handed to SLEPc as its relative tol, Solver/utils.py:236-238) */
@@ -138,15 +140,15 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
  *       "stream_stages" (0 = by level size, 2..12): ring depth; "stream_flags" (3): bit 0 wider tiles for narrow
  *       blocks, bit 1 single-copy tiles for contiguous blocks, bit 2 LDGSTS producer (measured slower);
  *   "use_clusters" (default 1): sweep the remaining multi-step levels with one thread-block cluster per front;
+ *       "invert_max_k" (4096): levels that are not streamed and whose pivot blocks are at most this wide get those
+ *       blocks inverted as a whole after the factorisation (one triangular matrix-vector product per front and
+ *       sweep, no dependent 128-pivot steps; 0 = off, wider blocks keep the step kernels below);
  *       "cluster_max_width" (16): CTAs per cluster; "cluster_max_rows" (8192): taller fronts get one grid-wide
  *       launch per 128-pivot step instead; "cluster_slices" (1): levels with <= 9 fronts use 16-CTA clusters that
  *       share every 128-row block by 8-row slices (DSMEM all-gather of the solved entries); "defer_cb" (1): the
- *       contribution rows are updated by one wide GEMV after the pivot steps; "cluster_lookahead" (0): look-ahead
- *       variant of the chunk-owning cluster kernel;
+ *       contribution rows are updated by one wide GEMV after the pivot steps;
  *   "ortho_refine_always" (default 0): second Gram-Schmidt pass for every basis column instead of SLEPc's
- *       refine-if-needed rule;
- *   "use_subtrees" (default 0): sweep the bottom of the tree with the persistent task-based kernel
- *       (kept for comparison: measured 2.7x - 7x slower than the level-synchronous sweep). */
+ *       refine-if-needed rule. */
 int lsa_set_option(lsa_handle* h, const char* name, double value);
 int lsa_symbolic_info_get(const lsa_handle* h, lsa_symbolic_info* out);
 /* Copies a named internal array (perm, iperm, sn_ptr, st_ptr, st_idx, ea_map, parent, level, front_k,

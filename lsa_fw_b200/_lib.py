@@ -206,6 +206,36 @@ _ARRAY_DTYPES = {
 }
 
 
+def device_pointer(obj):
+    """(raw device pointer, lsa_scalar, element count, keep-alive object) of a contiguous 1-D float64 /
+    complex128 array living on a CUDA device: torch tensor, `__cuda_array_interface__` exporter (CuPy, Numba)
+    or a `__dlpack__` exporter (imported through torch, zero copy)."""
+    if hasattr(obj, "__cuda_array_interface__") and not hasattr(obj, "data_ptr"):
+        cai = obj.__cuda_array_interface__
+        typestr = cai["typestr"]
+        if typestr not in ("<f8", "<c16"):
+            raise TypeError(f"device values must be float64 or complex128, got {typestr}")
+        if cai.get("strides") not in (None, (8 if typestr == "<f8" else 16,)):
+            raise ValueError("device values must be contiguous")
+        count = int(np.prod(cai["shape"])) if len(cai["shape"]) else 1
+        return int(cai["data"][0]), (LSA_C128 if typestr == "<c16" else LSA_F64), count, obj
+    if not hasattr(obj, "data_ptr") and hasattr(obj, "__dlpack__"):
+        import torch
+
+        obj = torch.from_dlpack(obj)
+    if hasattr(obj, "data_ptr"):
+        import torch
+
+        if not obj.is_cuda:
+            raise ValueError("expected a CUDA tensor (host arrays go through set_values)")
+        if obj.dtype not in (torch.float64, torch.complex128):
+            raise TypeError(f"device values must be float64 or complex128, got {obj.dtype}")
+        t = obj.contiguous().reshape(-1)
+        torch.cuda.current_stream(t.device).synchronize()   # the library reads on its own stream
+        return int(t.data_ptr()), (LSA_C128 if t.dtype == torch.complex128 else LSA_F64), int(t.numel()), t
+    raise TypeError("cannot take a device pointer from %r" % type(obj))
+
+
 class Handle:
     """Thin RAII wrapper over `lsa_handle*` (one solver object = one handle = one CUDA stream)."""
 
@@ -214,9 +244,17 @@ class Handle:
         self.n = int(n)
         self.device = device
         self._h = C.c_void_p()
+        # generations of the numeric state: solvers that share a handle (symbolic cache, adjoint reuse) check
+        # them before they trust factors / device-side results they did not just produce themselves
+        self.gen_factor = 0   # bumped by set_values and factor
+        self.gen_result = 0   # bumped by eigs (and by everything that bumps gen_factor)
         rc = self.lib.lsa_create(self.n, device, C.byref(self._h))
         if rc != 0:
             raise LsaError(rc, "cannot create a handle on CUDA device %d (no GPU? there is no CPU fallback)" % device)
+
+    @property
+    def closed(self) -> bool:
+        return not (getattr(self, "_h", None) is not None and self._h.value)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -284,10 +322,28 @@ class Handle:
             m_sc = LSA_C128 if np.iscomplexobj(m_vals) else LSA_F64
             m_vals = m_vals.astype(np.complex128 if m_sc else np.float64, copy=False)
             mp = m_vals.ctypes.data
+        self.gen_factor += 1
+        self.gen_result += 1
         self.check(self.lib.lsa_set_values(self._h, a_vals.ctypes.data, a_sc, mp, m_sc, 0))
+
+    def set_values_device(self, a_vals, m_vals=None) -> None:
+        """Values already resident on this handle's GPU, in the CSR entry order of the analysed pattern
+        (`on_device = 1` of the C ABI): torch CUDA tensors, CuPy arrays, anything with
+        `__cuda_array_interface__` or `__dlpack__` -- the hand-over of device-assembled matrices named in
+        BASELINE.json, replacing the reference's per-entry `setValue` loop (`FEM/utils.py:208-215`)."""
+        ap, a_sc, a_n, keep_a = device_pointer(a_vals)
+        mp, m_sc, keep_m = None, LSA_F64, None
+        if m_vals is not None:
+            mp, m_sc, m_n, keep_m = device_pointer(m_vals)
+        self.gen_factor += 1
+        self.gen_result += 1
+        self.check(self.lib.lsa_set_values(self._h, ap, a_sc, mp, m_sc, 1))
+        del keep_a, keep_m
 
     def factor(self, alpha: complex, beta: complex, scalar: int, tiny_pivot: float) -> FactorStats:
         st = FactorStats()
+        self.gen_factor += 1
+        self.gen_result += 1
         alpha, beta = complex(alpha), complex(beta)
         self.check(self.lib.lsa_factor(self._h, alpha.real, alpha.imag, beta.real, beta.imag, scalar,
                                        float(tiny_pivot), C.byref(st)))
@@ -298,6 +354,29 @@ class Handle:
         x = np.empty_like(b)
         self.check(self.lib.lsa_solve(self._h, trans, b.ctypes.data, x.ctypes.data, refine_steps, 0))
         return x
+
+    def solve_device(self, b, x, trans: int = LSA_OP_N, refine_steps: int = 0) -> None:
+        """x = F^-1 b with b, x complex128 device arrays of length n (`on_device = 1`); b may be x."""
+        bp, b_sc, b_n, kb = device_pointer(b)
+        xp, x_sc, x_n, kx = device_pointer(x)
+        if b_sc != LSA_C128 or x_sc != LSA_C128 or b_n != self.n or x_n != self.n:
+            raise ValueError("solve_device needs complex128 device vectors of length n")
+        self.check(self.lib.lsa_solve(self._h, trans, bp, xp, refine_steps, 1))
+
+    def spmv_device(self, which: int, x, y, trans: int = LSA_OP_N) -> None:
+        xp, x_sc, x_n, kx = device_pointer(x)
+        yp, y_sc, y_n, ky = device_pointer(y)
+        if x_sc != LSA_C128 or y_sc != LSA_C128 or x_n != self.n or y_n != self.n:
+            raise ValueError("spmv_device needs complex128 device vectors of length n")
+        self.check(self.lib.lsa_spmv(self._h, which, trans, xp, yp, 1))
+
+    def eigenvectors_device(self, out, count: int) -> int:
+        """Copies `count` eigenvectors into the complex128 device array `out` ((count, n) row-major = one
+        vector per row, i.e. column-major n x count as the C ABI has it).  Returns how many were written."""
+        op, o_sc, o_n, ko = device_pointer(out)
+        if o_sc != LSA_C128 or o_n < self.n * count:
+            raise ValueError("eigenvectors_device needs a complex128 device array of at least count * n entries")
+        return self.check(self.lib.lsa_get_eigenvectors(self._h, op, self.n, count, 1))
 
     def spmv(self, which: int, x: np.ndarray, trans: int = LSA_OP_N) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.complex128)
@@ -320,6 +399,7 @@ class Handle:
             keep = np.ascontiguousarray(v0, dtype=np.complex128)
             p.v0 = keep.ctypes.data_as(C.POINTER(C.c_double))
         res = EigsResult()
+        self.gen_result += 1
         self.check(self.lib.lsa_eigs(self._h, C.byref(p), C.byref(res)))
         return res
 

@@ -42,7 +42,7 @@ void free_csr(CsrDev& c) {
 
 void free_device(lsa_handle_impl& h) {
   drop_solve_graphs(h);
-  dfree(h.d_fronts); dfree(h.d_lvl_front); dfree(h.d_top_lvl_front); dfree(h.d_bot_list); dfree(h.d_is_bottom); dfree(h.d_bot_state); dfree(h.d_st_idx); dfree(h.d_ea_map); dfree(h.d_child_idx);
+  dfree(h.d_fronts); dfree(h.d_lvl_front); dfree(h.d_st_idx); dfree(h.d_ea_map); dfree(h.d_child_idx);
   dfree(h.d_a_dst); dfree(h.d_m_dst); dfree(h.d_perm); dfree(h.d_ipiv); dfree(h.d_gperm); dfree(h.d_stats);
   if (h.d_a_orig) cudaFree(h.d_a_orig);
   if (h.d_m_orig) cudaFree(h.d_m_orig);
@@ -51,6 +51,11 @@ void free_device(lsa_handle_impl& h) {
   if (h.d_fac) cudaFree(h.d_fac);
   h.d_fac = nullptr;
   h.fac_capacity_bytes = 0;
+  if (h.d_inv_scratch) cudaFree(h.d_inv_scratch);
+  h.d_inv_scratch = nullptr;
+  h.inv_scratch_bytes = h.inv_scratch_entries = 0;
+  dfree(h.d_inv_off);
+  h.solve_plan.clear();
   for (int q = 0; q < 2; ++q) {
     if (h.d_pool[q]) cudaFree(h.d_pool[q]);
     h.d_pool[q] = nullptr;
@@ -213,6 +218,8 @@ int fail(lsa_handle* h, int code, const std::string& msg) {
 #define LSA_API_END(h)                                             \
   }                                                                \
   catch (const lsa::CudaError& e) { return fail(h, LSA_ERR_CUDA, e.what()); } \
+  catch (const lsa::NonFiniteError& e) { return fail(h, LSA_ERR_NONFINITE, e.what()); } \
+  catch (const lsa::ArgError& e) { return fail(h, LSA_ERR_ARG, e.what()); } \
   catch (const std::bad_alloc&) { return fail(h, LSA_ERR_INTERNAL, "host out of memory"); } \
   catch (const std::exception& e) { return fail(h, LSA_ERR_INTERNAL, e.what()); }
 
@@ -313,14 +320,14 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   };
   auto build_dst = [&](const int64_t* rowptr, const int32_t* colidx, std::vector<long long>& dst) {
     dst.resize(rowptr[n]);
-    bool bad = false;
-#pragma omp parallel for schedule(dynamic, 512)
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 512) reduction(| : bad)
     for (int i = 0; i < n; ++i) {
       const int pi = sym.iperm[i];
       for (long long e = rowptr[i]; e < rowptr[i + 1]; ++e) {
         const int pj = sym.iperm[colidx[e]];
         if (pi < sym.n_iso || pj < sym.n_iso) {
-          if (pi != pj) bad = true;
+          if (pi != pj) bad |= 1;
           dst[e] = sym.diag_off + pi;
           continue;
         }
@@ -328,7 +335,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
         const Front& f = sym.fronts[s];
         const int lr = local_index(s, pi), lc = local_index(s, pj);
         if (lr < 0 || lc < 0) {
-          bad = true;
+          bad |= 1;
           continue;
         }
         const long long m = f.k + f.r;
@@ -351,10 +358,6 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     cudaStream_t st = h->stream;
     h->d_fronts = dupload(sym.fronts, st);
     h->d_lvl_front = dupload(sym.lvl_front, st);
-    h->d_top_lvl_front = dupload(sym.top_lvl_front, st);
-    h->d_bot_list = dupload(sym.bot_list, st);
-    h->d_is_bottom = dupload(sym.is_bottom, st);
-    h->d_bot_state = dalloc<int>((size_t)sym.ns + 2);
     {
       cudaDeviceProp prop;
       LSA_CUDA(cudaGetDeviceProperties(&prop, h->device));
@@ -375,7 +378,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     h->d_part = dalloc<z128>((size_t)1024 * 256);
     h->d_npart = dalloc<double>((size_t)cdiv(n, 256) + 1);
     h->d_h = dalloc<z128>(512);
-    h->d_flag = dalloc<int>(1);
+    h->d_flag = dalloc<int>(2);
     h->d_refine = dalloc<int>(2);
     h->d_wn2 = dalloc<double>(1024);
     h->d_ipart = dalloc<int>(256);
@@ -411,20 +414,19 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->stream_stages = (int)value;
   } else if (nm == "stream_flags") {
     h->stream_flags = (int)value & 7;
+  } else if (nm == "invert_max_k") {
+    if (value < 0 || value > 65536) return fail(h, LSA_ERR_ARG, "invert_max_k must lie in [0, 65536]");
+    h->invert_max_k = (int)value;
   } else if (nm == "defer_cb") {
     h->defer_cb = value != 0.0;
   } else if (nm == "cluster_slices") {
     h->cluster_slices = value != 0.0;
-  } else if (nm == "cluster_lookahead") {
-    h->cluster_lookahead = value != 0.0;
   } else if (nm == "cluster_max_rows") {
     h->cluster_max_rows = (int)value;
   } else if (nm == "cluster_max_width") {
     if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
       return fail(h, LSA_ERR_ARG, "cluster_max_width must be 1, 2, 4, 8 or 16");
     h->cluster_max_width = (int)value;
-  } else if (nm == "use_subtrees") {
-    h->use_subtrees = value != 0.0;
   } else {
     return fail(h, LSA_ERR_ARG, "unknown option " + nm);
   }
@@ -475,10 +477,6 @@ int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int
   if (nm == "ea_map") return give(s.ea_map.data(), s.ea_map.size(), 4);
   if (nm == "lvl_ptr") return give(s.lvl_ptr.data(), s.lvl_ptr.size(), 4);
   if (nm == "lvl_front") return give(s.lvl_front.data(), s.lvl_front.size(), 4);
-  if (nm == "bot_list") return give(s.bot_list.data(), s.bot_list.size(), 4);
-  if (nm == "is_bottom") return give(s.is_bottom.data(), s.is_bottom.size(), 4);
-  if (nm == "top_lvl_ptr") return give(s.top_lvl_ptr.data(), s.top_lvl_ptr.size(), 4);
-  if (nm == "top_lvl_front") return give(s.top_lvl_front.data(), s.top_lvl_front.size(), 4);
   if (nm == "a_dst") return give(s.a_dst.data(), s.a_dst.size(), 8);
   if (nm == "m_dst") return give(h->m_dst.data(), h->m_dst.size(), 8);
   if (nm == "parent") return from_fronts([](const Front& f) { return f.parent; }, 4);
@@ -563,11 +561,9 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   cudaEventRecord(e0, st);
   h->scalar = -1;
   drop_solve_graphs(*h);
-  if (const char* e = getenv("LSA_SUBTREES")) h->use_subtrees = atoi(e) != 0;
   if (const char* e = getenv("LSA_CLUSTER_MAX_ROWS")) h->cluster_max_rows = atoi(e);
   if (const char* e = getenv("LSA_DEFER_CB")) h->defer_cb = atoi(e) != 0;
   if (const char* e = getenv("LSA_CLUSTER_SLICES")) h->cluster_slices = atoi(e) != 0;
-  if (const char* e = getenv("LSA_CLUSTER_LOOKAHEAD")) h->cluster_lookahead = atoi(e) != 0;
   if (const char* e = getenv("LSA_CLUSTER_MAX_WIDTH")) h->cluster_max_width = atoi(e);
   if (const char* e = getenv("LSA_NO_STREAM")) h->use_stream = atoi(e) == 0;
   if (const char* e = getenv("LSA_STREAM_MIN_FRONTS")) h->stream_min_fronts = atoi(e);
@@ -580,6 +576,8 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   if (const char* e = getenv("LSA_NO_GRAPHS")) {
     if (atoi(e) != 0) h->use_graphs = false;
   }
+  if (const char* e = getenv("LSA_INVERT_MAX_K")) h->invert_max_k = atoi(e);
+  plan_solve(*h, scalar);
   if (scalar == LSA_C128) {
     factor_numeric<z128>(*h, alpha, beta, tiny_abs, &nk);
     post_factor<z128>(*h, &nk);
@@ -685,6 +683,8 @@ int lsa_eigs(lsa_handle* h, const lsa_eigs_params* p, lsa_eigs_result* out) {
   const bool needs_factor = p->transform == LSA_ST_SINVERT || h->has_m;
   if (needs_factor && h->scalar < 0) return fail(h, LSA_ERR_ARG, "lsa_eigs needs lsa_factor first");
   if (p->which < 1 || p->which > 9) return fail(h, LSA_ERR_ARG, "unsupported `which`");
+  if (std::min(p->ncv, h->n) > 256)
+    return fail(h, LSA_ERR_ARG, "ncv > 256: the device orthogonalisation / Rayleigh-Ritz kernels hold at most 256 basis columns");
   LSA_API_BEGIN
   const int ncv = std::max(1, std::min(p->ncv, h->n));
   ensure_krylov(*h, ncv);

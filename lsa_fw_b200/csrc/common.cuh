@@ -85,6 +85,12 @@ LSA_HD T cj(T a) {
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
+struct NonFiniteError : std::runtime_error {   // NaN / Inf met in the numeric path -> LSA_ERR_NONFINITE
+  using std::runtime_error::runtime_error;
+};
+struct ArgError : std::runtime_error {         // caller error detected below the C ABI -> LSA_ERR_ARG
+  using std::runtime_error::runtime_error;
+};
 
 #define LSA_CUDA(call)                                                                              \
   do {                                                                                              \

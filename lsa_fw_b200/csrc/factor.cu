@@ -396,7 +396,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 //   real    : A^ = A                                   (lda_r = lda)
 //   complex : rows/ld doubled (interleaved re,im);  A^[2i+a, 2k+b] = a==b ? Re A[i,k] : (a ? +Im : -Im)
 // CTA tile 64 x 64, 4 warps as 2 x 2, warp tile 32 x 32 = 4 x 4 m8n8k4 fragments, K chunk 16.
-template <bool CPLX>
+// AMASK / BMASK: the operand is a triangular matrix stored together with the other triangle of something else
+// (inverted pivot blocks: L11^-1 strictly below the diagonal, U11^-1 on and above it): 1 = unit lower, 2 = upper,
+// applied while loading (element coordinates relative to the operand's origin).
+// EPI: 0  C -= acc ;  1  C = -acc ;  2  C = acc.
+template <bool CPLX, int AMASK = 0, int BMASK = 0, int EPI = 0>
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long long lda_r, const double* __restrict__ B,
                                           long long ldb_r, double* __restrict__ C, long long ldc_r, int Mr, int N,
                                           int Kr, int m0, int n0) {
@@ -431,13 +435,25 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
 #pragma unroll
     for (int q = 0; q < A_PER_T; ++q) {
       const int ka = a_kg * A_PER_T + q;
-      ra[q] = (rok && (ka0 + ka) < ka_lim) ? __ldg(A + (m0 + a_row) + (long long)(ka0 + ka) * lda_r) : 0.0;
+      double v = (rok && (ka0 + ka) < ka_lim) ? __ldg(A + (m0 + a_row) + (long long)(ka0 + ka) * lda_r) : 0.0;
+      if (AMASK != 0) {
+        const int ci = CPLX ? (m0 + a_row) >> 1 : (m0 + a_row), ck = ka0 + ka;   // element (ci, ck) of the operand
+        if (AMASK == 1) v = ci > ck ? v : (ci == ck && (!CPLX || ((m0 + a_row) & 1) == 0) && rok) ? 1.0 : 0.0;
+        else v = ci <= ck ? v : 0.0;
+      }
+      ra[q] = v;
     }
     const bool nok = (n0 + b_n) < N;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int kk = k0 + b_kh + q;
-      rb[q] = (nok && kk < Kr) ? __ldg(B + kk + (long long)(n0 + b_n) * ldb_r) : 0.0;
+      double v = (nok && kk < Kr) ? __ldg(B + kk + (long long)(n0 + b_n) * ldb_r) : 0.0;
+      if (BMASK != 0) {
+        const int ck = CPLX ? kk >> 1 : kk, cn = n0 + b_n;
+        if (BMASK == 1) v = ck > cn ? v : (ck == cn && (!CPLX || (kk & 1) == 0) && nok && kk < Kr) ? 1.0 : 0.0;
+        else v = ck <= cn ? v : 0.0;
+      }
+      rb[q] = v;
     }
   };
   auto store_smem = [&](int buf) {
@@ -490,11 +506,11 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
       const int c0 = n0 + wn * 32 + nf * 8 + tg * 2;
       if (c0 < N) {
         double* p = C + R + (long long)c0 * ldc_r;
-        *p -= acc[mf][nf][0];
+        *p = EPI == 0 ? *p - acc[mf][nf][0] : EPI == 1 ? -acc[mf][nf][0] : acc[mf][nf][0];
       }
       if (c0 + 1 < N) {
         double* p = C + R + (long long)(c0 + 1) * ldc_r;
-        *p -= acc[mf][nf][1];
+        *p = EPI == 0 ? *p - acc[mf][nf][1] : EPI == 1 ? -acc[mf][nf][1] : acc[mf][nf][1];
       }
     }
   }
@@ -578,6 +594,63 @@ __global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fr
                       r * S, r, k * S, (t % tm1) * 64, (t / tm1) * 64);
   }
 }
+
+// ------------------------------------------------------ merging inverted diagonal blocks (post-factor)
+//
+// Two adjacent HB x HB diagonal blocks of a pivot block whose triangular inverses are known (A at j0, D at
+// jd = j0 + HB; each holds L^-1 strictly below and U^-1 on/above its diagonal) are merged into the inverse of
+// the 2 HB block in place:   lower  X = -D_l^-1 C A_l^-1   (C = P[jd.., j0..]),   upper  Y = -A_u^-1 B D_u^-1.
+// Each product is two GEMMs through a scratch block T:  phase 1  T = C A_l^-1 / T = B D_u^-1,
+// phase 2  X = -D_l^-1 T / Y = -A_u^-1 T.  grid: (tiles, block pairs, fronts of the batch).
+// Extends the 32 -> 64 -> 128 merges of solve.cu to whole pivot blocks: a front then needs ONE triangular
+// matrix-vector product per sweep instead of a chain of dependent 128-pivot steps.
+template <class T, int PHASE, bool UPPER>
+__global__ void __launch_bounds__(128) k_inv_merge(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, const long long* __restrict__ scr_off, int HB,
+                                                   T* __restrict__ fac, T* __restrict__ scratch) {
+  constexpr bool CPLX = scalar_traits<T>::is_complex;
+  constexpr int S = CPLX ? 2 : 1;
+  const Front f = fronts[lvl_front[first + blockIdx.z]];
+  const int k = f.k;
+  const int j0 = blockIdx.y * 2 * HB, jd = j0 + HB;
+  if (jd >= k) return;
+  const int hd = min(HB, k - jd);
+  const long long m = (long long)k + f.r;
+  T* P = fac + f.p_off;
+  T* Tm = scratch + scr_off[blockIdx.z] + (long long)blockIdx.y * 2 * HB * HB + (UPPER ? (long long)HB * HB : 0);
+  const int Mrows = UPPER ? HB : hd, Ncols = UPPER ? hd : HB;
+  const int tm = (Mrows * S + 63) / 64, tn = (Ncols + 63) / 64;
+  const int t = blockIdx.x;
+  if (t >= tm * tn) return;
+  const int m0 = (t % tm) * 64, n0 = (t / tm) * 64;
+  const double* Ablk = (const double*)(P + j0 + (long long)j0 * m);
+  const double* Dblk = (const double*)(P + jd + (long long)jd * m);
+  double* Cblk = (double*)(P + jd + (long long)j0 * m);   // below the diagonal
+  double* Bblk = (double*)(P + j0 + (long long)jd * m);   // above the diagonal
+  if (PHASE == 1) {
+    if (!UPPER) gemm_tile<CPLX, 0, 1, 2>(Cblk, m * S, Ablk, m * S, (double*)Tm, (long long)HB * S, hd * S, HB, HB * S, m0, n0);
+    else gemm_tile<CPLX, 0, 2, 2>(Bblk, m * S, Dblk, m * S, (double*)Tm, (long long)HB * S, HB * S, hd, hd * S, m0, n0);
+  } else {
+    if (!UPPER) gemm_tile<CPLX, 1, 0, 1>(Dblk, m * S, (const double*)Tm, (long long)HB * S, Cblk, m * S, hd * S, HB, hd * S, m0, n0);
+    else gemm_tile<CPLX, 2, 0, 1>(Ablk, m * S, (const double*)Tm, (long long)HB * S, Bblk, m * S, HB * S, hd, HB * S, m0, n0);
+  }
+}
+
+template <class T>
+void launch_inv_merge(cudaStream_t st, const Front* fronts, const int* lvl_front, int first, int cnt, const long long* scr_off,
+                      int HB, int maxk, T* fac, T* scratch) {
+  constexpr int S = scalar_traits<T>::is_complex ? 2 : 1;
+  const int pairs = cdiv(maxk, 2 * HB);
+  const int tiles = cdiv((long long)HB * S, 64) * cdiv(HB, 64);
+  const dim3 grid(tiles, pairs, cnt);
+  k_inv_merge<T, 1, false><<<grid, 128, 0, st>>>(fronts, lvl_front, first, scr_off, HB, fac, scratch);
+  k_inv_merge<T, 1, true><<<grid, 128, 0, st>>>(fronts, lvl_front, first, scr_off, HB, fac, scratch);
+  k_inv_merge<T, 2, false><<<grid, 128, 0, st>>>(fronts, lvl_front, first, scr_off, HB, fac, scratch);
+  k_inv_merge<T, 2, true><<<grid, 128, 0, st>>>(fronts, lvl_front, first, scr_off, HB, fac, scratch);
+  LSA_LAUNCH_CHECK();
+}
+template void launch_inv_merge<double>(cudaStream_t, const Front*, const int*, int, int, const long long*, int, int, double*, double*);
+template void launch_inv_merge<z128>(cudaStream_t, const Front*, const int*, int, int, const long long*, int, int, z128*, z128*);
 
 // stand-alone GEMM used by lsa_gemm_bench (same tile code as the front updates)
 template <bool CPLX>

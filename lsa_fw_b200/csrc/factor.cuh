@@ -63,6 +63,8 @@ void gemm_plain(cudaStream_t st, bool cplx, const void* A, long long lda, const 
 template <class T>
 void solve_permuted(lsa_handle_impl& h, int trans, z128* x, int* n_kernels);
 
+void plan_solve(lsa_handle_impl& h, int scalar);   // solve.cu: level plan of the sweeps, before post_factor
+
 // krylov.cu
 void spmv(lsa_handle_impl& h, const CsrDev& M, bool conj_vals, const z128* x, z128* y);
 void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out);

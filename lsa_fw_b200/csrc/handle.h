@@ -44,6 +44,14 @@ struct RrInfo {
   int pad;
 };
 
+// Sweep plan: which kernel family handles a chunk of a tree level (solve.cu)
+enum SolveMode { SOLVE_STREAM = 0, SOLVE_INVERTED = 1, SOLVE_STEPS = 2 };
+struct SolveChunk {
+  int level, first, cnt;    // position in lvl_front
+  int maxk, max_r, max_m;   // extents over the chunk's fronts
+  int mode;                 // SolveMode
+};
+
 struct Launch {
   int kind;   // see factor.cu
   int level;
@@ -69,10 +77,6 @@ struct lsa_handle_impl {
   // ---- device plan
   Front* d_fronts = nullptr;
   int* d_lvl_front = nullptr;
-  int* d_top_lvl_front = nullptr;
-  int* d_bot_list = nullptr;
-  int* d_is_bottom = nullptr;
-  int* d_bot_state = nullptr;   // [0] up queue, [1] down queue, [2 + s] completion flag of front s
   int num_sms = 148;
   int* d_st_idx = nullptr;
   int* d_ea_map = nullptr;
@@ -152,10 +156,14 @@ struct lsa_handle_impl {
     int launches;
   };
   std::vector<SolveGraph> solve_graphs;
+  std::vector<SolveChunk> solve_plan;   // levels in root-to-leaf order, rebuilt at every factorisation
+  int invert_max_k = 4096;              // levels whose pivot blocks are at most this wide get them inverted as a whole
+  void* d_inv_scratch = nullptr;        // scratch of the block-inverse merges
+  long long inv_scratch_bytes = 0, inv_scratch_entries = 0;
+  long long* d_inv_off = nullptr;       // per-front scratch offsets of the current batch
   bool use_graphs = true;
   bool defer_cb = true;          // cluster up sweeps: contribution rows updated by one wide GEMV after the pivot steps
   bool cluster_slices = true;    // levels with <= 9 fronts: 16-CTA clusters sharing every 128-row block by 8-row slices
-  bool cluster_lookahead = false; // cluster sweep with static chunk ownership, owner-only solves and split barriers (measured equal)
   int cluster_max_width = 16;   // CTAs per front in the cluster sweep (16 = non-portable cluster size)
   int cluster_max_rows = 8192;  // fronts taller than this are swept with one grid-wide launch per step (measured optimum)
   bool use_stream = true;     // single-step levels: bulk-copy/mbarrier streamed kernel (complex factors)
@@ -164,7 +172,6 @@ struct lsa_handle_impl {
   int stream_small_rows = 192; // levels whose fronts have at most this many rows use the small-CTA variant
   int stream_min_fronts = 96; // multi-step levels with at least this many fronts are streamed too (one CTA per front)
   bool use_clusters = true;
-  bool use_subtrees = false;  // sweep the bottom of the tree with the persistent task-based kernel (measured slower)   // sweep multi-step levels with thread-block clusters (one launch per level)
   double coupled_fraction = 0.5;
 };
 

@@ -164,13 +164,15 @@ __global__ void k_sub(int n, const z128* __restrict__ a, const z128* __restrict_
 
 // ------------------------------------------------------------------------------------- CGS2 kernels
 
-static constexpr int DOT_ROWS = 32;   // row lanes
-static constexpr int DOT_CG = 8;      // column groups
-static constexpr int MAXC_PER = 16;   // columns per thread -> up to 128 basis vectors
+static constexpr int DOT_CG = 8;      // column groups (warps per block)
 
-// part[blk * ldp + c] = sum over the block's rows of conj(V[i, c]) w[i],  c0 <= c < min(j, c0 + 128)
+// part[blk * ldp + c] = sum over the block's rows of conj(V[i, c]) w[i],  c0 <= c < min(j, c0 + 8 NQ)
 // wn2 (optional): wn2[blk] = sum over the block's rows of |w[i]|^2.  skip (optional): *skip == 0 -> nothing to do
-// (second CGS pass that the refinement criterion did not ask for).
+// (second Gram-Schmidt pass that the refinement criterion did not ask for).
+// Warp = column group (columns c0 + warp + 8 q), lanes along rows (512-byte coalesced reads of a column); every
+// thread issues the U x NQ column loads of U row slabs before it uses any of them, so narrow bases (few columns
+// per thread) still keep ~16 independent 16-byte loads per thread in flight.
+template <int NQ, int U>
 __global__ void __launch_bounds__(256) k_dots(int n, int j, int c0, const z128* __restrict__ V, long long ldv,
                                               const z128* __restrict__ w, z128* __restrict__ part, int ldp,
                                               int rows_per_block, double* __restrict__ wn2, const int* __restrict__ skip) {
@@ -178,17 +180,28 @@ __global__ void __launch_bounds__(256) k_dots(int n, int j, int c0, const z128* 
   const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min((long long)n, r0 + rows_per_block);
-  z128 acc[MAXC_PER];
+  z128 acc[NQ];
 #pragma unroll
-  for (int q = 0; q < MAXC_PER; ++q) acc[q] = mk(0, 0);
+  for (int q = 0; q < NQ; ++q) acc[q] = mk(0, 0);
   double wacc = 0.0;
-  for (long long i = r0 + lane; i < r1; i += DOT_ROWS) {
-    const z128 wi = w[i];
-    wacc += abs2(wi);
+  for (long long i = r0 + lane; i < r1; i += 32 * U) {
+    z128 wi[U], v[U][NQ];
 #pragma unroll
-    for (int q = 0; q < MAXC_PER; ++q) {
-      const int c = c0 + cg + q * DOT_CG;
-      if (c < j) acc[q] += conj_(V[i + c * ldv]) * wi;
+    for (int u = 0; u < U; ++u) {
+      const long long ii = i + 32 * u;
+      const bool ok = ii < r1;
+      wi[u] = ok ? w[ii] : mk(0, 0);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = c0 + cg + q * DOT_CG;
+        v[u][q] = (ok && c < j) ? V[ii + c * ldv] : mk(0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      wacc += abs2(wi[u]);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[q] += conj_(v[u][q]) * wi[u];
     }
   }
   if (wn2 && cg == 0) {
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(256) k_dots(int n, int j, int c0, const z128* 
     if (lane == 0) wn2[blockIdx.x] = wacc;
   }
 #pragma unroll
-  for (int q = 0; q < MAXC_PER; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const int c = c0 + cg + q * DOT_CG;
     if (c < j) {
       z128 a = acc[q];
@@ -206,6 +219,20 @@ __global__ void __launch_bounds__(256) k_dots(int n, int j, int c0, const z128* 
       }
       if (lane == 0) part[(long long)blockIdx.x * ldp + c] = a;
     }
+  }
+}
+
+// All partial dot products of w against V[:, 0:j]: chunks of up to 128 columns, columns per thread by chunk width.
+static void launch_dots(cudaStream_t st, int nblk, int n, int j, const z128* V, long long ldv, const z128* w, z128* part,
+                        int ldp, int rows_per_block, double* wn2, const int* skip) {
+  for (int c0 = 0; c0 < j; c0 += 128) {
+    const int cols = std::min(128, j - c0);
+    double* wn = c0 == 0 ? wn2 : nullptr;
+    if (cols <= 16) k_dots<2, 8><<<nblk, 256, 0, st>>>(n, j, c0, V, ldv, w, part, ldp, rows_per_block, wn, skip);
+    else if (cols <= 32) k_dots<4, 4><<<nblk, 256, 0, st>>>(n, j, c0, V, ldv, w, part, ldp, rows_per_block, wn, skip);
+    else if (cols <= 64) k_dots<8, 2><<<nblk, 256, 0, st>>>(n, j, c0, V, ldv, w, part, ldp, rows_per_block, wn, skip);
+    else if (cols <= 96) k_dots<12, 2><<<nblk, 256, 0, st>>>(n, j, c0, V, ldv, w, part, ldp, rows_per_block, wn, skip);
+    else k_dots<16, 1><<<nblk, 256, 0, st>>>(n, j, c0, V, ldv, w, part, ldp, rows_per_block, wn, skip);
   }
 }
 
@@ -305,7 +332,7 @@ __global__ void __launch_bounds__(256) k_norm2_part(int n, const z128* __restric
 
 // beta = sqrt(sum npart); out = w / beta.  Every block re-reduces the partials in the same order
 // (deterministic).  Block 0 stores beta (to *beta_out, and to *s_entry as a complex number) and
-// flags a breakdown (beta tiny relative to hnorm_ref) in *flag.
+// flags a breakdown (beta tiny relative to hnorm_ref) in flag[0] and a non-finite norm in flag[1].
 __global__ void __launch_bounds__(256) k_normalize(int n, const z128* __restrict__ w, z128* __restrict__ out,
                                                    const double* __restrict__ npart, int nparts,
                                                    double* __restrict__ beta_out, z128* __restrict__ s_entry,
@@ -326,12 +353,16 @@ __global__ void __launch_bounds__(256) k_normalize(int n, const z128* __restrict
     double hn = 0.0;
     for (int c = 0; c < hlen; ++c) hn += abs2(hcol[c]);
     hn = sqrt(hn);
-    const bool brk = !(beta > 1e-13 * fmax(hn, 1e-300)) || !(beta == beta);
+    // NaN / Inf in the new direction or in its Gram-Schmidt coefficients is NOT a breakdown: it is reported
+    // through flag[1] and ends the solve with LSA_ERR_NONFINITE
+    const bool bad = !(beta == beta) || isinf(beta) || !(hn == hn) || isinf(hn);
+    const bool brk = bad || !(beta > 1e-13 * fmax(hn, 1e-300));
     s_break = brk;
     if (blockIdx.x == 0) {
       if (beta_out) *beta_out = beta;
       if (s_entry) *s_entry = mk(brk ? 0.0 : beta, 0.0);
       if (brk && flag) atomicMin(flag, step);
+      if (bad && flag) flag[1] = 1;
     }
   }
   __syncthreads();
@@ -446,11 +477,16 @@ void dense_schur_device(lsa_handle_impl& h, int m, z128* dS, int ld, z128* dQ, i
 }
 
 // Eigenvectors of the leading nc x nc triangle of S: column c of Y (nc x nc, ld = ldy), unit 2-norm.
-__global__ void k_ritz_vectors(const z128* __restrict__ S, int ld, int nc, z128* __restrict__ Y, int ldy) {
+// With brow != nullptr Y gets one more row, Y[nc, c] = (b . y_c) / theta_c  (b = coupling row of the Krylov-Schur
+// relation  OP V = V S + v_next b^T):  V y + v_next (b . y) / theta  =  OP (V y) / theta, i.e. the purified Ritz
+// vector (one multiplication by OP, which removes components outside range(OP) when M is singular) at no
+// extra operator application -- what EPSComputeVectors does in SLEPc's Krylov-Schur.
+__global__ void k_ritz_vectors(const z128* __restrict__ S, int ld, int nc, z128* __restrict__ Y, int ldy,
+                               const z128* __restrict__ brow) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
   z128* y = Y + (long long)c * ldy;
-  for (int i = c + 1; i < nc; ++i) y[i] = mk(0, 0);
+  for (int i = c + 1; i < nc + (brow ? 1 : 0); ++i) y[i] = mk(0, 0);
   // brow unused: pass a zero row through y itself is not possible, so replicate the substitution here
   const z128 tkk = S[c + (long long)c * ld];
   double smax = 0.0;
@@ -468,6 +504,11 @@ __global__ void k_ritz_vectors(const z128* __restrict__ S, int ld, int nc, z128*
   for (int i = 0; i <= c; ++i) nrm2 += abs2(y[i]);
   const double inv = 1.0 / sqrt(nrm2);
   for (int i = 0; i <= c; ++i) y[i] = y[i] * inv;
+  if (brow) {
+    z128 dot = mk(0, 0);
+    for (int i = 0; i <= c; ++i) dot += brow[i] * y[i];
+    y[nc] = (tkk.x != 0.0 || tkk.y != 0.0) ? dot / tkk : mk(0, 0);
+  }
 }
 
 // ---- phase normalisation of a Ritz vector: rotate so that its largest component is real positive
@@ -668,7 +709,6 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   cudaStream_t st = h.stream;
   const int ncv = std::max(1, std::min(p.ncv, n));
   const int nev = std::max(1, std::min(p.nev, n));
-  if (ncv > 256) throw std::runtime_error("ncv > 256 is not supported by the orthogonalisation kernels");
   const int ld = ncv + 1;
   const int blocks = cdiv(n, 256);
   z128* V = h.d_V;
@@ -692,8 +732,8 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
 
   LSA_CUDA(cudaMemsetAsync(S, 0, sizeof(z128) * (size_t)ld * ncv, st));
   LSA_CUDA(cudaMemsetAsync(h.d_refine, 0, 2 * sizeof(int), st));
-  int h_flag = 0x7fffffff;
-  LSA_CUDA(cudaMemcpyAsync(h.d_flag, &h_flag, sizeof(int), cudaMemcpyHostToDevice, st));
+  int h_flag[2] = {0x7fffffff, 0};   // [0] first Arnoldi step that broke down, [1] NaN / Inf met
+  LSA_CUDA(cudaMemcpyAsync(h.d_flag, h_flag, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
 
   // ---- start vector: random (or caller supplied), pushed through OP once (range of OP; M singular)
   if (p.v0) {
@@ -709,7 +749,8 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
   LSA_LAUNCH_CHECK();
 
-  int nconv = 0, keep = 0, restarts = 0, breakdown = 0;
+  int nconv = 0, keep = 0, restarts = 0, breakdown = 0, m_last = ncv;
+  bool invariant = false;
   RrInfo info{};
   while (true) {
     restarts++;
@@ -723,13 +764,11 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       z128* scol = S + (long long)j * ld;
       // classical Gram-Schmidt, second pass only when the criterion asks for it (decided on the device: the
       // pass-2 kernels return at once when the flag is clear)
-      for (int c0 = 0; c0 < jj; c0 += 128)
-        k_dots<<<nblk, 256, 0, st>>>(n, jj, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, c0 == 0 ? h.d_wn2 : nullptr, nullptr);
+      launch_dots(st, nblk, n, jj, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, h.d_wn2, nullptr);
       k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 0, nullptr);
       k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart, nullptr);
       k_refine_flag<<<1, 256, 0, st>>>(nblk, h.d_wn2, blocks, h.d_npart, h.ortho_refine_always ? 1 : 0, h.d_refine, h.d_refine + 1);
-      for (int c0 = 0; c0 < jj; c0 += 128)
-        k_dots<<<nblk, 256, 0, st>>>(n, jj, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, nullptr, h.d_refine);
+      launch_dots(st, nblk, n, jj, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, nullptr, h.d_refine);
       k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 1, h.d_refine);
       k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart, h.d_refine);
       k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V + (long long)(j + 1) * ldv, h.d_npart, blocks, nullptr,
@@ -739,14 +778,16 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       t_ortho.end(e);
     }
     // ---- breakdown check (one small read-back per restart)
-    LSA_CUDA(cudaMemcpyAsync(&h_flag, h.d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LSA_CUDA(cudaMemcpyAsync(h_flag, h.d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     LSA_CUDA(cudaStreamSynchronize(st));
-    if (h_flag < ncv) {
-      m = h_flag + 1;
+    if (h_flag[1]) throw NonFiniteError("NaN/Inf met in the Krylov basis (non-finite triangular solve or SpMV result)");
+    if (h_flag[0] < ncv) {
+      m = h_flag[0] + 1;
       breakdown = 1;
     }
     // an exhausted Krylov space (breakdown, or m = n) is an exactly invariant subspace
-    const bool invariant = (h_flag < ncv) || m >= n;
+    invariant = (h_flag[0] < ncv) || m >= n;
+    m_last = m;
     const double beta_scale = invariant ? 0.0 : 1.0;
     // ---- Rayleigh-Ritz
     RrParams rp{};
@@ -788,14 +829,13 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       z128* vnew = V + (long long)keep * ldv;
       k_randn<<<blocks, 256, 0, st>>>(h.d_w, n, p.seed + 7919ULL * (unsigned long long)restarts);
       for (int pass = 0; pass < 2; ++pass) {
-        for (int c0 = 0; c0 < keep; c0 += 128)
-          k_dots<<<nblk, 256, 0, st>>>(n, keep, c0, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, nullptr, nullptr);
+        launch_dots(st, nblk, n, keep, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, nullptr, nullptr);
         k_reduce_h<<<cdiv(keep, 8), 256, 0, st>>>(keep, nblk, h.d_part, ldp, h.d_h, h.d_brow, 0, nullptr);
         k_update<<<blocks, 256, 0, st>>>(n, keep, V, ldv, h.d_h, h.d_w, pass ? h.d_npart : nullptr, nullptr);
       }
       k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, vnew, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
-      h_flag = 0x7fffffff;
-      LSA_CUDA(cudaMemcpyAsync(h.d_flag, &h_flag, sizeof(int), cudaMemcpyHostToDevice, st));
+      h_flag[0] = 0x7fffffff;
+      LSA_CUDA(cudaMemcpyAsync(h.d_flag, h_flag, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
       LSA_LAUNCH_CHECK();
     } else if (!done && keep != m) {
       k_copy<<<blocks, 256, 0, st>>>(n, V + (long long)m * ldv, V + (long long)keep * ldv);
@@ -814,14 +854,20 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       LSA_CUDA(cudaMalloc(&h.d_X, sizeof(z128) * (size_t)n * nconv));
       h.X_cols = nconv;
     }
-    k_ritz_vectors<<<cdiv(nconv, 64), 64, 0, st>>>(S, ld, nconv, Q, ncv);
-    const size_t smem = sizeof(z128) * (size_t)nconv * 33;
+    // purify = 1: purification through the Krylov-Schur relation (no operator application): the next basis
+    // vector v_{m+1} joins the Ritz-vector product with coefficient (b . y) / theta.  purify = 2: explicit OP apply.
+    const bool free_purify = p.purify == 1 && !invariant && nconv < ncv;
+    if (free_purify && nconv != m_last)
+      k_copy<<<blocks, 256, 0, st>>>(n, V + (long long)m_last * ldv, V + (long long)nconv * ldv);
+    k_ritz_vectors<<<cdiv(nconv, 64), 64, 0, st>>>(S, ld, nconv, Q, ncv, free_purify ? h.d_brow : nullptr);
+    const int mpx = nconv + (free_purify ? 1 : 0);
+    const size_t smem = sizeof(z128) * (size_t)mpx * 33;
     // Xp (permuted) staged in the tail of the basis is not possible in general -> use d_Xp
-    k_basis_gemm<<<cdiv(n, 32), 256, smem, st>>>(n, nconv, nconv, V, ldv, Q, ncv, h.d_Xp, n);
+    k_basis_gemm<<<cdiv(n, 32), 256, smem, st>>>(n, mpx, nconv, V, ldv, Q, ncv, h.d_Xp, n);
     LSA_LAUNCH_CHECK();
     for (int i = 0; i < nconv; ++i) {
       z128* xi = h.d_Xp + (long long)i * n;
-      if (p.purify) {
+      if (p.purify == 2) {
         apply_op(h, p, xi, h.d_w, t_spmv, t_solve);
         n_applies++;
         k_norm2_part<<<blocks, 256, 0, st>>>(n, h.d_w, h.d_npart);

@@ -47,11 +47,6 @@ struct Symbolic {
   std::vector<int> lvl_ptr;       // nlevels+1
   std::vector<int> lvl_front;     // fronts of each level sorted by descending k
   std::vector<Front> fronts;
-  // solve-phase partition: "bottom" fronts (sub-trees made of small fronts only; swept by one persistent
-  // dependency-driven kernel) and the remaining top of the tree (swept level by level)
-  std::vector<int> bot_list;                    // bottom fronts, ascending (= post-order)
-  std::vector<int> is_bottom;                   // per front
-  std::vector<int> top_lvl_ptr, top_lvl_front;  // level lists restricted to the top fronts
   std::vector<long long> a_dst;   // per entry of the input CSR pattern: destination in the factor store
   long long fac_size = 0;         // elements in the factor store (P and Q of all fronts + decoupled pivots)
   long long diag_off = 0;         // offset of the decoupled pivots in the factor store

@@ -10,14 +10,17 @@
 // nnz(L+U) * sizeof(T) bytes per solve plus the index vectors.  Launches are batched per assembly tree level;
 // within a front the pivot block advances in 128-wide steps whose diagonal blocks were inverted explicitly
 // after the factorisation (32 -> 64 -> 128), so a step is one small GEMV instead of a scalar substitution.
-// Which kernel sweeps a level depends on its shape (solve_impl at the end of the file):
+// Which kernel sweeps a level depends on its shape (plan_solve / solve_impl at the end of the file):
 //   many fronts (>= 96, or all fronts <= 128 pivots), complex   k_front_stream   bulk copies into a smem ring
-//   <= 9 tall fronts                                            k_sweep_slices   16-CTA clusters, 8-row slices
-//   10 .. 95 multi-step fronts                                  k_sweep_cluster  1-16 CTAs per front, by chunk
-//   fronts taller than cluster_max_rows, real wide levels       k_step           one launch per 128-pivot step
-//   rows outside the step chain                                 k_up_off / k_down_off (wide GEMVs)
+//   few fronts, pivot block <= invert_max_k                     k_tri_gemv       the WHOLE pivot block is inverted
+//                                                                explicitly after the factorisation (merges
+//                                                                128 -> 256 -> ... as DMMA GEMMs): one triangular
+//                                                                matrix-vector product, no dependent steps
+//   larger pivot blocks: <= 9 tall fronts                       k_sweep_slices   16-CTA clusters, 8-row slices
+//                        10 .. 95 multi-step fronts             k_sweep_cluster  1-16 CTAs per front, by chunk
+//                        taller than cluster_max_rows           k_step           one launch per 128-pivot step
+//   rows outside the pivot block                                k_up_off / k_down_off (wide GEMVs)
 //   children -> parent contributions                            k_up_gather
-// Kept for comparison behind options: k_sweep_cluster2 (look-ahead), k_bottom (task based).
 //
 //   trans = N :  up sweep   y_top = L11^-1 P x_top ;  contrib  -= L21 y_top
 //                down sweep y_top = U11^-1 (y_top - U12 y_anc)
@@ -152,6 +155,10 @@ __global__ void __launch_bounds__(256) k_merge_inv(const Front* __restrict__ fro
 }
 
 template <class T>
+void launch_inv_merge(cudaStream_t st, const Front* fronts, const int* lvl_front, int first, int cnt, const long long* scr_off,
+                      int HB, int maxk, T* fac, T* scratch);   // factor.cu
+
+template <class T>
 void post_factor(lsa_handle_impl& h, int* n_kernels) {
   const Symbolic& sym = h.sym;
   cudaStream_t st = h.stream;
@@ -180,6 +187,37 @@ void post_factor(lsa_handle_impl& h, int* n_kernels) {
       }
       if (n_kernels) (*n_kernels) += 3;
     }
+    // ---- levels swept with k_tri_gemv: merge on, 128 -> 256 -> ... -> whole pivot block (GEMMs on the DMMA
+    // pipe through a scratch block per pair; the fronts of a level chunk are batched as far as the scratch
+    // buffer reaches; fronts are sorted by descending k, those with k > 128 form a prefix)
+    for (const SolveChunk& c : h.solve_plan) {
+      if (c.mode != SOLVE_INVERTED || c.maxk <= SB) continue;
+      int q = c.first;
+      const int qend = c.first + c.cnt;
+      while (q < qend && sym.fronts[sym.lvl_front[q]].k > SB) {
+        std::vector<long long> off;
+        long long used = 0;
+        int q1 = q;
+        while (q1 < qend && sym.fronts[sym.lvl_front[q1]].k > SB) {
+          const long long kk = sym.fronts[sym.lvl_front[q1]].k;
+          // scratch region of a front: 2 k^2 entries (pair p of merge level HB uses [2 p HB^2, 2 (p + 1) HB^2),
+          // and (p + 1) 2 HB^2 < (k + HB) HB < 2 k^2 for every pair that exists)
+          if (!off.empty() && (used + 2 * kk * kk > h.inv_scratch_entries || off.size() >= 32768)) break;
+          off.push_back(used);
+          used += 2 * kk * kk;
+          ++q1;
+        }
+        LSA_CUDA(cudaMemcpyAsync(h.d_inv_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+        const int maxk = sym.fronts[sym.lvl_front[q]].k;
+        for (int HB = SB; HB < maxk; HB *= 2) {
+          launch_inv_merge<T>(st, h.d_fronts, h.d_lvl_front, q, q1 - q, h.d_inv_off, HB, maxk, (T*)h.d_fac, (T*)h.d_inv_scratch);
+          if (n_kernels) (*n_kernels) += 4;
+        }
+        // the offsets buffer is reused by the next batch: pageable copies are staged before the call returns,
+        // and the launches above are stream ordered behind them
+        q = q1;
+      }
+    }
   }
   if (n_kernels) (*n_kernels) += 2;
 }
@@ -197,49 +235,32 @@ __global__ void k_solve_decoupled(const T* __restrict__ diag, int n_iso, const z
 // ----------------------------------------------------------------------------------------- up sweep
 
 // One CTA per front: collect the children's contribution vectors, then move the pivot rows into
-// the work vector y (with the front's row permutation when PERM).
-template <bool PERM>
-__global__ void __launch_bounds__(256) k_up_gather(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                   int first, const int* __restrict__ child_idx,
-                                                   const int* __restrict__ ea_map, const int* __restrict__ gperm,
-                                                   z128* __restrict__ x, z128* __restrict__ y, z128* __restrict__ cb) {
+// the work vector y (with the front's row permutation when PERM).  The extend-add map of ONE child is injective,
+// so a child's entries are added without any ordering inside the CTA; children follow each other in a fixed
+// order (deterministic) with a block barrier in between.  NT = 1024 for the few tall fronts of the tree top
+// (3 passes over a 3 000-row child instead of 12), 256 for the wide levels.
+template <bool PERM, int NT>
+__global__ void __launch_bounds__(NT) k_up_gather(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                  int first, const int* __restrict__ child_idx,
+                                                  const int* __restrict__ ea_map, const int* __restrict__ gperm,
+                                                  z128* __restrict__ x, z128* __restrict__ y, z128* __restrict__ cb) {
   const Front p = fronts[lvl_front[first + blockIdx.x]];
   z128* cbp = cb + p.st0;
-  for (int t = threadIdx.x; t < p.r; t += blockDim.x) cbp[t] = mk(0, 0);
+  for (int t = threadIdx.x; t < p.r; t += NT) cbp[t] = mk(0, 0);
   __syncthreads();
-  // children two at a time: both records and both (target, value) streams are read together, the additions are
-  // still applied child after child (fixed order: deterministic)
-  for (int q = 0; q < p.nchild; q += 2) {
-    const bool two = q + 1 < p.nchild;
-    const int i0 = child_idx[p.child0 + q], i1 = two ? child_idx[p.child0 + q + 1] : i0;
-    const Front c0 = fronts[i0];
-    const Front c1 = fronts[i1];
-    const int r1 = two ? c1.r : 0;
-    const int* map0 = ea_map + c0.st0;
-    const int* map1 = ea_map + c1.st0;
-    const z128* cb0 = cb + c0.st0;
-    const z128* cb1 = cb + c1.st0;
-    const int rmax = max(c0.r, r1);
-    for (int t0 = 0; t0 < rmax; t0 += blockDim.x) {
-      const int t = t0 + threadIdx.x;
-      const bool h0 = t < c0.r, h1 = t < r1;
-      int ip0 = 0, ip1 = 0;
-      z128 v0 = mk(0, 0), v1 = mk(0, 0);
-      if (h0) { ip0 = map0[t]; v0 = cb0[t]; }
-      if (h1) { ip1 = map1[t]; v1 = cb1[t]; }
-      if (h0) {
-        if (ip0 < p.k) x[p.col0 + ip0] += v0;
-        else cbp[ip0 - p.k] += v0;
-      }
-      __syncthreads();
-      if (h1) {
-        if (ip1 < p.k) x[p.col0 + ip1] += v1;
-        else cbp[ip1 - p.k] += v1;
-      }
-      __syncthreads();
+  for (int q = 0; q < p.nchild; ++q) {
+    const Front c = fronts[child_idx[p.child0 + q]];
+    const int* map = ea_map + c.st0;
+    const z128* cbc = cb + c.st0;
+    for (int t = threadIdx.x; t < c.r; t += NT) {
+      const int ip = map[t];
+      const z128 v = cbc[t];
+      if (ip < p.k) x[p.col0 + ip] += v;
+      else cbp[ip - p.k] += v;
     }
+    __syncthreads();
   }
-  for (int i = threadIdx.x; i < p.k; i += blockDim.x) y[p.col0 + i] = x[PERM ? gperm[p.col0 + i] : p.col0 + i];
+  for (int i = threadIdx.x; i < p.k; i += NT) y[p.col0 + i] = x[PERM ? gperm[p.col0 + i] : p.col0 + i];
 }
 
 // --------------------------------------------------------------------------------------- down sweep
@@ -399,6 +420,90 @@ __global__ void __launch_bounds__(NW * 32) k_up_off(const Front* __restrict__ fr
       }
       const int j = r0 + wid + q * NW;
       if (lane == 0 && j < r) cb[f.st0 + j] -= a;
+    }
+  }
+}
+
+// --------------------------------------------------------------- whole pivot block inverted: one GEMV
+//
+// Fronts whose pivot block D = P[0:k, 0:k] was inverted as a whole after the factorisation (post_factor: L11^-1
+// strictly below the diagonal with an implied unit diagonal, U11^-1 on and above it) need no dependent 128-pivot
+// steps: the triangular solve of the front is ONE matrix-vector product, every row independent.
+//   up,N    z_i = y_i + sum_{c<i}  D[i,c] y_c            up,H    z_i = sum_{c<=i} conj(D[c,i]) y_c
+//   down,N  z_i =       sum_{c>=i} D[i,c] y_c            down,H  z_i = y_i + sum_{c>i} conj(D[c,i]) y_c
+// N reduces along rows (thread = row, warps = column groups, partial sums through shared memory), H along columns
+// (warp = 32 / NW output entries, lanes along the contiguous column).  grid: (chunks of 32 pivots, fronts).
+template <class T, bool H, bool UP, int NW>
+__global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, const T* __restrict__ fac, const z128* __restrict__ in,
+                                                   z128* __restrict__ out) {
+  constexpr int ROWS = 32;
+  constexpr int CHUNK = NW * 32;
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k;
+  const int r0 = blockIdx.x * ROWS;
+  if (r0 >= k) return;
+  const long long m = (long long)k + f.r;
+  const T* P = fac + f.p_off;
+  __shared__ z128 xs[CHUNK];
+  __shared__ z128 red[NW][ROWS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int rowN = r0 + lane;
+  z128 acc = mk(0, 0);
+  z128 accH[ROWS / NW];
+#pragma unroll
+  for (int q = 0; q < ROWS / NW; ++q) accH[q] = mk(0, 0);
+  // index range of the input entries this CTA's outputs depend on
+  const int c_lo = UP ? 0 : r0, c_hi = UP ? min(k, r0 + ROWS) : k;
+  for (int c0 = c_lo; c0 < c_hi; c0 += CHUNK) {
+    const int len = min(CHUNK, c_hi - c0);
+    __syncthreads();
+    if (tid < len) xs[tid] = in[f.col0 + c0 + tid];
+    __syncthreads();
+    if (!H) {
+      if (rowN < k) {
+        const T* a = P + rowN + (long long)c0 * m;
+#pragma unroll 8
+        for (int c = wid; c < len; c += NW) {
+          const int cc = c0 + c;
+          if (UP ? cc < rowN : cc >= rowN) acc += a[(long long)c * m] * xs[c];
+        }
+      }
+    } else {
+      for (int cb0 = 0; cb0 < len; cb0 += 32) {
+        const int c = cb0 + lane;
+        if (c < len) {
+          const int cc = c0 + c;
+          const z128 xc = xs[c];
+#pragma unroll
+          for (int q = 0; q < ROWS / NW; ++q) {
+            const int i = r0 + wid + q * NW;
+            if (i < k && (UP ? cc <= i : cc > i)) accH[q] += conj_(P[cc + (long long)i * m]) * xc;
+          }
+        }
+      }
+    }
+  }
+  if (!H) {
+    red[wid][lane] = acc;
+    __syncthreads();
+    if (tid < ROWS && r0 + tid < k) {
+      z128 sum = red[0][tid];
+#pragma unroll 8
+      for (int q = 1; q < NW; ++q) sum += red[q][tid];
+      if (UP) sum += in[f.col0 + r0 + tid];   // unit diagonal of L11^-1
+      out[f.col0 + r0 + tid] = sum;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < ROWS / NW; ++q) {
+      z128 a = accH[q];
+      for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      }
+      const int i = r0 + wid + q * NW;
+      if (lane == 0 && i < k) out[f.col0 + i] = UP ? a : a + in[f.col0 + i];   // unit diagonal of L11^-H
     }
   }
 }
@@ -743,217 +848,6 @@ static void launch_sweep_cluster(cudaStream_t st, int cnt, const Front* fronts, 
   LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb, pivots_only));
 }
 
-// ------------------------------------------------------------- cluster sweep with look-ahead (big fronts)
-//
-// Same job as k_sweep_cluster, organised so that the dependent chain of a front is as short as the
-// hardware allows:
-//  * the 128-row chunks of a front are owned STATICALLY (chunk g -> CTA g mod C of the cluster): all updates
-//    of a row come from one CTA, so nothing but the solved slices crosses CTAs;
-//  * only the owner of pivot block s applies the inverted diagonal block; it pushes the solved slice z_s into
-//    the shared memory of every CTA of the cluster (DSMEM stores) -- no redundant 128 x 128 GEMV per CTA;
-//  * split cluster barrier: a CTA ARRIVES for step s+1 as soon as its part of the critical path is done (the
-//    owner of block s+1: update that block with z_s, solve it, broadcast z_{s+1}; everybody else: at once),
-//    then updates the rest of its chunks with z_s, and only then WAITS.  The updates that are not on the
-//    critical path overlap the next triangular step.  Three z buffers: z_{s+2} can only be written after every
-//    CTA has arrived for step s+2, i.e. finished using z_s.
-template <class T, bool H, bool UP, int C>
-__global__ void __launch_bounds__(1024) k_sweep_cluster2(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                         int first, const T* __restrict__ fac, z128* in, z128* out,
-                                                         z128* cb) {
-  namespace cg = cooperative_groups;
-  constexpr int NT = 1024, CG = NT / SB, NWARP = NT / 32;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = C > 1 ? (int)cluster.block_rank() : 0;
-  const Front f = fronts[lvl_front[first + blockIdx.x / C]];
-  const int k = f.k;
-  const long long m = (long long)k + f.r;
-  const T* P = fac + f.p_off;
-  const T* Q = fac + f.q_off;
-  __shared__ z128 ys[SB];
-  __shared__ z128 zbuf[3][SB];
-  __shared__ z128 part[CG][SB];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nsteps = (k + SB - 1) / SB;
-  const int nchunks = (int)((m + SB - 1) / SB);
-
-  // ---- rows [lo, hi) of chunk g  -=  Off[rows, j0:j1) z      (plain loads/stores: the chunk is this CTA's)
-  auto update_chunk = [&](int j0, int len, int g, const z128* zs) {
-    const int j1 = j0 + len;
-    const int lo = UP ? max(j1, g * SB) : g * SB;
-    const int hi = UP ? (int)min(m, (long long)(g + 1) * SB) : min(j0, (g + 1) * SB);
-    if (hi <= lo) return;   // uniform over the CTA
-    const int base = g * SB;
-    if (!H) {
-      const int rr = tid & (SB - 1), cgi = tid >> 7;
-      const int row = base + rr;
-      z128 acc = mk(0, 0);
-      if (row >= lo && row < hi) {
-        const T* a = P + row + (long long)j0 * m;
-#pragma unroll 8
-        for (int c = cgi; c < len; c += CG) acc += a[(long long)c * m] * zs[c];
-      }
-      __syncthreads();
-      part[cgi][rr] = acc;
-      __syncthreads();
-      if (tid < SB && row >= lo && row < hi) {
-        z128 sum = part[0][tid];
-#pragma unroll
-        for (int q = 1; q < CG; ++q) sum += part[q][tid];
-        z128* dst = (!UP || row < k) ? in + f.col0 + row : cb + f.st0 + (row - k);
-        *dst = *dst - sum;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < SB / NWARP; ++q) {
-        const int row = base + wid + q * NWARP;
-        if (row < lo || row >= hi) continue;
-        const T* u = (!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
-        z128 acc = mk(0, 0);
-        for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * zs[c];
-        for (int o = 16; o > 0; o >>= 1) {
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        }
-        if (lane == 0) {
-          z128* dst = (!UP || row < k) ? in + f.col0 + row : cb + f.st0 + (row - k);
-          *dst = *dst - acc;
-        }
-      }
-    }
-    __syncthreads();
-  };
-
-  // ---- the owner of pivot block s: z_s = Op y_s, stored to `out` and pushed to every CTA's zbuf[slot]
-  auto solve_block = [&](int s, int slot) {
-    const int j0 = s * SB, len = min(SB, k - j0);
-    const T* D = P + j0 + (long long)j0 * m;
-    if (tid < len) ys[tid] = in[f.col0 + j0 + tid];
-    __syncthreads();
-    z128 z = mk(0, 0);
-    if (!H) {
-      const int i = tid & (SB - 1), cgi = tid >> 7;
-      z128 acc = mk(0, 0);
-      if (i < len) {
-        const T* row = D + i;
-        if (UP) {
-#pragma unroll 8
-          for (int c = cgi; c < i; c += CG) acc += row[(long long)c * m] * ys[c];
-        } else {
-#pragma unroll 8
-          for (int c = i + cgi; c < len; c += CG) acc += row[(long long)c * m] * ys[c];
-        }
-      }
-      part[cgi][i] = acc;
-      __syncthreads();
-      if (tid < len) {
-        z128 sum = part[0][tid];
-#pragma unroll
-        for (int q = 1; q < CG; ++q) sum += part[q][tid];
-        z = UP ? sum + ys[tid] : sum;
-      }
-    } else {
-      // one warp per column of the block, results collected in part[0][]
-      for (int i = wid; i < len; i += NWARP) {
-        const T* col = D + (long long)i * m;
-        z128 acc = mk(0, 0);
-        if (UP) {
-          for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
-        } else {
-          for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        }
-        if (lane == 0) part[0][i] = UP ? acc : acc + ys[i];
-      }
-      __syncthreads();
-      if (tid < len) z = part[0][tid];
-    }
-    if (tid < len) {
-      out[f.col0 + j0 + tid] = z;
-      if (C > 1) {
-#pragma unroll
-        for (int r = 0; r < C; ++r) cluster.map_shared_rank(&zbuf[slot][0], r)[tid] = z;
-      } else {
-        zbuf[slot][tid] = z;
-      }
-    }
-    __syncthreads();
-  };
-
-  // panel of step `s` for this CTA's chunks -> L2
-  auto prefetch_step = [&](int s) {
-    if (s < 0 || s >= nsteps) return;
-    const int j0 = s * SB, len = min(SB, k - j0), j1 = j0 + len;
-    if (rank == s % C && tid < len) prefetch_l2(P + j0 + (long long)(j0 + tid) * m, len);
-    const int q = tid >> 7, i = tid & (SB - 1);
-    const int g_lo = UP ? j1 / SB : 0, g_hi = UP ? nchunks : s;   // chunks touched at this step
-    int g = g_lo + ((rank - g_lo) % C + C) % C;                   // first chunk >= g_lo owned by this rank
-    g += q * C;
-    for (; g < g_hi; g += 8 * C) {
-      const int lo = UP ? max(j1, g * SB) : g * SB;
-      const int hi = UP ? (int)min(m, (long long)(g + 1) * SB) : (g + 1) * SB;
-      if (hi <= lo) continue;
-      if (!H) {
-        if (i < len) prefetch_l2(P + lo + (long long)(j0 + i) * m, hi - lo);
-      } else if (lo + i < hi) {
-        const int row = lo + i;
-        prefetch_l2((!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k, len);
-      }
-    }
-  };
-
-  auto step_of = [&](int i) { return UP ? i : nsteps - 1 - i; };
-  prefetch_step(step_of(0));
-  if (rank == step_of(0) % C) solve_block(step_of(0), 0);
-  if (C > 1) cluster.barrier_arrive();
-  for (int i = 0; i < nsteps; ++i) {
-    const int s = step_of(i);
-    const int j0 = s * SB, len = min(SB, k - j0), j1 = j0 + len;
-    const z128* zs = zbuf[i % 3];
-    if (C > 1) cluster.barrier_wait();   // z_s has arrived
-    else __syncthreads();
-    const bool more = i + 1 < nsteps;
-    const int sn = more ? step_of(i + 1) : -1;   // next pivot block = chunk sn
-    prefetch_step(sn);
-    if (more && rank == sn % C) {
-      update_chunk(j0, len, sn, zs);             // critical path first
-      solve_block(sn, (i + 1) % 3);
-    }
-    if (more && C > 1) cluster.barrier_arrive();
-    // the rest of this CTA's chunks
-    const int g_lo = UP ? j1 / SB : 0, g_hi = UP ? nchunks : s;
-    for (int g = g_lo + ((rank - g_lo) % C + C) % C; g < g_hi; g += C) {
-      if (more && g == sn) continue;
-      update_chunk(j0, len, g, zs);
-    }
-  }
-}
-
-template <class T, bool H, bool UP, int C>
-static void launch_sweep_cluster2(cudaStream_t st, int cnt, const Front* fronts, const int* lvl_front, int first,
-                                  const T* fac, z128* in, z128* out, z128* cb) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(C * cnt), 1, 1);
-  cfg.blockDim = dim3(1024, 1, 1);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (C > 8) {
-    static PerDeviceOnce allowed;   // per instantiation
-    if (allowed.first())
-      LSA_CUDA(cudaFuncSetAttribute(k_sweep_cluster2<T, H, UP, C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  }
-  LSA_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_cluster2<T, H, UP, C>, fronts, lvl_front, first, fac, in, out, cb));
-}
-
 // ------------------------------------------------- cluster sweep with row slices (few, tall fronts: the tree top)
 //
 // The top levels hold 1 ... 9 fronts; a 128-pivot step there is a chain of dependent 128 x 128 block products.
@@ -1295,17 +1189,7 @@ static int cluster_width(int cnt, int max_rows, int num_sms, int max_width) {
 
 template <class T, bool H, bool UP>
 static void sweep_cluster(cudaStream_t st, int csize, int cnt, const Front* fronts, const int* lvl_front, int first,
-                          const T* fac, z128* in, z128* out, z128* cb, bool lookahead, int pivots_only = 0) {
-  if (lookahead) {
-    switch (csize) {
-      case 1: launch_sweep_cluster2<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-      case 2: launch_sweep_cluster2<T, H, UP, 2>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-      case 4: launch_sweep_cluster2<T, H, UP, 4>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-      case 8: launch_sweep_cluster2<T, H, UP, 8>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-      default: launch_sweep_cluster2<T, H, UP, 16>(st, cnt, fronts, lvl_front, first, fac, in, out, cb); break;
-    }
-    return;
-  }
+                          const T* fac, z128* in, z128* out, z128* cb, int pivots_only = 0) {
   switch (csize) {
     case 1: launch_sweep_cluster<T, H, UP, 1>(st, cnt, fronts, lvl_front, first, fac, in, out, cb, pivots_only); break;
     case 2: launch_sweep_cluster<T, H, UP, 2>(st, cnt, fronts, lvl_front, first, fac, in, out, cb, pivots_only); break;
@@ -1813,239 +1697,6 @@ static bool launch_front_stream(lsa_handle_impl& h, cudaStream_t st, int cnt, co
   return launch_front_stream_t<H, UP, 256, 2>(h, st, cnt, lvl_front, first, maxk, maxr, fac, vin, vout, cb, anc);
 }
 
-// ------------------------------------------------------- bottom of the tree (persistent, task based)
-//
-// The lowest levels of the assembly tree hold most fronts but little data per front; sweeping them
-// level by level costs four dependent launches per level and a global barrier between levels.  The
-// bottom part (sub-trees made of small fronts only) is instead swept by ONE persistent kernel per
-// direction: CTAs take fronts from a queue in post-order (up) / reverse post-order (down) and wait on
-// per-front completion flags of their children (up) or parent (down) -- a front starts as soon as what
-// it depends on is done, there is no level barrier and no launch.  Forward progress: the grid is sized
-// to be fully resident and the queue order is a topological order, so everything a CTA can wait for has
-// already been handed to a running CTA.  Data produced by other CTAs is read through L2 (ld.cg) after a
-// fence; flags are written with a release fence.
-__device__ __forceinline__ int ld_flag(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-
-template <class T, bool H, bool UP>
-__global__ void __launch_bounds__(256) k_bottom(const Front* __restrict__ fronts, const int* __restrict__ bot_list, int nbot,
-                                                const int* __restrict__ is_bottom, int* __restrict__ queue,
-                                                int* __restrict__ done, const int* __restrict__ child_idx,
-                                                const int* __restrict__ ea_map, const int* __restrict__ gperm,
-                                                const int* __restrict__ st_idx, const T* __restrict__ fac, z128* x,
-                                                z128* y, z128* z, z128* cb) {
-  constexpr int NT = 256, CG = NT / SB, NWARP = NT / 32;
-  __shared__ z128 ys[SB];
-  __shared__ z128 zs[SB];
-  __shared__ z128 part[CG][SB];
-  __shared__ z128 xs[NT];
-  __shared__ z128 red[NWARP][33];
-  __shared__ int s_front;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int DONE = UP ? 1 : 2;  // flag value written by this sweep (the flags are zeroed once per solve)
-  while (true) {
-    __syncthreads();
-    if (tid == 0) {
-      const int q = atomicAdd(queue, 1);
-      s_front = q < nbot ? bot_list[UP ? q : nbot - 1 - q] : -1;
-    }
-    __syncthreads();
-    const int s = s_front;
-    if (s < 0) break;
-    const Front f = fronts[s];
-    // ---- wait for the fronts this one depends on
-    if (UP) {
-      for (int q = tid; q < f.nchild; q += NT) {
-        const int c = child_idx[f.child0 + q];
-        while (ld_flag(done + c) < 1) __nanosleep(64);
-      }
-    } else if (tid == 0 && f.parent >= 0 && is_bottom[f.parent]) {
-      while (ld_flag(done + f.parent) < 2) __nanosleep(64);
-    }
-    __threadfence();
-    __syncthreads();
-    const int k = f.k, r = f.r;
-    const long long m = (long long)k + r;
-    const T* P = fac + f.p_off;
-    const T* Q = fac + f.q_off;
-    if (UP) {
-      // ---- children contributions, then the pivot rows into the work vector
-      for (int t = tid; t < r; t += NT) cb[f.st0 + t] = mk(0, 0);
-      __syncthreads();
-      for (int q = 0; q < f.nchild; ++q) {
-        const Front c = fronts[child_idx[f.child0 + q]];
-        const int* map = ea_map + c.st0;
-        for (int t = tid; t < c.r; t += NT) {
-          const int ip = map[t];
-          const z128 v = ld_cg(cb + c.st0 + t);
-          z128* dst = ip < k ? x + f.col0 + ip : cb + f.st0 + (ip - k);
-          *dst = ld_cg(dst) + v;
-        }
-        __syncthreads();
-      }
-      for (int i = tid; i < k; i += NT) y[f.col0 + i] = ld_cg(x + (H ? f.col0 + i : gperm[f.col0 + i]));
-      __syncthreads();
-    } else if (r > 0) {
-      // ---- pivot rows -= Off * (final values of the ancestors)
-      const z128* anc = H ? x : y;
-      const int* idx = st_idx + f.st0;
-      for (int r0 = 0; r0 < k; r0 += 32) {
-        z128 acc = mk(0, 0);
-        z128 accH[32 / NWARP];
-#pragma unroll
-        for (int q = 0; q < 32 / NWARP; ++q) accH[q] = mk(0, 0);
-        for (int c0 = 0; c0 < r; c0 += NT) {
-          const int len = min(NT, r - c0);
-          __syncthreads();
-          if (tid < len) xs[tid] = ld_cg(anc + idx[c0 + tid]);
-          __syncthreads();
-          if (!H) {
-            if (r0 + lane < k) {
-              const T* a = Q + (r0 + lane) + (long long)c0 * k;
-#pragma unroll 8
-              for (int c = wid; c < len; c += NWARP) acc += a[(long long)c * k] * xs[c];
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32 / NWARP; ++q) {
-              const int row = r0 + wid + q * NWARP;
-              if (row < k) {
-                const T* l = P + k + c0 + (long long)row * m;
-                for (int c = lane; c < len; c += 32) accH[q] += conj_(l[c]) * xs[c];
-              }
-            }
-          }
-        }
-        if (!H) {
-          red[wid][lane] = acc;
-          __syncthreads();
-          if (tid < 32 && r0 + tid < k) {
-            z128 sum = red[0][tid];
-#pragma unroll
-            for (int q = 1; q < NWARP; ++q) sum += red[q][tid];
-            z128* dst = z + f.col0 + r0 + tid;
-            *dst = ld_cg(dst) - sum;
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 32 / NWARP; ++q) {
-            z128 a = accH[q];
-            for (int o = 16; o > 0; o >>= 1) {
-              a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
-              a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-            }
-            const int row = r0 + wid + q * NWARP;
-            if (lane == 0 && row < k) {
-              z128* dst = z + f.col0 + row;
-              *dst = ld_cg(dst) - a;
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    // ---- the front's pivot block in 128-wide steps
-    z128* in = UP ? y : z;
-    z128* out = UP ? z : y;
-    const int nsteps = (k + SB - 1) / SB;
-    for (int st = 0; st < nsteps; ++st) {
-      const int j0 = (UP ? st : nsteps - 1 - st) * SB;
-      const int len = min(SB, k - j0), j1 = j0 + len;
-      const int nrows = UP ? (int)(m - j1) : j0;
-      const T* D = P + j0 + (long long)j0 * m;
-      if (tid < len) ys[tid] = ld_cg(in + f.col0 + j0 + tid);
-      __syncthreads();
-      if (!H) {
-        const int i = tid & (SB - 1), cgi = tid >> 7;
-        z128 acc = mk(0, 0);
-        if (i < len) {
-          const T* row = D + i;
-          if (UP) {
-#pragma unroll 8
-            for (int c = cgi; c < i; c += CG) acc += row[(long long)c * m] * ys[c];
-          } else {
-#pragma unroll 8
-            for (int c = i + cgi; c < len; c += CG) acc += row[(long long)c * m] * ys[c];
-          }
-        }
-        part[cgi][i] = acc;
-        __syncthreads();
-        if (tid < len) {
-          z128 sum = part[0][tid];
-#pragma unroll
-          for (int q = 1; q < CG; ++q) sum += part[q][tid];
-          zs[tid] = UP ? sum + ys[tid] : sum;
-        }
-      } else {
-        for (int i = wid; i < len; i += NWARP) {
-          const T* col = D + (long long)i * m;
-          z128 acc = mk(0, 0);
-          if (UP) {
-            for (int c = lane; c <= i; c += 32) acc += conj_(col[c]) * ys[c];
-          } else {
-            for (int c = i + 1 + lane; c < len; c += 32) acc += conj_(col[c]) * ys[c];
-          }
-          for (int o = 16; o > 0; o >>= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-          }
-          if (lane == 0) zs[i] = UP ? acc : acc + ys[i];
-        }
-      }
-      __syncthreads();
-      if (tid < len) {
-        out[f.col0 + j0 + tid] = zs[tid];
-        if (!UP && H) x[gperm[f.col0 + j0 + tid]] = zs[tid];  // P^T of this front, final values
-      }
-      for (int r0 = 0; r0 < nrows; r0 += SB) {
-        if (!H) {
-          const int rr = tid & (SB - 1), cgi = tid >> 7;
-          const int row = (UP ? j1 : 0) + r0 + rr;
-          z128 acc = mk(0, 0);
-          if (r0 + rr < nrows) {
-            const T* a = P + row + (long long)j0 * m;
-#pragma unroll 8
-            for (int c = cgi; c < len; c += CG) acc += a[(long long)c * m] * zs[c];
-          }
-          __syncthreads();
-          part[cgi][rr] = acc;
-          __syncthreads();
-          if (tid < SB && r0 + tid < nrows) {
-            z128 sum = part[0][tid];
-#pragma unroll
-            for (int q = 1; q < CG; ++q) sum += part[q][tid];
-            const int rw = (UP ? j1 : 0) + r0 + tid;
-            z128* dst = (!UP || rw < k) ? in + f.col0 + rw : cb + f.st0 + (rw - k);
-            *dst = ld_cg(dst) - sum;
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < SB / NWARP; ++q) {
-            const int rr = wid + q * NWARP;
-            if (r0 + rr >= nrows) break;
-            const int row = (UP ? j1 : 0) + r0 + rr;
-            const T* u = (!UP || row < k) ? P + j0 + (long long)row * m : Q + j0 + (long long)(row - k) * k;
-            z128 acc = mk(0, 0);
-            for (int c = lane; c < len; c += 32) acc += conj_(u[c]) * zs[c];
-            for (int o = 16; o > 0; o >>= 1) {
-              acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-              acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-            }
-            if (lane == 0) {
-              z128* dst = (!UP || row < k) ? in + f.col0 + row : cb + f.st0 + (row - k);
-              *dst = ld_cg(dst) - acc;
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    // ---- publish: everything this front wrote is visible before its flag
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) atomicExch(done + s, DONE);
-  }
-}
-
 __global__ void k_unpermute(const z128* __restrict__ y, z128* __restrict__ x, const int* __restrict__ gperm, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[gperm[i]] = y[i];
@@ -2061,6 +1712,58 @@ __global__ void __launch_bounds__(256) k_level_unpermute(const Front* __restrict
 
 // ------------------------------------------------------------------------------------------- driver
 
+// Level plan of the sweeps (host, once per factorisation): chunks of <= 32768 fronts of one level, each with the
+// kernel family that sweeps it.  post_factor reads it to know which pivot blocks to invert as a whole.
+void plan_solve(lsa_handle_impl& h, int scalar) {
+  using namespace stream;
+  const Symbolic& sym = h.sym;
+  constexpr int YMAX = 32768;
+  h.solve_plan.clear();
+  long long scratch = 0, max_region = 0;
+  for (int d = 0; d < sym.nlevels; ++d) {
+    const int lbeg = sym.lvl_ptr[d], cnt_all = sym.lvl_ptr[d + 1] - lbeg;
+    for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
+      SolveChunk c{};
+      c.level = d;
+      c.first = lbeg + y0;
+      c.cnt = std::min(YMAX, cnt_all - y0);
+      long long sumk2 = 0;
+      for (int q = c.first; q < c.first + c.cnt; ++q) {
+        const Front& f = sym.fronts[sym.lvl_front[q]];
+        c.maxk = std::max(c.maxk, f.k);
+        c.max_r = std::max(c.max_r, f.r);
+        c.max_m = std::max(c.max_m, f.k + f.r);
+        if (f.k > SB) sumk2 += 2LL * f.k * f.k;
+      }
+      const int kmax = (c.maxk + 7) / 8 * 8, rmax = (c.max_r + 7) / 8 * 8;
+      const size_t fixed = sizeof(z128) * (4 * (size_t)kmax + 2 * (size_t)rmax) + 3 * sizeof(int) * (size_t)rmax;
+      const bool stream_fits = fixed + sizeof(z128) * 2 * (size_t)TILE <= (size_t)STREAM_MAX_SMEM;
+      if (scalar == LSA_C128 && h.use_stream && stream_fits && (c.maxk <= SB || c.cnt >= h.stream_min_fronts))
+        c.mode = SOLVE_STREAM;
+      else if (c.maxk <= h.invert_max_k)
+        c.mode = SOLVE_INVERTED;
+      else
+        c.mode = SOLVE_STEPS;
+      if (c.mode == SOLVE_INVERTED && c.maxk > SB) {
+        scratch = std::max(scratch, std::min<long long>(sumk2, 1LL << 26));
+        max_region = std::max(max_region, 2LL * c.maxk * c.maxk);
+      }
+      h.solve_plan.push_back(c);
+    }
+  }
+  // scratch of the whole-block inversions: every batch holds at least one front
+  scratch = std::max(scratch, max_region);
+  const long long bytes = scratch * (scalar == LSA_C128 ? 16 : 8);
+  if (bytes > h.inv_scratch_bytes) {
+    if (h.d_inv_scratch) cudaFree(h.d_inv_scratch);
+    h.d_inv_scratch = nullptr;
+    LSA_CUDA(cudaMalloc(&h.d_inv_scratch, bytes));
+    h.inv_scratch_bytes = bytes;
+  }
+  h.inv_scratch_entries = scratch;
+  if (!h.d_inv_off) LSA_CUDA(cudaMalloc(&h.d_inv_off, sizeof(long long) * YMAX));
+}
+
 template <class T, bool H>
 static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   const Symbolic& sym = h.sym;
@@ -2070,180 +1773,147 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   z128* z = h.d_t2;   // up sweep: solved values;     down sweep: pre-solve values
   z128* cb = h.d_cb;
   int launches = 0;
-  constexpr int YMAX = 32768;
   SweepTrace tr;
   tr.begin(st);
-  // optional: the bottom of the tree swept by k_bottom; the level loops then only see the top of the tree
-  const int nsub = h.use_subtrees ? (int)sym.bot_list.size() : 0;
-  const std::vector<int>& lvl_ptr = nsub ? sym.top_lvl_ptr : sym.lvl_ptr;
-  const std::vector<int>& lvl_front = nsub ? sym.top_lvl_front : sym.lvl_front;
-  const int* d_lvl_front = nsub ? h.d_top_lvl_front : h.d_lvl_front;
+  const std::vector<int>& lvl_front = sym.lvl_front;
+  const int* d_lvl_front = h.d_lvl_front;
   if (sym.n_iso > 0) {
     k_solve_decoupled<T, H><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, x, y);
     LSA_LAUNCH_CHECK();
     launches++;
   }
-  // ---- up sweep: bottom part (task based), then the top levels (deepest first)
-  int bottom_grid = 0;
-  if (nsub) {
-    // persistent grid: exactly as many CTAs as are resident at once
-    static int occ[2][2] = {{0, 0}, {0, 0}};
-    int& o = occ[scalar_traits<T>::is_complex][H];
-    if (o == 0) {
-      int a = 0, b = 0;
-      LSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_bottom<T, H, true>, 256, 0));
-      LSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_bottom<T, H, false>, 256, 0));
-      o = std::max(1, std::min(a, b));
-    }
-    bottom_grid = std::min(nsub, o * h.num_sms);
-    LSA_CUDA(cudaMemsetAsync(h.d_bot_state, 0, sizeof(int) * (size_t)(sym.ns + 2), st));
-    k_bottom<T, H, true><<<bottom_grid, 256, 0, st>>>(h.d_fronts, h.d_bot_list, nsub, h.d_is_bottom, h.d_bot_state,
-                                                      h.d_bot_state + 2, h.d_child_idx, h.d_ea_map, h.d_gperm, h.d_st_idx, fac,
-                                                      x, y, z, cb);
+  auto up_off = [&](const SolveChunk& c) {
+    if (c.max_r <= 0) return;
+    if (c.maxk > 512) k_up_off<T, H, 32><<<dim3(cdiv(c.max_r, 32), c.cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, z, cb);
+    else k_up_off<T, H, 8><<<dim3(cdiv(c.max_r, 32), c.cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, z, cb);
     LSA_LAUNCH_CHECK();
-    tr.mark("up_bottom", -1, 0, bottom_grid, 1);
+    tr.mark("up_off", c.level, 0, cdiv(c.max_r, 32), c.cnt);
     launches++;
-  }
-  for (int d = sym.nlevels - 1; d >= 0; --d) {
-    const int lbeg = lvl_ptr[d], cnt_all = lvl_ptr[d + 1] - lbeg;
-    for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
-      const int cnt = std::min(YMAX, cnt_all - y0), first = lbeg + y0;
-      k_up_gather<!H><<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+  };
+  // ---- up sweep: deepest level first
+  for (int ci = (int)h.solve_plan.size() - 1; ci >= 0; --ci) {
+    const SolveChunk& c = h.solve_plan[ci];
+    const int d = c.level, cnt = c.cnt, first = c.first, maxk = c.maxk, max_r = c.max_r, max_m = c.max_m;
+    if (cnt <= 2 * h.num_sms)
+      k_up_gather<!H, 1024><<<cnt, 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+    else
+      k_up_gather<!H, 256><<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+    LSA_LAUNCH_CHECK();
+    tr.mark("up_gather", d, 0, cnt, 1);
+    launches++;
+    if constexpr (scalar_traits<T>::is_complex) {
+      if (c.mode == SOLVE_STREAM) {
+        if (!launch_front_stream<H, true>(h, st, cnt, d_lvl_front, first, maxk, max_r, max_m, fac, y, z, cb, nullptr))
+          throw std::runtime_error("streamed sweep does not fit although the plan says so");
+        tr.mark("up_stream", d, 0, cnt, 1);
+        launches++;
+        continue;
+      }
+    }
+    if (c.mode == SOLVE_INVERTED) {
+      if (maxk > 512) k_tri_gemv<T, H, true, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, y, z);
+      else k_tri_gemv<T, H, true, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, y, z);
       LSA_LAUNCH_CHECK();
-      tr.mark("up_gather", d, 0, cnt, 1);
+      tr.mark("up_tri", d, 0, cdiv(maxk, 32), cnt);
       launches++;
-      const int maxk = sym.fronts[lvl_front[first]].k;
-      int max_m = 0, max_r = 0;
+      up_off(c);
+      continue;
+    }
+    // ---- pivot blocks too large to invert as a whole: chains of 128-pivot steps
+    const int csize = cluster_width(cnt, max_m, h.num_sms, h.cluster_max_width);
+    if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {
+      launch_sweep_slices<T, H, true>(st, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
+      tr.mark("up_slices", d, 16, 16 * cnt, 1);
+      launches++;
+      up_off(c);
+      continue;
+    }
+    // tall fronts need the whole GPU per step; up to `cluster_max_rows` rows a cluster of <= 8 SMs keeps up
+    // and saves the launches (inside a CUDA graph the two are within 3 % of each other, profiles/r1f_*)
+    if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
+      // contribution rows deferred to one wide GEMV
+      const int defer = (h.defer_cb && max_r > 0) ? 1 : 0;
+      const int cs = defer ? cluster_width(cnt, maxk, h.num_sms, h.cluster_max_width) : csize;
+      sweep_cluster<T, H, true>(st, cs, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb, defer);
+      tr.mark("up_cluster", d, cs, cs * cnt, 1);
+      launches++;
+      if (defer) up_off(c);
+      continue;
+    }
+    for (int j0 = 0; j0 < maxk; j0 += SB) {
+      int act = 0, max_rows = 0;
       for (int q = first; q < first + cnt; ++q) {
-        max_m = std::max(max_m, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
-        max_r = std::max(max_r, sym.fronts[lvl_front[q]].r);
+        const Front& f = sym.fronts[lvl_front[q]];
+        if (f.k <= j0) break;
+        act++;
+        max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
       }
-      const int csize = cluster_width(cnt, max_m, h.num_sms, h.cluster_max_width);
-      // tall fronts need the whole GPU per step; up to `cluster_max_rows` rows a cluster of <= 8 SMs keeps up
-      // and saves the launches (inside a CUDA graph the two are within 3 % of each other, profiles/r1f_*)
-      if constexpr (scalar_traits<T>::is_complex) {
-        if (h.use_stream && (maxk <= SB || cnt >= h.stream_min_fronts) &&
-            launch_front_stream<H, true>(h, st, cnt, d_lvl_front, first, maxk, max_r, max_m, fac, y, z, cb, nullptr)) {
-          tr.mark("up_stream", d, 0, cnt, 1);
-          launches++;
-          continue;
-        }
-      }
-      if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {
-        launch_sweep_slices<T, H, true>(st, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
-        tr.mark("up_slices", d, 16, 16 * cnt, 1);
-        launches++;
-        if (max_r > 0) {
-          if (maxk > 512) k_up_off<T, H, 32><<<dim3(cdiv(max_r, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, cb);
-          else k_up_off<T, H, 8><<<dim3(cdiv(max_r, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, cb);
-          LSA_LAUNCH_CHECK();
-          tr.mark("up_off", d, 0, cdiv(max_r, 32), cnt);
-          launches++;
-        }
-        continue;
-      }
-      if (maxk > SB && max_m <= h.cluster_max_rows && h.use_clusters) {
-        // contribution rows deferred to one wide GEMV (not with the look-ahead variant, which owns whole chunks)
-        const int defer = (h.defer_cb && !h.cluster_lookahead && max_r > 0) ? 1 : 0;
-        const int cs = defer ? cluster_width(cnt, maxk, h.num_sms, h.cluster_max_width) : csize;
-        sweep_cluster<T, H, true>(st, cs, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb, h.cluster_lookahead, defer);
-        tr.mark("up_cluster", d, cs, cs * cnt, 1);
-        launches++;
-        if (defer) {
-          if (maxk > 512) k_up_off<T, H, 32><<<dim3(cdiv(max_r, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, cb);
-          else k_up_off<T, H, 8><<<dim3(cdiv(max_r, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, cb);
-          LSA_LAUNCH_CHECK();
-          tr.mark("up_off", d, 0, cdiv(max_r, 32), cnt);
-          launches++;
-        }
-        continue;
-      }
-
-      for (int j0 = 0; j0 < maxk; j0 += SB) {
-        int act = 0, max_rows = 0;
-        for (int q = first; q < first + cnt; ++q) {
-          const Front& f = sym.fronts[lvl_front[q]];
-          if (f.k <= j0) break;
-          act++;
-          max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
-        }
-        const int gx = std::max(1, cdiv(max_rows, SB));
-        if (maxk > SB) k_step<T, H, true, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
-        else k_step<T, H, true, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
-        LSA_LAUNCH_CHECK();
-        tr.mark("up_step", d, j0, gx, act);
-        launches++;
-      }
+      const int gx = std::max(1, cdiv(max_rows, SB));
+      if (maxk > SB) k_step<T, H, true, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
+      else k_step<T, H, true, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
+      LSA_LAUNCH_CHECK();
+      tr.mark("up_step", d, j0, gx, act);
+      launches++;
     }
   }
   // ---- down sweep: roots first
-  for (int d = 0; d < sym.nlevels; ++d) {
-    const int lbeg = lvl_ptr[d], cnt_all = lvl_ptr[d + 1] - lbeg;
-    for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
-      const int cnt = std::min(YMAX, cnt_all - y0), first = lbeg + y0;
-      const int maxk = sym.fronts[lvl_front[first]].k;
-      int maxr = 0;
-      for (int q = first; q < first + cnt; ++q) maxr = std::max(maxr, sym.fronts[lvl_front[q]].r);
-      bool streamed = false;
-      if constexpr (scalar_traits<T>::is_complex) {
-        if (h.use_stream && (maxk <= SB || cnt >= h.stream_min_fronts) &&
-            launch_front_stream<H, false>(h, st, cnt, d_lvl_front, first, maxk, maxr, maxk + maxr, fac, z, y, cb, H ? x : y)) {
-          tr.mark("down_stream", d, 0, cnt, 1);
-          launches++;
-          streamed = true;
+  for (size_t ci = 0; ci < h.solve_plan.size(); ++ci) {
+    const SolveChunk& c = h.solve_plan[ci];
+    const int d = c.level, cnt = c.cnt, first = c.first, maxk = c.maxk, maxr = c.max_r, max_mk = c.max_m;
+    bool streamed = false;
+    if constexpr (scalar_traits<T>::is_complex) {
+      if (c.mode == SOLVE_STREAM) {
+        if (!launch_front_stream<H, false>(h, st, cnt, d_lvl_front, first, maxk, maxr, maxk + maxr, fac, z, y, cb, H ? x : y))
+          throw std::runtime_error("streamed sweep does not fit although the plan says so");
+        tr.mark("down_stream", d, 0, cnt, 1);
+        launches++;
+        streamed = true;
+      }
+    }
+    if (!streamed && maxr > 0) {
+      if (maxr > 512) k_down_off<T, H, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
+      else k_down_off<T, H, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
+      LSA_LAUNCH_CHECK();
+      tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
+      launches++;
+    }
+    if (streamed) {
+    } else if (c.mode == SOLVE_INVERTED) {
+      if (maxk > 512) k_tri_gemv<T, H, false, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, y);
+      else k_tri_gemv<T, H, false, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, y);
+      LSA_LAUNCH_CHECK();
+      tr.mark("down_tri", d, 0, cdiv(maxk, 32), cnt);
+      launches++;
+    } else if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {
+      launch_sweep_slices<T, H, false>(st, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
+      tr.mark("down_slices", d, 16, 16 * cnt, 1);
+      launches++;
+    } else if (maxk > SB && max_mk <= h.cluster_max_rows && h.use_clusters) {
+      const int csize = cluster_width(cnt, maxk, h.num_sms, h.cluster_max_width);
+      sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
+      tr.mark("down_cluster", d, csize, csize * cnt, 1);
+      launches++;
+    } else {
+      for (int j0 = ((maxk - 1) / SB) * SB; j0 >= 0; j0 -= SB) {
+        int act = 0;
+        for (int q = first; q < first + cnt; ++q) {
+          if (sym.fronts[lvl_front[q]].k <= j0) break;
+          act++;
         }
-      }
-      if (!streamed && maxr > 0) {
-        if (maxr > 512) k_down_off<T, H, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
-        else k_down_off<T, H, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
+        if (act == 0) continue;
+        const int gx = std::max(1, cdiv(j0, SB));
+        if (maxk > SB) k_step<T, H, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
+        else k_step<T, H, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
         LSA_LAUNCH_CHECK();
-        tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
-        launches++;
-      }
-      int max_mk = 0;
-      for (int q = first; q < first + cnt; ++q) max_mk = std::max(max_mk, sym.fronts[lvl_front[q]].k + sym.fronts[lvl_front[q]].r);
-      if (streamed) {
-      } else if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {
-        launch_sweep_slices<T, H, false>(st, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
-        tr.mark("down_slices", d, 16, 16 * cnt, 1);
-        launches++;
-      } else if (maxk > SB && max_mk <= h.cluster_max_rows && h.use_clusters) {
-        int max_m = 0;
-        for (int q = first; q < first + cnt; ++q) max_m = std::max(max_m, sym.fronts[lvl_front[q]].k);
-        const int csize = cluster_width(cnt, max_m, h.num_sms, h.cluster_max_width);
-        sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb, h.cluster_lookahead);
-        tr.mark("down_cluster", d, csize, csize * cnt, 1);
-        launches++;
-      } else {
-        for (int j0 = ((maxk - 1) / SB) * SB; j0 >= 0; j0 -= SB) {
-          int act = 0;
-          for (int q = first; q < first + cnt; ++q) {
-            if (sym.fronts[lvl_front[q]].k <= j0) break;
-            act++;
-          }
-          if (act == 0) continue;
-          const int gx = std::max(1, cdiv(j0, SB));
-          if (maxk > SB) k_step<T, H, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
-          else k_step<T, H, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
-          LSA_LAUNCH_CHECK();
-          tr.mark("down_step", d, j0, gx, act);
-          launches++;
-        }
-      }
-      if (H) {
-        k_level_unpermute<<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_gperm, y, x);
-        LSA_LAUNCH_CHECK();
+        tr.mark("down_step", d, j0, gx, act);
         launches++;
       }
     }
-  }
-  if (nsub) {
-    k_bottom<T, H, false><<<bottom_grid, 256, 0, st>>>(h.d_fronts, h.d_bot_list, nsub, h.d_is_bottom, h.d_bot_state + 1,
-                                                       h.d_bot_state + 2, h.d_child_idx, h.d_ea_map, h.d_gperm, h.d_st_idx, fac,
-                                                       x, y, z, cb);
-    LSA_LAUNCH_CHECK();
-    tr.mark("down_bottom", -1, 0, bottom_grid, 1);
-    launches++;
+    if (H) {
+      k_level_unpermute<<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_gperm, y, x);
+      LSA_LAUNCH_CHECK();
+      launches++;
+    }
   }
   if (H) {
     if (sym.n_iso > 0) k_unpermute<<<cdiv(sym.n_iso, 256), 256, 0, st>>>(y, x, h.d_gperm, sym.n_iso);

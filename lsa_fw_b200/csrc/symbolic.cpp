@@ -611,30 +611,6 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
     }
     sym.pool_size[d & 1] = std::max(sym.pool_size[d & 1], c);
   }
-  // ---- bottom part of the tree for the solve sweeps: every front whose whole sub-tree consists of
-  // small fronts (pivot block <= 256, <= 1024 remaining rows).  These are swept by ONE persistent,
-  // dependency-driven kernel (k_bottom); the rest ("top") is swept level by level.
-  {
-    std::vector<char> bottom(ns, 0);
-    for (int s = 0; s < ns; ++s) bottom[s] = sym.fronts[s].k <= 256 && sym.fronts[s].r <= 1024;
-    for (int s = 0; s < ns; ++s)  // children precede parents: a non-bottom child disqualifies its ancestors
-      if (!bottom[s] && parent[s] >= 0) bottom[parent[s]] = 0;
-    // (one pass suffices because indices are a post-order: parent[s] > s)
-    sym.bot_list.clear();
-    sym.is_bottom.assign(ns, 0);
-    for (int s = 0; s < ns; ++s)
-      if (bottom[s]) {
-        sym.bot_list.push_back(s);
-        sym.is_bottom[s] = 1;
-      }
-    sym.top_lvl_ptr.assign(nlev + 1, 0);
-    sym.top_lvl_front.clear();
-    for (int d = 0; d < nlev; ++d) {
-      for (int q = sym.lvl_ptr[d]; q < sym.lvl_ptr[d + 1]; ++q)
-        if (!bottom[sym.lvl_front[q]]) sym.top_lvl_front.push_back(sym.lvl_front[q]);
-      sym.top_lvl_ptr[d + 1] = (int)sym.top_lvl_front.size();
-    }
-  }
   double t3 = now();
   sym.seconds[2] = t3 - t2;
 
@@ -648,15 +624,15 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
     if (it == e || *it != idx) return -1;
     return f.k + (int)(it - b);
   };
-  bool bad = false;
+  int bad = 0;
   sym.ea_map.resize(sym.st_idx.size());
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 256) reduction(| : bad)
   for (int c = 0; c < ns; ++c) {
     const Front& f = sym.fronts[c];
     if (f.parent < 0) continue;
     for (int t = 0; t < f.r; ++t) {
       const int li = local_index(f.parent, sym.st_idx[f.st0 + t]);
-      if (li < 0) bad = true;
+      if (li < 0) bad |= 1;
       sym.ea_map[f.st0 + t] = li;
     }
   }

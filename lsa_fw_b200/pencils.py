@@ -45,10 +45,20 @@ class Pencil:
     coords: np.ndarray
     """(n, dim) coordinates of every DOF (geometric hint for the ordering; optional to use)."""
     meta: dict = field(default_factory=dict)
+    a_visc: np.ndarray | None = None
+    """dA/d(1/Re) on A's pattern (same entry order as `A.data`), filled with `split_viscous=True`: the viscous
+    term is the only Reynolds-dependent one for a fixed base flow, so a Reynolds sweep on one mesh
+    (`.examples/eigenvalues.py:61-108`, BASELINE config 3) re-uses pattern AND assembly."""
 
     @property
     def n(self) -> int:
         return self.A.shape[0]
+
+    def a_data_at(self, re: float) -> np.ndarray:
+        """`A.data` of the same pencil at Reynolds number `re` (same base flow, same pattern)."""
+        if self.a_visc is None:
+            raise ValueError("assemble with split_viscous=True to sweep the Reynolds number")
+        return self.A.data + (1.0 / re - 1.0 / self.meta["re"]) * self.a_visc
 
 
 # --------------------------------------------------------------------------- quadrature
@@ -192,6 +202,7 @@ def assemble_pencil(
     grading: tuple[float, ...] | None = None,
     quad_order: int = 4,
     chunk: int = 200_000,
+    split_viscous: bool = False,
 ) -> Pencil:
     """Assemble (A, M) for the linearised Navier-Stokes operator around `baseflow`.
 
@@ -271,12 +282,21 @@ def assemble_pencil(
             dphi[:, -1, i] = scale * np.prod(np.delete(lam, i, axis=1), axis=1)
     psi = lam  # pressure P1 basis (nq, nv)
 
+    # reference-element tensors of the element-matrix GEMMs below
+    ref_PP = np.einsum("qa,qb->qab", phi, phi).reshape(nq, nbv * nbv)
+    ref_S = np.einsum("q,qai,qbj->ijab", wq, dphi, dphi).reshape(nv * nv, nbv * nbv)
+    ref_T = np.einsum("qa,qbi->qiab", phi, dphi).reshape(nq * nv, nbv * nbv)
+    ref_R = np.einsum("q,qc,qai->iac", wq, psi, dphi)
+
     rows_A: list[np.ndarray] = []
     cols_A: list[np.ndarray] = []
     vals_A: list[np.ndarray] = []
     rows_M: list[np.ndarray] = []
     cols_M: list[np.ndarray] = []
     vals_M: list[np.ndarray] = []
+    rows_K: list[np.ndarray] = []
+    cols_K: list[np.ndarray] = []
+    vals_K: list[np.ndarray] = []
 
     for c0 in range(0, ncell, chunk):
         cv = cells[c0 : c0 + chunk]
@@ -289,19 +309,27 @@ def assemble_pencil(
         Jinv = np.linalg.inv(J)
         # grad lam_i: rows of Jinv for i>=1, minus their sum for i = 0  -> (ne, nv, dim)
         glam = np.concatenate([-Jinv.sum(axis=1, keepdims=True), Jinv], axis=1)
-        # basis gradients at quadrature points: (ne, nq, nbv, dim)
-        gphi = np.einsum("qbi,eid->eqbd", dphi, glam)
         xq = np.einsum("qi,eid->eqd", lam, X)
         U, GU = baseflow(xq.reshape(-1, dim))
         U = U.reshape(ne, nq, dim)
         GU = GU.reshape(ne, nq, dim, dim)
         w = wq[None, :] * detJ[:, None]  # (ne, nq)
 
-        mass = np.einsum("eq,qa,qb->eab", w, phi, phi)
-        stiff = np.einsum("eq,eqad,eqbd->eab", w, gphi, gphi)
-        conv = np.einsum("eq,qa,eqd,eqbd->eab", w, phi, U, gphi)
-        shear = np.einsum("eq,qa,qb,eqij->eaibj", w, phi, phi, GU)
-        grad_p = np.einsum("eq,qc,eqad->eadc", w, psi, gphi)  # (ne, nbv, dim, nv)
+        # Element matrices as GEMMs against reference-element tensors (the elements are affine, so the basis
+        # gradients are dphi/dlam contracted with the constant grad lam of the element):
+        #   mass  = sum_q w phi_a phi_b                         = w (ne x nq) @ PP (nq x nb^2)
+        #   stiff = sum_q w grad phi_a . grad phi_b             = G (ne x nv^2) @ S (nv^2 x nb^2)
+        #   conv  = sum_q w phi_a (U . grad phi_b)              = Cq (ne x nq nv) @ T (nq nv x nb^2)
+        #   shear = sum_q w phi_a phi_b dU_i/dx_j               = WG (ne dim^2 x nq) @ PP
+        #   grad_p= sum_q w psi_c d phi_a / dx_d                = detJ glam . R
+        mass = (w @ ref_PP).reshape(ne, nbv, nbv)
+        G = np.einsum("e,eid,ejd->eij", detJ, glam, glam).reshape(ne, nv * nv)
+        stiff = (G @ ref_S).reshape(ne, nbv, nbv)
+        Cq = np.einsum("eq,eqd,eid->eqi", w, U, glam, optimize=True).reshape(ne, nq * nv)
+        conv = (Cq @ ref_T).reshape(ne, nbv, nbv)
+        WG = np.ascontiguousarray((w[:, :, None, None] * GU).transpose(0, 2, 3, 1)).reshape(ne * dim * dim, nq)
+        shear = np.ascontiguousarray((WG @ ref_PP).reshape(ne, dim, dim, nbv, nbv).transpose(0, 3, 1, 4, 2))
+        grad_p = np.einsum("e,eid,iac->eadc", detJ, glam, ref_R, optimize=True)  # (ne, nbv, dim, nv)
 
         # global DOF ids
         vert_node = (cv * strides[None, None, :]).sum(axis=2)  # (ne, nv)
@@ -323,6 +351,11 @@ def assemble_pencil(
         r = np.broadcast_to(vd[:, :, :, None, None], Kuu.shape)
         c = np.broadcast_to(vd[:, None, None, :, :], Kuu.shape)
         rows_A.append(r.ravel()); cols_A.append(c.ravel()); vals_A.append(Kuu.ravel())
+        if split_viscous:
+            for comp in range(dim):
+                rows_K.append(np.broadcast_to(vd[:, :, comp, None], stiff.shape).ravel())
+                cols_K.append(np.broadcast_to(vd[:, None, :, comp], stiff.shape).ravel())
+                vals_K.append(-stiff.ravel())
         # pressure gradient (p, div v) and divergence (q, div u)
         r = np.broadcast_to(vd[:, :, :, None], grad_p.shape)
         c = np.broadcast_to(pd[:, None, None, :], grad_p.shape)
@@ -345,7 +378,12 @@ def assemble_pencil(
     M = sp.coo_matrix(
         (np.concatenate(vals_M), (np.concatenate(rows_M), np.concatenate(cols_M))), shape=(n, n)
     ).tocsr()
-    del rows_A, cols_A, vals_A, rows_M, cols_M, vals_M
+    Kv = None
+    if split_viscous:
+        Kv = sp.coo_matrix(
+            (np.concatenate(vals_K), (np.concatenate(rows_K), np.concatenate(cols_K))), shape=(n, n)
+        ).tocsr()
+    del rows_A, cols_A, vals_A, rows_M, cols_M, vals_M, rows_K, cols_K, vals_K
 
     # ---- DOF bookkeeping
     vel_nodes = np.nonzero(has_vel)[0]
@@ -377,28 +415,47 @@ def assemble_pencil(
         # pin_dof is applied to A only in the reference (FEM/utils.py:596-602); M row stays zero
         pass
 
+    A = _canonical(A)
+    a_visc = None
+    if Kv is not None:
+        # the viscous part on A's pattern: Dirichlet rows / columns dropped, entries located by (row, col) key
+        drop = np.zeros(n, dtype=bool)
+        drop[np.concatenate([bc, pinned])] = True
+        Kc = Kv.tocoo()
+        keep = ~(drop[Kc.row] | drop[Kc.col])
+        key_a = np.repeat(np.arange(n, dtype=np.int64), np.diff(A.indptr)) * n + A.indices
+        key_k = Kc.row[keep].astype(np.int64) * n + Kc.col[keep]
+        pos = np.searchsorted(key_a, key_k)
+        if not np.array_equal(key_a[pos], key_k):
+            raise RuntimeError("viscous entries outside the pattern of A")
+        a_visc = np.zeros(A.nnz)
+        a_visc[pos] = Kc.data[keep]
+        del Kc, key_a, key_k, pos
     meta = dict(
         dim=dim, shape=tuple(shape), lengths=tuple(lengths), re=re, space=space,
         n_u=len(dofs_u), n_p=len(dofs_p), n_dirichlet=len(bc), pinned=pinned.tolist(),
     )
     return Pencil(
-        A=_canonical(A), M=_canonical(M), dofs_u=dofs_u.astype(np.int64),
-        dofs_p=dofs_p.astype(np.int64), dirichlet=bc.astype(np.int64), coords=coords, meta=meta,
+        A=A, M=_canonical(M), dofs_u=dofs_u.astype(np.int64),
+        dofs_p=dofs_p.astype(np.int64), dirichlet=bc.astype(np.int64), coords=coords, meta=meta, a_visc=a_visc,
     )
 
 
 def _apply_identity_rows_cols(mat: sp.csr_matrix, dofs: np.ndarray) -> sp.csr_matrix:
+    """Rows and columns `dofs` removed from the pattern and replaced by a unit diagonal
+    (`FEM/operators.py:483-486`).  Purely structural: no entry is dropped because of its VALUE, so the pattern
+    is the same for every Reynolds number / base flow (one symbolic analysis per mesh)."""
     if len(dofs) == 0:
         return mat
     n = mat.shape[0]
-    keep = np.ones(n)
-    keep[dofs] = 0.0
-    D = sp.diags(keep)
-    out = (D @ mat @ D).tocsr()
-    ident = sp.csr_matrix((np.ones(len(dofs)), (dofs, dofs)), shape=(n, n))
-    out = (out + ident).tocsr()
-    out.eliminate_zeros()
-    return out
+    drop = np.zeros(n, dtype=bool)
+    drop[dofs] = True
+    coo = mat.tocoo()
+    keep = ~(drop[coo.row] | drop[coo.col])
+    rows = np.concatenate([coo.row[keep], dofs])
+    cols = np.concatenate([coo.col[keep], dofs])
+    vals = np.concatenate([coo.data[keep], np.ones(len(dofs))])
+    return sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
 
 
 def _canonical(mat: sp.csr_matrix) -> sp.csr_matrix:

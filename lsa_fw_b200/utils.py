@@ -154,30 +154,45 @@ _FACTOR_REGISTRY: dict[tuple[int, int], "weakref.ReferenceType[iEpsSolver]"] = {
 
 
 def clear_symbolic_cache() -> None:
-    """Drop cached symbolic analyses (and their device buffers)."""
-    for h in _SYM_CACHE.values():
-        h.close()
+    """Drop cached symbolic analyses.  A handle (and its device buffers) is released as soon as no solver
+    object refers to it any more; handles still in use by live solvers stay valid."""
     _SYM_CACHE.clear()
     _FACTOR_REGISTRY.clear()
 
 
-_HASH_MEMO: dict[tuple, bytes] = {}
+_HASH_MEMO: dict[int, tuple] = {}
+
+
+def _sample_digest(arr: np.ndarray) -> bytes:
+    n = arr.size
+    return hashlib.blake2b(arr[:: max(1, n // 4096)].tobytes(), digest_size=8).digest()
 
 
 def _array_digest(arr: np.ndarray) -> bytes:
-    """blake2b of an index array, memoised on (buffer address, length, 4096 sampled entries) so that the
-    repeated solves of a sweep do not re-hash ~100 MB of pattern per call."""
+    """blake2b of an index array.  Memoised per array OBJECT so that the repeated solves of a sweep do not
+    re-hash ~100 MB of pattern per call: the memo keeps a reference to the array (its address cannot be handed
+    to another array while the entry lives) and is only trusted when the array is the same object, of the same
+    length, with the same 4096 sampled entries and the same int64 checksum of a 64 Ki-entry stride sample."""
     arr = np.ascontiguousarray(arr)
     n = arr.size
-    sample = arr[:: max(1, n // 4096)].tobytes()
-    key = (arr.__array_interface__["data"][0], n, arr.dtype.str, hashlib.blake2b(sample, digest_size=8).digest())
-    dig = _HASH_MEMO.get(key)
-    if dig is None:
-        dig = hashlib.blake2b(arr.tobytes(), digest_size=16).digest()
-        if len(_HASH_MEMO) > 64:
-            _HASH_MEMO.clear()
-        _HASH_MEMO[key] = dig
+    probe = (n, arr.dtype.str, _sample_digest(arr), int(arr[:: max(1, n // 65536)].sum(dtype=np.int64)))
+    hit = _HASH_MEMO.get(id(arr))
+    if hit is not None and hit[0] is arr and hit[1] == probe:
+        return hit[2]
+    dig = hashlib.blake2b(arr.tobytes(), digest_size=16).digest()
+    if len(_HASH_MEMO) > 64:
+        _HASH_MEMO.clear()
+    _HASH_MEMO[id(arr)] = (arr, probe, dig)
     return dig
+
+
+def _values_token(mat) -> tuple:
+    """Identity + cheap content probe of a value array: (the array object, its sampled digest)."""
+    return (mat.data, _sample_digest(mat.data))
+
+
+def _same_values(token: tuple, mat) -> bool:
+    return token is not None and token[0] is mat.data and token[1] == _sample_digest(mat.data)
 
 
 def _pattern_key(a: sp.csr_matrix, m: sp.csr_matrix | None, extra: tuple) -> str:
@@ -293,10 +308,14 @@ class iEpsSolver:  # noqa: N801
         self._interval = None
         # backend options (extensions; all optional)
         self._opts = dict(leaf_size=64, coords=None, refine_steps=0, tiny_pivot=1e-13, seed=0, device=0,
-                          purify=True, nthreads=0, v0=None, force_complex=False, coupled_fraction=0.5)
+                          purify=True, nthreads=0, v0=None, force_complex=False, coupled_fraction=0.5,
+                          growth_limit=1e6, device_values=None)
         self._adjoint = False
         self._handle: _lib.Handle | None = None
         self._factor_key = None
+        self._factor_gen = -1      # generation of the handle's numeric state right after OUR factorisation
+        self._result_gen = -1      # ... right after OUR eigensolve (device-side results still ours)
+        self._factor_tokens = None  # identity + content probes of the value arrays that were factored
         self._stats: dict = {}
         self._nconv = 0
         self._eigenvalues: np.ndarray = np.zeros(0, dtype=complex)
@@ -359,7 +378,12 @@ class iEpsSolver:  # noqa: N801
     # ------------------------------------------------------------------ extensions
     def set_backend_options(self, **kw) -> None:
         """B200-backend knobs: leaf_size, coords (n x dim ordering hint), refine_steps, tiny_pivot,
-        seed, device, purify, nthreads, v0 (start vector), force_complex, coupled_fraction."""
+        seed, device, purify (True: through the Krylov-Schur relation; "explicit": one OP apply per vector),
+        nthreads, v0 (start vector), force_complex, coupled_fraction, growth_limit (largest LU multiplier
+        tolerated before the solve re-analyses / switches iterative refinement on), device_values
+        ((A_vals, M_vals) already resident on the GPU, in CSR entry order: torch CUDA tensors or any object
+        with `__cuda_array_interface__` / `__dlpack__`; the host copies in A / M are then only used for
+        their pattern)."""
         unknown = set(kw) - set(self._opts)
         if unknown:
             raise TypeError(f"unknown backend option(s): {sorted(unknown)}")
@@ -405,6 +429,15 @@ class iEpsSolver:  # noqa: N801
         ref = _FACTOR_REGISTRY.get((id(a0), id(m0) if m0 is not None else 0))
         other = ref() if ref is not None else None
         if other is None or other._handle is None or other._factor_key is None:
+            return None
+        # the handle may be shared (symbolic cache): it must still hold OUR donor's values and factors, and the
+        # donor's matrices must not have been changed since they were factored
+        if other._handle.closed or other._handle.gen_factor != other._factor_gen:
+            return None
+        toks = other._factor_tokens
+        if toks is None or not _same_values(toks[0], _as_csr(other._A)):
+            return None
+        if other._M is not None and not _same_values(toks[1], _as_csr(other._M)):
             return None
         if other._st_type != iSTType.SINVERT or self._st_type != iSTType.SINVERT:
             return None
@@ -457,24 +490,33 @@ class iEpsSolver:  # noqa: N801
             use_complex = data_complex or sigma.imag != 0.0 or self._opts["force_complex"]
             self._complex_mode = use_complex
             coords = self._opts["coords"]
-            key = _pattern_key(A, M, (self._opts["leaf_size"], None if coords is None else id(coords),
-                                      self._opts["device"], self._opts["coupled_fraction"]))
             t0 = time.perf_counter()
+            # zero diagonal of the matrix to be factored (pressure rows): ordered last inside their fronts.
+            # Shift-independent form for sinvert (rows whose diagonal vanishes in A AND in M), so that the
+            # analysis is valid for every shift of a sweep; part of the cache key together with the transform.
+            if sinvert:
+                order_last = ((A.diagonal() == 0) & ((M.diagonal() if M is not None else np.ones(n)) == 0))
+            else:
+                order_last = (M.diagonal() if M is not None else A.diagonal()) == 0
+            order_last = order_last.astype(np.uint8)
+            key = _pattern_key(A, M, (self._opts["leaf_size"],
+                                      None if coords is None else hashlib.blake2b(
+                                          np.ascontiguousarray(coords).tobytes(), digest_size=16).hexdigest(),
+                                      self._opts["device"], self._opts["coupled_fraction"], self._st_type.value,
+                                      hashlib.blake2b(order_last.tobytes(), digest_size=16).hexdigest()))
             h = _SYM_CACHE.get(key)
+            if h is not None and h.closed:
+                h = None
             if h is None:
                 h = _lib.Handle(n, self._opts["device"])
                 h.set_option("coupled_fraction", self._opts["coupled_fraction"])
-                # structurally zero diagonal of the matrix to be factored (pressure rows): ordered last
-                if sinvert:
-                    dF = A.diagonal() - sigma * (M.diagonal() if M is not None else np.ones(n))
-                else:
-                    dF = M.diagonal() if M is not None else A.diagonal()
-                order_last = (dF == 0).astype(np.uint8)
                 h.analyze(A.indptr, A.indices, None if M is None else M.indptr, None if M is None else M.indices,
                           leaf_size=self._opts["leaf_size"], coords=coords, order_last=order_last,
                           nthreads=self._opts["nthreads"])
                 while len(_SYM_CACHE) >= _SYM_CACHE_MAX:
-                    _SYM_CACHE.pop(next(iter(_SYM_CACHE))).close()
+                    # evicted handles are NOT closed here: live solvers (and adjoint donors) may still hold
+                    # them; the device buffers go when the last reference does
+                    _SYM_CACHE.pop(next(iter(_SYM_CACHE)))
                 _SYM_CACHE[key] = h
                 stats["symbolic_cached"] = False
             else:
@@ -486,7 +528,11 @@ class iEpsSolver:  # noqa: N801
                          n_decoupled=info.n_decoupled, max_front=info.max_front,
                          symbolic_phases=list(info.seconds))
             t0 = time.perf_counter()
-            h.set_values(A.data, None if M is None else M.data)
+            dv = self._opts["device_values"]
+            if dv is not None:
+                h.set_values_device(dv[0], None if M is None else dv[1])
+            else:
+                h.set_values(A.data, None if M is None else M.data)
             stats["upload_seconds"] = time.perf_counter() - t0
             sigma_fact = sigma
             if needs_factor:
@@ -502,18 +548,39 @@ class iEpsSolver:  # noqa: N801
                     self._opts["coupled_fraction"] = 1.0
                     self._factor_key = None
                     return self.solve()
+                refine_steps = int(self._opts["refine_steps"])
+                if sinvert and fs.max_multiplier > self._opts["growth_limit"]:
+                    # element growth of the restricted pivoting (candidates = the current 128-row block): the
+                    # factors are inaccurate.  First the robust placement of the zero-diagonal unknowns, then
+                    # iterative refinement inside every operator application.
+                    if self._opts["coupled_fraction"] < 1.0:
+                        logger.warning("LU multiplier growth %.2e > %.1e; re-analysing with coupled_fraction = 1",
+                                       fs.max_multiplier, self._opts["growth_limit"])
+                        self._opts["coupled_fraction"] = 1.0
+                        self._factor_key = None
+                        return self.solve()
+                    refine_steps = max(refine_steps, 2)
+                    logger.warning("LU multiplier growth %.2e > %.1e; %d iterative-refinement steps per solve enabled",
+                                   fs.max_multiplier, self._opts["growth_limit"], refine_steps)
+                    stats["refine_steps_forced"] = refine_steps
+                self._refine_steps_effective = refine_steps
                 stats.update(factor_seconds=fs.seconds, factor_flops=fs.flops, n_perturbed=fs.n_perturbed,
                              n_row_swaps=fs.n_row_swaps, min_pivot=fs.min_pivot, max_pivot=fs.max_pivot,
                              max_multiplier=fs.max_multiplier,
                              factor_kernels=fs.n_kernels)
                 self._factor_key = (sigma_fact, self._st_type)
+                self._factor_gen = h.gen_factor
+                self._factor_tokens = (_values_token(A), None if self._M is None else _values_token(M))
                 _FACTOR_REGISTRY[(id(self._A), id(self._M) if self._M is not None else 0)] = weakref.ref(self)
 
         which = self._which_effective()
         res = h.eigs(nev=self._nev, ncv=self._ncv_effective(), tol=self._tol, max_restarts=self._max_it,
                      which=which.value, transform=_lib.LSA_ST_SINVERT if sinvert else _lib.LSA_ST_SHIFT,
-                     sigma=sigma_fact, adjoint=adjoint, purify=self._opts["purify"] and sinvert,
-                     refine_steps=self._opts["refine_steps"], seed=self._opts["seed"], v0=self._opts["v0"])
+                     sigma=sigma_fact, adjoint=adjoint, purify=(2 if self._opts["purify"] == "explicit" else int(bool(self._opts["purify"]))) if sinvert else 0,
+                     refine_steps=(donor._refine_steps_effective if donor is not None
+                                   else getattr(self, "_refine_steps_effective", self._opts["refine_steps"])),
+                     seed=self._opts["seed"], v0=self._opts["v0"])
+        self._result_gen = h.gen_result
         self._nconv = res.nconv
         self._eigenvalues = h.eigenvalues(res.nconv)
         # the handle (and its device buffers) may be shared with other solver objects through the
@@ -599,4 +666,19 @@ class iEpsSolver:  # noqa: N801
         """||A x - λ M x|| / (||A||_F ||x||) of every converged pair, evaluated on the device."""
         if self._nconv == 0:
             return np.zeros(0)
+        if self._handle.closed or self._handle.gen_result != self._result_gen:
+            raise RuntimeError("the device-side results of this solver were overwritten by a later solve on the "
+                               "shared handle (same sparsity pattern); call solve() again before get_residuals()")
         return self._handle.residuals(self._nconv)
+
+    def release(self) -> None:
+        """Free the device memory behind this solver now (the handle also leaves the symbolic cache).  Other
+        solver objects that share the handle need a new `solve()` afterwards."""
+        h = self._handle
+        if h is None:
+            return
+        for k in [k for k, v in _SYM_CACHE.items() if v is h]:
+            del _SYM_CACHE[k]
+        h.close()
+        self._handle = None
+        self._factor_key = None

@@ -296,9 +296,9 @@ def test_gram_schmidt_refinement_if_needed_matches_always():
 
 
 def test_large_front_paths_real_factor():
-    """Same 3-D cavity with a REAL shift: real FP64 factor (the reference's real PETSc build) through the multi-step
-    kernels -- sliced / chunked cluster sweeps, deferred contribution rows, per-step launches; the streamed kernel is
-    complex-only, so the wide levels take the plain-load path here."""
+    """Same 3-D cavity with a REAL shift: real FP64 factor (the reference's real PETSc build): whole-block inverses +
+    triangular GEMVs on every level (the streamed kernel is complex-only), and with `invert_max_k` lowered the
+    multi-step kernels -- sliced / chunked cluster sweeps, deferred contribution rows, per-step launches."""
     import scipy.sparse.linalg as spla
 
     pc = pencils.cavity_3d(8)
@@ -312,9 +312,9 @@ def test_large_front_paths_real_factor():
     lu = spla.splu(C)
     b = np.random.default_rng(5).standard_normal(pc.n) + 1j * np.random.default_rng(6).standard_normal(pc.n)
     xs = lu.solve(b.real) + 1j * lu.solve(b.imag)
-    for opts in (dict(), dict(cluster_slices=0), dict(cluster_slices=0, defer_cb=0), dict(use_clusters=0),
-                 dict(cluster_slices=0, cluster_lookahead=1)):
-        for opt, val in dict(dict(cluster_slices=1, defer_cb=1, use_clusters=1, cluster_lookahead=0), **opts).items():
+    for opts in (dict(), dict(invert_max_k=256), dict(invert_max_k=0), dict(invert_max_k=0, cluster_slices=0),
+                 dict(invert_max_k=0, cluster_slices=0, defer_cb=0), dict(invert_max_k=0, use_clusters=0)):
+        for opt, val in dict(dict(cluster_slices=1, defer_cb=1, use_clusters=1, invert_max_k=4096), **opts).items():
             h.set_option(opt, val)
         fs = h.factor(1.0, -sigma, _lib.LSA_F64, 1e-13)
         assert fs.scalar == _lib.LSA_F64 and fs.n_perturbed == 0
@@ -526,8 +526,9 @@ def test_singular_pencil_is_perturbed_not_crashed(caplog):
 
 
 def test_large_front_paths_match_scipy_solve():
-    """3-D cavity with fronts of several hundred pivots: multi-step cluster sweeps, streamed (bulk-copy) sweeps in
-    every tile geometry / ring depth / CTA shape, per-step launches, rank-128 deferred updates."""
+    """3-D cavity with fronts of several hundred pivots: whole-block inverses + triangular GEMVs (default), and with
+    `invert_max_k` lowered the multi-step cluster sweeps; streamed (bulk-copy) sweeps in every tile geometry / ring
+    depth / CTA shape, per-step launches, rank-128 deferred updates."""
     import scipy.sparse.linalg as spla
 
     pc = pencils.cavity_3d(8)
@@ -542,15 +543,17 @@ def test_large_front_paths_match_scipy_solve():
     C = (pc.A - sigma * pc.M).tocsc()
     b = np.random.default_rng(3).standard_normal(pc.n) + 1j * np.random.default_rng(4).standard_normal(pc.n)
     xs = spla.splu(C).solve(b)
-    base = dict(use_clusters=1, use_subtrees=0, use_graphs=1, use_stream=1, stream_min_fronts=96, stream_flags=3,
-                stream_small_rows=192, stream_stages=0, cluster_max_rows=8192, cluster_max_width=16, cluster_lookahead=0, cluster_slices=1, defer_cb=1)
-    variants = (dict(), dict(use_subtrees=1), dict(use_clusters=0, use_subtrees=1), dict(use_clusters=0, use_graphs=0),
+    base = dict(use_clusters=1, use_graphs=1, use_stream=1, stream_min_fronts=96, stream_flags=3, invert_max_k=0,
+                stream_small_rows=192, stream_stages=0, cluster_max_rows=8192, cluster_max_width=16, cluster_slices=1, defer_cb=1)
+    variants = (dict(invert_max_k=4096), dict(invert_max_k=4096, use_graphs=0), dict(invert_max_k=4096, use_stream=0),
+                dict(invert_max_k=300), dict(invert_max_k=300, use_stream=0), dict(invert_max_k=128, stream_min_fronts=1),
+                dict(), dict(use_clusters=0, use_graphs=0),
                 dict(use_stream=0), dict(use_stream=0, use_clusters=0, cluster_max_rows=0),
                 dict(stream_min_fronts=1), dict(stream_min_fronts=1, stream_flags=0, stream_stages=2),
                 dict(stream_min_fronts=1, stream_flags=7, stream_small_rows=0),
                 dict(stream_min_fronts=4, stream_flags=1, stream_small_rows=100000, stream_stages=12),
-                dict(cluster_max_rows=1280, cluster_max_width=4), dict(cluster_slices=0), dict(cluster_slices=0, defer_cb=0), dict(cluster_slices=0, cluster_lookahead=1),
-                dict(cluster_slices=0, cluster_lookahead=1, use_stream=0, cluster_max_width=4), dict(use_stream=0, use_graphs=0),
+                dict(cluster_max_rows=1280, cluster_max_width=4), dict(cluster_slices=0), dict(cluster_slices=0, defer_cb=0),
+                dict(use_stream=0, use_graphs=0),
                 dict(use_stream=0, cluster_max_width=2), dict(use_stream=0, cluster_max_width=1),
                 dict(use_stream=0, cluster_max_width=8, use_graphs=0))
     for var in variants:

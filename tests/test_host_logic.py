@@ -94,25 +94,6 @@ def test_symbolic_counters_and_pattern_reuse():
     assert a_dst.max() < info.factor_entries
 
 
-def test_bottom_partition_is_closed_under_descendants():
-    pc = pencils.assemble_pencil((60, 30), (15.0, 6.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 3.0))
-    h = _lib.Handle(pc.n, device=-1)
-    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64,
-                     order_last=(pc.A.diagonal() == 0).astype(np.uint8))
-    bot, is_bot = h.symbolic_array("bot_list"), h.symbolic_array("is_bottom")
-    parent, k, r = h.symbolic_array("parent"), h.symbolic_array("front_k"), h.symbolic_array("front_r")
-    top, tp, level = h.symbolic_array("top_lvl_front"), h.symbolic_array("top_lvl_ptr"), h.symbolic_array("level")
-    assert len(bot) > 0 and np.all(np.diff(bot) > 0)                   # ascending = post-order (queue order)
-    assert sorted(bot.tolist()) == np.nonzero(is_bot)[0].tolist()
-    assert k[bot].max() <= 256 and r[bot].max() <= 1024
-    for s in range(info.n_fronts):                                      # a top front never sits below a bottom one
-        if parent[s] >= 0 and is_bot[parent[s]]:
-            assert is_bot[s]
-    assert sorted(top.tolist()) == np.nonzero(is_bot == 0)[0].tolist()
-    for d in range(info.n_levels):
-        assert np.all(level[top[tp[d]:tp[d + 1]]] == d)
-
-
 def test_options_and_pressure_placement_rule():
     pc = pencils.assemble_pencil((20, 10), (6.0, 2.0), re=40.0)
     flag = (pc.A.diagonal() == 0).astype(np.uint8)
@@ -142,15 +123,15 @@ def test_options_and_pressure_placement_rule():
     # sweep tuning knobs (include/lsa_b200.h): accepted without a device, value-checked where it matters
     for name, val in (("use_graphs", 0), ("use_clusters", 1), ("use_stream", 1), ("stream_min_fronts", 48),
                       ("stream_small_rows", 0), ("stream_stages", 6), ("stream_flags", 7), ("cluster_max_rows", 4096),
-                      ("cluster_max_width", 8), ("cluster_slices", 0), ("cluster_lookahead", 1), ("defer_cb", 0),
-                      ("ortho_refine_always", 1), ("use_subtrees", 0)):
+                      ("cluster_max_width", 8), ("cluster_slices", 0), ("invert_max_k", 1024), ("defer_cb", 0),
+                      ("ortho_refine_always", 1)):
         h.set_option(name, val)
-    for name, val in (("cluster_max_width", 3), ("stream_stages", 1), ("stream_stages", 13)):
+    for name, val in (("cluster_max_width", 3), ("stream_stages", 1), ("stream_stages", 13), ("invert_max_k", -1),
+                      ("use_subtrees", 1), ("cluster_lookahead", 1)):   # the last two were removed with their kernels
         with pytest.raises(_lib.LsaError):
             h.set_option(name, val)
     h.set_option("use_graphs", 0)
     h.set_option("use_clusters", 0)
-    h.set_option("use_subtrees", 0)
 
 
 # ------------------------------------------------------------------------------- Rayleigh-Ritz core
