@@ -99,6 +99,11 @@ typedef struct {
   double seconds_solve, seconds_spmv, seconds_ortho, seconds_rr, seconds_restart;
   int32_t n_kernels;
   int32_t n_reorth;             /* basis columns that needed the second Gram-Schmidt pass */
+  int32_t n_arnoldi;            /* Arnoldi expansion steps (one Gram-Schmidt each)         */
+  int32_t pad;
+  int64_t sum_cols;             /* sum over those steps of the number of basis columns orthogonalised against:
+                                   algorithmic bytes of the orthogonalisation =
+                                   (1 + n_reorth / n_arnoldi) * (2 sum_cols + 5 n_arnoldi) * n * 16   */
 } lsa_eigs_result;
 
 typedef struct {

@@ -69,7 +69,8 @@ class EigsResult(C.Structure):
         ("nconv", C.c_int32), ("n_restarts", C.c_int32), ("n_op_applies", C.c_int32), ("breakdown", C.c_int32),
         ("seconds", C.c_double), ("seconds_solve", C.c_double), ("seconds_spmv", C.c_double),
         ("seconds_ortho", C.c_double), ("seconds_rr", C.c_double), ("seconds_restart", C.c_double),
-        ("n_kernels", C.c_int32), ("n_reorth", C.c_int32),
+        ("n_kernels", C.c_int32), ("n_reorth", C.c_int32), ("n_arnoldi", C.c_int32), ("pad", C.c_int32),
+        ("sum_cols", C.c_int64),
     ]
 
 

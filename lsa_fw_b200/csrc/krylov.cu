@@ -742,7 +742,8 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   } else {
     k_randn<<<blocks, 256, 0, st>>>(h.d_x, n, p.seed);
   }
-  int n_applies = 0;
+  int n_applies = 0, n_arnoldi = 0;
+  long long sum_cols = 0;
   apply_op(h, p, h.d_x, h.d_w, t_spmv, t_solve);
   n_applies++;
   k_norm2_part<<<blocks, 256, 0, st>>>(n, h.d_w, h.d_npart);
@@ -761,6 +762,8 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       n_applies++;
       const size_t e = t_ortho.begin();
       const int jj = j + 1;  // orthogonalise against columns 0..j
+      n_arnoldi++;
+      sum_cols += jj;
       z128* scol = S + (long long)j * ld;
       // classical Gram-Schmidt, second pass only when the criterion asks for it (decided on the device: the
       // pass-2 kernels return at once when the flag is clear)
@@ -905,6 +908,8 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   LSA_CUDA(cudaMemcpyAsync(&n_reorth, h.d_refine + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   LSA_CUDA(cudaStreamSynchronize(st));
   out.n_reorth = n_reorth;
+  out.n_arnoldi = n_arnoldi;
+  out.sum_cols = sum_cols;
   out.nconv = nconv;
   out.n_restarts = restarts;
   out.n_op_applies = n_applies;

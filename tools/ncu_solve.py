@@ -17,9 +17,12 @@ trans = sys.argv[3] if len(sys.argv) > 3 else "N"
 pc, sigma = {"cfg2_quarter": (lambda: (pencils.backward_step_2d(334, 84), -0.35 + 0.1j)),
              "cfg2": (lambda: (pencils.backward_step_2d(), -0.35 + 0.1j)),
              "cfg1": (lambda: (pencils.cylinder_wake_2d(), 0.05 + 0.74j)),
-             "cav3d": (lambda: (pencils.cavity_3d(16), 0.1 + 0.3j))}[name]()
+             "cfg3": (lambda: (pencils.adapted_wake_2d(re=100.0), 0.135 + 0.727j)),
+             "cfg3_quarter": (lambda: (pencils.adapted_wake_2d(578, 145, re=100.0), 0.135 + 0.727j)),
+             "cav3d": (lambda: (pencils.cavity_3d(16), 0.1 + 0.3j)),
+             "cav3d24": (lambda: (pencils.cavity_3d(24), 0.1 + 0.3j))}[name]()
 h = _lib.Handle(pc.n, 0)
-flag = ((pc.A.diagonal() - sigma * pc.M.diagonal()) == 0).astype(np.uint8)
+flag = ((pc.A.diagonal() == 0) & (pc.M.diagonal() == 0)).astype(np.uint8)
 h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=flag)
 h.set_values(pc.A.data, pc.M.data)
 h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)

@@ -14,10 +14,13 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg2_quarter"
 pc, sigma = {"cfg2_quarter": (lambda: (pencils.backward_step_2d(334, 84), 1.0j)),
              "cfg2": (lambda: (pencils.backward_step_2d(), 1.0j)),
              "cfg1": (lambda: (pencils.cylinder_wake_2d(), 0.05 + 0.74j)),
-             "cav3d": (lambda: (pencils.cavity_3d(16), 0.1 + 0.3j))}[name]()
+             "cfg3": (lambda: (pencils.adapted_wake_2d(re=100.0), 0.135 + 0.727j)),
+             "cfg3_quarter": (lambda: (pencils.adapted_wake_2d(578, 145, re=100.0), 0.135 + 0.727j)),
+             "cav3d": (lambda: (pencils.cavity_3d(16), 0.1 + 0.3j)),
+             "cav3d24": (lambda: (pencils.cavity_3d(24), 0.1 + 0.3j))}[name]()
 os.environ.pop("LSA_TRACE", None)
 h = _lib.Handle(pc.n, 0)
-flag = ((pc.A.diagonal() - sigma * pc.M.diagonal()) == 0).astype(np.uint8)
+flag = ((pc.A.diagonal() == 0) & (pc.M.diagonal() == 0)).astype(np.uint8)
 h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=flag)
 h.set_values(pc.A.data, pc.M.data)
 h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
@@ -35,8 +38,7 @@ for _ in range(20):
 print(f"{name}: host-roundtrip solve {(time.perf_counter() - t0) / 20 * 1e3:.3f} ms (incl. 2 x {pc.n * 16 / 1e6:.0f} MB PCIe copies)", flush=True)
 r = h.eigs(nev=4, ncv=24, tol=1e-8, max_restarts=2, which="TARGET_MAGNITUDE", transform=_lib.LSA_ST_SINVERT, sigma=sigma, seed=1)
 print(f"{name}: device sweep {r.seconds_solve / r.n_op_applies * 1e3:.3f} ms/apply over {r.n_op_applies} applies "
-      f"(LSA_SUBTREE_DIV={os.environ.get('LSA_SUBTREE_DIV')}, NO_SUBTREES={os.environ.get('LSA_NO_SUBTREES')}, "
-      f"NO_GRAPHS={os.environ.get('LSA_NO_GRAPHS')})", flush=True)
+      f"(INVERT_MAX_K={os.environ.get('LSA_INVERT_MAX_K')}, NO_GRAPHS={os.environ.get('LSA_NO_GRAPHS')})", flush=True)
 os.environ["LSA_TRACE"] = "1"
 h.solve(b, _lib.LSA_OP_H if "--H" in sys.argv else _lib.LSA_OP_N)
 os.environ.pop("LSA_TRACE")
