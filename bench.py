@@ -337,6 +337,90 @@ def lu3d_line(n_cells: int, device_index: int, fp64_peak: float) -> dict:
         h.close()
 
 
+def partitioned_section(n_cells: int, rank: int, world: int, local_rank: int, device) -> dict | None:
+    """ONE factorisation + eigensolve of a 3-D cavity pencil split over the `world` GPUs (sub-trees per GPU,
+    replicated top, NCCL inside the CUDA library), against the same computation on one GPU (rank 0, alone)."""
+    import torch
+    import torch.distributed as dist
+
+    from lsa_fw_b200 import _lib, pencils
+    from lsa_fw_b200.partitioned import attach_comm, make_handle
+
+    pc = pencils.cavity_3d(n_cells)
+    sigma, nev, ncv = 0.1 + 0.3j, 10, 80
+    flags = order_last_flags(pc)
+    v0 = np.random.default_rng(4321).standard_normal(pc.n).astype(np.complex128)
+
+    def run(h):
+        h.set_values(pc.A.data, pc.M.data)
+        h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)                      # warm-up (allocations, communicator set-up)
+        dist.barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        fs = h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
+        t_f = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r = h.eigs(nev=nev, ncv=ncv, tol=TOL, max_restarts=MAX_RESTARTS, which="TARGET_MAGNITUDE",
+                   transform=_lib.LSA_ST_SINVERT, sigma=sigma, v0=v0)
+        t_e = time.perf_counter() - t0
+        lam = h.eigenvalues(min(nev, r.nconv))
+        res = float(h.residuals(min(nev, r.nconv)).max()) if r.nconv else None
+        return fs, r, t_f, t_e, lam, res
+
+    h = make_handle(pc.n, local_rank)
+    t0 = time.perf_counter()
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=flags)
+    t_sym = time.perf_counter() - t0
+    attach_comm(h)
+    pi = h.partition_info()
+    fs, r, t_f, t_e, lam, res = run(h)
+    t = torch.tensor([t_f, t_e, fs.seconds, r.seconds, r.seconds_solve, r.seconds_ortho, r.seconds_spmv], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mem = torch.tensor([float(info.factor_entries) * 16], dtype=torch.float64, device=device)
+    dist.all_reduce(mem, op=dist.ReduceOp.MAX)
+    h.close()
+    out = None
+    if rank == 0:
+        h1 = _lib.Handle(pc.n, local_rank)
+        i1 = h1.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=flags)
+        h1.set_values(pc.A.data, pc.M.data)
+        h1.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
+        t0 = time.perf_counter()
+        fs1 = h1.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
+        t_f1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r1 = h1.eigs(nev=nev, ncv=ncv, tol=TOL, max_restarts=MAX_RESTARTS, which="TARGET_MAGNITUDE",
+                     transform=_lib.LSA_ST_SINVERT, sigma=sigma, v0=v0)
+        t_e1 = time.perf_counter() - t0
+        lam1 = h1.eigenvalues(min(nev, r1.nconv))
+        h1.close()
+        tt = [float(x) for x in t.tolist()]
+        out = {
+            "workload": f"ONE factorisation + eigensolve (nev={nev}) of the 3D lid-driven-cavity surrogate, Taylor-Hood {n_cells}^3 x 6 tets "
+                        f"({pc.n} DOFs), complex shift, split over {world} GPUs",
+            "scheme": "assembly-tree sub-trees per GPU (proportional mapping), replicated top; NCCL: broadcast of the sub-tree roots' "
+                      "contribution blocks per factorisation, one all-reduce over the replicated rows per operator application, "
+                      "one all-reduce per Gram-Schmidt pass",
+            "factor_s": tt[0], "eigs_s": tt[1], "factor_device_s": tt[2], "eigs_device_s": tt[3], "solve_s": tt[4], "ortho_s": tt[5],
+            "spmv_s": tt[6], "op_applies": int(r.n_op_applies), "nconv": int(r.nconv), "resid_max": res,
+            "one_gpu": {"factor_s": t_f1, "eigs_s": t_e1, "factor_device_s": fs1.seconds, "eigs_device_s": r1.seconds,
+                        "solve_s": r1.seconds_solve, "ortho_s": r1.seconds_ortho, "op_applies": int(r1.n_op_applies),
+                        "factor_bytes": int(i1.factor_entries) * 16},
+            "speedup_factor": t_f1 / tt[0], "speedup_eigs": t_e1 / tt[1], "speedup_total": (t_f1 + t_e1) / (tt[0] + tt[1]),
+            "eig_rel_vs_one_gpu": float(max(min(abs(l - lam1)) / abs(l) for l in lam)) if len(lam) and len(lam1) else None,
+            "partition": {"top_fronts": pi.n_top_fronts, "fronts": pi.n_fronts_global, "replicated_rows": int(pi.n_replicated_rows),
+                          "cut_roots": pi.n_cut_roots, "bcast_bytes_per_factor": int(pi.cut_pool_entries) * 16,
+                          "allreduce_bytes_per_apply": int(pi.n_replicated_rows) * 16,
+                          "model_weights_s": {"replicated_top": pi.weight_top, "heaviest_gpu_subtrees": pi.weight_max_subtrees,
+                                              "total": pi.weight_total},
+                          "model_speedup_bound": pi.weight_total / (pi.weight_top + pi.weight_max_subtrees),
+                          "max_factor_bytes_per_gpu": float(mem.item()), "symbolic_s": t_sym},
+            "limit": "the replicated top of the tree (every GPU factors and sweeps it): stage 2 = cooperative top fronts",
+        }
+    dist.barrier()
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,6 +431,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the co-measured configurations and the 3-D LU line")
     ap.add_argument("--lu3d", type=int, default=int(os.environ.get("LSA_BENCH_LU3D_N", "32")))
+    ap.add_argument("--part3d", type=int, default=int(os.environ.get("LSA_BENCH_PART3D_N", "24")),
+                    help="N > 1: cells per edge of the 3-D cavity whose single solve is split over the GPUs (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -550,6 +636,12 @@ def main() -> None:
                 extras["roofline_lu_3d"] = lu3d_line(args.lu3d, local_rank, fp64_peak)
             except Exception as e:
                 extras["roofline_lu_3d_error"] = repr(e)
+    part = None
+    if world > 1 and args.part3d > 0:
+        try:
+            part = partitioned_section(args.part3d, rank, world, local_rank, device)
+        except Exception as e:
+            part = {"error": repr(e)}
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         m = cpu_measure("cfg1", 0)
@@ -634,13 +726,8 @@ def main() -> None:
                 line["parity"]["eig_rel_vs_oracle"] = c["eig_rel_vs_oracle"]
         if cb is not None:
             line["cpu_baseline"] = cb
-        if world > 1:
-            try:
-                from lsa_fw_b200 import partitioned  # noqa: F401
-
-                line["partitioned"] = "see the `partitioned` line printed by lsa_fw_b200.partitioned.bench (tools/bench_partitioned.py)"
-            except Exception:
-                pass
+        if part is not None:
+            line["partitioned"] = part
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -134,6 +134,34 @@ const char* lsa_version(void);
 int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx, const int64_t* m_rowptr,
                 const int32_t* m_colidx, int32_t leaf_size, int32_t dim, const double* coords,
                 const uint8_t* order_last, int32_t nthreads);
+/* -- one factorisation / eigensolve split over the GPUs of a node -----------------------------------
+ * The reference reaches several ranks through PETSc / SLEPc / MUMPS on PETSc.COMM_WORLD
+ * (Solver/utils.py:196-203, README.md:43).  Here: one process per GPU (torchrun); every process creates a handle,
+ * calls lsa_set_partition(rank, world) BEFORE lsa_analyze (each rank analyses the whole pattern, then keeps the
+ * sub-trees mapped to it plus the replicated top of the assembly tree), and lsa_set_comm with a 128-byte NCCL
+ * unique id obtained from lsa_nccl_unique_id on rank 0 and distributed by the caller (torch.distributed).  After
+ * that the SAME calls as on one GPU (set_values with the full value arrays, factor, solve, eigs) run collectively:
+ * all ranks must issue them in the same order.  NCCL traffic: broadcast of the sub-tree roots' contribution
+ * blocks (once per factorisation), one all-reduce over the replicated rows per operator application (SpMV partial
+ * sums + sub-tree contribution vectors in one payload), one small all-reduce per Gram-Schmidt pass (coefficients
+ * and |w|^2 in one payload).  Vectors passed to / returned by lsa_solve, lsa_spmv and lsa_get_eigenvectors are
+ * full-length and identical on every rank.                                                                      */
+typedef struct {
+  int32_t rank, world;
+  int32_t n_fronts_global, n_fronts_local;   /* local: replicated top + own sub-trees + ghost roots            */
+  int32_t n_top_fronts, n_top_levels, n_cut_roots, pad;
+  int64_t n_replicated_rows, n_own_rows;
+  int64_t cut_pool_entries;
+  int64_t nnz_lu_global;                     /* lsa_symbolic_info.nnz_lu is this rank's share (top + own)       */
+  double flops_real_global;
+  double weight_total, weight_top, weight_max_subtrees, weight_mine;   /* work model of the mapping (seconds-like) */
+} lsa_partition_info;
+int lsa_set_partition(lsa_handle* h, int32_t rank, int32_t world);
+int lsa_nccl_load(const char* path_or_null);      /* optional: where libnccl.so.2 lives (default: already loaded / ld path) */
+int lsa_nccl_unique_id(void* out128);
+int lsa_set_comm(lsa_handle* h, const void* id128);
+int lsa_partition_info_get(const lsa_handle* h, lsa_partition_info* out);
+
 /* Tuning knobs, to be set before lsa_analyze / lsa_factor:
  *   "coupled_fraction" (default 0.5): an unknown with a structurally zero diagonal (pressure) is eliminated
  *       no earlier than the front in which this share of its coupled regular unknowns has been eliminated

@@ -82,6 +82,16 @@ class Counters(C.Structure):
     ]
 
 
+class PartitionInfo(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int32), ("world", C.c_int32), ("n_fronts_global", C.c_int32), ("n_fronts_local", C.c_int32),
+        ("n_top_fronts", C.c_int32), ("n_top_levels", C.c_int32), ("n_cut_roots", C.c_int32), ("pad", C.c_int32),
+        ("n_replicated_rows", C.c_int64), ("n_own_rows", C.c_int64), ("cut_pool_entries", C.c_int64),
+        ("nnz_lu_global", C.c_int64), ("flops_real_global", C.c_double), ("weight_total", C.c_double),
+        ("weight_top", C.c_double), ("weight_max_subtrees", C.c_double), ("weight_mine", C.c_double),
+    ]
+
+
 _lib = None
 
 # ------------------------------------------------------------------ page-locked result buffers
@@ -170,6 +180,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lsa_last_error.restype = C.c_char_p
     lib.lsa_analyze.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32]
     lib.lsa_set_option.argtypes = [vp, C.c_char_p, dbl]
+    lib.lsa_set_partition.argtypes = [vp, i32, i32]
+    lib.lsa_nccl_load.argtypes = [C.c_char_p]
+    lib.lsa_nccl_unique_id.argtypes = [vp]
+    lib.lsa_set_comm.argtypes = [vp, vp]
+    lib.lsa_partition_info_get.argtypes = [vp, C.POINTER(PartitionInfo)]
     lib.lsa_symbolic_info_get.argtypes = [vp, C.POINTER(SymbolicInfo)]
     lib.lsa_symbolic_array.argtypes = [vp, C.c_char_p, vp, i64]
     lib.lsa_symbolic_array.restype = i64
@@ -196,6 +211,7 @@ EXPORTS = [
     "lsa_symbolic_array", "lsa_set_values", "lsa_factor", "lsa_solve", "lsa_spmv", "lsa_eigs",
     "lsa_get_eigenvalues", "lsa_get_eigenvectors", "lsa_get_residuals", "lsa_get_counters", "lsa_sync",
     "lsa_host_alloc", "lsa_host_free", "lsa_dense_schur", "lsa_gemm_bench",
+    "lsa_set_partition", "lsa_nccl_load", "lsa_nccl_unique_id", "lsa_set_comm", "lsa_partition_info_get",
 ]
 
 _ARRAY_DTYPES = {
@@ -204,6 +220,9 @@ _ARRAY_DTYPES = {
     "top_lvl_ptr": np.int32, "top_lvl_front": np.int32, "a_dst": np.int64, "m_dst": np.int64,
     "parent": np.int32, "level": np.int32, "front_k": np.int32, "front_r": np.int32, "p_off": np.int64,
     "q_off": np.int64, "c_off": np.int64,
+    "front_col0": np.int32, "front_flags": np.int32, "child_idx": np.int32, "child0": np.int32, "nchild": np.int32,
+    "owner": np.int32, "g2l": np.int32, "l2g": np.int32, "cut_roots": np.int32, "top_lo": np.int32, "top_hi": np.int32,
+    "own_lo": np.int32, "own_hi": np.int32,
 }
 
 
@@ -237,13 +256,25 @@ def device_pointer(obj):
     raise TypeError("cannot take a device pointer from %r" % type(obj))
 
 
+def nccl_unique_id() -> bytes:
+    """A fresh NCCL unique id (call on ONE rank, hand the bytes to the others)."""
+    lib = load()
+    buf = C.create_string_buffer(128)
+    if lib.lsa_nccl_unique_id(buf) != LSA_OK:
+        raise LsaError(-5, "NCCL is not available (libnccl.so.2 could not be loaded)")
+    return buf.raw
+
+
 class Handle:
     """Thin RAII wrapper over `lsa_handle*` (one solver object = one handle = one CUDA stream)."""
 
-    def __init__(self, n: int, device: int = 0) -> None:
+    def __init__(self, n: int, device: int = 0, rank: int = 0, world: int = 1) -> None:
+        """`rank`, `world` > 1: this handle holds one GPU's part of a factorisation / eigensolve split over
+        `world` GPUs (one process per GPU; include/lsa_b200.h, "split over the GPUs of a node")."""
         self.lib = load()
         self.n = int(n)
         self.device = device
+        self.rank, self.world = int(rank), int(world)
         self._h = C.c_void_p()
         # generations of the numeric state: solvers that share a handle (symbolic cache, adjoint reuse) check
         # them before they trust factors / device-side results they did not just produce themselves
@@ -252,6 +283,21 @@ class Handle:
         rc = self.lib.lsa_create(self.n, device, C.byref(self._h))
         if rc != 0:
             raise LsaError(rc, "cannot create a handle on CUDA device %d (no GPU? there is no CPU fallback)" % device)
+        if self.world > 1:
+            self.check(self.lib.lsa_set_partition(self._h, self.rank, self.world))
+
+    # -- partitioned solve
+    def partition_info(self) -> PartitionInfo:
+        info = PartitionInfo()
+        self.check(self.lib.lsa_partition_info_get(self._h, C.byref(info)))
+        return info
+
+    def set_comm(self, unique_id: bytes) -> None:
+        """NCCL communicator of the partitioned solve from a 128-byte unique id (the same on every rank)."""
+        if len(unique_id) != 128:
+            raise ValueError("an NCCL unique id has 128 bytes")
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.check(self.lib.lsa_set_comm(self._h, buf))
 
     @property
     def closed(self) -> bool:
@@ -409,8 +455,12 @@ class Handle:
         cnt = self.check(self.lib.lsa_get_eigenvalues(self._h, out.ctypes.data, count))
         return out[:cnt]
 
-    def eigenvectors(self, count: int) -> np.ndarray:
-        out = pinned_empty((max(count, 1), self.n), np.complex128, self.lib)
+    def eigenvectors(self, count: int, capacity: int | None = None) -> np.ndarray:
+        """`capacity` (>= count): size of the page-locked block in vectors, rounded up to a multiple of 8 so that the
+        solves of a sweep (which converge a few pairs more or less than nev) recycle the same blocks."""
+        cap = max(count, capacity or 0, 1)
+        cap = (cap + 7) // 8 * 8
+        out = pinned_empty((cap, self.n), np.complex128, self.lib)
         cnt = self.check(self.lib.lsa_get_eigenvectors(self._h, out.ctypes.data, self.n, count, 0))
         return out[:cnt].T
 

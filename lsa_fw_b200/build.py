@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "liblsa_b200.so"
-SOURCES = ["symbolic.cpp", "factor.cu", "solve.cu", "krylov.cu", "capi.cu"]
+SOURCES = ["symbolic.cpp", "partition.cpp", "comm.cpp", "factor.cu", "solve.cu", "krylov.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", str(LIB), *objs, "-Xcompiler", "-fopenmp", "-lcudart", "-lgomp"]
+    cmd = [NVCC, "-shared", "-o", str(LIB), *objs, "-Xcompiler", "-fopenmp", "-lcudart", "-lgomp", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -51,6 +51,10 @@ void free_device(lsa_handle_impl& h) {
   if (h.d_fac) cudaFree(h.d_fac);
   h.d_fac = nullptr;
   h.fac_capacity_bytes = 0;
+  if (h.d_cut_pool) cudaFree(h.d_cut_pool);
+  h.d_cut_pool = nullptr;
+  h.cut_pool_capacity_bytes = 0;
+  dfree(h.d_top_rows); dfree(h.d_topbuf); dfree(h.d_cut_own); dfree(h.d_red);
   if (h.d_inv_scratch) cudaFree(h.d_inv_scratch);
   h.d_inv_scratch = nullptr;
   h.inv_scratch_bytes = h.inv_scratch_entries = 0;
@@ -67,12 +71,29 @@ void free_device(lsa_handle_impl& h) {
   h.V_cols = 0; h.X_cols = 0; h.ncv_alloc = 0; h.scalar = -1; h.have_values = false;
 }
 
-// permuted CSR view of a matrix given in the caller's ordering
-void build_permuted(int n, const int64_t* rowptr, const int32_t* colidx, const Symbolic& sym, CsrHost& out) {
+// permuted CSR view of a matrix given in the caller's ordering.
+// `cls` (partitioned solve, per PERMUTED index: 2 = row of this GPU's sub-trees, 1 = replicated row, 0 = another
+// GPU's row): rows of class 2 keep all entries, rows of class 1 keep the columns of class 2 (and, on rank 0 only,
+// of class 1), rows of class 0 keep nothing -- so that the replicated rows of y = Op x SUM to the full product
+// over the GPUs (one all-reduce) while every GPU only needs the entries of x it maintains.
+void build_permuted(int n, const int64_t* rowptr, const int32_t* colidx, const Symbolic& sym, CsrHost& out,
+                    const std::vector<char>* cls = nullptr, bool top_top = true) {
+  auto keep = [&](int pi, int pj) {
+    if (!cls) return true;
+    const char ci = (*cls)[pi], cj = (*cls)[pj];
+    if (ci == 2) return true;
+    if (ci == 1) return cj == 2 || (cj == 1 && top_top);
+    return false;
+  };
   out.rowptr.assign(n + 1, 0);
   for (int i = 0; i < n; ++i) {
     const int v = sym.perm[i];
-    out.rowptr[i + 1] = out.rowptr[i] + (rowptr[v + 1] - rowptr[v]);
+    long long cnt = rowptr[v + 1] - rowptr[v];
+    if (cls) {
+      cnt = 0;
+      for (long long e = rowptr[v]; e < rowptr[v + 1]; ++e) cnt += keep(i, sym.iperm[colidx[e]]);
+    }
+    out.rowptr[i + 1] = out.rowptr[i] + cnt;
   }
   const long long nnz = out.rowptr[n];
   out.colidx.resize(nnz);
@@ -84,7 +105,8 @@ void build_permuted(int n, const int64_t* rowptr, const int32_t* colidx, const S
     for (int i = 0; i < n; ++i) {
       const int v = sym.perm[i];
       tmp.clear();
-      for (long long e = rowptr[v]; e < rowptr[v + 1]; ++e) tmp.emplace_back(sym.iperm[colidx[e]], e);
+      for (long long e = rowptr[v]; e < rowptr[v + 1]; ++e)
+        if (keep(i, sym.iperm[colidx[e]])) tmp.emplace_back(sym.iperm[colidx[e]], e);
       std::sort(tmp.begin(), tmp.end());
       long long o = out.rowptr[i];
       for (auto& t : tmp) {
@@ -270,6 +292,7 @@ void lsa_destroy(lsa_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_device(*h);
+    comm_destroy(h->comm);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -308,6 +331,40 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   if (const char* e = getenv("LSA_CAP_FRACTION")) opt.cap_fraction = atof(e);
   if (h->has_m) analyze(n, urow.data(), ucol.data(), opt, h->sym);
   else analyze(n, (const long long*)a_rowptr, a_colidx, opt, h->sym);
+  // ---- partitioned solve: every rank analyses the whole pattern (deterministic), then keeps its part
+  h->partitioned = h->part_world > 1;
+  std::vector<char> cls;
+  h->upd_ranges.clear();
+  h->dot_ranges.clear();
+  if (h->partitioned) {
+    Symbolic global;
+    global = std::move(h->sym);
+    partition(global, h->part_rank, h->part_world, h->sym, h->part);
+    cls.assign(n, 0);
+    const Partition& pt = h->part;
+    for (size_t q = 0; q < pt.top_lo.size(); ++q) std::fill(cls.begin() + pt.top_lo[q], cls.begin() + pt.top_hi[q], (char)1);
+    for (size_t q = 0; q < pt.own_lo.size(); ++q) std::fill(cls.begin() + pt.own_lo[q], cls.begin() + pt.own_hi[q], (char)2);
+    // maintained rows (replicated + own) and the rows this rank counts in dot products, as merged sorted ranges
+    for (int i = 0; i < n;) {
+      if (cls[i] == 0) { ++i; continue; }
+      int j = i;
+      while (j < n && cls[j] != 0) ++j;
+      h->upd_ranges.emplace_back(i, j);
+      i = j;
+    }
+    for (int i = 0; i < n;) {
+      const bool mine = cls[i] == 2 || (cls[i] == 1 && pt.rank == 0);
+      if (!mine) { ++i; continue; }
+      int j = i;
+      while (j < n && (cls[j] == 2 || (cls[j] == 1 && pt.rank == 0))) ++j;
+      h->dot_ranges.emplace_back(i, j);
+      i = j;
+    }
+  } else {
+    h->part = Partition();
+    h->upd_ranges.emplace_back(0, n);
+    h->dot_ranges.emplace_back(0, n);
+  }
   // scatter maps for the caller's entry order of A and M (the union map is recomputed per matrix)
   const Symbolic& sym = h->sym;
   auto local_index = [&](int s, int idx) -> int {
@@ -332,6 +389,10 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
           continue;
         }
         const int s = sym.sn_of[std::min(pi, pj)];
+        if (s < 0) {   // partitioned solve: the entry is assembled on another GPU
+          dst[e] = -1;
+          continue;
+        }
         const Front& f = sym.fronts[s];
         const int lr = local_index(s, pi), lc = local_index(s, pj);
         if (lr < 0 || lc < 0) {
@@ -346,8 +407,9 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   };
   build_dst(a_rowptr, a_colidx, h->sym.a_dst);
   if (h->has_m) build_dst(m_rowptr, m_colidx, h->m_dst);
-  build_permuted(n, a_rowptr, a_colidx, sym, h->hA);
-  if (h->has_m) build_permuted(n, m_rowptr, m_colidx, sym, h->hM);
+  const std::vector<char>* pcls = h->partitioned ? &cls : nullptr;
+  build_permuted(n, a_rowptr, a_colidx, sym, h->hA, pcls, h->part.rank == 0);
+  if (h->has_m) build_permuted(n, m_rowptr, m_colidx, sym, h->hM, pcls, h->part.rank == 0);
   h->hAt = CsrHost();
   h->hMt = CsrHost();
   h->analyzed = true;
@@ -383,11 +445,85 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     h->d_wn2 = dalloc<double>(1024);
     h->d_ipart = dalloc<int>(256);
     h->d_rr = dalloc<RrInfo>(1);
+    h->d_red = dalloc<double>(2 * 256 + 16);
+    if (h->partitioned) {
+      const Partition& pt = h->part;
+      std::vector<int> rows;
+      for (size_t q = 0; q < pt.top_lo.size(); ++q)
+        for (int i = pt.top_lo[q]; i < pt.top_hi[q]; ++i) rows.push_back(i);
+      h->d_top_rows = dupload(rows, st);
+      h->d_topbuf = dalloc<z128>(rows.size());
+      std::vector<int> cut;
+      for (int gs : pt.cut_roots)
+        if (pt.owner[gs] == pt.rank) cut.push_back(pt.g2l[gs]);
+      h->n_cut_own = (int)cut.size();
+      h->d_cut_own = dupload(cut, st);
+    }
     upload_csr(*h, h->hA, h->dA, false);
     if (h->has_m) upload_csr(*h, h->hM, h->dM, false);
     LSA_CUDA(cudaStreamSynchronize(st));
   }
   LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_set_partition(lsa_handle* h, int32_t rank, int32_t world) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return LSA_ERR_ARG;
+  if (h->analyzed) return fail(h, LSA_ERR_ARG, "lsa_set_partition must precede lsa_analyze");
+  h->part_rank = rank;
+  h->part_world = world;
+  return LSA_OK;
+}
+
+int lsa_nccl_load(const char* path) {
+  try {
+    nccl_load(path);
+  } catch (const std::exception&) {
+    return LSA_ERR_INTERNAL;
+  }
+  return LSA_OK;
+}
+
+int lsa_nccl_unique_id(void* out128) {
+  if (!out128) return LSA_ERR_ARG;
+  try {
+    nccl_unique_id(out128);
+  } catch (const std::exception&) {
+    return LSA_ERR_INTERNAL;
+  }
+  return LSA_OK;
+}
+
+int lsa_set_comm(lsa_handle* h, const void* id128) {
+  if (!h || !id128) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  LSA_API_BEGIN
+  comm_destroy(h->comm);
+  comm_init(h->comm, id128, h->part_rank, h->part_world);
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_partition_info_get(const lsa_handle* h, lsa_partition_info* out) {
+  if (!h || !out || !h->analyzed) return LSA_ERR_ARG;
+  std::memset(out, 0, sizeof(*out));
+  const Partition& p = h->part;
+  out->rank = h->part_rank;
+  out->world = h->part_world;
+  out->n_fronts_global = h->partitioned ? p.ns_global : h->sym.ns;
+  out->n_fronts_local = h->sym.ns;
+  out->n_top_levels = p.n_top_levels;
+  out->n_cut_roots = (int32_t)p.cut_roots.size();
+  for (int o : p.owner) out->n_top_fronts += o == -1;
+  out->n_replicated_rows = p.n_top_rows;
+  for (size_t q = 0; q < p.own_lo.size(); ++q) out->n_own_rows += p.own_hi[q] - p.own_lo[q];
+  out->cut_pool_entries = p.cut_pool_size;
+  out->nnz_lu_global = h->partitioned ? p.nnz_lu_global : h->sym.nnz_lu;
+  out->flops_real_global = h->partitioned ? p.flops_global : h->sym.flops;
+  out->weight_total = p.weight_total;
+  out->weight_top = p.weight_top;
+  out->weight_max_subtrees = p.weight_max;
+  out->weight_mine = p.weight_mine;
   return LSA_OK;
 }
 
@@ -479,6 +615,19 @@ int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int
   if (nm == "lvl_front") return give(s.lvl_front.data(), s.lvl_front.size(), 4);
   if (nm == "a_dst") return give(s.a_dst.data(), s.a_dst.size(), 8);
   if (nm == "m_dst") return give(h->m_dst.data(), h->m_dst.size(), 8);
+  if (nm == "front_col0") return from_fronts([](const Front& f) { return f.col0; }, 4);
+  if (nm == "front_flags") return from_fronts([](const Front& f) { return f.flags; }, 4);
+  if (nm == "child_idx") return give(s.child_idx.data(), s.child_idx.size(), 4);
+  if (nm == "child0") return from_fronts([](const Front& f) { return f.child0; }, 4);
+  if (nm == "nchild") return from_fronts([](const Front& f) { return f.nchild; }, 4);
+  if (nm == "owner") return give(h->part.owner.data(), h->part.owner.size(), 4);
+  if (nm == "g2l") return give(h->part.g2l.data(), h->part.g2l.size(), 4);
+  if (nm == "l2g") return give(h->part.l2g.data(), h->part.l2g.size(), 4);
+  if (nm == "cut_roots") return give(h->part.cut_roots.data(), h->part.cut_roots.size(), 4);
+  if (nm == "top_lo") return give(h->part.top_lo.data(), h->part.top_lo.size(), 4);
+  if (nm == "top_hi") return give(h->part.top_hi.data(), h->part.top_hi.size(), 4);
+  if (nm == "own_lo") return give(h->part.own_lo.data(), h->part.own_lo.size(), 4);
+  if (nm == "own_hi") return give(h->part.own_hi.data(), h->part.own_hi.size(), 4);
   if (nm == "parent") return from_fronts([](const Front& f) { return f.parent; }, 4);
   if (nm == "level") return from_fronts([](const Front& f) { return f.level; }, 4);
   if (nm == "front_k") return from_fronts([](const Front& f) { return f.k; }, 4);
@@ -549,6 +698,16 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
       h->d_pool[q] = nullptr;
       LSA_CUDA(cudaMalloc(&h->d_pool[q], std::max<long long>(pn, 16)));
       h->pool_capacity_bytes[q] = pn;
+    }
+  }
+  if (h->partitioned) {
+    if (!h->comm.nccl_comm) return fail(h, LSA_ERR_ARG, "partitioned handle: call lsa_set_comm before lsa_factor");
+    const long long cn = h->part.cut_pool_size * (long long)esz;
+    if (cn > h->cut_pool_capacity_bytes) {
+      if (h->d_cut_pool) cudaFree(h->d_cut_pool);
+      h->d_cut_pool = nullptr;
+      LSA_CUDA(cudaMalloc(&h->d_cut_pool, std::max<long long>(cn, 16)));
+      h->cut_pool_capacity_bytes = cn;
     }
   }
   const z128 alpha = mk(alpha_re, alpha_im), beta = mk(beta_re, beta_im);
@@ -629,6 +788,7 @@ int lsa_solve(lsa_handle* h, int32_t trans, const double* b, double* x, int32_t 
     src = h->d_io;
   }
   permute_gather(st, src, h->d_x, h->d_perm, n);
+  replicated_rows_to_partial(*h, h->d_x);   // partitioned solve: b is complete on every rank
   if (trans != LSA_OP_N && refine_steps > 0) ensure_transposes(*h);
   if (trans == LSA_OP_T) {
     k_conj_inplace<<<cdiv(n, 256), 256, 0, st>>>(h->d_x, n);
@@ -637,6 +797,7 @@ int lsa_solve(lsa_handle* h, int32_t trans, const double* b, double* x, int32_t 
   } else {
     op_solve(*h, trans, h->d_x, refine_steps);
   }
+  make_full(*h, h->d_x, 1, n);
   if (on_device) {
     permute_scatter(st, h->d_x, (z128*)x, h->d_perm, n);
   } else {
@@ -665,6 +826,8 @@ int lsa_spmv(lsa_handle* h, int32_t which_matrix, int32_t trans, const double* x
   if (trans != LSA_OP_N) ensure_transposes(*h);
   const CsrDev& mat = which_matrix == LSA_MAT_A ? (trans == LSA_OP_N ? h->dA : h->dAt) : (trans == LSA_OP_N ? h->dM : h->dMt);
   spmv(*h, mat, trans == LSA_OP_H, h->d_x, h->d_w);
+  if (h->partitioned)   // rows of other GPUs are empty here, replicated rows hold partial sums: one sum completes both
+    comm_allreduce_sum(h->comm, (double*)h->d_w, 2 * (size_t)n, st);
   if (on_device) {
     permute_scatter(st, h->d_w, (z128*)y, h->d_perm, n);
   } else {

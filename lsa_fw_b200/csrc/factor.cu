@@ -33,6 +33,7 @@ __global__ void k_scatter(T* __restrict__ fac, const long long* __restrict__ dst
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; e < nnz; e += stride) {
+    if (dst[e] < 0) continue;   // partitioned solve: the entry belongs to a front of another GPU
     z128 v;
     if constexpr (sizeof(VT) == 16) v = coef * vals[e];
     else v = coef * (double)vals[e];
@@ -75,7 +76,8 @@ __global__ void k_decoupled_pivots(T* __restrict__ diag, int n_iso, double tiny_
 template <class T>
 __global__ void k_extend_add(const Front* __restrict__ fronts, const int* __restrict__ lvl_front, int first,
                              const int* __restrict__ child_idx, const int* __restrict__ ea_map, int slot,
-                             T* __restrict__ fac, const T* __restrict__ pool_child, T* __restrict__ pool_parent) {
+                             T* __restrict__ fac, const T* __restrict__ pool_child, T* __restrict__ pool_parent,
+                             T* __restrict__ pool_cut) {
   constexpr int CHUNK = 2048;
   __shared__ int s_map[CHUNK];
   const Front p = fronts[lvl_front[first + blockIdx.y]];
@@ -84,10 +86,11 @@ __global__ void k_extend_add(const Front* __restrict__ fronts, const int* __rest
   const int rc = c.r;
   if (rc == 0) return;
   const int* map = ea_map + c.st0;
-  const T* cb = pool_child + c.c_off;
+  // flagged fronts (sub-tree roots of the partitioned solve) keep their contribution block in the cut pool
+  const T* cb = (c.flags ? pool_cut : pool_child) + c.c_off;
   T* P = fac + p.p_off;
   T* Q = fac + p.q_off;
-  T* C = pool_parent + p.c_off;
+  T* C = (p.flags ? pool_cut : pool_parent) + p.c_off;
   const long long kp = p.k, rp = p.r, mp = kp + rp;
   for (int base = 0; base < rc; base += CHUNK) {
     const int len = min(CHUNK, rc - base);
@@ -530,7 +533,7 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
 template <class T>
 __global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                     int first, int j0, int ob0, int mode, T* __restrict__ fac,
-                                                    T* __restrict__ pool) {
+                                                    T* __restrict__ pool, T* __restrict__ pool_cut) {
   constexpr bool CPLX = scalar_traits<T>::is_complex;
   constexpr int S = CPLX ? 2 : 1;
   const Front f = fronts[lvl_front[first + blockIdx.y]];
@@ -587,7 +590,7 @@ __global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fr
     }
   } else {
     if (r == 0 || k == 0) return;
-    T* C = pool + f.c_off;
+    T* C = (f.flags ? pool_cut : pool) + f.c_off;
     const int tm1 = (r * S + 63) / 64;
     if (t < tiles(r, r))
       gemm_tile<CPLX>((const double*)(P + k), m * S, (const double*)Q, (long long)k * S, (double*)C, (long long)r * S,
@@ -690,10 +693,13 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
   cudaStream_t st = h.stream;
   T* fac = (T*)h.d_fac;
   T* pool[2] = {(T*)h.d_pool[0], (T*)h.d_pool[1]};
+  T* pool_cut = (T*)h.d_cut_pool;
   int launches = 0;
   SweepTrace tr;
   tr.begin(st);
   LSA_CUDA(cudaMemsetAsync(fac, 0, sym.fac_size * sizeof(T), st));
+  if (h.partitioned && h.part.cut_pool_size > 0)
+    LSA_CUDA(cudaMemsetAsync(pool_cut, 0, h.part.cut_pool_size * sizeof(T), st));
   DevStats init{};
   init.min_piv_bits = (unsigned long long)0x7ff0000000000000ULL;  // +inf
   init.max_piv_bits = 0ULL;
@@ -736,11 +742,23 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
   for (int d = sym.nlevels - 1; d >= 0; --d) {
     const int lbeg = sym.lvl_ptr[d], lend = sym.lvl_ptr[d + 1];
     const int cnt_all = lend - lbeg;
+    if (h.partitioned && d == h.part.n_top_levels - 1) {
+      // ---- all sub-trees are factored: their roots' contribution blocks go to every GPU (NCCL broadcast from the
+      // owner, all roots in one group), then the replicated top is factored redundantly on identical data
+      constexpr int SR = scalar_traits<T>::is_complex ? 2 : 1;
+      comm_group_begin();
+      for (int gs : h.part.cut_roots) {
+        const Front& f = sym.fronts[h.part.g2l[gs]];
+        comm_bcast(h.comm, (double*)(pool_cut + f.c_off), (size_t)f.r * f.r * SR, h.part.owner[gs], st);
+      }
+      comm_group_end();
+      tr.mark("bcast_cut", d, 0, (int)h.part.cut_roots.size(), 1);
+    }
     // contribution blocks of this level start from zero
     long long pool_used = 0;
     for (int q = lbeg; q < lend; ++q) {
       const Front& f = sym.fronts[sym.lvl_front[q]];
-      pool_used = std::max(pool_used, f.c_off + (long long)f.r * f.r);
+      if (f.flags == FRONT_REGULAR) pool_used = std::max(pool_used, f.c_off + (long long)f.r * f.r);
     }
     if (pool_used > 0) LSA_CUDA(cudaMemsetAsync(pool[d & 1], 0, pool_used * sizeof(T), st));
     for (int y0 = 0; y0 < cnt_all; y0 += YMAX) {
@@ -758,7 +776,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
       for (int slot = 0; slot < maxchild; ++slot) {
         const int gx = std::max(1, std::min(64, max_rc / 8));
         k_extend_add<T><<<dim3(gx, cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_child_idx, h.d_ea_map, slot,
-                                                       fac, pool[(d + 1) & 1], pool[d & 1]);
+                                                       fac, pool[(d + 1) & 1], pool[d & 1], pool_cut);
         LSA_LAUNCH_CHECK();
         tr.mark("extend_add", d, slot, gx, cnt);
         launches++;
@@ -802,7 +820,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
           }
           if (gx_tiles > 0) {
             k_front_gemm<T><<<dim3((unsigned)gx_tiles, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, ob0, 0, fac,
-                                                                             pool[d & 1]);
+                                                                             pool[d & 1], pool_cut);
             LSA_LAUNCH_CHECK();
             tr.mark("gemm_inner", d, j0, (int)gx_tiles, act);
             launches++;
@@ -819,7 +837,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
           gx2 = std::max(gx2, tiles(m - ob1, f.k - ob1) + tiles(f.k - ob1, f.r));
         }
         if (act2 > 0 && gx2 > 0) {
-          k_front_gemm<T><<<dim3((unsigned)gx2, act2), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, ob0, 2, fac, pool[d & 1]);
+          k_front_gemm<T><<<dim3((unsigned)gx2, act2), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, ob0, 2, fac, pool[d & 1], pool_cut);
           LSA_LAUNCH_CHECK();
           tr.mark("gemm_outer", d, ob0, (int)gx2, act2);
           launches++;
@@ -833,7 +851,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
           gx_schur = (int)std::max<long long>(gx_schur, (long long)cdiv((long long)f.r * S, 64) * cdiv(f.r, 64));
       }
       if (gx_schur > 0) {
-        k_front_gemm<T><<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, 0, 1, fac, pool[d & 1]);
+        k_front_gemm<T><<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, 0, 1, fac, pool[d & 1], pool_cut);
         LSA_LAUNCH_CHECK();
         tr.mark("gemm_schur", d, 0, gx_schur, cnt);
         launches++;

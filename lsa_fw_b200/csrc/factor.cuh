@@ -63,7 +63,9 @@ void gemm_plain(cudaStream_t st, bool cplx, const void* A, long long lda, const 
 template <class T>
 void solve_permuted(lsa_handle_impl& h, int trans, z128* x, int* n_kernels);
 
-void plan_solve(lsa_handle_impl& h, int scalar);   // solve.cu: level plan of the sweeps, before post_factor
+void plan_solve(lsa_handle_impl& h, int scalar);
+void exchange_replicated_rows(lsa_handle_impl& h, z128* x, bool with_cut_contributions);   // partitioned solve
+void replicated_rows_to_partial(lsa_handle_impl& h, z128* x);   // solve.cu: level plan of the sweeps, before post_factor
 
 // krylov.cu
 void spmv(lsa_handle_impl& h, const CsrDev& M, bool conj_vals, const z128* x, z128* y);
@@ -71,6 +73,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
 void dense_schur_device(lsa_handle_impl& h, int m, z128* dS, int ld, z128* dQ, int which, int transform, z128 sigma);
 void op_solve(lsa_handle_impl& h, int trans, z128* x, int refine_steps);
 void drop_solve_graphs(lsa_handle_impl& h);
+void make_full(lsa_handle_impl& h, z128* vec, int ncols, long long ld);   // partitioned solve: complete, identical vectors on every GPU
 void permute_gather(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n);   // dst[i] = src[perm[i]]
 void permute_scatter(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n);  // dst[perm[i]] = src[i]
 void gather_values(cudaStream_t st, const void* orig, bool is_complex, const long long* src, void* out, long long nnz);

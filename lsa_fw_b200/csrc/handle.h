@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/lsa_b200.h"
+#include "comm.h"
 #include "common.cuh"
 #include "lsa_internal.h"
 
@@ -90,6 +91,20 @@ struct lsa_handle_impl {
   std::vector<int> lvl_maxchild;   // per level: max number of children of its fronts
   std::vector<int> lvl_maxk;       // per level: largest pivot count
   std::vector<int> lvl_maxrchild;  // per level: largest child contribution block order
+
+  // ---- partitioned solve over the GPUs of a node (stage 1: sub-trees per GPU, replicated top; lsa_internal.h)
+  int part_rank = 0, part_world = 1;     // lsa_set_partition, before lsa_analyze
+  bool partitioned = false;
+  Partition part;
+  Comm comm;
+  void* d_cut_pool = nullptr;            // contribution blocks of ALL sub-tree roots (own: computed, others: broadcast)
+  long long cut_pool_capacity_bytes = 0;
+  int* d_top_rows = nullptr;             // replicated rows (decoupled pivots + top fronts), permuted indices
+  z128* d_topbuf = nullptr;              // those rows packed: payload of the per-solve all-reduce
+  int* d_cut_own = nullptr;              // local ids of this rank's sub-tree roots that hang below a top front
+  int n_cut_own = 0;
+  std::vector<std::pair<int, int>> upd_ranges, dot_ranges;   // rows this rank maintains / counts in dot products
+  double* d_red = nullptr;               // all-reduce payload of a Gram-Schmidt pass: h (<= 256 complex), |w|^2
 
   // ---- values
   void* d_a_orig = nullptr;  // caller entry order

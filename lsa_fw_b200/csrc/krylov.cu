@@ -315,6 +315,81 @@ __global__ void __launch_bounds__(256) k_refine_flag(int nb_before, const double
   }
 }
 
+// ---- partitioned solve (row-sharded basis): the Gram-Schmidt coefficients of a pass and |w|^2 travel in ONE
+// all-reduce payload  red = [h_0 .. h_{j-1} (complex), |w|^2];  the norm after the update comes from Pythagoras,
+// |w - V h|^2 = |w|^2 - |h|^2 (what SLEPc's BV does for its refinement criterion): no second reduction per pass.
+__global__ void __launch_bounds__(256) k_reduce_red(int j, int nblk, const z128* __restrict__ part, int ldp,
+                                                    const double* __restrict__ wn2, double* __restrict__ red,
+                                                    const int* __restrict__ skip) {
+  if (skip && *skip == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c > j) return;
+  if (c == j) {   // one extra warp: |w|^2 over this rank's rows
+    double a = 0.0;
+    for (int b = lane; b < nblk; b += 32) a += wn2[b];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[2 * j] = a;
+    return;
+  }
+  z128 a = mk(0, 0);
+  for (int b = lane; b < nblk; b += 32) a += part[(long long)b * ldp + c];
+  for (int o = 16; o > 0; o >>= 1) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+  }
+  if (lane == 0) {
+    red[2 * c] = a.x;
+    red[2 * c + 1] = a.y;
+  }
+}
+// After the all-reduce: h <- red, S column, norm estimate and (pass 1) the refinement decision.
+//   pass 1: norm2 = max(|w|^2 - |h|^2, 0);  refine = always || !(norm2 >= 0.5 |w|^2)
+//   pass 2 (only when refine was set): norm2 = max(|w'|^2 - |h2|^2, 0) with |w'|^2 measured exactly in the pass
+__global__ void __launch_bounds__(256) k_apply_red(int j, const double* __restrict__ red, z128* __restrict__ h,
+                                                   z128* __restrict__ scol, int pass, int always,
+                                                   double* __restrict__ norm2, int* __restrict__ flag,
+                                                   int* __restrict__ count) {
+  if (pass == 2 && *flag == 0) return;
+  __shared__ double sh[256];
+  double hn = 0.0;
+  for (int c = threadIdx.x; c < j; c += 256) {
+    const z128 v = mk(red[2 * c], red[2 * c + 1]);
+    h[c] = v;
+    if (scol) scol[c] = pass == 2 ? scol[c] + v : v;
+    hn += abs2(v);
+  }
+  sh[threadIdx.x] = hn;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double wn = red[2 * j];
+    const double est = wn - sh[0];
+    *norm2 = (est == est) ? fmax(est, 0.0) : est;   // NaN stays NaN (reported as non-finite)
+    if (pass == 1) {
+      const int f = always || !(est >= 0.5 * wn);
+      *flag = f;
+      if (f && count) atomicAdd(count, 1);
+    }
+  }
+}
+// red[0] = sum of partials (single block)
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ part, int n, int stride, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += part[(long long)i * stride];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
 // npart[blk] = sum |w|^2 over the block's rows
 __global__ void __launch_bounds__(256) k_norm2_part(int n, const z128* __restrict__ w, double* __restrict__ npart) {
   __shared__ double red[8];
@@ -567,6 +642,127 @@ __global__ void k_perm_scatter_scaled(const z128* __restrict__ src, z128* __rest
   if (i < n) dst[perm[i]] = src[i] * (*phase);
 }
 
+// ------------------------------------------------------------------ row ranges (partitioned solve)
+//
+// Single GPU: one range [0, n).  Partitioned: `upd_ranges` = rows this GPU maintains (replicated rows + its
+// sub-trees), `dot_ranges` = rows it counts in dot products (its sub-trees; rank 0 also the replicated rows).
+typedef std::vector<std::pair<int, int>> Ranges;
+
+static int blocks_of(const Ranges& rg, int per_block) {
+  int b = 0;
+  for (auto& r : rg) b += cdiv(r.second - r.first, per_block);
+  return b;
+}
+// npart[..] = partial |w|^2 over `rg`; returns the number of partials
+static int norm2_partials(lsa_handle_impl& h, const Ranges& rg, const z128* w, double* npart) {
+  int boff = 0;
+  for (auto& r : rg) {
+    const int len = r.second - r.first, nb = cdiv(len, 256);
+    if (nb > 0) k_norm2_part<<<nb, 256, 0, h.stream>>>(len, w + r.first, npart + boff);
+    boff += nb;
+  }
+  return boff;
+}
+// out = w / |w| over the maintained rows; the norm is global (all-reduced when partitioned)
+static void normalize_vector(lsa_handle_impl& h, const z128* w, z128* out, double* beta_out, z128* s_entry,
+                             const z128* hcol, int hlen, int* flag, int step) {
+  cudaStream_t st = h.stream;
+  const double* np = h.d_npart;
+  int nparts = norm2_partials(h, h.dot_ranges, w, h.d_npart);
+  if (h.partitioned) {
+    k_sum_partials<<<1, 256, 0, st>>>(h.d_npart, nparts, 1, h.d_red + 516);
+    comm_allreduce_sum(h.comm, h.d_red + 516, 1, st);
+    np = h.d_red + 516;
+    nparts = 1;
+  }
+  for (auto& r : h.upd_ranges) {
+    const int len = r.second - r.first;
+    if (len > 0) k_normalize<<<cdiv(len, 256), 256, 0, st>>>(len, w + r.first, out + r.first, np, nparts, beta_out, s_entry, hcol, hlen, flag, step);
+  }
+  LSA_LAUNCH_CHECK();
+}
+static void basis_gemm(lsa_handle_impl& h, int mp, int nk, const z128* V, long long ldv, const z128* Qm, int ldq, z128* Out,
+                       long long ldo) {
+  const size_t smem = sizeof(z128) * (size_t)mp * 33;
+  for (auto& r : h.upd_ranges) {
+    const int len = r.second - r.first;
+    if (len > 0) k_basis_gemm<<<cdiv(len, 32), 256, smem, h.stream>>>(len, mp, nk, V + r.first, ldv, Qm, ldq, Out + r.first, ldo);
+  }
+  LSA_LAUNCH_CHECK();
+}
+// vec (n x ncols, ld) complete and identical on every GPU: rows outside dot_ranges zeroed, then summed
+void make_full(lsa_handle_impl& h, z128* vec, int ncols, long long ld) {
+  if (!h.partitioned) return;
+  for (int c = 0; c < ncols; ++c) {
+    int prev = 0;
+    for (size_t q = 0; q <= h.dot_ranges.size(); ++q) {
+      const int lo = q < h.dot_ranges.size() ? h.dot_ranges[q].first : h.n;
+      if (lo > prev) LSA_CUDA(cudaMemsetAsync(vec + (long long)c * ld + prev, 0, sizeof(z128) * (size_t)(lo - prev), h.stream));
+      if (q < h.dot_ranges.size()) prev = h.dot_ranges[q].second;
+    }
+    comm_allreduce_sum(h.comm, (double*)(vec + (long long)c * ld), 2 * (size_t)h.n, h.stream);
+  }
+}
+
+// w <- w - V[:, 0:jj] (V^H w), classical Gram-Schmidt with a second pass if needed (or `force_two`), then
+// out = w / |w|.  scol (optional): column of the projected matrix that receives the coefficients and, at
+// scol[jj], the norm.  Device-side decisions only; the host enqueues the same launches either way.
+static void orthonormalize(lsa_handle_impl& h, z128* V, long long ldv, int jj, z128* w, z128* out, z128* scol,
+                           int rows_per_block, int ldp, bool force_two, int* flag, int step) {
+  cudaStream_t st = h.stream;
+  const int always = (h.ortho_refine_always || force_two) ? 1 : 0;
+  auto dots = [&](const int* skip, bool want_wn2) {
+    int boff = 0;
+    for (auto& r : h.dot_ranges) {
+      const int len = r.second - r.first, nb = cdiv(len, rows_per_block);
+      if (nb > 0) launch_dots(st, nb, len, jj, V + r.first, ldv, w + r.first, h.d_part + (long long)boff * ldp, ldp, rows_per_block,
+                              want_wn2 ? h.d_wn2 + boff : nullptr, skip);
+      boff += nb;
+    }
+    return boff;
+  };
+  auto update = [&](const int* skip, double* npart) {
+    int boff = 0;
+    for (auto& r : h.upd_ranges) {
+      const int len = r.second - r.first, nb = cdiv(len, 256);
+      if (nb > 0) k_update<<<nb, 256, 0, st>>>(len, jj, V + r.first, ldv, h.d_h, w + r.first, npart ? npart + boff : nullptr, skip);
+      boff += nb;
+    }
+    return boff;
+  };
+  if (!h.partitioned) {
+    const int nblk = dots(nullptr, true);
+    k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol ? scol : h.d_brow, 0, nullptr);
+    const int nb = update(nullptr, h.d_npart);
+    k_refine_flag<<<1, 256, 0, st>>>(nblk, h.d_wn2, nb, h.d_npart, always, h.d_refine, h.d_refine + 1);
+    dots(h.d_refine, false);
+    k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol ? scol : h.d_brow, 1, h.d_refine);
+    update(h.d_refine, h.d_npart);
+    for (auto& r : h.upd_ranges)   // single range
+      k_normalize<<<cdiv(r.second - r.first, 256), 256, 0, st>>>(r.second - r.first, w + r.first, out + r.first, h.d_npart, nb, nullptr,
+                                                                  scol ? scol + jj : nullptr, scol, scol ? jj : 0, flag, step);
+  } else {
+    double* red = h.d_red;
+    double* norm2 = h.d_red + 514;
+    for (int pass = 1; pass <= 2; ++pass) {
+      const int* skip = pass == 2 ? h.d_refine : nullptr;
+      const int nblk = dots(skip, true);
+      k_reduce_red<<<cdiv(jj + 1, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_wn2, red, skip);
+      // every rank enqueues the all-reduce of both passes (the decision lives on the device); a pass that was
+      // not needed reduces stale numbers that k_apply_red then ignores
+      comm_allreduce_sum(h.comm, red, 2 * (size_t)jj + 1, st);
+      k_apply_red<<<1, 256, 0, st>>>(jj, red, h.d_h, scol, pass, always, norm2, h.d_refine, h.d_refine + 1);
+      update(skip, nullptr);
+    }
+    for (auto& r : h.upd_ranges) {
+      const int len = r.second - r.first;
+      if (len > 0) k_normalize<<<cdiv(len, 256), 256, 0, st>>>(len, w + r.first, out + r.first, norm2, 1, nullptr,
+                                                                scol ? scol + jj : nullptr, scol, scol ? jj : 0, flag, step);
+    }
+  }
+  LSA_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------------------------- OP and driver
 
 void drop_solve_graphs(lsa_handle_impl& h) {
@@ -583,7 +779,7 @@ static void solve_dispatch(lsa_handle_impl& h, int trans, z128* x, int* nk) {
     else solve_permuted<double>(h, trans, x, count);
   };
   int local = 0;
-  if (!h.use_graphs) {
+  if (!h.use_graphs || h.partitioned) {   // partitioned solve: NCCL calls inside the sweep, enqueued directly
     run(&local);
   } else {
     lsa_handle_impl::SolveGraph* found = nullptr;
@@ -621,6 +817,7 @@ void op_solve(lsa_handle_impl& h, int trans, z128* x, int refine_steps) {
     solve_dispatch(h, trans, x, &nk);
     return;
   }
+  if (h.partitioned) throw ArgError("iterative refinement (refine_steps > 0) is not available in the partitioned solve");
   // keep b in d_w2, iterate x_{k+1} = x_k + F^-1 (b - F x_k)
   z128* b = h.d_r1;
   z128* r = h.d_r2;
@@ -682,7 +879,10 @@ static void apply_op(lsa_handle_impl& h, const lsa_eigs_params& p, const z128* v
   if (p.transform == LSA_ST_SINVERT) {
     size_t e = t_spmv.begin();
     if (h.has_m) spmv(h, adj ? h.dMt : h.dM, adj, v, w);
-    else k_copy<<<blocks, 256, 0, h.stream>>>(n, v, w);
+    else {
+      k_copy<<<blocks, 256, 0, h.stream>>>(n, v, w);
+      replicated_rows_to_partial(h, w);   // the sweep expects replicated rows that SUM to the value over the GPUs
+    }
     t_spmv.end(e);
     e = t_solve.begin();
     op_solve(h, adj ? LSA_OP_H : LSA_OP_N, w, p.refine_steps);
@@ -696,6 +896,8 @@ static void apply_op(lsa_handle_impl& h, const lsa_eigs_params& p, const z128* v
       e = t_solve.begin();
       op_solve(h, adj ? LSA_OP_H : LSA_OP_N, w, p.refine_steps);
       t_solve.end(e);
+    } else if (h.partitioned) {
+      exchange_replicated_rows(h, w, false);   // no sweep follows: sum the partial products of the replicated rows here
     }
     z128 sg = mk(p.sigma_re, p.sigma_im);
     if (adj) sg = conj_(sg);
@@ -746,9 +948,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   long long sum_cols = 0;
   apply_op(h, p, h.d_x, h.d_w, t_spmv, t_solve);
   n_applies++;
-  k_norm2_part<<<blocks, 256, 0, st>>>(n, h.d_w, h.d_npart);
-  k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
-  LSA_LAUNCH_CHECK();
+  normalize_vector(h, h.d_w, V, nullptr, nullptr, nullptr, 0, nullptr, 0);
 
   int nconv = 0, keep = 0, restarts = 0, breakdown = 0, m_last = ncv;
   bool invariant = false;
@@ -767,16 +967,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       z128* scol = S + (long long)j * ld;
       // classical Gram-Schmidt, second pass only when the criterion asks for it (decided on the device: the
       // pass-2 kernels return at once when the flag is clear)
-      launch_dots(st, nblk, n, jj, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, h.d_wn2, nullptr);
-      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 0, nullptr);
-      k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart, nullptr);
-      k_refine_flag<<<1, 256, 0, st>>>(nblk, h.d_wn2, blocks, h.d_npart, h.ortho_refine_always ? 1 : 0, h.d_refine, h.d_refine + 1);
-      launch_dots(st, nblk, n, jj, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, nullptr, h.d_refine);
-      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol, 1, h.d_refine);
-      k_update<<<blocks, 256, 0, st>>>(n, jj, V, ldv, h.d_h, h.d_w, h.d_npart, h.d_refine);
-      k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V + (long long)(j + 1) * ldv, h.d_npart, blocks, nullptr,
-                                          scol + j + 1, scol, jj, h.d_flag, j);
-      LSA_LAUNCH_CHECK();
+      orthonormalize(h, V, ldv, jj, h.d_w, V + (long long)(j + 1) * ldv, scol, rows_per_block, ldp, false, h.d_flag, j);
       h.launch_count += 9;  // spmv + 8 orthogonalisation kernels
       t_ortho.end(e);
     }
@@ -818,25 +1009,16 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
     // ---- restart: V[:, nconv_old:keep] = V[:, nconv_old:m] Q[nconv_old:m, nconv_old:keep]
     e = t_restart.begin();
     const int mp = m - nconv_old, nk = keep - nconv_old;
-    if (nk > 0) {
-      const size_t smem = sizeof(z128) * (size_t)mp * 33;
-      k_basis_gemm<<<cdiv(n, 32), 256, smem, st>>>(n, mp, nk, V + (long long)nconv_old * ldv, ldv,
-                                                   Q + nconv_old + (long long)nconv_old * ncv, ncv,
-                                                   V + (long long)nconv_old * ldv, ldv);
-      LSA_LAUNCH_CHECK();
-    }
+    if (nk > 0)
+      basis_gemm(h, mp, nk, V + (long long)nconv_old * ldv, ldv, Q + nconv_old + (long long)nconv_old * ncv, ncv,
+                 V + (long long)nconv_old * ldv, ldv);
     const bool done = rp.last || nconv >= nev;
     if (!done && invariant) {
       // the invariant subspace found so far is locked (keep == m); continue from a fresh random
       // direction orthogonal to it (SLEPc does the same after a breakdown)
       z128* vnew = V + (long long)keep * ldv;
       k_randn<<<blocks, 256, 0, st>>>(h.d_w, n, p.seed + 7919ULL * (unsigned long long)restarts);
-      for (int pass = 0; pass < 2; ++pass) {
-        launch_dots(st, nblk, n, keep, V, ldv, h.d_w, h.d_part, ldp, rows_per_block, nullptr, nullptr);
-        k_reduce_h<<<cdiv(keep, 8), 256, 0, st>>>(keep, nblk, h.d_part, ldp, h.d_h, h.d_brow, 0, nullptr);
-        k_update<<<blocks, 256, 0, st>>>(n, keep, V, ldv, h.d_h, h.d_w, pass ? h.d_npart : nullptr, nullptr);
-      }
-      k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, vnew, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
+      orthonormalize(h, V, ldv, keep, h.d_w, vnew, nullptr, rows_per_block, ldp, true, nullptr, 0);
       h_flag[0] = 0x7fffffff;
       LSA_CUDA(cudaMemcpyAsync(h.d_flag, h_flag, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
       LSA_LAUNCH_CHECK();
@@ -864,10 +1046,10 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       k_copy<<<blocks, 256, 0, st>>>(n, V + (long long)m_last * ldv, V + (long long)nconv * ldv);
     k_ritz_vectors<<<cdiv(nconv, 64), 64, 0, st>>>(S, ld, nconv, Q, ncv, free_purify ? h.d_brow : nullptr);
     const int mpx = nconv + (free_purify ? 1 : 0);
-    const size_t smem = sizeof(z128) * (size_t)mpx * 33;
     // Xp (permuted) staged in the tail of the basis is not possible in general -> use d_Xp
-    k_basis_gemm<<<cdiv(n, 32), 256, smem, st>>>(n, mpx, nconv, V, ldv, Q, ncv, h.d_Xp, n);
-    LSA_LAUNCH_CHECK();
+    basis_gemm(h, mpx, nconv, V, ldv, Q, ncv, h.d_Xp, n);
+    // partitioned solve: from here on complete vectors, identical on every GPU (the result is handed out whole)
+    make_full(h, h.d_Xp, nconv, n);
     for (int i = 0; i < nconv; ++i) {
       z128* xi = h.d_Xp + (long long)i * n;
       if (p.purify == 2) {
@@ -956,26 +1138,36 @@ __global__ void __launch_bounds__(256) k_resid_part(int n, const z128* __restric
 void residual_norms(lsa_handle_impl& h, double* out_host, int count) {
   const int n = h.n, blocks = cdiv(n, 256);
   const bool adj = h.last_params.adjoint != 0;
-  std::vector<double> part(2 * (size_t)blocks);
   double* d_part = nullptr;
-  LSA_CUDA(cudaMalloc(&d_part, sizeof(double) * 2 * blocks));
+  LSA_CUDA(cudaMalloc(&d_part, sizeof(double) * 2 * (blocks + (int)h.dot_ranges.size())));
   for (int i = 0; i < count && i < h.nconv; ++i) {
     const int col = h.eig_order[i];
     // work in the permuted ordering: x_p = gather(x)
     permute_gather(h.stream, h.d_X + (long long)col * n, h.d_x, h.d_perm, n);
     spmv(h, adj ? h.dAt : h.dA, adj, h.d_x, h.d_w);
     if (h.has_m) spmv(h, adj ? h.dMt : h.dM, adj, h.d_x, h.d_r1);
-    else k_copy<<<blocks, 256, 0, h.stream>>>(n, h.d_x, h.d_r1);
-    k_resid_part<<<blocks, 256, 0, h.stream>>>(n, h.d_w, h.d_r1, h.eigenvalues[i], h.d_x, d_part);
-    LSA_LAUNCH_CHECK();
-    LSA_CUDA(cudaMemcpyAsync(part.data(), d_part, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, h.stream));
-    LSA_CUDA(cudaStreamSynchronize(h.stream));
-    double s1 = 0, s2 = 0;
-    for (int b = 0; b < blocks; ++b) {
-      s1 += part[2 * b];
-      s2 += part[2 * b + 1];
+    else {
+      k_copy<<<blocks, 256, 0, h.stream>>>(n, h.d_x, h.d_r1);
+      replicated_rows_to_partial(h, h.d_r1);
     }
-    out_host[i] = std::sqrt(s1) / (std::max(h.a_fro, 1e-300) * std::sqrt(std::max(s2, 1e-300)));
+    if (h.partitioned) {   // each GPU multiplied the columns it owns: complete the replicated rows
+      exchange_replicated_rows(h, h.d_w, false);
+      exchange_replicated_rows(h, h.d_r1, false);
+    }
+    int boff = 0;
+    for (auto& r : h.dot_ranges) {
+      const int len = r.second - r.first, nb = cdiv(len, 256);
+      if (nb > 0) k_resid_part<<<nb, 256, 0, h.stream>>>(len, h.d_w + r.first, h.d_r1 + r.first, h.eigenvalues[i], h.d_x + r.first, d_part + 2 * boff);
+      boff += nb;
+    }
+    k_sum_partials<<<1, 256, 0, h.stream>>>(d_part, boff, 2, h.d_red + 516);
+    k_sum_partials<<<1, 256, 0, h.stream>>>(d_part + 1, boff, 2, h.d_red + 517);
+    LSA_LAUNCH_CHECK();
+    comm_allreduce_sum(h.comm, h.d_red + 516, 2, h.stream);
+    double s12[2] = {0, 0};
+    LSA_CUDA(cudaMemcpyAsync(s12, h.d_red + 516, sizeof(s12), cudaMemcpyDeviceToHost, h.stream));
+    LSA_CUDA(cudaStreamSynchronize(h.stream));
+    out_host[i] = std::sqrt(s12[0]) / (std::max(h.a_fro, 1e-300) * std::sqrt(std::max(s12[1], 1e-300)));
   }
   cudaFree(d_part);
 }

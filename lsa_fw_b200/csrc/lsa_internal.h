@@ -28,8 +28,12 @@ struct Front {
   int level;        // depth in the assembly tree (roots are level 0)
   int child0;       // first entry in child_idx
   int nchild;       // number of children
-  int pad;
+  int flags;        // partitioned solve: 0 regular; FRONT_GHOST: root of a sub-tree owned by ANOTHER GPU, present
+                    // only as a contribution block (k = 0); FRONT_CUT: root of one of this GPU's sub-trees.
+                    // The contribution block of a flagged front lives in the cut pool (c_off refers to it), and
+                    // the sweeps hand its contribution vector over through the all-reduce of the replicated rows.
 };
+enum { FRONT_REGULAR = 0, FRONT_GHOST = 1, FRONT_CUT = 2 };
 
 struct Symbolic {
   int n = 0;        // matrix order
@@ -56,6 +60,31 @@ struct Symbolic {
   int max_k = 0, max_m = 0, max_r = 0;
   double seconds[4] = {0, 0, 0, 0};  // graph, ordering, structure, maps
 };
+
+// Split of ONE factorisation / solve over the GPUs of a node (stage 1): proportional mapping of the
+// assembly tree -- whole sub-trees go to single GPUs (no communication inside), the fronts above the cut ("top")
+// are REPLICATED: every GPU factors and sweeps them redundantly on identical data.  Exchange steps: the
+// contribution blocks of the sub-tree roots are broadcast once per factorisation; per operator application ONE
+// all-reduce over the replicated rows carries both the SpMV partial sums of those rows and the sub-tree roots'
+// contribution vectors.
+struct Partition {
+  int rank = 0, world = 1;
+  std::vector<int> owner;       // per GLOBAL front: -1 replicated top, else the owning GPU
+  std::vector<int> l2g, g2l;    // local front id <-> global front id (-1: not present on this rank)
+  std::vector<int> cut_roots;   // GLOBAL ids of the sub-tree roots with a (top) parent, ascending: broadcast order
+  int n_top_levels = 0;         // local levels [0, n_top_levels) hold the top fronts, deeper ones this GPU's sub-trees
+  std::vector<int> own_lo, own_hi;   // permuted row ranges [lo, hi) of this GPU's sub-trees
+  std::vector<int> top_lo, top_hi;   // replicated rows: decoupled pivots first, then the top fronts
+  long long n_top_rows = 0;
+  long long cut_pool_size = 0;  // entries of the cut pool (contribution blocks of ALL sub-tree roots)
+  double weight_total = 0, weight_top = 0, weight_max = 0, weight_mine = 0;   // work model (see partition.cpp)
+  int ns_global = 0;
+  long long nnz_lu_global = 0;
+  double flops_global = 0;
+};
+
+// partition.cpp: `global` -> this rank's local symbolic structures (only the fronts this GPU touches).
+void partition(const Symbolic& global, int rank, int world, Symbolic& local, Partition& part);
 
 struct AnalyzeOptions {
   int leaf_size = 64;

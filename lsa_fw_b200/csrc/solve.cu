@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(NT) k_up_gather(const Front* __restrict__ fron
   __syncthreads();
   for (int q = 0; q < p.nchild; ++q) {
     const Front c = fronts[child_idx[p.child0 + q]];
+    // partitioned solve: the contribution vector of a sub-tree root reaches the replicated rows through the
+    // all-reduce (k_cut_scatter), whichever GPU owns it
+    if (c.flags != FRONT_REGULAR) continue;
     const int* map = ea_map + c.st0;
     const z128* cbc = cb + c.st0;
     for (int t = threadIdx.x; t < c.r; t += NT) {
@@ -1710,6 +1713,58 @@ __global__ void __launch_bounds__(256) k_level_unpermute(const Front* __restrict
   for (int i = threadIdx.x; i < f.k; i += blockDim.x) x[gperm[f.col0 + i]] = y[f.col0 + i];
 }
 
+// ------------------------------------------------------ partitioned solve: exchange over the replicated rows
+//
+// After the up sweep of a GPU's own sub-trees every sub-tree root holds a contribution vector for rows of the
+// replicated top.  Contributions are additive on their way up the tree, so they are added straight to the
+// right-hand-side entries of their final rows (x[st_idx[...]]); then ONE all-reduce over the replicated rows
+// sums, in the same payload, the sub-tree contributions of all GPUs and the partial SpMV results of those rows
+// (each GPU multiplied only the columns it owns).  One CTA, the roots one after the other (a root's row set is
+// injective, two roots may share rows): deterministic.
+__global__ void __launch_bounds__(1024) k_cut_scatter(const Front* __restrict__ fronts, const int* __restrict__ cut_own,
+                                                      int ncut, const int* __restrict__ st_idx,
+                                                      const z128* __restrict__ cb, z128* __restrict__ x) {
+  for (int q = 0; q < ncut; ++q) {
+    const Front c = fronts[cut_own[q]];
+    for (int t = threadIdx.x; t < c.r; t += blockDim.x) x[st_idx[c.st0 + t]] += cb[c.st0 + t];
+    __syncthreads();
+  }
+}
+__global__ void k_pack_rows(const z128* __restrict__ x, const int* __restrict__ rows, int nrows, z128* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows) buf[i] = x[rows[i]];
+}
+__global__ void k_unpack_rows(z128* __restrict__ x, const int* __restrict__ rows, int nrows, const z128* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows) x[rows[i]] = buf[i];
+}
+__global__ void k_zero_rows(z128* __restrict__ x, const int* __restrict__ rows, int nrows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows) x[rows[i]] = mk(0, 0);
+}
+// A vector whose replicated rows hold the SAME (complete) values on every GPU becomes one whose replicated rows
+// sum to those values over the GPUs: the form the sweeps expect on entry.
+void replicated_rows_to_partial(lsa_handle_impl& h, z128* x) {
+  if (!h.partitioned || h.part.rank == 0 || h.part.n_top_rows == 0) return;
+  k_zero_rows<<<cdiv(h.part.n_top_rows, 256), 256, 0, h.stream>>>(x, h.d_top_rows, (int)h.part.n_top_rows);
+  LSA_LAUNCH_CHECK();
+}
+
+// x[replicated rows] <- sum over the GPUs (after adding this GPU's sub-tree contributions)
+void exchange_replicated_rows(lsa_handle_impl& h, z128* x, bool with_cut_contributions) {
+  cudaStream_t st = h.stream;
+  const int nrows = (int)h.part.n_top_rows;
+  if (with_cut_contributions && h.n_cut_own > 0) {
+    k_cut_scatter<<<1, 1024, 0, st>>>(h.d_fronts, h.d_cut_own, h.n_cut_own, h.d_st_idx, h.d_cb, x);
+    LSA_LAUNCH_CHECK();
+  }
+  if (nrows == 0) return;
+  k_pack_rows<<<cdiv(nrows, 256), 256, 0, st>>>(x, h.d_top_rows, nrows, h.d_topbuf);
+  comm_allreduce_sum(h.comm, (double*)h.d_topbuf, 2 * (size_t)nrows, st);
+  k_unpack_rows<<<cdiv(nrows, 256), 256, 0, st>>>(x, h.d_top_rows, nrows, h.d_topbuf);
+  LSA_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------------------------------- driver
 
 // Level plan of the sweeps (host, once per factorisation): chunks of <= 32768 fronts of one level, each with the
@@ -1777,11 +1832,6 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   tr.begin(st);
   const std::vector<int>& lvl_front = sym.lvl_front;
   const int* d_lvl_front = h.d_lvl_front;
-  if (sym.n_iso > 0) {
-    k_solve_decoupled<T, H><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, x, y);
-    LSA_LAUNCH_CHECK();
-    launches++;
-  }
   auto up_off = [&](const SolveChunk& c) {
     if (c.max_r <= 0) return;
     if (c.maxk > 512) k_up_off<T, H, 32><<<dim3(cdiv(c.max_r, 32), c.cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, z, cb);
@@ -1791,7 +1841,16 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     launches++;
   };
   // ---- up sweep: deepest level first
-  for (int ci = (int)h.solve_plan.size() - 1; ci >= 0; --ci) {
+  bool exchanged = !h.partitioned;
+  for (int ci = (int)h.solve_plan.size() - 1; ci >= -1; --ci) {
+    if (!exchanged && (ci < 0 || h.solve_plan[ci].level < h.part.n_top_levels)) {
+      // partitioned solve: this GPU's sub-trees are done -> all-reduce over the replicated rows, then the top
+      exchange_replicated_rows(h, x, true);
+      tr.mark("exchange", h.part.n_top_levels, 0, (int)h.part.n_top_rows, 1);
+      launches += 3;
+      exchanged = true;
+    }
+    if (ci < 0) break;
     const SolveChunk& c = h.solve_plan[ci];
     const int d = c.level, cnt = c.cnt, first = c.first, maxk = c.maxk, max_r = c.max_r, max_m = c.max_m;
     if (cnt <= 2 * h.num_sms)
@@ -1855,6 +1914,12 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       tr.mark("up_step", d, j0, gx, act);
       launches++;
     }
+  }
+  // decoupled 1 x 1 pivots (after the exchange of a partitioned solve: their right-hand sides are replicated rows)
+  if (sym.n_iso > 0) {
+    k_solve_decoupled<T, H><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, x, y);
+    LSA_LAUNCH_CHECK();
+    launches++;
   }
   // ---- down sweep: roots first
   for (size_t ci = 0; ci < h.solve_plan.size(); ++ci) {

@@ -186,6 +186,27 @@ def _array_digest(arr: np.ndarray) -> bytes:
     return dig
 
 
+_DIAG_MEMO: dict[int, tuple] = {}
+
+
+def _diagonal(mat: sp.csr_matrix) -> np.ndarray:
+    """`mat.diagonal()` through memoised diagonal positions (per pattern OBJECT, as `_array_digest`): a gather of n
+    values instead of SciPy's search over all nnz entries on every solve of a sweep."""
+    idx = mat.indices
+    hit = _DIAG_MEMO.get(id(idx))
+    if hit is None or hit[0] is not idx or hit[1] is not mat.indptr:
+        n = mat.shape[0]
+        rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(mat.indptr))
+        pos = np.nonzero(idx == rows)[0]
+        if len(_DIAG_MEMO) > 16:
+            _DIAG_MEMO.clear()
+        hit = (idx, mat.indptr, pos, rows[pos])
+        _DIAG_MEMO[id(idx)] = hit
+    d = np.zeros(mat.shape[0], dtype=mat.data.dtype)
+    d[hit[3]] = mat.data[hit[2]]   # (callers pass canonical matrices: no duplicate entries)
+    return d
+
+
 def _values_token(mat) -> tuple:
     """Identity + cheap content probe of a value array: (the array object, its sampled digest)."""
     return (mat.data, _sample_digest(mat.data))
@@ -309,7 +330,7 @@ class iEpsSolver:  # noqa: N801
         # backend options (extensions; all optional)
         self._opts = dict(leaf_size=64, coords=None, refine_steps=0, tiny_pivot=1e-13, seed=0, device=0,
                           purify=True, nthreads=0, v0=None, force_complex=False, coupled_fraction=0.5,
-                          growth_limit=1e6, device_values=None)
+                          growth_limit=1e6, device_values=None, partition=None)
         self._adjoint = False
         self._handle: _lib.Handle | None = None
         self._factor_key = None
@@ -383,7 +404,8 @@ class iEpsSolver:  # noqa: N801
         tolerated before the solve re-analyses / switches iterative refinement on), device_values
         ((A_vals, M_vals) already resident on the GPU, in CSR entry order: torch CUDA tensors or any object
         with `__cuda_array_interface__` / `__dlpack__`; the host copies in A / M are then only used for
-        their pattern)."""
+        their pattern), partition ("auto": split this factorisation / eigensolve over the GPUs of the initialised
+        torch.distributed group, one process per GPU, every rank making the same calls -- lsa_fw_b200/partitioned.py)."""
         unknown = set(kw) - set(self._opts)
         if unknown:
             raise TypeError(f"unknown backend option(s): {sorted(unknown)}")
@@ -413,6 +435,13 @@ class iEpsSolver:  # noqa: N801
             # EPSSetDimensions_Default: "The value of ncv must be at least nev"
             raise ValueError(f"The value of ncv ({self._ncv}) must be at least nev ({self._nev})")
         return max(1, min(ncv, n))
+
+    def _partition_world(self) -> tuple[int, int]:
+        if not self._opts["partition"]:
+            return 0, 1
+        from .partitioned import world_info
+
+        return world_info()
 
     def _which_effective(self) -> iEpsWhich:
         if self._which is not None:
@@ -495,24 +524,34 @@ class iEpsSolver:  # noqa: N801
             # Shift-independent form for sinvert (rows whose diagonal vanishes in A AND in M), so that the
             # analysis is valid for every shift of a sweep; part of the cache key together with the transform.
             if sinvert:
-                order_last = ((A.diagonal() == 0) & ((M.diagonal() if M is not None else np.ones(n)) == 0))
+                order_last = ((_diagonal(A) == 0) & ((_diagonal(M) if M is not None else np.ones(n)) == 0))
             else:
-                order_last = (M.diagonal() if M is not None else A.diagonal()) == 0
+                order_last = (_diagonal(M) if M is not None else _diagonal(A)) == 0
             order_last = order_last.astype(np.uint8)
             key = _pattern_key(A, M, (self._opts["leaf_size"],
                                       None if coords is None else hashlib.blake2b(
                                           np.ascontiguousarray(coords).tobytes(), digest_size=16).hexdigest(),
                                       self._opts["device"], self._opts["coupled_fraction"], self._st_type.value,
+                                      self._partition_world(),
                                       hashlib.blake2b(order_last.tobytes(), digest_size=16).hexdigest()))
             h = _SYM_CACHE.get(key)
             if h is not None and h.closed:
                 h = None
             if h is None:
-                h = _lib.Handle(n, self._opts["device"])
+                rank, world = self._partition_world()
+                h = _lib.Handle(n, self._opts["device"], rank, world)
                 h.set_option("coupled_fraction", self._opts["coupled_fraction"])
                 h.analyze(A.indptr, A.indices, None if M is None else M.indptr, None if M is None else M.indices,
                           leaf_size=self._opts["leaf_size"], coords=coords, order_last=order_last,
                           nthreads=self._opts["nthreads"])
+                if h.world > 1:
+                    from .partitioned import attach_comm
+
+                    attach_comm(h)
+                    pi = h.partition_info()
+                    stats.update(partition_rank=pi.rank, partition_world=pi.world, n_top_fronts=pi.n_top_fronts,
+                                 n_replicated_rows=int(pi.n_replicated_rows), n_own_rows=int(pi.n_own_rows),
+                                 partition_weights=(pi.weight_top, pi.weight_max_subtrees, pi.weight_total))
                 while len(_SYM_CACHE) >= _SYM_CACHE_MAX:
                     # evicted handles are NOT closed here: live solvers (and adjoint donors) may still hold
                     # them; the device buffers go when the last reference does
@@ -589,6 +628,8 @@ class iEpsSolver:  # noqa: N801
         self._handed_out = set()
         t0 = time.perf_counter()
         if res.nconv > 0:
+            # the pairs `EigenSolver.solve()` hands out (min(nconv, nev)) come to the host now: the handle and its
+            # device buffers may be shared; converged extras are fetched by the same call (one block, one size)
             self._fetch_vectors()
         stats["fetch_seconds"] = time.perf_counter() - t0
         stats.update(nconv=res.nconv, n_restarts=res.n_restarts, n_op_applies=res.n_op_applies,
@@ -613,7 +654,10 @@ class iEpsSolver:  # noqa: N801
 
     def _fetch_vectors(self) -> np.ndarray:
         if self._eigenvectors is None:
-            X = self._handle.eigenvectors(self._nconv)
+            if self._handle.closed or self._handle.gen_result != self._result_gen:
+                raise RuntimeError("the device-side results of this solver were overwritten by a later solve on the "
+                                   "shared handle; call solve() again")
+            X = self._handle.eigenvectors(self._nconv, capacity=max(self._nconv, self._nev))
             # (the arbitrary phase is fixed on the device: largest component real positive)
             if self._problem_type in (iEpsProblemType.GHEP,) and self._M is not None:
                 # SLEPc normalises GHEP eigenvectors to unit B-norm

@@ -590,8 +590,8 @@ def test_backward_step_pencil_against_oracle(shape):
 
     The pencil is strongly non-normal (kappa(lambda) from 4e7 for the leading pair to > 1e15 for the 20th mode: the
     oracle's OWN direct, adjoint and ARPACK runs agree only to kappa * 1e-16 there), so eigenvalue parity is a
-    statement about the modes whose conditioning admits one (kappa * 1e-14 <= 1e-6; every such mode must match to
-    max(1e-8, 1e-14 kappa)), kappa is printed per mode, and ALL modes must meet the backward-error bar
+    statement about the modes whose conditioning admits one (kappa <= 1e9; every such mode must match to
+    max(1e-8, 1e-14 kappa) <= 1e-5), kappa is printed per mode, and ALL modes must meet the backward-error bar
     ||A x - lambda M x|| / (||A||_F ||x||) <= 1e-10 -- each returned pair is an exact eigenpair of a pencil
     1e-10-close to the given one, which is all any backend can deliver for kappa ~ 1e15."""
     pc = pencils.backward_step_2d(*shape, re=500.0)
@@ -616,14 +616,14 @@ def test_backward_step_pencil_against_oracle(shape):
             j, kappa = _kappa(pc, d, a, lt)
             err = abs(lt - d.eigenvalues[j]) / abs(lt)
             print(f"step {shape} {tag}: lambda = {lt:.10g}  kappa = {kappa:.2e}  |d lambda|/|lambda| = {err:.1e}")
-            if 1e-14 * kappa <= 1e-6:
+            if kappa <= 1e9:
                 well += 1
                 assert err < max(EIG_RTOL, 1e-14 * kappa), (tag, l, d.eigenvalues[j], kappa)
     assert well >= 2          # the leading conjugate pair is always well enough conditioned
     # the set of wanted modes: every oracle mode that is both well conditioned and among its 10 nearest to sigma is found
     for l in d.eigenvalues[:10]:
         j, kappa = _kappa(pc, d, a, l)
-        if 1e-14 * kappa <= 1e-6:
+        if kappa <= 1e9:
             assert min(abs(lam - l)) / abs(l) < max(EIG_RTOL, 1e-14 * kappa)
 
 
@@ -816,3 +816,26 @@ def test_multiplier_growth_triggers_reanalysis_then_refinement(caplog):
     es0, pairs0 = _run(pc, sigma, nev=4)
     assert np.allclose([p[0] for p in pairs], [p[0] for p in pairs0], rtol=1e-9)
     assert es.solver.get_residuals()[:4].max() < RESID_BAR
+
+
+# ------------------------------------------------------------------ one solve split over several GPUs (row e)
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_solve_over_gpus(world):
+    """Sub-trees per GPU + replicated top, NCCL broadcast / all-reduce inside the CUDA library: solves to 1e-12,
+    eigenvalues identical to the single-GPU run, same results on every rank (tests/workers/partitioned_gpu_worker.py)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29650 + world),
+                          os.path.join(root, "tests", "workers", "partitioned_gpu_worker.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-4000:])
+    assert "PARTITIONED_OK" in out.stdout
+    print(out.stdout[-1500:])
