@@ -215,6 +215,13 @@ int lsa_solve(lsa_handle* h, int32_t trans, const double* b, double* x, int32_t 
 /* lsa_spmv <- MatMult / MatMultHermitianTranspose with A or M    (Solver/eigen2.py:174, :52-53). */
 int lsa_spmv(lsa_handle* h, int32_t which_matrix, int32_t trans, const double* x, double* y, int32_t on_device);
 
+/* lsa_bilinear <- the scalar contractions of the sensitivity analysis, a^H B v with B on the sparsity pattern of A
+ * (or M) and caller-supplied values in the ORIGINAL CSR entry order: bi-orthonormalisation a^H M v
+ * (Sensitivity/__init__.py:280-287) and d lambda = a^H (dA/dRe) v with a pre-assembled derivative operator in place
+ * of the UFL integrals of Sensitivity/__init__.py:354-385.  a, v: n complex numbers, original ordering.     */
+int lsa_bilinear(lsa_handle* h, int32_t which_matrix, const void* vals, int32_t scalar, const double* a, const double* v,
+                 int32_t on_device, double* out_c128);
+
 /* -- eigensolve ------------------------------------------------------------------------------
  * lsa_eigs <- SLEPc.EPS.solve()  (Solver/utils.py:268-270): Krylov-Schur on OP, Gram-Schmidt with
  * refinement if needed (up to 256 basis columns),

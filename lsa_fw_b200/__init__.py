@@ -2,12 +2,14 @@
 
 from .carriers import iComplexPETScVector, iPETScMatrix, iPETScVector
 from .eigen import EigenSolver, EigensolverConfig
-from .sensitivity import direct_and_adjoint_modes, normalize_adjoint, select_mode
+from .linear import KSPType, LinearSolver, iKSP
+from .sensitivity import direct_and_adjoint_modes, eigenvalue_sensitivity, normalize_adjoint, select_mode
 from .utils import (LsaError, PreconditionerType, clear_symbolic_cache, iEpsProblemType, iEpsSolver, iEpsWhich,
                     iSTType)
 
 __all__ = [
     "EigenSolver", "EigensolverConfig", "iEpsSolver", "iEpsProblemType", "iEpsWhich", "iSTType",
     "PreconditionerType", "iPETScMatrix", "iPETScVector", "iComplexPETScVector", "LsaError",
-    "clear_symbolic_cache", "select_mode", "normalize_adjoint", "direct_and_adjoint_modes",
+    "clear_symbolic_cache", "select_mode", "normalize_adjoint", "direct_and_adjoint_modes", "eigenvalue_sensitivity",
+    "KSPType", "iKSP", "LinearSolver",
 ]

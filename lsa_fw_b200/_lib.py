@@ -193,6 +193,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lsa_solve.argtypes = [vp, i32, vp, vp, i32, i32]
     lib.lsa_spmv.argtypes = [vp, i32, i32, vp, vp, i32]
     lib.lsa_eigs.argtypes = [vp, C.POINTER(EigsParams), C.POINTER(EigsResult)]
+    lib.lsa_bilinear.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp]
     lib.lsa_get_eigenvalues.argtypes = [vp, vp, i32]
     lib.lsa_get_eigenvectors.argtypes = [vp, vp, i64, i32, i32]
     lib.lsa_get_residuals.argtypes = [vp, vp, i32]
@@ -211,7 +212,7 @@ EXPORTS = [
     "lsa_symbolic_array", "lsa_set_values", "lsa_factor", "lsa_solve", "lsa_spmv", "lsa_eigs",
     "lsa_get_eigenvalues", "lsa_get_eigenvectors", "lsa_get_residuals", "lsa_get_counters", "lsa_sync",
     "lsa_host_alloc", "lsa_host_free", "lsa_dense_schur", "lsa_gemm_bench",
-    "lsa_set_partition", "lsa_nccl_load", "lsa_nccl_unique_id", "lsa_set_comm", "lsa_partition_info_get",
+    "lsa_bilinear", "lsa_set_partition", "lsa_nccl_load", "lsa_nccl_unique_id", "lsa_set_comm", "lsa_partition_info_get",
 ]
 
 _ARRAY_DTYPES = {
@@ -430,6 +431,17 @@ class Handle:
         y = np.empty_like(x)
         self.check(self.lib.lsa_spmv(self._h, which, trans, x.ctypes.data, y.ctypes.data, 0))
         return y
+
+    def bilinear(self, which: int, vals: np.ndarray, a: np.ndarray, v: np.ndarray) -> complex:
+        """a^H B v on the device, B = the pattern of A (or M) with `vals` in the caller's CSR entry order."""
+        vals = np.ascontiguousarray(vals)
+        sc = LSA_C128 if np.iscomplexobj(vals) else LSA_F64
+        vals = vals.astype(np.complex128 if sc else np.float64, copy=False)
+        a = np.ascontiguousarray(a, dtype=np.complex128)
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        out = np.zeros(1, dtype=np.complex128)
+        self.check(self.lib.lsa_bilinear(self._h, which, vals.ctypes.data, sc, a.ctypes.data, v.ctypes.data, 0, out.ctypes.data))
+        return complex(out[0])
 
     def eigs(self, *, nev, ncv, tol, max_restarts, which, transform, sigma=0.0, adjoint=False, purify=True,
              refine_steps=0, seed=0, v0=None) -> EigsResult:

@@ -840,6 +840,62 @@ int lsa_spmv(lsa_handle* h, int32_t which_matrix, int32_t trans, const double* x
   return LSA_OK;
 }
 
+int lsa_bilinear(lsa_handle* h, int32_t which_matrix, const void* vals, int32_t scalar, const double* a, const double* v,
+                 int32_t on_device, double* out_c128) {
+  if (!h || !vals || !a || !v || !out_c128 || !h->analyzed) return LSA_ERR_ARG;
+  if (which_matrix == LSA_MAT_M && !h->has_m) return fail(h, LSA_ERR_ARG, "no M operator");
+  if (int rc = need_device(h)) return rc;
+  if (h->partitioned) return fail(h, LSA_ERR_ARG, "lsa_bilinear is not available on a partitioned handle");
+  LSA_API_BEGIN
+  const int n = h->n;
+  cudaStream_t st = h->stream;
+  const bool cplx = scalar == LSA_C128;
+  const CsrDev& pat = which_matrix == LSA_MAT_A ? h->dA : h->dM;
+  const size_t esz = cplx ? 16 : 8;
+  void* d_orig = nullptr;
+  void* d_perm_vals = nullptr;
+  z128* d_a = nullptr;
+  try {
+    const void* src_vals = vals;
+    if (!on_device) {
+      LSA_CUDA(cudaMalloc(&d_orig, std::max<size_t>(16, (size_t)pat.nnz * esz)));
+      LSA_CUDA(cudaMemcpyAsync(d_orig, vals, (size_t)pat.nnz * esz, cudaMemcpyHostToDevice, st));
+      src_vals = d_orig;
+    }
+    LSA_CUDA(cudaMalloc(&d_perm_vals, std::max<size_t>(16, (size_t)pat.nnz * esz)));
+    gather_values(st, src_vals, cplx, pat.src, d_perm_vals, pat.nnz);
+    CsrDev tmp = pat;          // same pattern, the caller's values
+    tmp.vals = d_perm_vals;
+    tmp.is_complex = cplx;
+    d_a = dalloc<z128>(n);
+    const z128* av = (const z128*)a;
+    const z128* vv = (const z128*)v;
+    if (!on_device) {
+      LSA_CUDA(cudaMemcpyAsync(h->d_io, a, sizeof(z128) * (size_t)n, cudaMemcpyHostToDevice, st));
+      permute_gather(st, h->d_io, d_a, h->d_perm, n);
+      LSA_CUDA(cudaMemcpyAsync(h->d_io, v, sizeof(z128) * (size_t)n, cudaMemcpyHostToDevice, st));
+      permute_gather(st, h->d_io, h->d_x, h->d_perm, n);
+    } else {
+      permute_gather(st, av, d_a, h->d_perm, n);
+      permute_gather(st, vv, h->d_x, h->d_perm, n);
+    }
+    spmv(*h, tmp, false, h->d_x, h->d_w);
+    z128 res = dot_conj(*h, d_a, h->d_w);   // a^H (B v)
+    out_c128[0] = res.x;
+    out_c128[1] = res.y;
+  } catch (...) {
+    if (d_orig) cudaFree(d_orig);
+    if (d_perm_vals) cudaFree(d_perm_vals);
+    if (d_a) cudaFree(d_a);
+    throw;
+  }
+  if (d_orig) cudaFree(d_orig);
+  cudaFree(d_perm_vals);
+  cudaFree(d_a);
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
 int lsa_eigs(lsa_handle* h, const lsa_eigs_params* p, lsa_eigs_result* out) {
   if (!h || !p || !out || !h->have_values) return LSA_ERR_ARG;
   if (int rc = need_device(h)) return rc;

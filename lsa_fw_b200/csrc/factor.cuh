@@ -73,6 +73,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
 void dense_schur_device(lsa_handle_impl& h, int m, z128* dS, int ld, z128* dQ, int which, int transform, z128 sigma);
 void op_solve(lsa_handle_impl& h, int trans, z128* x, int refine_steps);
 void drop_solve_graphs(lsa_handle_impl& h);
+z128 dot_conj(lsa_handle_impl& h, const z128* a, const z128* w);   // a^H w (single GPU)
 void make_full(lsa_handle_impl& h, z128* vec, int ncols, long long ld);   // partitioned solve: complete, identical vectors on every GPU
 void permute_gather(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n);   // dst[i] = src[perm[i]]
 void permute_scatter(cudaStream_t st, const z128* src, z128* dst, const int* perm, int n);  // dst[perm[i]] = src[i]

@@ -763,6 +763,20 @@ static void orthonormalize(lsa_handle_impl& h, z128* V, long long ldv, int jj, z
   LSA_LAUNCH_CHECK();
 }
 
+// a^H w on the device (single GPU): the tall-skinny dot kernel with a one-column "basis"
+z128 dot_conj(lsa_handle_impl& h, const z128* a, const z128* w) {
+  const int n = h.n;
+  const int rows_per_block = std::max(1024, (int)(((long long)n + 591) / 592 + 31) / 32 * 32);
+  const int nblk = cdiv(n, rows_per_block);
+  launch_dots(h.stream, nblk, n, 1, a, n, w, h.d_part, 256, rows_per_block, nullptr, nullptr);
+  k_reduce_h<<<1, 256, 0, h.stream>>>(1, nblk, h.d_part, 256, h.d_h, h.d_brow, 0, nullptr);
+  LSA_LAUNCH_CHECK();
+  z128 res;
+  LSA_CUDA(cudaMemcpyAsync(&res, h.d_h, sizeof(z128), cudaMemcpyDeviceToHost, h.stream));
+  LSA_CUDA(cudaStreamSynchronize(h.stream));
+  return res;
+}
+
 // ------------------------------------------------------------------------------------- OP and driver
 
 void drop_solve_graphs(lsa_handle_impl& h) {

@@ -2,8 +2,10 @@
 (`Sensitivity/__init__.py:171-203` direct mode, `:230-311` adjoint mode).  Host-side helpers on top of the
 carriers; the heavy part (both eigensolves, the second one on the factors of the first) is the CUDA path.
 
-SURVEY 8f row 2 ("next"): only the mode selection and the bi-orthonormal scaling `a^H M v = 1` live here; the
-derivative contraction `a^H (dA/dRe) v` needs the reference's UFL forms and stays out of scope.
+SURVEY 8f row 2: mode selection, the bi-orthonormal scaling `a^H M v = 1`, and the eigenvalue sensitivity
+`d lambda / d p = a^H (dA/dp - lambda dM/dp) v / (a^H M v)` as contractions with PRE-ASSEMBLED sparse derivative
+operators on the device (`lsa_bilinear`), standing in for the UFL integrals of `Sensitivity/__init__.py:354-385`
+(the explicit Reynolds term is `dA/dRe = -(1/Re^2) dA/d(1/Re)`, the viscous operator the assembler splits off).
 """
 
 from __future__ import annotations
@@ -14,7 +16,7 @@ import numpy as np
 
 from .carriers import iComplexPETScVector, iPETScMatrix, iPETScVector
 
-__all__ = ["select_mode", "normalize_adjoint", "direct_and_adjoint_modes"]
+__all__ = ["select_mode", "normalize_adjoint", "direct_and_adjoint_modes", "eigenvalue_sensitivity"]
 
 
 def select_mode(pairs: Iterable[tuple[complex, iComplexPETScVector]], target: complex):
@@ -85,3 +87,36 @@ def direct_and_adjoint_modes(A: iPETScMatrix, M: iPETScMatrix, sigma: complex, c
     lam_adj, a = select_mode(pairs_adj, np.conj(sigma))
     normalize_adjoint(a, M, v)
     return (lam, v), (lam_adj, a)
+
+
+def eigenvalue_sensitivity(solver, lam: complex, v, a, dA_values, *, dM_values=None, m_values=None) -> complex:
+    """First-order change of the eigenvalue `lam` of `A v = lam M v` with left eigenvector `a` under a change of
+    the operators given as VALUE arrays on the patterns of A and M (CSR entry order of the matrices the solver
+    analysed):
+
+        d lambda = a^H (dA - lam dM) v / (a^H M v)
+
+    evaluated on the GPU that holds the pencil (`solver`: the `iEpsSolver` / `EigenSolver` that computed `v`).
+    With `dA_values = -(1/Re^2) * pencil.a_visc` this is the explicit part of d sigma / d Re
+    (`Sensitivity/__init__.py:372-374`); the implicit base-flow part is the same contraction with the operator
+    `dA/dU . u_mu` assembled by the caller (`:376-381`).  `m_values`: values of M (default: the solver's own M)."""
+    from . import _lib
+    from .utils import _as_csr
+
+    eps = getattr(solver, "solver", solver)
+    h = eps.handle
+    if h is None or h.closed:
+        raise RuntimeError("the solver holds no device state; call solve() first")
+    vc = _as_complex_vector(v).as_array().astype(np.complex128)
+    ac = _as_complex_vector(a).as_array().astype(np.complex128)
+    num = h.bilinear(_lib.LSA_MAT_A, np.asarray(dA_values), ac, vc)
+    if dM_values is not None:
+        num -= lam * h.bilinear(_lib.LSA_MAT_M, np.asarray(dM_values), ac, vc)
+    if eps._M is not None:
+        mv = _as_csr(eps._M).data if m_values is None else np.asarray(m_values)
+        den = h.bilinear(_lib.LSA_MAT_M, mv, ac, vc)
+    else:
+        den = complex(np.vdot(ac, vc))
+    if den == 0:
+        raise RuntimeError("a^H M v = 0: the modes are not a direct / adjoint pair")
+    return num / den

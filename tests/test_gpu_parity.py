@@ -839,3 +839,87 @@ def test_partitioned_solve_over_gpus(world):
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-4000:])
     assert "PARTITIONED_OK" in out.stdout
     print(out.stdout[-1500:])
+
+
+# ------------------------------------------------------------------ rows f2 / f3: the callers on either side of the path
+def test_linear_solver_seam_runs_on_the_lu_kernels():
+    """`Solver/linear.py:38-87` / `Solver/nonlinear2.py:61-70`: direct (PREONLY + LU) and LU-preconditioned GMRES solves
+    of Jacobian-like systems (sparsity of A, real FP64), symbolic analysis reused from one Newton step to the next."""
+    import scipy.sparse.linalg as spla
+
+    L.clear_symbolic_cache()
+    pc = pencils.assemble_pencil((24, 12), (8.0, 3.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.5), split_viscous=True)
+    rng = np.random.default_rng(8)
+    b = rng.standard_normal(pc.n)
+    cached = []
+    for re_ in (50.0, 60.0, 75.0):                         # "Newton steps": new values on the same pattern
+        J = sp.csr_matrix((pc.a_data_at(re_), pc.A.indices, pc.A.indptr), shape=pc.A.shape)
+        ref = spla.splu(J.tocsc()).solve(b)
+        ksp = L.iKSP(L.iPETScMatrix(J))
+        ksp.set_type(L.KSPType.PREONLY)
+        ksp.set_preconditioner(L.PreconditionerType.LU)
+        x = ksp.solve(L.iPETScVector.from_array(b.copy()))
+        xa = x.as_array()
+        assert not np.iscomplexobj(xa) and ksp.stats["scalar"] == "f64"
+        assert np.linalg.norm(J @ xa - b) / np.linalg.norm(b) < 1e-11
+        assert np.linalg.norm(xa - ref) / np.linalg.norm(ref) < 1e-8
+        assert ksp.get_iteration_number() == 1 and ksp.raw.getType() == "preonly"
+        cached.append(ksp.stats["symbolic_cached"])
+    assert cached == [False, True, True]
+    J = sp.csr_matrix((pc.a_data_at(50.0), pc.A.indices, pc.A.indptr), shape=pc.A.shape)
+    sol = L.LinearSolver.solve(L.iPETScMatrix(J), L.iPETScVector.from_array(b.copy()), ksp_type=L.KSPType.GMRES, tol=1e-14, rtol=1e-13)
+    assert np.linalg.norm(J @ sol.as_array() - b) / np.linalg.norm(b) < 1e-12
+    # complex system, solution written into a caller-owned vector
+    Jc = (J + 0.3j * pc.M).tocsr()
+    bc = b + 1j * rng.standard_normal(pc.n)
+    ksp = L.iKSP(L.iPETScMatrix(Jc))
+    ksp.set_type(L.KSPType.GMRES)
+    ksp.set_tolerances(tol=1e-14, rtol=1e-13, max_it=5)
+    out = L.iPETScVector.from_array(np.zeros(pc.n, dtype=complex))
+    ksp.solve(L.iPETScVector.from_array(bc.copy()), out)
+    assert np.linalg.norm(Jc @ out.as_array() - bc) / np.linalg.norm(bc) < 1e-12 and ksp.get_residual_norm() < 1e-10
+    assert ksp.get_solution() is out
+    with pytest.raises(ValueError):
+        L.LinearSolver.solve(L.iPETScMatrix(J), L.iPETScVector.from_array(b), ksp_type=L.KSPType.CG)
+    bad = L.iKSP(L.iPETScMatrix(J))
+    bad.set_preconditioner(L.PreconditionerType.JACOBI)
+    with pytest.raises(NotImplementedError):
+        bad.solve(L.iPETScVector.from_array(b))
+
+
+def test_eigenvalue_sensitivity_contraction_matches_finite_differences():
+    """`Sensitivity/__init__.py:354-385` with pre-assembled operators: d lambda / d Re = a^H (dA/dRe) v / (a^H M v),
+    dA/dRe = -(1/Re^2) dA/d(1/Re), contracted on the device; checked against centred differences of the
+    eigenvalue itself (fixed base flow: the explicit term is the whole derivative)."""
+    pc = pencils.assemble_pencil((24, 12), (8.0, 3.0), re=50.0, baseflow=pencils.wake_profile(0.9, 1.2, 1.5), split_viscous=True)
+    re0, sigma = 50.0, 0.05 + 0.6j
+    M_c = L.iPETScMatrix(pc.M)
+
+    def modes(re_, adjoint=False):
+        A = sp.csr_matrix((pc.a_data_at(re_), pc.A.indices, pc.A.indptr), shape=pc.A.shape)
+        cfg = L.EigensolverConfig(num_eig=4, atol=1e-12, max_it=300, ncv=40)
+        es = L.EigenSolver(L.iPETScMatrix(A), M_c, cfg, check_hermitian=False)
+        es.solver.set_st_type(L.iSTType.SINVERT)
+        es.solver.set_target(sigma)
+        es.solver.set_st_pc_type(L.PreconditionerType.LU)
+        es.solver.set_backend_options(leaf_size=32)
+        es.solver.set_adjoint(adjoint)
+        return es, es.solve()
+
+    es, pairs = modes(re0)
+    lam, v = L.select_mode(pairs, sigma)
+    ea, pairs_adj = modes(re0, adjoint=True)
+    lam_adj, a = L.select_mode(pairs_adj, np.conj(lam))
+    assert abs(np.conj(lam_adj) - lam) < 1e-9 * abs(lam)
+    dl = L.eigenvalue_sensitivity(es, lam, v, a, -(1.0 / re0**2) * pc.a_visc)
+    # host check of the contraction itself
+    va, aa = _vec(v), _vec(a)
+    K = sp.csr_matrix((pc.a_visc, pc.A.indices, pc.A.indptr), shape=pc.A.shape)
+    assert dl == pytest.approx(-(1.0 / re0**2) * np.vdot(aa, K @ va) / np.vdot(aa, pc.M @ va), rel=1e-10)
+    # finite differences of the eigenvalue
+    d = 0.05
+    lp = L.select_mode(modes(re0 + d)[1], lam)[0]
+    lm = L.select_mode(modes(re0 - d)[1], lam)[0]
+    fd = (lp - lm) / (2 * d)
+    print(f"d lambda / d Re: contraction {dl:.8e}  finite differences {fd:.8e}")
+    assert abs(dl - fd) < 1e-5 * abs(fd) + 1e-9
