@@ -180,6 +180,8 @@ int lsa_partition_info_get(const lsa_handle* h, lsa_partition_info* out);
  *       launch per 128-pivot step instead; "cluster_slices" (1): levels with <= 9 fronts use 16-CTA clusters that
  *       share every 128-row block by 8-row slices (DSMEM all-gather of the solved entries); "defer_cb" (1): the
  *       contribution rows are updated by one wide GEMV after the pivot steps;
+ *   "fuse_ortho" (default 1): the update of the first Gram-Schmidt pass and the dot products of the second one in
+ *       one kernel (the basis is read three times per column instead of four);
  *   "ortho_refine_always" (default 0): second Gram-Schmidt pass for every basis column instead of SLEPc's
  *       refine-if-needed rule. */
 int lsa_set_option(lsa_handle* h, const char* name, double value);
@@ -191,7 +193,8 @@ int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int
 
 /* lsa_set_values <- values of the AIJ matrices handed to eps.setOperators; may be called again
  * with new values on the same pattern (Reynolds sweep, BASELINE config 3).  `a_scalar`/`m_scalar`
- * are lsa_scalar; values are in the ORIGINAL CSR entry order.  on_device: pointers are device memory. */
+ * are lsa_scalar; values are in the ORIGINAL CSR entry order.  on_device: pointers are device memory.
+ * m_vals == NULL on a handle that already holds values keeps M (only A changes along a Reynolds sweep). */
 int lsa_set_values(lsa_handle* h, const void* a_vals, int32_t a_scalar, const void* m_vals, int32_t m_scalar,
                    int32_t on_device);
 

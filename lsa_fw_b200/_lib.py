@@ -279,6 +279,7 @@ class Handle:
         self._h = C.c_void_p()
         # generations of the numeric state: solvers that share a handle (symbolic cache, adjoint reuse) check
         # them before they trust factors / device-side results they did not just produce themselves
+        self.m_token = None   # identity + content probe of the M values resident on the device
         self.gen_factor = 0   # bumped by set_values and factor
         self.gen_result = 0   # bumped by eigs (and by everything that bumps gen_factor)
         rc = self.lib.lsa_create(self.n, device, C.byref(self._h))
@@ -373,6 +374,8 @@ class Handle:
         self.gen_factor += 1
         self.gen_result += 1
         self.check(self.lib.lsa_set_values(self._h, a_vals.ctypes.data, a_sc, mp, m_sc, 0))
+        if m_vals is not None:
+            self.m_token = None     # set by callers that want to skip an unchanged M next time (utils.py)
 
     def set_values_device(self, a_vals, m_vals=None) -> None:
         """Values already resident on this handle's GPU, in the CSR entry order of the analysed pattern
@@ -386,6 +389,7 @@ class Handle:
         self.gen_factor += 1
         self.gen_result += 1
         self.check(self.lib.lsa_set_values(self._h, ap, a_sc, mp, m_sc, 1))
+        self.m_token = None
         del keep_a, keep_m
 
     def factor(self, alpha: complex, beta: complex, scalar: int, tiny_pivot: float) -> FactorStats:

@@ -59,6 +59,8 @@ void free_device(lsa_handle_impl& h) {
   h.d_inv_scratch = nullptr;
   h.inv_scratch_bytes = h.inv_scratch_entries = 0;
   dfree(h.d_inv_off);
+  dfree(h.d_tri_scratch); dfree(h.d_tri_tickets);
+  h.tri_slots = 0;
   h.solve_plan.clear();
   for (int q = 0; q < 2; ++q) {
     if (h.d_pool[q]) cudaFree(h.d_pool[q]);
@@ -67,7 +69,7 @@ void free_device(lsa_handle_impl& h) {
   }
   dfree(h.d_x); dfree(h.d_w); dfree(h.d_t); dfree(h.d_t2); dfree(h.d_cb); dfree(h.d_io); dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q);
   dfree(h.d_part); dfree(h.d_npart); dfree(h.d_h); dfree(h.d_brow); dfree(h.d_ywork); dfree(h.d_r1); dfree(h.d_r2);
-  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_refine); dfree(h.d_wn2); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
+  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_refine); dfree(h.d_wn2); dfree(h.d_wn2b); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
   h.V_cols = 0; h.X_cols = 0; h.ncv_alloc = 0; h.scalar = -1; h.have_values = false;
 }
 
@@ -443,6 +445,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     h->d_flag = dalloc<int>(2);
     h->d_refine = dalloc<int>(2);
     h->d_wn2 = dalloc<double>(1024);
+    h->d_wn2b = dalloc<double>(1024);
     h->d_ipart = dalloc<int>(256);
     h->d_rr = dalloc<RrInfo>(1);
     h->d_red = dalloc<double>(2 * 256 + 16);
@@ -539,6 +542,8 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->use_clusters = value != 0.0;
   } else if (nm == "ortho_refine_always") {
     h->ortho_refine_always = value != 0.0;
+  } else if (nm == "fuse_ortho") {
+    h->fuse_ortho = value != 0.0;
   } else if (nm == "use_stream") {
     h->use_stream = value != 0.0;
   } else if (nm == "stream_min_fronts") {
@@ -641,7 +646,7 @@ int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int
 int lsa_set_values(lsa_handle* h, const void* a_vals, int32_t a_scalar, const void* m_vals, int32_t m_scalar,
                    int32_t on_device) {
   if (!h || !h->analyzed || !a_vals) return LSA_ERR_ARG;
-  if (h->has_m && !m_vals) return fail(h, LSA_ERR_ARG, "M values missing");
+  if (h->has_m && !m_vals && !h->have_values) return fail(h, LSA_ERR_ARG, "M values missing");
   if (int rc = need_device(h)) return rc;
   LSA_API_BEGIN
   cudaStream_t st = h->stream;
@@ -656,17 +661,19 @@ int lsa_set_values(lsa_handle* h, const void* a_vals, int32_t a_scalar, const vo
     flag = cplx;
     if (nnz > 0) LSA_CUDA(cudaMemcpyAsync(dst, src, (size_t)nnz * (cplx ? 16 : 8), kind, st));
   };
+  // m_vals == NULL on a handle that already holds values: M is kept (a Reynolds sweep changes A only)
+  const bool new_m = h->has_m && m_vals;
   put(h->d_a_orig, a_vals, h->nnz_a, a_scalar == LSA_C128, h->a_complex);
-  if (h->has_m) put(h->d_m_orig, m_vals, h->nnz_m, m_scalar == LSA_C128, h->m_complex);
+  if (new_m) put(h->d_m_orig, m_vals, h->nnz_m, m_scalar == LSA_C128, h->m_complex);
   refresh_values(*h, h->dA, h->d_a_orig, h->a_complex);
-  if (h->has_m) refresh_values(*h, h->dM, h->d_m_orig, h->m_complex);
+  if (new_m) refresh_values(*h, h->dM, h->d_m_orig, h->m_complex);
   if (h->dAt.rowptr) {
     refresh_values(*h, h->dAt, h->d_a_orig, h->a_complex);
-    if (h->has_m) refresh_values(*h, h->dMt, h->d_m_orig, h->m_complex);
+    if (new_m) refresh_values(*h, h->dMt, h->d_m_orig, h->m_complex);
   }
   value_norms(*h, h->d_a_orig, h->a_complex, h->nnz_a, &h->a_fro, &h->a_max);
   double dummy = 0;
-  if (h->has_m) value_norms(*h, h->d_m_orig, h->m_complex, h->nnz_m, &dummy, &h->m_max);
+  if (new_m) value_norms(*h, h->d_m_orig, h->m_complex, h->nnz_m, &dummy, &h->m_max);
   h->have_values = true;
   h->scalar = -1;  // previous factors are stale
   LSA_CUDA(cudaStreamSynchronize(st));

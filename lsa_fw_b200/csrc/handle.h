@@ -146,6 +146,8 @@ struct lsa_handle_impl {
   int* d_flag = nullptr;
   int* d_refine = nullptr;    // [0] second Gram-Schmidt pass wanted for the current column, [1] how many were
   double* d_wn2 = nullptr;    // partial |w|^2 before orthogonalisation (refinement criterion)
+  double* d_wn2b = nullptr;   // partial |w|^2 after the first pass (fused update + dots kernel)
+  bool fuse_ortho = true;     // pass-1 update fused with the pass-2 dot products
   bool ortho_refine_always = false;
   int* d_ipart = nullptr;  // arg-max partial indices
   RrInfo* d_rr = nullptr;
@@ -176,6 +178,9 @@ struct lsa_handle_impl {
   void* d_inv_scratch = nullptr;        // scratch of the block-inverse merges
   long long inv_scratch_bytes = 0, inv_scratch_entries = 0;
   long long* d_inv_off = nullptr;       // per-front scratch offsets of the current batch
+  z128* d_tri_scratch = nullptr;        // partial sums of the split triangular GEMVs
+  int* d_tri_tickets = nullptr;         // arrival counters of their row chunks (self-resetting)
+  long long tri_slots = 0;
   bool use_graphs = true;
   bool defer_cb = true;          // cluster up sweeps: contribution rows updated by one wide GEMV after the pivot steps
   bool cluster_slices = true;    // levels with <= 9 fronts: 16-CTA clusters sharing every 128-row block by 8-row slices

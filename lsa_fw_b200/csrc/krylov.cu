@@ -222,6 +222,100 @@ __global__ void __launch_bounds__(256) k_dots(int n, int j, int c0, const z128* 
   }
 }
 
+// Fused "update of pass 1 + dots of pass 2" of the two-pass Gram-Schmidt: w <- w - V h over the block's rows and,
+// with the SAME tile of V still in registers, the partial products conj(V)^T w_new of the second pass -- the basis
+// is read three times per column instead of four when the second pass is taken (it is for > 99 % of the columns of
+// the shift-and-invert runs measured here), and the second pass' dot products come for free when it is not.
+// Same thread layout as k_dots (warp = column group, lanes = rows); the row sums of the update cross the eight
+// warps through shared memory, one slab of 32 U rows at a time.  j <= 8 NQ (all columns in one block).
+// part[blk, c] = partial h2[c];  wn2[blk] = partial |w_new|^2 (norm after the first pass).
+template <int NQ, int U>
+__global__ void __launch_bounds__(256) k_update_dots(int n, int j, const z128* __restrict__ V, long long ldv,
+                                                     const z128* __restrict__ h, z128* __restrict__ w,
+                                                     z128* __restrict__ part, int ldp, int rows_per_block,
+                                                     double* __restrict__ wn2) {
+  __shared__ z128 hs[8 * NQ];
+  __shared__ z128 red[DOT_CG][U][33];
+  __shared__ z128 wsh[U][32];
+  const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;
+  if ((int)threadIdx.x < 8 * NQ) hs[threadIdx.x] = (int)threadIdx.x < j ? h[threadIdx.x] : mk(0, 0);
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min((long long)n, r0 + rows_per_block);
+  z128 acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q] = mk(0, 0);
+  double wacc = 0.0;
+  for (long long i0 = r0; i0 < r1; i0 += 32 * U) {
+    z128 v[U][NQ];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long ii = i0 + lane + 32 * u;
+      const bool ok = ii < r1;
+      z128 s = mk(0, 0);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int c = cg + q * DOT_CG;
+        v[u][q] = (ok && c < j) ? V[ii + c * ldv] : mk(0, 0);
+        s += v[u][q] * hs[c];
+      }
+      red[cg][u][lane] = s;
+    }
+    __syncthreads();
+    if (cg < U) {   // warp u finishes slab u: w_new = w - sum over the column groups
+      const long long ii = i0 + lane + 32 * cg;
+      z128 wn = mk(0, 0);
+      if (ii < r1) {
+        z128 s = red[0][cg][lane];
+#pragma unroll
+        for (int g = 1; g < DOT_CG; ++g) s += red[g][cg][lane];
+        wn = w[ii] - s;
+        w[ii] = wn;
+        wacc += abs2(wn);
+      }
+      wsh[cg][lane] = wn;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const z128 wn = wsh[u][lane];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[q] += conj_(v[u][q]) * wn;
+    }
+  }
+  // |w_new|^2 of the block: the U finishing warps each hold a share
+  __shared__ double wred[8];
+  for (int o = 16; o > 0; o >>= 1) wacc += __shfl_xor_sync(0xffffffffu, wacc, o);
+  if (lane == 0) wred[cg] = wacc;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int c = cg + q * DOT_CG;
+    if (c < j) {
+      z128 a = acc[q];
+      for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      }
+      if (lane == 0) part[(long long)blockIdx.x * ldp + c] = a;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sacc = 0.0;
+    for (int g = 0; g < U && g < 8; ++g) sacc += wred[g];
+    wn2[blockIdx.x] = sacc;
+  }
+}
+
+static void launch_update_dots(cudaStream_t st, int nblk, int n, int j, const z128* V, long long ldv, const z128* h, z128* w,
+                               z128* part, int ldp, int rows_per_block, double* wn2) {
+  if (j <= 16) k_update_dots<2, 8><<<nblk, 256, 0, st>>>(n, j, V, ldv, h, w, part, ldp, rows_per_block, wn2);
+  else if (j <= 32) k_update_dots<4, 4><<<nblk, 256, 0, st>>>(n, j, V, ldv, h, w, part, ldp, rows_per_block, wn2);
+  else if (j <= 64) k_update_dots<8, 2><<<nblk, 256, 0, st>>>(n, j, V, ldv, h, w, part, ldp, rows_per_block, wn2);
+  else if (j <= 96) k_update_dots<12, 2><<<nblk, 256, 0, st>>>(n, j, V, ldv, h, w, part, ldp, rows_per_block, wn2);
+  else k_update_dots<16, 1><<<nblk, 256, 0, st>>>(n, j, V, ldv, h, w, part, ldp, rows_per_block, wn2);
+}
+
 // All partial dot products of w against V[:, 0:j]: chunks of up to 128 columns, columns per thread by chunk width.
 static void launch_dots(cudaStream_t st, int nblk, int n, int j, const z128* V, long long ldv, const z128* w, z128* part,
                         int ldp, int rows_per_block, double* wn2, const int* skip) {
@@ -412,8 +506,15 @@ __global__ void __launch_bounds__(256) k_normalize(int n, const z128* __restrict
                                                    const double* __restrict__ npart, int nparts,
                                                    double* __restrict__ beta_out, z128* __restrict__ s_entry,
                                                    const z128* __restrict__ hcol, int hlen, int* __restrict__ flag,
-                                                   int step) {
+                                                   int step, const double* __restrict__ npart_alt = nullptr,
+                                                   int nparts_alt = 0, const int* __restrict__ use_alt_if_zero = nullptr) {
   __shared__ double red[256];
+  // fused Gram-Schmidt: when the second pass was NOT taken (*use_alt_if_zero == 0) the norm is the one measured
+  // after the first pass (npart_alt)
+  if (use_alt_if_zero && *use_alt_if_zero == 0) {
+    npart = npart_alt;
+    nparts = nparts_alt;
+  }
   double s = 0.0;
   for (int b = threadIdx.x; b < nparts; b += blockDim.x) s += npart[b];
   red[threadIdx.x] = s;
@@ -733,14 +834,24 @@ static void orthonormalize(lsa_handle_impl& h, z128* V, long long ldv, int jj, z
   if (!h.partitioned) {
     const int nblk = dots(nullptr, true);
     k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol ? scol : h.d_brow, 0, nullptr);
-    const int nb = update(nullptr, h.d_npart);
-    k_refine_flag<<<1, 256, 0, st>>>(nblk, h.d_wn2, nb, h.d_npart, always, h.d_refine, h.d_refine + 1);
-    dots(h.d_refine, false);
-    k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol ? scol : h.d_brow, 1, h.d_refine);
-    update(h.d_refine, h.d_npart);
-    for (auto& r : h.upd_ranges)   // single range
-      k_normalize<<<cdiv(r.second - r.first, 256), 256, 0, st>>>(r.second - r.first, w + r.first, out + r.first, h.d_npart, nb, nullptr,
-                                                                  scol ? scol + jj : nullptr, scol, scol ? jj : 0, flag, step);
+    const int len = h.upd_ranges[0].second - h.upd_ranges[0].first;
+    if (jj <= 128 && h.fuse_ortho) {
+      // pass-1 update fused with the pass-2 dot products (V read once for both); norm after pass 1 -> d_wn2b
+      launch_update_dots(st, nblk, len, jj, V, ldv, h.d_h, w, h.d_part, ldp, rows_per_block, h.d_wn2b);
+      k_refine_flag<<<1, 256, 0, st>>>(nblk, h.d_wn2, nblk, h.d_wn2b, always, h.d_refine, h.d_refine + 1);
+      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol ? scol : h.d_brow, 1, h.d_refine);
+      const int nb = update(h.d_refine, h.d_npart);
+      k_normalize<<<cdiv(len, 256), 256, 0, st>>>(len, w, out, h.d_npart, nb, nullptr, scol ? scol + jj : nullptr, scol,
+                                                   scol ? jj : 0, flag, step, h.d_wn2b, nblk, h.d_refine);
+    } else {
+      const int nb = update(nullptr, h.d_npart);
+      k_refine_flag<<<1, 256, 0, st>>>(nblk, h.d_wn2, nb, h.d_npart, always, h.d_refine, h.d_refine + 1);
+      dots(h.d_refine, false);
+      k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol ? scol : h.d_brow, 1, h.d_refine);
+      update(h.d_refine, h.d_npart);
+      k_normalize<<<cdiv(len, 256), 256, 0, st>>>(len, w, out, h.d_npart, nb, nullptr, scol ? scol + jj : nullptr, scol,
+                                                   scol ? jj : 0, flag, step);
+    }
   } else {
     double* red = h.d_red;
     double* norm2 = h.d_red + 514;

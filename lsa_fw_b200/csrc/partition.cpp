@@ -73,26 +73,35 @@ void partition(const Symbolic& g, int rank, int world, Symbolic& loc, Partition&
     return tw + (w.empty() ? 0.0 : lpt_makespan(w, world));
   };
   if (world > 1) {
-    while (true) {
-      int hi = -1;
-      for (int i = 0; i < (int)subs.size(); ++i)
-        if (g.fronts[subs[i]].nchild > 0 && (hi < 0 || sw[subs[i]] > sw[subs[hi]])) hi = i;
-      if (hi < 0) break;
-      // only the overall heaviest sub-tree is worth opening; if it is a leaf front, stop
-      int heaviest = 0;
-      for (int i = 1; i < (int)subs.size(); ++i)
-        if (sw[subs[i]] > sw[subs[heaviest]]) heaviest = i;
-      if (heaviest != hi) break;
-      const int s = subs[hi];
-      std::vector<int> next(subs);
-      next.erase(next.begin() + hi);
-      for (int c = 0; c < g.fronts[s].nchild; ++c) next.push_back(g.child_idx[g.fronts[s].child0 + c]);
-      const double before = model(subs, top_w), after = model(next, top_w + fw[s]);
-      if ((int)subs.size() >= world && !(after < before)) break;
-      if ((int)next.size() > 64 * world) break;
+    // Open the heaviest sub-tree again and again (its root joins the replicated top) and remember the modelled
+    // time after every step; keep the prefix of openings with the smallest one.  (One step alone rarely pays: the
+    // sibling of the opened sub-tree still bounds the makespan until it is opened too.)  A GPU may end up without a
+    // sub-tree: with a replicated top, one more level of a 3-D tree can cost every GPU more than it returns.
+    std::vector<int> cur(subs), opened;
+    double tw = 0.0, best = model(cur, 0.0);
+    size_t best_steps = 0;
+    while ((int)cur.size() <= 64 * world) {
+      int hi = 0;
+      for (int i = 1; i < (int)cur.size(); ++i)
+        if (sw[cur[i]] > sw[cur[hi]]) hi = i;
+      const int s = cur[hi];
+      if (g.fronts[s].nchild == 0) break;   // the heaviest sub-tree is a single front
+      cur.erase(cur.begin() + hi);
+      for (int c = 0; c < g.fronts[s].nchild; ++c) cur.push_back(g.child_idx[g.fronts[s].child0 + c]);
+      tw += fw[s];
+      opened.push_back(s);
+      const double t = model(cur, tw);
+      if (t < best) {
+        best = t;
+        best_steps = opened.size();
+      }
+    }
+    for (size_t q = 0; q < best_steps; ++q) {
+      const int s = opened[q];
       is_top[s] = 1;
       top_w += fw[s];
-      subs.swap(next);
+      subs.erase(std::find(subs.begin(), subs.end(), s));
+      for (int c = 0; c < g.fronts[s].nchild; ++c) subs.push_back(g.child_idx[g.fronts[s].child0 + c]);
     }
   }
   std::sort(subs.begin(), subs.end());

@@ -266,6 +266,37 @@ __global__ void __launch_bounds__(NT) k_up_gather(const Front* __restrict__ fron
   for (int i = threadIdx.x; i < p.k; i += NT) y[p.col0 + i] = x[PERM ? gperm[p.col0 + i] : p.col0 + i];
 }
 
+// Same job for the wide levels near the leaves (tens of thousands of fronts with a few dozen rows each): one WARP
+// per front, eight fronts per CTA, warp barriers only.  With one 256-thread CTA per front those levels ran at
+// < 1 TB/s (a CTA's worth of barriers and scheduling for ~100 useful entries).
+template <bool PERM>
+__global__ void __launch_bounds__(256) k_up_gather_warp(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                        int first, int cnt, const int* __restrict__ child_idx,
+                                                        const int* __restrict__ ea_map, const int* __restrict__ gperm,
+                                                        z128* __restrict__ x, z128* __restrict__ y, z128* __restrict__ cb) {
+  const int lane = threadIdx.x & 31;
+  const int fi = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (fi >= cnt) return;
+  const Front p = fronts[lvl_front[first + fi]];
+  z128* cbp = cb + p.st0;
+  for (int t = lane; t < p.r; t += 32) cbp[t] = mk(0, 0);
+  __syncwarp();
+  for (int q = 0; q < p.nchild; ++q) {
+    const Front c = fronts[child_idx[p.child0 + q]];
+    if (c.flags != FRONT_REGULAR) continue;
+    const int* map = ea_map + c.st0;
+    const z128* cbc = cb + c.st0;
+    for (int t = lane; t < c.r; t += 32) {
+      const int ip = map[t];
+      const z128 v = cbc[t];
+      if (ip < p.k) x[p.col0 + ip] += v;
+      else cbp[ip - p.k] += v;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < p.k; i += 32) y[p.col0 + i] = x[PERM ? gperm[p.col0 + i] : p.col0 + i];
+}
+
 // --------------------------------------------------------------------------------------- down sweep
 
 // y_top -= Off * anc[ancestor rows].  N: Off = U12 = Q (k x r);  H: Off = L21^H, L21 = P[k:m, 0:k].
@@ -427,6 +458,11 @@ __global__ void __launch_bounds__(NW * 32) k_up_off(const Front* __restrict__ fr
   }
 }
 
+__device__ __forceinline__ z128 ld_cg(const z128* p) {  // L2 read (data written by a peer CTA of the cluster)
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return mk(v.x, v.y);
+}
+
 // --------------------------------------------------------------- whole pivot block inverted: one GEMV
 //
 // Fronts whose pivot block D = P[0:k, 0:k] was inverted as a whole after the factorisation (post_factor: L11^-1
@@ -436,10 +472,14 @@ __global__ void __launch_bounds__(NW * 32) k_up_off(const Front* __restrict__ fr
 //   down,N  z_i =       sum_{c>=i} D[i,c] y_c            down,H  z_i = y_i + sum_{c>i} conj(D[c,i]) y_c
 // N reduces along rows (thread = row, warps = column groups, partial sums through shared memory), H along columns
 // (warp = 32 / NW output entries, lanes along the contiguous column).  grid: (chunks of 32 pivots, fronts).
+// Levels with very few fronts (the root: k / 32 = 46 CTAs on 148 SMs) split every row chunk's input range over
+// gridDim.z CTAs: each writes its partial sums to a scratch slot, the LAST one to arrive (atomic ticket) adds the
+// partials in split order -- deterministic -- and finishes the outputs; the ticket resets itself.
 template <class T, bool H, bool UP, int NW>
 __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                    int first, const T* __restrict__ fac, const z128* __restrict__ in,
-                                                   z128* __restrict__ out) {
+                                                   z128* __restrict__ out, z128* __restrict__ scratch,
+                                                   int* __restrict__ tickets) {
   constexpr int ROWS = 32;
   constexpr int CHUNK = NW * 32;
   const Front f = fronts[lvl_front[first + blockIdx.y]];
@@ -450,14 +490,21 @@ __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ 
   const T* P = fac + f.p_off;
   __shared__ z128 xs[CHUNK];
   __shared__ z128 red[NW][ROWS + 1];
+  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int rowN = r0 + lane;
   z128 acc = mk(0, 0);
   z128 accH[ROWS / NW];
 #pragma unroll
   for (int q = 0; q < ROWS / NW; ++q) accH[q] = mk(0, 0);
-  // index range of the input entries this CTA's outputs depend on
-  const int c_lo = UP ? 0 : r0, c_hi = UP ? min(k, r0 + ROWS) : k;
+  // index range of the input entries this CTA's outputs depend on, and this split's share of it
+  int c_lo = UP ? 0 : r0, c_hi = UP ? min(k, r0 + ROWS) : k;
+  const int nsplit = gridDim.z;
+  if (nsplit > 1) {
+    const int span = ((c_hi - c_lo + nsplit - 1) / nsplit + CHUNK - 1) / CHUNK * CHUNK;
+    c_lo = c_lo + (int)blockIdx.z * span;
+    c_hi = min(c_hi, c_lo + span);
+  }
   for (int c0 = c_lo; c0 < c_hi; c0 += CHUNK) {
     const int len = min(CHUNK, c_hi - c0);
     __syncthreads();
@@ -487,15 +534,15 @@ __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ 
       }
     }
   }
+  // ---- the CTA's 32 partial results -> red[0][0..31]
   if (!H) {
     red[wid][lane] = acc;
     __syncthreads();
-    if (tid < ROWS && r0 + tid < k) {
+    if (tid < ROWS) {
       z128 sum = red[0][tid];
 #pragma unroll 8
       for (int q = 1; q < NW; ++q) sum += red[q][tid];
-      if (UP) sum += in[f.col0 + r0 + tid];   // unit diagonal of L11^-1
-      out[f.col0 + r0 + tid] = sum;
+      red[0][tid] = sum;
     }
   } else {
 #pragma unroll
@@ -505,9 +552,34 @@ __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ 
         a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
         a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
       }
-      const int i = r0 + wid + q * NW;
-      if (lane == 0 && i < k) out[f.col0 + i] = UP ? a : a + in[f.col0 + i];   // unit diagonal of L11^-H
+      if (lane == 0) red[0][wid + q * NW] = a;
     }
+  }
+  __syncthreads();
+  z128 sum = tid < ROWS ? red[0][tid] : mk(0, 0);
+  if (nsplit > 1) {
+    const long long slot = ((long long)blockIdx.y * gridDim.x + blockIdx.x);
+    z128* mine = scratch + (slot * nsplit + blockIdx.z) * ROWS;
+    if (tid < ROWS) mine[tid] = sum;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int t = atomicAdd(tickets + slot, 1);
+      s_last = t == nsplit - 1;
+      if (s_last) tickets[slot] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < ROWS) {
+      sum = mk(0, 0);
+      for (int z = 0; z < nsplit; ++z) sum += ld_cg(scratch + (slot * nsplit + z) * ROWS + tid);
+    }
+  }
+  if (tid < ROWS && r0 + tid < k) {
+    // unit diagonals: L11^-1 (up, N) and L11^-H (down, H)
+    if (UP != H) sum += in[f.col0 + r0 + tid];
+    out[f.col0 + r0 + tid] = sum;
   }
 }
 
@@ -646,10 +718,6 @@ __global__ void __launch_bounds__(NT) k_step(const Front* __restrict__ fronts, c
   }
 }
 
-__device__ __forceinline__ z128 ld_cg(const z128* p) {  // L2 read (data written by a peer CTA of the cluster)
-  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-  return mk(v.x, v.y);
-}
 
 // ---------------------------------------------------------------------- cluster sweep (big fronts)
 //
@@ -1765,6 +1833,25 @@ void exchange_replicated_rows(lsa_handle_impl& h, z128* x, bool with_cut_contrib
   LSA_LAUNCH_CHECK();
 }
 
+// splits of a chunk's triangular GEMV: enough CTAs for two waves over the SMs, at most 8 per row chunk
+static int tri_splits(const lsa_handle_impl& h, const SolveChunk& c) {
+  const long long ctas = (long long)cdiv(c.maxk, 32) * c.cnt;
+  if (c.maxk <= 512 || ctas >= 2LL * h.num_sms) return 1;
+  return (int)std::min<long long>(8, std::max<long long>(1, (2LL * h.num_sms + ctas - 1) / ctas));
+}
+
+template <class T, bool H, bool UP>
+static void launch_tri_gemv(lsa_handle_impl& h, cudaStream_t st, const SolveChunk& c, const int* d_lvl_front, const T* fac,
+                            const z128* in, z128* out) {
+  const int ns = tri_splits(h, c);
+  const dim3 grid(cdiv(c.maxk, 32), c.cnt, ns);
+  if (ns > 1 || c.maxk <= 512)
+    k_tri_gemv<T, H, UP, 8><<<grid, 256, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, in, out, h.d_tri_scratch, h.d_tri_tickets);
+  else
+    k_tri_gemv<T, H, UP, 32><<<grid, 1024, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, in, out, h.d_tri_scratch, h.d_tri_tickets);
+  LSA_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------------------------------- driver
 
 // Level plan of the sweeps (host, once per factorisation): chunks of <= 32768 fronts of one level, each with the
@@ -1817,6 +1904,20 @@ void plan_solve(lsa_handle_impl& h, int scalar) {
   }
   h.inv_scratch_entries = scratch;
   if (!h.d_inv_off) LSA_CUDA(cudaMalloc(&h.d_inv_off, sizeof(long long) * YMAX));
+  // scratch + tickets of the split triangular GEMVs (tri_splits)
+  long long slots = 0;
+  for (const SolveChunk& c : h.solve_plan)
+    if (c.mode == SOLVE_INVERTED && tri_splits(h, c) > 1) slots = std::max(slots, (long long)cdiv(c.maxk, 32) * c.cnt);
+  if (slots > h.tri_slots) {
+    if (h.d_tri_scratch) cudaFree(h.d_tri_scratch);
+    if (h.d_tri_tickets) cudaFree(h.d_tri_tickets);
+    h.d_tri_scratch = nullptr;
+    h.d_tri_tickets = nullptr;
+    LSA_CUDA(cudaMalloc(&h.d_tri_scratch, sizeof(z128) * (size_t)slots * 8 * 32));
+    LSA_CUDA(cudaMalloc(&h.d_tri_tickets, sizeof(int) * (size_t)slots));
+    LSA_CUDA(cudaMemsetAsync(h.d_tri_tickets, 0, sizeof(int) * (size_t)slots, h.stream));
+    h.tri_slots = slots;
+  }
 }
 
 template <class T, bool H>
@@ -1855,6 +1956,8 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     const int d = c.level, cnt = c.cnt, first = c.first, maxk = c.maxk, max_r = c.max_r, max_m = c.max_m;
     if (cnt <= 2 * h.num_sms)
       k_up_gather<!H, 1024><<<cnt, 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+    else if (max_m <= 512 && cnt >= 16 * h.num_sms)
+      k_up_gather_warp<!H><<<cdiv(cnt, 8), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, cnt, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
     else
       k_up_gather<!H, 256><<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
     LSA_LAUNCH_CHECK();
@@ -1870,9 +1973,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       }
     }
     if (c.mode == SOLVE_INVERTED) {
-      if (maxk > 512) k_tri_gemv<T, H, true, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, y, z);
-      else k_tri_gemv<T, H, true, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, y, z);
-      LSA_LAUNCH_CHECK();
+      launch_tri_gemv<T, H, true>(h, st, c, d_lvl_front, fac, y, z);
       tr.mark("up_tri", d, 0, cdiv(maxk, 32), cnt);
       launches++;
       up_off(c);
@@ -1944,9 +2045,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     }
     if (streamed) {
     } else if (c.mode == SOLVE_INVERTED) {
-      if (maxk > 512) k_tri_gemv<T, H, false, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, y);
-      else k_tri_gemv<T, H, false, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, fac, z, y);
-      LSA_LAUNCH_CHECK();
+      launch_tri_gemv<T, H, false>(h, st, c, d_lvl_front, fac, z, y);
       tr.mark("down_tri", d, 0, cdiv(maxk, 32), cnt);
       launches++;
     } else if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {

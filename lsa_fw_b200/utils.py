@@ -570,8 +570,12 @@ class iEpsSolver:  # noqa: N801
             dv = self._opts["device_values"]
             if dv is not None:
                 h.set_values_device(dv[0], None if M is None else dv[1])
+            elif M is not None and self._M is not None and _same_values(h.m_token, M):
+                h.set_values(A.data, None)          # M unchanged since the last upload to this handle: A only
+                stats["m_upload_skipped"] = True
             else:
                 h.set_values(A.data, None if M is None else M.data)
+                h.m_token = _values_token(M) if (M is not None and self._M is not None) else None
             stats["upload_seconds"] = time.perf_counter() - t0
             sigma_fact = sigma
             if needs_factor:

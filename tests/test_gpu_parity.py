@@ -281,19 +281,24 @@ def test_gram_schmidt_refinement_if_needed_matches_always():
     h.set_values(pc.A.data, pc.M.data)
     h.factor(1.0, -sigma, _lib.LSA_C128, 1e-13)
     out = {}
-    for always in (1, 0):
-        h.set_option("ortho_refine_always", always)
-        r = h.eigs(nev=6, ncv=40, tol=1e-11, max_restarts=100, which="TARGET_MAGNITUDE", transform=_lib.LSA_ST_SINVERT,
-                   sigma=sigma, seed=1)
-        assert r.nconv >= 6
-        X = h.eigenvectors(6)
-        out[always] = (r, h.eigenvalues(6), h.residuals(6), X)
-    ra, la, resa, _ = out[1]
-    ri, li, resi, Xi = out[0]
-    assert ra.n_reorth > 0 and ri.n_reorth < ra.n_reorth
-    assert np.abs(li - la).max() < EIG_RTOL * np.abs(la).max()
-    assert resi.max() < RESID_BAR and resa.max() < RESID_BAR
-    assert np.linalg.norm(Xi, axis=0) == pytest.approx(1.0, abs=1e-12)
+    for fuse in (1, 0):         # fused "update of pass 1 + dots of pass 2" kernel and the separate kernels
+        h.set_option("fuse_ortho", fuse)
+        for always in (1, 0):
+            h.set_option("ortho_refine_always", always)
+            r = h.eigs(nev=6, ncv=40, tol=1e-11, max_restarts=100, which="TARGET_MAGNITUDE", transform=_lib.LSA_ST_SINVERT,
+                       sigma=sigma, seed=1)
+            assert r.nconv >= 6
+            X = h.eigenvectors(6)
+            out[fuse, always] = (r, h.eigenvalues(6), h.residuals(6), X)
+        ra, la, resa, _ = out[fuse, 1]
+        ri, li, resi, Xi = out[fuse, 0]
+        assert ra.n_reorth > 0 and ri.n_reorth < ra.n_reorth
+        assert np.abs(li - la).max() < EIG_RTOL * np.abs(la).max()
+        assert resi.max() < RESID_BAR and resa.max() < RESID_BAR
+        assert np.linalg.norm(Xi, axis=0) == pytest.approx(1.0, abs=1e-12)
+    # both kernel organisations compute the same thing
+    assert out[1, 0][0].n_reorth == out[0, 0][0].n_reorth and out[1, 0][0].n_op_applies == out[0, 0][0].n_op_applies
+    assert np.abs(out[1, 0][1] - out[0, 0][1]).max() < 1e-12 * np.abs(out[0, 0][1]).max()
     h.close()
 
 
