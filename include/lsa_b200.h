@@ -237,6 +237,11 @@ int lsa_get_eigenvectors(const lsa_handle* h, double* out_c128, int64_t ld, int3
 int lsa_get_residuals(lsa_handle* h, double* out, int32_t capacity);
 int lsa_get_counters(const lsa_handle* h, lsa_counters* out);
 int lsa_sync(lsa_handle* h);
+/* Host helper (no GPU): out[q] = 1 when the diagonal entry of row rows[q] (rows == NULL: row q, nrows = n) of a CSR
+ * matrix with SORTED column indices is absent or zero -- the structurally-zero-diagonal (pressure) flags that
+ * lsa_analyze takes as `order_last`, without a pass over all nnz entries per solve of a sweep. */
+int lsa_host_diag_is_zero(int32_t n, const void* indptr, int32_t indptr_is_64, const int32_t* colidx, const void* vals,
+                          int32_t scalar, const int32_t* rows, int32_t nrows, uint8_t* out);
 /* Page-locked host memory for result buffers (eigenvectors leave the device at PCIe speed instead of through
  * the driver's bounce buffers; VecGetArray of the reference hands out host memory as well, Solver/utils.py:280-297).
  * Plain cudaHostAlloc / cudaFreeHost; no handle needed. */

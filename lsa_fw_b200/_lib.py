@@ -199,6 +199,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lsa_get_residuals.argtypes = [vp, vp, i32]
     lib.lsa_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.lsa_sync.argtypes = [vp]
+    lib.lsa_host_diag_is_zero.argtypes = [i32, vp, i32, vp, vp, i32, vp, i32, vp]
     lib.lsa_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
     lib.lsa_host_free.argtypes = [C.c_void_p]
     lib.lsa_dense_schur.argtypes = [vp, i32, vp, i32, vp, i32, i32, dbl, dbl]
@@ -212,7 +213,7 @@ EXPORTS = [
     "lsa_symbolic_array", "lsa_set_values", "lsa_factor", "lsa_solve", "lsa_spmv", "lsa_eigs",
     "lsa_get_eigenvalues", "lsa_get_eigenvectors", "lsa_get_residuals", "lsa_get_counters", "lsa_sync",
     "lsa_host_alloc", "lsa_host_free", "lsa_dense_schur", "lsa_gemm_bench",
-    "lsa_bilinear", "lsa_set_partition", "lsa_nccl_load", "lsa_nccl_unique_id", "lsa_set_comm", "lsa_partition_info_get",
+    "lsa_bilinear", "lsa_host_diag_is_zero", "lsa_set_partition", "lsa_nccl_load", "lsa_nccl_unique_id", "lsa_set_comm", "lsa_partition_info_get",
 ]
 
 _ARRAY_DTYPES = {
@@ -255,6 +256,31 @@ def device_pointer(obj):
         torch.cuda.current_stream(t.device).synchronize()   # the library reads on its own stream
         return int(t.data_ptr()), (LSA_C128 if t.dtype == torch.complex128 else LSA_F64), int(t.numel()), t
     raise TypeError("cannot take a device pointer from %r" % type(obj))
+
+
+def diag_is_zero(mat, rows: np.ndarray | None = None) -> np.ndarray:
+    """Flags of the rows (all rows when `rows` is None) of a SciPy CSR matrix with sorted indices whose diagonal entry
+    is absent or zero (host helper of the library, OpenMP; falls back to nothing: the library is always present)."""
+    lib = load()
+    n = mat.shape[0]
+    indptr = mat.indptr
+    if indptr.dtype not in (np.int32, np.int64):
+        indptr = indptr.astype(np.int64)
+    indptr = np.ascontiguousarray(indptr)
+    colidx = np.ascontiguousarray(mat.indices, dtype=np.int32)
+    vals = np.ascontiguousarray(mat.data)
+    sc = LSA_C128 if np.iscomplexobj(vals) else LSA_F64
+    vals = vals.astype(np.complex128 if sc else np.float64, copy=False)
+    rp, cnt = None, n
+    if rows is not None:
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        rp, cnt = rows.ctypes.data, len(rows)
+    out = np.empty(cnt, dtype=np.uint8)
+    rc = lib.lsa_host_diag_is_zero(n, indptr.ctypes.data, int(indptr.dtype == np.int64), colidx.ctypes.data, vals.ctypes.data, sc,
+                                   rp, cnt, out.ctypes.data)
+    if rc != LSA_OK:
+        raise LsaError(rc, "lsa_host_diag_is_zero failed")
+    return out
 
 
 def nccl_unique_id() -> bytes:

@@ -975,6 +975,28 @@ int lsa_get_counters(const lsa_handle* h, lsa_counters* out) {
   return LSA_OK;
 }
 
+int lsa_host_diag_is_zero(int32_t n, const void* indptr, int32_t indptr_is_64, const int32_t* colidx, const void* vals,
+                          int32_t scalar, const int32_t* rows, int32_t nrows, uint8_t* out) {
+  if (!indptr || !colidx || !vals || !out || n < 0 || nrows < 0) return LSA_ERR_ARG;
+  const int32_t* p32 = (const int32_t*)indptr;
+  const int64_t* p64 = (const int64_t*)indptr;
+  const int cnt = rows ? nrows : n;
+#pragma omp parallel for schedule(static)
+  for (int q = 0; q < cnt; ++q) {
+    const int i = rows ? rows[q] : q;
+    const long long b = indptr_is_64 ? p64[i] : p32[i], e = indptr_is_64 ? p64[i + 1] : p32[i + 1];
+    const int32_t* lo = std::lower_bound(colidx + b, colidx + e, i);
+    uint8_t zero = 1;
+    if (lo != colidx + e && *lo == i) {
+      const long long pos = lo - colidx;
+      if (scalar == LSA_C128) zero = ((const double*)vals)[2 * pos] == 0.0 && ((const double*)vals)[2 * pos + 1] == 0.0;
+      else zero = ((const double*)vals)[pos] == 0.0;
+    }
+    out[q] = zero;
+  }
+  return LSA_OK;
+}
+
 int lsa_host_alloc(uint64_t bytes, void** ptr) {
   if (!ptr || bytes == 0) return LSA_ERR_ARG;
   *ptr = nullptr;

@@ -25,7 +25,7 @@ import scipy.sparse as sp
 
 from . import _lib
 from .carriers import iPETScMatrix, iPETScVector
-from .utils import PreconditionerType, _SYM_CACHE, _SYM_CACHE_MAX, _as_csr, _pattern_key
+from .utils import PreconditionerType, _SYM_CACHE, _as_csr, _raw_csr
 
 logger = logging.getLogger(__name__)
 
@@ -129,25 +129,24 @@ class iKSP:  # noqa: N801
             raise NotImplementedError(f"preconditioner '{self._pc}' is not built on the B200 backend (direct LU only)")
         if self._type in (KSPType.CHEBYSHEV, KSPType.QCG):
             raise NotImplementedError(f"KSP type '{self._type}' is not built on the B200 backend")
-        A = _as_csr(self._A)
+        t0 = time.perf_counter()
+        coords = self._opts["coords"]
+        extra = ("linear", self._opts["leaf_size"], self._opts["device"],
+                 None if coords is None else np.ascontiguousarray(coords).tobytes()[:64])
+        A = _raw_csr(self._A)
+        h = _SYM_CACHE.lookup(A, None, extra) if A is not None and len(_SYM_CACHE) else None
+        if h is None:
+            A = _as_csr(self._A)
+            h = _SYM_CACHE.lookup(A, None, extra)
         n = A.shape[0]
         if A.shape[0] != A.shape[1]:
             raise ValueError("Matrix must be square.")
         cplx = np.iscomplexobj(A.data)
-        coords = self._opts["coords"]
-        key = _pattern_key(A, None, ("linear", self._opts["leaf_size"], self._opts["device"],
-                                     None if coords is None else np.ascontiguousarray(coords).tobytes()[:64]))
-        h = _SYM_CACHE.get(key)
-        if h is not None and h.closed:
-            h = None
-        t0 = time.perf_counter()
         if h is None:
             h = _lib.Handle(n, self._opts["device"])
             h.analyze(A.indptr, A.indices, None, None, leaf_size=self._opts["leaf_size"], coords=coords,
                       order_last=(A.diagonal() == 0).astype(np.uint8), nthreads=self._opts["nthreads"])
-            while len(_SYM_CACHE) >= _SYM_CACHE_MAX:
-                _SYM_CACHE.pop(next(iter(_SYM_CACHE)))
-            _SYM_CACHE[key] = h
+            _SYM_CACHE.store(A, None, extra, h)
             self.stats["symbolic_cached"] = False
         else:
             self.stats["symbolic_cached"] = True

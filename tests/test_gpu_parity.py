@@ -298,7 +298,7 @@ def test_gram_schmidt_refinement_if_needed_matches_always():
         assert np.linalg.norm(Xi, axis=0) == pytest.approx(1.0, abs=1e-12)
     # both kernel organisations compute the same thing
     assert out[1, 0][0].n_reorth == out[0, 0][0].n_reorth and out[1, 0][0].n_op_applies == out[0, 0][0].n_op_applies
-    assert np.abs(out[1, 0][1] - out[0, 0][1]).max() < 1e-12 * np.abs(out[0, 0][1]).max()
+    assert np.abs(out[1, 0][1] - out[0, 0][1]).max() < EIG_RTOL * np.abs(out[0, 0][1]).max()
     h.close()
 
 
