@@ -218,6 +218,14 @@ int lsa_solve(lsa_handle* h, int32_t trans, const double* b, double* x, int32_t 
 /* lsa_spmv <- MatMult / MatMultHermitianTranspose with A or M    (Solver/eigen2.py:174, :52-53). */
 int lsa_spmv(lsa_handle* h, int32_t which_matrix, int32_t trans, const double* x, double* y, int32_t on_device);
 
+/* lsa_set_nullspace <- MatSetNullSpace on the operator (FEM/utils.py:604-607, FEM/operators.py:534-545: the
+ * constant-pressure vector of an enclosed flow).  `count` ORTHONORMAL vectors (n complex numbers each, original
+ * ordering, column after column; count = 0 detaches).  The shifted operator is then singular: the factorisation
+ * replaces the vanishing pivot (tiny_pivot > 0), every operator application removes the nullspace component from the
+ * right-hand side before the sweeps and from the solution after them (KSP's behaviour with an attached nullspace;
+ * explicit in Solver/eigen2.py:171-176), and lsa_solve does the same.                                          */
+int lsa_set_nullspace(lsa_handle* h, int32_t count, const double* vecs_c128);
+
 /* lsa_bilinear <- the scalar contractions of the sensitivity analysis, a^H B v with B on the sparsity pattern of A
  * (or M) and caller-supplied values in the ORIGINAL CSR entry order: bi-orthonormalisation a^H M v
  * (Sensitivity/__init__.py:280-287) and d lambda = a^H (dA/dRe) v with a pre-assembled derivative operator in place

@@ -194,6 +194,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lsa_spmv.argtypes = [vp, i32, i32, vp, vp, i32]
     lib.lsa_eigs.argtypes = [vp, C.POINTER(EigsParams), C.POINTER(EigsResult)]
     lib.lsa_bilinear.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp]
+    lib.lsa_set_nullspace.argtypes = [vp, i32, vp]
     lib.lsa_get_eigenvalues.argtypes = [vp, vp, i32]
     lib.lsa_get_eigenvectors.argtypes = [vp, vp, i64, i32, i32]
     lib.lsa_get_residuals.argtypes = [vp, vp, i32]
@@ -213,7 +214,7 @@ EXPORTS = [
     "lsa_symbolic_array", "lsa_set_values", "lsa_factor", "lsa_solve", "lsa_spmv", "lsa_eigs",
     "lsa_get_eigenvalues", "lsa_get_eigenvectors", "lsa_get_residuals", "lsa_get_counters", "lsa_sync",
     "lsa_host_alloc", "lsa_host_free", "lsa_dense_schur", "lsa_gemm_bench",
-    "lsa_bilinear", "lsa_host_diag_is_zero", "lsa_set_partition", "lsa_nccl_load", "lsa_nccl_unique_id", "lsa_set_comm", "lsa_partition_info_get",
+    "lsa_bilinear", "lsa_set_nullspace", "lsa_host_diag_is_zero", "lsa_set_partition", "lsa_nccl_load", "lsa_nccl_unique_id", "lsa_set_comm", "lsa_partition_info_get",
 ]
 
 _ARRAY_DTYPES = {
@@ -306,6 +307,7 @@ class Handle:
         # generations of the numeric state: solvers that share a handle (symbolic cache, adjoint reuse) check
         # them before they trust factors / device-side results they did not just produce themselves
         self.m_token = None   # identity + content probe of the M values resident on the device
+        self.ns_count = 0     # attached nullspace vectors
         self.gen_factor = 0   # bumped by set_values and factor
         self.gen_result = 0   # bumped by eigs (and by everything that bumps gen_factor)
         rc = self.lib.lsa_create(self.n, device, C.byref(self._h))
@@ -461,6 +463,16 @@ class Handle:
         y = np.empty_like(x)
         self.check(self.lib.lsa_spmv(self._h, which, trans, x.ctypes.data, y.ctypes.data, 0))
         return y
+
+    def set_nullspace(self, vectors: np.ndarray | None) -> None:
+        """Attach (n x count array of ORTHONORMAL columns) or detach (None) the nullspace of the shifted operator."""
+        if vectors is None or np.size(vectors) == 0:
+            self.check(self.lib.lsa_set_nullspace(self._h, 0, None))
+            self.ns_count = 0
+            return
+        V = np.ascontiguousarray(np.asarray(vectors, dtype=np.complex128).reshape(self.n, -1).T)   # one vector per row
+        self.check(self.lib.lsa_set_nullspace(self._h, V.shape[0], V.ctypes.data))
+        self.ns_count = V.shape[0]
 
     def bilinear(self, which: int, vals: np.ndarray, a: np.ndarray, v: np.ndarray) -> complex:
         """a^H B v on the device, B = the pattern of A (or M) with `vals` in the caller's CSR entry order."""

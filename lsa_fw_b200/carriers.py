@@ -228,6 +228,7 @@ class iPETScMatrix:  # noqa: N801
             mat = mat._m
         self._m = sp.csr_matrix(mat)
         self._adjoint_of: "iPETScMatrix | None" = None
+        self._nullspace: "iPETScNullSpace | None" = None
 
     # -- constructors
     @classmethod
@@ -281,6 +282,7 @@ class iPETScMatrix:  # noqa: N801
         adjoint problem (`Sensitivity/__init__.py:246-262`) on the factors of the direct one."""
         out = iPETScMatrix(self._m.conj().T.tocsr())
         out._adjoint_of = self
+        out._nullspace = self._nullspace
         return out
 
     def is_numerically_symmetric(self, tol: float = 1e-6) -> bool:
@@ -335,6 +337,14 @@ class iPETScMatrix:  # noqa: N801
         D = sp.diags(keep)
         self._m = (D @ self._m @ D + sp.csr_matrix((np.full(len(rows), diag), (rows, rows)), shape=self._m.shape)).tocsr()
 
+    def attach_nullspace(self, nullspace: "iPETScNullSpace") -> None:
+        """Attach a nullspace (`FEM/utils.py:604-607`); the eigensolver then projects it out of every operator
+        application instead of requiring a pinned DOF."""
+        self._nullspace = nullspace
+
+    def get_nullspace(self) -> "iPETScNullSpace | None":
+        return self._nullspace
+
     def pin_dof(self, index: int) -> None:
         """Zero row and column `index`, unit diagonal (`FEM/utils.py:596-602`)."""
         self.zero_row_columns([index], diag=1.0)
@@ -365,3 +375,59 @@ class iPETScMatrix:  # noqa: N801
 
     def __str__(self) -> str:
         return f"iPETScMatrix(shape={self.shape}, nnz={self.nonzero_entries})"
+
+
+class iPETScNullSpace:  # noqa: N801
+    """Nullspace carrier (reference `FEM/utils.py:1247-1380`): a list of basis vectors, orthonormalised on creation."""
+
+    def __init__(self, vectors: list, constant: bool = False, size: int | None = None) -> None:
+        cols = [np.asarray(v.raw.getArray() if hasattr(v, "raw") else v) for v in vectors]
+        if constant:
+            if size is None and not cols:
+                raise ValueError("a constant nullspace needs a size")
+            cols.insert(0, np.ones(size if size is not None else len(cols[0])))
+        if not cols:
+            raise ValueError("Cannot create NullSpace from empty vector list")
+        B = np.stack([np.asarray(c, dtype=np.complex128) for c in cols], axis=1)
+        Q, R = np.linalg.qr(B)
+        if np.min(np.abs(np.diag(R))) < 1e-12 * max(1.0, np.max(np.abs(np.diag(R)))):
+            raise ValueError("nullspace basis vectors are linearly dependent")
+        self._Q = Q
+        self._constant = constant
+
+    @classmethod
+    def from_vectors(cls, vectors: list) -> "iPETScNullSpace":
+        return cls(list(vectors))
+
+    @classmethod
+    def create_constant(cls, size: int, comm=None) -> "iPETScNullSpace":
+        return cls([], constant=True, size=size)
+
+    @property
+    def dimension(self) -> int:
+        return self._Q.shape[1]
+
+    @property
+    def basis(self) -> list[iPETScVector]:
+        return [iPETScVector.from_array(self._Q[:, i].copy()) for i in range(self._Q.shape[1])]
+
+    def has_constant(self) -> bool:
+        return self._constant
+
+    def as_array(self) -> np.ndarray:
+        """(n, dimension) orthonormal basis."""
+        return self._Q
+
+    def test_matrix(self, mat: iPETScMatrix, tol: float = 1e-12) -> tuple[bool, float]:
+        nrm = float(np.max(np.linalg.norm(mat.as_scipy_array() @ self._Q, axis=0)))
+        return nrm < tol, nrm
+
+    def remove(self, vec: iPETScVector) -> None:
+        a = vec.raw.getArray()
+        a[...] = a - (self._Q @ (self._Q.conj().T @ a)).astype(a.dtype if np.iscomplexobj(a) else np.float64)
+
+    def attach_to(self, mat: iPETScMatrix) -> None:
+        mat.attach_nullspace(self)
+
+    def detach_from(self, mat: iPETScMatrix) -> None:
+        mat._nullspace = None

@@ -69,7 +69,8 @@ void free_device(lsa_handle_impl& h) {
   }
   dfree(h.d_x); dfree(h.d_w); dfree(h.d_t); dfree(h.d_t2); dfree(h.d_cb); dfree(h.d_io); dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q);
   dfree(h.d_part); dfree(h.d_npart); dfree(h.d_h); dfree(h.d_brow); dfree(h.d_ywork); dfree(h.d_r1); dfree(h.d_r2);
-  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_flag); dfree(h.d_refine); dfree(h.d_wn2); dfree(h.d_wn2b); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
+  dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_ns); dfree(h.d_flag); dfree(h.d_refine); dfree(h.d_wn2); dfree(h.d_wn2b); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
+  h.ns_count = 0;
   h.V_cols = 0; h.X_cols = 0; h.ncv_alloc = 0; h.scalar = -1; h.have_values = false;
 }
 
@@ -843,6 +844,27 @@ int lsa_spmv(lsa_handle* h, int32_t which_matrix, int32_t trans, const double* x
   }
   LSA_CUDA(cudaStreamSynchronize(st));
   h->counters.n_spmv++;
+  LSA_API_END(h)
+  return LSA_OK;
+}
+
+int lsa_set_nullspace(lsa_handle* h, int32_t count, const double* vecs_c128) {
+  if (!h || !h->analyzed || count < 0 || count > 16 || (count > 0 && !vecs_c128)) return LSA_ERR_ARG;
+  if (int rc = need_device(h)) return rc;
+  if (h->partitioned && count > 0) return fail(h, LSA_ERR_ARG, "nullspace projection is not available on a partitioned handle");
+  LSA_API_BEGIN
+  const int n = h->n;
+  dfree(h->d_ns);
+  h->ns_count = 0;
+  if (count > 0) {
+    h->d_ns = dalloc<z128>((size_t)n * count);
+    for (int c = 0; c < count; ++c) {
+      LSA_CUDA(cudaMemcpyAsync(h->d_io, (const z128*)vecs_c128 + (size_t)c * n, sizeof(z128) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+      permute_gather(h->stream, h->d_io, h->d_ns + (size_t)c * n, h->d_perm, n);
+    }
+    LSA_CUDA(cudaStreamSynchronize(h->stream));
+    h->ns_count = count;
+  }
   LSA_API_END(h)
   return LSA_OK;
 }

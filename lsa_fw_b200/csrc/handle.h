@@ -154,6 +154,8 @@ struct lsa_handle_impl {
   z128* d_theta = nullptr;
   double* d_resid = nullptr;
   int ncv_alloc = 0;
+  z128* d_ns = nullptr;    // attached nullspace: n x ns_count orthonormal columns, permuted ordering
+  int ns_count = 0;
 
   // ---- results
   int nconv = 0;

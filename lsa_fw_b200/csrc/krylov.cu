@@ -934,10 +934,29 @@ static void solve_dispatch(lsa_handle_impl& h, int trans, z128* x, int* nk) {
   if (nk) *nk += local;
 }
 
+// x <- x - N (N^H x): removes the attached nullspace (orthonormal columns N) from a vector, one Gram-Schmidt pass
+// with the basis kernels
+static void remove_nullspace(lsa_handle_impl& h, z128* x) {
+  const int n = h.n, j = h.ns_count;
+  const int rows_per_block = std::max(1024, (int)(((long long)n + 591) / 592 + 31) / 32 * 32);
+  const int nblk = cdiv(n, rows_per_block);
+  launch_dots(h.stream, nblk, n, j, h.d_ns, n, x, h.d_part, 256, rows_per_block, nullptr, nullptr);
+  k_reduce_h<<<cdiv(j, 8), 256, 0, h.stream>>>(j, nblk, h.d_part, 256, h.d_h, h.d_brow, 0, nullptr);
+  k_update<<<cdiv(n, 256), 256, 0, h.stream>>>(n, j, h.d_ns, n, h.d_h, x, nullptr, nullptr);
+  LSA_LAUNCH_CHECK();
+}
+
 // x <- F^-1 x (or F^-H x) with optional iterative refinement against F = alpha A + beta M.
 void op_solve(lsa_handle_impl& h, int trans, z128* x, int refine_steps) {
   int nk = 0;
   const int n = h.n;
+  if (h.ns_count > 0) {
+    // singular F with a known nullspace: compatible right-hand side in, nullspace-free solution out
+    remove_nullspace(h, x);
+    solve_dispatch(h, trans, x, &nk);
+    remove_nullspace(h, x);
+    return;
+  }
   if (refine_steps <= 0) {
     solve_dispatch(h, trans, x, &nk);
     return;

@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ 
   int c_lo = UP ? 0 : r0, c_hi = UP ? min(k, r0 + ROWS) : k;
   const int nsplit = gridDim.z;
   if (nsplit > 1) {
-    const int span = ((c_hi - c_lo + nsplit - 1) / nsplit + CHUNK - 1) / CHUNK * CHUNK;
+    const int span = ((c_hi - c_lo + nsplit - 1) / nsplit + 31) / 32 * 32;
     c_lo = c_lo + (int)blockIdx.z * span;
     c_hi = min(c_hi, c_lo + span);
   }
@@ -1833,11 +1833,12 @@ void exchange_replicated_rows(lsa_handle_impl& h, z128* x, bool with_cut_contrib
   LSA_LAUNCH_CHECK();
 }
 
-// splits of a chunk's triangular GEMV: enough CTAs for two waves over the SMs, at most 8 per row chunk
+// splits of a chunk's triangular GEMV: only where the row chunks alone leave most SMs idle (the root: 46 CTAs);
+// measured on config 3: splitting levels that already fill the GPU once costs more than it returns
 static int tri_splits(const lsa_handle_impl& h, const SolveChunk& c) {
   const long long ctas = (long long)cdiv(c.maxk, 32) * c.cnt;
-  if (c.maxk <= 512 || ctas >= 2LL * h.num_sms) return 1;
-  return (int)std::min<long long>(8, std::max<long long>(1, (2LL * h.num_sms + ctas - 1) / ctas));
+  if (c.maxk <= 512 || 2 * ctas > h.num_sms) return 1;
+  return (int)std::min<long long>(8, h.num_sms / ctas);
 }
 
 template <class T, bool H, bool UP>
@@ -1845,7 +1846,7 @@ static void launch_tri_gemv(lsa_handle_impl& h, cudaStream_t st, const SolveChun
                             const z128* in, z128* out) {
   const int ns = tri_splits(h, c);
   const dim3 grid(cdiv(c.maxk, 32), c.cnt, ns);
-  if (ns > 1 || c.maxk <= 512)
+  if (c.maxk <= 512)
     k_tri_gemv<T, H, UP, 8><<<grid, 256, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, in, out, h.d_tri_scratch, h.d_tri_tickets);
   else
     k_tri_gemv<T, H, UP, 32><<<grid, 1024, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, in, out, h.d_tri_scratch, h.d_tri_tickets);

@@ -637,13 +637,20 @@ class iEpsSolver:  # noqa: N801
                 h.m_token = _values_token(M) if (M is not None and self._M is not None) else None
             stats["upload_seconds"] = time.perf_counter() - t0
             sigma_fact = sigma
+            # attached nullspace (constant pressure of an enclosed flow, FEM/operators.py:534-545): projected out of
+            # every operator application; the vanishing pivot of the singular shifted operator is replaced
+            ns = getattr(self._A, "get_nullspace", lambda: None)()
+            ns_arr = None if ns is None else np.asarray(ns.as_array() if hasattr(ns, "as_array") else ns)
+            if ns_arr is not None or h.ns_count:
+                h.set_nullspace(ns_arr)
+            stats["nullspace_dimension"] = 0 if ns_arr is None else int(ns_arr.reshape(n, -1).shape[1])
             if needs_factor:
                 scalar = _lib.LSA_C128 if use_complex else _lib.LSA_F64
                 if sinvert:
                     fs = h.factor(1.0, -sigma, scalar, self._opts["tiny_pivot"])
                 else:
                     fs = h.factor(0.0, 1.0, scalar, 0.0)  # plain M^-1: an exactly singular M must raise
-                if sinvert and fs.n_perturbed > 0 and self._opts["coupled_fraction"] < 1.0:
+                if sinvert and fs.n_perturbed > stats["nullspace_dimension"] and self._opts["coupled_fraction"] < 1.0:
                     # tiny pivots were replaced: the cheap placement of the zero-diagonal unknowns was not
                     # enough for this pencil -> redo the analysis with the robust rule and factor again
                     logger.warning("%d tiny pivots replaced; re-analysing with coupled_fraction = 1", fs.n_perturbed)

@@ -928,3 +928,51 @@ def test_eigenvalue_sensitivity_contraction_matches_finite_differences():
     fd = (lp - lm) / (2 * d)
     print(f"d lambda / d Re: contraction {dl:.8e}  finite differences {fd:.8e}")
     assert abs(dl - fd) < 1e-5 * abs(fd) + 1e-9
+
+
+def test_attached_pressure_nullspace_is_projected_not_pinned():
+    """Enclosed flow WITHOUT a pinned pressure DOF: A and M share the constant-pressure nullspace, A - sigma M is singular
+    for every shift.  With the nullspace attached to A (`FEM/operators.py:534-545`, `FEM/utils.py:604-607`) the solver
+    replaces the vanishing pivot and projects the nullspace out of every operator application (KSP's behaviour;
+    `Solver/eigen2.py:171-176`): same spectrum as the pinned formulation (`FEM/utils.py:596-602`)."""
+    pinned = pencils.cavity_3d(6)
+    free = pencils.cavity_3d(6, pin_pressure=False)
+    sigma = -1.2 + 0.1j          # next to the least damped physical modes, away from the spurious lambda = 1 cluster
+    nvec = np.zeros(free.n)
+    nvec[free.dofs_p] = 1.0
+    ns = L.iPETScNullSpace.from_vectors([L.iPETScVector.from_array(nvec)])
+    A = L.iPETScMatrix(free.A)
+    ok, nrm = ns.test_matrix(A, tol=1e-10)
+    assert ok, nrm
+    ns.attach_to(A)
+    assert A.get_nullspace() is ns and ns.dimension == 1
+    cfg = L.EigensolverConfig(num_eig=6, atol=1e-11, max_it=200, ncv=40)
+
+    def run(Ac, Mc):
+        es = L.EigenSolver(Ac, Mc, cfg, check_hermitian=False)
+        es.solver.set_st_type(L.iSTType.SINVERT)
+        es.solver.set_target(sigma)
+        es.solver.set_st_pc_type(L.PreconditionerType.LU)
+        es.solver.set_backend_options(leaf_size=32)
+        return es, es.solve()
+
+    es, pairs = run(A, L.iPETScMatrix(free.M))
+    assert es.solver.stats["nullspace_dimension"] == 1 and es.solver.stats["n_perturbed"] >= 1
+    es_p, pairs_p = run(L.iPETScMatrix(pinned.A), L.iPETScMatrix(pinned.M))
+    lam, lam_p = np.array([p[0] for p in pairs]), np.array([p[0] for p in pairs_p])
+    # the pinned formulation carries one more spurious eigenvalue 1 (the pinned row); physical modes agree
+    phys = lam_p[np.abs(lam_p - 1.0) > 1e-6]
+    mine = lam[np.abs(lam - 1.0) > 1e-6]
+    assert len(mine) >= 3 and _match(mine[:3], phys) < EIG_RTOL
+    X = np.stack([_vec(v) for _, v in pairs], axis=1)
+    assert O.north_star_residuals(free.A, free.M, lam, X).max() < RESID_BAR
+    assert np.abs(nvec @ X).max() / np.linalg.norm(nvec) < 1e-9          # no constant-pressure component in the modes
+    # the adjoint modes on the same (singular) factorisation
+    ea = L.EigenSolver(A.H, L.iPETScMatrix(free.M).H, cfg, check_hermitian=False)
+    ea.solver.set_st_type(L.iSTType.SINVERT)
+    ea.solver.set_target(np.conj(sigma))
+    ea.solver.set_st_pc_type(L.PreconditionerType.LU)
+    ea.solver.set_backend_options(leaf_size=32)
+    lam_a = np.array([p[0] for p in ea.solve()])
+    mine_a = lam_a[np.abs(lam_a - 1.0) > 1e-6]
+    assert _match(np.conj(mine_a[:3]), phys) < EIG_RTOL
