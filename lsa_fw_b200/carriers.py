@@ -237,6 +237,39 @@ class iPETScMatrix:  # noqa: N801
         return cls(scipy.io.mmread(str(path)).tocsr())
 
     @classmethod
+    def load(cls, path: Path, comm=None) -> "iPETScMatrix":
+        """PETSc binary ingest (`FEM/utils.py:222-230`: `PETSc.Mat().load(viewer)`) without PETSc: the MATAIJ binary
+        layout is big-endian int32 {classid 1211216, rows, cols, nnz}, per-row counts, column indices, then the
+        values (float64, or interleaved re/im float64 for the complex build -- told apart by the file size).  The
+        arrays go straight into CSR: no per-entry `setValue` loop."""
+        raw = np.fromfile(str(path), dtype=np.uint8)
+        hdr = raw[:16].view(">i4")
+        if len(raw) < 16 or int(hdr[0]) != 1211216:
+            raise ValueError(f"{path}: not a PETSc binary matrix (MAT_FILE_CLASSID missing)")
+        m, n, nnz = int(hdr[1]), int(hdr[2]), int(hdr[3])
+        if nnz < 0:
+            raise ValueError(f"{path}: dense / special PETSc binary layouts are not supported")
+        off = 16
+        counts = raw[off: off + 4 * m].view(">i4").astype(np.int64)
+        off += 4 * m
+        cols = raw[off: off + 4 * nnz].view(">i4").astype(np.int32)
+        off += 4 * nnz
+        rest = len(raw) - off
+        if rest == 8 * nnz:
+            vals = raw[off:].view(">f8").astype(np.float64)
+        elif rest == 16 * nnz:
+            vals = raw[off:].view(">f8").astype(np.float64).view(np.complex128)
+        else:
+            raise ValueError(f"{path}: value block of {rest} bytes fits neither float64 nor complex128 for nnz = {nnz} "
+                             "(64-bit-index PETSc builds are not supported)")
+        indptr = np.concatenate([[0], np.cumsum(counts)])
+        if int(indptr[-1]) != nnz:
+            raise ValueError(f"{path}: row counts do not add up to nnz")
+        out = cls(sp.csr_matrix((vals, cols, indptr), shape=(m, n)))
+        out._m.sort_indices()
+        return out
+
+    @classmethod
     def from_matrix(cls, matrix, comm=None) -> "iPETScMatrix":
         """From a dense array or SciPy sparse matrix (`FEM/utils.py:183-220`)."""
         if sp.issparse(matrix):
@@ -363,8 +396,23 @@ class iPETScMatrix:  # noqa: N801
         return self._csr()
 
     def export(self, path: Path) -> None:
-        """MatrixMarket export (`FEM/utils.py:616-659`, the `.mtx` branch)."""
-        scipy.io.mmwrite(str(path), self._m)
+        """Export (`FEM/utils.py:616-659`): `*.mtx` -> MatrixMarket, anything else -> PETSc binary (MATAIJ layout,
+        32-bit indices; real or complex values as the data are), readable by `PETSc.Mat().load` of the matching
+        build and by `iPETScMatrix.load`."""
+        path = Path(path)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        if path.suffix.lower() == ".mtx":
+            scipy.io.mmwrite(str(path), self._m)
+            return
+        m = self._csr()
+        with open(path, "wb") as f:
+            np.array([1211216, m.shape[0], m.shape[1], m.nnz], dtype=">i4").tofile(f)
+            np.diff(m.indptr).astype(">i4").tofile(f)
+            m.indices.astype(">i4").tofile(f)
+            if np.iscomplexobj(m.data):
+                np.ascontiguousarray(m.data, dtype=np.complex128).view(np.float64).astype(">f8").tofile(f)
+            else:
+                np.asarray(m.data, dtype=np.float64).astype(">f8").tofile(f)
 
     def __matmul__(self, other):
         if isinstance(other, iPETScVector):

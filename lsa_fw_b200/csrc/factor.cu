@@ -412,8 +412,14 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
   constexpr int LDB_S = KC + 4;
   constexpr int KA = CPLX ? KC / 2 : KC;      // stored A columns per chunk
   constexpr int A_PER_T = BM * KA / 128;      // 8 real, 4 complex
-  __shared__ double As[2][KA * LDA_S];
-  __shared__ double Bs[2][BN * LDB_S];
+  // one block of shared memory: the operand double buffers during the K loop, then (complex) the 64 x 64 tile of
+  // results on its way to a coalesced read-modify-write of C
+  constexpr int A_SZ = KA * LDA_S, B_SZ = BN * LDB_S;
+  constexpr int LDC_S = BM + 2;
+  constexpr int SMEM_D = 2 * (A_SZ + B_SZ) > BN * LDC_S ? 2 * (A_SZ + B_SZ) : BN * LDC_S;
+  __shared__ __align__(16) double smem_all[SMEM_D];
+  double(*As)[A_SZ] = reinterpret_cast<double(*)[A_SZ]>(smem_all);
+  double(*Bs)[B_SZ] = reinterpret_cast<double(*)[B_SZ]>(smem_all + 2 * A_SZ);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wm = wid & 1, wn = wid >> 1;
   const int g = lane >> 2, tg = lane & 3;
@@ -499,7 +505,49 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
     if (kc + 1 < nchunks) store_smem(cur ^ 1);
     __syncthreads();
   }
-  // epilogue: C -= acc
+  // ---- epilogue
+  if (CPLX) {
+    // Complex: rows of the real view come in (re, im) pairs, C and ldc are 16-byte aligned.  The m8n8k4 accumulator
+    // layout gives every thread two ADJACENT COLUMNS of one row -- scattered 8-byte accesses in column-major C (the
+    // rank-32 updates and the small-K Schur complements are bound by exactly this traffic).  The tile goes through
+    // shared memory instead and is applied with one 16-byte read-modify-write per thread and instruction, a warp
+    // covering 512 contiguous bytes of a column.  (The loop above ended with a block barrier: the buffers are free.)
+    double* Cs = smem_all;
+#pragma unroll
+    for (int mf = 0; mf < 4; ++mf) {
+      const int row = wm * 32 + mf * 8 + g;
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) {
+        const int col = wn * 32 + nf * 8 + tg * 2;
+        Cs[col * LDC_S + row] = acc[mf][nf][0];
+        Cs[(col + 1) * LDC_S + row] = acc[mf][nf][1];
+      }
+    }
+    __syncthreads();
+    const int rp = (tid & 31) * 2, cq = tid >> 5;
+#pragma unroll 4
+    for (int i = 0; i < BN / 4; ++i) {
+      const int col = cq + 4 * i;
+      if (m0 + rp < Mr && n0 + col < N) {   // Mr is even: the pair is inside or outside together
+        double2* p = reinterpret_cast<double2*>(C + (m0 + rp) + (long long)(n0 + col) * ldc_r);
+        const double2 a = *reinterpret_cast<const double2*>(Cs + col * LDC_S + rp);
+        double2 c;
+        if (EPI == 0) {
+          c = *p;
+          c.x -= a.x;
+          c.y -= a.y;
+        } else if (EPI == 1) {
+          c.x = -a.x;
+          c.y = -a.y;
+        } else {
+          c = a;
+        }
+        *p = c;
+      }
+    }
+    __syncthreads();   // the buffers are reused by the caller's next tile (persistent callers) -- and by nobody else
+    return;
+  }
 #pragma unroll
   for (int mf = 0; mf < 4; ++mf) {
     const int R = m0 + wm * 32 + mf * 8 + g;
@@ -803,7 +851,9 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
             const int max_pk = std::min(sym.fronts[sym.lvl_front[first]].k, ob0 + OB) - j0;
             const long long want = (long long)max_pk * NB * (long long)sizeof(T);
             const int panel_smem = (int)std::min<long long>(want, PANEL_SMEM_CAP);
-            k_panel_lu<T><<<act, 256, panel_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs,
+            // the pivot candidates are the <= 128 rows of the current outer block: 128 threads cover them (one
+            // row each in the scaling / rank-1 step), with half the warps to synchronise per column step
+            k_panel_lu<T><<<act, 128, panel_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs,
                                                         h.d_stats, panel_smem, ob0);
           }
           LSA_LAUNCH_CHECK();

@@ -743,6 +743,29 @@ __global__ void k_perm_scatter_scaled(const z128* __restrict__ src, z128* __rest
   if (i < n) dst[perm[i]] = src[i] * (*phase);
 }
 
+// Rows per block of the Gram-Schmidt dot kernels: the grid must be ONE wave of resident blocks.  The register
+// footprint (and with it the number of resident blocks per SM) depends on the column variant; 578 blocks on 444
+// slots meant a second, almost empty wave and 2.6 TB/s where the same kernel streams > 4 TB/s in one wave
+// (profiles/r2e_ncu_full_ortho_summary.txt).
+static int gs_rows_per_block(int n, int j, int num_sms) {
+  static int slots_per_sm[5] = {0, 0, 0, 0, 0};
+  const int v = j <= 16 ? 0 : j <= 32 ? 1 : j <= 64 ? 2 : j <= 96 ? 3 : 4;
+  if (slots_per_sm[v] == 0) {
+    int a = 1, b = 1;
+    switch (v) {
+      case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_dots<2, 8>, 256, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_update_dots<2, 8>, 256, 0); break;
+      case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_dots<4, 4>, 256, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_update_dots<4, 4>, 256, 0); break;
+      case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_dots<8, 2>, 256, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_update_dots<8, 2>, 256, 0); break;
+      case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_dots<12, 2>, 256, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_update_dots<12, 2>, 256, 0); break;
+      default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_dots<16, 1>, 256, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_update_dots<16, 1>, 256, 0); break;
+    }
+    slots_per_sm[v] = std::max(1, std::min(a, b));
+  }
+  const long long slots = (long long)slots_per_sm[v] * num_sms;
+  const long long rpb = (((long long)n + slots - 1) / slots + 255) / 256 * 256;
+  return (int)std::max<long long>(1024, rpb);
+}
+
 // ------------------------------------------------------------------ row ranges (partitioned solve)
 //
 // Single GPU: one range [0, n).  Partitioned: `upd_ranges` = rows this GPU maintains (replicated rows + its
@@ -1092,7 +1115,9 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   long long sum_cols = 0;
   apply_op(h, p, h.d_x, h.d_w, t_spmv, t_solve);
   n_applies++;
-  normalize_vector(h, h.d_w, V, nullptr, nullptr, nullptr, 0, nullptr, 0);
+  // (flag: a NaN / Inf start vector or first operator application is reported through flag[1]; the step number is
+  // out of range, so a vanishing norm here does not register as an Arnoldi breakdown)
+  normalize_vector(h, h.d_w, V, nullptr, nullptr, nullptr, 0, h.d_flag, 0x7fffffff);
 
   int nconv = 0, keep = 0, restarts = 0, breakdown = 0, m_last = ncv;
   bool invariant = false;
@@ -1111,7 +1136,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       z128* scol = S + (long long)j * ld;
       // classical Gram-Schmidt, second pass only when the criterion asks for it (decided on the device: the
       // pass-2 kernels return at once when the flag is clear)
-      orthonormalize(h, V, ldv, jj, h.d_w, V + (long long)(j + 1) * ldv, scol, rows_per_block, ldp, false, h.d_flag, j);
+      orthonormalize(h, V, ldv, jj, h.d_w, V + (long long)(j + 1) * ldv, scol, gs_rows_per_block(n, jj, h.num_sms), ldp, false, h.d_flag, j);
       h.launch_count += 9;  // spmv + 8 orthogonalisation kernels
       t_ortho.end(e);
     }
@@ -1162,7 +1187,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       // direction orthogonal to it (SLEPc does the same after a breakdown)
       z128* vnew = V + (long long)keep * ldv;
       k_randn<<<blocks, 256, 0, st>>>(h.d_w, n, p.seed + 7919ULL * (unsigned long long)restarts);
-      orthonormalize(h, V, ldv, keep, h.d_w, vnew, nullptr, rows_per_block, ldp, true, nullptr, 0);
+      orthonormalize(h, V, ldv, keep, h.d_w, vnew, nullptr, gs_rows_per_block(n, keep, h.num_sms), ldp, true, nullptr, 0);
       h_flag[0] = 0x7fffffff;
       LSA_CUDA(cudaMemcpyAsync(h.d_flag, h_flag, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
       LSA_LAUNCH_CHECK();

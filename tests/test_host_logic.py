@@ -330,6 +330,29 @@ def test_carriers_follow_reference_semantics(tmp_path):
 
 
 # ------------------------------------------------------------------------------- replicas (gloo, world 2)
+def test_petsc_binary_and_matrix_market_round_trip(tmp_path):
+    """Row f1: MatrixMarket (`FEM/utils.py:143-147`) and PETSc binary (`:222-230`, `:616-659`) ingest / export without
+    PETSc, real and complex, incl. the explicit zeros dolfinx leaves in the pattern."""
+    rng = np.random.default_rng(4)
+    A = sp.random(40, 40, 0.1, random_state=5, format="csr") + sp.eye(40, format="csr")
+    A.data[3] = 0.0                                   # an explicit zero stays part of the pattern
+    for mat in (A.tocsr(), (A + 1j * sp.random(40, 40, 0.05, random_state=6, format="csr")).tocsr()):
+        c = L.iPETScMatrix(mat)
+        c.export(tmp_path / "m.bin")
+        back = L.iPETScMatrix.load(tmp_path / "m.bin")
+        b = back.as_scipy_array()
+        assert b.dtype == mat.dtype and np.array_equal(b.indptr, mat.indptr) and np.array_equal(b.indices, mat.indices)
+        assert np.array_equal(b.data, mat.data)
+        c.export(tmp_path / "m.mtx")
+        mm = L.iPETScMatrix.from_path(tmp_path / "m.mtx").as_scipy_array()
+        assert abs(mm - mat).max() == 0
+    raw = np.fromfile(tmp_path / "m.bin", dtype=">i4", count=4)
+    assert raw[0] == 1211216 and raw[1] == 40 and raw[2] == 40          # the header PETSc's MatLoad expects
+    (tmp_path / "junk.bin").write_bytes(b"\0" * 64)
+    with pytest.raises(ValueError):
+        L.iPETScMatrix.load(tmp_path / "junk.bin")
+
+
 def test_shard_tasks():
     from lsa_fw_b200.replicas import shard_tasks
 
