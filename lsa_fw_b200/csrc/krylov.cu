@@ -743,10 +743,11 @@ __global__ void k_perm_scatter_scaled(const z128* __restrict__ src, z128* __rest
   if (i < n) dst[perm[i]] = src[i] * (*phase);
 }
 
-// Rows per block of the Gram-Schmidt dot kernels: the grid must be ONE wave of resident blocks.  The register
-// footprint (and with it the number of resident blocks per SM) depends on the column variant; 578 blocks on 444
-// slots meant a second, almost empty wave and 2.6 TB/s where the same kernel streams > 4 TB/s in one wave
-// (profiles/r2e_ncu_full_ortho_summary.txt).
+// Rows per block of the Gram-Schmidt dot kernels: the grid is a whole number of waves of resident blocks.  The
+// register footprint (and with it the number of resident blocks per SM) depends on the column variant; a grid
+// that is not a multiple of the resident capacity ends in an almost empty wave (578 blocks on 444 slots: 2.6 TB/s,
+// profiles/r2e_ncu_full_ortho_summary.txt).  Measured on config 3 (profiles/r2g_*): 2 waves 0.123 s of
+// Gram-Schmidt per step, 1 wave 0.141 s, 3 waves 0.131 s.  LSA_GS_WAVES overrides for experiments.
 static int gs_rows_per_block(int n, int j, int num_sms) {
   static int slots_per_sm[5] = {0, 0, 0, 0, 0};
   const int v = j <= 16 ? 0 : j <= 32 ? 1 : j <= 64 ? 2 : j <= 96 ? 3 : 4;
@@ -761,7 +762,11 @@ static int gs_rows_per_block(int n, int j, int num_sms) {
     }
     slots_per_sm[v] = std::max(1, std::min(a, b));
   }
-  const long long slots = (long long)slots_per_sm[v] * num_sms;
+  long long slots = (long long)slots_per_sm[v] * num_sms;
+  double waves = 2.0;
+  if (const char* e = getenv("LSA_GS_WAVES")) waves = atof(e);
+  slots = (long long)(waves * (double)slots);
+  slots = std::max<long long>(1, std::min<long long>(slots, 1000));
   const long long rpb = (((long long)n + slots - 1) / slots + 255) / 256 * 256;
   return (int)std::max<long long>(1024, rpb);
 }
