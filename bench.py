@@ -71,6 +71,7 @@ WORKLOADS = {
 }
 TOL = 1e-11
 MAX_RESTARTS = 100
+LEAF = int(os.environ.get("LSA_BENCH_LEAF", "64"))   # leaf size of the nested dissection (experiments; 64 = library default)
 METRIC = "shift-invert eigensolve s (nev=10, LU included) per (Re, sigma) pair"
 
 
@@ -472,7 +473,7 @@ def main() -> None:
     # ------------- device-resident arm: C ABI directly, the values of every pair already in HBM
     h = _lib.Handle(n, local_rank)
     t0 = time.perf_counter()
-    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=order_last_flags(pc))
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=LEAF, order_last=order_last_flags(pc))
     t_symbolic = time.perf_counter() - t0
     my_steps = [i for i in range(args.steps) if i % world == rank]   # strong scaling: the K steps are dealt over the ranks
     # only the pairs this rank touches are materialised (8 ranks x 8 value arrays x 0.7 GB would be host memory for nothing)
@@ -584,7 +585,7 @@ def main() -> None:
         es.solver.set_st_type(L.iSTType.SINVERT)
         es.solver.set_target(sigma)
         es.solver.set_st_pc_type(L.PreconditionerType.LU)
-        es.solver.set_backend_options(device=local_rank, v0=v0)
+        es.solver.set_backend_options(device=local_rank, v0=v0, leaf_size=LEAF)
         pairs = es.solve()
         d2h = len(pairs) * n * 16
         if w["adjoint"]:

@@ -434,7 +434,17 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
   const int a_row = tid & 63, a_kg = tid >> 6;  // 2 groups of stored columns
   const int b_n = tid >> 1, b_kh = (tid & 1) * 8;
   double ra[A_PER_T], rb[8];
-  const int nchunks = (Kr + KC - 1) / KC;
+  // K range of the tile: a triangular operand (mask) is zero outside it -- lower B: k >= n0, upper B: k < n0 + BN,
+  // lower A: k < m0 + BM, upper A: k >= m0 (real-view indices; complex rows / K come in pairs, so the same bounds
+  // scaled by the view factor) -- which halves the work of the block-inverse merges
+  constexpr int SV = CPLX ? 2 : 1;
+  int k_begin = 0, k_end = Kr;
+  if (BMASK == 1) k_begin = max(k_begin, n0 * SV);
+  if (BMASK == 2) k_end = min(k_end, (n0 + BN) * SV);
+  if (AMASK == 1) k_end = min(k_end, m0 + BM);
+  if (AMASK == 2) k_begin = max(k_begin, m0);
+  const int kc_first = k_begin / KC;
+  const int nchunks = max(kc_first, (k_end + KC - 1) / KC);
 
   auto load_global = [&](int kc) {
     const int k0 = kc * KC;  // real-view K offset
@@ -472,10 +482,12 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
     for (int q = 0; q < 8; ++q) Bs[buf][b_n * LDB_S + b_kh + q] = rb[q];
   };
 
-  load_global(0);
-  store_smem(0);
+  if (kc_first < nchunks) {
+    load_global(kc_first);
+    store_smem(kc_first & 1);
+  }
   __syncthreads();
-  for (int kc = 0; kc < nchunks; ++kc) {
+  for (int kc = kc_first; kc < nchunks; ++kc) {
     const int cur = kc & 1;
     if (kc + 1 < nchunks) load_global(kc + 1);
     const double* as = As[cur];

@@ -824,7 +824,7 @@ def test_multiplier_growth_triggers_reanalysis_then_refinement(caplog):
 
 
 # ------------------------------------------------------------------ one solve split over several GPUs (row e)
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_solve_over_gpus(world):
     """Sub-trees per GPU + replicated top, NCCL broadcast / all-reduce inside the CUDA library: solves to 1e-12,
     eigenvalues identical to the single-GPU run, same results on every rank (tests/workers/partitioned_gpu_worker.py)."""
