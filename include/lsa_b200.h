@@ -173,13 +173,15 @@ int lsa_partition_info_get(const lsa_handle* h, lsa_partition_info* out);
  *       "stream_stages" (0 = by level size, 2..12): ring depth; "stream_flags" (3): bit 0 wider tiles for narrow
  *       blocks, bit 1 single-copy tiles for contiguous blocks, bit 2 LDGSTS producer (measured slower);
  *   "use_clusters" (default 1): sweep the remaining multi-step levels with one thread-block cluster per front;
- *       "invert_max_k" (4096): levels that are not streamed and whose pivot blocks are at most this wide get those
+ *       "invert_max_k" (8192): levels that are not streamed and whose pivot blocks are at most this wide get those
  *       blocks inverted as a whole after the factorisation (one triangular matrix-vector product per front and
  *       sweep, no dependent 128-pivot steps; 0 = off, wider blocks keep the step kernels below);
  *       "cluster_max_width" (16): CTAs per cluster; "cluster_max_rows" (8192): taller fronts get one grid-wide
  *       launch per 128-pivot step instead; "cluster_slices" (1): levels with <= 9 fronts use 16-CTA clusters that
  *       share every 128-row block by 8-row slices (DSMEM all-gather of the solved entries); "defer_cb" (1): the
  *       contribution rows are updated by one wide GEMV after the pivot steps;
+ *   "partition_graphs" (default 1): partitioned solve: the sweeps, NCCL all-reduce included, are replayed from CUDA
+ *       graphs like the single-GPU ones;
  *   "fuse_ortho" (default 1): the update of the first Gram-Schmidt pass and the dot products of the second one in
  *       one kernel (the basis is read three times per column instead of four);
  *   "ortho_refine_always" (default 0): second Gram-Schmidt pass for every basis column instead of SLEPc's

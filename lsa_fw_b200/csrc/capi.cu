@@ -504,6 +504,12 @@ int lsa_set_comm(lsa_handle* h, const void* id128) {
   LSA_API_BEGIN
   comm_destroy(h->comm);
   comm_init(h->comm, id128, h->part_rank, h->part_world);
+  // first collective outside any stream capture: NCCL sets its channels up lazily
+  double* warm = dalloc<double>(8);
+  LSA_CUDA(cudaMemsetAsync(warm, 0, 8 * sizeof(double), h->stream));
+  comm_allreduce_sum(h->comm, warm, 8, h->stream);
+  LSA_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(warm);
   LSA_API_END(h)
   return LSA_OK;
 }
@@ -543,6 +549,8 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->use_clusters = value != 0.0;
   } else if (nm == "ortho_refine_always") {
     h->ortho_refine_always = value != 0.0;
+  } else if (nm == "partition_graphs") {
+    h->part_graphs = value != 0.0;
   } else if (nm == "fuse_ortho") {
     h->fuse_ortho = value != 0.0;
   } else if (nm == "use_stream") {
@@ -744,6 +752,7 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
     if (atoi(e) != 0) h->use_graphs = false;
   }
   if (const char* e = getenv("LSA_INVERT_MAX_K")) h->invert_max_k = atoi(e);
+  if (const char* e = getenv("LSA_PARTITION_GRAPHS")) h->part_graphs = atoi(e) != 0;
   plan_solve(*h, scalar);
   if (scalar == LSA_C128) {
     factor_numeric<z128>(*h, alpha, beta, tiny_abs, &nk);

@@ -680,7 +680,10 @@ __global__ void __launch_bounds__(128) k_inv_merge(const Front* __restrict__ fro
   const int hd = min(HB, k - jd);
   const long long m = (long long)k + f.r;
   T* P = fac + f.p_off;
-  T* Tm = scratch + scr_off[blockIdx.z] + (long long)blockIdx.y * 2 * HB * HB + (UPPER ? (long long)HB * HB : 0);
+  // scratch slot of pair p: [2 p HB^2, ...): T (hd x HB, ld = hd) then T2 (HB x hd, ld = HB) -- 2 hd HB entries, so a
+  // front needs at most k HB <= k^2 / 2 entries at any merge level (post_factor sizes the regions accordingly)
+  T* Tm = scratch + scr_off[blockIdx.z] + (long long)blockIdx.y * 2 * HB * HB + (UPPER ? (long long)hd * HB : 0);
+  const long long ldt = UPPER ? HB : hd;
   const int Mrows = UPPER ? HB : hd, Ncols = UPPER ? hd : HB;
   const int tm = (Mrows * S + 63) / 64, tn = (Ncols + 63) / 64;
   const int t = blockIdx.x;
@@ -691,11 +694,11 @@ __global__ void __launch_bounds__(128) k_inv_merge(const Front* __restrict__ fro
   double* Cblk = (double*)(P + jd + (long long)j0 * m);   // below the diagonal
   double* Bblk = (double*)(P + j0 + (long long)jd * m);   // above the diagonal
   if (PHASE == 1) {
-    if (!UPPER) gemm_tile<CPLX, 0, 1, 2>(Cblk, m * S, Ablk, m * S, (double*)Tm, (long long)HB * S, hd * S, HB, HB * S, m0, n0);
-    else gemm_tile<CPLX, 0, 2, 2>(Bblk, m * S, Dblk, m * S, (double*)Tm, (long long)HB * S, HB * S, hd, hd * S, m0, n0);
+    if (!UPPER) gemm_tile<CPLX, 0, 1, 2>(Cblk, m * S, Ablk, m * S, (double*)Tm, ldt * S, hd * S, HB, HB * S, m0, n0);
+    else gemm_tile<CPLX, 0, 2, 2>(Bblk, m * S, Dblk, m * S, (double*)Tm, ldt * S, HB * S, hd, hd * S, m0, n0);
   } else {
-    if (!UPPER) gemm_tile<CPLX, 1, 0, 1>(Dblk, m * S, (const double*)Tm, (long long)HB * S, Cblk, m * S, hd * S, HB, hd * S, m0, n0);
-    else gemm_tile<CPLX, 2, 0, 1>(Ablk, m * S, (const double*)Tm, (long long)HB * S, Bblk, m * S, HB * S, hd, HB * S, m0, n0);
+    if (!UPPER) gemm_tile<CPLX, 1, 0, 1>(Dblk, m * S, (const double*)Tm, ldt * S, Cblk, m * S, hd * S, HB, hd * S, m0, n0);
+    else gemm_tile<CPLX, 2, 0, 1>(Ablk, m * S, (const double*)Tm, ldt * S, Bblk, m * S, HB * S, hd, HB * S, m0, n0);
   }
 }
 

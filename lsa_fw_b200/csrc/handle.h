@@ -95,6 +95,7 @@ struct lsa_handle_impl {
   // ---- partitioned solve over the GPUs of a node (stage 1: sub-trees per GPU, replicated top; lsa_internal.h)
   int part_rank = 0, part_world = 1;     // lsa_set_partition, before lsa_analyze
   bool partitioned = false;
+  bool part_graphs = true;               // partitioned sweeps (incl. their NCCL all-reduce) replayed from CUDA graphs
   Partition part;
   Comm comm;
   void* d_cut_pool = nullptr;            // contribution blocks of ALL sub-tree roots (own: computed, others: broadcast)
@@ -176,7 +177,7 @@ struct lsa_handle_impl {
   };
   std::vector<SolveGraph> solve_graphs;
   std::vector<SolveChunk> solve_plan;   // levels in root-to-leaf order, rebuilt at every factorisation
-  int invert_max_k = 4096;              // levels whose pivot blocks are at most this wide get them inverted as a whole
+  int invert_max_k = 8192;              // levels whose pivot blocks are at most this wide get them inverted as a whole
   void* d_inv_scratch = nullptr;        // scratch of the block-inverse merges
   long long inv_scratch_bytes = 0, inv_scratch_entries = 0;
   long long* d_inv_off = nullptr;       // per-front scratch offsets of the current batch

@@ -932,7 +932,9 @@ static void solve_dispatch(lsa_handle_impl& h, int trans, z128* x, int* nk) {
     else solve_permuted<double>(h, trans, x, count);
   };
   int local = 0;
-  if (!h.use_graphs || h.partitioned) {   // partitioned solve: NCCL calls inside the sweep, enqueued directly
+  // partitioned solve: the sweep contains an NCCL all-reduce; NCCL kernels are captured like any other launch
+  // (the communicator was warmed up outside any capture in lsa_set_comm).  "partition_graphs" = 0 enqueues directly.
+  if (!h.use_graphs || (h.partitioned && !h.part_graphs)) {
     run(&local);
   } else {
     lsa_handle_impl::SolveGraph* found = nullptr;

@@ -158,6 +158,22 @@ template <class T>
 void launch_inv_merge(cudaStream_t st, const Front* fronts, const int* lvl_front, int first, int cnt, const long long* scr_off,
                       int HB, int maxk, T* fac, T* scratch);   // factor.cu
 
+// scratch entries the block-inverse merges of a k-pivot front need (see k_inv_merge): max over the merge levels
+// HB = 128, 256, ... < k of  2 HB^2 floor((k - HB) / (2 HB)) + 2 HB hd_last
+static long long inv_region(long long k) {
+  long long need = 0;
+  for (long long HB = SB; HB < k; HB *= 2) {
+    const long long pairs = (k + 2 * HB - 1) / (2 * HB);
+    long long last = -1;
+    for (long long p = pairs - 1; p >= 0 && last < 0; --p)
+      if (p * 2 * HB + HB < k) last = p;
+    if (last < 0) continue;
+    const long long hd = std::min(HB, k - (last * 2 * HB + HB));
+    need = std::max(need, last * 2 * HB * HB + 2 * hd * HB);
+  }
+  return (need + 3) & ~3LL;
+}
+
 template <class T>
 void post_factor(lsa_handle_impl& h, int* n_kernels) {
   const Symbolic& sym = h.sym;
@@ -200,11 +216,11 @@ void post_factor(lsa_handle_impl& h, int* n_kernels) {
         int q1 = q;
         while (q1 < qend && sym.fronts[sym.lvl_front[q1]].k > SB) {
           const long long kk = sym.fronts[sym.lvl_front[q1]].k;
-          // scratch region of a front: 2 k^2 entries (pair p of merge level HB uses [2 p HB^2, 2 (p + 1) HB^2),
-          // and (p + 1) 2 HB^2 < (k + HB) HB < 2 k^2 for every pair that exists)
-          if (!off.empty() && (used + 2 * kk * kk > h.inv_scratch_entries || off.size() >= 32768)) break;
+          // scratch region of a front: pair p of merge level HB starts at 2 p HB^2 and uses 2 hd HB entries (hd = HB
+          // for all but the last pair), i.e. at most k HB <= k^2 / 2 + k entries at any level (inv_region)
+          if (!off.empty() && (used + inv_region(kk) > h.inv_scratch_entries || off.size() >= 32768)) break;
           off.push_back(used);
-          used += 2 * kk * kk;
+          used += inv_region(kk);
           ++q1;
         }
         LSA_CUDA(cudaMemcpyAsync(h.d_inv_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
@@ -1876,20 +1892,20 @@ void plan_solve(lsa_handle_impl& h, int scalar) {
         c.maxk = std::max(c.maxk, f.k);
         c.max_r = std::max(c.max_r, f.r);
         c.max_m = std::max(c.max_m, f.k + f.r);
-        if (f.k > SB) sumk2 += 2LL * f.k * f.k;
+        if (f.k > SB) sumk2 += inv_region(f.k);
       }
       const int kmax = (c.maxk + 7) / 8 * 8, rmax = (c.max_r + 7) / 8 * 8;
       const size_t fixed = sizeof(z128) * (4 * (size_t)kmax + 2 * (size_t)rmax) + 3 * sizeof(int) * (size_t)rmax;
       const bool stream_fits = fixed + sizeof(z128) * 2 * (size_t)TILE <= (size_t)STREAM_MAX_SMEM;
       if (scalar == LSA_C128 && h.use_stream && stream_fits && (c.maxk <= SB || c.cnt >= h.stream_min_fronts))
         c.mode = SOLVE_STREAM;
-      else if (c.maxk <= h.invert_max_k)
-        c.mode = SOLVE_INVERTED;
+      else if (c.maxk <= h.invert_max_k && inv_region(c.maxk) <= (4LL << 30) / (scalar == LSA_C128 ? 16 : 8))
+        c.mode = SOLVE_INVERTED;   // (whole-block inverses need a scratch region per front: capped at 4 GiB)
       else
         c.mode = SOLVE_STEPS;
       if (c.mode == SOLVE_INVERTED && c.maxk > SB) {
         scratch = std::max(scratch, std::min<long long>(sumk2, 1LL << 26));
-        max_region = std::max(max_region, 2LL * c.maxk * c.maxk);
+        max_region = std::max(max_region, inv_region(c.maxk));
       }
       h.solve_plan.push_back(c);
     }
