@@ -163,6 +163,12 @@ int lsa_set_comm(lsa_handle* h, const void* id128);
 int lsa_partition_info_get(const lsa_handle* h, lsa_partition_info* out);
 
 /* Tuning knobs, to be set before lsa_analyze / lsa_factor:
+ *   "symmetric" (default 0; before lsa_analyze): the pencil is real symmetric and the shift real (GHEP / HEP with
+ *       st_pc_type CHOLESKY, Elasticity/utils.py:139-155, tests/benchmark/vibrating_membrane.py): F = L D L^T without
+ *       pivoting (tiny pivots replaced, growth monitored), only the P blocks [L11 \ D L11^T; L21] are stored --
+ *       nnz_lu = sum k^2 + k r instead of k^2 + 2 k r -- the Schur complements are formed as C -= L21 (D L21^T) with the
+ *       scaled, transposed operand built in the GEMM loader, and a solve is  L-sweep, diagonal scaling, L^T-sweep.
+ *       scalar must be LSA_F64; lsa_solve gives the same result for every `trans`;
  *   "coupled_fraction" (default 0.5): an unknown with a structurally zero diagonal (pressure) is eliminated
  *       no earlier than the front in which this share of its coupled regular unknowns has been eliminated
  *       (1.0 = all of them: most robust, ~+40-70 % flops in 2-D);

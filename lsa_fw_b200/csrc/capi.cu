@@ -330,6 +330,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   opt.order_last = order_last;
   opt.nthreads = nthreads;
   opt.coupled_fraction = h->coupled_fraction;
+  opt.symmetric = h->symmetric;
   if (const char* e = getenv("LSA_COUPLED_FRACTION")) opt.coupled_fraction = atof(e);
   if (const char* e = getenv("LSA_CAP_FRACTION")) opt.cap_fraction = atof(e);
   if (h->has_m) analyze(n, urow.data(), ucol.data(), opt, h->sym);
@@ -403,6 +404,10 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
           continue;
         }
         const long long m = f.k + f.r;
+        if (sym.symmetric && lc >= f.k) {   // U12 entry: its mirror image lands in L21, nothing is stored for it
+          dst[e] = -1;
+          continue;
+        }
         dst[e] = lc < f.k ? f.p_off + lr + (long long)lc * m : f.q_off + lr + (long long)(lc - f.k) * f.k;
       }
     }
@@ -540,7 +545,10 @@ int lsa_partition_info_get(const lsa_handle* h, lsa_partition_info* out) {
 int lsa_set_option(lsa_handle* h, const char* name, double value) {
   if (!h || !name) return LSA_ERR_ARG;
   const std::string nm(name);
-  if (nm == "coupled_fraction") {
+  if (nm == "symmetric") {
+    if (h->analyzed) return fail(h, LSA_ERR_ARG, "option symmetric must be set before lsa_analyze");
+    h->symmetric = value != 0.0;
+  } else if (nm == "coupled_fraction") {
     if (!(value >= 0.0 && value <= 1.0)) return fail(h, LSA_ERR_ARG, "coupled_fraction must lie in [0, 1]");
     h->coupled_fraction = value;
   } else if (nm == "use_graphs") {
@@ -696,6 +704,8 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
   if (int rc = need_device(h)) return rc;
   if (scalar == LSA_F64 && (alpha_im != 0.0 || beta_im != 0.0 || h->a_complex || (h->has_m && h->m_complex)))
     return fail(h, LSA_ERR_ARG, "real factorisation requested for complex data or a complex shift");
+  if (h->sym.symmetric && scalar != LSA_F64)
+    return fail(h, LSA_ERR_ARG, "the symmetric factorisation (option symmetric) is built for real FP64 only");
   LSA_API_BEGIN
   const Symbolic& sym = h->sym;
   cudaStream_t st = h->stream;

@@ -77,7 +77,7 @@ template <class T>
 __global__ void k_extend_add(const Front* __restrict__ fronts, const int* __restrict__ lvl_front, int first,
                              const int* __restrict__ child_idx, const int* __restrict__ ea_map, int slot,
                              T* __restrict__ fac, const T* __restrict__ pool_child, T* __restrict__ pool_parent,
-                             T* __restrict__ pool_cut) {
+                             T* __restrict__ pool_cut, int symmetric) {
   constexpr int CHUNK = 2048;
   __shared__ int s_map[CHUNK];
   const Front p = fronts[lvl_front[first + blockIdx.y]];
@@ -115,8 +115,10 @@ __global__ void k_extend_add(const Front* __restrict__ fronts, const int* __rest
         if (mode == 0) {
           dcol[ip] = dcol[ip] + v;
         } else if (ip < kp) {
-          T* d = Q + ip + (jp - kp) * kp;
-          *d = *d + v;
+          if (!symmetric) {   // symmetric factorisation: U12 is not stored (its mirror image went into L21 above)
+            T* d = Q + ip + (jp - kp) * kp;
+            *d = *d + v;
+          }
         } else {
           T* d = C + (ip - kp) + (jp - kp) * rp;
           *d = *d + v;
@@ -145,7 +147,7 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
 template <class T>
 __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                   int first, int j0, T* __restrict__ fac, int* __restrict__ ipiv,
-                                                  double tiny_abs, DevStats* st, int smem_bytes, int ob0) {
+                                                  double tiny_abs, DevStats* st, int smem_bytes, int ob0, int nopivot) {
   const Front f = fronts[lvl_front[first + blockIdx.x]];
   const int k = f.k;
   if (k <= j0) return;
@@ -179,7 +181,8 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
   for (int jl = 0; jl < jb; ++jl) {
     // 1. pivot search in column jl, local rows [jl, pk)
     ArgMax best{-1.0, 0x7fffffff};
-    for (int i = jl + tid; i < pcand; i += blockDim.x) {
+    // nopivot (symmetric factorisation): the diagonal entry is the pivot; only its size is checked
+    for (int i = jl + tid; i < (nopivot ? jl + 1 : pcand); i += blockDim.x) {
       double a = abs1(base[i + jl * ld]);
       if (!(a == a)) a = INFINITY;  // propagate NaN as "largest" so it is detected below
       best = better(best, ArgMax{a, i});
@@ -258,14 +261,14 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
 template <class T>
 __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                    int first, int j0, T* __restrict__ fac,
-                                                   const int* __restrict__ ipiv) {
+                                                   const int* __restrict__ ipiv, int symmetric) {
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k, r = f.r;
   if (k <= j0) return;
   const int jb = min(NB, k - j0), j1 = j0 + jb;
   const long long m = (long long)k + r;
   // logical column space: [0, j0) left of panel | [j1, k) right of panel in P | [0, r) of Q
-  const int n_left = j0, n_right = k - j1, ncols = n_left + n_right + r;
+  const int n_left = j0, n_right = k - j1, ncols = n_left + n_right + (symmetric ? 0 : r);   // symmetric: no Q
   const int cbase = blockIdx.x * 128;
   if (cbase >= ncols) return;
   T* P = fac + f.p_off;
@@ -403,10 +406,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // (inverted pivot blocks: L11^-1 strictly below the diagonal, U11^-1 on and above it): 1 = unit lower, 2 = upper,
 // applied while loading (element coordinates relative to the operand's origin).
 // EPI: 0  C -= acc ;  1  C = -acc ;  2  C = acc.
-template <bool CPLX, int AMASK = 0, int BMASK = 0, int EPI = 0>
+// BT (real only): the B operand is given TRANSPOSED and row-scaled, B[kk, n] = Bsrc[n + kk * ldb] * dg[kk * dg_stride]
+// -- the Schur complement of the symmetric factorisation, C -= L21 (D L21^T), without ever forming D L21^T.
+template <bool CPLX, int AMASK = 0, int BMASK = 0, int EPI = 0, int BT = 0>
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long long lda_r, const double* __restrict__ B,
                                           long long ldb_r, double* __restrict__ C, long long ldc_r, int Mr, int N,
-                                          int Kr, int m0, int n0) {
+                                          int Kr, int m0, int n0, const double* __restrict__ dg = nullptr,
+                                          long long dg_stride = 0) {
   constexpr int BM = 64, BN = 64, KC = 16;
   constexpr int LDA_S = BM + 4;               // conflict-free fragment reads
   constexpr int LDB_S = KC + 4;
@@ -466,7 +472,9 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int kk = k0 + b_kh + q;
-      double v = (nok && kk < Kr) ? __ldg(B + kk + (long long)(n0 + b_n) * ldb_r) : 0.0;
+      double v;
+      if (BT) v = (nok && kk < Kr) ? __ldg(B + (n0 + b_n) + (long long)kk * ldb_r) * __ldg(dg + (long long)kk * dg_stride) : 0.0;
+      else v = (nok && kk < Kr) ? __ldg(B + kk + (long long)(n0 + b_n) * ldb_r) : 0.0;
       if (BMASK != 0) {
         const int ck = CPLX ? kk >> 1 : kk, cn = n0 + b_n;
         if (BMASK == 1) v = ck > cn ? v : (ck == cn && (!CPLX || (kk & 1) == 0) && nok && kk < Kr) ? 1.0 : 0.0;
@@ -593,7 +601,7 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
 template <class T>
 __global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                     int first, int j0, int ob0, int mode, T* __restrict__ fac,
-                                                    T* __restrict__ pool, T* __restrict__ pool_cut) {
+                                                    T* __restrict__ pool, T* __restrict__ pool_cut, int symmetric) {
   constexpr bool CPLX = scalar_traits<T>::is_complex;
   constexpr int S = CPLX ? 2 : 1;
   const Front f = fronts[lvl_front[first + blockIdx.y]];
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fr
     }
     t -= nt;
     nt = tiles(R2, C3);
-    if (t < nt)
+    if (t < nt && !symmetric)   // symmetric: no U12 rows to update
       gemm_tile<CPLX>(A, m * S, (const double*)(Q + j0), (long long)k * S, (double*)(Q + j1), (long long)k * S, R2 * S, C3,
                       jb * S, (t % tm2) * 64, (t / tm2) * 64);
   } else if (mode == 2) {
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(128) k_front_gemm(const Front* __restrict__ fr
     }
     t -= nt;
     nt = tiles(R2, C2);
-    if (t < nt) {
+    if (t < nt && !symmetric) {
       const int tm2 = (R2 * S + 63) / 64;
       gemm_tile<CPLX>(A, m * S, (const double*)(Q + ob0), (long long)k * S, (double*)(Q + ob1), (long long)k * S, R2 * S, C2,
                       OB * S, (t % tm2) * 64, (t / tm2) * 64);
@@ -718,6 +726,23 @@ void launch_inv_merge(cudaStream_t st, const Front* fronts, const int* lvl_front
 template void launch_inv_merge<double>(cudaStream_t, const Front*, const int*, int, int, const long long*, int, int, double*, double*);
 template void launch_inv_merge<z128>(cudaStream_t, const Front*, const int*, int, int, const long long*, int, int, z128*, z128*);
 
+// Schur complement of the symmetric factorisation (real FP64): C -= L21 (D L21^T) with the transposed, diagonally
+// scaled B operand taken straight from L21 and diag(U11) in the tile loader.  grid: (tiles, fronts of the level).
+__global__ void __launch_bounds__(128) k_front_schur_sym(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                         int first, double* __restrict__ fac, double* __restrict__ pool,
+                                                         double* __restrict__ pool_cut) {
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
+  const int k = f.k, r = f.r;
+  if (r == 0 || k == 0) return;
+  const long long m = (long long)k + r;
+  const double* P = fac + f.p_off;
+  double* C = (f.flags ? pool_cut : pool) + f.c_off;
+  const int tm1 = (r + 63) / 64;
+  const int t = blockIdx.x;
+  if (t >= tm1 * ((r + 63) / 64)) return;
+  gemm_tile<false, 0, 0, 0, 1>(P + k, m, P + k, m, C, (long long)r, r, r, k, (t % tm1) * 64, (t / tm1) * 64, P, m + 1);
+}
+
 // stand-alone GEMM used by lsa_gemm_bench (same tile code as the front updates)
 template <bool CPLX>
 __global__ void __launch_bounds__(128) k_gemm_plain(const double* A, long long lda_r, const double* B, long long ldb_r,
@@ -757,6 +782,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
   T* fac = (T*)h.d_fac;
   T* pool[2] = {(T*)h.d_pool[0], (T*)h.d_pool[1]};
   T* pool_cut = (T*)h.d_cut_pool;
+  const int symm = sym.symmetric ? 1 : 0;   // F = L D L^T: diagonal pivots, no Q blocks (real FP64 only, checked by the caller)
   int launches = 0;
   SweepTrace tr;
   tr.begin(st);
@@ -839,7 +865,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
       for (int slot = 0; slot < maxchild; ++slot) {
         const int gx = std::max(1, std::min(64, max_rc / 8));
         k_extend_add<T><<<dim3(gx, cnt), 256, 0, st>>>(h.d_fronts, h.d_lvl_front, first, h.d_child_idx, h.d_ea_map, slot,
-                                                       fac, pool[(d + 1) & 1], pool[d & 1], pool_cut);
+                                                       fac, pool[(d + 1) & 1], pool[d & 1], pool_cut, symm);
         LSA_LAUNCH_CHECK();
         tr.mark("extend_add", d, slot, gx, cnt);
         launches++;
@@ -869,11 +895,11 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
             // the pivot candidates are the <= 128 rows of the current outer block: 128 threads cover them (one
             // row each in the scaling / rank-1 step), with half the warps to synchronise per column step
             k_panel_lu<T><<<act, 128, panel_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs,
-                                                        h.d_stats, panel_smem, ob0);
+                                                        h.d_stats, panel_smem, ob0, symm);
           }
           LSA_LAUNCH_CHECK();
           tr.mark("panel_lu", d, j0, act, 1);
-          k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv);
+          k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, symm);
           LSA_LAUNCH_CHECK();
           tr.mark("swap_trsm", d, j0, gx_cols, act);
           launches += 2;
@@ -885,7 +911,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
           }
           if (gx_tiles > 0) {
             k_front_gemm<T><<<dim3((unsigned)gx_tiles, act), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, j0, ob0, 0, fac,
-                                                                             pool[d & 1], pool_cut);
+                                                                             pool[d & 1], pool_cut, symm);
             LSA_LAUNCH_CHECK();
             tr.mark("gemm_inner", d, j0, (int)gx_tiles, act);
             launches++;
@@ -902,7 +928,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
           gx2 = std::max(gx2, tiles(m - ob1, f.k - ob1) + tiles(f.k - ob1, f.r));
         }
         if (act2 > 0 && gx2 > 0) {
-          k_front_gemm<T><<<dim3((unsigned)gx2, act2), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, ob0, 2, fac, pool[d & 1], pool_cut);
+          k_front_gemm<T><<<dim3((unsigned)gx2, act2), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, ob0, 2, fac, pool[d & 1], pool_cut, symm);
           LSA_LAUNCH_CHECK();
           tr.mark("gemm_outer", d, ob0, (int)gx2, act2);
           launches++;
@@ -915,8 +941,14 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
         if (f.r > 0 && f.k > 0)
           gx_schur = (int)std::max<long long>(gx_schur, (long long)cdiv((long long)f.r * S, 64) * cdiv(f.r, 64));
       }
-      if (gx_schur > 0) {
-        k_front_gemm<T><<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, 0, 1, fac, pool[d & 1], pool_cut);
+      if (gx_schur > 0 && symm) {
+        if constexpr (!scalar_traits<T>::is_complex)
+          k_front_schur_sym<<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, fac, pool[d & 1], pool_cut);
+        LSA_LAUNCH_CHECK();
+        tr.mark("schur_sym", d, 0, gx_schur, cnt);
+        launches++;
+      } else if (gx_schur > 0) {
+        k_front_gemm<T><<<dim3(gx_schur, cnt), 128, 0, st>>>(h.d_fronts, h.d_lvl_front, first, 0, 0, 1, fac, pool[d & 1], pool_cut, symm);
         LSA_LAUNCH_CHECK();
         tr.mark("gemm_schur", d, 0, gx_schur, cnt);
         launches++;

@@ -196,6 +196,7 @@ struct lsa_handle_impl {
   int stream_min_fronts = 96; // multi-step levels with at least this many fronts are streamed too (one CTA per front)
   bool use_clusters = true;
   double coupled_fraction = 0.5;
+  bool symmetric = false;     // option "symmetric" (before lsa_analyze): F = L D L^T, real FP64, no pivoting, half the factor store
 };
 
 }  // namespace lsa

@@ -59,6 +59,7 @@ struct Symbolic {
   double flops = 0.0;             // sum 2/3 k^3 + 2 k^2 r + 2 k r^2 (real-arithmetic flops for T = double)
   int max_k = 0, max_m = 0, max_r = 0;
   double seconds[4] = {0, 0, 0, 0};  // graph, ordering, structure, maps
+  bool symmetric = false;         // symmetric factorisation F = L D L^T: no Q (U12) blocks in the factor store
 };
 
 // Split of ONE factorisation / solve over the GPUs of a node (stage 1): proportional mapping of the
@@ -94,6 +95,7 @@ struct AnalyzeOptions {
   int nthreads = 0;
   double cap_fraction = 0.15;     // end-cap thickness (share of the diameter) of the graph bisector; 0: point pair
   double coupled_fraction = 1.0;  // share of a flagged unknown's regular neighbours eliminated before it
+  bool symmetric = false;         // lay the factor store out for F = L D L^T (P blocks only: half the entries)
 };
 
 // Host symbolic phase: nested dissection, supernode partition, row structures, assembly tree,

@@ -147,6 +147,7 @@ void partition(const Symbolic& g, int rank, int world, Symbolic& loc, Partition&
   }
   part.n_top_levels = top_levels;
 
+  if (g.symmetric) throw std::runtime_error("the symmetric factorisation is not available in the partitioned solve");
   loc = Symbolic();
   loc.n = g.n;
   loc.n_iso = g.n_iso;

@@ -1937,7 +1937,22 @@ void plan_solve(lsa_handle_impl& h, int scalar) {
   }
 }
 
-template <class T, bool H>
+// z[pivot rows] *= 1 / d  between the two sweeps of the symmetric factorisation (the inverted diagonal blocks
+// carry 1 / u_ii on their diagonal)
+template <class T>
+__global__ void __launch_bounds__(128) k_scale_diag(const Front* __restrict__ fronts, int ns, const T* __restrict__ fac,
+                                                    z128* __restrict__ z) {
+  const int s = blockIdx.x;
+  if (s >= ns) return;
+  const Front f = fronts[s];
+  const long long m = (long long)f.k + f.r;
+  const T* P = fac + f.p_off;
+  for (int i = threadIdx.x; i < f.k; i += blockDim.x) z[f.col0 + i] = P[i + (long long)i * m] * z[f.col0 + i];
+}
+
+// HU / HD: conjugate-transposed (adjoint) kernels in the up / down sweep.  <false, false>: F^-1; <true, true>: F^-H;
+// <false, true> (real symmetric factorisation F = L D L^T): L-sweep up, scaling by D^-1, L^T-sweep down.
+template <class T, bool HU, bool HD>
 static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   const Symbolic& sym = h.sym;
   cudaStream_t st = h.stream;
@@ -1952,8 +1967,8 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
   const int* d_lvl_front = h.d_lvl_front;
   auto up_off = [&](const SolveChunk& c) {
     if (c.max_r <= 0) return;
-    if (c.maxk > 512) k_up_off<T, H, 32><<<dim3(cdiv(c.max_r, 32), c.cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, z, cb);
-    else k_up_off<T, H, 8><<<dim3(cdiv(c.max_r, 32), c.cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, z, cb);
+    if (c.maxk > 512) k_up_off<T, HU, 32><<<dim3(cdiv(c.max_r, 32), c.cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, z, cb);
+    else k_up_off<T, HU, 8><<<dim3(cdiv(c.max_r, 32), c.cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, z, cb);
     LSA_LAUNCH_CHECK();
     tr.mark("up_off", c.level, 0, cdiv(c.max_r, 32), c.cnt);
     launches++;
@@ -1972,17 +1987,17 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     const SolveChunk& c = h.solve_plan[ci];
     const int d = c.level, cnt = c.cnt, first = c.first, maxk = c.maxk, max_r = c.max_r, max_m = c.max_m;
     if (cnt <= 2 * h.num_sms)
-      k_up_gather<!H, 1024><<<cnt, 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+      k_up_gather<!HU, 1024><<<cnt, 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
     else if (max_m <= 512 && cnt >= 16 * h.num_sms)
-      k_up_gather_warp<!H><<<cdiv(cnt, 8), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, cnt, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+      k_up_gather_warp<!HU><<<cdiv(cnt, 8), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, cnt, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
     else
-      k_up_gather<!H, 256><<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
+      k_up_gather<!HU, 256><<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_child_idx, h.d_ea_map, h.d_gperm, x, y, cb);
     LSA_LAUNCH_CHECK();
     tr.mark("up_gather", d, 0, cnt, 1);
     launches++;
     if constexpr (scalar_traits<T>::is_complex) {
       if (c.mode == SOLVE_STREAM) {
-        if (!launch_front_stream<H, true>(h, st, cnt, d_lvl_front, first, maxk, max_r, max_m, fac, y, z, cb, nullptr))
+        if (!launch_front_stream<HU, true>(h, st, cnt, d_lvl_front, first, maxk, max_r, max_m, fac, y, z, cb, nullptr))
           throw std::runtime_error("streamed sweep does not fit although the plan says so");
         tr.mark("up_stream", d, 0, cnt, 1);
         launches++;
@@ -1990,7 +2005,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       }
     }
     if (c.mode == SOLVE_INVERTED) {
-      launch_tri_gemv<T, H, true>(h, st, c, d_lvl_front, fac, y, z);
+      launch_tri_gemv<T, HU, true>(h, st, c, d_lvl_front, fac, y, z);
       tr.mark("up_tri", d, 0, cdiv(maxk, 32), cnt);
       launches++;
       up_off(c);
@@ -1999,7 +2014,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     // ---- pivot blocks too large to invert as a whole: chains of 128-pivot steps
     const int csize = cluster_width(cnt, max_m, h.num_sms, h.cluster_max_width);
     if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {
-      launch_sweep_slices<T, H, true>(st, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
+      launch_sweep_slices<T, HU, true>(st, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb);
       tr.mark("up_slices", d, 16, 16 * cnt, 1);
       launches++;
       up_off(c);
@@ -2011,7 +2026,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       // contribution rows deferred to one wide GEMV
       const int defer = (h.defer_cb && max_r > 0) ? 1 : 0;
       const int cs = defer ? cluster_width(cnt, maxk, h.num_sms, h.cluster_max_width) : csize;
-      sweep_cluster<T, H, true>(st, cs, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb, defer);
+      sweep_cluster<T, HU, true>(st, cs, cnt, h.d_fronts, d_lvl_front, first, fac, y, z, cb, defer);
       tr.mark("up_cluster", d, cs, cs * cnt, 1);
       launches++;
       if (defer) up_off(c);
@@ -2026,16 +2041,22 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         max_rows = std::max(max_rows, f.k + f.r - std::min(f.k, j0 + SB));
       }
       const int gx = std::max(1, cdiv(max_rows, SB));
-      if (maxk > SB) k_step<T, H, true, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
-      else k_step<T, H, true, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
+      if (maxk > SB) k_step<T, HU, true, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
+      else k_step<T, HU, true, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, y, z, cb);
       LSA_LAUNCH_CHECK();
       tr.mark("up_step", d, j0, gx, act);
       launches++;
     }
   }
+  if (HU != HD) {
+    // symmetric factorisation: D^-1 between the L-sweep and the L^T-sweep
+    if (sym.ns > 0) k_scale_diag<T><<<sym.ns, 128, 0, st>>>(h.d_fronts, sym.ns, fac, z);
+    LSA_LAUNCH_CHECK();
+    launches++;
+  }
   // decoupled 1 x 1 pivots (after the exchange of a partitioned solve: their right-hand sides are replicated rows)
   if (sym.n_iso > 0) {
-    k_solve_decoupled<T, H><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, x, y);
+    k_solve_decoupled<T, HD><<<cdiv(sym.n_iso, 256), 256, 0, st>>>(fac + sym.diag_off, sym.n_iso, x, y);
     LSA_LAUNCH_CHECK();
     launches++;
   }
@@ -2046,7 +2067,7 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
     bool streamed = false;
     if constexpr (scalar_traits<T>::is_complex) {
       if (c.mode == SOLVE_STREAM) {
-        if (!launch_front_stream<H, false>(h, st, cnt, d_lvl_front, first, maxk, maxr, maxk + maxr, fac, z, y, cb, H ? x : y))
+        if (!launch_front_stream<HD, false>(h, st, cnt, d_lvl_front, first, maxk, maxr, maxk + maxr, fac, z, y, cb, HD ? x : y))
           throw std::runtime_error("streamed sweep does not fit although the plan says so");
         tr.mark("down_stream", d, 0, cnt, 1);
         launches++;
@@ -2054,24 +2075,24 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
       }
     }
     if (!streamed && maxr > 0) {
-      if (maxr > 512) k_down_off<T, H, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
-      else k_down_off<T, H, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, H ? x : y, z);
+      if (maxr > 512) k_down_off<T, HD, 32><<<dim3(cdiv(maxk, 32), cnt), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, HD ? x : y, z);
+      else k_down_off<T, HD, 8><<<dim3(cdiv(maxk, 32), cnt), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_st_idx, fac, HD ? x : y, z);
       LSA_LAUNCH_CHECK();
       tr.mark("down_off", d, 0, cdiv(maxk, 32), cnt);
       launches++;
     }
     if (streamed) {
     } else if (c.mode == SOLVE_INVERTED) {
-      launch_tri_gemv<T, H, false>(h, st, c, d_lvl_front, fac, z, y);
+      launch_tri_gemv<T, HD, false>(h, st, c, d_lvl_front, fac, z, y);
       tr.mark("down_tri", d, 0, cdiv(maxk, 32), cnt);
       launches++;
     } else if (maxk > SB && h.use_clusters && h.cluster_slices && cnt * 16 <= h.num_sms) {
-      launch_sweep_slices<T, H, false>(st, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
+      launch_sweep_slices<T, HD, false>(st, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
       tr.mark("down_slices", d, 16, 16 * cnt, 1);
       launches++;
     } else if (maxk > SB && max_mk <= h.cluster_max_rows && h.use_clusters) {
       const int csize = cluster_width(cnt, maxk, h.num_sms, h.cluster_max_width);
-      sweep_cluster<T, H, false>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
+      sweep_cluster<T, HD, false>(st, csize, cnt, h.d_fronts, d_lvl_front, first, fac, z, y, cb);
       tr.mark("down_cluster", d, csize, csize * cnt, 1);
       launches++;
     } else {
@@ -2083,20 +2104,20 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
         }
         if (act == 0) continue;
         const int gx = std::max(1, cdiv(j0, SB));
-        if (maxk > SB) k_step<T, H, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
-        else k_step<T, H, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
+        if (maxk > SB) k_step<T, HD, false, 1024><<<dim3(gx, act), 1024, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
+        else k_step<T, HD, false, 256><<<dim3(gx, act), 256, 0, st>>>(h.d_fronts, d_lvl_front, first, j0, fac, z, y, cb);
         LSA_LAUNCH_CHECK();
         tr.mark("down_step", d, j0, gx, act);
         launches++;
       }
     }
-    if (H) {
+    if (HD) {
       k_level_unpermute<<<cnt, 256, 0, st>>>(h.d_fronts, d_lvl_front, first, h.d_gperm, y, x);
       LSA_LAUNCH_CHECK();
       launches++;
     }
   }
-  if (H) {
+  if (HD) {
     if (sym.n_iso > 0) k_unpermute<<<cdiv(sym.n_iso, 256), 256, 0, st>>>(y, x, h.d_gperm, sym.n_iso);
     LSA_LAUNCH_CHECK();
   } else {
@@ -2109,8 +2130,12 @@ static void solve_impl(lsa_handle_impl& h, z128* x, int* n_kernels) {
 
 template <class T>
 void solve_permuted(lsa_handle_impl& h, int trans, z128* x, int* n_kernels) {
-  if (trans == LSA_OP_H) solve_impl<T, true>(h, x, n_kernels);
-  else solve_impl<T, false>(h, x, n_kernels);
+  if (h.sym.symmetric) {
+    // real symmetric F = L D L^T: F^-1 = F^-T = F^-H, one sweep pair with the L blocks only
+    if constexpr (!scalar_traits<T>::is_complex) solve_impl<T, false, true>(h, x, n_kernels);
+    else throw std::runtime_error("symmetric factorisation with a complex factor");
+  } else if (trans == LSA_OP_H) solve_impl<T, true, true>(h, x, n_kernels);
+  else solve_impl<T, false, false>(h, x, n_kernels);
 }
 template void solve_permuted<double>(lsa_handle_impl&, int, z128*, int*);
 template void solve_permuted<z128>(lsa_handle_impl&, int, z128*, int*);

@@ -416,6 +416,7 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
   double t0 = now();
   sym = Symbolic();
   sym.n = n;
+  sym.symmetric = opt.symmetric;
   Graph g = build_graph(n, rowptr, colidx);
   double t1 = now();
   sym.seconds[0] = t1 - t0;
@@ -591,9 +592,10 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
     f.p_off = off;
     off = align(off + m * k);
     f.q_off = off;
-    off = align(off + k * r);
-    sym.nnz_lu += k * k + 2 * k * r;
-    sym.flops += (2.0 / 3.0) * k * k * k + 2.0 * k * k * r + 2.0 * k * r * r;
+    if (!opt.symmetric) off = align(off + k * r);   // symmetric: U12 = D L21^T is never stored
+    sym.nnz_lu += opt.symmetric ? k * k + k * r : k * k + 2 * k * r;
+    sym.flops += opt.symmetric ? (2.0 / 3.0) * k * k * k + 1.0 * k * k * r + 2.0 * k * r * r
+                               : (2.0 / 3.0) * k * k * k + 2.0 * k * k * r + 2.0 * k * r * r;
     sym.max_k = std::max(sym.max_k, f.k);
     sym.max_r = std::max(sym.max_r, f.r);
     sym.max_m = std::max(sym.max_m, f.k + f.r);

@@ -78,6 +78,7 @@ class iKSP:  # noqa: N801
         self._handle: _lib.Handle | None = None
         self._factor_gen = -1
         self._values_ref = None
+        self._sym_failed = False
         self._its = 0
         self._rnorm = float("nan")
         self._sol: iPETScVector | None = None
@@ -96,6 +97,7 @@ class iKSP:  # noqa: N801
             raise NotImplementedError("a preconditioning matrix different from A is not built on the B200 backend")
         self._A = A
         self._factor_gen = -1
+        self._sym_failed = False
 
     def set_type(self, ksp_type: KSPType) -> None:
         self._type = KSPType(ksp_type)
@@ -131,9 +133,12 @@ class iKSP:  # noqa: N801
             raise NotImplementedError(f"KSP type '{self._type}' is not built on the B200 backend")
         t0 = time.perf_counter()
         coords = self._opts["coords"]
-        extra = ("linear", self._opts["leaf_size"], self._opts["device"],
-                 None if coords is None else np.ascontiguousarray(coords).tobytes()[:64])
         A = _raw_csr(self._A)
+        # PCCHOLESKY on real data: symmetric L D L^T at half the factor storage (falls back to LU on a vanishing pivot)
+        use_sym = (self._pc is PreconditionerType.CHOLESKY and not self._sym_failed
+                   and not np.iscomplexobj((A if A is not None else _as_csr(self._A)).data))
+        extra = ("linear", use_sym, self._opts["leaf_size"], self._opts["device"],
+                 None if coords is None else np.ascontiguousarray(coords).tobytes()[:64])
         h = _SYM_CACHE.lookup(A, None, extra) if A is not None and len(_SYM_CACHE) else None
         if h is None:
             A = _as_csr(self._A)
@@ -144,6 +149,8 @@ class iKSP:  # noqa: N801
         cplx = np.iscomplexobj(A.data)
         if h is None:
             h = _lib.Handle(n, self._opts["device"])
+            if use_sym:
+                h.set_option("symmetric", 1)
             h.analyze(A.indptr, A.indices, None, None, leaf_size=self._opts["leaf_size"], coords=coords,
                       order_last=(A.diagonal() == 0).astype(np.uint8), nthreads=self._opts["nthreads"])
             _SYM_CACHE.store(A, None, extra, h)
@@ -154,9 +161,12 @@ class iKSP:  # noqa: N801
         if h is not self._handle or h.gen_factor != self._factor_gen or self._values_ref is not A.data:
             h.set_values(A.data, None)
             fs = h.factor(1.0, 0.0, _lib.LSA_C128 if cplx else _lib.LSA_F64, self._opts["tiny_pivot"])
+            if use_sym and (fs.n_perturbed > 0 or fs.max_multiplier > 1e8):
+                self._sym_failed = True
+                return self._ensure_factor()
             self._factor_gen = h.gen_factor
             self._values_ref = A.data
-            self.stats.update(factor_seconds=fs.seconds, factor_flops=fs.flops, n_perturbed=int(fs.n_perturbed),
+            self.stats.update(symmetric_factorisation=use_sym, factor_seconds=fs.seconds, factor_flops=fs.flops, n_perturbed=int(fs.n_perturbed),
                               max_multiplier=fs.max_multiplier, scalar="c128" if cplx else "f64")
         self._handle = h
         return h, A, cplx

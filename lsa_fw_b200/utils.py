@@ -374,7 +374,7 @@ class iEpsSolver:  # noqa: N801
         # backend options (extensions; all optional)
         self._opts = dict(leaf_size=64, coords=None, refine_steps=0, tiny_pivot=1e-13, seed=0, device=0,
                           purify=True, nthreads=0, v0=None, force_complex=False, coupled_fraction=0.5,
-                          growth_limit=1e6, device_values=None, partition=None)
+                          growth_limit=1e6, device_values=None, partition=None, symmetric="auto")
         self._adjoint = False
         self._handle: _lib.Handle | None = None
         self._factor_key = None
@@ -449,7 +449,9 @@ class iEpsSolver:  # noqa: N801
         ((A_vals, M_vals) already resident on the GPU, in CSR entry order: torch CUDA tensors or any object
         with `__cuda_array_interface__` / `__dlpack__`; the host copies in A / M are then only used for
         their pattern), partition ("auto": split this factorisation / eigensolve over the GPUs of the initialised
-        torch.distributed group, one process per GPU, every rank making the same calls -- lsa_fw_b200/partitioned.py)."""
+        torch.distributed group, one process per GPU, every rank making the same calls -- lsa_fw_b200/partitioned.py),
+        symmetric ("auto": real symmetric problems -- HEP / GHEP with st_pc_type CHOLESKY, real data, real shift -- are
+        factored as L D L^T at half the factor storage; True / False force / forbid it)."""
         unknown = set(kw) - set(self._opts)
         if unknown:
             raise TypeError(f"unknown backend option(s): {sorted(unknown)}")
@@ -556,7 +558,20 @@ class iEpsSolver:  # noqa: N801
         else:
             t0 = time.perf_counter()
             coords = self._opts["coords"]
-            extra_base = (self._opts["leaf_size"],
+            # symmetric factorisation L D L^T (the reference's GHEP + CHOLESKY use, Elasticity/utils.py:139-155): real data,
+            # real shift, a Hermitian problem type, one GPU
+            a0, m0 = _raw_csr(self._A), (_raw_csr(self._M) if self._M is not None else None)
+            real_data = (a0 is None or not np.iscomplexobj(a0.data)) and (m0 is None or not np.iscomplexobj(m0.data)) \
+                and (a0 is not None or not np.iscomplexobj(_as_csr(self._A).data))
+            sym_ok = (real_data and sigma.imag == 0.0 and not self._opts["force_complex"] and self._partition_world()[1] == 1
+                      and needs_factor)
+            want = self._opts["symmetric"]
+            if want is True and not sym_ok:
+                raise ValueError("symmetric=True needs real matrices, a real shift and a single GPU")
+            use_sym = bool(sym_ok and (want is True or (want == "auto" and self._problem_type in _HERMITIAN
+                                                        and self._pc_type == "cholesky")))
+            stats["symmetric_factorisation"] = use_sym
+            extra_base = (use_sym, self._opts["leaf_size"],
                           None if coords is None else hashlib.blake2b(np.ascontiguousarray(coords).tobytes(), digest_size=16).hexdigest(),
                           self._opts["device"], self._opts["coupled_fraction"], self._st_type.value, self._partition_world(),
                           self._M is None)
@@ -603,6 +618,8 @@ class iEpsSolver:  # noqa: N801
                 rank, world = self._partition_world()
                 h = _lib.Handle(n, self._opts["device"], rank, world)
                 h.set_option("coupled_fraction", self._opts["coupled_fraction"])
+                if use_sym:
+                    h.set_option("symmetric", 1)
                 h.analyze(A.indptr, A.indices, None if M is None else M.indptr, None if M is None else M.indices,
                           leaf_size=self._opts["leaf_size"], coords=coords, order_last=ol,
                           nthreads=self._opts["nthreads"])
@@ -650,6 +667,13 @@ class iEpsSolver:  # noqa: N801
                     fs = h.factor(1.0, -sigma, scalar, self._opts["tiny_pivot"])
                 else:
                     fs = h.factor(0.0, 1.0, scalar, 0.0)  # plain M^-1: an exactly singular M must raise
+                if use_sym and (fs.n_perturbed > stats["nullspace_dimension"] or fs.max_multiplier > self._opts["growth_limit"]):
+                    # L D L^T without pivoting met a vanishing pivot / element growth (indefinite shift): general LU
+                    logger.warning("symmetric factorisation unstable (%d pivots replaced, growth %.2e); using the general LU",
+                                   fs.n_perturbed, fs.max_multiplier)
+                    self._opts["symmetric"] = False
+                    self._factor_key = None
+                    return self.solve()
                 if sinvert and fs.n_perturbed > stats["nullspace_dimension"] and self._opts["coupled_fraction"] < 1.0:
                     # tiny pivots were replaced: the cheap placement of the zero-diagonal unknowns was not
                     # enough for this pencil -> redo the analysis with the robust rule and factor again

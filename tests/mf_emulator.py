@@ -301,3 +301,78 @@ class PartEmulator(Emulator):
         out = np.empty_like(full)
         out[self.perm] = full
         return out
+
+
+class SymEmulator(Emulator):
+    """Symmetric factorisation F = L D L^T (option "symmetric": real FP64, diagonal pivots, no Q blocks), following the
+    symmetric branches of factor.cu / solve.cu: the scatter maps skip the U12 entries, extend-add skips the Q part,
+    the Schur complement is C -= L21 (D L21^T), a solve is L-sweep, D^-1, L^T-sweep."""
+
+    def factor(self, a_vals, m_vals, alpha, beta, dtype=np.float64, pivot_block=128):
+        fac = np.zeros(self.fac_size, dtype=dtype)
+        ok = self.a_dst >= 0
+        fac[self.a_dst[ok]] = alpha * a_vals[ok]
+        if m_vals is not None:
+            okm = self.m_dst >= 0
+            np.add.at(fac, self.m_dst[okm], beta * m_vals[okm])
+        self.fac = fac
+        ns = self.ns
+        self.cb = [None] * ns
+        self.children = [[] for _ in range(ns)]
+        for s in range(ns):
+            if self.parent[s] >= 0:
+                self.children[self.parent[s]].append(s)
+        for s in np.argsort(-self.level, kind="stable"):
+            k, r = int(self.k[s]), int(self.r[s])
+            m = k + r
+            P = fac[self.p_off[s]: self.p_off[s] + m * k].reshape((m, k), order="F")
+            Cb = np.zeros((r, r), dtype=dtype)
+            for c in self.children[s]:
+                mp = self.ea_map[self.st_ptr[c]: self.st_ptr[c + 1]]
+                cbc = self.cb[c]
+                top = mp < k
+                bot = ~top
+                P[np.ix_(mp, mp[top])] += cbc[:, top]
+                Cb[np.ix_(mp[bot] - k, mp[bot] - k)] += cbc[np.ix_(bot, bot)]
+                self.cb[c] = None
+            for j in range(k):                       # no pivoting: the diagonal entry is the pivot
+                P[j + 1:, j] /= P[j, j]
+                P[j + 1:, j + 1:] -= np.outer(P[j + 1:, j], P[j, j + 1:])
+            d = np.diag(P[:k, :k]).copy()
+            Cb -= P[k:, :] @ (d[:, None] * P[k:, :].T)
+            self.cb[s] = Cb
+        if self.n_iso:
+            self.diag = fac[self.diag_off: self.diag_off + self.n_iso]
+
+    def solve(self, b, trans="N"):
+        x = np.asarray(b, dtype=complex)[self.perm].copy()
+        if self.n_iso:
+            x[: self.n_iso] = x[: self.n_iso] / self.diag
+        up = np.argsort(-self.level, kind="stable")
+        cbv = [None] * self.ns
+        for s in up:
+            k, r, P, _ = self._front_p(s)
+            c0 = self.sn_ptr[s]
+            bot = np.zeros(r, dtype=complex)
+            for c in self.children[s]:
+                mp = self.ea_map[self.st_ptr[c]: self.st_ptr[c + 1]]
+                top = mp < k
+                x[c0 + mp[top]] += cbv[c][top]
+                bot[mp[~top] - k] += cbv[c][~top]
+            xt = sla.solve_triangular(P[:k, :k], x[c0: c0 + k], lower=True, unit_diagonal=True)
+            bot -= P[k:, :] @ xt
+            x[c0: c0 + k] = xt / np.diag(P[:k, :k])
+            cbv[s] = bot
+        for s in up[::-1]:
+            k, r, P, _ = self._front_p(s)
+            c0 = self.sn_ptr[s]
+            anc = x[self.st_idx[self.st_ptr[s]: self.st_ptr[s + 1]]]
+            x[c0: c0 + k] = sla.solve_triangular(P[:k, :k].T, x[c0: c0 + k] - P[k:, :].T @ anc, lower=False, unit_diagonal=True)
+        out = np.empty_like(x)
+        out[self.perm] = x
+        return out
+
+    def _front_p(self, s):
+        k, r = int(self.k[s]), int(self.r[s])
+        m = k + r
+        return k, r, self.fac[self.p_off[s]: self.p_off[s] + m * k].reshape((m, k), order="F"), None

@@ -976,3 +976,94 @@ def test_attached_pressure_nullspace_is_projected_not_pinned():
     lam_a = np.array([p[0] for p in ea.solve()])
     mine_a = lam_a[np.abs(lam_a - 1.0) > 1e-6]
     assert _match(np.conj(mine_a[:3]), phys) < EIG_RTOL
+
+
+def _poisson3d(n1: int) -> sp.csr_matrix:
+    t = sp.diags([-np.ones(n1 - 1), 2.0 * np.ones(n1), -np.ones(n1 - 1)], [-1, 0, 1])
+    e = sp.identity(n1)
+    return (sp.kron(sp.kron(t, e), e) + sp.kron(sp.kron(e, t), e) + sp.kron(sp.kron(e, e), t)).tocsr()
+
+
+def test_symmetric_ldlt_factor_and_sweeps():
+    """Row f4: the symmetric L D L^T variant (no U blocks, no pivoting; `Elasticity/utils.py:139-155` asks PETSc for
+    CHOLESKY).  3-D Poisson + mass shift: half the factor storage of the LU, same solutions, N = T = H."""
+    import scipy.sparse.linalg as spla
+
+    K = _poisson3d(22)
+    n = K.shape[0]
+    Mm = sp.identity(n, format="csr") * 0.5
+    Mm = sp.csr_matrix((np.full(K.nnz, 0.0), K.indices, K.indptr), shape=K.shape) + Mm   # same pattern family, diagonal mass
+    Mm.sort_indices()
+    rng = np.random.default_rng(12)
+    b = rng.standard_normal(n)
+    stats = {}
+    for symm in (0, 1):
+        h = _lib.Handle(n)
+        if symm:
+            h.set_option("symmetric", 1)
+        info = h.analyze(K.indptr, K.indices, Mm.indptr, Mm.indices, leaf_size=32)
+        h.set_values(K.data, Mm.data)
+        for sigma in (-0.3, 0.013):          # definite, and a shift just above the lowest modes (indefinite, no growth here)
+            fs = h.factor(1.0, -sigma, _lib.LSA_F64, 0.0)
+            assert fs.n_perturbed == 0
+            C = (K - sigma * Mm).tocsc()
+            ref = spla.splu(C).solve(b)
+            for trans in (_lib.LSA_OP_N, _lib.LSA_OP_T, _lib.LSA_OP_H):
+                x = h.solve(b.astype(complex), trans)
+                assert np.abs(x.imag).max() == 0.0
+                assert np.linalg.norm(C @ x.real - b) / np.linalg.norm(b) < 1e-12
+                assert np.linalg.norm(x.real - ref) / np.linalg.norm(ref) < 1e-10
+            bc = b + 1j * rng.standard_normal(n)     # real factor, complex right-hand side
+            xc = h.solve(bc)
+            assert np.linalg.norm(C @ xc - bc) / np.linalg.norm(bc) < 1e-12
+        stats[symm] = (info.nnz_lu, fs.flops, info.max_front)
+        if symm:
+            with pytest.raises(Exception):
+                h.factor(1.0, 0.1j, _lib.LSA_C128, 0.0)      # the symmetric mode is real FP64 only
+        h.close()
+    assert stats[1][0] < 0.62 * stats[0][0] and stats[1][1] < 0.7 * stats[0][1]
+    assert stats[1][2] > 256                                  # root separator beyond one 128-pivot panel
+
+
+def test_ghep_with_cholesky_uses_the_symmetric_factor_and_matches_lu():
+    """GHEP + SINVERT at 0 + CHOLESKY (the reference's elasticity modal solve, `Elasticity/utils.py:139-155`) runs on the
+    L D L^T factor; eigenpairs equal those of the general LU path.  An indefinite shift that breaks the unpivoted
+    factorisation falls back to LU."""
+    L.clear_symbolic_cache()
+    pm = pencils.membrane_pencil(40, 40, 1.0, 0.83)
+    out = {}
+    for pc in (L.PreconditionerType.LU, L.PreconditionerType.CHOLESKY):
+        cfg = L.EigensolverConfig(num_eig=12, problem_type=L.iEpsProblemType.GHEP, atol=1e-12, max_it=200)
+        es = L.EigenSolver(L.iPETScMatrix(pm.A), L.iPETScMatrix(pm.M), cfg, check_hermitian=False)
+        es.solver.set_st_type(L.iSTType.SINVERT)
+        es.solver.set_target(0.0)
+        es.solver.set_st_pc_type(pc)
+        pairs = es.solve()
+        lam = np.array([v for v, _ in pairs][:12])
+        X = np.stack([_vec(v) for _, v in pairs[:12]], axis=1)
+        assert O.north_star_residuals(pm.A, pm.M, lam, X).max() < RESID_BAR
+        out[pc] = (np.sort(lam.real), dict(es.solver.stats))
+    assert out[L.PreconditionerType.CHOLESKY][1]["symmetric_factorisation"] is True
+    assert out[L.PreconditionerType.LU][1]["symmetric_factorisation"] is False
+    assert out[L.PreconditionerType.CHOLESKY][1]["nnz_lu"] < 0.65 * out[L.PreconditionerType.LU][1]["nnz_lu"]
+    a, b = out[L.PreconditionerType.LU][0], out[L.PreconditionerType.CHOLESKY][0]
+    assert np.abs(a - b).max() <= EIG_RTOL * np.abs(a).max()
+    # linear seam: PREONLY + CHOLESKY
+    K = (pm.A + 0.5 * pm.M).tocsr()
+    rhs = np.random.default_rng(3).standard_normal(pm.n)
+    ksp = L.iKSP(L.iPETScMatrix(K))
+    ksp.set_type(L.KSPType.PREONLY)
+    ksp.set_preconditioner(L.PreconditionerType.CHOLESKY)
+    x = ksp.solve(L.iPETScVector.from_array(rhs.copy())).as_array()
+    assert ksp.stats["symmetric_factorisation"] is True
+    assert np.linalg.norm(K @ x - rhs) / np.linalg.norm(rhs) < 1e-12
+    # a saddle-point matrix (zero diagonal block) cannot be factored without pivoting: the solver falls back to LU
+    pc = pencils.assemble_pencil((10, 6), (4.0, 2.0), re=20.0, baseflow=pencils.zero_flow())
+    S = ((pc.A + pc.A.T) * 0.5).tocsr()
+    S.sort_indices()
+    rhs = np.random.default_rng(4).standard_normal(pc.n)
+    ksp = L.iKSP(L.iPETScMatrix(S))
+    ksp.set_type(L.KSPType.PREONLY)
+    ksp.set_preconditioner(L.PreconditionerType.CHOLESKY)
+    x = ksp.solve(L.iPETScVector.from_array(rhs.copy())).as_array()
+    assert np.linalg.norm(S @ x - rhs) / np.linalg.norm(rhs) < 1e-10

@@ -82,6 +82,36 @@ def test_symbolic_structures_drive_a_correct_multifrontal_lu(name, geo, kw, use_
     assert np.linalg.norm(C.conj().T @ em.solve(b, "H") - b) / np.linalg.norm(b) < 1e-11
 
 
+def test_symmetric_layout_drives_a_correct_ldlt():
+    """Row f4 host logic: option "symmetric" lays the factor store out without Q blocks (nnz_lu = sum k^2 + k r), the
+    scatter maps drop the U12 entries, and the structures drive a correct L D L^T factorisation + solve (membrane
+    stiffness / mass pencil, the reference's GHEP + Cholesky use, `Elasticity/utils.py:139-155`)."""
+    from mf_emulator import SymEmulator
+
+    pm = pencils.membrane_pencil(14, 10)
+    n = pm.n
+    sizes = {}
+    for symm in (0, 1):
+        h = _lib.Handle(n, device=-1)
+        h.set_option("symmetric", symm)
+        info = h.analyze(pm.A.indptr, pm.A.indices, pm.M.indptr, pm.M.indices, leaf_size=24)
+        k, r = h.symbolic_array("front_k").astype(float), h.symbolic_array("front_r").astype(float)
+        sizes[symm] = (info.nnz_lu, info.factor_entries, info.flops_real)
+        assert info.nnz_lu == int((k * k + (1 if symm else 2) * k * r).sum()) + info.n_decoupled
+    assert sizes[1][1] < 0.75 * sizes[0][1] and sizes[1][2] < sizes[0][2]
+    a_dst = h.symbolic_array("a_dst")
+    assert (a_dst < 0).sum() > 0 and (a_dst >= 0).sum() >= pm.A.nnz // 2
+    sigma = 0.0
+    em = SymEmulator(h, n)
+    em.factor(pm.A.data, pm.M.data, 1.0, -sigma)
+    C = (pm.A - sigma * pm.M).tocsc()
+    b = np.random.default_rng(0).standard_normal(n)
+    x = em.solve(b)
+    assert np.linalg.norm(C @ x - b) / np.linalg.norm(b) < 1e-11
+    with pytest.raises(_lib.LsaError):
+        h.set_option("symmetric", 0)          # after the analysis: too late
+
+
 def test_symbolic_counters_and_pattern_reuse():
     pc = pencils.assemble_pencil((20, 10), (6.0, 2.0), re=40.0)
     h = _lib.Handle(pc.n, device=-1)
