@@ -605,13 +605,15 @@ def main() -> None:
     barrier()
     t0 = time.perf_counter()
     d2h_total = 0
+    e2e_uploads = []
     for i in my_steps:
         es, pairs, d2h = e2e_step(i)
         d2h_total += d2h
+        e2e_uploads.append(round(es.solver.stats.get("upload_seconds", 0.0), 4))
     barrier()
     my_e2e_s = time.perf_counter() - t0
     st = es.solver.stats
-    h2d = (pc.A.nnz + pc.M.nnz) * 8
+    h2d = pc.A.nnz * 8 + (0 if st.get("m_upload_skipped") else pc.M.nnz * 8)   # M is uploaded once per sweep
     lam0 = complex(pairs[0][0]) if pairs else None
     es.solver.release()
     del A_cs, M_c
@@ -711,6 +713,7 @@ def main() -> None:
             "symbolic": {"seconds": t_symbolic, "phases": list(info.seconds), "fronts": info.n_fronts, "levels": info.n_levels,
                          "nnz_lu": int(info.nnz_lu), "flops_real": info.flops_real, "max_front": info.max_front,
                          "max_pivots": info.max_pivots, "decoupled": info.n_decoupled},
+            "e2e_upload_s_by_step": e2e_uploads, "e2e_host_timing": st.get("host_timing"), "e2e_inputs_not_page_locked": int(_lib.pinned_fallbacks),
             "e2e_phases": {k: st.get(k) for k in ("symbolic_seconds", "upload_seconds", "factor_seconds", "eigs_seconds", "fetch_seconds", "total_seconds")},
             "parity": {"resid_direct_max": resid_direct, "resid_adjoint_max": resid_adj, "nconv_min": nconv_min,
                        "lambda0": [lam0.real, lam0.imag] if lam0 else None,

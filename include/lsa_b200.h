@@ -258,6 +258,10 @@ int lsa_sync(lsa_handle* h);
  * lsa_analyze takes as `order_last`, without a pass over all nnz entries per solve of a sweep. */
 int lsa_host_diag_is_zero(int32_t n, const void* indptr, int32_t indptr_is_64, const int32_t* colidx, const void* vals,
                           int32_t scalar, const int32_t* rows, int32_t nrows, uint8_t* out);
+/* Host helper (no GPU): 1 when the two byte ranges are identical, 0 otherwise (a few threads; the exact comparison of
+ * a candidate sparsity pattern with a cached one -- ~0.5 GB of indices for config 3 -- that replaces SLEPc's
+ * "same nonzero pattern" promise of a sweep). */
+int lsa_host_equal(const void* a, const void* b, uint64_t bytes);
 /* Page-locked host memory for result buffers (eigenvectors leave the device at PCIe speed instead of through
  * the driver's bounce buffers; VecGetArray of the reference hands out host memory as well, Solver/utils.py:280-297).
  * Plain cudaHostAlloc / cudaFreeHost; no handle needed. */

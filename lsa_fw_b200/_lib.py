@@ -102,14 +102,17 @@ _PINNED_POOL: dict[int, list[int]] = {}
 _PINNED_POOL_MAX_BYTES = 4 << 30
 _PINNED_MIN_BYTES = 1 << 20
 _pinned_pool_bytes = 0
+pinned_fallbacks = 0      # big requests that could not be page-locked (served from pageable memory)
 
 
 class _PinnedBlock:
-    """Owner of one page-locked allocation; exposes it through the array interface."""
+    """Owner of one page-locked allocation; exposes it through the array interface in the element type asked for (an
+    array over it must not look like a small view of a much larger base: SciPy's CSR constructor copies those)."""
 
-    def __init__(self, ptr: int, nbytes: int) -> None:
+    def __init__(self, ptr: int, nbytes: int, dtype: np.dtype) -> None:
         self.ptr, self.nbytes = ptr, nbytes
-        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        self.size = nbytes // dtype.itemsize
+        self.__array_interface__ = {"shape": (self.size,), "typestr": dtype.str, "data": (ptr, False), "version": 3}
 
 
 def _pinned_release(lib, ptr: int, nbytes: int) -> None:
@@ -127,7 +130,7 @@ def _pinned_release(lib, ptr: int, nbytes: int) -> None:
 def pinned_empty(shape, dtype, lib=None) -> np.ndarray:
     """`np.empty(shape, dtype)` on page-locked memory (plain pageable memory for small arrays or when the
     allocation fails)."""
-    global _pinned_pool_bytes
+    global _pinned_pool_bytes, pinned_fallbacks
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
     if nbytes < _PINNED_MIN_BYTES:
@@ -140,11 +143,12 @@ def pinned_empty(shape, dtype, lib=None) -> np.ndarray:
     else:
         p = C.c_void_p()
         if lib.lsa_host_alloc(C.c_uint64(nbytes), C.byref(p)) != LSA_OK or not p.value:
+            pinned_fallbacks += 1
             return np.empty(shape, dtype=dtype)
         ptr = p.value
-    blk = _PinnedBlock(ptr, nbytes)
+    blk = _PinnedBlock(ptr, nbytes, dtype)
     weakref.finalize(blk, _pinned_release, lib, ptr, nbytes)
-    return np.asarray(blk).view(dtype).reshape(shape)
+    return np.asarray(blk).reshape(shape)
 
 
 def pinned_pool_clear() -> None:
@@ -201,6 +205,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.lsa_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.lsa_sync.argtypes = [vp]
     lib.lsa_host_diag_is_zero.argtypes = [i32, vp, i32, vp, vp, i32, vp, i32, vp]
+    lib.lsa_host_equal.argtypes = [vp, vp, C.c_uint64]
     lib.lsa_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
     lib.lsa_host_free.argtypes = [C.c_void_p]
     lib.lsa_dense_schur.argtypes = [vp, i32, vp, i32, vp, i32, i32, dbl, dbl]
@@ -213,7 +218,7 @@ EXPORTS = [
     "lsa_version", "lsa_create", "lsa_destroy", "lsa_last_error", "lsa_analyze", "lsa_set_option", "lsa_symbolic_info_get",
     "lsa_symbolic_array", "lsa_set_values", "lsa_factor", "lsa_solve", "lsa_spmv", "lsa_eigs",
     "lsa_get_eigenvalues", "lsa_get_eigenvectors", "lsa_get_residuals", "lsa_get_counters", "lsa_sync",
-    "lsa_host_alloc", "lsa_host_free", "lsa_dense_schur", "lsa_gemm_bench",
+    "lsa_host_alloc", "lsa_host_free", "lsa_host_equal", "lsa_dense_schur", "lsa_gemm_bench",
     "lsa_bilinear", "lsa_set_nullspace", "lsa_host_diag_is_zero", "lsa_set_partition", "lsa_nccl_load", "lsa_nccl_unique_id", "lsa_set_comm", "lsa_partition_info_get",
 ]
 
@@ -282,6 +287,15 @@ def diag_is_zero(mat, rows: np.ndarray | None = None) -> np.ndarray:
     if rc != LSA_OK:
         raise LsaError(rc, "lsa_host_diag_is_zero failed")
     return out
+
+
+def host_equal(a: np.ndarray, b: np.ndarray) -> bool:
+    """Exact equality of two contiguous arrays of one dtype and shape (`lsa_host_equal`: a few threads)."""
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    if not (a.flags.c_contiguous and b.flags.c_contiguous):
+        return bool(np.array_equal(a, b))
+    return bool(load().lsa_host_equal(a.ctypes.data, b.ctypes.data, a.nbytes))
 
 
 def nccl_unique_id() -> bytes:
@@ -401,7 +415,10 @@ class Handle:
             mp = m_vals.ctypes.data
         self.gen_factor += 1
         self.gen_result += 1
+        import time as _t
+        t0 = _t.perf_counter()
         self.check(self.lib.lsa_set_values(self._h, a_vals.ctypes.data, a_sc, mp, m_sc, 0))
+        self.set_values_seconds = _t.perf_counter() - t0
         if m_vals is not None:
             self.m_token = None     # set by callers that want to skip an unchanged M next time (utils.py)
 

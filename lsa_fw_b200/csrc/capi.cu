@@ -1,4 +1,5 @@
 // C ABI of the B200 shift-and-invert eigensolve backend (see include/lsa_b200.h).
+#include <omp.h>
 #include <algorithm>
 #include <cstring>
 #include <numeric>
@@ -296,6 +297,10 @@ void lsa_destroy(lsa_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_device(*h);
     comm_destroy(h->comm);
+    for (int q = 0; q < 2; ++q) {
+      if (h->h_stage[q]) cudaFreeHost(h->h_stage[q]);
+      if (h->ev_stage[q]) cudaEventDestroy(h->ev_stage[q]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -660,6 +665,42 @@ int64_t lsa_symbolic_array(const lsa_handle* h, const char* name, void* out, int
   return LSA_ERR_ARG;
 }
 
+// Pageable host memory -> device: the driver stages such copies through one bounce buffer at ~10 GB/s.  Here a few
+// threads copy 16 MiB pieces into two page-locked staging buffers while the previous piece is on the wire.
+static bool is_page_locked(const void* p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static void upload_pageable(lsa_handle_impl& h, void* dst, const void* src, size_t len) {
+  constexpr size_t PIECE = 16u << 20;
+  if (!h.h_stage[0]) {
+    for (int q = 0; q < 2; ++q) {
+      LSA_CUDA(cudaHostAlloc(&h.h_stage[q], PIECE, cudaHostAllocDefault));
+      LSA_CUDA(cudaEventCreateWithFlags(&h.ev_stage[q], cudaEventDisableTiming));
+    }
+  }
+  const int nth = std::max(1, std::min(omp_get_max_threads(), 8));
+  size_t off = 0;
+  for (int it = 0; off < len; ++it, off += PIECE) {
+    const int q = it & 1;
+    const size_t n = std::min(PIECE, len - off);
+    if (it >= 2) LSA_CUDA(cudaEventSynchronize(h.ev_stage[q]));   // the piece sent from this buffer two rounds ago has left
+    const size_t part = ((n + nth - 1) / nth + 63) & ~(size_t)63;
+#pragma omp parallel for schedule(static) num_threads(nth)
+    for (int t = 0; t < nth; ++t) {
+      const size_t b = std::min(n, (size_t)t * part), e = std::min(n, b + part);
+      if (e > b) std::memcpy((char*)h.h_stage[q] + b, (const char*)src + off + b, e - b);
+    }
+    LSA_CUDA(cudaMemcpyAsync((char*)dst + off, h.h_stage[q], n, cudaMemcpyHostToDevice, h.stream));
+    LSA_CUDA(cudaEventRecord(h.ev_stage[q], h.stream));
+  }
+}
+
 int lsa_set_values(lsa_handle* h, const void* a_vals, int32_t a_scalar, const void* m_vals, int32_t m_scalar,
                    int32_t on_device) {
   if (!h || !h->analyzed || !a_vals) return LSA_ERR_ARG;
@@ -676,7 +717,10 @@ int lsa_set_values(lsa_handle* h, const void* a_vals, int32_t a_scalar, const vo
     const size_t bytes = std::max<size_t>(16, (size_t)nnz * (cplx ? 16 : 8));
     if (!dst) LSA_CUDA(cudaMalloc(&dst, bytes));
     flag = cplx;
-    if (nnz > 0) LSA_CUDA(cudaMemcpyAsync(dst, src, (size_t)nnz * (cplx ? 16 : 8), kind, st));
+    const size_t len = (size_t)nnz * (cplx ? 16 : 8);
+    if (nnz == 0) return;
+    if (!on_device && len >= (size_t)(32u << 20) && !is_page_locked(src)) upload_pageable(*h, dst, src, len);
+    else LSA_CUDA(cudaMemcpyAsync(dst, src, len, kind, st));
   };
   // m_vals == NULL on a handle that already holds values: M is kept (a Reynolds sweep changes A only)
   const bool new_m = h->has_m && m_vals;
@@ -1022,7 +1066,9 @@ int lsa_host_diag_is_zero(int32_t n, const void* indptr, int32_t indptr_is_64, c
   const int32_t* p32 = (const int32_t*)indptr;
   const int64_t* p64 = (const int64_t*)indptr;
   const int cnt = rows ? nrows : n;
-#pragma omp parallel for schedule(static)
+  // a few hundred thousand binary searches: a handful of threads (waking a whole many-core team costs more than the work)
+  const int nth = std::max(1, std::min({omp_get_max_threads(), 16, cnt / 4096 + 1}));
+#pragma omp parallel for schedule(static) num_threads(nth)
   for (int q = 0; q < cnt; ++q) {
     const int i = rows ? rows[q] : q;
     const long long b = indptr_is_64 ? p64[i] : p32[i], e = indptr_is_64 ? p64[i + 1] : p32[i + 1];
@@ -1036,6 +1082,21 @@ int lsa_host_diag_is_zero(int32_t n, const void* indptr, int32_t indptr_is_64, c
     out[q] = zero;
   }
   return LSA_OK;
+}
+
+int lsa_host_equal(const void* a, const void* b, uint64_t bytes) {
+  if (a == b || bytes == 0) return 1;
+  if (!a || !b) return 0;
+  const uint64_t chunk = 1u << 20;
+  const long long nchunks = (long long)((bytes + chunk - 1) / chunk);
+  const int nth = (int)std::max<long long>(1, std::min<long long>({(long long)omp_get_max_threads(), 12LL, nchunks / 8 + 1}));
+  int differ = 0;
+#pragma omp parallel for schedule(static) num_threads(nth) reduction(| : differ)
+  for (long long c = 0; c < nchunks; ++c) {
+    const uint64_t o = (uint64_t)c * chunk, len = std::min<uint64_t>(chunk, bytes - o);
+    if (std::memcmp((const char*)a + o, (const char*)b + o, len) != 0) differ |= 1;
+  }
+  return differ ? 0 : 1;
 }
 
 int lsa_host_alloc(uint64_t bytes, void** ptr) {

@@ -92,6 +92,38 @@ __global__ void k_extend_add(const Front* __restrict__ fronts, const int* __rest
   T* Q = fac + p.q_off;
   T* C = (p.flags ? pool_cut : pool_parent) + p.c_off;
   const long long kp = p.k, rp = p.r, mp = kp + rp;
+  if (symmetric) {
+    // Symmetric factorisation: only the lower triangle of a contribution block is computed (tile rows >= tile columns)
+    // and only entries on / below the diagonal are read.  The map is increasing, so they land on / below the parent's
+    // diagonal: L21 and the lower triangle of C directly; inside the pivot block (factored as a full square) the
+    // mirror image is written as well.  U12 is not stored.
+    for (int base = 0; base < rc; base += CHUNK) {
+      const int len = min(CHUNK, rc - base);
+      __syncthreads();
+      for (int t = threadIdx.x; t < len; t += blockDim.x) s_map[t] = map[base + t];
+      __syncthreads();
+      for (int b = blockIdx.x; b < base + len; b += gridDim.x) {
+        const long long jp = map[b];
+        const T* col = cb + (long long)b * rc + base;
+        for (int t = max(b - base, 0) + threadIdx.x; t < len; t += blockDim.x) {
+          const long long ip = s_map[t];
+          const T v = col[t];
+          if (jp < kp) {
+            T* d = P + jp * mp + ip;
+            *d = *d + v;
+            if (ip < kp && ip != jp) {
+              T* u = P + ip * mp + jp;
+              *u = *u + v;
+            }
+          } else {
+            T* d = C + (ip - kp) + (jp - kp) * rp;
+            *d = *d + v;
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int base = 0; base < rc; base += CHUNK) {
     const int len = min(CHUNK, rc - base);
     __syncthreads();
@@ -115,10 +147,8 @@ __global__ void k_extend_add(const Front* __restrict__ fronts, const int* __rest
         if (mode == 0) {
           dcol[ip] = dcol[ip] + v;
         } else if (ip < kp) {
-          if (!symmetric) {   // symmetric factorisation: U12 is not stored (its mirror image went into L21 above)
-            T* d = Q + ip + (jp - kp) * kp;
-            *d = *d + v;
-          }
+          T* d = Q + ip + (jp - kp) * kp;
+          *d = *d + v;
         } else {
           T* d = C + (ip - kp) + (jp - kp) * rp;
           *d = *d + v;
@@ -440,6 +470,8 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
   const int a_row = tid & 63, a_kg = tid >> 6;  // 2 groups of stored columns
   const int b_n = tid >> 1, b_kh = (tid & 1) * 8;
   double ra[A_PER_T], rb[8];
+  double rd[BT ? 8 : 1];   // BT: diagonal scale factors, applied when the chunk goes to shared memory (after the MMA loop,
+                           // so that the loads stay in flight behind the arithmetic)
   // K range of the tile: a triangular operand (mask) is zero outside it -- lower B: k >= n0, upper B: k < n0 + BN,
   // lower A: k < m0 + BM, upper A: k >= m0 (real-view indices; complex rows / K come in pairs, so the same bounds
   // scaled by the view factor) -- which halves the work of the block-inverse merges
@@ -473,8 +505,10 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
     for (int q = 0; q < 8; ++q) {
       const int kk = k0 + b_kh + q;
       double v;
-      if (BT) v = (nok && kk < Kr) ? __ldg(B + (n0 + b_n) + (long long)kk * ldb_r) * __ldg(dg + (long long)kk * dg_stride) : 0.0;
-      else v = (nok && kk < Kr) ? __ldg(B + kk + (long long)(n0 + b_n) * ldb_r) : 0.0;
+      if (BT) {
+        v = (nok && kk < Kr) ? __ldg(B + (n0 + b_n) + (long long)kk * ldb_r) : 0.0;
+        rd[q] = kk < Kr ? __ldg(dg + (long long)kk * dg_stride) : 0.0;
+      } else v = (nok && kk < Kr) ? __ldg(B + kk + (long long)(n0 + b_n) * ldb_r) : 0.0;
       if (BMASK != 0) {
         const int ck = CPLX ? kk >> 1 : kk, cn = n0 + b_n;
         if (BMASK == 1) v = ck > cn ? v : (ck == cn && (!CPLX || (kk & 1) == 0) && nok && kk < Kr) ? 1.0 : 0.0;
@@ -487,7 +521,7 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, long lon
 #pragma unroll
     for (int q = 0; q < A_PER_T; ++q) As[buf][(a_kg * A_PER_T + q) * LDA_S + a_row] = ra[q];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) Bs[buf][b_n * LDB_S + b_kh + q] = rb[q];
+    for (int q = 0; q < 8; ++q) Bs[buf][b_n * LDB_S + b_kh + q] = BT ? rb[q] * rd[q] : rb[q];
   };
 
   if (kc_first < nchunks) {
@@ -737,10 +771,15 @@ __global__ void __launch_bounds__(128) k_front_schur_sym(const Front* __restrict
   const long long m = (long long)k + r;
   const double* P = fac + f.p_off;
   double* C = (f.flags ? pool_cut : pool) + f.c_off;
+  // lower triangle of tiles only: t -> (tm, tn), tn <= tm
   const int tm1 = (r + 63) / 64;
   const int t = blockIdx.x;
-  if (t >= tm1 * ((r + 63) / 64)) return;
-  gemm_tile<false, 0, 0, 0, 1>(P + k, m, P + k, m, C, (long long)r, r, r, k, (t % tm1) * 64, (t / tm1) * 64, P, m + 1);
+  if (t >= tm1 * (tm1 + 1) / 2) return;
+  int tm = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while (tm * (tm + 1) / 2 > t) --tm;
+  while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
+  const int tn = t - tm * (tm + 1) / 2;
+  gemm_tile<false, 0, 0, 0, 1>(P + k, m, P + k, m, C, (long long)r, r, r, k, tm * 64, tn * 64, P, m + 1);
 }
 
 // stand-alone GEMM used by lsa_gemm_bench (same tile code as the front updates)
@@ -938,8 +977,10 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
       int gx_schur = 0;
       for (int q = first; q < first + cnt; ++q) {
         const Front& f = sym.fronts[sym.lvl_front[q]];
-        if (f.r > 0 && f.k > 0)
-          gx_schur = (int)std::max<long long>(gx_schur, (long long)cdiv((long long)f.r * S, 64) * cdiv(f.r, 64));
+        if (f.r > 0 && f.k > 0) {
+          const long long tr_ = cdiv(f.r, 64);
+          gx_schur = (int)std::max<long long>(gx_schur, symm ? tr_ * (tr_ + 1) / 2 : (long long)cdiv((long long)f.r * S, 64) * tr_);
+        }
       }
       if (gx_schur > 0 && symm) {
         if constexpr (!scalar_traits<T>::is_complex)

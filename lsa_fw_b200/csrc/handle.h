@@ -65,6 +65,8 @@ struct lsa_handle_impl {
   int n = 0;
   int device = -1;
   cudaStream_t stream = nullptr;
+  void* h_stage[2] = {nullptr, nullptr};        // page-locked staging buffers for uploads from pageable memory
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   std::string err;
 
   // ---- host symbolic

@@ -594,7 +594,7 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
     f.q_off = off;
     if (!opt.symmetric) off = align(off + k * r);   // symmetric: U12 = D L21^T is never stored
     sym.nnz_lu += opt.symmetric ? k * k + k * r : k * k + 2 * k * r;
-    sym.flops += opt.symmetric ? (2.0 / 3.0) * k * k * k + 1.0 * k * k * r + 2.0 * k * r * r
+    sym.flops += opt.symmetric ? (2.0 / 3.0) * k * k * k + 1.0 * k * k * r + 1.0 * k * r * r
                                : (2.0 / 3.0) * k * k * k + 2.0 * k * k * r + 2.0 * k * r * r;
     sym.max_k = std::max(sym.max_k, f.k);
     sym.max_r = std::max(sym.max_r, f.r);

@@ -166,7 +166,7 @@ def _sample_digest(arr: np.ndarray) -> bytes:
 
 def _same_index_arrays(a: np.ndarray, b: np.ndarray) -> bool:
     """Exact equality of two index arrays: identity first, then a strided sample, then the full comparison
-    (one streaming pass, ~0.1 s per 10^8 entries -- an order of magnitude cheaper than a cryptographic hash)."""
+    (one streaming pass by a few threads, `lsa_host_equal` -- far cheaper than a cryptographic hash)."""
     if a is b:
         return True
     if a.shape != b.shape:
@@ -174,7 +174,7 @@ def _same_index_arrays(a: np.ndarray, b: np.ndarray) -> bool:
     st = max(1, a.size // 4096)
     if not np.array_equal(a[::st], b[::st]):
         return False
-    return bool(np.array_equal(a, b))
+    return _lib.host_equal(a, b)
 
 
 class _SymbolicCache:
@@ -592,14 +592,22 @@ class iEpsSolver:  # noqa: N801
 
             # fast path: the raw arrays against the cached canonical patterns (a hit proves canonical form)
             h = None
+            ht = stats.setdefault("host_timing", {})
+            ht["prologue"] = time.perf_counter() - t0
             A, M = _raw_csr(self._A), (_raw_csr(self._M) if self._M is not None else None)
             if A is not None and (self._M is None or M is not None) and len(_SYM_CACHE):
                 Mx = M
                 if Mx is None and sinvert:
                     Mx = _identity_csr(n)
+                t1 = time.perf_counter()
                 ol = order_last_of(A, Mx)
+                ht["order_last"] = time.perf_counter() - t1
+                t1 = time.perf_counter()
                 extra = extra_base + (hashlib.blake2b(ol.tobytes(), digest_size=16).hexdigest(),)
+                ht["order_last_digest"] = time.perf_counter() - t1
+                t1 = time.perf_counter()
                 h = _SYM_CACHE.lookup(A, Mx, extra)
+                ht["lookup"] = time.perf_counter() - t1
                 if h is not None:
                     M = Mx
             if h is None:
@@ -647,12 +655,14 @@ class iEpsSolver:  # noqa: N801
             if dv is not None:
                 h.set_values_device(dv[0], None if M is None else dv[1])
             elif M is not None and self._M is not None and _same_values(h.m_token, M):
+                ht["m_token_check"] = time.perf_counter() - t0
                 h.set_values(A.data, None)          # M unchanged since the last upload to this handle: A only
                 stats["m_upload_skipped"] = True
             else:
                 h.set_values(A.data, None if M is None else M.data)
                 h.m_token = _values_token(M) if (M is not None and self._M is not None) else None
             stats["upload_seconds"] = time.perf_counter() - t0
+            ht["set_values_native"] = getattr(h, "set_values_seconds", None)
             sigma_fact = sigma
             # attached nullspace (constant pressure of an enclosed flow, FEM/operators.py:534-545): projected out of
             # every operator application; the vanishing pivot of the singular shifted operator is replaced

@@ -305,8 +305,10 @@ class PartEmulator(Emulator):
 
 class SymEmulator(Emulator):
     """Symmetric factorisation F = L D L^T (option "symmetric": real FP64, diagonal pivots, no Q blocks), following the
-    symmetric branches of factor.cu / solve.cu: the scatter maps skip the U12 entries, extend-add skips the Q part,
-    the Schur complement is C -= L21 (D L21^T), a solve is L-sweep, D^-1, L^T-sweep."""
+    symmetric branches of factor.cu / solve.cu: the scatter maps skip the U12 entries, extend-add reads only the lower
+    triangle of a contribution block (mirroring it inside the parent's pivot block) and skips the Q part, the Schur
+    complement C -= L21 (D L21^T) is formed on / below the diagonal only (the strict upper triangle is poisoned here to
+    prove nothing reads it), a solve is L-sweep, D^-1, L^T-sweep."""
 
     def factor(self, a_vals, m_vals, alpha, beta, dtype=np.float64, pivot_block=128):
         fac = np.zeros(self.fac_size, dtype=dtype)
@@ -329,17 +331,22 @@ class SymEmulator(Emulator):
             Cb = np.zeros((r, r), dtype=dtype)
             for c in self.children[s]:
                 mp = self.ea_map[self.st_ptr[c]: self.st_ptr[c + 1]]
-                cbc = self.cb[c]
+                assert np.all(np.diff(mp) > 0)          # increasing map: lower triangle lands in the lower triangle
+                cbc = np.tril(self.cb[c])               # entries on / below the diagonal only
+                assert np.isfinite(cbc).all()
                 top = mp < k
                 bot = ~top
                 P[np.ix_(mp, mp[top])] += cbc[:, top]
+                nt = int(top.sum())
+                P[np.ix_(mp[top], mp[top])] += np.tril(cbc[:nt, :nt], -1).T      # mirror inside the pivot block
                 Cb[np.ix_(mp[bot] - k, mp[bot] - k)] += cbc[np.ix_(bot, bot)]
                 self.cb[c] = None
             for j in range(k):                       # no pivoting: the diagonal entry is the pivot
                 P[j + 1:, j] /= P[j, j]
                 P[j + 1:, j + 1:] -= np.outer(P[j + 1:, j], P[j, j + 1:])
             d = np.diag(P[:k, :k]).copy()
-            Cb -= P[k:, :] @ (d[:, None] * P[k:, :].T)
+            Cb -= np.tril(P[k:, :] @ (d[:, None] * P[k:, :].T))
+            Cb[np.triu_indices(r, 1)] = np.nan
             self.cb[s] = Cb
         if self.n_iso:
             self.diag = fac[self.diag_off: self.diag_off + self.n_iso]

@@ -1021,7 +1021,7 @@ def test_symmetric_ldlt_factor_and_sweeps():
             with pytest.raises(Exception):
                 h.factor(1.0, 0.1j, _lib.LSA_C128, 0.0)      # the symmetric mode is real FP64 only
         h.close()
-    assert stats[1][0] < 0.62 * stats[0][0] and stats[1][1] < 0.7 * stats[0][1]
+    assert stats[1][0] < 0.62 * stats[0][0] and stats[1][1] < 0.62 * stats[0][1]
     assert stats[1][2] > 256                                  # root separator beyond one 128-pivot panel
 
 
@@ -1045,7 +1045,7 @@ def test_ghep_with_cholesky_uses_the_symmetric_factor_and_matches_lu():
         out[pc] = (np.sort(lam.real), dict(es.solver.stats))
     assert out[L.PreconditionerType.CHOLESKY][1]["symmetric_factorisation"] is True
     assert out[L.PreconditionerType.LU][1]["symmetric_factorisation"] is False
-    assert out[L.PreconditionerType.CHOLESKY][1]["nnz_lu"] < 0.65 * out[L.PreconditionerType.LU][1]["nnz_lu"]
+    assert out[L.PreconditionerType.CHOLESKY][1]["nnz_lu"] < 0.7 * out[L.PreconditionerType.LU][1]["nnz_lu"]
     a, b = out[L.PreconditionerType.LU][0], out[L.PreconditionerType.CHOLESKY][0]
     assert np.abs(a - b).max() <= EIG_RTOL * np.abs(a).max()
     # linear seam: PREONLY + CHOLESKY

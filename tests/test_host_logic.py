@@ -515,3 +515,53 @@ def test_select_mode_and_biorthonormal_scaling():
     assert L.select_mode(pairs, 0.25 - 0.4j)[1] == "y" and L.select_mode(pairs, np.conj(0.25 - 0.4j))[1] == "z"
     with pytest.raises(RuntimeError):
         L.select_mode([], 0.0)
+
+
+def test_page_locked_arrays_survive_the_scipy_constructor_without_a_copy():
+    """Arrays handed out by `pinned_empty` must not look like small views of a larger base: SciPy's CSR constructor
+    prunes (copies) those, which silently moves the values back to pageable memory (5x slower uploads)."""
+    import ctypes as C
+
+    from lsa_fw_b200 import _lib
+
+    keep = []
+
+    class FakeLib:      # page-locked allocation stands in: plain host memory
+        @staticmethod
+        def lsa_host_alloc(nbytes, ref):
+            buf = C.create_string_buffer(int(nbytes.value))
+            keep.append(buf)
+            ref._obj.value = C.addressof(buf)
+            return _lib.LSA_OK
+
+        @staticmethod
+        def lsa_host_free(ptr):
+            return _lib.LSA_OK
+
+    n = 1 << 18
+    for dtype in (np.float64, np.complex128):
+        a = _lib.pinned_empty((n,), dtype, lib=FakeLib)
+        assert a.ctypes.data == C.addressof(keep[-1]) and a.dtype == dtype and a.shape == (n,)
+        a[...] = 1.0
+        m = sp.csr_matrix((a, np.arange(n, dtype=np.int32) % 1000, np.arange(0, n + 1, n // 1000, dtype=np.int32)), shape=(1000, 1000))
+        assert m.data.ctypes.data == a.ctypes.data
+        carrier = L.iPETScMatrix(m)
+        assert carrier.as_scipy_array().data.ctypes.data == a.ctypes.data
+    b = _lib.pinned_empty((n // 8, 8), np.complex128, lib=FakeLib)
+    assert b.shape == (n // 8, 8) and b.flags.c_contiguous
+
+
+def test_host_equal_is_an_exact_comparison():
+    from lsa_fw_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 1 << 30, size=(1 << 22) + 12345, dtype=np.int32)
+    b = a.copy()
+    assert _lib.host_equal(a, b) and _lib.host_equal(a, a)
+    for pos in (0, 1 << 20, a.size - 1):
+        b[pos] ^= 1
+        assert not _lib.host_equal(a, b)
+        b[pos] ^= 1
+    assert _lib.host_equal(a, b)
+    assert not _lib.host_equal(a, b[:-1]) and not _lib.host_equal(a, b.astype(np.int64))
+    assert _lib.host_equal(a[::2], b[::2]) and _lib.host_equal(a[:0], b[:0])
