@@ -91,6 +91,13 @@ typedef struct {
   double sigma_re, sigma_im;    /* shift / target                                        */
   uint64_t seed;                /* start vector: splitmix64 Gaussian stream, OP applied once */
   const double* v0;             /* optional host start vector (n complex); NULL = seeded random */
+  int32_t b_mode;               /* Hermitian-definite problems (EPS_GHEP, M Hermitian positive (semi)definite):
+                                   0: Euclidean inner products, unit 2-norm vectors (general problems);
+                                   1: as 0, returned vectors scaled to unit M-norm on the device (x^H M x = 1);
+                                   2: M-inner products throughout -- M-orthonormal Krylov basis (symmetric
+                                      Lanczos / Krylov-Schur: the projected matrix is Hermitian, as SLEPc's
+                                      EPSKrylovSchur does for GHEP), M-orthonormal returned vectors.  Needs M. */
+  int32_t pad_;
 } lsa_eigs_params;
 
 typedef struct {

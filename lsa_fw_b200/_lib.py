@@ -60,7 +60,7 @@ class EigsParams(C.Structure):
         ("nev", C.c_int32), ("ncv", C.c_int32), ("max_restarts", C.c_int32), ("which", C.c_int32),
         ("transform", C.c_int32), ("adjoint", C.c_int32), ("purify", C.c_int32), ("refine_steps", C.c_int32),
         ("tol", C.c_double), ("sigma_re", C.c_double), ("sigma_im", C.c_double), ("seed", C.c_uint64),
-        ("v0", C.POINTER(C.c_double)),
+        ("v0", C.POINTER(C.c_double)), ("b_mode", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -503,7 +503,7 @@ class Handle:
         return complex(out[0])
 
     def eigs(self, *, nev, ncv, tol, max_restarts, which, transform, sigma=0.0, adjoint=False, purify=True,
-             refine_steps=0, seed=0, v0=None) -> EigsResult:
+             refine_steps=0, seed=0, v0=None, b_mode=0) -> EigsResult:
         p = EigsParams()
         p.nev, p.ncv, p.max_restarts = int(nev), int(ncv), int(max_restarts)
         p.which = WHICH[which] if isinstance(which, str) else int(which)
@@ -512,6 +512,7 @@ class Handle:
         sigma = complex(sigma)
         p.sigma_re, p.sigma_im = sigma.real, sigma.imag
         p.seed = int(seed)
+        p.b_mode = int(b_mode)
         keep = None
         if v0 is not None:
             keep = np.ascontiguousarray(v0, dtype=np.complex128)

@@ -69,6 +69,7 @@ void free_device(lsa_handle_impl& h) {
     h.pool_capacity_bytes[q] = 0;
   }
   dfree(h.d_x); dfree(h.d_w); dfree(h.d_t); dfree(h.d_t2); dfree(h.d_cb); dfree(h.d_io); dfree(h.d_V); dfree(h.d_S); dfree(h.d_Q);
+  dfree(h.d_U); dfree(h.d_mw); dfree(h.d_bn); h.U_cols = 0;
   dfree(h.d_part); dfree(h.d_npart); dfree(h.d_h); dfree(h.d_brow); dfree(h.d_ywork); dfree(h.d_r1); dfree(h.d_r2);
   dfree(h.d_r3); dfree(h.d_Xp); dfree(h.d_ns); dfree(h.d_flag); dfree(h.d_refine); dfree(h.d_wn2); dfree(h.d_wn2b); dfree(h.d_ipart); dfree(h.d_rr); dfree(h.d_theta); dfree(h.d_resid); dfree(h.d_X);
   h.ns_count = 0;
@@ -996,9 +997,21 @@ int lsa_eigs(lsa_handle* h, const lsa_eigs_params* p, lsa_eigs_result* out) {
   if (p->which < 1 || p->which > 9) return fail(h, LSA_ERR_ARG, "unsupported `which`");
   if (std::min(p->ncv, h->n) > 256)
     return fail(h, LSA_ERR_ARG, "ncv > 256: the device orthogonalisation / Rayleigh-Ritz kernels hold at most 256 basis columns");
+  if (p->b_mode < 0 || p->b_mode > 2) return fail(h, LSA_ERR_ARG, "b_mode must be 0, 1 or 2");
+  if (p->b_mode == 2 && (!h->has_m || h->partitioned || p->adjoint))
+    return fail(h, LSA_ERR_ARG, "b_mode = 2 (M-inner products) needs M, a single GPU and the direct problem");
   LSA_API_BEGIN
   const int ncv = std::max(1, std::min(p->ncv, h->n));
   ensure_krylov(*h, ncv);
+  if (p->b_mode == 2 && h->U_cols < ncv + 1) {
+    dfree(h->d_U);
+    h->d_U = dalloc<z128>((size_t)h->n * (size_t)(ncv + 1));
+    h->U_cols = ncv + 1;
+  }
+  if (p->b_mode != 0 && !h->d_mw) {
+    h->d_mw = dalloc<z128>((size_t)h->n);
+    h->d_bn = dalloc<z128>(2);
+  }
   if (p->adjoint || p->refine_steps > 0) ensure_transposes(*h);
   h->last_params = *p;
   h->last_params.v0 = nullptr;

@@ -141,6 +141,10 @@ struct lsa_handle_impl {
   double* d_npart = nullptr;  // partial squared norms
   z128* d_h = nullptr;     // CGS coefficients
   z128* d_brow = nullptr;
+  z128* d_U = nullptr;     // M-inner-product mode: U = M V, n x (ncv + 1)
+  z128* d_mw = nullptr;    // M w work vector (n)
+  z128* d_bn = nullptr;    // w^H M w (one complex number)
+  int U_cols = 0;
   z128* d_ywork = nullptr;
   z128* d_r1 = nullptr;    // refinement / residual scratch vectors
   z128* d_r2 = nullptr;

@@ -902,6 +902,39 @@ static void orthonormalize(lsa_handle_impl& h, z128* V, long long ldv, int jj, z
   LSA_LAUNCH_CHECK();
 }
 
+// beta^2 = w^H M w (real part) -> h.d_bn, with M w left in h.d_mw.  Single GPU.
+static void m_norm2(lsa_handle_impl& h, const z128* w) {
+  const int n = h.n;
+  if (h.has_m) spmv(h, h.dM, false, w, h.d_mw);
+  else k_copy<<<cdiv(n, 256), 256, 0, h.stream>>>(n, w, h.d_mw);
+  const int rpb = std::max(1024, (int)(((long long)n + 591) / 592 + 31) / 32 * 32);
+  const int nblk = cdiv(n, rpb);
+  launch_dots(h.stream, nblk, n, 1, w, n, h.d_mw, h.d_part, 256, rpb, nullptr, nullptr);
+  k_reduce_h<<<1, 256, 0, h.stream>>>(1, nblk, h.d_part, 256, h.d_bn, h.d_bn + 1, 0, nullptr);
+}
+
+// M-inner-product Gram-Schmidt (Hermitian-definite problems, b_mode = 2): U = M V is kept next to V, so
+// V^H M w = U^H w costs no extra product with M.  w <- w - V (U^H w), twice (the refinement criterion of the
+// Euclidean path compares 2-norms and does not carry over; two passes are what SLEPc's symmetric Krylov-Schur
+// ends up doing on shift-and-invert operators anyway), then beta = sqrt(w^H M w), out_v = w / beta,
+// out_u = M w / beta.
+static void orthonormalize_m(lsa_handle_impl& h, const z128* V, const z128* U, long long ldv, int jj, z128* w, z128* out_v,
+                             z128* out_u, z128* scol, int rows_per_block, int ldp, int* flag, int step) {
+  cudaStream_t st = h.stream;
+  const int n = h.n;
+  const int nblk = cdiv(n, rows_per_block);
+  for (int pass = 0; pass < 2; ++pass) {
+    launch_dots(st, nblk, n, jj, U, ldv, w, h.d_part, ldp, rows_per_block, nullptr, nullptr);
+    k_reduce_h<<<cdiv(jj, 8), 256, 0, st>>>(jj, nblk, h.d_part, ldp, h.d_h, scol ? scol : h.d_brow, pass, nullptr);
+    k_update<<<cdiv(n, 256), 256, 0, st>>>(n, jj, V, ldv, h.d_h, w, nullptr, nullptr);
+  }
+  m_norm2(h, w);
+  const double* b2 = reinterpret_cast<const double*>(h.d_bn);
+  k_normalize<<<cdiv(n, 256), 256, 0, st>>>(n, w, out_v, b2, 1, nullptr, scol ? scol + jj : nullptr, scol, scol ? jj : 0, flag, step);
+  k_normalize<<<cdiv(n, 256), 256, 0, st>>>(n, h.d_mw, out_u, b2, 1, nullptr, nullptr, nullptr, 0, nullptr, 0);
+  LSA_LAUNCH_CHECK();
+}
+
 // a^H w on the device (single GPU): the tall-skinny dot kernel with a one-column "basis"
 z128 dot_conj(lsa_handle_impl& h, const z128* a, const z128* w) {
   const int n = h.n;
@@ -1047,12 +1080,13 @@ struct EventTimer {
 
 // w = OP v   (all vectors in the permuted ordering)
 static void apply_op(lsa_handle_impl& h, const lsa_eigs_params& p, const z128* v, z128* w, EventTimer& t_spmv,
-                     EventTimer& t_solve) {
+                     EventTimer& t_solve, const z128* mv = nullptr) {
   const bool adj = p.adjoint != 0;
   const int n = h.n, blocks = cdiv(n, 256);
   if (p.transform == LSA_ST_SINVERT) {
     size_t e = t_spmv.begin();
-    if (h.has_m) spmv(h, adj ? h.dMt : h.dM, adj, v, w);
+    if (mv) k_copy<<<blocks, 256, 0, h.stream>>>(n, mv, w);   // M v is at hand (M-inner-product mode keeps U = M V)
+    else if (h.has_m) spmv(h, adj ? h.dMt : h.dM, adj, v, w);
     else {
       k_copy<<<blocks, 256, 0, h.stream>>>(n, v, w);
       replicated_rows_to_partial(h, w);   // the sweep expects replicated rows that SUM to the value over the GPUs
@@ -1120,11 +1154,20 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
   }
   int n_applies = 0, n_arnoldi = 0;
   long long sum_cols = 0;
+  const bool bmode = p.b_mode == 2;   // M-inner products (Hermitian-definite problem)
+  z128* U = h.d_U;
   apply_op(h, p, h.d_x, h.d_w, t_spmv, t_solve);
   n_applies++;
   // (flag: a NaN / Inf start vector or first operator application is reported through flag[1]; the step number is
   // out of range, so a vanishing norm here does not register as an Arnoldi breakdown)
-  normalize_vector(h, h.d_w, V, nullptr, nullptr, nullptr, 0, h.d_flag, 0x7fffffff);
+  if (bmode) {
+    m_norm2(h, h.d_w);
+    const double* b2 = reinterpret_cast<const double*>(h.d_bn);
+    k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, V, b2, 1, nullptr, nullptr, nullptr, 0, h.d_flag, 0x7fffffff);
+    k_normalize<<<blocks, 256, 0, st>>>(n, h.d_mw, U, b2, 1, nullptr, nullptr, nullptr, 0, nullptr, 0);
+  } else {
+    normalize_vector(h, h.d_w, V, nullptr, nullptr, nullptr, 0, h.d_flag, 0x7fffffff);
+  }
 
   int nconv = 0, keep = 0, restarts = 0, breakdown = 0, m_last = ncv;
   bool invariant = false;
@@ -1134,7 +1177,7 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
     int m = ncv;
     // ---- Arnoldi expansion with CGS2
     for (int j = keep; j < ncv; ++j) {
-      apply_op(h, p, V + (long long)j * ldv, h.d_w, t_spmv, t_solve);
+      apply_op(h, p, V + (long long)j * ldv, h.d_w, t_spmv, t_solve, bmode ? U + (long long)j * ldv : nullptr);
       n_applies++;
       const size_t e = t_ortho.begin();
       const int jj = j + 1;  // orthogonalise against columns 0..j
@@ -1143,7 +1186,11 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
       z128* scol = S + (long long)j * ld;
       // classical Gram-Schmidt, second pass only when the criterion asks for it (decided on the device: the
       // pass-2 kernels return at once when the flag is clear)
-      orthonormalize(h, V, ldv, jj, h.d_w, V + (long long)(j + 1) * ldv, scol, gs_rows_per_block(n, jj, h.num_sms), ldp, false, h.d_flag, j);
+      if (bmode)
+        orthonormalize_m(h, V, U, ldv, jj, h.d_w, V + (long long)(j + 1) * ldv, U + (long long)(j + 1) * ldv, scol,
+                         gs_rows_per_block(n, jj, h.num_sms), ldp, h.d_flag, j);
+      else
+        orthonormalize(h, V, ldv, jj, h.d_w, V + (long long)(j + 1) * ldv, scol, gs_rows_per_block(n, jj, h.num_sms), ldp, false, h.d_flag, j);
       h.launch_count += 9;  // spmv + 8 orthogonalisation kernels
       t_ortho.end(e);
     }
@@ -1185,21 +1232,27 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
     // ---- restart: V[:, nconv_old:keep] = V[:, nconv_old:m] Q[nconv_old:m, nconv_old:keep]
     e = t_restart.begin();
     const int mp = m - nconv_old, nk = keep - nconv_old;
-    if (nk > 0)
+    if (nk > 0) {
       basis_gemm(h, mp, nk, V + (long long)nconv_old * ldv, ldv, Q + nconv_old + (long long)nconv_old * ncv, ncv,
                  V + (long long)nconv_old * ldv, ldv);
+      if (bmode)   // U = M V follows the same rotation
+        basis_gemm(h, mp, nk, U + (long long)nconv_old * ldv, ldv, Q + nconv_old + (long long)nconv_old * ncv, ncv,
+                   U + (long long)nconv_old * ldv, ldv);
+    }
     const bool done = rp.last || nconv >= nev;
     if (!done && invariant) {
       // the invariant subspace found so far is locked (keep == m); continue from a fresh random
       // direction orthogonal to it (SLEPc does the same after a breakdown)
       z128* vnew = V + (long long)keep * ldv;
       k_randn<<<blocks, 256, 0, st>>>(h.d_w, n, p.seed + 7919ULL * (unsigned long long)restarts);
-      orthonormalize(h, V, ldv, keep, h.d_w, vnew, nullptr, gs_rows_per_block(n, keep, h.num_sms), ldp, true, nullptr, 0);
+      if (bmode) orthonormalize_m(h, V, U, ldv, keep, h.d_w, vnew, U + (long long)keep * ldv, nullptr, gs_rows_per_block(n, keep, h.num_sms), ldp, nullptr, 0);
+      else orthonormalize(h, V, ldv, keep, h.d_w, vnew, nullptr, gs_rows_per_block(n, keep, h.num_sms), ldp, true, nullptr, 0);
       h_flag[0] = 0x7fffffff;
       LSA_CUDA(cudaMemcpyAsync(h.d_flag, h_flag, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
       LSA_LAUNCH_CHECK();
     } else if (!done && keep != m) {
       k_copy<<<blocks, 256, 0, st>>>(n, V + (long long)m * ldv, V + (long long)keep * ldv);
+      if (bmode) k_copy<<<blocks, 256, 0, st>>>(n, U + (long long)m * ldv, U + (long long)keep * ldv);
     }
     t_restart.end(e);
     if (done) break;
@@ -1233,9 +1286,14 @@ void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out
         n_applies++;
         k_norm2_part<<<blocks, 256, 0, st>>>(n, h.d_w, h.d_npart);
         k_normalize<<<blocks, 256, 0, st>>>(n, h.d_w, xi, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
-      } else {
+      } else if (p.b_mode == 0) {
         k_norm2_part<<<blocks, 256, 0, st>>>(n, xi, h.d_npart);
         k_normalize<<<blocks, 256, 0, st>>>(n, xi, xi, h.d_npart, blocks, nullptr, nullptr, nullptr, 0, nullptr, 0);
+      }
+      if (p.b_mode != 0) {
+        // Hermitian-definite problem: unit M-norm, x^H M x = 1 (SLEPc's normalisation for EPS_GHEP)
+        m_norm2(h, xi);
+        k_normalize<<<blocks, 256, 0, st>>>(n, xi, xi, reinterpret_cast<const double*>(h.d_bn), 1, nullptr, nullptr, nullptr, 0, nullptr, 0);
       }
       {
         const int nb = std::min(blocks, 256);

@@ -441,7 +441,7 @@ def assemble_pencil(
     )
 
 
-def _apply_identity_rows_cols(mat: sp.csr_matrix, dofs: np.ndarray) -> sp.csr_matrix:
+def _apply_identity_rows_cols(mat: sp.csr_matrix, dofs: np.ndarray, diagonal: float = 1.0) -> sp.csr_matrix:
     """Rows and columns `dofs` removed from the pattern and replaced by a unit diagonal
     (`FEM/operators.py:483-486`).  Purely structural: no entry is dropped because of its VALUE, so the pattern
     is the same for every Reynolds number / base flow (one symbolic analysis per mesh)."""
@@ -454,7 +454,7 @@ def _apply_identity_rows_cols(mat: sp.csr_matrix, dofs: np.ndarray) -> sp.csr_ma
     keep = ~(drop[coo.row] | drop[coo.col])
     rows = np.concatenate([coo.row[keep], dofs])
     cols = np.concatenate([coo.col[keep], dofs])
-    vals = np.concatenate([coo.data[keep], np.ones(len(dofs))])
+    vals = np.concatenate([coo.data[keep], np.full(len(dofs), float(diagonal))])
     return sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
 
 
@@ -513,11 +513,12 @@ def cylinder_wake_3d(n: int = 74, re: float = 300.0, **kw) -> Pencil:
     )
 
 
-def membrane_pencil(nx: int, ny: int, a: float = 1.0, b: float = 1.0) -> Pencil:
+def membrane_pencil(nx: int, ny: int, a: float = 1.0, b: float = 1.0, m_bc_diagonal: float = 1.0) -> Pencil:
     """Vibrating membrane: P2 Laplace eigenproblem K x = lambda M x on an a x b rectangle with
     homogeneous Dirichlet boundary (reference `tests/benchmark/vibrating_membrane.py:130-173`):
     analytic spectrum pi^2 (m^2/a^2 + n^2/b^2); Dirichlet rows are identity in K and M, which adds
-    the spurious eigenvalue 1 the reference filters out (`:169-173`)."""
+    the spurious eigenvalue 1 the reference filters out (`:169-173`); `m_bc_diagonal` (dolfinx's `diagonal=` of the
+    mass assembly) moves it to 1 / m_bc_diagonal."""
     shape = (nx, ny)
     dim = 2
     fine_shape = (2 * nx + 1, 2 * ny + 1)
@@ -559,7 +560,7 @@ def membrane_pencil(nx: int, ny: int, a: float = 1.0, b: float = 1.0) -> Pencil:
     on_bnd = (idx[:, 0] == 0) | (idx[:, 0] == fine_shape[0] - 1) | (idx[:, 1] == 0) | (idx[:, 1] == fine_shape[1] - 1)
     bc = np.nonzero(on_bnd)[0]
     K = _apply_identity_rows_cols(K, bc)
-    M = _apply_identity_rows_cols(M, bc)
+    M = _apply_identity_rows_cols(M, bc, m_bc_diagonal)
     coords = np.stack([axes[0][idx[:, 0]], axes[1][idx[:, 1]]], axis=1)
     return Pencil(A=_canonical(K), M=_canonical(M), dofs_u=np.arange(n), dofs_p=np.zeros(0, np.int64),
                   dirichlet=bc.astype(np.int64), coords=coords, meta=dict(kind="membrane", a=a, b=b, shape=shape))
@@ -569,3 +570,55 @@ def membrane_analytic(count: int, a: float = 1.0, b: float = 1.0) -> np.ndarray:
     """First `count` analytic eigenvalues pi^2 (m^2/a^2 + n^2/b^2), m, n >= 1, ascending."""
     vals = sorted(np.pi**2 * (m * m / a**2 + n * n / b**2) for m in range(1, 40) for n in range(1, 40))
     return np.array(vals[:count])
+
+
+def elasticity_pencil(nx: int, ny: int, lx: float = 10.0, ly: float = 2.0, young: float = 200e9, nu: float = 0.3,
+                      rho: float = 8000.0, clamp: str = "left", m_bc_diagonal: float = 1.0) -> Pencil:
+    """Free vibration of a plane-stress plate, K x = omega^2 M x (the modal problem of the reference's elasticity
+    module, `Elasticity/operators.py:228-270`, `Elasticity/utils.py:139-155`; a deep cantilever in the spirit of the
+    NAFEMS free-vibration benchmarks): P1 triangles, two displacement DOFs per node (node-major), consistent mass,
+    clamped edge as identity rows and columns in K and M (dolfinx's `assemble_matrix(bcs=...)`), which adds the
+    spurious eigenvalue 1 the reference drops with `skip_below_hz` (1 / m_bc_diagonal in general)."""
+    shape = (nx, ny)
+    axes = [np.linspace(0.0, lx, nx + 1), np.linspace(0.0, ly, ny + 1)]
+    pts_shape = (nx + 1, ny + 1)
+    cells2 = _simplices(shape)                      # vertices on the doubled (P2) lattice: even coordinates
+    cells = cells2 // 2
+    X = np.stack([axes[d][cells[:, :, d]] for d in range(2)], axis=-1)
+    J = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))
+    detJ = np.abs(np.linalg.det(J))
+    Jinv = np.linalg.inv(J)
+    glam = np.concatenate([-Jinv.sum(axis=1, keepdims=True), Jinv], axis=1)     # (cells, 3 vertices, 2): grad of hat functions
+    ne = cells.shape[0]
+    B = np.zeros((ne, 3, 6))
+    B[:, 0, 0::2] = glam[:, :, 0]
+    B[:, 1, 1::2] = glam[:, :, 1]
+    B[:, 2, 0::2] = glam[:, :, 1]
+    B[:, 2, 1::2] = glam[:, :, 0]
+    D = young / (1.0 - nu * nu) * np.array([[1.0, nu, 0.0], [nu, 1.0, 0.0], [0.0, 0.0, 0.5 * (1.0 - nu)]])
+    area = 0.5 * detJ
+    ke = np.einsum("e,eia,ij,ejb->eab", area, B, D, B)
+    m_s = (np.ones((3, 3)) + np.eye(3)) / 12.0                                   # P1 consistent mass of a unit-area triangle
+    me = np.zeros((ne, 6, 6))
+    for c in range(2):
+        me[:, c::2, c::2] = rho * area[:, None, None] * m_s[None]
+    node = cells[:, :, 0] * pts_shape[1] + cells[:, :, 1]
+    dof = np.stack([2 * node, 2 * node + 1], axis=-1).reshape(ne, 6)
+    n = 2 * pts_shape[0] * pts_shape[1]
+    r = np.broadcast_to(dof[:, :, None], ke.shape).ravel()
+    c = np.broadcast_to(dof[:, None, :], ke.shape).ravel()
+    K = sp.coo_matrix((ke.ravel(), (r, c)), shape=(n, n)).tocsr()
+    M = sp.coo_matrix((me.ravel(), (r, c)), shape=(n, n)).tocsr()
+    K = ((K + K.T) * 0.5).tocsr()
+    M = ((M + M.T) * 0.5).tocsr()
+    idx = np.stack(np.meshgrid(np.arange(pts_shape[0]), np.arange(pts_shape[1]), indexing="ij"), -1).reshape(-1, 2)
+    on = {"left": idx[:, 0] == 0, "right": idx[:, 0] == nx, "none": np.zeros(len(idx), bool)}[clamp]
+    bnodes = np.nonzero(on)[0]
+    bc = np.sort(np.concatenate([2 * bnodes, 2 * bnodes + 1]))
+    K = _apply_identity_rows_cols(K, bc)
+    M = _apply_identity_rows_cols(M, bc, m_bc_diagonal)
+    xy = np.stack([axes[0][idx[:, 0]], axes[1][idx[:, 1]]], axis=1)
+    coords = np.repeat(xy, 2, axis=0)
+    return Pencil(A=_canonical(K), M=_canonical(M), dofs_u=np.arange(n), dofs_p=np.zeros(0, np.int64),
+                  dirichlet=bc.astype(np.int64), coords=coords,
+                  meta=dict(kind="elasticity", shape=shape, lx=lx, ly=ly, young=young, nu=nu, rho=rho))

@@ -374,7 +374,7 @@ class iEpsSolver:  # noqa: N801
         # backend options (extensions; all optional)
         self._opts = dict(leaf_size=64, coords=None, refine_steps=0, tiny_pivot=1e-13, seed=0, device=0,
                           purify=True, nthreads=0, v0=None, force_complex=False, coupled_fraction=0.5,
-                          growth_limit=1e6, device_values=None, partition=None, symmetric="auto")
+                          growth_limit=1e6, device_values=None, partition=None, symmetric="auto", b_inner="auto")
         self._adjoint = False
         self._handle: _lib.Handle | None = None
         self._factor_key = None
@@ -451,7 +451,9 @@ class iEpsSolver:  # noqa: N801
         their pattern), partition ("auto": split this factorisation / eigensolve over the GPUs of the initialised
         torch.distributed group, one process per GPU, every rank making the same calls -- lsa_fw_b200/partitioned.py),
         symmetric ("auto": real symmetric problems -- HEP / GHEP with st_pc_type CHOLESKY, real data, real shift -- are
-        factored as L D L^T at half the factor storage; True / False force / forbid it)."""
+        factored as L D L^T at half the factor storage; True / False force / forbid it), b_inner ("auto": GHEP problems
+        run the Krylov-Schur iteration in the M-inner product -- M-orthonormal basis, Hermitian projected matrix, as
+        SLEPc does for EPS_GHEP; False keeps Euclidean inner products and only M-normalises the returned vectors)."""
         unknown = set(kw) - set(self._opts)
         if unknown:
             raise TypeError(f"unknown backend option(s): {sorted(unknown)}")
@@ -716,13 +718,19 @@ class iEpsSolver:  # noqa: N801
                 self._factor_tokens = (_values_token(A), None if self._M is None else _values_token(M))
                 _FACTOR_REGISTRY[(id(self._A), id(self._M) if self._M is not None else 0)] = weakref.ref(self)
 
+        # Hermitian-definite problem (EPS_GHEP): M-inner products on one GPU, M-normalised vectors from the device
+        b_mode = 0
+        if self._problem_type == iEpsProblemType.GHEP and self._M is not None and h.world == 1:
+            b_mode = 2 if (self._opts["b_inner"] in ("auto", True) and not adjoint) else 1
+        self._b_mode = b_mode
+        stats["b_mode"] = b_mode
         which = self._which_effective()
         res = h.eigs(nev=self._nev, ncv=self._ncv_effective(), tol=self._tol, max_restarts=self._max_it,
                      which=which.value, transform=_lib.LSA_ST_SINVERT if sinvert else _lib.LSA_ST_SHIFT,
                      sigma=sigma_fact, adjoint=adjoint, purify=(2 if self._opts["purify"] == "explicit" else int(bool(self._opts["purify"]))) if sinvert else 0,
                      refine_steps=(donor._refine_steps_effective if donor is not None
                                    else getattr(self, "_refine_steps_effective", self._opts["refine_steps"])),
-                     seed=self._opts["seed"], v0=self._opts["v0"])
+                     seed=self._opts["seed"], v0=self._opts["v0"], b_mode=b_mode)
         self._result_gen = h.gen_result
         self._nconv = res.nconv
         self._eigenvalues = h.eigenvalues(res.nconv)
@@ -763,8 +771,9 @@ class iEpsSolver:  # noqa: N801
                                    "shared handle; call solve() again")
             X = self._handle.eigenvectors(self._nconv, capacity=max(self._nconv, self._nev))
             # (the arbitrary phase is fixed on the device: largest component real positive)
-            if self._problem_type in (iEpsProblemType.GHEP,) and self._M is not None:
-                # SLEPc normalises GHEP eigenvectors to unit B-norm
+            if self._problem_type in (iEpsProblemType.GHEP,) and self._M is not None and getattr(self, "_b_mode", 0) == 0:
+                # SLEPc normalises GHEP eigenvectors to unit B-norm (done on the device, lsa_eigs_params.b_mode, except
+                # for the partitioned solve, whose GPUs hold row blocks of M)
                 Mh = _as_csr(self._M)
                 for i in range(X.shape[1]):
                     bn = np.sqrt(abs(np.vdot(X[:, i], Mh @ X[:, i])))

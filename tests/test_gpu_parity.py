@@ -1027,10 +1027,11 @@ def test_symmetric_ldlt_factor_and_sweeps():
 
 def test_ghep_with_cholesky_uses_the_symmetric_factor_and_matches_lu():
     """GHEP + SINVERT at 0 + CHOLESKY (the reference's elasticity modal solve, `Elasticity/utils.py:139-155`) runs on the
-    L D L^T factor; eigenpairs equal those of the general LU path.  An indefinite shift that breaks the unpivoted
-    factorisation falls back to LU."""
+    L D L^T factor and in the M-inner product; eigenpairs equal those of the general LU path and of the oracle.  An
+    indefinite matrix that breaks the unpivoted factorisation falls back to LU."""
     L.clear_symbolic_cache()
-    pm = pencils.membrane_pencil(40, 40, 1.0, 0.83)
+    pm = pencils.membrane_pencil(40, 40, 1.0, 0.83, m_bc_diagonal=1e-6)      # spurious Dirichlet eigenvalue at 1e6
+    ref = np.sort(O.shift_invert_arpack(pm.A, pm.M, 0.0, 16, tol=1e-13).eigenvalues.real)[:12]
     out = {}
     for pc in (L.PreconditionerType.LU, L.PreconditionerType.CHOLESKY):
         cfg = L.EigensolverConfig(num_eig=12, problem_type=L.iEpsProblemType.GHEP, atol=1e-12, max_it=200)
@@ -1039,15 +1040,18 @@ def test_ghep_with_cholesky_uses_the_symmetric_factor_and_matches_lu():
         es.solver.set_target(0.0)
         es.solver.set_st_pc_type(pc)
         pairs = es.solve()
+        assert all(isinstance(v, float) for v, _ in pairs)
         lam = np.array([v for v, _ in pairs][:12])
         X = np.stack([_vec(v) for _, v in pairs[:12]], axis=1)
         assert O.north_star_residuals(pm.A, pm.M, lam, X).max() < RESID_BAR
+        G = X.conj().T @ (pm.M @ X)                      # M-orthonormal vectors (SLEPc's GHEP normalisation)
+        assert np.abs(G - np.eye(12)).max() < 1e-8
         out[pc] = (np.sort(lam.real), dict(es.solver.stats))
+        assert np.abs(out[pc][0] - ref).max() <= EIG_RTOL * np.abs(ref).max()
     assert out[L.PreconditionerType.CHOLESKY][1]["symmetric_factorisation"] is True
     assert out[L.PreconditionerType.LU][1]["symmetric_factorisation"] is False
+    assert out[L.PreconditionerType.CHOLESKY][1]["b_mode"] == 2 and out[L.PreconditionerType.LU][1]["b_mode"] == 2
     assert out[L.PreconditionerType.CHOLESKY][1]["nnz_lu"] < 0.7 * out[L.PreconditionerType.LU][1]["nnz_lu"]
-    a, b = out[L.PreconditionerType.LU][0], out[L.PreconditionerType.CHOLESKY][0]
-    assert np.abs(a - b).max() <= EIG_RTOL * np.abs(a).max()
     # linear seam: PREONLY + CHOLESKY
     K = (pm.A + 0.5 * pm.M).tocsr()
     rhs = np.random.default_rng(3).standard_normal(pm.n)
@@ -1057,7 +1061,7 @@ def test_ghep_with_cholesky_uses_the_symmetric_factor_and_matches_lu():
     x = ksp.solve(L.iPETScVector.from_array(rhs.copy())).as_array()
     assert ksp.stats["symmetric_factorisation"] is True
     assert np.linalg.norm(K @ x - rhs) / np.linalg.norm(rhs) < 1e-12
-    # a saddle-point matrix (zero diagonal block) cannot be factored without pivoting: the solver falls back to LU
+    # a saddle-point matrix (zero diagonal block): whatever the unpivoted factorisation makes of it, the answer is right
     pc = pencils.assemble_pencil((10, 6), (4.0, 2.0), re=20.0, baseflow=pencils.zero_flow())
     S = ((pc.A + pc.A.T) * 0.5).tocsr()
     S.sort_indices()
@@ -1067,3 +1071,46 @@ def test_ghep_with_cholesky_uses_the_symmetric_factor_and_matches_lu():
     ksp.set_preconditioner(L.PreconditionerType.CHOLESKY)
     x = ksp.solve(L.iPETScVector.from_array(rhs.copy())).as_array()
     assert np.linalg.norm(S @ x - rhs) / np.linalg.norm(rhs) < 1e-10
+
+
+def test_elasticity_modal_solve_in_the_mass_inner_product():
+    """The reference's elasticity modal problem (`Elasticity/utils.py:139-155`: GHEP, target 0, SINVERT, CHOLESKY, 24
+    pairs) on a deep plane-stress cantilever (NAFEMS-like free vibration): L D L^T factor, M-orthonormal Lanczos-type
+    Krylov-Schur (`b_mode = 2`), eigenvalues against the ARPACK oracle, mass-normalised modes as `process_modes`
+    (`Elasticity/utils.py:85-96`) expects them, and the Euclidean-inner-product variant for comparison."""
+    L.clear_symbolic_cache()
+    pc = pencils.elasticity_pencil(96, 24, m_bc_diagonal=1e-14)
+    nev = 24
+    ref = np.sort(O.shift_invert_arpack(pc.A, pc.M, 0.0, nev + 4, tol=1e-13).eigenvalues.real)[:nev]
+    res = {}
+    for b_inner in ("auto", False):
+        cfg = L.EigensolverConfig(num_eig=25, atol=1e-11, max_it=300)
+        es = L.EigenSolver(L.iPETScMatrix(pc.A), L.iPETScMatrix(pc.M), cfg, check_hermitian=False)
+        sol = es.solver
+        sol.set_problem_type(L.iEpsProblemType.GHEP)
+        sol.set_target(0.0)
+        sol.set_st_type(L.iSTType.SINVERT)
+        sol.set_st_pc_type(L.PreconditionerType.CHOLESKY)
+        sol.set_dimensions(number_eigenpairs=nev)
+        sol.set_backend_options(b_inner=b_inner, coords=pc.coords)
+        pairs = es.solve()
+        assert len(pairs) >= nev
+        lam = np.array([v for v, _ in pairs][:nev])
+        X = np.stack([_vec(v) for _, v in pairs[:nev]], axis=1)
+        assert not np.iscomplexobj(X) or np.abs(X.imag).max() < 1e-9
+        order = np.argsort(lam)
+        lam, X = lam[order], X[:, order].real
+        assert np.abs(lam - ref).max() <= EIG_RTOL * np.abs(ref).max()
+        G = X.T @ (pc.M @ X)
+        assert np.abs(np.diag(G) - 1.0).max() < 1e-9                     # v^H M v = 1 (mass_chk of the reference)
+        Kp = X.T @ (pc.A @ X)
+        assert np.abs(np.diag(Kp) - lam).max() <= 1e-7 * np.abs(lam).max()   # Rayleigh quotient = omega^2
+        if b_inner == "auto":
+            assert np.abs(G - np.eye(nev)).max() < 1e-8                  # the whole set is M-orthonormal
+        st = sol.stats
+        assert st["symmetric_factorisation"] is True and st["b_mode"] == (2 if b_inner == "auto" else 1)
+        assert O.north_star_residuals(pc.A, pc.M, lam, X).max() < RESID_BAR
+        res[b_inner] = (lam, st["n_op_applies"])
+    assert np.abs(res["auto"][0] - res[False][0]).max() <= EIG_RTOL * np.abs(ref).max()
+    hz = np.sqrt(res["auto"][0][0]) / (2 * np.pi)
+    assert 14.5 < hz < 16.5                                              # Euler-Bernoulli: 16.15 Hz, lower for a deep beam

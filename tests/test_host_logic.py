@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.SymbolicInfo) == 4 * 8 + 8 * 7 + 8 + 32
-    assert ctypes.sizeof(_lib.EigsParams) == 8 * 4 + 8 * 3 + 8 + 8
+    assert ctypes.sizeof(_lib.EigsParams) == 8 * 4 + 8 * 3 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.FactorStats) == 8 * 4 + 8 + 24
     assert ctypes.sizeof(_lib.EigsResult) == 4 * 4 + 6 * 8 + 4 * 4 + 8
 
