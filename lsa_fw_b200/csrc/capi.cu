@@ -36,6 +36,8 @@ void free_csr(CsrDev& c) {
   dfree(c.rowptr);
   dfree(c.colidx);
   dfree(c.src);
+  dfree(c.rowblk);
+  c.n_rowblk = 0;
   if (c.vals) cudaFree(c.vals);
   c.vals = nullptr;
   c.nnz = 0;
@@ -139,12 +141,22 @@ void build_transpose(int n, const CsrHost& a, CsrHost& t) {
     }
 }
 
+void cut_row_blocks(lsa_handle_impl& h, const CsrHost& c, CsrDev& d) {
+  dfree(d.rowblk);
+  const std::vector<int> blk = spmv_row_blocks(h.n, c.rowptr.data(), h.spmv_block);
+  d.rowblk = dupload(blk, h.stream);
+  LSA_CUDA(cudaStreamSynchronize(h.stream));   // `blk` is pageable and goes out of scope
+  d.n_rowblk = (int)blk.size() - 1;
+  d.block_entries = h.spmv_block;
+}
+
 void upload_csr(lsa_handle_impl& h, const CsrHost& c, CsrDev& d, bool is_complex) {
   free_csr(d);
   d.nnz = (long long)c.colidx.size();
   d.rowptr = dupload(c.rowptr, h.stream);
   d.colidx = dupload(c.colidx, h.stream);
   d.src = dupload(c.src, h.stream);
+  cut_row_blocks(h, c, d);
   d.is_complex = is_complex;
   LSA_CUDA(cudaMalloc(&d.vals, std::max<size_t>(16, (size_t)d.nnz * (is_complex ? 16 : 8))));
 }
@@ -578,6 +590,15 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     h->stream_stages = (int)value;
   } else if (nm == "stream_flags") {
     h->stream_flags = (int)value & 7;
+  } else if (nm == "spmv_block") {
+    if (value != 512 && value != 1024 && value != 2048) return fail(h, LSA_ERR_ARG, "spmv_block must be 512, 1024 or 2048");
+    h->spmv_block = (int)value;
+    LSA_API_BEGIN
+    if (h->dA.rowptr) cut_row_blocks(*h, h->hA, h->dA);
+    if (h->dM.rowptr) cut_row_blocks(*h, h->hM, h->dM);
+    if (h->dAt.rowptr) cut_row_blocks(*h, h->hAt, h->dAt);
+    if (h->dMt.rowptr) cut_row_blocks(*h, h->hMt, h->dMt);
+    LSA_API_END(h)
   } else if (nm == "invert_max_k") {
     if (value < 0 || value > 65536) return fail(h, LSA_ERR_ARG, "invert_max_k must lie in [0, 65536]");
     h->invert_max_k = (int)value;

@@ -174,10 +174,15 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
 // the row is swapped by k_swap_trsm).  The panel is staged in shared memory whenever it fits
 // (`smem_bytes`), so the 32 dependent column steps run at shared-memory latency; taller panels are
 // processed in place in global memory (L2).
+// (A register-resident variant -- thread = row, 32 entries in registers, two barriers per column step -- was
+// measured in round 2 (profiles/r2s_*, r2t_*): 78 us per 32-column panel at the tree top against 65 us here, and 3.5 x
+// slower on the leaf levels, where its 255 registers leave two CTAs per SM; a column step is a ~2 us chain of
+// shuffle / barrier / FP64-division latencies either way.)
 template <class T>
 __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                   int first, int j0, T* __restrict__ fac, int* __restrict__ ipiv,
-                                                  double tiny_abs, DevStats* st, int smem_bytes, int ob0, int nopivot) {
+                                                  int* __restrict__ wperm, double tiny_abs, DevStats* st, int smem_bytes,
+                                                  int ob0, int nopivot) {
   const Front f = fronts[lvl_front[first + blockIdx.x]];
   const int k = f.k;
   if (k <= j0) return;
@@ -195,6 +200,9 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
   __shared__ ArgMax s_red[8];
   __shared__ int s_piv;
   __shared__ T s_inv;
+  __shared__ T s_cinv[OB];     // reciprocals of the pivot candidates of the current column
+  __shared__ int s_orig[OB];   // which row of the pivot window (before this panel's interchanges) sits at each position
+  if (threadIdx.x < OB) s_orig[threadIdx.x] = threadIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   T* base = G;
   long long ld = m;
@@ -213,9 +221,13 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
     ArgMax best{-1.0, 0x7fffffff};
     // nopivot (symmetric factorisation): the diagonal entry is the pivot; only its size is checked
     for (int i = jl + tid; i < (nopivot ? jl + 1 : pcand); i += blockDim.x) {
-      double a = abs1(base[i + jl * ld]);
+      const T v = base[i + jl * ld];
+      double a = abs1(v);
       if (!(a == a)) a = INFINITY;  // propagate NaN as "largest" so it is detected below
       best = better(best, ArgMax{a, i});
+      // every candidate's reciprocal, computed while the search reduces (independent instructions): the divisions
+      // leave the single-thread section between the barriers below
+      s_cinv[i] = recip(v);
     }
     for (int o = 16; o > 0; o >>= 1) {
       ArgMax other{__shfl_down_sync(0xffffffffu, best.v, o), __shfl_down_sync(0xffffffffu, best.i, o)};
@@ -228,8 +240,10 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
       for (int w = 1; w < (int)(blockDim.x >> 5); ++w) b = better(b, s_red[w]);
       int piv = b.i;
       double a = b.v;
+      bool replaced = false;
       if (isinf(a)) st->nonfinite = 1;
       if (a <= tiny_abs) {
+        replaced = true;
         if (tiny_abs == 0.0) {
           st->zero_pivot = 1;
           a = 1.0;  // keep going with a harmless value; the host reports the error
@@ -250,6 +264,10 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
       if (piv != jl) atomicAdd(&st->n_swaps, 1ULL);
       ipiv[f.col0 + j0 + jl] = j0 + piv;  // front-local row index
       s_piv = piv;
+      const int o = s_orig[jl];
+      s_orig[jl] = s_orig[piv];
+      s_orig[piv] = o;
+      s_inv = replaced ? recip(base[piv + jl * ld]) : s_cinv[piv];   // (the pivot is still in its old row)
     }
     __syncthreads();
     // 2. interchange inside the panel
@@ -260,15 +278,24 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
       base[piv + tid * ld] = a;
     }
     __syncthreads();
-    if (tid == 0) s_inv = recip(base[jl + jl * ld]);
-    __syncthreads();
     // 3. scale the column and rank-1 update of the remaining panel columns
     const T inv = s_inv;
     for (int i = jl + 1 + tid; i < pcand; i += blockDim.x) {
       const T l = base[i + jl * ld] * inv;
       lmax = fmax(lmax, abs1(l));
       base[i + jl * ld] = l;
-      for (int c = jl + 1; c < jb; ++c) base[i + c * ld] = base[i + c * ld] - l * base[jl + c * ld];
+      // (loads of four columns issued together: written as one statement per column, every load would wait for the
+      // previous column's store -- the compiler cannot tell that they never alias)
+      int c = jl + 1;
+      for (; c + 4 <= jb; c += 4) {
+        const T p0 = base[jl + c * ld], p1 = base[jl + (c + 1) * ld], p2 = base[jl + (c + 2) * ld], p3 = base[jl + (c + 3) * ld];
+        const T a0 = base[i + c * ld], a1 = base[i + (c + 1) * ld], a2 = base[i + (c + 2) * ld], a3 = base[i + (c + 3) * ld];
+        base[i + c * ld] = a0 - l * p0;
+        base[i + (c + 1) * ld] = a1 - l * p1;
+        base[i + (c + 2) * ld] = a2 - l * p2;
+        base[i + (c + 3) * ld] = a3 - l * p3;
+      }
+      for (; c < jb; ++c) base[i + c * ld] = base[i + c * ld] - l * base[jl + c * ld];
     }
     __syncthreads();
   }
@@ -278,6 +305,8 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
       G[il + (long long)cl * m] = sm[il + (long long)cl * pcand];
     }
   }
+  // the interchanges of this panel composed (front-local indices; k_swap_trsm moves the rest of those rows with it)
+  if (tid < pcand) wperm[f.col0 + j0 + tid] = j0 + s_orig[tid];
   for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
   if (lane == 0 && lmax > 0.0) atomicMax(&st->max_l_bits, (unsigned long long)__double_as_longlong(lmax));
 }
@@ -287,11 +316,14 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
 // After panel [j0, j0+jb): apply its interchanges to every other column of the k pivot rows
 // (left part of P, right part of P, all of Q) and solve the unit-lower block system for the columns
 // to the right (U12 rows).  grid: (column groups of 128, fronts); block 128 threads.
-// The jb x 128 tile is staged through shared memory so that global traffic is coalesced.
+// The interchanges arrive COMPOSED (k_panel_lu: `wperm[p]` = the row that position p of the <= 128-row pivot window
+// holds afterwards), so a column is permuted with independent loads followed by independent stores -- one warp per
+// column, lanes along the window rows -- instead of 32 dependent read-modify-write swaps per thread.  The jb x 128
+// tile of U rows is staged through shared memory so that global traffic is coalesced.
 template <class T>
 __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
-                                                   int first, int j0, T* __restrict__ fac,
-                                                   const int* __restrict__ ipiv, int symmetric) {
+                                                   int first, int j0, int ob0, T* __restrict__ fac,
+                                                   const int* __restrict__ wperm, int symmetric) {
   const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int k = f.k, r = f.r;
   if (k <= j0) return;
@@ -301,73 +333,87 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
   const int n_left = j0, n_right = k - j1, ncols = n_left + n_right + (symmetric ? 0 : r);   // symmetric: no Q
   const int cbase = blockIdx.x * 128;
   if (cbase >= ncols) return;
+  const int W = min(k, ob0 + OB) - j0;   // rows of the pivot window
   T* P = fac + f.p_off;
   T* Q = fac + f.q_off;
   extern __shared__ unsigned char smem_raw[];
   T* s_L = reinterpret_cast<T*>(smem_raw);  // NB x NB, column-major, unit lower
   T* s_tile = s_L + NB * NB;                // 128 columns x (NB+1)
-  __shared__ int s_piv[NB];
-  const int tid = threadIdx.x;
+  __shared__ int s_src[OB];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int e = tid; e < NB * NB; e += 128) {
     const int i = e % NB, c = e / NB;
     s_L[e] = (i < jb && c < jb && i > c) ? P[(j0 + i) + (long long)(j0 + c) * m] : scalar_traits<T>::zero();
   }
-  if (tid < NB) s_piv[tid] = tid < jb ? ipiv[f.col0 + j0 + tid] : -1;
+  s_src[tid] = tid < W ? wperm[f.col0 + j0 + tid] : j0 + tid;
   __syncthreads();
-  // this thread's column
-  const int lc = cbase + tid;
-  T* col = nullptr;
-  bool right = false;
-  if (lc < ncols) {
-    if (lc < n_left) col = P + (long long)lc * m;
-    else if (lc < n_left + n_right) {
-      col = P + (long long)(j1 + lc - n_left) * m;
-      right = true;
-    } else {
-      col = Q + (long long)(lc - n_left - n_right) * k;
-      right = true;
-    }
-    for (int t = 0; t < jb; ++t) {
-      const int piv = s_piv[t];
-      if (piv != j0 + t) {
-        T a = col[j0 + t], b = col[piv];
-        col[j0 + t] = b;
-        col[piv] = a;
+  auto column = [&](int g) -> T* {
+    if (g < n_left) return P + (long long)g * m;
+    if (g < n_left + n_right) return P + (long long)(j1 + g - n_left) * m;
+    return Q + (long long)(g - n_left - n_right) * k;
+  };
+  // ---- interchanges; the U rows of the right columns go to the tile.  A warp takes CB columns per round: all their
+  // loads are in flight together (one column per round is a chain of 32 dependent L2 round trips per warp)
+  int src[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) src[q] = s_src[lane + 32 * q];
+  constexpr int CB = 8;
+  for (int cb = wid * CB; cb < 128; cb += 4 * CB) {
+    if (cbase + cb >= ncols) break;
+    T v[CB][4];
+#pragma unroll
+    for (int u = 0; u < CB; ++u) {
+      const int g = cbase + cb + u;
+      const bool right = g >= n_left;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = lane + 32 * q;
+        v[u][q] = scalar_traits<T>::zero();
+        if (g < ncols && i < W && (src[q] != j0 + i || (q == 0 && right && lane < jb))) v[u][q] = column(g)[src[q]];
       }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < CB; ++u) {
+      const int g = cbase + cb + u;
+      if (g >= ncols) continue;
+      const bool right = g >= n_left;
+      T* col = column(g);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = lane + 32 * q;
+        if (q == 0 && right && lane < jb) continue;   // written back after the triangular solve
+        if (i < W && src[q] != j0 + i) col[j0 + i] = v[u][q];
+      }
+      if (right) s_tile[(cb + u) * (NB + 1) + lane] = lane < jb ? v[u][0] : scalar_traits<T>::zero();
     }
   }
   // whole block: either all "left" columns (nothing more to do) or some right columns
   const bool block_has_right = cbase + 127 >= n_left;
   if (!block_has_right) return;
   __syncthreads();
-  // stage rows [j0, j1) of the 128 columns: one warp per column, lanes along rows (coalesced)
-  const int lane = tid & 31, wid = tid >> 5;
-  for (int c = wid; c < 128; c += 4) {
-    const int g = cbase + c;
-    T v = scalar_traits<T>::zero();
-    if (g < ncols && g >= n_left && lane < jb) {
-      const T* src = g < n_left + n_right ? P + (long long)(j1 + g - n_left) * m : Q + (long long)(g - n_left - n_right) * k;
-      v = src[j0 + lane];
-    }
-    s_tile[c * (NB + 1) + lane] = v;
-  }
-  __syncthreads();
-  if (right) {
+  const int lc = cbase + tid;
+  if (lc < ncols && lc >= n_left) {
     T* u = s_tile + tid * (NB + 1);
 #pragma unroll 1
     for (int t = 1; t < jb; ++t) {
-      T acc = u[t];
-      for (int s = 0; s < t; ++s) acc = acc - s_L[t + s * NB] * u[s];
-      u[t] = acc;
+      // four partial sums: the chain of dependent multiply-adds per row is a quarter as long
+      T a0 = u[t], a1 = scalar_traits<T>::zero(), a2 = a1, a3 = a1;
+      int s = 0;
+      for (; s + 4 <= t; s += 4) {
+        a0 = a0 - s_L[t + s * NB] * u[s];
+        a1 = a1 - s_L[t + (s + 1) * NB] * u[s + 1];
+        a2 = a2 - s_L[t + (s + 2) * NB] * u[s + 2];
+        a3 = a3 - s_L[t + (s + 3) * NB] * u[s + 3];
+      }
+      for (; s < t; ++s) a0 = a0 - s_L[t + s * NB] * u[s];
+      u[t] = (a0 + a1) + (a2 + a3);
     }
   }
   __syncthreads();
   for (int c = wid; c < 128; c += 4) {
     const int g = cbase + c;
-    if (g < ncols && g >= n_left && lane < jb) {
-      T* dst = g < n_left + n_right ? P + (long long)(j1 + g - n_left) * m : Q + (long long)(g - n_left - n_right) * k;
-      dst[j0 + lane] = s_tile[c * (NB + 1) + lane];
-    }
+    if (g < ncols && g >= n_left && lane < jb) column(g)[j0 + lane] = s_tile[c * (NB + 1) + lane];
   }
 }
 
@@ -402,21 +448,25 @@ __global__ void __launch_bounds__(128) k_trsm_cols(const Front* __restrict__ fro
   const int row = blockIdx.x * 128 + threadIdx.x;
   if (row >= r) return;
   T* x = P + rbase + row + (long long)j0 * m;
+  // all 32 loads first, all stores last: with a load and a store per column the row is a chain of 32 dependent
+  // memory round trips (the compiler cannot move a load above the previous column's store)
   T xs[NB];
   double lmax = 0.0;
 #pragma unroll
+  for (int c = 0; c < NB; ++c) xs[c] = c < jb ? x[(long long)c * m] : scalar_traits<T>::zero();
+#pragma unroll
   for (int c = 0; c < NB; ++c) {
     if (c < jb) {
-      T acc = x[(long long)c * m];
+      T acc = xs[c];
 #pragma unroll
       for (int s = 0; s < c; ++s) acc = acc - xs[s] * s_U[s + c * NB];
       xs[c] = acc * s_U[c + c * NB];
       lmax = fmax(lmax, abs1(xs[c]));
-      x[(long long)c * m] = xs[c];
-    } else {
-      xs[c] = scalar_traits<T>::zero();
     }
   }
+#pragma unroll
+  for (int c = 0; c < NB; ++c)
+    if (c < jb) x[(long long)c * m] = xs[c];
   atomicMax(&st->max_l_bits, (unsigned long long)__double_as_longlong(lmax));
 }
 
@@ -933,12 +983,12 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
             const int panel_smem = (int)std::min<long long>(want, PANEL_SMEM_CAP);
             // the pivot candidates are the <= 128 rows of the current outer block: 128 threads cover them (one
             // row each in the scaling / rank-1 step), with half the warps to synchronise per column step
-            k_panel_lu<T><<<act, 128, panel_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, tiny_abs,
+            k_panel_lu<T><<<act, 128, panel_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, h.d_gperm, tiny_abs,
                                                         h.d_stats, panel_smem, ob0, symm);
           }
           LSA_LAUNCH_CHECK();
           tr.mark("panel_lu", d, j0, act, 1);
-          k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, symm);
+          k_swap_trsm<T><<<dim3(gx_cols, act), 128, swap_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, ob0, fac, h.d_gperm, symm);
           LSA_LAUNCH_CHECK();
           tr.mark("swap_trsm", d, j0, gx_cols, act);
           launches += 2;

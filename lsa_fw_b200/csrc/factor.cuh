@@ -69,6 +69,7 @@ void replicated_rows_to_partial(lsa_handle_impl& h, z128* x);   // solve.cu: lev
 
 // krylov.cu
 void spmv(lsa_handle_impl& h, const CsrDev& M, bool conj_vals, const z128* x, z128* y);
+std::vector<int> spmv_row_blocks(int n, const long long* rowptr, int block_entries);
 void run_eigs(lsa_handle_impl& h, const lsa_eigs_params& p, lsa_eigs_result& out);
 void dense_schur_device(lsa_handle_impl& h, int m, z128* dS, int ld, z128* dQ, int which, int transform, z128 sigma);
 void op_solve(lsa_handle_impl& h, int trans, z128* x, int refine_steps);

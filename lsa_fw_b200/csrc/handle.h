@@ -23,6 +23,9 @@ struct CsrDev {
   long long* rowptr = nullptr;
   int* colidx = nullptr;
   long long* src = nullptr;
+  int* rowblk = nullptr;   // row blocks of the streamed SpMV (krylov.cu: spmv_row_blocks), n_rowblk + 1 entries
+  int n_rowblk = 0;
+  int block_entries = 0;   // entries per row block the blocks were cut for (512, 1024 or 2048)
   void* vals = nullptr;  // permuted values, double or z128 (is_complex)
   bool is_complex = false;
 };
@@ -202,6 +205,7 @@ struct lsa_handle_impl {
   int stream_min_fronts = 96; // multi-step levels with at least this many fronts are streamed too (one CTA per front)
   bool use_clusters = true;
   double coupled_fraction = 0.5;
+  int spmv_block = 1024;      // entries per row block of the streamed SpMV (option "spmv_block": 512, 1024, 2048)
   bool symmetric = false;     // option "symmetric" (before lsa_analyze): F = L D L^T, real FP64, no pivoting, half the factor store
 };
 

@@ -19,34 +19,99 @@ namespace lsa {
 
 // ---------------------------------------------------------------------------------------- SpMV
 
-// y = Op x, CSR with 8 lanes per row (rows of the FE pencils hold 10-100 entries).
-template <class VT, bool CONJ>
-__global__ void __launch_bounds__(256) k_spmv(int n, const long long* __restrict__ rowptr, const int* __restrict__ colidx,
-                                              const VT* __restrict__ vals, const z128* __restrict__ x,
-                                              z128* __restrict__ y) {
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = gid >> 3, sub = gid & 7;
-  z128 acc = mk(0, 0);
-  if (row < n) {
-    const long long b = rowptr[row], e = rowptr[row + 1];
-    for (long long p = b + sub; p < e; p += 8) acc += cj<CONJ>(vals[p]) * x[colidx[p]];
+// y = Op x, CSR, "stream" form: a CTA owns a block of consecutive rows holding at most SPMV_T = 256 U entries (row blocks
+// cut on the host when the pattern is uploaded, CsrDev::rowblk).  Phase 1: all threads walk the block's entries in
+// storage order -- values and column indices are read fully coalesced, eight independent (value, index, x[index])
+// loads per thread in flight -- and leave the products in shared memory.  Phase 2: one thread per row sums its
+// segment in storage order (deterministic, independent of the launch geometry).  Rows of the FE pencils hold 0-100
+// entries (pressure rows of M are empty), which starves a lanes-per-row kernel; a single row longer than SPMV_T
+// entries gets a block of its own and a block-wide reduction.
+constexpr int SPMV_ROWS = 1024;   // at most this many rows per block (stretches of empty rows)
+
+template <class VT, bool CONJ, int U>
+__global__ void __launch_bounds__(256) k_spmv(const int* __restrict__ rowblk, const long long* __restrict__ rowptr,
+                                              const int* __restrict__ colidx, const VT* __restrict__ vals,
+                                              const z128* __restrict__ x, z128* __restrict__ y) {
+  constexpr int SPMV_T = 256 * U;
+  __shared__ z128 prod[SPMV_T];
+  const int tid = threadIdx.x;
+  const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
+  const long long e0 = rowptr[r0], e1 = rowptr[r1];
+  if (e1 - e0 > SPMV_T) {   // one long row
+    z128 acc = mk(0, 0);
+    for (long long p = e0 + tid; p < e1; p += 256) acc += cj<CONJ>(vals[p]) * x[colidx[p]];
+    prod[tid] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) prod[tid] += prod[tid + o];
+      __syncthreads();
+    }
+    if (tid == 0) y[r0] = prod[0];
+    return;
   }
-  for (int o = 4; o > 0; o >>= 1) {
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+  const int cnt = (int)(e1 - e0);
+  const VT* __restrict__ vb = vals + e0;
+  const int* __restrict__ cb = colidx + e0;
+  int c[U];
+  VT v[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = tid + u * 256;
+    c[u] = i < cnt ? cb[i] : -1;
   }
-  if (row < n && sub == 0) y[row] = acc;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = tid + u * 256;
+    if (i < cnt) v[u] = vb[i];
+  }
+  z128 xv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (c[u] >= 0) xv[u] = x[c[u]];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (c[u] >= 0) prod[tid + u * 256] = cj<CONJ>(v[u]) * xv[u];
+  __syncthreads();
+  for (int r = r0 + tid; r < r1; r += 256) {
+    const int b = (int)(rowptr[r] - e0), e = (int)(rowptr[r + 1] - e0);
+    z128 acc = mk(0, 0);
+    for (int p = b; p < e; ++p) acc += prod[p];
+    y[r] = acc;
+  }
+}
+
+// row blocks of a CSR pattern for k_spmv: consecutive rows, at most `block_entries` entries and SPMV_ROWS rows per block
+std::vector<int> spmv_row_blocks(int n, const long long* rowptr, int block_entries) {
+  std::vector<int> blk;
+  blk.push_back(0);
+  int r = 0;
+  while (r < n) {
+    const long long e0 = rowptr[r];
+    int q = r + 1;   // a block holds at least one row
+    while (q < n && q - r < SPMV_ROWS && rowptr[q + 1] - e0 <= block_entries) ++q;
+    blk.push_back(q);
+    r = q;
+  }
+  return blk;
+}
+
+template <int U>
+static void launch_spmv(cudaStream_t st, const CsrDev& M, bool conj_vals, const z128* x, z128* y) {
+  const int blocks = M.n_rowblk;
+  if (M.is_complex) {
+    if (conj_vals) k_spmv<z128, true, U><<<blocks, 256, 0, st>>>(M.rowblk, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
+    else k_spmv<z128, false, U><<<blocks, 256, 0, st>>>(M.rowblk, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
+  } else {
+    k_spmv<double, false, U><<<blocks, 256, 0, st>>>(M.rowblk, M.rowptr, M.colidx, (const double*)M.vals, x, y);
+  }
 }
 
 void spmv(lsa_handle_impl& h, const CsrDev& M, bool conj_vals, const z128* x, z128* y) {
-  const int n = h.n;
-  const int blocks = cdiv((long long)n * 8, 256);
-  if (M.is_complex) {
-    if (conj_vals) k_spmv<z128, true><<<blocks, 256, 0, h.stream>>>(n, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
-    else k_spmv<z128, false><<<blocks, 256, 0, h.stream>>>(n, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
-  } else {
-    k_spmv<double, false><<<blocks, 256, 0, h.stream>>>(n, M.rowptr, M.colidx, (const double*)M.vals, x, y);
-  }
+  if (M.n_rowblk <= 0) return;
+  if (M.block_entries == 512) launch_spmv<2>(h.stream, M, conj_vals, x, y);
+  else if (M.block_entries == 1024) launch_spmv<4>(h.stream, M, conj_vals, x, y);
+  else if (M.block_entries == 2048) launch_spmv<8>(h.stream, M, conj_vals, x, y);
+  else throw std::runtime_error("spmv: unsupported row-block size");
   LSA_LAUNCH_CHECK();
 }
 

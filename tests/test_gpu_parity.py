@@ -400,6 +400,41 @@ def test_spmv_all_operators(factored):
             assert np.linalg.norm(y - op @ x) <= 1e-14 * np.linalg.norm(op @ x)
 
 
+def test_spmv_row_blocks_with_empty_stretches_and_long_rows():
+    """The streamed SpMV cuts the rows into blocks of <= 2048 entries / <= 1024 rows: stretches of empty rows (pressure
+    rows of M), rows longer than one block (handled by a block-wide reduction) and complex values, N / T / H."""
+    import scipy.sparse as sp
+
+    n = 7000
+    rng = np.random.default_rng(11)
+    A = sp.random(n, n, density=4e-3, random_state=3, format="lil", dtype=np.float64)
+    A.setdiag(4.0)
+    A[17, :] = 0.0
+    A[17, ::2] = rng.standard_normal(n // 2)             # 3500 entries in one row
+    A[:, 4001] = rng.standard_normal((n, 1))             # ... and, transposed, in one row of A^T
+    A = A.tocsr().astype(np.complex128)
+    A.data = A.data + 1j * rng.standard_normal(A.nnz)
+    A.sort_indices()
+    M = sp.random(n, n, density=2e-3, random_state=4, format="lil", dtype=np.float64)
+    M[2000:4500, :] = 0.0                                 # 2500 consecutive empty rows
+    M[5000, 100:5100] = 1.5                               # a long real row
+    M = M.tocsr()
+    M.eliminate_zeros()
+    M.sort_indices()
+    h = _lib.Handle(n, 0)
+    try:
+        h.analyze(A.indptr, A.indices, M.indptr, M.indices, leaf_size=32)
+        h.set_values(A.data, M.data)
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        for which, mat in ((_lib.LSA_MAT_A, A), (_lib.LSA_MAT_M, M)):
+            for trans, op in ((_lib.LSA_OP_N, mat), (_lib.LSA_OP_T, mat.T), (_lib.LSA_OP_H, mat.conj().T)):
+                y = h.spmv(which, x, trans)
+                ref = op @ x
+                assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+    finally:
+        h.close()
+
+
 def test_real_factor_with_complex_vectors():
     pc, _ = _ns("th2d")
     h = _lib.Handle(pc.n, 0)

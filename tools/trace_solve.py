@@ -42,4 +42,12 @@ print(f"{name}: device sweep {r.seconds_solve / r.n_op_applies * 1e3:.3f} ms/app
 os.environ["LSA_TRACE"] = "1"
 h.solve(b, _lib.LSA_OP_H if "--H" in sys.argv else _lib.LSA_OP_N)
 os.environ.pop("LSA_TRACE")
+if "--spmv-variants" in sys.argv:
+    # streamed SpMV: entries per row block (device time per M v from the eigensolver's event timer)
+    bytes_m = pc.M.nnz * 12 + 8 * (pc.n + 1) + 32 * pc.n
+    for blk in (512, 1024, 2048):
+        h.set_option("spmv_block", blk)
+        r = h.eigs(nev=4, ncv=24, tol=1e-8, max_restarts=2, which="TARGET_MAGNITUDE", transform=_lib.LSA_ST_SINVERT, sigma=sigma, seed=1)
+        t = r.seconds_spmv / r.n_op_applies
+        print(f"{name}: spmv_block {blk}: {t * 1e6:.1f} us per M v, {bytes_m / t / 1e9:.0f} GB/s algorithmic", flush=True)
 h.close()
