@@ -599,6 +599,9 @@ int lsa_set_option(lsa_handle* h, const char* name, double value) {
     if (h->dAt.rowptr) cut_row_blocks(*h, h->hAt, h->dAt);
     if (h->dMt.rowptr) cut_row_blocks(*h, h->hMt, h->dMt);
     LSA_API_END(h)
+  } else if (nm == "tri_span") {
+    if (value < 0 || value > 65536) return fail(h, LSA_ERR_ARG, "tri_span must lie in [0, 65536]");
+    h->tri_span = (int)value / 32 * 32;
   } else if (nm == "invert_max_k") {
     if (value < 0 || value > 65536) return fail(h, LSA_ERR_ARG, "invert_max_k must lie in [0, 65536]");
     h->invert_max_k = (int)value;
@@ -828,6 +831,7 @@ int lsa_factor(lsa_handle* h, double alpha_re, double alpha_im, double beta_re, 
     if (atoi(e) != 0) h->use_graphs = false;
   }
   if (const char* e = getenv("LSA_INVERT_MAX_K")) h->invert_max_k = atoi(e);
+  if (const char* e = getenv("LSA_TRI_SPAN")) h->tri_span = std::max(0, atoi(e)) / 32 * 32;
   if (const char* e = getenv("LSA_PARTITION_GRAPHS")) h->part_graphs = atoi(e) != 0;
   plan_solve(*h, scalar);
   if (scalar == LSA_C128) {

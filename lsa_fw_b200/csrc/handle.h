@@ -193,6 +193,7 @@ struct lsa_handle_impl {
   z128* d_tri_scratch = nullptr;        // partial sums of the split triangular GEMVs
   int* d_tri_tickets = nullptr;         // arrival counters of their row chunks (self-resetting)
   long long tri_slots = 0;
+  int tri_span = 512;                   // input entries per CTA of a split triangular GEMV (0: never split)
   bool use_graphs = true;
   bool defer_cb = true;          // cluster up sweeps: contribution rows updated by one wide GEMV after the pivot steps
   bool cluster_slices = true;    // levels with <= 9 fronts: 16-CTA clusters sharing every 128-row block by 8-row slices
@@ -202,7 +203,7 @@ struct lsa_handle_impl {
   int stream_stages = 0;      // ring depth of the streamed kernel (0 = by level size)
   int stream_flags = 3;       // bit 0: wider tiles for narrow blocks, bit 1: single-copy tiles for contiguous blocks
   int stream_small_rows = 192; // levels whose fronts have at most this many rows use the small-CTA variant
-  int stream_min_fronts = 96; // multi-step levels with at least this many fronts are streamed too (one CTA per front)
+  int stream_min_fronts = 192;// multi-step levels with at least this many fronts are streamed too (one CTA per front)
   bool use_clusters = true;
   double coupled_fraction = 0.5;
   int spmv_block = 1024;      // entries per row block of the streamed SpMV (option "spmv_block": 512, 1024, 2048)

@@ -178,6 +178,8 @@ template <class T>
 void post_factor(lsa_handle_impl& h, int* n_kernels) {
   const Symbolic& sym = h.sym;
   cudaStream_t st = h.stream;
+  SweepTrace tr;
+  tr.begin(st);
   if (h.n > 0) k_iota<<<cdiv(h.n, 256), 256, 0, st>>>(h.d_gperm, h.n);
   LSA_LAUNCH_CHECK();
   if (sym.ns > 0) {
@@ -202,6 +204,7 @@ void post_factor(lsa_handle_impl& h, int* n_kernels) {
         LSA_LAUNCH_CHECK();
       }
       if (n_kernels) (*n_kernels) += 3;
+      tr.mark("inv_128", -1, s0, cdiv(maxk, 128), cnt);
     }
     // ---- levels swept with k_tri_gemv: merge on, 128 -> 256 -> ... -> whole pivot block (GEMMs on the DMMA
     // pipe through a scratch block per pair; the fronts of a level chunk are batched as far as the scratch
@@ -228,6 +231,7 @@ void post_factor(lsa_handle_impl& h, int* n_kernels) {
         for (int HB = SB; HB < maxk; HB *= 2) {
           launch_inv_merge<T>(st, h.d_fronts, h.d_lvl_front, q, q1 - q, h.d_inv_off, HB, maxk, (T*)h.d_fac, (T*)h.d_inv_scratch);
           if (n_kernels) (*n_kernels) += 4;
+          tr.mark("inv_merge", c.level, HB, cdiv(maxk, 2 * HB), q1 - q);
         }
         // the offsets buffer is reused by the next batch: pageable copies are staged before the call returns,
         // and the launches above are stream ordered behind them
@@ -236,6 +240,7 @@ void post_factor(lsa_handle_impl& h, int* n_kernels) {
     }
   }
   if (n_kernels) (*n_kernels) += 2;
+  tr.end();
 }
 template void post_factor<double>(lsa_handle_impl&, int*);
 template void post_factor<z128>(lsa_handle_impl&, int*);
@@ -495,7 +500,7 @@ template <class T, bool H, bool UP, int NW>
 __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
                                                    int first, const T* __restrict__ fac, const z128* __restrict__ in,
                                                    z128* __restrict__ out, z128* __restrict__ scratch,
-                                                   int* __restrict__ tickets) {
+                                                   int* __restrict__ tickets, int span) {
   constexpr int ROWS = 32;
   constexpr int CHUNK = NW * 32;
   const Front f = fronts[lvl_front[first + blockIdx.y]];
@@ -513,13 +518,15 @@ __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ 
   z128 accH[ROWS / NW];
 #pragma unroll
   for (int q = 0; q < ROWS / NW; ++q) accH[q] = mk(0, 0);
-  // index range of the input entries this CTA's outputs depend on, and this split's share of it
+  // index range of the input entries this CTA's outputs depend on, and this split's share of it: spans of `span`
+  // entries, so that only the long rows of the triangle are split (a row chunk near the apex stays one CTA) and no
+  // CTA streams more than 32 x span entries
   int c_lo = UP ? 0 : r0, c_hi = UP ? min(k, r0 + ROWS) : k;
-  const int nsplit = gridDim.z;
+  const int nsplit = gridDim.z > 1 ? min((int)gridDim.z, (c_hi - c_lo + span - 1) / span) : 1;
+  if ((int)blockIdx.z >= nsplit) return;
   if (nsplit > 1) {
-    const int span = ((c_hi - c_lo + nsplit - 1) / nsplit + 31) / 32 * 32;
     c_lo = c_lo + (int)blockIdx.z * span;
-    c_hi = min(c_hi, c_lo + span);
+    if ((int)blockIdx.z + 1 < nsplit) c_hi = min(c_hi, c_lo + span);
   }
   for (int c0 = c_lo; c0 < c_hi; c0 += CHUNK) {
     const int len = min(CHUNK, c_hi - c0);
@@ -575,7 +582,8 @@ __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ 
   z128 sum = tid < ROWS ? red[0][tid] : mk(0, 0);
   if (nsplit > 1) {
     const long long slot = ((long long)blockIdx.y * gridDim.x + blockIdx.x);
-    z128* mine = scratch + (slot * nsplit + blockIdx.z) * ROWS;
+    const int zmax = gridDim.z;
+    z128* mine = scratch + (slot * zmax + blockIdx.z) * ROWS;
     if (tid < ROWS) mine[tid] = sum;
     __threadfence();
     __syncthreads();
@@ -589,7 +597,7 @@ __global__ void __launch_bounds__(NW * 32) k_tri_gemv(const Front* __restrict__ 
     __threadfence();
     if (tid < ROWS) {
       sum = mk(0, 0);
-      for (int z = 0; z < nsplit; ++z) sum += ld_cg(scratch + (slot * nsplit + z) * ROWS + tid);
+      for (int z = 0; z < nsplit; ++z) sum += ld_cg(scratch + (slot * zmax + z) * ROWS + tid);
     }
   }
   if (tid < ROWS && r0 + tid < k) {
@@ -1849,23 +1857,26 @@ void exchange_replicated_rows(lsa_handle_impl& h, z128* x, bool with_cut_contrib
   LSA_LAUNCH_CHECK();
 }
 
-// splits of a chunk's triangular GEMV: only where the row chunks alone leave most SMs idle (the root: 46 CTAs);
-// measured on config 3: splitting levels that already fill the GPU once costs more than it returns
+// splits of a chunk's triangular GEMV (gridDim.z; a CTA handles `tri_span` input entries of its 32 rows): only for the
+// few wide fronts of the tree top, where one CTA per 32-row chunk leaves SMs idle while the longest rows of the
+// triangle (32 x k entries) bound the launch
 static int tri_splits(const lsa_handle_impl& h, const SolveChunk& c) {
   const long long ctas = (long long)cdiv(c.maxk, 32) * c.cnt;
-  if (c.maxk <= 512 || 2 * ctas > h.num_sms) return 1;
-  return (int)std::min<long long>(8, h.num_sms / ctas);
+  if (c.maxk <= 512 || ctas > 3LL * h.num_sms || h.tri_span <= 0) return 1;
+  return std::min(8, cdiv(c.maxk, h.tri_span));
 }
 
 template <class T, bool H, bool UP>
 static void launch_tri_gemv(lsa_handle_impl& h, cudaStream_t st, const SolveChunk& c, const int* d_lvl_front, const T* fac,
                             const z128* in, z128* out) {
-  const int ns = tri_splits(h, c);
+  int ns = tri_splits(h, c);
+  if ((long long)cdiv(c.maxk, 32) * c.cnt > h.tri_slots) ns = 1;   // (option changed after the plan was made)
   const dim3 grid(cdiv(c.maxk, 32), c.cnt, ns);
+  const int span = std::max(32, h.tri_span);
   if (c.maxk <= 512)
-    k_tri_gemv<T, H, UP, 8><<<grid, 256, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, in, out, h.d_tri_scratch, h.d_tri_tickets);
+    k_tri_gemv<T, H, UP, 8><<<grid, 256, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, in, out, h.d_tri_scratch, h.d_tri_tickets, span);
   else
-    k_tri_gemv<T, H, UP, 32><<<grid, 1024, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, in, out, h.d_tri_scratch, h.d_tri_tickets);
+    k_tri_gemv<T, H, UP, 32><<<grid, 1024, 0, st>>>(h.d_fronts, d_lvl_front, c.first, fac, in, out, h.d_tri_scratch, h.d_tri_tickets, span);
   LSA_LAUNCH_CHECK();
 }
 
