@@ -37,6 +37,7 @@ void free_csr(CsrDev& c) {
   dfree(c.colidx);
   dfree(c.src);
   dfree(c.rowblk);
+  dfree(c.blk_e0);
   c.n_rowblk = 0;
   if (c.vals) cudaFree(c.vals);
   c.vals = nullptr;
@@ -143,8 +144,12 @@ void build_transpose(int n, const CsrHost& a, CsrHost& t) {
 
 void cut_row_blocks(lsa_handle_impl& h, const CsrHost& c, CsrDev& d) {
   dfree(d.rowblk);
+  dfree(d.blk_e0);
   const std::vector<int> blk = spmv_row_blocks(h.n, c.rowptr.data(), h.spmv_block);
+  std::vector<long long> e0(blk.size());
+  for (size_t i = 0; i < blk.size(); ++i) e0[i] = c.rowptr[blk[i]];
   d.rowblk = dupload(blk, h.stream);
+  d.blk_e0 = dupload(e0, h.stream);
   LSA_CUDA(cudaStreamSynchronize(h.stream));   // `blk` is pageable and goes out of scope
   d.n_rowblk = (int)blk.size() - 1;
   d.block_entries = h.spmv_block;

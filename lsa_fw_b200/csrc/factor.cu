@@ -74,7 +74,7 @@ __global__ void k_decoupled_pivots(T* __restrict__ diag, int n_iso, double tiny_
 // Children are processed slot by slot in separate launches, so no two blocks ever add to the same
 // destination concurrently: deterministic, no atomics.
 template <class T>
-__global__ void k_extend_add(const Front* __restrict__ fronts, const int* __restrict__ lvl_front, int first,
+__global__ void __launch_bounds__(256, 4) k_extend_add(const Front* __restrict__ fronts, const int* __restrict__ lvl_front, int first,
                              const int* __restrict__ child_idx, const int* __restrict__ ea_map, int slot,
                              T* __restrict__ fac, const T* __restrict__ pool_child, T* __restrict__ pool_parent,
                              T* __restrict__ pool_cut, int symmetric) {
@@ -129,30 +129,35 @@ __global__ void k_extend_add(const Front* __restrict__ fronts, const int* __rest
     __syncthreads();
     for (int t = threadIdx.x; t < len; t += blockDim.x) s_map[t] = map[base + t];
     __syncthreads();
-    for (int b = blockIdx.x; b < rc; b += gridDim.x) {
-      const long long jp = map[b];
-      const T* col = cb + (long long)b * rc + base;
-      T* dcol;
-      int mode;
-      if (jp < kp) {
-        dcol = P + jp * mp;  // rows anywhere in [0, m)
-        mode = 0;
-      } else {
-        mode = 1;
-        dcol = nullptr;
+    // four child columns per pass: their loads (child entry + parent entry each) are issued together and the four
+    // read-modify-writes completed afterwards -- the destinations are distinct (the map is injective), which the
+    // compiler cannot know; one column at a time every entry was a dependent L2 round trip
+    for (int b0 = blockIdx.x; b0 < rc; b0 += 4 * gridDim.x) {
+      long long jp[4];
+      const T* col[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = b0 + u * gridDim.x;
+        ok[u] = b < rc;
+        jp[u] = ok[u] ? map[b] : 0;
+        col[u] = cb + (long long)(ok[u] ? b : 0) * rc + base;
       }
       for (int t = threadIdx.x; t < len; t += blockDim.x) {
         const long long ip = s_map[t];
-        const T v = col[t];
-        if (mode == 0) {
-          dcol[ip] = dcol[ip] + v;
-        } else if (ip < kp) {
-          T* d = Q + ip + (jp - kp) * kp;
-          *d = *d + v;
-        } else {
-          T* d = C + (ip - kp) + (jp - kp) * rp;
-          *d = *d + v;
+        T* d[4];
+        T v[4], o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          d[u] = jp[u] < kp ? P + jp[u] * mp + ip : ip < kp ? Q + ip + (jp[u] - kp) * kp : C + (ip - kp) + (jp[u] - kp) * rp;
+          if (ok[u]) {
+            v[u] = col[u][t];
+            o[u] = *d[u];
+          }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ok[u]) *d[u] = o[u] + v[u];
       }
     }
   }

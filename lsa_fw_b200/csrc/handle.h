@@ -24,6 +24,7 @@ struct CsrDev {
   int* colidx = nullptr;
   long long* src = nullptr;
   int* rowblk = nullptr;   // row blocks of the streamed SpMV (krylov.cu: spmv_row_blocks), n_rowblk + 1 entries
+  long long* blk_e0 = nullptr;   // first entry of every row block (rowptr[rowblk[.]]), n_rowblk + 1 entries
   int n_rowblk = 0;
   int block_entries = 0;   // entries per row block the blocks were cut for (512, 1024 or 2048)
   void* vals = nullptr;  // permuted values, double or z128 (is_complex)

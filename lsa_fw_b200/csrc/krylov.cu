@@ -29,14 +29,23 @@ namespace lsa {
 constexpr int SPMV_ROWS = 1024;   // at most this many rows per block (stretches of empty rows)
 
 template <class VT, bool CONJ, int U>
-__global__ void __launch_bounds__(256) k_spmv(const int* __restrict__ rowblk, const long long* __restrict__ rowptr,
-                                              const int* __restrict__ colidx, const VT* __restrict__ vals,
-                                              const z128* __restrict__ x, z128* __restrict__ y) {
+__global__ void __launch_bounds__(256) k_spmv(const int* __restrict__ rowblk, const long long* __restrict__ blk_e0,
+                                              const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+                                              const VT* __restrict__ vals, const z128* __restrict__ x,
+                                              z128* __restrict__ y) {
   constexpr int SPMV_T = 256 * U;
   __shared__ z128 prod[SPMV_T];
   const int tid = threadIdx.x;
+  // a CTA is a chain of dependent memory round trips (block bounds -> entries -> x -> row sums): the block's first
+  // entry comes from its own array instead of rowptr[rowblk[.]], and the row bounds of phase 2 are fetched together
+  // with the entries -- three round trips instead of five
   const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
-  const long long e0 = rowptr[r0], e1 = rowptr[r1];
+  const long long e0 = blk_e0[blockIdx.x], e1 = blk_e0[blockIdx.x + 1];
+  long long rp0 = 0, rp1 = 0;
+  if (r0 + tid < r1) {
+    rp0 = rowptr[r0 + tid];
+    rp1 = rowptr[r0 + tid + 1];
+  }
   if (e1 - e0 > SPMV_T) {   // one long row
     z128 acc = mk(0, 0);
     for (long long p = e0 + tid; p < e1; p += 256) acc += cj<CONJ>(vals[p]) * x[colidx[p]];
@@ -73,7 +82,11 @@ __global__ void __launch_bounds__(256) k_spmv(const int* __restrict__ rowblk, co
     if (c[u] >= 0) prod[tid + u * 256] = cj<CONJ>(v[u]) * xv[u];
   __syncthreads();
   for (int r = r0 + tid; r < r1; r += 256) {
-    const int b = (int)(rowptr[r] - e0), e = (int)(rowptr[r + 1] - e0);
+    if (r != r0 + tid) {
+      rp0 = rowptr[r];
+      rp1 = rowptr[r + 1];
+    }
+    const int b = (int)(rp0 - e0), e = (int)(rp1 - e0);
     z128 acc = mk(0, 0);
     for (int p = b; p < e; ++p) acc += prod[p];
     y[r] = acc;
@@ -99,10 +112,10 @@ template <int U>
 static void launch_spmv(cudaStream_t st, const CsrDev& M, bool conj_vals, const z128* x, z128* y) {
   const int blocks = M.n_rowblk;
   if (M.is_complex) {
-    if (conj_vals) k_spmv<z128, true, U><<<blocks, 256, 0, st>>>(M.rowblk, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
-    else k_spmv<z128, false, U><<<blocks, 256, 0, st>>>(M.rowblk, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
+    if (conj_vals) k_spmv<z128, true, U><<<blocks, 256, 0, st>>>(M.rowblk, M.blk_e0, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
+    else k_spmv<z128, false, U><<<blocks, 256, 0, st>>>(M.rowblk, M.blk_e0, M.rowptr, M.colidx, (const z128*)M.vals, x, y);
   } else {
-    k_spmv<double, false, U><<<blocks, 256, 0, st>>>(M.rowblk, M.rowptr, M.colidx, (const double*)M.vals, x, y);
+    k_spmv<double, false, U><<<blocks, 256, 0, st>>>(M.rowblk, M.blk_e0, M.rowptr, M.colidx, (const double*)M.vals, x, y);
   }
 }
 

@@ -68,8 +68,9 @@ __global__ void k_iota(int* p, int n) {
 // Inverts the 32 x 32 diagonal blocks of L11 (unit lower) and U11 (upper) in place.
 // grid: (diagonal blocks, fronts); block: 32 threads, thread c computes column c of both inverses.
 template <class T>
-__global__ void __launch_bounds__(32) k_invert_diag(const Front* __restrict__ fronts, int first, T* __restrict__ fac) {
-  const Front f = fronts[first + blockIdx.y];
+__global__ void __launch_bounds__(32) k_invert_diag(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                    int first, T* __restrict__ fac) {
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int j0 = blockIdx.x * IB;
   if (j0 >= f.k) return;
   const int nb = min(IB, f.k - j0);
@@ -93,13 +94,17 @@ __global__ void __launch_bounds__(32) k_invert_diag(const Front* __restrict__ fr
   for (int j = 0; j < nb; ++j)
     if (c < nb && c > j) D[c + (long long)j * m] = s_x[j][c];
   __syncwarp();
+  // reciprocals of the diagonal once (one per lane) instead of up to 31 dependent divisions per column
+  __shared__ T s_rd[IB];
+  if (c < nb) s_rd[c] = recip(s_a[c][c]);
+  __syncwarp();
   if (c < nb) {
     // upper inverse, column c
-    s_x[c][c] = recip(s_a[c][c]);
+    s_x[c][c] = s_rd[c];
     for (int i = c - 1; i >= 0; --i) {
       T acc = scalar_traits<T>::zero();
       for (int s = i + 1; s <= c; ++s) acc = acc + s_a[i][s] * s_x[c][s];
-      s_x[c][i] = scalar_traits<T>::zero() - acc * recip(s_a[i][i]);
+      s_x[c][i] = scalar_traits<T>::zero() - acc * s_rd[i];
     }
   }
   __syncwarp();
@@ -113,8 +118,9 @@ __global__ void __launch_bounds__(32) k_invert_diag(const Front* __restrict__ fr
 // (upper) end up explicitly inverted: the solve sweeps then need ONE small GEMV per 128 pivots
 // instead of a chain of dependent substitutions.   grid: (block pairs, fronts); block 256.
 template <class T, int HB>
-__global__ void __launch_bounds__(256) k_merge_inv(const Front* __restrict__ fronts, int first, T* __restrict__ fac) {
-  const Front f = fronts[first + blockIdx.y];
+__global__ void __launch_bounds__(256) k_merge_inv(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
+                                                   int first, T* __restrict__ fac) {
+  const Front f = fronts[lvl_front[first + blockIdx.y]];
   const int j0 = blockIdx.x * 2 * HB, jd = j0 + HB;
   if (jd >= f.k) return;
   const int hd = min(HB, f.k - jd);
@@ -185,26 +191,30 @@ void post_factor(lsa_handle_impl& h, int* n_kernels) {
   if (sym.ns > 0) {
     k_compose_perm<<<cdiv(sym.ns, 64), 64, 0, st>>>(h.d_fronts, sym.ns, h.d_ipiv, h.d_gperm);
     LSA_LAUNCH_CHECK();
-    for (int s0 = 0; s0 < sym.ns; s0 += 32768) {
-      const int cnt = std::min(32768, sym.ns - s0);
-      int maxk = 0;
-      for (int s = s0; s < s0 + cnt; ++s) maxk = std::max(maxk, sym.fronts[s].k);
-      k_invert_diag<T><<<dim3(cdiv(maxk, IB), cnt), 32, 0, st>>>(h.d_fronts, s0, (T*)h.d_fac);
+    // 32 x 32 diagonal blocks inverted, merged pairwise up to 128 x 128: per level chunk of the sweep plan (fronts of a
+    // level are sorted by descending k, so the grids are tight; batches by front number mixed the 1 444-pivot root
+    // with the leaves and launched 1.5 M CTAs per batch that had nothing to do)
+    for (const SolveChunk& c : h.solve_plan) {
+      const int s0 = c.first, cnt = c.cnt, maxk = c.maxk;
+      if (maxk <= 0) continue;
+      k_invert_diag<T><<<dim3(cdiv(maxk, IB), cnt), 32, 0, st>>>(h.d_fronts, h.d_lvl_front, s0, (T*)h.d_fac);
       LSA_LAUNCH_CHECK();
+      tr.mark("inv_32", c.level, s0, cdiv(maxk, IB), cnt);
       if (maxk > 32) {
-        k_merge_inv<T, 32><<<dim3(cdiv(maxk, 64), cnt), 256, 32 * 32 * sizeof(T), st>>>(h.d_fronts, s0, (T*)h.d_fac);
+        k_merge_inv<T, 32><<<dim3(cdiv(maxk, 64), cnt), 256, 32 * 32 * sizeof(T), st>>>(h.d_fronts, h.d_lvl_front, s0, (T*)h.d_fac);
         LSA_LAUNCH_CHECK();
+        tr.mark("inv_64", c.level, s0, cdiv(maxk, 64), cnt);
       }
       if (maxk > 64) {
         static PerDeviceOnce attr_done;   // per instantiation (T)
         if (attr_done.first())
           LSA_CUDA(cudaFuncSetAttribute(k_merge_inv<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(64 * 64 * sizeof(T))));
-        k_merge_inv<T, 64><<<dim3(cdiv(maxk, 128), cnt), 256, 64 * 64 * sizeof(T), st>>>(h.d_fronts, s0, (T*)h.d_fac);
+        k_merge_inv<T, 64><<<dim3(cdiv(maxk, 128), cnt), 256, 64 * 64 * sizeof(T), st>>>(h.d_fronts, h.d_lvl_front, s0, (T*)h.d_fac);
         LSA_LAUNCH_CHECK();
+        tr.mark("inv_128", c.level, s0, cdiv(maxk, 128), cnt);
       }
       if (n_kernels) (*n_kernels) += 3;
-      tr.mark("inv_128", -1, s0, cdiv(maxk, 128), cnt);
     }
     // ---- levels swept with k_tri_gemv: merge on, 128 -> 256 -> ... -> whole pivot block (GEMMs on the DMMA
     // pipe through a scratch block per pair; the fronts of a level chunk are batched as far as the scratch
