@@ -705,8 +705,11 @@ def main() -> None:
                                "bound": "hbm", "achieved": ortho_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ortho_gbs / hbm_peak,
                                "algorithmic_bytes": bytes_ortho, "seconds": acc["ortho"], "share_of_step": acc["ortho"] / tot,
                                "second_pass_share": acc["reorth"] / max(1, acc["arnoldi"])},
-            "roofline_spmv": {"bound": "hbm", "achieved": counters.bytes_spmv_m / spmv_mean / 1e9 if spmv_mean > 0 else 0.0,
-                              "peak": hbm_peak, "unit": "GB/s", "share_of_step": acc["spmv"] / tot},
+            "roofline_spmv": {"kernel": "k_spmv (streamed CSR: row blocks of <= 1024 entries, products through shared memory)",
+                              "bound": "hbm", "achieved": counters.bytes_spmv_m / spmv_mean / 1e9 if spmv_mean > 0 else 0.0,
+                              "peak": hbm_peak, "unit": "GB/s",
+                              "frac": (counters.bytes_spmv_m / spmv_mean / 1e9 / hbm_peak) if spmv_mean > 0 else 0.0,
+                              "share_of_step": acc["spmv"] / tot},
             "phases_s_per_step": {k: acc[k] / nmine for k in ("set", "factor", "eigs", "solve", "spmv", "ortho", "rr", "restart")},
             "op_applies_per_step": acc["applies"] / nmine, "restarts_per_step": acc["restarts"] / nmine,
             "reorthogonalised_columns_per_step": acc["reorth"] / nmine,

@@ -181,7 +181,7 @@ int lsa_partition_info_get(const lsa_handle* h, lsa_partition_info* out);
  *       (1.0 = all of them: most robust, ~+40-70 % flops in 2-D);
  *   "use_graphs" (default 1): replay the triangular-solve sweeps from CUDA graphs;
  *   "use_stream" (default 1): complex factors, levels with many fronts: streamed sweep kernel (bulk copies into
- *       a shared-memory ring); "stream_min_fronts" (96): multi-step levels with at least this many fronts are
+ *       a shared-memory ring); "stream_min_fronts" (192): multi-step levels with at least this many fronts are
  *       streamed too; "stream_small_rows" (192): levels whose fronts are at most this tall use the small CTA shape;
  *       "stream_stages" (0 = by level size, 2..12): ring depth; "stream_flags" (3): bit 0 wider tiles for narrow
  *       blocks, bit 1 single-copy tiles for contiguous blocks, bit 2 LDGSTS producer (measured slower);
@@ -193,6 +193,11 @@ int lsa_partition_info_get(const lsa_handle* h, lsa_partition_info* out);
  *       launch per 128-pivot step instead; "cluster_slices" (1): levels with <= 9 fronts use 16-CTA clusters that
  *       share every 128-row block by 8-row slices (DSMEM all-gather of the solved entries); "defer_cb" (1): the
  *       contribution rows are updated by one wide GEMV after the pivot steps;
+ *       "tri_span" (512, multiple of 32; 0 = never): the triangular matrix-vector products of the few wide fronts of the
+ *       tree top split the long rows of the triangle over several CTAs, `tri_span` input entries each (partial sums
+ *       combined in a fixed order by the last CTA to arrive: deterministic);
+ *   "spmv_block" (1024; 512 / 1024 / 2048): entries per row block of the streamed SpMV (a CTA multiplies the entries
+ *       of one block of consecutive rows in storage order and sums the rows out of shared memory);
  *   "partition_graphs" (default 1): partitioned solve: the sweeps, NCCL all-reduce included, are replayed from CUDA
  *       graphs like the single-GPU ones;
  *   "fuse_ortho" (default 1): the update of the first Gram-Schmidt pass and the dot products of the second one in
