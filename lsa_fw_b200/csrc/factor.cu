@@ -320,10 +320,10 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
 
 // After panel [j0, j0+jb): apply its interchanges to every other column of the k pivot rows
 // (left part of P, right part of P, all of Q) and solve the unit-lower block system for the columns
-// to the right (U12 rows).  grid: (column groups of 128, fronts); block 128 threads.
+// to the right (U12 rows).  grid: (column groups of 64, fronts); block 128 threads.
 // The interchanges arrive COMPOSED (k_panel_lu: `wperm[p]` = the row that position p of the <= 128-row pivot window
 // holds afterwards), so a column is permuted with independent loads followed by independent stores -- one warp per
-// column, lanes along the window rows -- instead of 32 dependent read-modify-write swaps per thread.  The jb x 128
+// column, lanes along the window rows -- instead of 32 dependent read-modify-write swaps per thread.  The jb x 64
 // tile of U rows is staged through shared memory so that global traffic is coalesced.
 template <class T>
 __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fronts, const int* __restrict__ lvl_front,
@@ -336,14 +336,16 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
   const long long m = (long long)k + r;
   // logical column space: [0, j0) left of panel | [j1, k) right of panel in P | [0, r) of Q
   const int n_left = j0, n_right = k - j1, ncols = n_left + n_right + (symmetric ? 0 : r);   // symmetric: no Q
-  const int cbase = blockIdx.x * 128;
+  constexpr int TC = 64;   // columns per CTA: 50 KB of shared memory and ~128 registers -> four CTAs per SM (with 128
+                           // columns and eight columns per gather round it was two, and the SM issued 35 % of the time)
+  const int cbase = blockIdx.x * TC;
   if (cbase >= ncols) return;
   const int W = min(k, ob0 + OB) - j0;   // rows of the pivot window
   T* P = fac + f.p_off;
   T* Q = fac + f.q_off;
   extern __shared__ unsigned char smem_raw[];
   T* s_L = reinterpret_cast<T*>(smem_raw);  // NB x NB, column-major, unit lower
-  T* s_tile = s_L + NB * NB;                // 128 columns x (NB+1)
+  T* s_tile = s_L + NB * NB;                // TC columns x (NB+1)
   __shared__ int s_src[OB];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int e = tid; e < NB * NB; e += 128) {
@@ -362,8 +364,8 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
   int src[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) src[q] = s_src[lane + 32 * q];
-  constexpr int CB = 8;
-  for (int cb = wid * CB; cb < 128; cb += 4 * CB) {
+  constexpr int CB = 4;
+  for (int cb = wid * CB; cb < TC; cb += 4 * CB) {
     if (cbase + cb >= ncols) break;
     T v[CB][4];
 #pragma unroll
@@ -394,11 +396,11 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
     }
   }
   // whole block: either all "left" columns (nothing more to do) or some right columns
-  const bool block_has_right = cbase + 127 >= n_left;
+  const bool block_has_right = cbase + TC - 1 >= n_left;
   if (!block_has_right) return;
   __syncthreads();
   const int lc = cbase + tid;
-  if (lc < ncols && lc >= n_left) {
+  if (tid < TC && lc < ncols && lc >= n_left) {
     T* u = s_tile + tid * (NB + 1);
 #pragma unroll 1
     for (int t = 1; t < jb; ++t) {
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(128) k_swap_trsm(const Front* __restrict__ fro
     }
   }
   __syncthreads();
-  for (int c = wid; c < 128; c += 4) {
+  for (int c = wid; c < TC; c += 4) {
     const int g = cbase + c;
     if (g < ncols && g >= n_left && lane < jb) column(g)[j0 + lane] = s_tile[c * (NB + 1) + lane];
   }
@@ -913,7 +915,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
     launches++;
   }
 
-  const size_t swap_smem = (size_t)(NB * NB + 128 * (NB + 1)) * sizeof(T);
+  const size_t swap_smem = (size_t)(NB * NB + 64 * (NB + 1)) * sizeof(T);
   static PerDeviceOnce attr_set;   // per instantiation (T)
   if (attr_set.first()) {
     LSA_CUDA(cudaFuncSetAttribute(k_swap_trsm<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem));
@@ -976,7 +978,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
             act++;
             const int jb = std::min(NB, f.k - j0), j1 = j0 + jb, ob1 = std::min(ob0 + OB, f.k);
             const long long m = (long long)f.k + f.r;
-            gx_cols = std::max(gx_cols, cdiv((long long)j0 + (f.k - j1) + f.r, 128));
+            gx_cols = std::max(gx_cols, cdiv((long long)j0 + (f.k - j1) + f.r, 64));
             gx_rows = std::max(gx_rows, cdiv(m - ob1, 128));
             gx_tiles = std::max(gx_tiles, tiles(m - j1, ob1 - j1) + tiles(ob1 - j1, f.k - ob1) + tiles(ob1 - j1, f.r));
           }
