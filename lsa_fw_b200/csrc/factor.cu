@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
   __shared__ T s_inv;
   __shared__ T s_cinv[OB];     // reciprocals of the pivot candidates of the current column
   __shared__ int s_orig[OB];   // which row of the pivot window (before this panel's interchanges) sits at each position
-  if (threadIdx.x < OB) s_orig[threadIdx.x] = threadIdx.x;
+  for (int i = threadIdx.x; i < OB; i += blockDim.x) s_orig[i] = i;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   T* base = G;
   long long ld = m;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) k_panel_lu(const Front* __restrict__ fron
     }
   }
   // the interchanges of this panel composed (front-local indices; k_swap_trsm moves the rest of those rows with it)
-  if (tid < pcand) wperm[f.col0 + j0 + tid] = j0 + s_orig[tid];
+  for (int i = tid; i < pcand; i += blockDim.x) wperm[f.col0 + j0 + i] = j0 + s_orig[i];
   for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
   if (lane == 0 && lmax > 0.0) atomicMax(&st->max_l_bits, (unsigned long long)__double_as_longlong(lmax));
 }
@@ -990,6 +990,7 @@ void factor_numeric(lsa_handle_impl& h, z128 alpha, z128 beta, double tiny_abs, 
             const int panel_smem = (int)std::min<long long>(want, PANEL_SMEM_CAP);
             // the pivot candidates are the <= 128 rows of the current outer block: 128 threads cover them (one
             // row each in the scaling / rank-1 step), with half the warps to synchronise per column step
+            // (32 / 64 threads for the <= 32 / <= 64-row panels of the leaf-side levels measured slower: 33.3 vs 31.5 ms)
             k_panel_lu<T><<<act, 128, panel_smem, st>>>(h.d_fronts, h.d_lvl_front, first, j0, fac, h.d_ipiv, h.d_gperm, tiny_abs,
                                                         h.d_stats, panel_smem, ob0, symm);
           }
