@@ -134,6 +134,15 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------- CPU arm
+def rank_host_threads(world: int) -> int:
+    """Host threads one rank may use for the symbolic analysis: torchrun exports OMP_NUM_THREADS=1 to every rank, which
+    triples the host analysis of config 3 (18.5 s against 6.5 s); a rank takes its share of the host cores instead.
+    0 = leave the OpenMP default alone (single-process runs)."""
+    if world <= 1:
+        return 0
+    return max(1, (os.cpu_count() or 1) // world)
+
+
 def host_threads() -> int:
     try:
         from threadpoolctl import threadpool_info
@@ -370,7 +379,8 @@ def partitioned_section(n_cells: int, rank: int, world: int, local_rank: int, de
 
     h = make_handle(pc.n, local_rank)
     t0 = time.perf_counter()
-    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=flags)
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=64, order_last=flags,
+                     nthreads=rank_host_threads(world))
     t_sym = time.perf_counter() - t0
     attach_comm(h)
     pi = h.partition_info()
@@ -473,7 +483,8 @@ def main() -> None:
     # ------------- device-resident arm: C ABI directly, the values of every pair already in HBM
     h = _lib.Handle(n, local_rank)
     t0 = time.perf_counter()
-    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=LEAF, order_last=order_last_flags(pc))
+    info = h.analyze(pc.A.indptr, pc.A.indices, pc.M.indptr, pc.M.indices, leaf_size=LEAF, order_last=order_last_flags(pc),
+                     nthreads=rank_host_threads(world))
     t_symbolic = time.perf_counter() - t0
     my_steps = [i for i in range(args.steps) if i % world == rank]   # strong scaling: the K steps are dealt over the ranks
     # only the pairs this rank touches are materialised (8 ranks x 8 value arrays x 0.7 GB would be host memory for nothing)
@@ -585,7 +596,7 @@ def main() -> None:
         es.solver.set_st_type(L.iSTType.SINVERT)
         es.solver.set_target(sigma)
         es.solver.set_st_pc_type(L.PreconditionerType.LU)
-        es.solver.set_backend_options(device=local_rank, v0=v0, leaf_size=LEAF)
+        es.solver.set_backend_options(device=local_rank, v0=v0, leaf_size=LEAF, nthreads=rank_host_threads(world))
         pairs = es.solve()
         d2h = len(pairs) * n * 16
         if w["adjoint"]:
@@ -593,7 +604,7 @@ def main() -> None:
             ea.solver.set_st_type(L.iSTType.SINVERT)
             ea.solver.set_st_pc_type(L.PreconditionerType.LU)
             ea.solver.set_target(np.conj(sigma))
-            ea.solver.set_backend_options(device=local_rank, v0=v0)
+            ea.solver.set_backend_options(device=local_rank, v0=v0, nthreads=rank_host_threads(world))
             d2h += len(ea.solve()) * n * 16
         return es, pairs, d2h
 

@@ -332,6 +332,14 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   if (!h || !a_rowptr || !a_colidx) return LSA_ERR_ARG;
   LSA_API_BEGIN
   const int n = h->n;
+  const bool trace_an = getenv("LSA_TRACE_ANALYZE") != nullptr;
+  double t_an = omp_get_wtime();
+  auto mark = [&](const char* what) {
+    if (!trace_an) return;
+    const double t = omp_get_wtime();
+    fprintf(stderr, "[lsa_analyze] %-28s %8.3f s\n", what, t - t_an);
+    t_an = t;
+  };
   h->has_m = m_rowptr != nullptr;
   h->nnz_a = a_rowptr[n];
   h->nnz_m = h->has_m ? m_rowptr[n] : 0;
@@ -354,10 +362,12 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   opt.nthreads = nthreads;
   opt.coupled_fraction = h->coupled_fraction;
   opt.symmetric = h->symmetric;
+  mark("union pattern");
   if (const char* e = getenv("LSA_COUPLED_FRACTION")) opt.coupled_fraction = atof(e);
   if (const char* e = getenv("LSA_CAP_FRACTION")) opt.cap_fraction = atof(e);
   if (h->has_m) analyze(n, urow.data(), ucol.data(), opt, h->sym);
   else analyze(n, (const long long*)a_rowptr, a_colidx, opt, h->sym);
+  mark("analyze (graph, ND, symbolic)");
   // ---- partitioned solve: every rank analyses the whole pattern (deterministic), then keeps its part
   h->partitioned = h->part_world > 1;
   std::vector<char> cls;
@@ -436,11 +446,14 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     }
     if (bad) throw std::runtime_error("front structure does not cover the matrix pattern");
   };
+  mark("partition");
   build_dst(a_rowptr, a_colidx, h->sym.a_dst);
   if (h->has_m) build_dst(m_rowptr, m_colidx, h->m_dst);
+  mark("scatter maps");
   const std::vector<char>* pcls = h->partitioned ? &cls : nullptr;
   build_permuted(n, a_rowptr, a_colidx, sym, h->hA, pcls, h->part.rank == 0);
   if (h->has_m) build_permuted(n, m_rowptr, m_colidx, sym, h->hM, pcls, h->part.rank == 0);
+  mark("permuted CSR");
   h->hAt = CsrHost();
   h->hMt = CsrHost();
   h->analyzed = true;
@@ -494,6 +507,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     upload_csr(*h, h->hA, h->dA, false);
     if (h->has_m) upload_csr(*h, h->hM, h->dM, false);
     LSA_CUDA(cudaStreamSynchronize(st));
+    mark("device structures");
   }
   LSA_API_END(h)
   return LSA_OK;
