@@ -2,6 +2,7 @@
 #include <omp.h>
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <numeric>
 
 #include "factor.cuh"
@@ -20,8 +21,8 @@ T* dalloc(size_t count) {
   LSA_CUDA(cudaMalloc(&p, count * sizeof(T)));
   return p;
 }
-template <class T>
-T* dupload(const std::vector<T>& v, cudaStream_t st) {
+template <class T, class A>
+T* dupload(const std::vector<T, A>& v, cudaStream_t st) {
   T* p = dalloc<T>(v.size());
   if (!v.empty()) LSA_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
   return p;
@@ -104,7 +105,7 @@ void build_permuted(int n, const int64_t* rowptr, const int32_t* colidx, const S
     out.rowptr[i + 1] = out.rowptr[i] + cnt;
   }
   const long long nnz = out.rowptr[n];
-  out.colidx.resize(nnz);
+  out.colidx.resize(nnz);   // uninitialised (hvec): first touched by the threads of the fill below
   out.src.resize(nnz);
 #pragma omp parallel
   {
@@ -345,13 +346,15 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   h->nnz_m = h->has_m ? m_rowptr[n] : 0;
   // union pattern for the graph
   std::vector<long long> urow(n + 1, 0);
-  std::vector<int> ucol;
+  std::unique_ptr<int[]> ucol;
   if (h->has_m) {
-    ucol.reserve(h->nnz_a + h->nnz_m);
+    ucol.reset(new int[(size_t)(h->nnz_a + h->nnz_m)]);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i <= n; ++i) urow[i] = a_rowptr[i] + m_rowptr[i];
+#pragma omp parallel for schedule(dynamic, 2048)
     for (int i = 0; i < n; ++i) {
-      ucol.insert(ucol.end(), a_colidx + a_rowptr[i], a_colidx + a_rowptr[i + 1]);
-      ucol.insert(ucol.end(), m_colidx + m_rowptr[i], m_colidx + m_rowptr[i + 1]);
-      urow[i + 1] = (long long)ucol.size();
+      int* o = std::copy(a_colidx + a_rowptr[i], a_colidx + a_rowptr[i + 1], ucol.get() + urow[i]);
+      std::copy(m_colidx + m_rowptr[i], m_colidx + m_rowptr[i + 1], o);
     }
   }
   AnalyzeOptions opt;
@@ -365,7 +368,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
   mark("union pattern");
   if (const char* e = getenv("LSA_COUPLED_FRACTION")) opt.coupled_fraction = atof(e);
   if (const char* e = getenv("LSA_CAP_FRACTION")) opt.cap_fraction = atof(e);
-  if (h->has_m) analyze(n, urow.data(), ucol.data(), opt, h->sym);
+  if (h->has_m) analyze(n, urow.data(), ucol.get(), opt, h->sym);
   else analyze(n, (const long long*)a_rowptr, a_colidx, opt, h->sym);
   mark("analyze (graph, ND, symbolic)");
   // ---- partitioned solve: every rank analyses the whole pattern (deterministic), then keeps its part
@@ -412,7 +415,7 @@ int lsa_analyze(lsa_handle* h, const int64_t* a_rowptr, const int32_t* a_colidx,
     const int* it = std::lower_bound(b, e, idx);
     return (it == e || *it != idx) ? -1 : f.k + (int)(it - b);
   };
-  auto build_dst = [&](const int64_t* rowptr, const int32_t* colidx, std::vector<long long>& dst) {
+  auto build_dst = [&](const int64_t* rowptr, const int32_t* colidx, hvec<long long>& dst) {
     dst.resize(rowptr[n]);
     int bad = 0;
 #pragma omp parallel for schedule(dynamic, 512) reduction(| : bad)

@@ -15,8 +15,8 @@ namespace lsa {
 // CSR operator in the PERMUTED ordering, values gathered from the caller's entry order.
 struct CsrHost {
   std::vector<long long> rowptr;
-  std::vector<int> colidx;
-  std::vector<long long> src;  // permuted entry -> original entry
+  hvec<int> colidx;
+  hvec<long long> src;  // permuted entry -> original entry
 };
 struct CsrDev {
   long long nnz = 0;
@@ -78,7 +78,7 @@ struct lsa_handle_impl {
   bool analyzed = false;
   bool has_m = false;
   CsrHost hA, hM, hAt, hMt;     // permuted patterns (transposes built on demand)
-  std::vector<long long> m_dst;  // like sym.a_dst for the entries of M
+  hvec<long long> m_dst;  // like sym.a_dst for the entries of M
   long long nnz_a = 0, nnz_m = 0;
 
   // ---- device plan

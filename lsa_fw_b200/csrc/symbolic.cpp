@@ -21,8 +21,10 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <stdexcept>
 
@@ -37,46 +39,68 @@ double now() {
 struct Graph {
   int n = 0;
   std::vector<long long> xadj;
-  std::vector<int> adj;
+  std::unique_ptr<int[]> adj;   // xadj[n] entries, uninitialised until build_graph fills them in parallel
 };
 
-// Pattern of A + A^T without the diagonal, sorted and de-duplicated.
+// Pattern of A + A^T without the diagonal, sorted and de-duplicated.  Every pass runs over the rows in parallel
+// (the transposed entries claim their slots with atomic counters; the per-row sort makes the result independent
+// of the order in which they arrive); the scratch array is left uninitialised so that its pages are first touched
+// by the threads that fill them.
 Graph build_graph(int n, const long long* rowptr, const int* colidx) {
   Graph g;
   g.n = n;
-  std::vector<long long> cnt(n + 1, 0);
-  for (int i = 0; i < n; ++i)
+  std::vector<long long> cnt(n + 1, 0);   // cnt[i + 1]: own off-diagonal entries of row i + entries (j, i) of other rows
+  std::vector<int> own(n, 0);
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(| : bad)
+  for (int i = 0; i < n; ++i) {
+    int c = 0;
     for (long long e = rowptr[i]; e < rowptr[i + 1]; ++e) {
-      int j = colidx[e];
+      const int j = colidx[e];
       if (j == i) continue;
-      if (j < 0 || j >= n) throw std::runtime_error("column index out of range");
-      cnt[i + 1]++;
+      if (j < 0 || j >= n) {
+        bad |= 1;
+        continue;
+      }
+      ++c;
+#pragma omp atomic
       cnt[j + 1]++;
     }
-  for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
-  std::vector<int> raw(cnt[n]);
-  std::vector<long long> pos(cnt.begin(), cnt.end() - 1);
-  for (int i = 0; i < n; ++i)
+    own[i] = c;
+  }
+  if (bad) throw std::runtime_error("column index out of range");
+  for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i] + own[i];
+  std::unique_ptr<int[]> raw(new int[(size_t)cnt[n]]);
+  std::vector<long long> pos(n);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) pos[i] = cnt[i] + own[i];
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int i = 0; i < n; ++i) {
+    long long o = cnt[i];
     for (long long e = rowptr[i]; e < rowptr[i + 1]; ++e) {
-      int j = colidx[e];
+      const int j = colidx[e];
       if (j == i) continue;
-      raw[pos[i]++] = j;
-      raw[pos[j]++] = i;
+      raw[o++] = j;
+      long long q;
+#pragma omp atomic capture
+      q = pos[j]++;
+      raw[q] = i;
     }
+  }
   std::vector<long long> deg(n + 1, 0);
 #pragma omp parallel for schedule(dynamic, 1024)
   for (int i = 0; i < n; ++i) {
-    int* b = raw.data() + cnt[i];
-    int* e = raw.data() + cnt[i + 1];
+    int* b = raw.get() + cnt[i];
+    int* e = raw.get() + cnt[i + 1];
     std::sort(b, e);
     deg[i + 1] = std::unique(b, e) - b;
   }
   for (int i = 0; i < n; ++i) deg[i + 1] += deg[i];
   g.xadj = deg;
-  g.adj.resize(deg[n]);
+  g.adj.reset(new int[(size_t)deg[n]]);
 #pragma omp parallel for schedule(dynamic, 1024)
   for (int i = 0; i < n; ++i)
-    std::copy(raw.data() + cnt[i], raw.data() + cnt[i] + (deg[i + 1] - deg[i]), g.adj.data() + deg[i]);
+    std::copy(raw.get() + cnt[i], raw.get() + cnt[i] + (deg[i + 1] - deg[i]), g.adj.get() + deg[i]);
   return g;
 }
 
@@ -85,58 +109,126 @@ struct NDResult {
   std::vector<int> sn_sizes;  // consecutive supernode sizes covering `order`
 };
 
+// A dissection node works on a COMPACT copy of its subgraph: local vertex numbers 0..nv-1 in the order of its
+// vertex list, adjacency lists in the order of the global graph (sorted by global number) restricted to the
+// subgraph.  The six breadth-first sweeps, the cut detection and the matching of a node then touch nv-sized
+// arrays only (cache-resident from a few levels below the root), and the children's copies are filtered from the
+// parent's, not from the global graph.  Orders of visit are the ones of a walk over the global graph with
+// membership marks, so the ordering produced is independent of this storage choice.
+struct SubGraph {
+  std::vector<int> gid;           // local -> global vertex number
+  std::unique_ptr<int[]> xadj;    // nv + 1
+  std::unique_ptr<int[]> adj;     // local numbers
+  int nv() const { return (int)gid.size(); }
+};
+
 class Dissector {
  public:
-  Dissector(const Graph& g, const AnalyzeOptions& opt)
-      : g_(g), opt_(opt), mark_(g.n, -1), da_(g.n, -1), db_(g.n, -1), side_(g.n, 0), token_(0) {}
+  Dissector(const Graph& g, const AnalyzeOptions& opt) : g_(g), opt_(opt) {}
 
   void run(std::vector<int>& verts, NDResult& out) {
 #pragma omp parallel
 #pragma omp single nowait
-    rec(verts, 0, out);
+    {
+      SubGraph top;
+      {
+        std::vector<int> loc(g_.n, -1);
+        const int nv = (int)verts.size();
+        for (int i = 0; i < nv; ++i) loc[verts[i]] = i;
+        top.gid = verts;
+        top.xadj.reset(new int[(size_t)nv + 1]);
+        top.xadj[0] = 0;
+        std::vector<int> deg(nv);
+#pragma omp taskloop grainsize(8192) shared(deg, loc, verts)
+        for (int i = 0; i < nv; ++i) {
+          const int v = verts[i];
+          int c = 0;
+          for (long long e = g_.xadj[v]; e < g_.xadj[v + 1]; ++e) c += loc[g_.adj[e]] >= 0;
+          deg[i] = c;
+        }
+        long long tot = 0;
+        for (int i = 0; i < nv; ++i) {
+          tot += deg[i];
+          top.xadj[i + 1] = (int)tot;   // analyze() has checked that the whole graph fits 32-bit offsets
+        }
+        top.adj.reset(new int[(size_t)tot]);
+#pragma omp taskloop grainsize(8192) shared(top, loc, verts)
+        for (int i = 0; i < nv; ++i) {
+          const int v = verts[i];
+          int o = top.xadj[i];
+          for (long long e = g_.xadj[v]; e < g_.xadj[v + 1]; ++e) {
+            const int u = loc[g_.adj[e]];
+            if (u >= 0) top.adj[o++] = u;
+          }
+        }
+      }
+      rec(top, 0, out);
+    }
   }
 
  private:
   const Graph& g_;
   const AnalyzeOptions& opt_;
-  std::vector<int> mark_, da_, db_;
-  std::vector<unsigned char> side_;
-  std::atomic<int> token_;
 
-  // BFS inside the subgraph {v : mark_[v] == tok}; dist must be -1 on entry for its vertices.
-  int bfs(int start, int tok, std::vector<int>& dist, std::vector<int>& queue) {
-    size_t head = queue.size();
-    queue.push_back(start);
+  // Work queue of the breadth-first sweeps: capacity nv + 1 so that the sweep can store a candidate before it
+  // knows whether the vertex is new (branch-free inner loop: the store is kept only if the tail advances).
+  struct Queue {
+    std::vector<int> q;
+    size_t tail = 0;
+    explicit Queue(int nv) : q((size_t)nv + 1) {}
+    void clear() { tail = 0; }
+    size_t size() const { return tail; }
+    int back() const { return q[tail - 1]; }
+  };
+
+  // BFS over the subgraph from `start`, appended to `queue`; dist must be -1 on entry for the vertices reached.
+  static int bfs(const SubGraph& sg, int start, std::vector<int>& dist_v, Queue& queue) {
+    int* q = queue.q.data();
+    int* dist = dist_v.data();
+    size_t head = queue.tail, tail = queue.tail;
+    q[tail++] = start;
     dist[start] = 0;
-    while (head < queue.size()) {
-      int v = queue[head++];
-      for (long long e = g_.xadj[v]; e < g_.xadj[v + 1]; ++e) {
-        int u = g_.adj[e];
-        if (mark_[u] == tok && dist[u] < 0) {
-          dist[u] = dist[v] + 1;
-          queue.push_back(u);
-        }
+    const int* xadj = sg.xadj.get();
+    const int* adj = sg.adj.get();
+    while (head < tail) {
+      const int v = q[head++];
+      const int dv = dist[v] + 1;
+      for (int e = xadj[v]; e < xadj[v + 1]; ++e) {
+        const int u = adj[e];
+        const int du = dist[u];
+        const bool fresh = du < 0;
+        q[tail] = u;
+        tail += fresh;
+        dist[u] = fresh ? dv : du;
       }
     }
-    return queue.back();
+    queue.tail = tail;
+    return q[tail - 1];
   }
 
-  void bfs_multi(const std::vector<int>& sources, int tok, std::vector<int>& dist, std::vector<int>& queue) {
-    queue.clear();
+  static void bfs_multi(const SubGraph& sg, const std::vector<int>& sources, std::vector<int>& dist_v, Queue& queue) {
+    int* q = queue.q.data();
+    int* dist = dist_v.data();
+    size_t tail = 0;
     for (int v : sources) {
       dist[v] = 0;
-      queue.push_back(v);
+      q[tail++] = v;
     }
-    for (size_t head = 0; head < queue.size(); ++head) {
-      const int v = queue[head];
-      for (long long e = g_.xadj[v]; e < g_.xadj[v + 1]; ++e) {
-        const int u = g_.adj[e];
-        if (mark_[u] == tok && dist[u] < 0) {
-          dist[u] = dist[v] + 1;
-          queue.push_back(u);
-        }
+    const int* xadj = sg.xadj.get();
+    const int* adj = sg.adj.get();
+    for (size_t head = 0; head < tail; ++head) {
+      const int v = q[head];
+      const int dv = dist[v] + 1;
+      for (int e = xadj[v]; e < xadj[v + 1]; ++e) {
+        const int u = adj[e];
+        const int du = dist[u];
+        const bool fresh = du < 0;
+        q[tail] = u;
+        tail += fresh;
+        dist[u] = fresh ? dv : du;
       }
     }
+    queue.tail = tail;
   }
 
   static void emit_leaf(const std::vector<int>& verts, NDResult& out) {
@@ -144,22 +236,23 @@ class Dissector {
     out.sn_sizes.push_back((int)verts.size());
   }
 
-  // Hopcroft-Karp maximum matching + Koenig construction on the cut graph (SL x SR).
-  std::vector<int> min_vertex_cover(const std::vector<int>& SL, const std::vector<int>& SR, int tok) {
+  // Hopcroft-Karp maximum matching + Koenig construction on the cut graph (SL x SR); local numbers in and out.
+  static std::vector<int> min_vertex_cover(const SubGraph& sg, const std::vector<int>& SL, const std::vector<int>& SR,
+                                           const std::vector<unsigned char>& side, std::vector<int>& rid) {
     const int nl = (int)SL.size(), nr = (int)SR.size();
     if (nl == 0 || nr == 0) return {};
-    // local ids of the right side via db_ (scratch, reset afterwards)
-    for (int j = 0; j < nr; ++j) db_[SR[j]] = -2 - j;
+    // position of a right-side vertex in SR (scratch, reset afterwards)
+    for (int j = 0; j < nr; ++j) rid[SR[j]] = j;
     std::vector<int> xadj(nl + 1, 0), adj;
     for (int i = 0; i < nl; ++i) {
       const int v = SL[i];
-      for (long long e = g_.xadj[v]; e < g_.xadj[v + 1]; ++e) {
-        const int u = g_.adj[e];
-        if (mark_[u] == tok && side_[u] == 1 && db_[u] <= -2) adj.push_back(-2 - db_[u]);
+      for (int e = sg.xadj[v]; e < sg.xadj[v + 1]; ++e) {
+        const int u = sg.adj[e];
+        if (side[u] == 1 && rid[u] >= 0) adj.push_back(rid[u]);
       }
       xadj[i + 1] = (int)adj.size();
     }
-    for (int j = 0; j < nr; ++j) db_[SR[j]] = -1;
+    for (int j = 0; j < nr; ++j) rid[SR[j]] = -1;
     std::vector<int> matchL(nl, -1), matchR(nr, -1), dist(nl), queue, it(nl);
     const int INF = 0x3fffffff;
     auto bfs_layers = [&]() {
@@ -256,38 +349,74 @@ class Dissector {
     return cover;
   }
 
-  void rec(std::vector<int>& verts, int depth, NDResult& out) {
-    const int nv = (int)verts.size();
+  // compact copy of the subgraph induced by `keep` (local numbers of `sg`, in the order the child visits them)
+  static void induce(const SubGraph& sg, const std::vector<int>& keep, std::vector<int>& loc, SubGraph& out) {
+    const int nc = (int)keep.size();
+    out.gid.resize(nc);
+    out.xadj.reset(new int[(size_t)nc + 1]);
+    out.xadj[0] = 0;
+    for (int i = 0; i < nc; ++i) loc[keep[i]] = i;
+    const bool par = nc > 200000;
+    const int* pxadj = sg.xadj.get();
+    const int* padj = sg.adj.get();
+    std::vector<int> deg(nc);
+#pragma omp taskloop grainsize(8192) shared(deg, loc, keep, out, sg) if (par)
+    for (int i = 0; i < nc; ++i) {
+      const int v = keep[i];
+      out.gid[i] = sg.gid[v];
+      int c = 0;
+      for (int e = pxadj[v]; e < pxadj[v + 1]; ++e) c += loc[padj[e]] >= 0;
+      deg[i] = c;
+    }
+    for (int i = 0; i < nc; ++i) out.xadj[i + 1] = out.xadj[i] + deg[i];
+    out.adj.reset(new int[(size_t)out.xadj[nc]]);
+#pragma omp taskloop grainsize(8192) shared(loc, keep, out, sg) if (par)
+    for (int i = 0; i < nc; ++i) {
+      const int v = keep[i];
+      int o = out.xadj[i];
+      for (int e = pxadj[v]; e < pxadj[v + 1]; ++e) {
+        const int u = loc[padj[e]];
+        if (u >= 0) out.adj[o++] = u;
+      }
+    }
+    for (int i = 0; i < nc; ++i) loc[keep[i]] = -1;
+  }
+
+  void rec(SubGraph& sg, int depth, NDResult& out) {
+    const int nv = sg.nv();
     if (nv == 0) return;
     if (nv <= opt_.leaf_size) {
-      emit_leaf(verts, out);
+      emit_leaf(sg.gid, out);
       return;
     }
-    const int tok = token_.fetch_add(1);
-    for (int v : verts) {
-      mark_[v] = tok;
-      da_[v] = -1;
-      db_[v] = -1;
-    }
-    std::vector<int> queue;
-    queue.reserve(nv);
-    int far0 = bfs(verts[0], tok, da_, queue);
-    std::vector<int> L, R, S;
+    std::vector<int> da(nv, -1), db(nv, -1);
+    const bool tr = depth <= 1 && getenv("LSA_TRACE_ANALYZE") != nullptr;
+    double tt = tr ? now() : 0.0;
+    auto lap = [&](const char* what) {
+      if (!tr) return;
+      const double t = now();
+      fprintf(stderr, "[dissect depth %d, %d vertices] %-18s %7.3f s\n", depth, nv, what, t - tt);
+      tt = t;
+    };
+    Queue queue(nv);
+    int far0 = bfs(sg, 0, da, queue);
+    lap("first sweep");
+    std::vector<int> L, R, S;   // local numbers
     if ((int)queue.size() < nv) {
       // disconnected: distribute the components over two bins, no separator needed
       std::vector<std::pair<int, int>> comps;  // (start, end) in queue
       comps.emplace_back(0, (int)queue.size());
-      for (int v : verts)
-        if (da_[v] < 0) {
+      for (int v = 0; v < nv; ++v)
+        if (da[v] < 0) {
           int s = (int)queue.size();
-          bfs(v, tok, da_, queue);
+          bfs(sg, v, da, queue);
           comps.emplace_back(s, (int)queue.size());
         }
       std::sort(comps.begin(), comps.end(),
                 [](auto& a, auto& b) { return (a.second - a.first) > (b.second - b.first); });
       for (auto& c : comps) {
         auto& bin = (L.size() <= R.size()) ? L : R;
-        bin.insert(bin.end(), queue.begin() + c.first, queue.begin() + c.second);
+        bin.insert(bin.end(), queue.q.begin() + c.first, queue.q.begin() + c.second);
       }
     } else {
       std::vector<double> key(nv);
@@ -297,7 +426,7 @@ class Dissector {
         double ext = -1;
         for (int a = 0; a < opt_.dim; ++a) {
           double lo = 1e300, hi = -1e300;
-          for (int v : verts) {
+          for (int v : sg.gid) {
             double c = opt_.coords[(size_t)v * opt_.dim + a];
             lo = std::min(lo, c);
             hi = std::max(hi, c);
@@ -308,48 +437,62 @@ class Dissector {
           }
         }
         if (ext > 0) {
-          for (int i = 0; i < nv; ++i) key[i] = opt_.coords[(size_t)verts[i] * opt_.dim + best];
+          for (int i = 0; i < nv; ++i) key[i] = opt_.coords[(size_t)sg.gid[i] * opt_.dim + best];
           have_key = true;
         }
       }
       if (!have_key) {
         // two pseudo-peripheral vertices a, b; key = d(a, v) - d(b, v)
-        for (int v : verts) da_[v] = -1;
+        std::fill(da.begin(), da.end(), -1);
         queue.clear();
-        int b = bfs(far0, tok, da_, queue);
+        int b = bfs(sg, far0, da, queue);
+        lap("  sweep from far0");
         queue.clear();
-        int a2 = bfs(b, tok, db_, queue);
+        int a2 = bfs(sg, b, db, queue);
+        lap("  sweep from b");
         // one more sweep improves the pair on elongated domains
-        for (int v : verts) da_[v] = -1;
+        std::fill(da.begin(), da.end(), -1);
         queue.clear();
-        bfs(a2, tok, da_, queue);
-        // da_ = d(a, .), db_ = d(b, .).  The bisector of two POINTS is slanted on meshes whose hop metric
+        bfs(sg, a2, da, queue);
+        lap("  sweep from a2");
+        // da = d(a, .), db = d(b, .).  The bisector of two POINTS is slanted on meshes whose hop metric
         // is anisotropic (structured triangulations); the bisector of the two END CAPS
         //   A = {v : d(b, v) >= (1 - eps) D},  B = {v : d(a, v) >= (1 - eps) D}
         // is perpendicular to the long axis whatever the metric: multi-source BFS from the caps.
         if (opt_.cap_fraction > 0.0) {
           int D = 0;
-          for (int v : verts) D = std::max(D, da_[v]);
+          for (int v = 0; v < nv; ++v) D = std::max(D, da[v]);
           const int thr = (int)std::floor((1.0 - opt_.cap_fraction) * D);
           std::vector<int> capA, capB;
-          for (int v : verts) {
-            if (db_[v] >= thr) capA.push_back(v);
-            if (da_[v] >= thr) capB.push_back(v);
+          for (int v = 0; v < nv; ++v) {
+            if (db[v] >= thr) capA.push_back(v);
+            if (da[v] >= thr) capB.push_back(v);
           }
           if (!capA.empty() && !capB.empty()) {
-            for (int v : verts) {
-              da_[v] = -1;
-              db_[v] = -1;
+            std::fill(da.begin(), da.end(), -1);
+            std::fill(db.begin(), db.end(), -1);
+            // the two cap sweeps are independent: side by side when the node is large (near the root the other
+            // threads of the team have nothing else to do yet)
+            if (nv > 100000) {
+              Queue queue_b(nv);
+#pragma omp task shared(sg, capA, da, queue)
+              bfs_multi(sg, capA, da, queue);
+              bfs_multi(sg, capB, db, queue_b);
+#pragma omp taskwait
+            } else {
+              bfs_multi(sg, capA, da, queue);
+              bfs_multi(sg, capB, db, queue);
             }
-            bfs_multi(capA, tok, da_, queue);
-            bfs_multi(capB, tok, db_, queue);
+            lap("  sweeps from the caps");
           }
         }
-        for (int i = 0; i < nv; ++i) key[i] = (double)da_[verts[i]] - (double)db_[verts[i]];
+        for (int i = 0; i < nv; ++i) key[i] = (double)da[i] - (double)db[i];
       }
+      lap("bisection key");
       std::vector<double> tmp(key);
       std::nth_element(tmp.begin(), tmp.begin() + nv / 2, tmp.end());
       const double t = tmp[nv / 2];
+      std::vector<double>().swap(tmp);
       int n_lt = 0, n_le = 0;
       for (double k : key) {
         n_lt += k < t;
@@ -364,48 +507,65 @@ class Dissector {
         use_le = std::abs(n_le - nv / 2) < std::abs(n_lt - nv / 2);
       int nL = use_le ? n_le : n_lt;
       if (nL == 0 || nL == nv) {  // all keys equal: cannot bisect, keep as one dense front
-        emit_leaf(verts, out);
+        emit_leaf(sg.gid, out);
         return;
       }
-      for (int i = 0; i < nv; ++i) side_[verts[i]] = use_le ? (key[i] > t) : (key[i] >= t);
+      std::vector<unsigned char> side(nv);
+      for (int i = 0; i < nv; ++i) side[i] = use_le ? (key[i] > t) : (key[i] >= t);
+      std::vector<double>().swap(key);
       std::vector<int> SL, SR;
-      for (int v : verts) {
-        const unsigned char sv = side_[v];
+      for (int v = 0; v < nv; ++v) {
+        const unsigned char sv = side[v];
         bool cut = false;
-        for (long long e = g_.xadj[v]; e < g_.xadj[v + 1] && !cut; ++e) {
-          int u = g_.adj[e];
-          cut = (mark_[u] == tok) && (side_[u] != sv);
-        }
+        for (int e = sg.xadj[v]; e < sg.xadj[v + 1] && !cut; ++e) cut = side[sg.adj[e]] != sv;
         if (cut) (sv ? SR : SL).push_back(v);
       }
       // minimum vertex separator for this edge cut = minimum vertex cover of the bipartite graph of
       // cut edges between the two boundary layers (Koenig's theorem via Hopcroft-Karp matching).
       // On FE graphs (every element is a clique) this is about half of either boundary layer.
-      S = min_vertex_cover(SL, SR, tok);
+      lap("edge cut");
+      std::fill(db.begin(), db.end(), -1);
+      S = min_vertex_cover(sg, SL, SR, side, db);
+      lap("vertex cover");
       if ((double)S.size() > 0.45 * nv) {
-        emit_leaf(verts, out);
+        emit_leaf(sg.gid, out);
         return;
       }
-      for (int v : S) side_[v] = 2;
-      for (int v : verts) {
-        if (side_[v] == 0) L.push_back(v);
-        else if (side_[v] == 1) R.push_back(v);
+      for (int v : S) side[v] = 2;
+      for (int v = 0; v < nv; ++v) {
+        if (side[v] == 0) L.push_back(v);
+        else if (side[v] == 1) R.push_back(v);
       }
     }
-    std::vector<int>().swap(queue);
+    std::vector<int>().swap(queue.q);
+    std::vector<int>().swap(da);
+    // children's compact copies, then this node's adjacency is released before the recursion
+    SubGraph sgL, sgR;
+    std::fill(db.begin(), db.end(), -1);
+    induce(sg, L, db, sgL);
+    induce(sg, R, db, sgR);
+    lap("children's graphs");
+    std::vector<int> Sg(S.size());
+    for (size_t i = 0; i < S.size(); ++i) Sg[i] = sg.gid[S[i]];
+    sg.adj.reset();
+    sg.xadj.reset();
+    std::vector<int>().swap(sg.gid);
+    std::vector<int>().swap(db);
+    std::vector<int>().swap(L);
+    std::vector<int>().swap(R);
     NDResult outL, outR;
     const bool spawn = nv > 20000;
-#pragma omp task shared(L, outL) firstprivate(depth) if (spawn)
-    rec(L, depth + 1, outL);
-#pragma omp task shared(R, outR) firstprivate(depth) if (spawn)
-    rec(R, depth + 1, outR);
+#pragma omp task shared(sgL, outL) firstprivate(depth) if (spawn)
+    rec(sgL, depth + 1, outL);
+#pragma omp task shared(sgR, outR) firstprivate(depth) if (spawn)
+    rec(sgR, depth + 1, outR);
 #pragma omp taskwait
     out.order.reserve(out.order.size() + nv);
     out.order.insert(out.order.end(), outL.order.begin(), outL.order.end());
     out.order.insert(out.order.end(), outR.order.begin(), outR.order.end());
     out.sn_sizes.insert(out.sn_sizes.end(), outL.sn_sizes.begin(), outL.sn_sizes.end());
     out.sn_sizes.insert(out.sn_sizes.end(), outR.sn_sizes.begin(), outR.sn_sizes.end());
-    if (!S.empty()) emit_leaf(S, out);
+    if (!Sg.empty()) emit_leaf(Sg, out);
   }
 };
 
@@ -426,9 +586,13 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
   for (int v = 0; v < n; ++v) (g.xadj[v + 1] == g.xadj[v] ? iso : rest).push_back(v);
   sym.n_iso = (int)iso.size();
   NDResult nd;
+  if (g.xadj[n] > 0x7fffffffLL) throw std::runtime_error("graph too large for the dissection's 32-bit adjacency offsets");
+  const bool trace_an = getenv("LSA_TRACE_ANALYZE") != nullptr;
   {
+    const double ta = now();
     Dissector d(g, opt);
     d.run(rest, nd);
+    if (trace_an) fprintf(stderr, "[analyze] nested dissection            %8.3f s\n", now() - ta);
   }
   // ---- constrained placement of structurally-zero-diagonal unknowns (pressure): such an unknown
   // must not be eliminated before at least one of the regular unknowns it is coupled to, otherwise
@@ -501,6 +665,7 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
     for (int i = sym.sn_ptr[s]; i < sym.sn_ptr[s + 1]; ++i) sym.sn_of[i] = s;
   double t2 = now();
   sym.seconds[1] = t2 - t1;
+  if (trace_an) fprintf(stderr, "[analyze] graph %.3f s, ordering phase %.3f s\n", sym.seconds[0], sym.seconds[1]);
 
   // ---- supernodal symbolic factorisation on the permuted pattern of A + A^T
   const int ns = sym.ns;

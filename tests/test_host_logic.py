@@ -565,3 +565,50 @@ def test_host_equal_is_an_exact_comparison():
     assert _lib.host_equal(a, b)
     assert not _lib.host_equal(a, b[:-1]) and not _lib.host_equal(a, b.astype(np.int64))
     assert _lib.host_equal(a[::2], b[::2]) and _lib.host_equal(a[:0], b[:0])
+
+
+def test_symbolic_analysis_is_pinned_and_thread_count_independent():
+    """The host analysis (parallel graph build with atomically claimed slots, task-parallel nested dissection on
+    compact per-node subgraphs, first-touch arrays) returns the SAME ordering, fronts and scatter maps (a) as the
+    analysis all GPU records of the round were taken on (`tests/golden/symbolic_digests.json`, written before the
+    host-side rework), (b) whatever the number of host threads, including on a graph large enough to spawn the
+    dissection tasks and the task loops of the sub-graph copies."""
+    import json
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_symbolic_digests as G
+
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "symbolic_digests.json")))
+    assert G.compute() == gold
+
+    # 9-point grid graph, 640 x 420 = 268 800 vertices (> 200 000: task loops; > 20 000: dissection tasks),
+    # structurally unsymmetric input (strict upper triangle dropped on every third row), one isolated vertex
+    nx, ny = 640, 420
+    ex = sp.diags([1.0, 1.0, 1.0], [-1, 0, 1], shape=(nx, nx))
+    ey = sp.diags([1.0, 1.0, 1.0], [-1, 0, 1], shape=(ny, ny))
+    a = sp.kron(ex, ey, format="csr")
+    keep = np.ones(a.nnz, dtype=bool)
+    rows = np.repeat(np.arange(a.shape[0]), np.diff(a.indptr))
+    keep[(rows % 3 == 0) & (a.indices > rows)] = False
+    iso = 12345
+    keep[(rows == iso) | (a.indices == iso)] = False
+    keep[(rows == iso) & (a.indices == iso)] = True
+    a = sp.csr_matrix((a.data[keep], (rows[keep], a.indices[keep])), shape=a.shape)
+    a.sort_indices()
+    n = a.shape[0]
+    ref = None
+    try:
+        for nthreads in (1, 3, 8):
+            h = _lib.Handle(n, device=-1)
+            info = h.analyze(a.indptr, a.indices, leaf_size=48, nthreads=nthreads)
+            got = {nm: h.symbolic_array(nm) for nm in ("perm", "sn_ptr", "st_idx", "ea_map", "a_dst", "lvl_front")}
+            h.close()
+            assert info.n_decoupled == 1
+            if ref is None:
+                ref = got
+                assert sorted(got["perm"].tolist()) == list(range(n))
+            else:
+                for nm, v in got.items():
+                    assert np.array_equal(v, ref[nm]), (nm, nthreads)
+    finally:
+        _lib.Handle(3, device=-1).analyze(np.array([0, 1, 2, 3]), np.array([0, 1, 2]), nthreads=os.cpu_count() or 1)
