@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <numeric>
 #include <stdexcept>
@@ -382,12 +383,14 @@ class Dissector {
     for (int i = 0; i < nc; ++i) loc[keep[i]] = -1;
   }
 
-  void rec(SubGraph& sg, int depth, NDResult& out) {
+  // One dissection step.  false: the node stays one front (emitted to `out`; nothing for an empty node);
+  // true: it was split into the compact sub-graphs sgL, sgR and the separator Sg (global numbers), `sg` is released.
+  bool split(SubGraph& sg, int depth, NDResult& out, SubGraph& sgL, SubGraph& sgR, std::vector<int>& Sg) {
     const int nv = sg.nv();
-    if (nv == 0) return;
+    if (nv == 0) return false;
     if (nv <= opt_.leaf_size) {
       emit_leaf(sg.gid, out);
-      return;
+      return false;
     }
     std::vector<int> da(nv, -1), db(nv, -1);
     const bool tr = depth <= 1 && getenv("LSA_TRACE_ANALYZE") != nullptr;
@@ -508,7 +511,7 @@ class Dissector {
       int nL = use_le ? n_le : n_lt;
       if (nL == 0 || nL == nv) {  // all keys equal: cannot bisect, keep as one dense front
         emit_leaf(sg.gid, out);
-        return;
+        return false;
       }
       std::vector<unsigned char> side(nv);
       for (int i = 0; i < nv; ++i) side[i] = use_le ? (key[i] > t) : (key[i] >= t);
@@ -529,7 +532,7 @@ class Dissector {
       lap("vertex cover");
       if ((double)S.size() > 0.45 * nv) {
         emit_leaf(sg.gid, out);
-        return;
+        return false;
       }
       for (int v : S) side[v] = 2;
       for (int v = 0; v < nv; ++v) {
@@ -539,33 +542,64 @@ class Dissector {
     }
     std::vector<int>().swap(queue.q);
     std::vector<int>().swap(da);
-    // children's compact copies, then this node's adjacency is released before the recursion
-    SubGraph sgL, sgR;
+    // children's compact copies, then this node's adjacency is released
     std::fill(db.begin(), db.end(), -1);
     induce(sg, L, db, sgL);
     induce(sg, R, db, sgR);
     lap("children's graphs");
-    std::vector<int> Sg(S.size());
+    Sg.resize(S.size());
     for (size_t i = 0; i < S.size(); ++i) Sg[i] = sg.gid[S[i]];
     sg.adj.reset();
     sg.xadj.reset();
     std::vector<int>().swap(sg.gid);
-    std::vector<int>().swap(db);
-    std::vector<int>().swap(L);
-    std::vector<int>().swap(R);
-    NDResult outL, outR;
-    const bool spawn = nv > 20000;
-#pragma omp task shared(sgL, outL) firstprivate(depth) if (spawn)
-    rec(sgL, depth + 1, outL);
-#pragma omp task shared(sgR, outR) firstprivate(depth) if (spawn)
-    rec(sgR, depth + 1, outR);
+    return true;
+  }
+
+  // Dissection of a sub-graph: order = [order of L][order of R][separator].  The LARGER child is continued in a
+  // loop, the smaller one is recursed into (as a task near the root), so the call depth is bounded by log2(n)
+  // whatever the splits look like: graphs with hub vertices peel one vertex per step (n steps deep), which must
+  // not be n stack frames.  Pieces are concatenated at the end in the order of the plain recursion.
+  struct Pending {
+    SubGraph sg;            // the smaller child
+    NDResult res;           // its ordering
+    std::vector<int> sep;   // separator of the step
+    bool small_first;       // the smaller child is L: its ordering precedes the continued child's
+  };
+
+  void rec(SubGraph& sg0, int depth, NDResult& out) {
+    std::deque<Pending> pend;   // stable addresses: tasks hold references into it
+    SubGraph cur = std::move(sg0);
+    NDResult core;
+    for (;; ++depth) {
+      const int nv = cur.nv();
+      SubGraph sgL, sgR;
+      std::vector<int> Sg;
+      if (!split(cur, depth, core, sgL, sgR, Sg)) break;
+      pend.emplace_back();
+      Pending& p = pend.back();
+      p.sep.swap(Sg);
+      p.small_first = sgL.nv() < sgR.nv();
+      p.sg = std::move(p.small_first ? sgL : sgR);
+      cur = std::move(p.small_first ? sgR : sgL);
+      const bool spawn = nv > 20000;
+#pragma omp task shared(p) firstprivate(depth) if (spawn)
+      rec(p.sg, depth + 1, p.res);
+    }
 #pragma omp taskwait
-    out.order.reserve(out.order.size() + nv);
-    out.order.insert(out.order.end(), outL.order.begin(), outL.order.end());
-    out.order.insert(out.order.end(), outR.order.begin(), outR.order.end());
-    out.sn_sizes.insert(out.sn_sizes.end(), outL.sn_sizes.begin(), outL.sn_sizes.end());
-    out.sn_sizes.insert(out.sn_sizes.end(), outR.sn_sizes.begin(), outR.sn_sizes.end());
-    if (!Sg.empty()) emit_leaf(Sg, out);
+    size_t total = core.order.size();
+    for (const Pending& p : pend) total += p.res.order.size() + p.sep.size();
+    out.order.reserve(out.order.size() + total);
+    auto append = [&](const NDResult& r) {
+      out.order.insert(out.order.end(), r.order.begin(), r.order.end());
+      out.sn_sizes.insert(out.sn_sizes.end(), r.sn_sizes.begin(), r.sn_sizes.end());
+    };
+    for (const Pending& p : pend)
+      if (p.small_first) append(p.res);
+    append(core);
+    for (auto it = pend.rbegin(); it != pend.rend(); ++it) {
+      if (!it->small_first) append(it->res);
+      if (!it->sep.empty()) emit_leaf(it->sep, out);
+    }
   }
 };
 

@@ -39,6 +39,20 @@ def cases():
         yield f"cav8_w2r{r}", pc, dict(leaf_size=64, order_last=ol), True, (r, 2)
 
 
+def hub_pattern():
+    """4000 unknowns, random sparse pattern with one dense row and one dense column (hub vertices)."""
+    import scipy.sparse as sp
+
+    n = 4000
+    a = sp.random(n, n, density=6e-3, random_state=3, format="lil", dtype=np.float64)
+    a.setdiag(4.0)
+    a[17, ::2] = 1.0
+    a[:, 2001] = 1.0
+    a = a.tocsr()
+    a.sort_indices()
+    return a
+
+
 def compute() -> dict:
     from lsa_fw_b200 import _lib
 
@@ -55,4 +69,11 @@ def compute() -> dict:
 
 
 if __name__ == "__main__":
-    json.dump(compute(), open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "symbolic_digests.json"), "w"), indent=1)
+    from lsa_fw_b200 import _lib
+
+    out = compute()
+    hub = hub_pattern()
+    h = _lib.Handle(hub.shape[0], device=-1)
+    h.analyze(hub.indptr, hub.indices, leaf_size=32)
+    out["hub"] = digest(h)
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "symbolic_digests.json"), "w"), indent=1)

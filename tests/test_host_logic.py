@@ -579,6 +579,7 @@ def test_symbolic_analysis_is_pinned_and_thread_count_independent():
     import make_symbolic_digests as G
 
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "symbolic_digests.json")))
+    gold_hub = gold.pop("hub")
     assert G.compute() == gold
 
     # 9-point grid graph, 640 x 420 = 268 800 vertices (> 200 000: task loops; > 20 000: dissection tasks),
@@ -612,3 +613,13 @@ def test_symbolic_analysis_is_pinned_and_thread_count_independent():
                     assert np.array_equal(v, ref[nm]), (nm, nthreads)
     finally:
         _lib.Handle(3, device=-1).analyze(np.array([0, 1, 2, 3]), np.array([0, 1, 2]), nthreads=os.cpu_count() or 1)
+
+    # a graph with hub vertices (one dense row, one dense column) peels one vertex per dissection step: ~n steps deep.
+    # The dissection loops on the larger child, so this must neither overflow the stack nor change the ordering
+    # (digest of the plain recursion, written by tests/golden/make_symbolic_digests.py before the rework).
+    hub = G.hub_pattern()
+    h = _lib.Handle(hub.shape[0], device=-1)
+    info = h.analyze(hub.indptr, hub.indices, leaf_size=32)
+    assert info.n_fronts > 3000
+    assert G.digest(h) == gold_hub
+    h.close()
