@@ -623,3 +623,69 @@ def test_symbolic_analysis_is_pinned_and_thread_count_independent():
     assert info.n_fronts > 3000
     assert G.digest(h) == gold_hub
     h.close()
+
+
+def _random_pattern(seed: int, n: int, density: float, n_hubs: int, n_decoupled: int, n_blocks: int):
+    """Random sparse test matrix: `n_blocks` diagonal blocks without coupling between them, hub rows / columns, rows that
+    hold only their diagonal entry (decoupled 1x1 pivots), structurally unsymmetric, diagonally dominant values."""
+    rng = np.random.default_rng(seed)
+    a = sp.lil_matrix((n, n))
+    cuts = np.sort(rng.choice(np.arange(1, n), size=min(n_blocks - 1, n - 1), replace=False)) if n_blocks > 1 else []
+    lo = 0
+    for hi in list(cuts) + [n]:
+        m = hi - lo
+        blk = sp.random(m, m, density=min(1.0, density), random_state=int(rng.integers(1 << 30)), format="lil")
+        a[lo:hi, lo:hi] = blk
+        lo = hi
+    for _ in range(n_hubs):
+        v = int(rng.integers(n))
+        a[v, rng.random(n) < 0.5] = 1.0
+        if rng.random() < 0.5:
+            a[rng.random(n) < 0.5, v] = 1.0
+    dec = rng.choice(n, size=min(n_decoupled, n), replace=False)
+    for v in dec:
+        a[v, :] = 0.0
+        a[:, v] = 0.0
+    a = a.tocsr()
+    a.data[:] = rng.standard_normal(a.nnz)
+    a = (a + sp.diags(np.asarray(abs(a).sum(axis=1)).ravel() + np.asarray(abs(a).sum(axis=0)).ravel() + 1.0)).tocsr()
+    a.sort_indices()
+    return a
+
+
+def test_symbolic_analysis_on_random_patterns_property():
+    """Property test of the host analysis on patterns no FE mesh produces (disconnected blocks, hub rows and columns,
+    decoupled rows, tiny orders): the permutation is a permutation, the assembly tree is a postordered forest whose fronts
+    cover the pattern (the scatter maps are complete), and the structures drive an LU whose N and H solves are exact."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(seed=st.integers(0, 2**20), n=st.integers(1, 160), density=st.sampled_from([0.0, 0.01, 0.05, 0.3]),
+           n_hubs=st.integers(0, 2), n_decoupled=st.integers(0, 5), n_blocks=st.integers(1, 4),
+           leaf=st.sampled_from([1, 2, 8, 32]))
+    def check(seed, n, density, n_hubs, n_decoupled, n_blocks, leaf):
+        a = _random_pattern(seed, n, density, n_hubs, n_decoupled, n_blocks)
+        h = _lib.Handle(n, device=-1)
+        try:
+            info = h.analyze(a.indptr, a.indices, leaf_size=leaf)
+            perm = h.symbolic_array("perm")
+            assert sorted(perm.tolist()) == list(range(n))
+            parent = h.symbolic_array("parent")
+            has_parent = parent >= 0
+            assert np.all(parent[has_parent] > np.nonzero(has_parent)[0])
+            assert np.all(h.symbolic_array("a_dst") >= 0)
+            offdiag = a - sp.diags(a.diagonal())
+            offdiag.eliminate_zeros()
+            lonely = (np.diff(offdiag.tocsr().indptr) == 0) & (np.diff(offdiag.tocsc().indptr) == 0)
+            assert info.n_decoupled == int(lonely.sum())
+            em = Emulator(h, n)
+            em.factor(a.data.astype(np.complex128), None, 1.0, 0.0)
+            rng = np.random.default_rng(seed)
+            b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+            assert np.linalg.norm(a @ em.solve(b) - b) <= 1e-11 * np.linalg.norm(b)
+            assert np.linalg.norm(a.conj().T @ em.solve(b, "H") - b) <= 1e-11 * np.linalg.norm(b)
+        finally:
+            h.close()
+
+    check()
