@@ -22,7 +22,7 @@ import scipy.sparse as sp
 
 from . import _lib
 from ._lib import LsaError
-from .carriers import iComplexPETScVector, iPETScMatrix, iPETScVector
+from .carriers import iComplexPETScVector, iPETScMatrix, iPETScNullSpace, iPETScVector
 
 logger = logging.getLogger(__name__)
 
@@ -669,7 +669,10 @@ class iEpsSolver:  # noqa: N801
             # attached nullspace (constant pressure of an enclosed flow, FEM/operators.py:534-545): projected out of
             # every operator application; the vanishing pivot of the singular shifted operator is replaced
             ns = getattr(self._A, "get_nullspace", lambda: None)()
-            ns_arr = None if ns is None else np.asarray(ns.as_array() if hasattr(ns, "as_array") else ns)
+            if isinstance(ns, iPETScNullSpace):
+                ns_arr = np.asarray(ns.as_array(n))     # a constant-only nullspace takes its size from the operator
+            else:
+                ns_arr = None if ns is None else np.asarray(ns.as_array() if hasattr(ns, "as_array") else ns)
             if ns_arr is not None or h.ns_count:
                 h.set_nullspace(ns_arr)
             stats["nullspace_dimension"] = 0 if ns_arr is None else int(ns_arr.reshape(n, -1).shape[1])
