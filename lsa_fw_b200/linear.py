@@ -44,6 +44,10 @@ class KSPType(StrEnum):
     PREONLY = auto()
     QCG = auto()
     CGS = auto()
+    GCR = auto()
+    LSQR = auto()
+    LGMRES = auto()
+    FGMRES = auto()
 
     def to_petsc(self) -> str:
         return self.value
@@ -129,7 +133,7 @@ class iKSP:  # noqa: N801
             raise ValueError("Operators must be set before solve().")
         if self._pc not in (PreconditionerType.LU, PreconditionerType.CHOLESKY):
             raise NotImplementedError(f"preconditioner '{self._pc}' is not built on the B200 backend (direct LU only)")
-        if self._type in (KSPType.CHEBYSHEV, KSPType.QCG):
+        if self._type in (KSPType.CHEBYSHEV, KSPType.QCG, KSPType.LSQR):
             raise NotImplementedError(f"KSP type '{self._type}' is not built on the B200 backend")
         t0 = time.perf_counter()
         coords = self._opts["coords"]
@@ -213,6 +217,14 @@ class iKSP:  # noqa: N801
 
     def get_iteration_number(self) -> int:
         return int(self._its)
+
+    def reset(self) -> None:
+        """Forget the solver state for fresh reuse (`Solver/utils.py:417-419`, `KSPReset`): the next solve factors
+        again; the symbolic analysis of the pattern stays in the cache."""
+        self._factor_gen = -1
+        self._values_ref = None
+        self._sym_failed = False
+        self._its, self._rnorm, self._sol = 0, float("nan"), None
 
     def get_residual_norm(self) -> float:
         return float(self._rnorm)

@@ -245,6 +245,14 @@ def test_enums_keep_reference_names_and_alias():
     with pytest.raises(ValueError):
         L.iEpsWhich.TARGET_REAL.to_arpack()
     assert {t.name for t in L.iSTType} == {"SHELL", "SHIFT", "SINVERT", "CAYLEY", "PRECOND", "FILTER"}
+    assert [t.name for t in L.KSPType] == ["CG", "GMRES", "BICG", "BICGSTAB", "RICHARDSON", "CHEBYSHEV", "PREONLY", "QCG",
+                                           "CGS", "GCR", "LSQR", "LGMRES", "FGMRES"]          # Solver/utils.py:96-124
+    assert L.KSPType.FGMRES.to_petsc() == "fgmres"
+    ksp = L.iKSP()
+    ksp.set_type(L.KSPType.LGMRES)
+    assert ksp.get_type() == "lgmres" and ksp.raw.getType() == "lgmres"
+    ksp.reset()                                                           # Solver/utils.py:417-419
+    assert ksp.get_iteration_number() == 0
 
 
 def test_config_defaults_and_solver_properties():
