@@ -582,8 +582,9 @@ class Dissector {
       p.sg = std::move(p.small_first ? sgL : sgR);
       cur = std::move(p.small_first ? sgR : sgL);
       const bool spawn = nv > 20000;
-#pragma omp task shared(p) firstprivate(depth) if (spawn)
-      rec(p.sg, depth + 1, p.res);
+      Pending* pp = &p;   // the task outlives this iteration: it takes the element's address by value
+#pragma omp task firstprivate(pp, depth) if (spawn)
+      rec(pp->sg, depth + 1, pp->res);
     }
 #pragma omp taskwait
     size_t total = core.order.size();
