@@ -415,7 +415,7 @@ def test_run_sharded_gloo_world_size_2(tmp_path):
     assert out.stdout.count("ok") == 2
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_partitioned_solve_gloo(world):
     """Row e (multi-GPU) host logic on CPU: sub-tree -> rank mapping, rank-local structures (ghost roots, cut pool,
     local levels), broadcast of the sub-tree roots' contribution blocks, ONE all-reduce over the replicated rows
