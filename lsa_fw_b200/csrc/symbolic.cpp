@@ -730,8 +730,11 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
   const int ns = sym.ns;
   std::vector<int> parent(ns, -1), first_child(ns, -1), next_sib(ns, -1), last_child(ns, -1);
   std::vector<std::vector<int>> st(ns);
+  // (a) rows a front gets from the matrix itself: every front on its own, in parallel (one mark array per thread)
+#pragma omp parallel
   {
     std::vector<int> mark(n, -1);
+#pragma omp for schedule(dynamic, 64)
     for (int s = 0; s < ns; ++s) {
       const int last = sym.sn_ptr[s + 1] - 1;
       std::vector<int>& rows = st[s];
@@ -745,12 +748,23 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
           }
         }
       }
-      for (int c = first_child[s]; c >= 0; c = next_sib[c])
-        for (int j : st[c])
-          if (j > last && mark[j] != s) {
-            mark[j] = s;
-            rows.push_back(j);
-          }
+    }
+  }
+  // (b) rows inherited from the children, in elimination order (a front's parent is known once its rows are)
+  {
+    std::vector<int> mark(n, -1);
+    for (int s = 0; s < ns; ++s) {
+      const int last = sym.sn_ptr[s + 1] - 1;
+      std::vector<int>& rows = st[s];
+      if (first_child[s] >= 0) {
+        for (int j : rows) mark[j] = s;
+        for (int c = first_child[s]; c >= 0; c = next_sib[c])
+          for (int j : st[c])
+            if (j > last && mark[j] != s) {
+              mark[j] = s;
+              rows.push_back(j);
+            }
+      }
       std::sort(rows.begin(), rows.end());
       if (!rows.empty()) {
         const int p = sym.sn_of[rows[0]];
