@@ -667,12 +667,15 @@ void analyze(int n, const long long* rowptr, const int* colidx, const AnalyzeOpt
     }
     const int ns0 = (int)nd.sn_sizes.size();
     std::vector<int> target(n, -1);
-    std::vector<int> nb;
     int moved = 0;
     if (opt.order_last) {
-      for (int v : nd.order) {
+      const int n_ord = (int)nd.order.size();
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : moved)
+      for (int q_ord = 0; q_ord < n_ord; ++q_ord) {
+        const int v = nd.order[q_ord];
         target[v] = sn_tmp[v];
         if (!opt.order_last[v]) continue;
+        std::vector<int> nb;
         // front index such that at least `frac` of the regular neighbours are eliminated no later
         nb.clear();
         for (long long e = g.xadj[v]; e < g.xadj[v + 1]; ++e) {
