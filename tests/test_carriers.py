@@ -321,3 +321,18 @@ def test_complex_vector_matrix_products_norm_dot_equality():
     assert b == a
     a[0] = 9.0
     assert b != a and not (a == "something else")
+
+
+def test_example_sweep_script_loads_its_cases(tmp_path):
+    """`examples/eigenvalues_sweep.py --synthetic --dry-run`: writes MatrixMarket cases in the reference's directory
+    layout and reads them back through `iPETScMatrix.from_path` (no GPU needed up to the solve)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "eigenvalues_sweep.py"), str(tmp_path / "cases"),
+                          "--synthetic", "--dry-run"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stderr.count("A: shape=") == 11 and "All cases processed." in out.stderr
+    assert (tmp_path / "cases" / "reynolds_40.0" / "matrices" / "M.mtx").exists()
