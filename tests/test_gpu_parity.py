@@ -179,6 +179,18 @@ def test_eigenpairs_match_oracle(kind, use_coords):
         print(f"{kind}: lambda = {l:.12g}  kappa = {kappa:.3e}  |d lambda|/|lambda| = {abs(l - orc.eigenvalues[j]) / abs(l):.2e}")
         assert 1e-14 * kappa <= 1e-6, ("eigenvalue too ill-conditioned for a parity statement", l, kappa)
         assert abs(l - orc.eigenvalues[j]) / abs(l) < max(EIG_RTOL, 1e-14 * kappa), (l, orc.eigenvalues[j], kappa)
+    # ... and against the COMMITTED oracle values of the same pencil (tests/golden/lns_eigs.json; the CPU suite checks
+    # that the live oracle still reproduces them)
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lns_eigs.json")))[kind]
+    gl = np.array([complex(*z) for z in g["eigenvalues"]])
+    assert g["n"] == pc.n and complex(*g["sigma"]) == complex(sigma)
+    for l in lam:
+        j = int(np.argmin(abs(gl - l)))
+        kg = g["kappa"][j] or 0.0
+        assert abs(l - gl[j]) / abs(l) < max(EIG_RTOL, 1e-14 * kg), (l, gl[j], kg)
     # `which` order: increasing |lambda - sigma| (TARGET_MAGNITUDE default under sinvert)
     assert np.all(np.diff(np.abs(lam - sigma)) >= -1e-9 * np.abs(lam[:-1] - sigma))
     X = np.stack([_vec(v) for _, v in pairs], axis=1)

@@ -121,3 +121,30 @@ def test_pencil_structure_matches_reference_assembly():
     Muu = M[np.ix_(pc.dofs_u, pc.dofs_u)]
     assert np.allclose(Muu, Muu.T) and np.linalg.eigvalsh(Muu).min() > 0
     assert pencils.th_dofs((110, 50)) == 50303 and pencils.th_dofs((54, 54, 54)) == 4051462
+
+
+def test_oracle_reproduces_committed_lns_eigenvalues():
+    """The oracle against the committed eigenvalues of the small linearised Navier-Stokes test pencils
+    (`tests/golden/lns_eigs.json`, written by `tests/golden/make_lns_golden.py`): a SciPy / LAPACK change that moves the
+    checker shows up here, on CPU, before it can blur a GPU parity statement.  Tolerance: 1e-9 relative, or what double
+    precision leaves of an eigenvalue with condition number kappa (1e-13 kappa)."""
+    import importlib.util
+    import json
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_lns_golden", os.path.join(here, "make_lns_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    gold = json.load(open(os.path.join(here, "lns_eigs.json")))
+    assert set(gold) == set(G.KINDS)
+    for kind in G.KINDS:
+        pc, sigma = G.pencil(kind)
+        g = gold[kind]
+        assert pc.n == g["n"] and complex(*g["sigma"]) == complex(sigma)
+        orc = O.shift_invert_krylov_schur(pc.A, pc.M, sigma, g["nev"], ncv=g["ncv"], tol=g["tol"])
+        lam = orc.eigenvalues[: g["nev"]]
+        for z, kappa in zip(g["eigenvalues"], g["kappa"]):
+            z = complex(*z)
+            tol = max(1e-9, 1e-13 * kappa) if kappa is not None else 1e-9
+            assert min(abs(lam - z)) <= tol * abs(z), (kind, z, kappa)
